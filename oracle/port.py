@@ -1,0 +1,158 @@
+"""ctypes wrapper of the CPU restatement (oracle/rfslam_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline
+leg -- never by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Dict, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(_HERE, "librfslam_oracle.so")
+_lib = None
+
+_pd = C.POINTER(C.c_double)
+_pi = C.POINTER(C.c_int)
+
+
+class OrcArgs(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("n", "p", "ntree", "mtry", "nodesize", "nodedepth", "rule", "seed", "max_boot")] + [
+        ("k_for_alpha", C.c_double),
+        ("x", _pd), ("y", _pd), ("rt", _pd), ("strat", _pi), ("samp", _pi), ("boot_size", _pi),
+        ("split_weight", _pd), ("tree_seeds", _pi)]
+
+
+class OrcOut(C.Structure):
+    _fields_ = [("ntree", C.c_int), ("n", C.c_int),
+                ("total_nodes", C.c_long), ("total_leaves", C.c_long), ("candidates", C.c_long), ("rmbr_stride", C.c_long),
+                ("treeID", _pi), ("nodeID", _pi), ("parmID", _pi), ("contPT", _pd), ("splitStat", _pd),
+                ("leafCount", _pi), ("seed", _pi), ("bootMembership", _pi), ("nodeMembership", _pi),
+                ("tnRCNT", _pi), ("tnACNT", _pi), ("tnCLAS", _pi), ("rmbr", _pi), ("ambr", _pi),
+                ("oobNum", _pd), ("allNum", _pd), ("oobDen", _pi), ("allDen", _pi), ("oobEns", _pd), ("allEns", _pd)]
+
+
+def build(force: bool = False) -> None:
+    src = os.path.join(_HERE, "rfslam_oracle.c")
+    if force or not os.path.exists(PORT_SO) or os.path.getmtime(PORT_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "port"], stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(PORT_SO)
+        L.orc_grow.restype = C.POINTER(OrcOut); L.orc_grow.argtypes = [C.POINTER(OrcArgs)]
+        L.orc_free.restype = None; L.orc_free.argtypes = [C.POINTER(OrcOut)]
+        L.orc_poisson_stat.restype = C.c_double
+        L.orc_poisson_stat.argtypes = [C.c_int, C.c_int, C.c_double, C.c_char_p, _pd, _pd, _pd]
+        L.orc_chain_seeds.restype = None; L.orc_chain_seeds.argtypes = [C.c_int, C.c_int, _pi, _pi]
+        L.orc_chain_seeds_restore.restype = None; L.orc_chain_seeds_restore.argtypes = [C.c_int, _pi]
+        L.orc_bootstrap.restype = None; L.orc_bootstrap.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _pi]
+        L.orc_ran1_stream.restype = None; L.orc_ran1_stream.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float)]
+        L.orc_predict.restype = None
+        L.orc_predict.argtypes = [C.c_int, C.c_int, C.c_long, _pi, _pi, _pi, _pd, _pi, _pi, _pi, _pd, C.c_int, _pd, _pi]
+        _lib = L
+    return _lib
+
+
+def _dp(a): return a.ctypes.data_as(_pd)
+def _ip(a): return a.ctypes.data_as(_pi)
+
+
+def _arr(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
+def grow(x, y, rt, strat, *, rule=4, ntree=4, mtry=None, nodesize=5, nodedepth=-1, seed=-12345,
+         k_for_alpha=2.0, samp=None, split_weight=None, tree_seeds=None) -> Dict[str, np.ndarray]:
+    L = lib()
+    p, n = x.shape
+    x = np.ascontiguousarray(x, np.float64); y = np.ascontiguousarray(y, np.float64)
+    rt = np.ascontiguousarray(rt, np.float64); strat = np.ascontiguousarray(strat, np.int32)
+    if mtry is None:
+        mtry = int(np.ceil(np.sqrt(p)))
+    a = OrcArgs()
+    a.n, a.p, a.ntree, a.mtry, a.nodesize, a.nodedepth, a.rule, a.seed = n, p, ntree, mtry, nodesize, nodedepth, rule, seed
+    a.k_for_alpha = k_for_alpha
+    a.x, a.y, a.rt, a.strat = _dp(x), _dp(y), _dp(rt), _ip(strat)
+    keep = [x, y, rt, strat]
+    a.max_boot = n
+    if samp is not None:
+        samp = np.ascontiguousarray(samp, np.int32); keep.append(samp)
+        a.samp = _ip(samp); a.max_boot = int(samp.sum(axis=1).max())
+    if split_weight is not None:
+        sw = np.ascontiguousarray(split_weight, np.float64); keep.append(sw); a.split_weight = _dp(sw)
+    if tree_seeds is not None:
+        ts = np.ascontiguousarray(tree_seeds, np.int32); keep.append(ts); a.tree_seeds = _ip(ts)
+    op = L.orc_grow(C.byref(a))
+    o = op.contents
+    tn, tl = o.total_nodes, o.total_leaves
+    res = {
+        "treeID": _arr(o.treeID, tn, np.int32), "nodeID": _arr(o.nodeID, tn, np.int32),
+        "parmID": _arr(o.parmID, tn, np.int32), "contPT": _arr(o.contPT, tn, np.float64),
+        "splitStat": _arr(o.splitStat, tn, np.float64), "mwcpSZ": np.zeros(tn, np.int32),
+        "leafCount": _arr(o.leafCount, ntree, np.int32), "seed": _arr(o.seed, ntree, np.int32),
+        "bootMembership": _arr(o.bootMembership, ntree * n, np.int32),
+        "nodeMembership": _arr(o.nodeMembership, ntree * n, np.int32),
+        "tnRCNT": _arr(o.tnRCNT, tl, np.int32), "tnACNT": _arr(o.tnACNT, tl, np.int32),
+        "tnCLAS": _arr(o.tnCLAS, 2 * tl, np.int32),
+        "rmbrMembership": _arr(o.rmbr, ntree * o.rmbr_stride, np.int32),
+        "ambrMembership": _arr(o.ambr, ntree * n, np.int32),
+        "oobEnsbCLS": _arr(o.oobEns, 2 * n, np.float64), "allEnsbCLS": _arr(o.allEns, 2 * n, np.float64),
+        "candidates": np.array([o.candidates], np.int64),
+    }
+    L.orc_free(op)
+    return res
+
+
+def poisson_stat(rule, k_for_alpha, membership, response, strat, rt) -> float:
+    """One plugin call, 0-based arrays; membership 1 = LEFT (splitCustom.h:5-6)."""
+    L = lib()
+    mem = np.ascontiguousarray(membership, np.int8)
+    r = np.ascontiguousarray(response, np.float64); s = np.ascontiguousarray(strat, np.float64)
+    t = np.ascontiguousarray(rt, np.float64)
+    return L.orc_poisson_stat(rule, r.size, k_for_alpha, mem.ctypes.data_as(C.c_char_p), _dp(r), _dp(s), _dp(t))
+
+
+def chain_seeds(seed: int, ntree: int):
+    L = lib()
+    a = np.zeros(ntree, np.int32); b = np.zeros(ntree, np.int32)
+    L.orc_chain_seeds(seed, ntree, _ip(a), _ip(b))
+    return a, b
+
+
+def bootstrap(seed: int, ntree: int, n: int, tree: int) -> np.ndarray:
+    L = lib()
+    d = np.zeros(n, np.int32)
+    L.orc_bootstrap(seed, ntree, n, tree, _ip(d))
+    return d
+
+
+def ran1_stream(seed: int, count: int) -> np.ndarray:
+    L = lib()
+    out = np.zeros(count, np.float32)
+    L.orc_ran1_stream(seed, count, out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
+def predict(forest: Dict[str, np.ndarray], fx: np.ndarray):
+    """forest: trimmed arrays in tree order (treeID ascending) + leafCount/tnRCNT/tnCLAS."""
+    L = lib()
+    fx = np.ascontiguousarray(fx, np.float64)
+    p, m = fx.shape
+    ntree = forest["leafCount"].size
+    tid = np.ascontiguousarray(forest["treeID"], np.int32); nid = np.ascontiguousarray(forest["nodeID"], np.int32)
+    pid = np.ascontiguousarray(forest["parmID"], np.int32); cpt = np.ascontiguousarray(forest["contPT"], np.float64)
+    lc = np.ascontiguousarray(forest["leafCount"], np.int32); rc = np.ascontiguousarray(forest["tnRCNT"], np.int32)
+    te = np.ascontiguousarray(forest["tnCLAS"].reshape(-1, 2)[:, 1], np.int32)
+    ens = np.zeros(2 * m, np.float64); mem = np.zeros(ntree * m, np.int32)
+    L.orc_predict(ntree, p, tid.size, _ip(tid), _ip(nid), _ip(pid), _dp(cpt), _ip(lc), _ip(rc), _ip(te), _dp(fx), m, _dp(ens), _ip(mem))
+    return ens, mem

@@ -1,0 +1,475 @@
+/*
+ * rfslam_oracle.c -- CPU restatement of the rfSLAM Poisson-split tree-growing path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
+ * leg may build, load or call this file; the product path (rfslam_b200/) never does.
+ *
+ * This is a from-scratch restatement (plain C99, scalar, one thread) of what the reference
+ * computes on the hot path, written against the behaviour of the files below (paths relative to
+ * /root/reference/src; rf.c = randomForestSRC.c, sc.c = splitCustom.c).  It is pinned against
+ * the reference itself: tests/test_oracle_vs_ref.py runs the UNMODIFIED reference
+ * (oracle/_ref/librfslam_ref.so, built by oracle/Makefile) and this file on the same seeded
+ * inputs and requires identical forests; tests/golden/ holds outputs of the reference for the
+ * GPU box, where /root/reference does not exist.
+ *
+ *   RNG + seeding .......... rf.c:5976-6117 (ran1_generic, lcgenerator), rf.c:6664-6692
+ *   bootstrap .............. rf.c:492-627 (by.root SWR rf.c:529-533, by.user rf.c:520-526)
+ *   node gate / purity ..... rf.c:15342-15457, rf.c:6370-6426, rf.c:13235-13270
+ *   covariate draws ........ rf.c:14793-15150, rf.c:8362-8386, rf.c:8305-8308, rf.c:8206-8214
+ *   cut enumeration ........ rf.c:14433-14568 (nsplit = 0), rf.c:15165-15216 (LEFT iff cut - x >= 0)
+ *   split statistics ....... sc.c:639-1687 (poissonSplit1..6), called from rf.c:13404-13529
+ *   best-split tracker ..... rf.c:15471-15551 (EPSILON = 1e-9 absolute, rf.h:169)
+ *   fork / node ids ........ rf.c:10568-10734, rf.c:21620-21691
+ *   leaf statistics ........ rf.c:755-858, rf.c:7585-7657
+ *   ensembles .............. rf.c:859-973, rf.c:8113-8125
+ *   forest record order .... rf.c:10735-10806 (pre-order)
+ *
+ * Deliberate differences from the reference (none changes a result beyond floating-point
+ * summation order, which the reference itself does not fix: its quicksort is unstable,
+ * rf.c:5575-5640):
+ *   - per-cut per-side sufficient statistics (E, N, T, W per stratum) come from one forward and
+ *     one backward pass over the covariate-sorted rows instead of a fresh O(m) pass per cut;
+ *   - trees are stored in tree order 1..ntree (the reference appends in thread-completion order);
+ *   - outputs are sized by the actual node counts.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "rfslam_oracle.h"
+
+/* ------------------------------------------------------------------ RNG (rf.c:5976-6117) */
+
+#define RAN_IA 16807
+#define RAN_IM 2147483647
+#define RAN_IQ 127773
+#define RAN_IR 2836
+#define RAN_NTAB 32
+#define RAN_NDIV (1 + (RAN_IM - 1) / RAN_NTAB)
+
+typedef struct { int iy; int iv[RAN_NTAB]; int idum; } ran1_t;
+
+static void ran1_seed(ran1_t *s, int seed) { s->iy = 0; s->idum = seed; memset(s->iv, 0, sizeof s->iv); }
+
+static int ran1_step(int v) {           /* Schrage: v * 16807 mod (2^31 - 1) */
+  int k = v / RAN_IQ;
+  v = RAN_IA * (v - k * RAN_IQ) - RAN_IR * k;
+  if (v < 0) v += RAN_IM;
+  return v;
+}
+
+float orc_ran1(ran1_t *s) {
+  const double am = 1.0 / RAN_IM;
+  const double rnmx = 1.0 - 1.2e-7;
+  if (s->idum <= 0 || s->iy == 0) {
+    s->idum = (-(s->idum) < 1) ? 1 : -(s->idum);
+    for (int j = RAN_NTAB + 7; j >= 0; j--) {
+      s->idum = ran1_step(s->idum);
+      if (j < RAN_NTAB) s->iv[j] = s->idum;
+    }
+    s->iy = s->iv[1];                 /* sic: the reference's generic variant reads slot 1 (rf.c:6095) */
+  }
+  s->idum = ran1_step(s->idum);
+  int j = s->iy / RAN_NDIV;
+  s->iy = s->iv[j];
+  s->iv[j] = s->idum;
+  float t = (float) (am * s->iy);
+  if ((double) t > rnmx) return (float) rnmx;
+  return t;
+}
+
+static unsigned lcg_next(unsigned s) { return (1366u * s + 150889u) % 714025u; }
+
+/* chain seeds for trees 1..ntree, three chains A (bootstrap), B (covariates), C (unused here) */
+void orc_chain_seeds(int seed, int ntree, int *seedA, int *seedB) {
+  unsigned s = (unsigned) abs(seed);
+  if (s >= 714025u) s %= 714025u;
+  for (int pass = 0; pass < 2; pass++) {
+    for (int b = 0; b < ntree; b++) {
+      s = lcg_next(s);
+      s = lcg_next(s);
+      while (s == 0) s = lcg_next(s);
+      if (pass == 0) seedA[b] = -(int) s; else seedB[b] = -(int) s;
+    }
+  }
+}
+
+/* in predict / restore mode the LCG starts from 0 and chain A comes from forest$seed
+   (rf.c:6453, rf.c:6665, rf.c:7046-7050) */
+void orc_chain_seeds_restore(int ntree, int *seedB) {
+  unsigned s = 0;
+  for (int b = 0; b < ntree; b++) {
+    s = lcg_next(s);
+    s = lcg_next(s);
+    while (s == 0) s = lcg_next(s);
+    seedB[b] = -(int) s;
+  }
+}
+
+/* ------------------------------------------------------------ split statistic (sc.c:639-1687) */
+
+typedef struct { double E, N, T, W; } suff_t;     /* per (side, stratum) sufficient statistics */
+
+static int rule_stratified(int rule) { return rule == 1 || rule == 3 || rule == 4 || rule == 6; }
+static int rule_unit_time(int rule)  { return rule == 3 || rule == 6; }
+static int rule_bayes(int rule)      { return rule <= 3; }
+
+/* one side's statistic: sum over strata 1..K in ascending order (sc.c:751-764, sc.c:1262-1290) */
+static double side_stat(int rule, int K, const suff_t *s, double alpha, double beta) {
+  double stat = 0.0;
+  if (rule_bayes(rule)) {
+    for (int j = 1; j <= K; j++) {
+      double lam = (s[j].E + alpha) / (beta + s[j].T);
+      stat += s[j].E * log(lam);
+    }
+  } else {
+    for (int j = 1; j <= K; j++) {
+      double mu = (s[j].T == 0) ? 0.0 : s[j].W / s[j].T;
+      if (mu != 0) stat += (s[j].E * log(mu)) - (s[j].N * mu);
+    }
+  }
+  return stat;
+}
+
+/* Restatement of one plugin call (sc.c: poissonSplitN) for direct comparison with the reference
+   symbol; arrays are 0-based here, membership 1 = LEFT. */
+double orc_poisson_stat(int rule, int n, double k_for_alpha, const char *membership,
+                        const double *response, const double *strat, const double *rt) {
+  int K = 1;
+  if (rule_stratified(rule)) { K = 0; for (int i = 0; i < n; i++) if (strat[i] > K) K = (int) strat[i]; }
+  double ysum = 0, rtsum = 0;
+  for (int i = 0; i < n; i++) { ysum += response[i]; rtsum += rt[i]; }
+  double alpha = 1 / (k_for_alpha * k_for_alpha);
+  double beta = alpha / (ysum / rtsum);
+  suff_t *P = calloc(3 * (size_t) (K + 1), sizeof(suff_t)), *L = P + (K + 1), *R = L + (K + 1);
+  for (int i = 0; i < n; i++) {
+    int j = rule_stratified(rule) ? (int) strat[i] : 1;
+    double t = rule_unit_time(rule) ? 1.0 : rt[i];
+    double e = response[i] - 1;
+    suff_t *S = (membership[i] == 1) ? L : R;
+    if (response[i] == 2.0) { P[j].E++; S[j].E++; }
+    P[j].N++; S[j].N++;
+    P[j].T += t; S[j].T += t;
+    P[j].W += e * t; S[j].W += e * t;
+  }
+  double d = side_stat(rule, K, L, alpha, beta) + side_stat(rule, K, R, alpha, beta) - side_stat(rule, K, P, alpha, beta);
+  free(P);
+  return d;
+}
+
+/* -------------------------------------------------------------------------- tree growth */
+
+typedef struct {
+  const orc_args *a;
+  int b;                       /* 0-based tree */
+  ran1_t chainB;
+  int leafCount;
+  int Kmax;
+  /* growing per-tree outputs */
+  int *nodeID, *parmID; double *contPT, *stat; long nnodes, cap;
+  int *nodeMembership;         /* [n] leaf id of every row */
+  int *tnRCNT, *tnACNT, *tnE;  /* indexed by leaf id (1-based), capacity n+1 */
+  int *rmbr, *ambr; long rmbrIter, ambrIter;
+  long candidates;
+  /* scratch */
+  double *xs; int *ord; suff_t *L, *R, *P; double *statL, *statR; double *gval; int *gend;
+} tree_ctx;
+
+static void push_node(tree_ctx *c, int nodeID, int parm, double cut, double stat) {
+  if (c->nnodes == c->cap) {
+    c->cap = c->cap ? 2 * c->cap : 1024;
+    c->nodeID = realloc(c->nodeID, c->cap * sizeof(int));
+    c->parmID = realloc(c->parmID, c->cap * sizeof(int));
+    c->contPT = realloc(c->contPT, c->cap * sizeof(double));
+    c->stat   = realloc(c->stat,   c->cap * sizeof(double));
+  }
+  c->nodeID[c->nnodes] = nodeID; c->parmID[c->nnodes] = parm; c->contPT[c->nnodes] = cut; c->stat[c->nnodes] = stat;
+  c->nnodes++;
+}
+
+static const double *g_sort_key;
+static int cmp_ord(const void *pa, const void *pb) {
+  int a = *(const int *) pa, b = *(const int *) pb;
+  double xa = g_sort_key[a], xb = g_sort_key[b];
+  if (xa < xb) return -1;
+  if (xa > xb) return 1;
+  return (a > b) - (a < b);
+}
+
+/* Score every cut of covariate `cov` in a node whose in-bag rows are rep[0..m); feed each delta
+   (already multiplied by the split weight) to the sequential tracker of rf.c:15471-15551.
+   Returns the number of distinct values. */
+static int score_covariate(tree_ctx *c, int cov, const int *rep, int m,
+                           int *have_best, double *best_delta, int *best_cov, double *best_cut) {
+  const orc_args *a = c->a;
+  const double *col = a->x + (size_t) cov * a->n;
+  const int rule = a->rule;
+  double *xs = c->xs; int *ord = c->ord;
+  for (int i = 0; i < m; i++) { xs[i] = col[rep[i]]; ord[i] = i; }
+  g_sort_key = xs;
+  qsort(ord, m, sizeof(int), cmp_ord);
+  /* distinct-value groups (rf.c:14989-14996): gend[g] = one past the last sorted position of group g */
+  int D = 0;
+  for (int i = 0; i < m; i++) {
+    if (i == 0 || xs[ord[i]] > c->gval[D - 1]) { c->gval[D] = xs[ord[i]]; D++; }
+    c->gend[D - 1] = i + 1;
+  }
+  if (D < 2) return D;
+  c->candidates += D - 1;
+
+  int K = 1;
+  if (rule_stratified(rule)) { K = 0; for (int i = 0; i < m; i++) if (a->strat[rep[i]] > K) K = a->strat[rep[i]]; }
+  double ysum = 0, rtsum = 0;
+  for (int i = 0; i < m; i++) { int r = rep[ord[i]]; ysum += a->y[r]; rtsum += a->rt[r]; }
+  double alpha = 1 / (a->k_for_alpha * a->k_for_alpha);
+  double beta = alpha / (ysum / rtsum);
+
+  suff_t *L = c->L, *R = c->R, *P = c->P;
+  memset(L, 0, (K + 1) * sizeof(suff_t)); memset(R, 0, (K + 1) * sizeof(suff_t)); memset(P, 0, (K + 1) * sizeof(suff_t));
+#define ADD_ROW(S, r) do { \
+    int j_ = rule_stratified(rule) ? a->strat[r] : 1; \
+    double t_ = rule_unit_time(rule) ? 1.0 : a->rt[r]; \
+    double e_ = a->y[r] - 1; \
+    if (a->y[r] == 2.0) (S)[j_].E++; \
+    (S)[j_].N++; (S)[j_].T += t_; (S)[j_].W += e_ * t_; } while (0)
+  /* forward pass: left-side statistic after each group except the last */
+  int pos = 0;
+  for (int g = 0; g < D; g++) {
+    for (; pos < c->gend[g]; pos++) { int r = rep[ord[pos]]; ADD_ROW(L, r); ADD_ROW(P, r); }
+    if (g < D - 1) c->statL[g] = side_stat(rule, K, L, alpha, beta);
+  }
+  double statP = side_stat(rule, K, P, alpha, beta);
+  /* backward pass: right-side statistic for the cut after group g = rows of groups g+1..D-1 */
+  pos = m;
+  for (int g = D - 1; g >= 1; g--) {
+    for (; pos > c->gend[g - 1]; pos--) { int r = rep[ord[pos - 1]]; ADD_ROW(R, r); }
+    c->statR[g - 1] = side_stat(rule, K, R, alpha, beta);
+  }
+#undef ADD_ROW
+  double w = a->split_weight ? a->split_weight[cov] : 1.0;
+  for (int g = 0; g < D - 1; g++) {
+    double delta = (c->statL[g] + c->statR[g] - statP) * w;
+    int flag;
+    if (!*have_best) flag = 1;
+    else flag = (delta - *best_delta) > 1.0e-9;
+    if (flag) { *have_best = 1; *best_delta = delta; *best_cov = cov; *best_cut = c->gval[g]; }
+  }
+  return D;
+}
+
+static void grow_node(tree_ctx *c, int *rep, int m, int *all, int na, int depth, int nodeID, char *perm) {
+  const orc_args *a = c->a;
+  int have_best = 0, best_cov = -1; double best_delta = 0, best_cut = 0;
+  int attempt = (m >= 2 * a->nodesize) && (a->nodedepth < 0 || depth < a->nodedepth);
+  if (attempt) {
+    /* purity: variance of the response codes over in-bag rows (rf.c:6391-6416) */
+    double mean = 0; for (int i = 0; i < m; i++) mean += a->y[rep[i]];
+    mean /= (double) m;
+    double var = 0; for (int i = 0; i < m; i++) var += pow(mean - a->y[rep[i]], 2.0);
+    var /= (double) m;
+    if (var <= 1.0e-9) attempt = 0;
+  }
+  if (attempt) {
+    int *pool = malloc((a->p + 1) * sizeof(int)); int size = 0;
+    for (int k = 0; k < a->p; k++) if (perm[k]) pool[++size] = k;     /* 1-based slots, rf.c:8209-8213 */
+    int count = 0;
+    while (count < a->mtry && size > 0) {
+      count++;
+      int slot = (int) ceil((double) orc_ran1(&c->chainB) * (size * 1.0));
+      int cov = pool[slot];
+      pool[slot] = pool[size]; size--;
+      int D = score_covariate(c, cov, rep, m, &have_best, &best_delta, &best_cov, &best_cut);
+      if (D < 2) perm[cov] = 0;                                        /* rf.c:15004-15007 */
+    }
+    free(pool);
+  }
+  if (have_best) {
+    push_node(c, nodeID, best_cov + 1, best_cut, best_delta);
+    c->leafCount++;
+    int leftID = nodeID, rightID = c->leafCount;
+    const double *col = a->x + (size_t) best_cov * a->n;
+    int *repL = malloc((size_t) m * sizeof(int)), *repR = malloc((size_t) m * sizeof(int)); int mL = 0, mR = 0;
+    for (int i = 0; i < m; i++) { if (best_cut - col[rep[i]] >= 0.0) repL[mL++] = rep[i]; else repR[mR++] = rep[i]; }
+    int *allL = malloc((size_t) na * sizeof(int)), *allR = malloc((size_t) na * sizeof(int)); int aL = 0, aR = 0;
+    for (int i = 0; i < na; i++) { if (best_cut - col[all[i]] >= 0.0) allL[aL++] = all[i]; else allR[aR++] = all[i]; }
+    char *permL = malloc(a->p), *permR = malloc(a->p);
+    memcpy(permL, perm, a->p); memcpy(permR, perm, a->p);
+    grow_node(c, repL, mL, allL, aL, depth + 1, leftID, permL);
+    grow_node(c, repR, mR, allR, aR, depth + 1, rightID, permR);
+    free(repL); free(repR); free(allL); free(allR); free(permL); free(permR);
+  } else {
+    push_node(c, nodeID, 0, NAN, NAN);
+    int E = 0; for (int i = 0; i < m; i++) if (a->y[rep[i]] == 2.0) E++;
+    c->tnRCNT[nodeID] = m; c->tnACNT[nodeID] = na; c->tnE[nodeID] = E;
+    for (int i = 0; i < na; i++) { c->nodeMembership[all[i]] = nodeID; c->ambr[c->ambrIter++] = all[i] + 1; }
+    for (int i = 0; i < m; i++) c->rmbr[c->rmbrIter++] = rep[i] + 1;
+  }
+}
+
+orc_out *orc_grow(const orc_args *a) {
+  const int n = a->n, ntree = a->ntree;
+  orc_out *o = calloc(1, sizeof *o);
+  o->ntree = ntree; o->n = n;
+  o->leafCount = calloc(ntree, sizeof(int));
+  o->seed = calloc(ntree, sizeof(int));
+  o->bootMembership = calloc((size_t) ntree * n, sizeof(int));
+  o->nodeMembership = calloc((size_t) ntree * n, sizeof(int));
+  o->rmbr_stride = (a->max_boot > 0 ? a->max_boot : n);           /* RF-SRC sizes rmbr by maxBootstrapSize (rf.c:18296) */
+  o->rmbr = calloc((size_t) ntree * o->rmbr_stride, sizeof(int));
+  o->ambr = calloc((size_t) ntree * n, sizeof(int));
+  o->oobNum = calloc(2 * (size_t) n, sizeof(double)); o->allNum = calloc(2 * (size_t) n, sizeof(double));
+  o->oobDen = calloc(n, sizeof(int)); o->allDen = calloc(n, sizeof(int));
+  o->oobEns = calloc(2 * (size_t) n, sizeof(double)); o->allEns = calloc(2 * (size_t) n, sizeof(double));
+  int *seedA = malloc(ntree * sizeof(int)), *seedB = malloc(ntree * sizeof(int));
+  if (a->tree_seeds) { memcpy(seedA, a->tree_seeds, ntree * sizeof(int)); orc_chain_seeds_restore(ntree, seedB); }
+  else orc_chain_seeds(a->seed, ntree, seedA, seedB);
+  int Kmax = 1; for (int i = 0; i < n; i++) if (a->strat[i] > Kmax) Kmax = a->strat[i];
+
+  long leaf_cap = 0, node_cap = 0;
+  for (int b = 0; b < ntree; b++) {
+    tree_ctx c; memset(&c, 0, sizeof c);
+    c.a = a; c.b = b; c.Kmax = Kmax;
+    o->seed[b] = seedA[b];
+    ran1_t chainA; ran1_seed(&chainA, seedA[b]); ran1_seed(&c.chainB, seedB[b]);
+    /* bootstrap (rf.c:520-533) */
+    int bs; int *rep;
+    int *boot = o->bootMembership + (size_t) b * n;
+    if (a->samp) {
+      const int *cnt = a->samp + (size_t) b * n; bs = 0;
+      for (int k = 0; k < n; k++) bs += cnt[k];
+      rep = malloc((size_t) (bs > 0 ? bs : 1) * sizeof(int)); int i = 0;
+      for (int k = 0; k < n; k++) for (int j = 0; j < cnt[k]; j++) rep[i++] = k;
+    } else {
+      bs = a->boot_size ? a->boot_size[b] : n;
+      rep = malloc((size_t) bs * sizeof(int));
+      for (int i = 0; i < bs; i++) {
+        int k = (int) ceil((double) orc_ran1(&chainA) * (n * 1.0));
+        rep[i] = k - 1;
+      }
+    }
+    for (int i = 0; i < bs; i++) boot[rep[i]]++;
+    int *all = malloc((size_t) n * sizeof(int)); for (int i = 0; i < n; i++) all[i] = i;
+    char *perm = malloc(a->p); memset(perm, 1, a->p);
+    c.nodeMembership = o->nodeMembership + (size_t) b * n;
+    c.tnRCNT = calloc((size_t) n + 2, sizeof(int)); c.tnACNT = calloc((size_t) n + 2, sizeof(int)); c.tnE = calloc((size_t) n + 2, sizeof(int));
+    c.rmbr = o->rmbr + (size_t) b * o->rmbr_stride; c.ambr = o->ambr + (size_t) b * n;
+    c.xs = malloc((size_t) bs * sizeof(double)); c.ord = malloc((size_t) bs * sizeof(int));
+    c.L = malloc((Kmax + 1) * sizeof(suff_t)); c.R = malloc((Kmax + 1) * sizeof(suff_t)); c.P = malloc((Kmax + 1) * sizeof(suff_t));
+    c.statL = malloc((size_t) bs * sizeof(double)); c.statR = malloc((size_t) bs * sizeof(double));
+    c.gval = malloc((size_t) bs * sizeof(double)); c.gend = malloc((size_t) bs * sizeof(int));
+    c.leafCount = 1;
+    grow_node(&c, rep, bs, all, n, 0, 1, perm);
+    o->leafCount[b] = c.leafCount;
+    o->candidates += c.candidates;
+    /* append forest records */
+    if (o->total_nodes + c.nnodes > node_cap) {
+      node_cap = 2 * (o->total_nodes + c.nnodes);
+      o->treeID = realloc(o->treeID, node_cap * sizeof(int)); o->nodeID = realloc(o->nodeID, node_cap * sizeof(int));
+      o->parmID = realloc(o->parmID, node_cap * sizeof(int)); o->contPT = realloc(o->contPT, node_cap * sizeof(double));
+      o->splitStat = realloc(o->splitStat, node_cap * sizeof(double));
+    }
+    for (long k = 0; k < c.nnodes; k++) {
+      long q = o->total_nodes + k;
+      o->treeID[q] = b + 1; o->nodeID[q] = c.nodeID[k]; o->parmID[q] = c.parmID[k]; o->contPT[q] = c.contPT[k]; o->splitStat[q] = c.stat[k];
+    }
+    o->total_nodes += c.nnodes;
+    if (o->total_leaves + c.leafCount > leaf_cap) {
+      leaf_cap = 2 * (o->total_leaves + c.leafCount);
+      o->tnRCNT = realloc(o->tnRCNT, leaf_cap * sizeof(int)); o->tnACNT = realloc(o->tnACNT, leaf_cap * sizeof(int));
+      o->tnCLAS = realloc(o->tnCLAS, 2 * leaf_cap * sizeof(int));
+    }
+    for (int l = 1; l <= c.leafCount; l++) {
+      long q = o->total_leaves + l - 1;
+      o->tnRCNT[q] = c.tnRCNT[l]; o->tnACNT[q] = c.tnACNT[l];
+      o->tnCLAS[2 * q] = c.tnRCNT[l] - c.tnE[l]; o->tnCLAS[2 * q + 1] = c.tnE[l];
+    }
+    o->total_leaves += c.leafCount;
+    /* ensembles (rf.c:928-962): class proportion of the leaf's in-bag members */
+    for (int i = 0; i < n; i++) {
+      int l = c.nodeMembership[i];
+      double p1 = (double) (c.tnRCNT[l] - c.tnE[l]) / (double) c.tnRCNT[l];
+      double p2 = (double) c.tnE[l] / (double) c.tnRCNT[l];
+      o->allDen[i]++; o->allNum[i] += p1; o->allNum[n + i] += p2;
+      if (boot[i] == 0) { o->oobDen[i]++; o->oobNum[i] += p1; o->oobNum[n + i] += p2; }
+    }
+    free(rep); free(all); free(perm); free(c.tnRCNT); free(c.tnACNT); free(c.tnE);
+    free(c.xs); free(c.ord); free(c.L); free(c.R); free(c.P); free(c.statL); free(c.statR); free(c.gval); free(c.gend);
+    free(c.nodeID); free(c.parmID); free(c.contPT); free(c.stat);
+  }
+  for (int i = 0; i < n; i++) {                     /* rf.c:8113-8125 */
+    for (int k = 0; k < 2; k++) {
+      o->allEns[(size_t) k * n + i] = o->allDen[i] ? o->allNum[(size_t) k * n + i] / o->allDen[i] : 0.0;
+      o->oobEns[(size_t) k * n + i] = o->oobDen[i] ? o->oobNum[(size_t) k * n + i] / o->oobDen[i] : 0.0;  /* never-OOB rows keep the 0 the output was allocated with (rf.c:8115) */
+    }
+  }
+  free(seedA); free(seedB);
+  return o;
+}
+
+/* Predict: route rows of fx ([p][m] columns) down every tree of a pre-order forest and average the
+   leaf class proportions (rf.c:3687-3747 routing, rf.c:928-962 ensemble).  leaf class counts come
+   from tnCLAS-style arrays (per tree, indexed by leaf id). */
+void orc_predict(int ntree, int p, long total_nodes, const int *treeID, const int *nodeID, const int *parmID,
+                 const double *contPT, const int *leafCount, const int *tnRCNT, const int *tnE,
+                 const double *fx, int m, double *ens /* [2][m] */, int *membership /* [ntree][m] */) {
+  (void) p;
+  long *child = malloc(total_nodes * sizeof(long));   /* right-child record index for internal nodes */
+  /* pre-order: left child of record q is q+1; right child follows the whole left subtree */
+  long *stack = malloc((total_nodes + 1) * sizeof(long)); long sp = 0;
+  for (long q = 0; q < total_nodes; q++) child[q] = -1;
+  for (long q = 0; q < total_nodes; q++) {
+    /* a record closes the most recent internal node still waiting for its right child when the
+       previous record ended a left subtree */
+    if (q > 0 && treeID[q] == treeID[q - 1] && parmID[q - 1] == 0) {
+      long par = stack[--sp];
+      child[par] = q;
+    }
+    if (q > 0 && treeID[q] != treeID[q - 1]) sp = 0;
+    if (parmID[q] != 0) stack[sp++] = q;
+  }
+  memset(ens, 0, 2 * (size_t) m * sizeof(double));
+  long root = 0, leafoff = 0;
+  for (int b = 0; b < ntree; b++) {
+    for (int i = 0; i < m; i++) {
+      long q = root;
+      while (parmID[q] != 0) {
+        double xv = fx[(size_t) (parmID[q] - 1) * m + i];
+        q = (contPT[q] - xv >= 0.0) ? q + 1 : child[q];
+      }
+      int l = nodeID[q];
+      if (membership) membership[(size_t) b * m + i] = l;
+      double cnt = (double) tnRCNT[leafoff + l - 1], e = (double) tnE[leafoff + l - 1];
+      ens[i] += (cnt - e) / cnt; ens[(size_t) m + i] += e / cnt;
+    }
+    root += 2 * (long) leafCount[b] - 1;
+    leafoff += leafCount[b];
+  }
+  for (size_t i = 0; i < 2 * (size_t) m; i++) ens[i] /= (double) ntree;
+  free(child); free(stack);
+}
+
+void orc_free(orc_out *o) {
+  if (!o) return;
+  free(o->treeID); free(o->nodeID); free(o->parmID); free(o->contPT); free(o->splitStat);
+  free(o->leafCount); free(o->seed); free(o->bootMembership); free(o->nodeMembership);
+  free(o->tnRCNT); free(o->tnACNT); free(o->tnCLAS); free(o->rmbr); free(o->ambr);
+  free(o->oobNum); free(o->allNum); free(o->oobDen); free(o->allDen); free(o->oobEns); free(o->allEns);
+  free(o);
+}
+
+/* bootstrap-only entry (chain A replay) for the in-bag parity tests */
+void orc_bootstrap(int seed, int ntree, int n, int tree /* 0-based */, int *draws /* [n], 1-based row ids */) {
+  int *seedA = malloc(ntree * sizeof(int)), *seedB = malloc(ntree * sizeof(int));
+  orc_chain_seeds(seed, ntree, seedA, seedB);
+  ran1_t s; ran1_seed(&s, seedA[tree]);
+  for (int i = 0; i < n; i++) draws[i] = (int) ceil((double) orc_ran1(&s) * (n * 1.0));
+  free(seedA); free(seedB);
+}
+
+/* first `count` floats of a ran1 chain started from `seed` (unit test of the generator) */
+void orc_ran1_stream(int seed, int count, float *out) {
+  ran1_t s; ran1_seed(&s, seed);
+  for (int i = 0; i < count; i++) out[i] = orc_ran1(&s);
+}

@@ -1,0 +1,48 @@
+/* rfslam_oracle.h -- TEST INFRASTRUCTURE ONLY: interface of the CPU restatement (see rfslam_oracle.c). */
+#ifndef RFSLAM_ORACLE_H
+#define RFSLAM_ORACLE_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+  int n, p, ntree, mtry, nodesize, nodedepth, rule, seed, max_boot;
+  double k_for_alpha;
+  const double *x;            /* [p][n] */
+  const double *y;            /* [n] in {1,2} */
+  const double *rt;           /* [n] */
+  const int    *strat;        /* [n] >= 1 */
+  const int    *samp;         /* [ntree][n] in-bag counts (bootstrap = by.user) or NULL */
+  const int    *boot_size;    /* [ntree] or NULL (= n) */
+  const double *split_weight; /* [p] or NULL */
+  const int    *tree_seeds;   /* [ntree] chain-A seeds (restore) or NULL (grow) */
+} orc_args;
+
+typedef struct {
+  int ntree, n;
+  long total_nodes, total_leaves, candidates, rmbr_stride;
+  int *treeID, *nodeID, *parmID; double *contPT, *splitStat;      /* pre-order, tree order */
+  int *leafCount, *seed;
+  int *bootMembership, *nodeMembership;                            /* [ntree][n] */
+  int *tnRCNT, *tnACNT, *tnCLAS;                                   /* per tree, leafCount[b] entries */
+  int *rmbr, *ambr;                                                /* [ntree][stride], [ntree][n] */
+  double *oobNum, *allNum; int *oobDen, *allDen;
+  double *oobEns, *allEns;                                         /* [2][n] class-major */
+} orc_out;
+
+orc_out *orc_grow(const orc_args *a);
+void     orc_free(orc_out *o);
+void     orc_predict(int ntree, int p, long total_nodes, const int *treeID, const int *nodeID, const int *parmID,
+                     const double *contPT, const int *leafCount, const int *tnRCNT, const int *tnE,
+                     const double *fx, int m, double *ens, int *membership);
+double   orc_poisson_stat(int rule, int n, double k_for_alpha, const char *membership,
+                          const double *response, const double *strat, const double *rt);
+void     orc_chain_seeds(int seed, int ntree, int *seedA, int *seedB);
+void     orc_chain_seeds_restore(int ntree, int *seedB);
+void     orc_bootstrap(int seed, int ntree, int n, int tree, int *draws);
+void     orc_ran1_stream(int seed, int count, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,115 @@
+"""Regenerate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/librfslam_ref.so).
+
+Run in the build container only (needs /root/reference to have been compiled by
+`make -C oracle ref`):   python tests/golden/make_golden.py
+Each file holds the seeded synthetic inputs and the reference's own outputs for them, with the
+forest records re-ordered by treeID (the reference appends trees in thread-completion order,
+randomForestSRC.c:20938-20946) and trimmed the way R/rfsrc.R:1766-1861 trims them.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import refdriver as rd          # noqa: E402
+from rfslam_b200.synth import make_cpiu     # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def canon(r, n):
+    t = rd.trim_forest(r, n)
+    order = np.argsort(t["treeID"], kind="stable")
+    for k in ("treeID", "nodeID", "parmID", "contPT", "mwcpSZ"):
+        t[k] = t[k][order]
+    return t
+
+
+GROW_CASES = [
+    # name, n, p, levels, rule, ntree, nodesize, mtry, forest seed, data seed, by.user
+    ("grow_r1_q64", 1500, 9, 64, 1, 6, 5, None, -12345, 20260101, False),
+    ("grow_r2_q64", 1500, 9, 64, 2, 6, 5, None, -12345, 20260101, False),
+    ("grow_r3_q64", 1500, 9, 64, 3, 6, 5, None, -12345, 20260101, False),
+    ("grow_r4_q64", 1500, 9, 64, 4, 6, 5, None, -12345, 20260101, False),
+    ("grow_r5_q64", 1500, 9, 64, 5, 6, 5, None, -12345, 20260101, False),
+    ("grow_r6_q64", 1500, 9, 64, 6, 6, 5, None, -12345, 20260101, False),
+    ("grow_r4_cont", 2500, 12, 0, 4, 5, 20, None, -777, 11, False),
+    ("grow_r1_cont", 1200, 7, 0, 1, 5, 3, 7, -31, 12, False),
+    ("grow_r4_byuser", 1800, 10, 32, 4, 5, 5, None, -99, 13, True),
+    ("grow_r4_q256_big", 12000, 20, 256, 4, 4, 20, None, -4242, 14, False),
+    ("grow_r1_mtry1", 900, 6, 16, 1, 8, 2, 1, -5, 15, False),
+]
+
+
+def main():
+    for (name, n, p, levels, rule, ntree, nodesize, mtry, seed, dseed, byuser) in GROW_CASES:
+        d = make_cpiu(n, p, levels=levels, seed=dseed)
+        samp = None
+        if byuser:
+            rng = np.random.default_rng(dseed + 1)
+            samp = rng.multinomial(int(0.8 * n), np.full(n, 1.0 / n), size=ntree).astype(np.int32)
+        r = rd.grow(d.x, d.y, d.rt, d.strat, rule=rule, ntree=ntree, nodesize=nodesize, mtry=mtry,
+                    seed=seed, samp=samp)
+        t = canon(r, n)
+        dt = make_cpiu(max(200, n // 3), p, levels=levels, seed=dseed + 1000)
+        pr = rd.predict(d.x, d.y, t, dt.x, samp=samp, nodesize=nodesize)
+        save = dict(
+            x=d.x, y=d.y, rt=d.rt, strat=d.strat,
+            params=np.array([n, p, levels, rule, ntree, nodesize, -1 if mtry is None else mtry, seed, dseed, int(byuser)], np.int64),
+            fx=dt.x, pred_allEnsbCLS=pr["allEnsbCLS"], pred_nodeMembership=pr["nodeMembership"])
+        if samp is not None:
+            save["samp"] = samp
+        for k in ("oobEnsbCLS", "allEnsbCLS", "leafCount", "seed", "nodeMembership", "bootMembership",
+                  "treeID", "nodeID", "parmID", "contPT", "mwcpSZ", "tnRCNT", "tnACNT",
+                  "rmbrMembership", "ambrMembership"):
+            save["ref_" + k] = t[k]
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **save)
+        print(name, "nodes", t["treeID"].size, "bytes", os.path.getsize(os.path.join(OUT, name + ".npz")))
+
+    # known-answer vectors for the six plugin functions themselves (splitCustom.c:639-1687),
+    # called the way randomForestSRC.c:13469-13482 calls them (1-based arrays, featureCount = 2)
+    L = rd.lib()
+    rng = np.random.default_rng(7)
+    kat = {}
+    proto = C.CFUNCTYPE(C.c_double, C.c_uint, C.c_double, C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint,
+                        C.c_void_p, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_uint,
+                        C.POINTER(C.POINTER(C.c_double)), C.c_uint)
+    cases = []
+    for m in (2, 3, 17, 64, 333, 2000):
+        for K in (1, 4, 16):
+            cases.append((m, K))
+    idx = 0
+    for (m, K) in cases:
+        resp = 1.0 + (rng.random(m) < 0.2)
+        strat = rng.integers(1, K + 1, m).astype(np.float64)
+        rtv = np.where(rng.random(m) < 0.8, 0.5, rng.uniform(0.01, 0.5, m))
+        left = max(1, min(m - 1, int(rng.integers(1, m))))
+        memb = np.zeros(m, np.int8); memb[:left] = 1
+        rng.shuffle(memb)
+        kfa = float(rng.choice([0.5, 1.0, 2.0, 3.0]))
+        stats = np.zeros(6)
+        r1 = np.concatenate([[0.0], resp]); s1 = np.concatenate([[0.0], strat]); t1 = np.concatenate([[0.0], rtv])
+        m1 = np.concatenate([[0], memb]).astype(np.int8)
+        feat = (C.POINTER(C.c_double) * 3)(None, s1.ctypes.data_as(C.POINTER(C.c_double)), t1.ctypes.data_as(C.POINTER(C.c_double)))
+        for rule in range(1, 7):
+            fn = proto(("poissonSplit%d" % rule, L))
+            stats[rule - 1] = fn(m, kfa, m1.ctypes.data_as(C.c_char_p), None, None, 0, 0, None,
+                                 r1.ctypes.data_as(C.POINTER(C.c_double)), 0.0, 0.0, 2, feat, 2)
+        kat["resp_%d" % idx] = resp; kat["strat_%d" % idx] = strat; kat["rt_%d" % idx] = rtv
+        kat["memb_%d" % idx] = memb; kat["kfa_%d" % idx] = np.array([kfa]); kat["stat_%d" % idx] = stats
+        idx += 1
+    kat["count"] = np.array([idx])
+    np.savez_compressed(os.path.join(OUT, "plugin_kat.npz"), **kat)
+    print("plugin_kat", idx, "cases")
+
+    # RNG known answers: chain seeds and the first draws of the bootstrap, read back from the
+    # reference's own outputs (seed[] and bootMembership are enough to pin chain A; chain B is
+    # pinned by the grown trees).
+    print("done")
+
+
+if __name__ == "__main__":
+    main()

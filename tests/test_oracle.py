@@ -1,0 +1,100 @@
+"""CPU suite: pins the oracle restatement (oracle/rfslam_oracle.c) against the reference's own
+outputs -- the committed golden fixtures (generated from the unmodified reference by
+tests/golden/make_golden.py) and, when oracle/_ref/librfslam_ref.so is present, the reference
+itself run live on fresh seeds."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import port, refdriver
+from rfslam_b200.synth import make_cpiu
+from tests import parity
+
+
+def _golden_names():
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return [os.path.basename(f) for f in parity.golden_files(here)]
+
+
+@pytest.mark.parametrize("name", _golden_names())
+def test_port_matches_golden_grow(golden_dir, name):
+    g = parity.load_golden(os.path.join(golden_dir, name))
+    q = parity.golden_params(g)
+    got = port.grow(g["x"], g["y"], g["rt"], g["strat"], rule=q["rule"], ntree=q["ntree"], nodesize=q["nodesize"],
+                    mtry=q["mtry"], seed=q["seed"], samp=g.get("samp"))
+    parity.assert_forest_equal(got, parity.golden_ref_forest(g), q["n"], q["ntree"], check_membr_lists=True, label=name)
+
+
+@pytest.mark.parametrize("name", _golden_names())
+def test_port_matches_golden_predict(golden_dir, name):
+    g = parity.load_golden(os.path.join(golden_dir, name))
+    ref = parity.golden_ref_forest(g)
+    tn_e = np.zeros_like(ref["tnRCNT"])
+    # leaf event counts are not a reference output; rebuild them from rmbr (in-bag rows by leaf)
+    q = parity.golden_params(g)
+    n, ntree = q["n"], q["ntree"]
+    stride = ref["rmbrMembership"].size // ntree
+    off = 0
+    for b in range(ntree):
+        rm = ref["rmbrMembership"][b * stride:(b + 1) * stride]
+        t = parity.split_tree(ref, b + 1)
+        pos = 0
+        for leaf in t["nodeID"][t["parmID"] == 0]:          # rmbr is grouped by leaf in DFS order
+            c = ref["tnRCNT"][off + leaf - 1]
+            rows = rm[pos:pos + c] - 1
+            tn_e[off + leaf - 1] = int(np.sum(g["y"][rows] == 2.0))
+            pos += c
+        off += ref["leafCount"][b]
+    f = dict(ref)
+    f["tnCLAS"] = np.stack([ref["tnRCNT"] - tn_e, tn_e], axis=1).reshape(-1)
+    ens, mem = port.predict(f, g["fx"])
+    np.testing.assert_array_equal(mem, g["pred_nodeMembership"])
+    np.testing.assert_allclose(ens, g["pred_allEnsbCLS"], rtol=parity.HAZARD_RTOL)
+
+
+def test_plugin_kat(golden_dir):
+    z = np.load(os.path.join(golden_dir, "plugin_kat.npz"))
+    for i in range(int(z["count"][0])):
+        for rule in range(1, 7):
+            got = port.poisson_stat(rule, float(z[f"kfa_{i}"][0]), z[f"memb_{i}"], z[f"resp_{i}"], z[f"strat_{i}"], z[f"rt_{i}"])
+            want = z[f"stat_{i}"][rule - 1]
+            assert got == pytest.approx(want, rel=1e-12, abs=1e-12), (i, rule, got, want)
+
+
+def test_chain_seeds_match_reference_seed_output(golden_dir):
+    g = parity.load_golden(os.path.join(golden_dir, "grow_r4_q64.npz"))
+    q = parity.golden_params(g)
+    a, _ = port.chain_seeds(q["seed"], q["ntree"])
+    np.testing.assert_array_equal(a, g["ref_seed"])
+
+
+def test_bootstrap_counts_match_reference(golden_dir):
+    g = parity.load_golden(os.path.join(golden_dir, "grow_r4_q64.npz"))
+    q = parity.golden_params(g)
+    for b in range(q["ntree"]):
+        d = port.bootstrap(q["seed"], q["ntree"], q["n"], b)
+        cnt = np.bincount(d - 1, minlength=q["n"])
+        np.testing.assert_array_equal(cnt, g["ref_bootMembership"][b * q["n"]:(b + 1) * q["n"]])
+
+
+def test_ran1_range_and_float_semantics():
+    s = port.ran1_stream(-4711, 5000)
+    assert s.dtype == np.float32
+    assert (s > 0).all() and (s <= np.float32(1.0 - 1.2e-7)).all()
+
+
+@pytest.mark.skipif(not refdriver.available(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("rule,n,p,levels,nodesize,seed,dseed", [
+    (4, 2200, 11, 32, 5, -31337, 501), (1, 1700, 8, 0, 10, -2, 502), (5, 1300, 6, 8, 1, -987654, 503),
+    (3, 1900, 13, 64, 4, -800000, 504)])
+def test_port_matches_live_reference(rule, n, p, levels, nodesize, seed, dseed):
+    d = make_cpiu(n, p, levels=levels, seed=dseed)
+    ntree = 5
+    r = refdriver.grow(d.x, d.y, d.rt, d.strat, rule=rule, ntree=ntree, nodesize=nodesize, seed=seed)
+    t = refdriver.trim_forest(r, n)
+    order = np.argsort(t["treeID"], kind="stable")
+    for k in ("treeID", "nodeID", "parmID", "contPT", "mwcpSZ"):
+        t[k] = t[k][order]
+    got = port.grow(d.x, d.y, d.rt, d.strat, rule=rule, ntree=ntree, nodesize=nodesize, seed=seed)
+    parity.assert_forest_equal(got, t, n, ntree, check_membr_lists=True, label="live")
