@@ -1,0 +1,219 @@
+/*
+ * rfslam_b200.h -- C-ABI of the B200-native rfSLAM hot path (librfslam_b200.so).
+ *
+ * This is the drop-in boundary: plain C, raw pointers and sizes, no torch
+ * or CUDA types.  Every entry point names the reference interface it replaces; paths are
+ * relative to /root/reference/src (rf.c = randomForestSRC.c, sc.c = splitCustom.c).
+ *
+ *   rfslam_b200_grow      <->  SEXP rfsrcGrow(44 x SEXP)      rf.c:22110-22217
+ *   rfslam_b200_predict   <->  SEXP rfsrcPredict(58 x SEXP)   rf.c:22219-22402
+ *   rfslam_b200_rule_of_slot / rfslam_b200_register_this
+ *                         <->  registerCustomFunctions / registerThis  sc.c:23-67, rf.c:8856-8866
+ *   rfslam_b200_score_node<->  one covariate's worth of customFunction calls
+ *                              (rf.c:13404-13529 -> sc.c poissonSplit1..6)
+ *
+ * All host arrays are caller-owned and read-only for the duration of the call (as R vectors are,
+ * rf.c:22169-22204); outputs are allocated by the callee and released with rfslam_b200_free_*().
+ * Every function returns 0 on success, non-zero on error; rfslam_b200_last_error() gives the text.
+ * There is no CPU fallback: without a CUDA device every compute entry fails with RFSLAM_ENODEV.
+ */
+#ifndef RFSLAM_B200_H
+#define RFSLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFSLAM_OK        0
+#define RFSLAM_EINVAL    1   /* bad argument (the reference would call RF_nativeExit) */
+#define RFSLAM_ENODEV    2   /* no CUDA device / CUDA failure */
+#define RFSLAM_ENOSUP    3   /* valid for the reference but outside the accelerated path */
+#define RFSLAM_ENOMEM    4
+
+/* option bits the path understands; same values as the reference (rf.h:108-158) */
+#define RFSLAM_OPT_BOOT_TYP1   0x00080000u   /* optLow  (by.user = TYP1|TYP2, rf.c:520) */
+#define RFSLAM_OPT_BOOT_TYP2   0x00100000u
+#define RFSLAM_OPTH_MEMB_USER  0x00000040u   /* optHigh: return nodeMembership / bootMembership */
+#define RFSLAM_OPTH_SPLT_CUST  0x00000F00u   /* optHigh: custom split slot - 1 (rf.h:147) */
+#define RFSLAM_OPTH_MEMB_OUTG  0x00010000u   /* optHigh: return rmbr/ambr/tnRCNT/tnACNT */
+
+/* ---------------------------------------------------------------- grow ------------------------ */
+
+/* Mirrors the 44 .Call arguments of rfsrcGrow in their order (rf.c:22110-22155); scalars by value,
+   vectors as pointers.  Fields the Poisson class path never reads are kept so that a binding can
+   forward every argument; they are validated, not ignored (see rfslam_b200_grow). */
+typedef struct rfslam_grow_args {
+  int32_t        trace_flag;
+  int32_t        seed;                /* must be < 0 (rf.c:6454) */
+  uint32_t       opt_low;
+  uint32_t       opt_high;
+  int32_t        split_rule;          /* 16 = custom (rf.h:189) */
+  int32_t        nsplit;              /* 0 = every distinct value is a cut */
+  int32_t        mtry;
+  int32_t        htry;                /* must be 0 (rf.c:6490-6494) */
+  int32_t        ytry;
+  int32_t        node_size;
+  int32_t        node_depth;          /* < 0 = unlimited */
+  int32_t        cr_weight_size;
+  const double  *cr_weight;
+  int32_t        ntree;
+  int32_t        observation_size;    /* n */
+  int32_t        y_size;              /* 1 */
+  const char    *r_type;              /* y_size chars; 'C' / 'I' / 'B' */
+  const int32_t *r_levels;
+  const double  *r_data;              /* [y_size][n] response codes 1.0 / 2.0 */
+  int32_t        x_size;              /* p */
+  const char    *x_type;              /* p chars; 'R' real, 'C' unordered factor (ENOSUP) */
+  const int32_t *x_levels;
+  const double  *risk_time;           /* [n] */
+  const int32_t *stratifier;          /* [n] >= 1 */
+  int32_t        max_strat;
+  const int32_t *var_categories;      /* [p] */
+  const double  *category_weights;    /* [n_categories] */
+  int32_t        n_categories;
+  const int32_t *to_fix;
+  int32_t        n_to_fix;
+  double         k_for_alpha;
+  int32_t        max_bootstrap_size;
+  const int32_t *bootstrap_size;      /* [ntree] */
+  const int32_t *bootstrap;           /* [ntree][n] in-bag counts when by.user, else unused */
+  const double  *case_weight;         /* [n] must be uniform */
+  const double  *x_split_stat_weight; /* [p] */
+  const double  *y_weight;            /* [y_size] */
+  const double  *x_weight;            /* [p] must be uniform */
+  const double  *x_data;              /* [p][n]: p contiguous columns of n (rf.c:22190, rf.c:22469) */
+  int32_t        time_interest_size;
+  const double  *time_interest;
+  int32_t        n_impute;
+  int32_t        perf_block;
+  int32_t        num_threads;         /* ignored: trees are scheduled on the GPU */
+
+  /* --- build-specific knobs (no reference counterpart) --- */
+  int32_t        device;              /* CUDA device ordinal; < 0 = current */
+  int32_t        tree_first;          /* this process grows trees tree_first, tree_first+tree_step, ... */
+  int32_t        tree_step;           /*   (1-based ids; 0/0 = all).  Seeds are derived for all ntree */
+                                      /*   trees on every rank, so tree b is identical for any sharding. */
+  int32_t        finalize_ensembles;  /* 1: divide by the denominators (single process); 0: return sums */
+} rfslam_grow_args;
+
+/* The reference's named output list for the class family (rf.c:9-79), sized by the
+   ACTUAL node counts (R trims the reference's theoretical-maximum arrays to exactly this,
+   R/rfsrc.R:1766-1861).  Trees appear in ascending treeID order, records in pre-order. */
+typedef struct rfslam_forest_out {
+  int32_t   ntree;             /* trees grown by this call (shard) */
+  int32_t   n;
+  int64_t   total_nodes;       /* sum over trees of 2*leafCount-1 */
+  int64_t   total_leaves;
+  int32_t  *tree_ids;          /* [ntree] which tree ids this shard holds */
+  int32_t  *treeID;            /* [total_nodes] */
+  int32_t  *nodeID;            /* [total_nodes] */
+  int32_t  *parmID;            /* [total_nodes] 0 = terminal */
+  double   *contPT;            /* [total_nodes] NA_REAL at terminals */
+  int32_t  *mwcpSZ;            /* [total_nodes] all 0 (no factor splits on this path) */
+  double   *splitStat;         /* [total_nodes] winning delta (NaN at terminals); not a reference output */
+  int32_t  *leafCount;         /* [ntree] */
+  int32_t  *seed;              /* [ntree] chain-A seed, as forest$seed */
+  int32_t  *tnRCNT;            /* [total_leaves] in-bag count per leaf, by tree then leaf id */
+  int32_t  *tnACNT;            /* [total_leaves] all-row count per leaf */
+  int32_t  *tnCLAS;            /* [total_leaves][2] in-bag class counts (non-event, event) */
+  int32_t  *nodeMembership;    /* [ntree][n] or NULL */
+  int32_t  *bootMembership;    /* [ntree][n] or NULL */
+  int32_t  *rmbrMembership;    /* [ntree][max_bootstrap_size] or NULL */
+  int32_t  *ambrMembership;    /* [ntree][n] or NULL */
+  double   *oobEnsbCLS;        /* [2][n] class-major: sums or ratios, see finalize_ensembles */
+  double   *allEnsbCLS;        /* [2][n] */
+  uint32_t *oobEnsbDen;        /* [n] */
+  uint32_t *allEnsbDen;        /* [n] */
+  /* measurement */
+  int64_t   split_candidates;  /* (node, covariate, cutpoint) triples scored */
+  int64_t   algorithmic_bytes; /* sum over attempted nodes of B_score + B_part + 4n per tree */
+  double    grow_kernel_ms;    /* device time of the tree-growing kernel(s), CUDA events */
+  double    total_device_ms;   /* device time of the whole call incl. bootstrap and ensembles */
+} rfslam_forest_out;
+
+int  rfslam_b200_grow(const rfslam_grow_args *args, rfslam_forest_out *out);
+void rfslam_b200_free_forest(rfslam_forest_out *out);
+
+/* Resident variant: upload + rank-code the CPIU table once, grow many forests from HBM.
+   rfslam_b200_grow() == dataset_create + grow_resident + dataset_destroy. */
+typedef struct rfslam_dataset rfslam_dataset;
+int  rfslam_b200_dataset_create(const rfslam_grow_args *args, rfslam_dataset **ds);
+int  rfslam_b200_grow_resident(rfslam_dataset *ds, const rfslam_grow_args *args, rfslam_forest_out *out);
+void rfslam_b200_dataset_destroy(rfslam_dataset *ds);
+/* bytes of HBM held by the resident table (codes + per-row arrays) */
+int64_t rfslam_b200_dataset_bytes(const rfslam_dataset *ds);
+
+/* ---------------------------------------------------------------- predict --------------------- */
+
+/* The subset of rfsrcPredict's 58 arguments the class path reads (rf.c:22219-22279): a forest in
+   the wire format of rf.c:10735-10806 plus held-out covariates.  Leaf class counts replace the
+   reference's "drop the training rows again" step (rf.c:3687-3747, rf.c:755-858). */
+typedef struct rfslam_predict_args {
+  int32_t        ntree;
+  int32_t        x_size;            /* p */
+  int64_t        total_nodes;
+  const int32_t *treeID;            /* [total_nodes] trees contiguous, records pre-order */
+  const int32_t *nodeID;
+  const int32_t *parmID;
+  const double  *contPT;
+  const int32_t *leafCount;         /* [ntree] in the order trees appear in treeID */
+  const int32_t *tnCLAS;            /* [total_leaves][2] by tree (same order) then leaf id */
+  int32_t        fobservation_size; /* m_test */
+  const double  *fx_data;           /* [p][m_test] */
+  int32_t        want_membership;   /* 1: fill nodeMembership */
+  int32_t        device;
+  int32_t        finalize_ensembles;
+} rfslam_predict_args;
+
+typedef struct rfslam_predict_out {
+  int32_t   m;
+  int32_t   ntree;
+  double   *allEnsbCLS;       /* [2][m] */
+  uint32_t *allEnsbDen;       /* [m] */
+  int32_t  *nodeMembership;   /* [ntree][m] or NULL */
+  double    kernel_ms;
+} rfslam_predict_out;
+
+int  rfslam_b200_predict(const rfslam_predict_args *args, rfslam_predict_out *out);
+void rfslam_b200_free_predict(rfslam_predict_out *out);
+
+/* ---------------------------------------------------------------- split-rule registry --------- */
+
+/* The reference selects a rule by family + slot: registerThis(func, family, slot) (rf.c:8856-8866),
+   slot = ((optHigh & 0x0F00) >> 8) + 1 (rf.c:18457-18504); "poisson.splitN" is CLAS_FAM slot N+1
+   (sc.c:47-62).  Here the six Poisson rules are device kernels; any other slot has no GPU
+   implementation and is refused (no CPU fallback). */
+#define RFSLAM_CLAS_FAM 0
+#define RFSLAM_REGR_FAM 1
+#define RFSLAM_SURV_FAM 2
+#define RFSLAM_CRSK_FAM 3
+/* rule 1..6 for a CLAS_FAM slot 2..7, 0 when the slot has no device rule */
+int  rfslam_b200_rule_of_slot(int family, int slot);
+/* re-map a slot to one of the six device rules (what registerThis does for function pointers) */
+int  rfslam_b200_register_this(int rule, int family, int slot);
+void rfslam_b200_register_defaults(void);
+
+/* Score every cutpoint of ONE covariate in ONE node on the device: the work of the reference's
+   per-cut loop rf.c:13404-13529 (virtuallySplitNode + gather + plugin call).
+   In: m rows of the node: x (the covariate), response codes (1/2), stratum (>= 1), risk time.
+   Out: the distinct values in ascending order and delta for the cut after each of them except the
+   last (cut_value[k], delta[k], k < *n_cuts), exactly what the plugin returns for that membership. */
+int  rfslam_b200_score_node(int rule, double k_for_alpha, int m, const double *x, const double *response,
+                            const int32_t *stratum, const double *risk_time,
+                            double *cut_value /* [m] */, double *delta /* [m] */, int32_t *n_cuts,
+                            int device);
+
+/* Chain-A replay only (rf.c:529-533): in-bag counts of tree `tree` (1-based) of an ntree forest. */
+int  rfslam_b200_bootstrap_counts(int seed, int ntree, int n, int tree, int32_t *counts /* [n] */, int device);
+
+const char *rfslam_b200_last_error(void);
+const char *rfslam_b200_version(void);
+int  rfslam_b200_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,125 @@
+// api.cu -- the extern "C" surface declared in include/rfslam_b200.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "internal.h"
+
+namespace rfslam {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+// family x slot -> device rule; the reference's customFunctionArray[4][16] (rf.c:486) with the
+// registrations of sc.c:47-62 (poissonSplitN in CLAS_FAM slot N+1)
+static int g_rule_table[4][16];
+static bool g_rule_init = false;
+
+static void ensure_defaults() {
+  if (!g_rule_init) {
+    memset(g_rule_table, 0, sizeof g_rule_table);
+    for (int r = 1; r <= 6; r++) g_rule_table[RFSLAM_CLAS_FAM][r] = r;      // slot r+1 -> index r
+    g_rule_init = true;
+  }
+}
+
+}  // namespace rfslam
+
+using namespace rfslam;
+
+extern "C" {
+
+const char* rfslam_b200_last_error(void) { return g_err; }
+const char* rfslam_b200_version(void) { return "rfslam_b200 0.1 (sm_100a)"; }
+
+int rfslam_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+void rfslam_b200_register_defaults(void) { g_rule_init = false; ensure_defaults(); }
+
+int rfslam_b200_register_this(int rule, int family, int slot) {
+  ensure_defaults();
+  if (family < 0 || family > 3 || slot < 1 || slot > 16) { set_error("family must be 0..3 and slot 1..16 (rf.c:8856-8866)"); return RFSLAM_EINVAL; }
+  if (rule < 0 || rule > 6) { set_error("only the six Poisson rules have device implementations"); return RFSLAM_ENOSUP; }
+  if (rule != 0 && family != RFSLAM_CLAS_FAM) { set_error("the Poisson rules are classification-family rules (sc.c:47-62)"); return RFSLAM_ENOSUP; }
+  g_rule_table[family][slot - 1] = rule;
+  return RFSLAM_OK;
+}
+
+int rfslam_b200_rule_of_slot(int family, int slot) {
+  ensure_defaults();
+  if (family < 0 || family > 3 || slot < 1 || slot > 16) return 0;
+  return g_rule_table[family][slot - 1];
+}
+
+int rfslam_b200_dataset_create(const rfslam_grow_args* args, rfslam_dataset** ds) {
+  if (!args || !ds) { set_error("null arguments"); return RFSLAM_EINVAL; }
+  return dataset_build(args, ds);
+}
+
+void rfslam_b200_dataset_destroy(rfslam_dataset* ds) { dataset_free(ds); }
+
+int64_t rfslam_b200_dataset_bytes(const rfslam_dataset* ds) { return ds ? ds->bytes : 0; }
+
+int rfslam_b200_grow_resident(rfslam_dataset* ds, const rfslam_grow_args* args, rfslam_forest_out* out) {
+  if (!ds || !args || !out) { set_error("null arguments"); return RFSLAM_EINVAL; }
+  return grow_forest(ds, args, out);
+}
+
+int rfslam_b200_grow(const rfslam_grow_args* args, rfslam_forest_out* out) {
+  if (!args || !out) { set_error("null arguments"); return RFSLAM_EINVAL; }
+  memset(out, 0, sizeof(*out));
+  GrowConfig cfg;
+  int rc = validate_grow_args(args, &cfg);
+  if (rc) return rc;
+  rfslam_dataset* ds = nullptr;
+  rc = dataset_build(args, &ds);
+  if (rc) return rc;
+  rc = grow_forest(ds, args, out);
+  dataset_free(ds);
+  return rc;
+}
+
+void rfslam_b200_free_forest(rfslam_forest_out* o) {
+  if (!o) return;
+  free(o->tree_ids); free(o->treeID); free(o->nodeID); free(o->parmID); free(o->contPT); free(o->mwcpSZ); free(o->splitStat);
+  free(o->leafCount); free(o->seed); free(o->tnRCNT); free(o->tnACNT); free(o->tnCLAS);
+  free(o->nodeMembership); free(o->bootMembership); free(o->rmbrMembership); free(o->ambrMembership);
+  free(o->oobEnsbCLS); free(o->allEnsbCLS); free(o->oobEnsbDen); free(o->allEnsbDen);
+  memset(o, 0, sizeof(*o));
+}
+
+int rfslam_b200_predict(const rfslam_predict_args* args, rfslam_predict_out* out) {
+  if (!args || !out) { set_error("null arguments"); return RFSLAM_EINVAL; }
+  return predict_forest(args, out);
+}
+
+void rfslam_b200_free_predict(rfslam_predict_out* o) {
+  if (!o) return;
+  free(o->allEnsbCLS); free(o->allEnsbDen); free(o->nodeMembership);
+  memset(o, 0, sizeof(*o));
+}
+
+int rfslam_b200_score_node(int rule, double k_for_alpha, int m, const double* x, const double* response,
+                           const int32_t* stratum, const double* risk_time, double* cut_value, double* delta,
+                           int32_t* n_cuts, int device) {
+  if (!x || !response || !stratum || !risk_time || !cut_value || !delta || !n_cuts) { set_error("null arguments"); return RFSLAM_EINVAL; }
+  return score_node_impl(rule, k_for_alpha, m, x, response, stratum, risk_time, cut_value, delta, n_cuts, device);
+}
+
+int rfslam_b200_bootstrap_counts(int seed, int ntree, int n, int tree, int32_t* counts, int device) {
+  if (!counts) { set_error("null arguments"); return RFSLAM_EINVAL; }
+  return bootstrap_counts_impl(seed, ntree, n, tree, counts, device);
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+// common.cuh -- shared device/host helpers for the B200-native rfSLAM hot path (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include <string>
+
+namespace rfslam {
+
+// ------------------------------------------------------------------------------------------
+// error plumbing: every CUDA failure becomes a non-zero C-ABI status with a message
+// ------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+struct CudaFail { int code; };
+
+#define RF_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      rfslam::set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), __FILE__, __LINE__, #call); \
+      throw rfslam::CudaFail{2};                                                                   \
+    }                                                                                              \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// constants of the path
+// ------------------------------------------------------------------------------------------
+constexpr int      kThreads     = 256;          // CTA size of the tree kernel
+constexpr int      kWarps       = kThreads / 32;
+constexpr int      kHistBins    = 256;          // covariates with <= 256 distinct values score by histogram
+constexpr int      kMaxCand     = 16;           // mtry limit of the joint histogram pass
+constexpr int      kMaxStrata   = 256;          // largest stratum id held in shared memory
+constexpr uint32_t kRowBits     = 26;           // in-bag entry = (multiplicity-1) << 26 | internal row
+constexpr uint32_t kRowMask     = (1u << kRowBits) - 1u;
+constexpr uint32_t kMaxMult     = 64;
+constexpr int      kStackCap    = 4096;         // pending right children per tree
+constexpr int      kRecChunk    = 1024;         // node records per pool chunk
+constexpr double   kEpsilon     = 1.0e-9;       // rf.h:169 EPSILON (absolute hysteresis of the tracker)
+
+// ------------------------------------------------------------------------------------------
+// ran1 chain replay (rf.c:5976-6117); state kept in one small struct so it can live in smem
+// ------------------------------------------------------------------------------------------
+struct Ran1 {
+  int iy;
+  int idum;
+  int iv[32];
+};
+
+__host__ __device__ inline int ran1_step(int v) {
+  // Schrage's factorisation of v * 16807 mod (2^31 - 1)
+  int k = v / 127773;
+  v = 16807 * (v - k * 127773) - 2836 * k;
+  if (v < 0) v += 2147483647;
+  return v;
+}
+
+__host__ __device__ inline void ran1_seed(Ran1& s, int seed) {
+  s.iy = 0;
+  s.idum = seed;
+}
+
+__host__ __device__ inline float ran1_next(Ran1& s) {
+  if (s.idum <= 0 || s.iy == 0) {
+    s.idum = (-(s.idum) < 1) ? 1 : -(s.idum);
+    for (int j = 39; j >= 0; j--) {
+      s.idum = ran1_step(s.idum);
+      if (j < 32) s.iv[j] = s.idum;
+    }
+    s.iy = s.iv[1];                       // the reference's generic variant reads slot 1 (rf.c:6095)
+  }
+  s.idum = ran1_step(s.idum);
+  int j = s.iy / 67108864;                // NDIV = 1 + (IM - 1) / 32 = 2^26
+  s.iy = s.iv[j];
+  s.iv[j] = s.idum;
+  float t = (float)((1.0 / 2147483647.0) * (double)s.iy);
+  const double rnmx = 1.0 - 1.2e-7;
+  if ((double)t > rnmx) return (float)rnmx;
+  return t;
+}
+
+// draw k in [1, size]: (uint) ceil(ran1 * (size * 1.0))  (rf.c:531, rf.c:8380)
+__host__ __device__ inline uint32_t ran1_index(Ran1& s, uint32_t size) {
+  return (uint32_t)ceil((double)ran1_next(s) * ((double)size * 1.0));
+}
+
+inline unsigned lcg_next(unsigned s) { return (1366u * s + 150889u) % 714025u; }
+
+// ------------------------------------------------------------------------------------------
+// the six Poisson rules (sc.c:639-1687) as one per-(side, stratum) term
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline bool rule_is_bayes(int rule)      { return rule <= 3; }
+__host__ __device__ inline bool rule_is_stratified(int rule) { return rule == 1 || rule == 3 || rule == 4 || rule == 6; }
+__host__ __device__ inline bool rule_unit_time(int rule)     { return rule == 3 || rule == 6; }
+
+// E, N: event / row counts; T: exposure; W: sum of event * exposure.  Zero-event cells contribute
+// exactly 0 under every rule (Bayes: 0 * log(.), sc.c:761; raw: mu = 0 is skipped, sc.c:1282).
+__host__ __device__ inline double side_term(bool bayes, double E, double N, double T, double W, double alpha, double beta) {
+  if (E == 0.0) return 0.0;
+  if (bayes) {
+    double lam = (E + alpha) / (beta + T);
+    return E * log(lam);
+  }
+  if (T == 0.0) return 0.0;
+  double mu = W / T;
+  if (mu == 0.0) return 0.0;
+  return (E * log(mu)) - (N * mu);
+}
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------
+// warp / block primitives
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_incl_scan(T v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    T u = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += u;
+  }
+  return v;
+}
+
+// block-wide sum; every thread gets the result.  `scratch` holds kWarps elements of T in smem.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane_id() == 0) scratch[warp_id()] = v;
+  __syncthreads();
+  T r = scratch[0];
+#pragma unroll
+  for (int w = 1; w < kWarps; w++) r += scratch[w];
+  return r;
+}
+
+// block-wide inclusive scan (kThreads elements, one per thread); returns the inclusive prefix and
+// the block total through `total`.  `scratch` holds kWarps elements.
+template <typename T>
+__device__ __forceinline__ T block_incl_scan(T v, T* scratch, T& total) {
+  T inc = warp_incl_scan(v);
+  __syncthreads();
+  if (lane_id() == 31) scratch[warp_id()] = inc;
+  __syncthreads();
+  T off = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; w++) {
+    T s = scratch[w];
+    if (w < warp_id()) off += s;
+    tot += s;
+  }
+  total = tot;
+  return inc + off;
+}
+
+__device__ __forceinline__ uint32_t load_code(const void* p, int width, uint32_t row) {
+  if (width == 1) return ((const uint8_t*)p)[row];
+  if (width == 2) return ((const uint16_t*)p)[row];
+  return ((const uint32_t*)p)[row];
+}
+#endif  // __CUDACC__
+
+}  // namespace rfslam

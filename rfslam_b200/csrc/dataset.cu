@@ -1,0 +1,260 @@
+// dataset.cu -- upload the CPIU table once and lay it out in HBM for the tree kernels.
+//
+// What the reference does per NODE and per CANDIDATE (gather the column, indexx() argsort, dedupe
+// into splitVector: rf.c:14946-14996) is hoisted here to once per DATASET: every covariate column
+// is rank-coded (code = index of the value among the column's sorted distinct values).  Cut values
+// returned by the path are looked up in uniq[], so contPT is still the exact data value
+// (rf.c:15539).  CUB's radix sort is used for this one-off preparation step only; nothing in the
+// per-tree hot path calls a library.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstring>
+
+#include "internal.h"
+
+namespace rfslam {
+
+namespace {
+
+__global__ void iota_kernel(uint32_t* v, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = (uint32_t)i;
+}
+
+__global__ void strat_keys_kernel(const int32_t* strat, uint32_t* keys, int n, int* bad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    int s = strat[i];
+    if (s < 1) atomicExch(bad, 1);
+    keys[i] = (uint32_t)s;
+  }
+}
+
+__global__ void invert_kernel(const uint32_t* perm, uint32_t* inv, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) inv[perm[i]] = (uint32_t)i;
+}
+
+// sb[k] = first internal row whose stratum is >= k  (k = 0..K+1)
+__global__ void strat_bounds_kernel(const uint32_t* sorted_strat, int n, int K, uint32_t* sb) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > K + 1) return;
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (sorted_strat[mid] < (uint32_t)k) lo = mid + 1; else hi = mid;
+  }
+  sb[k] = (uint32_t)lo;
+}
+
+__global__ void row_arrays_kernel(const uint32_t* perm, const double* y, const double* rt_in, const uint32_t* sorted_strat,
+                                  uint8_t* ev, double* rt, uint16_t* strat, int n, int* bad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    uint32_t r = perm[i];
+    double yy = y[r];
+    if (!(yy == 1.0 || yy == 2.0)) atomicExch(bad, 2);       // sc.c:676-687: the plugin exits on other codes
+    ev[i] = (yy == 2.0) ? 1 : 0;
+    double t = rt_in[r];
+    if (!(t == t)) atomicExch(bad, 3);
+    rt[i] = t;
+    strat[i] = (uint16_t)sorted_strat[i];
+  }
+}
+
+// keys = x + 0.0 (folds -0.0 onto +0.0: the reference compares doubles, rf.c:14992), NaN flagged
+__global__ void column_keys_kernel(const double* x, double* keys, int n, int* bad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    double v = x[i];
+    if (!(v == v)) atomicExch(bad, 4);
+    keys[i] = v + 0.0;
+  }
+}
+
+__global__ void diff_flags_kernel(const double* sorted, uint32_t* flag, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (i > 0 && sorted[i] != sorted[i - 1]) ? 1u : 0u;
+}
+
+template <typename CodeT>
+__global__ void scatter_codes_kernel(const double* sorted, const uint32_t* sorted_row, const uint32_t* rank,
+                                     const uint32_t* inv, CodeT* codes, double* uniq, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    uint32_t r = rank[i];
+    codes[inv[sorted_row[i]]] = (CodeT)r;
+    if (i == 0 || sorted[i] != sorted[i - 1]) uniq[r] = sorted[i];
+  }
+}
+
+template <typename T>
+T* dalloc(rfslam_dataset* ds, size_t count, bool resident = true) {
+  void* p = nullptr;
+  RF_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+  ds->allocs.push_back(p);
+  if (resident) ds->bytes += (int64_t)(count * sizeof(T));
+  return (T*)p;
+}
+
+}  // namespace
+
+void dataset_free(rfslam_dataset* ds) {
+  if (!ds) return;
+  cudaSetDevice(ds->device);
+  for (void* p : ds->allocs) cudaFree(p);
+  delete ds;
+}
+
+int dataset_build(const rfslam_grow_args* a, rfslam_dataset** out) {
+  *out = nullptr;
+  const int n = a->observation_size, p = a->x_size;
+  if (n < 2 || p < 1) { set_error("observationSize must be >= 2 and xSize >= 1"); return RFSLAM_EINVAL; }
+  if ((uint64_t)n > (uint64_t)kRowMask) {
+    set_error("observationSize %d exceeds the %u rows an in-bag entry can address", n, kRowMask);
+    return RFSLAM_ENOSUP;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: librfslam_b200 has no CPU fallback");
+    return RFSLAM_ENODEV;
+  }
+  rfslam_dataset* ds = new rfslam_dataset();
+  try {
+    if (a->device >= 0) RF_CUDA(cudaSetDevice(a->device));
+    RF_CUDA(cudaGetDevice(&ds->device));
+    ds->n = n; ds->p = p;
+    const int T = 256, G = (n + T - 1) / T;
+
+    int* d_bad = nullptr;
+    RF_CUDA(cudaMalloc(&d_bad, sizeof(int)));
+    RF_CUDA(cudaMemset(d_bad, 0, sizeof(int)));
+
+    // ---- transient buffers -------------------------------------------------------------
+    int32_t* d_strat_in; double *d_col, *d_keys, *d_keys_sorted, *d_y, *d_rt_in;
+    uint32_t *d_iota, *d_rows_sorted, *d_u32a, *d_u32b;
+    RF_CUDA(cudaMalloc(&d_strat_in, (size_t)n * 4));
+    RF_CUDA(cudaMalloc(&d_col, (size_t)n * 8));
+    RF_CUDA(cudaMalloc(&d_keys, (size_t)n * 8));
+    RF_CUDA(cudaMalloc(&d_keys_sorted, (size_t)n * 8));
+    RF_CUDA(cudaMalloc(&d_y, (size_t)n * 8));
+    RF_CUDA(cudaMalloc(&d_rt_in, (size_t)n * 8));
+    RF_CUDA(cudaMalloc(&d_iota, (size_t)n * 4));
+    RF_CUDA(cudaMalloc(&d_rows_sorted, (size_t)n * 4));
+    RF_CUDA(cudaMalloc(&d_u32a, (size_t)n * 4));
+    RF_CUDA(cudaMalloc(&d_u32b, (size_t)n * 4));
+    std::vector<void*> transient = {d_strat_in, d_col, d_keys, d_keys_sorted, d_y, d_rt_in, d_iota, d_rows_sorted, d_u32a, d_u32b, d_bad};
+    auto free_transient = [&]() { for (void* q : transient) cudaFree(q); transient.clear(); };
+
+    size_t tmp_bytes = 0, tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, n);
+    tmp_bytes = std::max(tmp_bytes, tb);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, (const double*)nullptr, (double*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, n);
+    tmp_bytes = std::max(tmp_bytes, tb);
+    cub::DeviceScan::InclusiveSum(nullptr, tb, (const uint32_t*)nullptr, (uint32_t*)nullptr, n);
+    tmp_bytes = std::max(tmp_bytes, tb);
+    void* d_tmp = nullptr;
+    RF_CUDA(cudaMalloc(&d_tmp, tmp_bytes));
+    transient.push_back(d_tmp);
+
+    try {
+      // ---- internal row order: stable sort by stratum ------------------------------------
+      RF_CUDA(cudaMemcpy(d_strat_in, a->stratifier, (size_t)n * 4, cudaMemcpyHostToDevice));
+      RF_CUDA(cudaMemcpy(d_y, a->r_data, (size_t)n * 8, cudaMemcpyHostToDevice));
+      RF_CUDA(cudaMemcpy(d_rt_in, a->risk_time, (size_t)n * 8, cudaMemcpyHostToDevice));
+      iota_kernel<<<G, T>>>(d_iota, n);
+      strat_keys_kernel<<<G, T>>>(d_strat_in, d_u32a, n, d_bad);
+      uint32_t* perm = dalloc<uint32_t>(ds, n);
+      uint32_t* inv = dalloc<uint32_t>(ds, n);
+      tb = tmp_bytes;
+      RF_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_u32a, d_u32b, d_iota, perm, n));   // stable
+      invert_kernel<<<G, T>>>(perm, inv, n);
+      uint32_t maxs = 0;
+      RF_CUDA(cudaMemcpy(&maxs, d_u32b + (n - 1), 4, cudaMemcpyDeviceToHost));
+      int bad = 0;
+      RF_CUDA(cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost));
+      if (bad == 1) { set_error("stratifier must be >= 1"); throw CudaFail{RFSLAM_EINVAL}; }
+      if (maxs > (uint32_t)kMaxStrata) {
+        set_error("largest stratum %u exceeds the %d strata the device path holds in shared memory", maxs, kMaxStrata);
+        throw CudaFail{RFSLAM_ENOSUP};
+      }
+      ds->K = (int)maxs;
+      uint32_t* sb = dalloc<uint32_t>(ds, ds->K + 2);
+      strat_bounds_kernel<<<(ds->K + 2 + 63) / 64, 64>>>(d_u32b, n, ds->K, sb);
+      uint8_t* ev = dalloc<uint8_t>(ds, n);
+      double* rt = dalloc<double>(ds, n);
+      uint16_t* strat = dalloc<uint16_t>(ds, n);
+      row_arrays_kernel<<<G, T>>>(perm, d_y, d_rt_in, d_u32b, ev, rt, strat, n, d_bad);
+
+      // ---- rank-code every covariate column ----------------------------------------------
+      ds->D.resize(p); ds->width.resize(p); ds->codes_h.resize(p); ds->uniq_h.resize(p);
+      for (int c = 0; c < p; c++) {
+        if (a->x_type && !(a->x_type[c] == 'R' || a->x_type[c] == 'I' || a->x_type[c] == 'B')) {
+          set_error("covariate %d has type '%c': unordered-factor (MWCP) splits are outside the accelerated path", c + 1, a->x_type[c]);
+          throw CudaFail{RFSLAM_ENOSUP};
+        }
+        RF_CUDA(cudaMemcpy(d_col, a->x_data + (size_t)c * n, (size_t)n * 8, cudaMemcpyHostToDevice));
+        column_keys_kernel<<<G, T>>>(d_col, d_keys, n, d_bad);
+        tb = tmp_bytes;
+        RF_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_keys, d_keys_sorted, d_iota, d_rows_sorted, n));
+        diff_flags_kernel<<<G, T>>>(d_keys_sorted, d_u32a, n);
+        tb = tmp_bytes;
+        RF_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tb, d_u32a, d_u32b, n));
+        uint32_t last = 0;
+        RF_CUDA(cudaMemcpy(&last, d_u32b + (n - 1), 4, cudaMemcpyDeviceToHost));
+        int D = (int)last + 1;
+        ds->D[c] = D;
+        ds->max_D = std::max(ds->max_D, D);
+        double* uniq = dalloc<double>(ds, D);
+        ds->uniq_h[c] = uniq;
+        if (D <= 256) {
+          ds->width[c] = 1;
+          uint8_t* codes = dalloc<uint8_t>(ds, n);
+          ds->codes_h[c] = codes;
+          scatter_codes_kernel<uint8_t><<<G, T>>>(d_keys_sorted, d_rows_sorted, d_u32b, inv, codes, uniq, n);
+        } else if (D <= 65536) {
+          ds->width[c] = 2;
+          uint16_t* codes = dalloc<uint16_t>(ds, n);
+          ds->codes_h[c] = codes;
+          scatter_codes_kernel<uint16_t><<<G, T>>>(d_keys_sorted, d_rows_sorted, d_u32b, inv, codes, uniq, n);
+        } else {
+          ds->width[c] = 4;
+          uint32_t* codes = dalloc<uint32_t>(ds, n);
+          ds->codes_h[c] = codes;
+          scatter_codes_kernel<uint32_t><<<G, T>>>(d_keys_sorted, d_rows_sorted, d_u32b, inv, codes, uniq, n);
+        }
+      }
+      RF_CUDA(cudaDeviceSynchronize());
+      RF_CUDA(cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost));
+      if (bad == 2) { set_error("response codes must be 1.0 or 2.0 (two-class CPIU outcome, splitCustom.c:676-687)"); throw CudaFail{RFSLAM_EINVAL}; }
+      if (bad == 3 || bad == 4) { set_error("missing values (NA/NaN) are outside the accelerated path"); throw CudaFail{RFSLAM_ENOSUP}; }
+
+      // ---- device-side tables of per-column pointers --------------------------------------
+      const void** d_codes = (const void**)dalloc<void*>(ds, p);
+      const double** d_uniq = (const double**)dalloc<double*>(ds, p);
+      uint8_t* d_width = dalloc<uint8_t>(ds, p);
+      int* d_D = dalloc<int>(ds, p);
+      RF_CUDA(cudaMemcpy(d_codes, ds->codes_h.data(), (size_t)p * sizeof(void*), cudaMemcpyHostToDevice));
+      RF_CUDA(cudaMemcpy(d_uniq, ds->uniq_h.data(), (size_t)p * sizeof(double*), cudaMemcpyHostToDevice));
+      RF_CUDA(cudaMemcpy(d_width, ds->width.data(), (size_t)p, cudaMemcpyHostToDevice));
+      RF_CUDA(cudaMemcpy(d_D, ds->D.data(), (size_t)p * sizeof(int), cudaMemcpyHostToDevice));
+
+      DevData& d = ds->dev;
+      d.n = n; d.p = p; d.K = ds->K;
+      d.perm = perm; d.inv = inv; d.sb = sb; d.ev = ev; d.rt = rt; d.strat = strat;
+      d.codes = (const void* const*)d_codes; d.width = d_width; d.D = d_D; d.uniq = (const double* const*)d_uniq;
+    } catch (...) {
+      free_transient();
+      throw;
+    }
+    free_transient();
+  } catch (CudaFail f) {
+    dataset_free(ds);
+    return f.code;
+  }
+  *out = ds;
+  return RFSLAM_OK;
+}
+
+}  // namespace rfslam

@@ -1,0 +1,536 @@
+// grow.cu -- host orchestration of forest growth plus the supporting kernels either side of the
+// tree kernel: chain-A bootstrap replay (K1), record compaction, and the row-parallel traversal
+// that yields node membership, all-row leaf counts and the OOB / full ensembles (K4/K5).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "grow_kernel.cuh"
+#include "internal.h"
+
+namespace rfslam {
+
+void chain_seeds(int seed, int ntree, std::vector<int>& seedA, std::vector<int>& seedB) {
+  // rf.c:6666-6692: one LCG (modulus 714025) stepped twice per tree, first for all chain-A seeds,
+  // then for all chain-B seeds (chain C, the vimp chain, is not on this path)
+  unsigned s = (unsigned)std::abs(seed);
+  if (s >= 714025u) s %= 714025u;
+  seedA.resize(ntree); seedB.resize(ntree);
+  for (int pass = 0; pass < 2; pass++)
+    for (int b = 0; b < ntree; b++) {
+      s = lcg_next(s); s = lcg_next(s);
+      while (s == 0) s = lcg_next(s);
+      (pass == 0 ? seedA : seedB)[b] = -(int)s;
+    }
+}
+
+namespace {
+
+// K1a: chain-A replay, one warp per tree with lane 0 walking the (inherently sequential)
+// Bays-Durham shuffle; trees run concurrently on different SMs.  draws are 0-based original rows.
+__global__ void bootstrap_draw_kernel(const int* seedA, const int* bootSize, uint32_t* draws, size_t stride, int n) {
+  __shared__ Ran1 rng;
+  const int t = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  ran1_seed(rng, seedA[t]);
+  uint32_t* out = draws + (size_t)t * stride;
+  const int bs = bootSize[t];
+  for (int i = 0; i < bs; i++) out[i] = ran1_index(rng, (uint32_t)n) - 1u;     // rf.c:531
+}
+
+// K1b: in-bag multiplicity per INTERNAL row (u16 packed two per word, native 32-bit atomics)
+__global__ void bag_count_kernel(const uint32_t* draws, size_t dstride, const int* bootSize, const uint32_t* inv,
+                                 uint32_t* cnt32, size_t cstride32) {
+  const int t = blockIdx.y;
+  const int bs = bootSize[t];
+  const uint32_t* dr = draws + (size_t)t * dstride;
+  uint32_t* c = cnt32 + (size_t)t * cstride32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < bs; i += gridDim.x * blockDim.x) {
+    uint32_t ii = inv[dr[i]];
+    atomicAdd(&c[ii >> 1], 1u << (16u * (ii & 1u)));
+  }
+}
+
+// by.user bootstrap (rf.c:520-526): the caller supplies the in-bag counts per original row
+__global__ void user_count_kernel(const int32_t* samp, const uint32_t* perm, uint16_t* cnt, int n, int* bad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    int32_t v = samp[perm[i]];
+    if (v < 0 || v > 65535) { atomicExch(bad, 1); v = 0; }
+    cnt[i] = (uint16_t)v;
+  }
+}
+
+// compaction: pool chunks -> flat pre-order arrays at the tree's offset
+__global__ void compact_kernel(GrowWork w, DevData d, const int* treeIds, const unsigned long long* nodeOff,
+                               const unsigned long long* leafOff,
+                               int32_t* treeID, int32_t* nodeID, int32_t* parmID, double* contPT, double* splitStat,
+                               uint32_t* code, uint32_t* right, int32_t* tnRCNT, int32_t* tnCLAS) {
+  const int t = blockIdx.y;
+  const uint32_t cntN = w.nodeCount[t];
+  const unsigned long long off = nodeOff[t], loff = leafOff[t];
+  const double na = __longlong_as_double(0x7FF00000000007A2LL);     // R's NA_real_ (payload 1954)
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < cntN; q += gridDim.x * blockDim.x) {
+    uint32_t c = w.ctab[(size_t)t * w.maxChunksPerTree + q / kRecChunk];
+    size_t at = (size_t)c * kRecChunk + (q % kRecChunk);
+    Rec r = w.pool[at];
+    treeID[off + q] = treeIds[t];
+    nodeID[off + q] = (int32_t)r.nodeID;
+    parmID[off + q] = (int32_t)r.parm;
+    splitStat[off + q] = w.statPool[at];
+    if (r.parm) {
+      contPT[off + q] = d.uniq[r.parm - 1][r.a];
+      code[off + q] = r.a; right[off + q] = r.b;
+    } else {
+      contPT[off + q] = na;
+      code[off + q] = 0; right[off + q] = 0;
+      tnRCNT[loff + r.nodeID - 1] = (int32_t)r.b;
+      tnCLAS[2 * (loff + r.nodeID - 1)] = (int32_t)(r.b - r.a);
+      tnCLAS[2 * (loff + r.nodeID - 1) + 1] = (int32_t)r.a;
+    }
+  }
+}
+
+// K4/K5: one thread per internal row walks every tree of the batch (rf.c:10610 routing on codes:
+// LEFT iff code <= cut code  <=>  cut - x >= 0), accumulating the class proportions of the leaf
+// (rf.c:928-962) into the full ensemble and, when the row is out of bag, the OOB ensemble.
+__global__ void membership_kernel(DevData d, int ntrees, const unsigned long long* nodeOff, const unsigned long long* leafOff,
+                                  const int32_t* nodeID, const int32_t* parmID, const uint32_t* code, const uint32_t* right,
+                                  const int32_t* tnRCNT, const int32_t* tnCLAS, const uint16_t* cnt,
+                                  int32_t* tnACNT, double* allNum, double* oobNum, uint32_t* allDen, uint32_t* oobDen,
+                                  int32_t* nodeMembership, int32_t* bootMembership, int batchFirst, size_t cntStride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.n) return;
+  const uint32_t orig = d.perm[i];
+  double a1 = 0.0, a2 = 0.0, o1 = 0.0, o2 = 0.0; uint32_t od = 0;
+  for (int t = 0; t < ntrees; t++) {
+    const unsigned long long off = nodeOff[t];
+    unsigned long long q = off;
+    int pm;
+    while ((pm = parmID[q]) != 0) {
+      uint32_t cd = load_code(d.codes[pm - 1], d.width[pm - 1], (uint32_t)i);
+      q = (cd <= code[q]) ? q + 1 : off + right[q];
+    }
+    const int leaf = nodeID[q];
+    const unsigned long long li = leafOff[t] + (unsigned long long)leaf - 1ull;
+    const double rc = (double)tnRCNT[li];
+    const double p1 = (double)tnCLAS[2 * li] / rc, p2 = (double)tnCLAS[2 * li + 1] / rc;
+    a1 += p1; a2 += p2;
+    const uint16_t c = cnt[(size_t)t * cntStride + i];
+    if (c == 0) { o1 += p1; o2 += p2; od++; }
+    atomicAdd(&tnACNT[li], 1);
+    if (nodeMembership) nodeMembership[(size_t)(batchFirst + t) * d.n + orig] = leaf;
+    if (bootMembership) bootMembership[(size_t)(batchFirst + t) * d.n + orig] = (int32_t)c;
+  }
+  allNum[orig] += a1; allNum[(size_t)d.n + orig] += a2; allDen[orig] += (uint32_t)ntrees;
+  oobNum[orig] += o1; oobNum[(size_t)d.n + orig] += o2; oobDen[orig] += od;
+}
+
+__global__ void finalize_kernel(double* num, const uint32_t* den, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    uint32_t dd = den[i];
+    if (dd) { num[i] /= (double)dd; num[(size_t)n + i] /= (double)dd; }     // rf.c:8115-8121
+  }
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t count = 0;
+  void alloc(size_t c) {
+    count = c;
+    RF_CUDA(cudaMalloc((void**)&p, std::max<size_t>(c, 1) * sizeof(T)));
+  }
+  void zero() { RF_CUDA(cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T))); }
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+
+template <typename T>
+T* host_copy(const T* dev, size_t count) {
+  T* h = (T*)malloc(std::max<size_t>(count, 1) * sizeof(T));
+  if (!h) { set_error("out of host memory"); throw CudaFail{RFSLAM_ENOMEM}; }
+  if (count) RF_CUDA(cudaMemcpy(h, dev, count * sizeof(T), cudaMemcpyDeviceToHost));
+  return h;
+}
+
+}  // namespace
+
+int validate_grow_args(const rfslam_grow_args* a, GrowConfig* cfg) {
+  if (!a) { set_error("null arguments"); return RFSLAM_EINVAL; }
+  if (a->seed >= 0) { set_error("Random seed must be less than zero (rf.c:6454)"); return RFSLAM_EINVAL; }
+  if (a->ntree < 1) { set_error("ntree must be >= 1"); return RFSLAM_EINVAL; }
+  if (a->y_size != 1) { set_error("the Poisson class path takes exactly one response (ySize = %d)", a->y_size); return RFSLAM_ENOSUP; }
+  if (a->r_type && !(a->r_type[0] == 'C' || a->r_type[0] == 'I' || a->r_type[0] == 'B')) {
+    set_error("response must be a factor (rType '%c'); the regression slots of the custom rules abort in the reference too (sc.c:785-805)", a->r_type[0]);
+    return RFSLAM_ENOSUP;
+  }
+  if (a->split_rule != 16) { set_error("splitRule %d is not the custom rule (16): no device implementation", a->split_rule); return RFSLAM_ENOSUP; }
+  int slot = (int)((a->opt_high & RFSLAM_OPTH_SPLT_CUST) >> 8) + 1;
+  int rule = rfslam_b200_rule_of_slot(RFSLAM_CLAS_FAM, slot);
+  if (rule < 1) { set_error("custom split slot %d has no device rule (only the six Poisson rules are accelerated; no CPU fallback)", slot); return RFSLAM_ENOSUP; }
+  if (a->nsplit != 0) { set_error("nsplit = %d: random cutpoint subsets are outside the accelerated path (SURVEY 8f-2)", a->nsplit); return RFSLAM_ENOSUP; }
+  if (a->htry != 0) { set_error("htry must be 0 (rf.c:6490-6494)"); return RFSLAM_EINVAL; }
+  if (a->mtry < 1 || a->mtry > a->x_size) { set_error("mtry must be in [1, xSize]"); return RFSLAM_EINVAL; }
+  if (a->mtry > kMaxCand) { set_error("mtry %d exceeds the %d candidates scored jointly per node", a->mtry, kMaxCand); return RFSLAM_ENOSUP; }
+  if (a->x_size > 1024) { set_error("xSize %d exceeds 1024 covariates", a->x_size); return RFSLAM_ENOSUP; }
+  if (a->node_size < 1) { set_error("nodeSize must be >= 1"); return RFSLAM_EINVAL; }
+  if (a->n_impute > 1) { set_error("multiple imputation is outside the accelerated path"); return RFSLAM_ENOSUP; }
+  if (a->n_categories > 1 || (a->n_categories == 1 && a->category_weights && a->category_weights[0] != 1.0)) {
+    set_error("variable categories: only the default single category of weight 1 is accelerated"); return RFSLAM_ENOSUP;
+  }
+  if (a->n_to_fix > 0) { set_error("fixed_during_bootstrap covariates are outside the accelerated path"); return RFSLAM_ENOSUP; }
+  if (a->opt_high & 0x1000u) { set_error("sampling without replacement is outside the accelerated path"); return RFSLAM_ENOSUP; }
+  bool t1 = (a->opt_low & RFSLAM_OPT_BOOT_TYP1) != 0, t2 = (a->opt_low & RFSLAM_OPT_BOOT_TYP2) != 0;
+  if (t1 != t2) { set_error("bootstrap must be by.root or by.user"); return RFSLAM_ENOSUP; }
+  if (a->case_weight) {
+    for (int i = 1; i < a->observation_size; i++)
+      if (a->case_weight[i] != a->case_weight[0]) { set_error("non-uniform case weights are outside the accelerated path"); return RFSLAM_ENOSUP; }
+  }
+  if (a->x_weight) {
+    for (int i = 1; i < a->x_size; i++)
+      if (a->x_weight[i] != a->x_weight[0]) { set_error("non-uniform covariate weights are outside the accelerated path"); return RFSLAM_ENOSUP; }
+  }
+  if (!(a->k_for_alpha > 0.0)) { set_error("k_for_alpha must be > 0"); return RFSLAM_EINVAL; }
+  if (!a->r_data || !a->x_data || !a->risk_time || !a->stratifier) { set_error("null data pointer"); return RFSLAM_EINVAL; }
+  cfg->rule = rule; cfg->mtry = a->mtry; cfg->nodesize = a->node_size; cfg->nodedepth = a->node_depth;
+  cfg->alpha = 1.0 / (a->k_for_alpha * a->k_for_alpha);
+  cfg->ntree = a->ntree; cfg->seed = a->seed; cfg->by_user = t1 && t2;
+  cfg->want_membership = (a->opt_high & RFSLAM_OPTH_MEMB_USER) != 0;
+  cfg->want_membr_lists = false;
+  cfg->finalize = a->finalize_ensembles != 0;
+  if (cfg->by_user && !a->bootstrap) { set_error("bootstrap = by.user needs the samp matrix"); return RFSLAM_EINVAL; }
+  return RFSLAM_OK;
+}
+
+int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out* out) {
+  memset(out, 0, sizeof(*out));
+  GrowConfig cfg;
+  int rc = validate_grow_args(a, &cfg);
+  if (rc) return rc;
+  if (a->observation_size != ds->n || a->x_size != ds->p) { set_error("arguments do not match the resident dataset"); return RFSLAM_EINVAL; }
+  const int n = ds->n, p = ds->p;
+  try {
+    RF_CUDA(cudaSetDevice(ds->device));
+    // ---- which trees does this process grow? (tree b -> rank (b-1) mod G) ----
+    std::vector<int> ids;
+    int first = a->tree_first > 0 ? a->tree_first : 1, step = a->tree_step > 0 ? a->tree_step : 1;
+    for (int b = first; b <= cfg.ntree; b += step) ids.push_back(b);
+    const int T = (int)ids.size();
+    std::vector<int> seedA, seedB;
+    chain_seeds(cfg.seed, cfg.ntree, seedA, seedB);
+    std::vector<int> bootSize(T);
+    int maxBoot = 1;
+    for (int t = 0; t < T; t++) {
+      if (cfg.by_user) {
+        long sum = 0;
+        const int32_t* sp = a->bootstrap + (size_t)(ids[t] - 1) * n;
+        for (int i = 0; i < n; i++) sum += sp[i];
+        bootSize[t] = (int)sum;
+      } else {
+        bootSize[t] = a->bootstrap_size ? a->bootstrap_size[ids[t] - 1] : n;
+      }
+      if (bootSize[t] < 1) { set_error("empty bootstrap sample for tree %d", ids[t]); return RFSLAM_EINVAL; }
+      maxBoot = std::max(maxBoot, bootSize[t]);
+    }
+
+    // ---- kernel parameters ----
+    GrowParams g{};
+    g.rule = cfg.rule; g.mtry = cfg.mtry; g.nodesize = cfg.nodesize; g.nodedepth = cfg.nodedepth; g.alpha = cfg.alpha;
+    g.pw = (p + 31) / 32; g.ncmax = std::min(cfg.mtry, kMaxCand);
+    g.has_sort = ds->max_D > kHistBins;
+    DevBuf<double> d_sw;
+    if (a->x_split_stat_weight) {
+      bool allOne = true;
+      for (int i = 0; i < p; i++) if (a->x_split_stat_weight[i] != 1.0) allOne = false;
+      if (!allOne) {
+        d_sw.alloc(p);
+        RF_CUDA(cudaMemcpy(d_sw.p, a->x_split_stat_weight, (size_t)p * 8, cudaMemcpyHostToDevice));
+        g.split_weight = d_sw.p;
+      }
+    }
+    const size_t smem = grow_smem_bytes(g.ncmax, ds->K);
+    RF_CUDA(cudaFuncSetAttribute(rfslam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    // ---- batch size from free memory ----
+    size_t freeB = 0, totalB = 0;
+    RF_CUDA(cudaMemGetInfo(&freeB, &totalB));
+    const size_t perTree = (size_t)n * (8 + 2 + (g.has_sort ? 16 : 0)) + (cfg.by_user ? 0 : (size_t)maxBoot * 4)
+                         + (size_t)kStackCap * (sizeof(NodeEnt) + (size_t)g.pw * 4) + 4096;
+    const size_t worstNodes = 2ull * (size_t)std::min(n, maxBoot) + 1;
+    size_t estNodes = std::min<size_t>(worstNodes, 4ull * (size_t)maxBoot / (size_t)std::max(1, cfg.nodesize) + 256);
+    size_t budget = (size_t)(0.80 * (double)freeB);
+    size_t fixed = (size_t)n * (16 + 16 + 8) + (64u << 20);
+    int B = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, (budget > fixed ? budget - fixed : 0) / (perTree + estNodes * 48)));
+    if (const char* e = getenv("RFSLAM_TREES_PER_BATCH")) { int v = atoi(e); if (v > 0) B = std::min(T, v); }
+
+    // ---- persistent accumulators ----
+    DevBuf<double> d_allNum, d_oobNum; DevBuf<uint32_t> d_allDen, d_oobDen;
+    d_allNum.alloc(2 * (size_t)n); d_oobNum.alloc(2 * (size_t)n); d_allDen.alloc(n); d_oobDen.alloc(n);
+    d_allNum.zero(); d_oobNum.zero(); d_allDen.zero(); d_oobDen.zero();
+    DevBuf<int32_t> d_nodeMemb, d_bootMemb;
+    if (cfg.want_membership) { d_nodeMemb.alloc((size_t)T * n); d_bootMemb.alloc((size_t)T * n); }
+
+    std::vector<int32_t> h_treeID, h_nodeID, h_parmID, h_leafCount(T), h_seed(T), h_tnRCNT, h_tnACNT, h_tnCLAS;
+    std::vector<double> h_contPT, h_stat;
+    long long totalCand = 0, totalAlgo = 0;
+    float growMs = 0.f, totalMs = 0.f;
+    cudaEvent_t ev0, ev1, ev2, ev3;
+    RF_CUDA(cudaEventCreate(&ev0)); RF_CUDA(cudaEventCreate(&ev1)); RF_CUDA(cudaEventCreate(&ev2)); RF_CUDA(cudaEventCreate(&ev3));
+
+    // ---- per-batch buffers ----
+    DevBuf<uint32_t> d_lists, d_sort, d_draws, d_stackPerm, d_ctab, d_nodeCount, d_leafCount, d_cursor;
+    DevBuf<uint16_t> d_cnt; DevBuf<NodeEnt> d_stack; DevBuf<int> d_seedA, d_seedB, d_boot, d_ids, d_status;
+    DevBuf<unsigned long long> d_cand, d_algo, d_nodeOff, d_leafOff;
+    DevBuf<int32_t> d_samp;
+    const size_t cntStride = ((size_t)n + 1) & ~(size_t)1;         // u16 count rows stay 4-byte aligned
+    d_lists.alloc((size_t)B * 2 * n);
+    if (g.has_sort) d_sort.alloc((size_t)B * 4 * n);
+    if (!cfg.by_user) d_draws.alloc((size_t)B * maxBoot); else d_samp.alloc(n);
+    d_cnt.alloc((size_t)B * cntStride);
+    d_stack.alloc((size_t)B * kStackCap); d_stackPerm.alloc((size_t)B * kStackCap * g.pw);
+    d_nodeCount.alloc(B); d_leafCount.alloc(B); d_cursor.alloc(1); d_status.alloc(1);
+    d_seedA.alloc(B); d_seedB.alloc(B); d_boot.alloc(B); d_ids.alloc(B);
+    d_cand.alloc(B); d_algo.alloc(B); d_nodeOff.alloc(B + 1); d_leafOff.alloc(B + 1);
+    const uint32_t maxChunksPerTree = (uint32_t)((worstNodes + kRecChunk - 1) / kRecChunk) + 1;
+    d_ctab.alloc((size_t)B * maxChunksPerTree);
+
+    for (int b0 = 0; b0 < T; b0 += B) {
+      const int nb = std::min(B, T - b0);
+      std::vector<int> hsA(nb), hsB(nb), hbs(nb), hid(nb);
+      for (int t = 0; t < nb; t++) { hsA[t] = seedA[ids[b0 + t] - 1]; hsB[t] = seedB[ids[b0 + t] - 1]; hbs[t] = bootSize[b0 + t]; hid[t] = ids[b0 + t]; h_seed[b0 + t] = hsA[t]; }
+      RF_CUDA(cudaMemcpy(d_seedA.p, hsA.data(), nb * 4, cudaMemcpyHostToDevice));
+      RF_CUDA(cudaMemcpy(d_seedB.p, hsB.data(), nb * 4, cudaMemcpyHostToDevice));
+      RF_CUDA(cudaMemcpy(d_boot.p, hbs.data(), nb * 4, cudaMemcpyHostToDevice));
+      RF_CUDA(cudaMemcpy(d_ids.p, hid.data(), nb * 4, cudaMemcpyHostToDevice));
+
+      size_t poolChunks = std::max<size_t>((size_t)nb * 2, (estNodes * nb + kRecChunk - 1) / kRecChunk + nb);
+      for (int attempt = 0;; attempt++) {
+        DevBuf<Rec> d_pool; DevBuf<double> d_statPool;
+        d_pool.alloc(poolChunks * kRecChunk); d_statPool.alloc(poolChunks * kRecChunk);
+        RF_CUDA(cudaEventRecord(ev0));
+        // K1: bootstrap
+        d_cnt.zero();
+        if (cfg.by_user) {
+          int* d_bad = d_status.p;
+          RF_CUDA(cudaMemset(d_bad, 0, 4));
+          for (int t = 0; t < nb; t++) {
+            RF_CUDA(cudaMemcpy(d_samp.p, a->bootstrap + (size_t)(hid[t] - 1) * n, (size_t)n * 4, cudaMemcpyHostToDevice));
+            user_count_kernel<<<(n + 255) / 256, 256>>>(d_samp.p, ds->dev.perm, d_cnt.p + (size_t)t * cntStride, n, d_bad);
+          }
+          int bad = 0;
+          RF_CUDA(cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost));
+          if (bad) { set_error("by.user in-bag counts must be in [0, 65535]"); throw CudaFail{RFSLAM_EINVAL}; }
+        } else {
+          bootstrap_draw_kernel<<<nb, 32>>>(d_seedA.p, d_boot.p, d_draws.p, (size_t)maxBoot, n);
+          dim3 gc((unsigned)std::min<size_t>(((size_t)maxBoot + 255) / 256, 1024), (unsigned)nb);
+          bag_count_kernel<<<gc, 256>>>(d_draws.p, (size_t)maxBoot, d_boot.p, ds->dev.inv, (uint32_t*)d_cnt.p, cntStride / 2);
+        }
+        RF_CUDA(cudaGetLastError());
+        // K2: grow
+        RF_CUDA(cudaMemset(d_cursor.p, 0, 4)); RF_CUDA(cudaMemset(d_status.p, 0, 4));
+        GrowWork w{};
+        w.ntrees = nb; w.seedB = d_seedB.p; w.bootSize = d_boot.p; w.lists = d_lists.p; w.cnt = d_cnt.p; w.cntStride = cntStride;
+        w.sortbuf = g.has_sort ? d_sort.p : nullptr; w.stack = d_stack.p; w.stackPerm = d_stackPerm.p;
+        w.pool = d_pool.p; w.statPool = d_statPool.p; w.poolChunks = (uint32_t)poolChunks; w.poolCursor = d_cursor.p;
+        w.ctab = d_ctab.p; w.maxChunksPerTree = maxChunksPerTree; w.nodeCount = d_nodeCount.p; w.leafCount = d_leafCount.p;
+        w.candCount = d_cand.p; w.algoBytes = d_algo.p; w.status = d_status.p;
+        DevData dd = ds->dev;
+        RF_CUDA(cudaEventRecord(ev1));
+        rfslam_grow_kernel<<<nb, kThreads, smem>>>(dd, g, w);
+        RF_CUDA(cudaEventRecord(ev2));
+        RF_CUDA(cudaGetLastError());
+        int status = 0;
+        RF_CUDA(cudaMemcpy(&status, d_status.p, 4, cudaMemcpyDeviceToHost));
+        if (status == 1) {
+          if (attempt > 8) { set_error("record pool kept overflowing"); throw CudaFail{RFSLAM_ENOMEM}; }
+          poolChunks *= 2;
+          continue;                                            // deterministic: simply regrow the batch
+        }
+        if (status == 2) { set_error("tree deeper than %d pending nodes", kStackCap); throw CudaFail{RFSLAM_ENOSUP}; }
+
+        // ---- offsets, compaction, traversal ----
+        std::vector<uint32_t> hNodes(nb), hLeaves(nb);
+        std::vector<unsigned long long> hCand(nb), hAlgo(nb), nodeOff(nb + 1, 0), leafOff(nb + 1, 0);
+        RF_CUDA(cudaMemcpy(hNodes.data(), d_nodeCount.p, nb * 4, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(hLeaves.data(), d_leafCount.p, nb * 4, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(hCand.data(), d_cand.p, nb * 8, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(hAlgo.data(), d_algo.p, nb * 8, cudaMemcpyDeviceToHost));
+        for (int t = 0; t < nb; t++) {
+          nodeOff[t + 1] = nodeOff[t] + hNodes[t]; leafOff[t + 1] = leafOff[t] + hLeaves[t];
+          totalCand += (long long)hCand[t]; totalAlgo += (long long)hAlgo[t];
+          h_leafCount[b0 + t] = (int32_t)hLeaves[t];
+          if (hNodes[t] != 2 * hLeaves[t] - 1) { set_error("internal: tree %d has %u records for %u leaves", hid[t], hNodes[t], hLeaves[t]); throw CudaFail{RFSLAM_EINVAL}; }
+        }
+        RF_CUDA(cudaMemcpy(d_nodeOff.p, nodeOff.data(), (nb + 1) * 8, cudaMemcpyHostToDevice));
+        RF_CUDA(cudaMemcpy(d_leafOff.p, leafOff.data(), (nb + 1) * 8, cudaMemcpyHostToDevice));
+        const size_t NN = nodeOff[nb], NL = leafOff[nb];
+        DevBuf<int32_t> f_tree, f_node, f_parm, f_rcnt, f_acnt, f_clas; DevBuf<double> f_cont, f_stat; DevBuf<uint32_t> f_code, f_right;
+        f_tree.alloc(NN); f_node.alloc(NN); f_parm.alloc(NN); f_cont.alloc(NN); f_stat.alloc(NN); f_code.alloc(NN); f_right.alloc(NN);
+        f_rcnt.alloc(NL); f_acnt.alloc(NL); f_clas.alloc(2 * NL); f_acnt.zero();
+        uint32_t maxNodes = *std::max_element(hNodes.begin(), hNodes.end());
+        dim3 gk((unsigned)std::min<uint32_t>((maxNodes + 255) / 256, 2048), (unsigned)nb);
+        compact_kernel<<<gk, 256>>>(w, ds->dev, d_ids.p, d_nodeOff.p, d_leafOff.p, f_tree.p, f_node.p, f_parm.p, f_cont.p, f_stat.p,
+                                    f_code.p, f_right.p, f_rcnt.p, f_clas.p);
+        membership_kernel<<<(n + 127) / 128, 128>>>(ds->dev, nb, d_nodeOff.p, d_leafOff.p, f_node.p, f_parm.p, f_code.p, f_right.p,
+                                                    f_rcnt.p, f_clas.p, d_cnt.p, f_acnt.p, d_allNum.p, d_oobNum.p, d_allDen.p, d_oobDen.p,
+                                                    d_nodeMemb.p, d_bootMemb.p, b0, cntStride);
+        RF_CUDA(cudaEventRecord(ev3));
+        RF_CUDA(cudaGetLastError());
+        RF_CUDA(cudaEventSynchronize(ev3));
+        float ms = 0.f;
+        RF_CUDA(cudaEventElapsedTime(&ms, ev1, ev2)); growMs += ms;
+        RF_CUDA(cudaEventElapsedTime(&ms, ev0, ev3)); totalMs += ms;
+
+        // ---- append to host output ----
+        size_t o0 = h_treeID.size(), l0 = h_tnRCNT.size();
+        h_treeID.resize(o0 + NN); h_nodeID.resize(o0 + NN); h_parmID.resize(o0 + NN); h_contPT.resize(o0 + NN); h_stat.resize(o0 + NN);
+        h_tnRCNT.resize(l0 + NL); h_tnACNT.resize(l0 + NL); h_tnCLAS.resize(2 * (l0 + NL));
+        RF_CUDA(cudaMemcpy(h_treeID.data() + o0, f_tree.p, NN * 4, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_nodeID.data() + o0, f_node.p, NN * 4, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_parmID.data() + o0, f_parm.p, NN * 4, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_contPT.data() + o0, f_cont.p, NN * 8, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_stat.data() + o0, f_stat.p, NN * 8, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_tnRCNT.data() + l0, f_rcnt.p, NL * 4, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_tnACNT.data() + l0, f_acnt.p, NL * 4, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_tnCLAS.data() + 2 * l0, f_clas.p, 2 * NL * 4, cudaMemcpyDeviceToHost));
+        // B_part's all-row term: 16 bytes per row of every split node
+        {
+          std::vector<uint32_t> hr(NN);
+          RF_CUDA(cudaMemcpy(hr.data(), f_right.p, NN * 4, cudaMemcpyDeviceToHost));
+          std::vector<long long> acc(NN);
+          for (int t = 0; t < nb; t++) {
+            size_t off = nodeOff[t];
+            for (long long q = (long long)hNodes[t] - 1; q >= 0; q--) {
+              size_t at = off + (size_t)q;
+              if (h_parmID[o0 + at] == 0) acc[at] = h_tnACNT[l0 + leafOff[t] + (size_t)h_nodeID[o0 + at] - 1];
+              else { acc[at] = acc[at + 1] + acc[off + hr[at]]; totalAlgo += 16ll * acc[at]; }
+            }
+          }
+        }
+        break;
+      }
+    }
+
+    if (cfg.finalize) {
+      finalize_kernel<<<(n + 255) / 256, 256>>>(d_allNum.p, d_allDen.p, n);
+      finalize_kernel<<<(n + 255) / 256, 256>>>(d_oobNum.p, d_oobDen.p, n);
+      RF_CUDA(cudaGetLastError());
+    }
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2); cudaEventDestroy(ev3);
+
+    // ---- hand over ----
+    auto give_i = [](const std::vector<int32_t>& v) { int32_t* q = (int32_t*)malloc(std::max<size_t>(v.size(), 1) * 4); memcpy(q, v.data(), v.size() * 4); return q; };
+    auto give_d = [](const std::vector<double>& v) { double* q = (double*)malloc(std::max<size_t>(v.size(), 1) * 8); memcpy(q, v.data(), v.size() * 8); return q; };
+    out->ntree = T; out->n = n;
+    out->total_nodes = (int64_t)h_treeID.size(); out->total_leaves = (int64_t)h_tnRCNT.size();
+    std::vector<int32_t> idv(ids.begin(), ids.end());
+    out->tree_ids = give_i(idv);
+    out->treeID = give_i(h_treeID); out->nodeID = give_i(h_nodeID); out->parmID = give_i(h_parmID);
+    out->contPT = give_d(h_contPT); out->splitStat = give_d(h_stat);
+    out->mwcpSZ = (int32_t*)calloc(std::max<size_t>(h_treeID.size(), 1), 4);
+    out->leafCount = give_i(h_leafCount); out->seed = give_i(h_seed);
+    out->tnRCNT = give_i(h_tnRCNT); out->tnACNT = give_i(h_tnACNT); out->tnCLAS = give_i(h_tnCLAS);
+    out->oobEnsbCLS = host_copy(d_oobNum.p, 2 * (size_t)n); out->allEnsbCLS = host_copy(d_allNum.p, 2 * (size_t)n);
+    out->oobEnsbDen = host_copy(d_oobDen.p, (size_t)n); out->allEnsbDen = host_copy(d_allDen.p, (size_t)n);
+    if (cfg.want_membership) {
+      out->nodeMembership = host_copy(d_nodeMemb.p, (size_t)T * n);
+      out->bootMembership = host_copy(d_bootMemb.p, (size_t)T * n);
+    }
+    out->split_candidates = totalCand; out->algorithmic_bytes = totalAlgo;
+    out->grow_kernel_ms = growMs; out->total_device_ms = totalMs;
+  } catch (CudaFail f) {
+    rfslam_b200_free_forest(out);
+    return f.code;
+  }
+  return RFSLAM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// rfslam_b200_score_node: every cut of one covariate in one node, scored by the same device code
+// the tree kernel runs (emit-only mode), for direct comparison with the reference plugin.
+// ---------------------------------------------------------------------------------------------
+int score_node_impl(int rule, double k_for_alpha, int m, const double* x, const double* response,
+                    const int32_t* stratum, const double* risk_time, double* cut_value, double* delta,
+                    int32_t* n_cuts, int device) {
+  if (rule < 1 || rule > 6) { set_error("rule must be 1..6"); return RFSLAM_EINVAL; }
+  if (!(k_for_alpha > 0.0)) { set_error("k_for_alpha must be > 0"); return RFSLAM_EINVAL; }
+  rfslam_grow_args a;
+  memset(&a, 0, sizeof(a));
+  a.observation_size = m; a.x_size = 1; a.x_data = x; a.r_data = response; a.risk_time = risk_time;
+  a.stratifier = stratum; a.device = device; a.x_type = "R";
+  rfslam_dataset* ds = nullptr;
+  int rc = dataset_build(&a, &ds);
+  if (rc) return rc;
+  try {
+    const int n = m;
+    GrowParams g{};
+    g.rule = rule; g.mtry = 1; g.nodesize = 1; g.nodedepth = -1; g.alpha = 1.0 / (k_for_alpha * k_for_alpha);
+    g.pw = 1; g.ncmax = 1; g.has_sort = ds->max_D > kHistBins;
+    const size_t smem = grow_smem_bytes(g.ncmax, ds->K);
+    RF_CUDA(cudaFuncSetAttribute(rfslam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DevBuf<uint32_t> d_lists, d_sort, d_stackPerm, d_ctab, d_nodeCount, d_leafCount, d_cursor;
+    DevBuf<uint16_t> d_cnt; DevBuf<NodeEnt> d_stack; DevBuf<int> d_seedB, d_boot, d_status, d_sinkCount;
+    DevBuf<unsigned long long> d_cand, d_algo; DevBuf<Rec> d_pool; DevBuf<double> d_statPool, d_sinkCut, d_sinkDelta;
+    const size_t cntStride = ((size_t)n + 1) & ~(size_t)1;
+    d_lists.alloc(2 * (size_t)n); if (g.has_sort) d_sort.alloc(4 * (size_t)n);
+    d_cnt.alloc(cntStride); d_stack.alloc(kStackCap); d_stackPerm.alloc(kStackCap);
+    d_ctab.alloc(4); d_nodeCount.alloc(1); d_leafCount.alloc(1); d_cursor.alloc(1); d_status.alloc(1);
+    d_seedB.alloc(1); d_boot.alloc(1); d_cand.alloc(1); d_algo.alloc(1); d_pool.alloc(2 * kRecChunk); d_statPool.alloc(2 * kRecChunk);
+    d_sinkCut.alloc(n); d_sinkDelta.alloc(n); d_sinkCount.alloc(1);
+    std::vector<uint16_t> ones(cntStride, 1);
+    RF_CUDA(cudaMemcpy(d_cnt.p, ones.data(), cntStride * 2, cudaMemcpyHostToDevice));
+    int sb = -1, bs = n;
+    RF_CUDA(cudaMemcpy(d_seedB.p, &sb, 4, cudaMemcpyHostToDevice));
+    RF_CUDA(cudaMemcpy(d_boot.p, &bs, 4, cudaMemcpyHostToDevice));
+    d_cursor.zero(); d_status.zero(); d_sinkCount.zero();
+    GrowWork w{};
+    w.ntrees = 1; w.seedB = d_seedB.p; w.bootSize = d_boot.p; w.lists = d_lists.p; w.cnt = d_cnt.p; w.cntStride = cntStride;
+    w.sortbuf = g.has_sort ? d_sort.p : nullptr; w.stack = d_stack.p; w.stackPerm = d_stackPerm.p;
+    w.pool = d_pool.p; w.statPool = d_statPool.p; w.poolChunks = 2; w.poolCursor = d_cursor.p; w.ctab = d_ctab.p; w.maxChunksPerTree = 4;
+    w.nodeCount = d_nodeCount.p; w.leafCount = d_leafCount.p; w.candCount = d_cand.p; w.algoBytes = d_algo.p; w.status = d_status.p;
+    w.sinkCut = d_sinkCut.p; w.sinkDelta = d_sinkDelta.p; w.sinkCount = d_sinkCount.p;
+    rfslam_grow_kernel<<<1, kThreads, smem>>>(ds->dev, g, w);
+    RF_CUDA(cudaGetLastError());
+    RF_CUDA(cudaDeviceSynchronize());
+    int nc = 0;
+    RF_CUDA(cudaMemcpy(&nc, d_sinkCount.p, 4, cudaMemcpyDeviceToHost));
+    *n_cuts = nc;
+    if (nc > 0) {
+      RF_CUDA(cudaMemcpy(cut_value, d_sinkCut.p, (size_t)nc * 8, cudaMemcpyDeviceToHost));
+      RF_CUDA(cudaMemcpy(delta, d_sinkDelta.p, (size_t)nc * 8, cudaMemcpyDeviceToHost));
+    }
+  } catch (CudaFail f) {
+    dataset_free(ds);
+    return f.code;
+  }
+  dataset_free(ds);
+  return RFSLAM_OK;
+}
+
+int bootstrap_counts_impl(int seed, int ntree, int n, int tree, int32_t* counts, int device) {
+  if (seed >= 0 || ntree < 1 || tree < 1 || tree > ntree || n < 1) { set_error("bad bootstrap arguments"); return RFSLAM_EINVAL; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: librfslam_b200 has no CPU fallback"); return RFSLAM_ENODEV; }
+  try {
+    if (device >= 0) RF_CUDA(cudaSetDevice(device));
+    std::vector<int> sA, sB;
+    chain_seeds(seed, ntree, sA, sB);
+    DevBuf<int> d_seed, d_bs; DevBuf<uint32_t> d_draws;
+    d_seed.alloc(1); d_bs.alloc(1); d_draws.alloc(n);
+    RF_CUDA(cudaMemcpy(d_seed.p, &sA[tree - 1], 4, cudaMemcpyHostToDevice));
+    RF_CUDA(cudaMemcpy(d_bs.p, &n, 4, cudaMemcpyHostToDevice));
+    bootstrap_draw_kernel<<<1, 32>>>(d_seed.p, d_bs.p, d_draws.p, (size_t)n, n);
+    RF_CUDA(cudaGetLastError());
+    std::vector<uint32_t> h(n);
+    RF_CUDA(cudaMemcpy(h.data(), d_draws.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) counts[i] = 0;
+    for (int i = 0; i < n; i++) counts[h[i]]++;
+  } catch (CudaFail f) {
+    return f.code;
+  }
+  return RFSLAM_OK;
+}
+
+}  // namespace rfslam

@@ -1,0 +1,804 @@
+// grow_kernel.cuh -- the persistent tree-growing kernel: one CTA grows one whole tree, depth
+// first, with no host round trips.
+//
+// Why one CTA per tree: chain B of the reference's RNG is consumed in
+// left-first DFS node order (rf.c:21666-21691, rf.c:14915), so a node's draws are unknown until
+// every node before it in DFS order has been grown; trees, however, are independent
+// (rf.c:7082-7087).  148+ trees in flight (one or two per SM) keep every SM streaming its share
+// of HBM while each CTA follows the sequential DFS the results are defined by.
+//
+// Per attempted node the CTA does (reference functions replaced in brackets):
+//   1. draw <= mtry covariates without replacement          [selectRandomCovariates rf.c:14793]
+//   2. ONE pass over the node's in-bag entries, stratum segment by stratum segment, building
+//      per-(candidate, code) sufficient statistics for all candidates at once in shared memory
+//      [the per-cut regather rf.c:13455-13465 + the O(m) passes of poissonSplitN sc.c:710-747]
+//   3. per stratum: prefix sums over codes, the rule's term at every code where the stratum has
+//      rows, fill-forward, accumulate into per-cut left/right statistics in ascending stratum
+//      order [sc.c:751-764 / sc.c:1262-1290]
+//   4. sequential epsilon-hysteresis tracker over candidates in draw order and cuts in ascending
+//      order, exact and parallel via warp ballots           [updateMaximumSplit rf.c:15471]
+//   5. stable partition of the entry list into the two children [forkAndUpdate rf.c:10568,
+//      rf.c:21653-21663]
+// Covariates with more than 256 distinct values take the sorted-walk path instead of 2-3: the
+// CTA radix-sorts the node's codes in global scratch and walks the sorted order with block scans.
+#pragma once
+#include "common.cuh"
+#include "internal.h"
+
+namespace rfslam {
+
+struct Rec {            // one forest record (pre-order); 16 bytes
+  uint32_t nodeID;
+  uint32_t parm;        // covariate + 1, 0 = terminal
+  uint32_t a;           // internal: cut code      terminal: in-bag events (with multiplicity)
+  uint32_t b;           // internal: record index of the right child   terminal: in-bag count
+};
+
+struct NodeEnt {        // a pending node of the DFS
+  uint32_t start, len;  // entry range in the tree's list buffer
+  uint32_t m, E;        // in-bag rows / events with multiplicity
+  double   rtsum;       // sum of multiplicity * risk time (beta of the Bayes rules, sc.c:662-667)
+  uint32_t nodeID;
+  uint32_t parentRec;   // record whose right-child link is this node, or kNone
+  uint32_t depth;
+  uint32_t buf;         // which of the two list buffers holds the entries
+};
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+struct GrowParams {
+  int rule, mtry, nodesize, nodedepth;
+  double alpha;
+  const double* split_weight;    // [p] or nullptr
+  int pw;                        // words of a permissible-covariate mask
+  int ncmax;                     // min(mtry, kMaxCand)
+  int has_sort;                  // any covariate with D > kHistBins
+};
+
+struct GrowWork {
+  int ntrees;
+  const int* seedB;              // [ntrees]
+  const int* bootSize;           // [ntrees] sum of in-bag counts
+  uint32_t* lists;               // [ntrees][2][n]
+  const uint16_t* cnt;           // [ntrees][cntStride] in-bag count per internal row
+  size_t cntStride;
+  uint32_t* sortbuf;             // [ntrees][4][n] or nullptr
+  NodeEnt* stack;                // [ntrees][kStackCap]
+  uint32_t* stackPerm;           // [ntrees][kStackCap][pw]
+  Rec* pool; double* statPool;   // [poolChunks * kRecChunk]
+  uint32_t poolChunks;
+  uint32_t* poolCursor;
+  uint32_t* ctab;                // [ntrees][maxChunksPerTree]
+  uint32_t maxChunksPerTree;
+  uint32_t* nodeCount;           // [ntrees]
+  uint32_t* leafCount;           // [ntrees]
+  unsigned long long* candCount; // [ntrees]
+  unsigned long long* algoBytes; // [ntrees]
+  int* status;                   // 0 ok, 1 record pool exhausted, 2 DFS stack overflow
+  // single-node scoring mode (rfslam_b200_score_node): emit every cut instead of tracking
+  double* sinkCut; double* sinkDelta; int* sinkCount;
+};
+
+// fixed-size part of the CTA's shared memory
+struct GrowShared {
+  Ran1 rng;
+  NodeEnt cur;
+  uint32_t perm[32];                 // permissible covariates of the current node (p <= 1024)
+  uint16_t pool[1024];
+  int nc;
+  int candCov[kMaxCand];
+  int candD[kMaxCand];
+  int candW[kMaxCand];
+  int candHist[kMaxCand];
+  const void* candPtr[kMaxCand];
+  // tracker
+  int have; double bestDelta; int bestCand; uint32_t bestCode;
+  int cutsSeen;
+  // scratch for block reductions / scans
+  double scrD[kWarps]; unsigned long long scrU[kWarps]; int scrI[kWarps];
+  // sorted-walk tile
+  double tileTL[kThreads]; double tileTR[kThreads]; double tileDelta[kThreads];
+  uint32_t tileKey[kThreads]; uint8_t tileCut[kThreads];
+  uint32_t radixBase[256];
+  uint32_t nodeCount, leafCount, sp;
+  unsigned long long candCount, algoBytes;
+  int abort;
+  int ptotReady;
+};
+
+__device__ __forceinline__ Rec* rec_ptr(const GrowWork& w, int tree, uint32_t q) {
+  uint32_t c = w.ctab[(size_t)tree * w.maxChunksPerTree + q / kRecChunk];
+  return w.pool + (size_t)c * kRecChunk + (q % kRecChunk);
+}
+
+__device__ __forceinline__ int block_incl_scan_max(int v, int* scratch) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int u = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v = max(v, u);
+  }
+  __syncthreads();
+  if (lane == 31) scratch[warp_id()] = v;
+  __syncthreads();
+  int off = -1;
+  for (int w2 = 0; w2 < warp_id(); w2++) off = max(off, scratch[w2]);
+  return max(v, off);
+}
+
+// dynamic shared memory carve-up
+struct GrowSmem {
+  double *sL, *sR, *hT, *hW, *statP;
+  uint32_t *hN, *hE, *pres;
+  uint32_t *segpos, *PN, *PE, *cN, *cE;
+  double *PT, *PW, *cT, *cW, *cTL, *cTR;
+  GrowShared* s;
+};
+
+__host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K) {
+  size_t KS = (size_t)K + 2;
+  size_t b = 0;
+  b += (size_t)ncmax * kHistBins * 8 * 4;      // sL sR hT hW
+  b += (size_t)ncmax * 8;                      // statP
+  b += (size_t)ncmax * kHistBins * 4 * 2;      // hN hE
+  b += (size_t)ncmax * 8 * 4;                  // pres
+  b += KS * 8 * 6;                             // PT PW cT cW cTL cTR
+  b += KS * 4 * 5;                             // segpos PN PE cN cE
+  b = (b + 15) & ~(size_t)15;
+  b += sizeof(GrowShared);
+  return b + 16;
+}
+
+__device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K) {
+  GrowSmem m;
+  size_t KS = (size_t)K + 2;
+  double* d = (double*)raw;
+  m.sL = d; d += (size_t)ncmax * kHistBins;
+  m.sR = d; d += (size_t)ncmax * kHistBins;
+  m.hT = d; d += (size_t)ncmax * kHistBins;
+  m.hW = d; d += (size_t)ncmax * kHistBins;
+  m.statP = d; d += ncmax;
+  m.PT = d; d += KS; m.PW = d; d += KS; m.cT = d; d += KS; m.cW = d; d += KS; m.cTL = d; d += KS; m.cTR = d; d += KS;
+  uint32_t* u = (uint32_t*)d;
+  m.hN = u; u += (size_t)ncmax * kHistBins;
+  m.hE = u; u += (size_t)ncmax * kHistBins;
+  m.pres = u; u += (size_t)ncmax * 8;
+  m.segpos = u; u += KS; m.PN = u; u += KS; m.PE = u; u += KS; m.cN = u; u += KS; m.cE = u; u += KS;
+  uintptr_t p = ((uintptr_t)u + 15) & ~(uintptr_t)15;
+  m.s = (GrowShared*)p;
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------
+// tracker: the reference's updateMaximumSplit applied to one 32-wide chunk of candidate cuts in
+// ascending order.  `val` is this lane's delta, `present` whether the lane holds a real cut.
+// have/best/bestLane are warp-uniform; returns the number of selections (bestLane = last one).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void track_chunk(bool present, double val, int& have, double& best, int& selLane) {
+  unsigned pend = __ballot_sync(0xffffffffu, present);
+  const int lane = threadIdx.x & 31;
+  selLane = -1;
+  while (pend) {
+    int j;
+    if (!have) {
+      j = __ffs(pend) - 1;
+    } else {
+      bool beat = ((pend >> lane) & 1u) && ((val - best) > kEpsilon);
+      unsigned mask = __ballot_sync(0xffffffffu, beat);
+      if (!mask) break;
+      j = __ffs(mask) - 1;
+    }
+    best = __shfl_sync(0xffffffffu, val, j);
+    have = 1;
+    selLane = j;
+    pend &= ~((2u << j) - 1u);
+  }
+}
+
+struct NodeCtx {
+  const DevData& d;
+  const GrowParams& g;
+  const GrowWork& w;
+  GrowSmem& m;
+  const uint32_t* list;   // the node's entries: list[0..len)
+  int tree;
+  bool bayes, unit, strat;
+  double beta;
+  int Kloop;
+};
+
+// ---- per-stratum flush of the joint histograms (step 3) -------------------------------------
+__device__ inline void flush_stratum(const NodeCtx& c, int nc) {
+  GrowSmem& m = c.m;
+  GrowShared* s = m.s;
+  const int lane = lane_id();
+  for (int ci = warp_id(); ci < nc; ci += kWarps) {
+    if (!s->candHist[ci]) continue;
+    const int Dc = s->candD[ci];
+    const int nch = (Dc + 31) >> 5;
+    uint32_t* hN = m.hN + ci * kHistBins; uint32_t* hE = m.hE + ci * kHistBins;
+    double* hT = m.hT + ci * kHistBins;   double* hW = m.hW + ci * kHistBins;
+    // stratum totals
+    uint32_t tN = 0, tE = 0; double tT = 0.0, tW = 0.0;
+    for (int ch = 0; ch < nch; ch++) {
+      int bin = (ch << 5) + lane;
+      if (bin < Dc) { tN += hN[bin]; tE += hE[bin]; if (!c.unit) { tT += hT[bin]; tW += hW[bin]; } }
+    }
+    tN = warp_sum(tN); tE = warp_sum(tE);
+    if (c.unit) { tT = (double)tN; tW = (double)tE; } else { tT = warp_sum(tT); tW = warp_sum(tW); }
+    if (tN == 0) continue;
+    const bool active = tE > 0;
+    double termP = 0.0;
+    if (active) {
+      termP = side_term(c.bayes, (double)tE, (double)tN, tT, tW, c.g.alpha, c.beta);
+      if (lane == 0) m.statP[ci] += termP;
+    }
+    uint32_t cN = 0, cE = 0; double cT = 0.0, cW = 0.0;     // carries (warp-uniform)
+    double cTL = 0.0, cTR = termP;
+    for (int ch = 0; ch < nch; ch++) {
+      int bin = (ch << 5) + lane;
+      uint32_t vN = 0, vE = 0; double vT = 0.0, vW = 0.0;
+      if (bin < Dc) {
+        vN = hN[bin]; vE = hE[bin];
+        if (!c.unit) { vT = hT[bin]; vW = hW[bin]; }
+        hN[bin] = 0; hE[bin] = 0; hT[bin] = 0.0; hW[bin] = 0.0;      // leave the histogram clean
+      }
+      unsigned own = __ballot_sync(0xffffffffu, vN > 0);
+      if (lane == 0 && own) m.pres[ci * 8 + ch] |= own;
+      if (!active) continue;
+      if (c.unit) { vT = (double)vN; vW = (double)vE; }
+      uint32_t iN = warp_incl_scan(vN) + cN, iE = warp_incl_scan(vE) + cE;
+      double iT = warp_incl_scan(vT) + cT, iW = warp_incl_scan(vW) + cW;
+      double tL = 0.0, tR = 0.0;
+      if (vN > 0) {
+        tL = side_term(c.bayes, (double)iE, (double)iN, iT, iW, c.g.alpha, c.beta);
+        tR = side_term(c.bayes, (double)(tE - iE), (double)(tN - iN), tT - iT, tW - iW, c.g.alpha, c.beta);
+      }
+      // fill-forward from the nearest lane <= me that holds rows of this stratum
+      unsigned le = own & (0xffffffffu >> (31 - lane));
+      int src = le ? (31 - __clz(le)) : -1;
+      double fL = __shfl_sync(0xffffffffu, tL, src < 0 ? 0 : src);
+      double fR = __shfl_sync(0xffffffffu, tR, src < 0 ? 0 : src);
+      if (src < 0) { fL = cTL; fR = cTR; }
+      if (bin < Dc) { m.sL[ci * kHistBins + bin] += fL; m.sR[ci * kHistBins + bin] += fR; }
+      cN = __shfl_sync(0xffffffffu, iN, 31); cE = __shfl_sync(0xffffffffu, iE, 31);
+      cT = __shfl_sync(0xffffffffu, iT, 31); cW = __shfl_sync(0xffffffffu, iW, 31);
+      cTL = __shfl_sync(0xffffffffu, fL, 31); cTR = __shfl_sync(0xffffffffu, fR, 31);
+    }
+  }
+}
+
+// ---- tracker over one histogram candidate (warp 0 only) -------------------------------------
+__device__ inline void track_hist(const NodeCtx& c, int ci) {
+  GrowSmem& m = c.m;
+  GrowShared* s = m.s;
+  const int lane = lane_id();
+  const int Dc = s->candD[ci];
+  const int nch = (Dc + 31) >> 5;
+  uint32_t word = (lane < 8) ? m.pres[ci * 8 + lane] : 0u;
+  int np = warp_sum((int)__popc(word));
+  int last = word ? (lane * 32 + 31 - __clz(word)) : -1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  const int cov = s->candCov[ci];
+  if (np < 2) {                       // constant in this node: not permissible below (rf.c:15004-15007)
+    if (lane == 0) s->perm[cov >> 5] &= ~(1u << (cov & 31));
+    return;
+  }
+  const double wgt = c.g.split_weight ? c.g.split_weight[cov] : 1.0;
+  const double statP = m.statP[ci];
+  int have = s->have; double best = s->bestDelta; int bestBin = -1;
+  int emitted = s->cutsSeen;
+  for (int ch = 0; ch < nch; ch++) {
+    int bin = (ch << 5) + lane;
+    uint32_t wd = m.pres[ci * 8 + ch];
+    bool present = ((wd >> lane) & 1u) && bin != last;
+    double val = present ? (m.sL[ci * kHistBins + bin] + m.sR[ci * kHistBins + bin] - statP) * wgt : 0.0;
+    if (c.w.sinkDelta) {
+      unsigned pm = __ballot_sync(0xffffffffu, present);
+      if (present) {
+        int k = emitted + __popc(pm & ((1u << lane) - 1u));
+        c.w.sinkDelta[k] = val;
+        c.w.sinkCut[k] = c.d.uniq[cov][bin];
+      }
+      emitted += __popc(pm);
+    }
+    int sel;
+    track_chunk(present, val, have, best, sel);
+    if (sel >= 0) bestBin = (ch << 5) + sel;
+  }
+  if (lane == 0) {
+    s->candCount += (unsigned long long)(np - 1);
+    s->cutsSeen = emitted;
+    if (bestBin >= 0) { s->have = 1; s->bestDelta = best; s->bestCand = ci; s->bestCode = (uint32_t)bestBin; }
+  }
+}
+
+// ---- sorted-walk path for covariates with more than kHistBins distinct values ----------------
+__device__ inline void radix_pass(const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout,
+                                  uint32_t len, int shift, GrowShared* s) {
+  const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+  __syncthreads();
+  s->radixBase[tid] = 0;
+  __syncthreads();
+  for (uint32_t i = tid; i < len; i += kThreads) atomicAdd(&s->radixBase[(kin[i] >> shift) & 255u], 1u);
+  __syncthreads();
+  uint32_t cnt = s->radixBase[tid];
+  unsigned long long tot;
+  unsigned long long inc = block_incl_scan<unsigned long long>((unsigned long long)cnt, s->scrU, tot);
+  __syncthreads();
+  s->radixBase[tid] = (uint32_t)(inc - cnt);
+  __syncthreads();
+  const uint32_t ntiles = (len + kThreads - 1) / kThreads;
+  for (uint32_t t = 0; t < ntiles; t++) {
+    uint32_t i = t * kThreads + tid;
+    bool valid = i < len;
+    uint32_t key = valid ? kin[i] : 0u;
+    uint32_t val = valid ? vin[i] : 0u;
+    uint32_t dgt = valid ? ((key >> shift) & 255u) : (0x100u + (uint32_t)lane);
+    uint32_t pos = 0;
+    for (int wv = 0; wv < kWarps; wv++) {           // warps take turns so equal digits keep their order
+      if (wid == wv) {
+        unsigned peers = __match_any_sync(0xffffffffu, dgt);
+        uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        if (valid) pos = s->radixBase[dgt] + rank;
+        __syncwarp();
+        if (valid && rank == 0) s->radixBase[dgt] += __popc(peers);
+      }
+      __syncthreads();
+    }
+    if (valid) { kout[pos] = key; vout[pos] = val; }
+  }
+  __syncthreads();
+}
+
+// per-stratum totals of the node (needed up front by the sorted walk)
+__device__ inline void stratum_totals(const NodeCtx& c, uint32_t len) {
+  GrowSmem& m = c.m;
+  GrowShared* s = m.s;
+  for (int k = 1; k <= c.Kloop; k++) {
+    uint32_t s0 = m.segpos[k], s1 = m.segpos[k + 1];
+    unsigned long long ne = 0; double vT = 0.0, vW = 0.0;
+    for (uint32_t i = s0 + threadIdx.x; i < s1; i += kThreads) {
+      uint32_t ent = c.list[i];
+      uint32_t row = ent & kRowMask, mult = (ent >> kRowBits) + 1u;
+      uint32_t e = c.d.ev[row];
+      double t = c.unit ? 1.0 : c.d.rt[row];
+      ne += ((unsigned long long)mult << 32) | (unsigned long long)(e ? mult : 0u);
+      vT += (double)mult * t;
+      if (e) vW += (double)mult * t;
+    }
+    unsigned long long tne = block_sum<unsigned long long>(ne, s->scrU);
+    double tT = block_sum<double>(vT, s->scrD);
+    double tW = block_sum<double>(vW, s->scrD);
+    if (threadIdx.x == 0) {
+      m.PN[k] = (uint32_t)(tne >> 32); m.PE[k] = (uint32_t)(tne & 0xffffffffu);
+      m.PT[k] = tT; m.PW[k] = tW;
+    }
+  }
+  (void)len;
+  __syncthreads();
+}
+
+__device__ inline void sort_candidate(const NodeCtx& c, int ci, uint32_t len) {
+  GrowSmem& m = c.m;
+  GrowShared* s = m.s;
+  const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+  const int n = c.d.n;
+  uint32_t* kA = c.w.sortbuf + (size_t)c.tree * 4 * n;
+  uint32_t* kB = kA + n; uint32_t* vA = kB + n; uint32_t* vB = vA + n;
+  const void* ptr = s->candPtr[ci]; const int wd = s->candW[ci]; const int Dc = s->candD[ci]; const int cov = s->candCov[ci];
+  for (uint32_t i = tid; i < len; i += kThreads) {
+    uint32_t row = c.list[i] & kRowMask;
+    kA[i] = load_code(ptr, wd, row);
+    vA[i] = i;
+  }
+  int bits = 32 - __clz(Dc - 1);
+  int npass = (bits + 7) >> 3;
+  uint32_t *ks = kA, *vs = vA, *kd = kB, *vd = vB;
+  for (int ps = 0; ps < npass; ps++) {
+    radix_pass(ks, vs, kd, vd, len, 8 * ps, s);
+    uint32_t* t1 = ks; ks = kd; kd = t1;
+    uint32_t* t2 = vs; vs = vd; vd = t2;
+  }
+  __syncthreads();
+  // parent statistic and carries
+  double statP = 0.0;
+  for (int a = 1; a <= c.Kloop; a++)
+    if (m.PE[a] > 0) statP += side_term(c.bayes, (double)m.PE[a], (double)m.PN[a], m.PT[a], m.PW[a], c.g.alpha, c.beta);
+  for (int a = 1 + tid; a <= c.Kloop; a += kThreads) {
+    m.cN[a] = 0; m.cE[a] = 0; m.cT[a] = 0.0; m.cW[a] = 0.0; m.cTL[a] = 0.0;
+    m.cTR[a] = (m.PE[a] > 0) ? side_term(c.bayes, (double)m.PE[a], (double)m.PN[a], m.PT[a], m.PW[a], c.g.alpha, c.beta) : 0.0;
+  }
+  __syncthreads();
+  const double wgt = c.g.split_weight ? c.g.split_weight[cov] : 1.0;
+  const uint32_t ntiles = (len + kThreads - 1) / kThreads;
+  int have = s->have; double best = s->bestDelta; uint32_t bestKey = 0; int gotBest = 0;   // warp 0's view
+  int totalCuts = 0;
+  int emitted = s->cutsSeen;
+  for (uint32_t t = 0; t < ntiles; t++) {
+    uint32_t j = t * kThreads + tid;
+    bool valid = j < len;
+    uint32_t key = 0, mult = 0, e = 0; int sa = 0; double tt = 0.0;
+    bool cut = false;
+    if (valid) {
+      key = ks[j];
+      uint32_t ent = c.list[vs[j]];
+      uint32_t row = ent & kRowMask; mult = (ent >> kRowBits) + 1u;
+      e = c.d.ev[row]; tt = c.unit ? 1.0 : c.d.rt[row];
+      sa = c.strat ? (int)c.d.strat[row] : 1;
+      cut = (j + 1 < len) && (ks[j + 1] != key);
+    }
+    double accL = 0.0, accR = 0.0;
+    for (int a = 1; a <= c.Kloop; a++) {
+      if (m.PE[a] == 0) continue;                            // uniform: PE is shared
+      bool f = valid && sa == a;
+      unsigned long long vne = f ? (((unsigned long long)mult << 32) | (unsigned long long)(e ? mult : 0u)) : 0ull;
+      double vT = f ? (double)mult * tt : 0.0;
+      double vW = (f && e) ? (double)mult * tt : 0.0;
+      unsigned long long tne; double totT, totW;
+      unsigned long long ine = block_incl_scan<unsigned long long>(vne, s->scrU, tne);
+      double iT = block_incl_scan<double>(vT, s->scrD, totT);
+      double iW = block_incl_scan<double>(vW, s->scrD, totW);
+      uint32_t LN = (uint32_t)(ine >> 32) + m.cN[a], LE = (uint32_t)(ine & 0xffffffffu) + m.cE[a];
+      double LT = iT + m.cT[a], LW = iW + m.cW[a];
+      if (f) {
+        s->tileTL[tid] = side_term(c.bayes, (double)LE, (double)LN, LT, LW, c.g.alpha, c.beta);
+        s->tileTR[tid] = side_term(c.bayes, (double)(m.PE[a] - LE), (double)(m.PN[a] - LN), m.PT[a] - LT, m.PW[a] - LW, c.g.alpha, c.beta);
+      }
+      int src = block_incl_scan_max(f ? tid : -1, s->scrI);
+      __syncthreads();
+      double myL = (src >= 0) ? s->tileTL[src] : m.cTL[a];
+      double myR = (src >= 0) ? s->tileTR[src] : m.cTR[a];
+      if (cut) { accL += myL; accR += myR; }
+      __syncthreads();
+      if (tid == kThreads - 1) {
+        m.cN[a] = LN; m.cE[a] = LE; m.cT[a] = LT; m.cW[a] = LW; m.cTL[a] = myL; m.cTR[a] = myR;
+      }
+      __syncthreads();
+    }
+    s->tileDelta[tid] = cut ? (accL + accR - statP) * wgt : 0.0;
+    s->tileCut[tid] = cut ? 1 : 0;
+    s->tileKey[tid] = key;
+    __syncthreads();
+    if (wid == 0) {
+      for (int ch = 0; ch < kWarps; ch++) {
+        int q = (ch << 5) + lane;
+        bool present = s->tileCut[q] != 0;
+        double val = s->tileDelta[q];
+        unsigned pm = __ballot_sync(0xffffffffu, present);
+        if (c.w.sinkDelta && present) {
+          int k = emitted + __popc(pm & ((1u << lane) - 1u));
+          c.w.sinkDelta[k] = val;
+          c.w.sinkCut[k] = c.d.uniq[cov][s->tileKey[q]];
+        }
+        emitted += __popc(pm);
+        totalCuts += __popc(pm);
+        int sel;
+        track_chunk(present, val, have, best, sel);
+        if (sel >= 0) { bestKey = s->tileKey[(ch << 5) + sel]; gotBest = 1; }
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    s->cutsSeen = emitted;
+    if (totalCuts == 0) {
+      s->perm[cov >> 5] &= ~(1u << (cov & 31));
+    } else {
+      s->candCount += (unsigned long long)totalCuts;
+      if (gotBest) { s->have = 1; s->bestDelta = best; s->bestCand = ci; s->bestCode = bestKey; }
+    }
+  }
+  __syncthreads();
+}
+
+// ---- score all drawn candidates of the current node (steps 2-4) ------------------------------
+__device__ inline void score_node(const DevData& d, const GrowParams& g, const GrowWork& w, GrowSmem& m, int tree) {
+  GrowShared* s = m.s;
+  const int tid = threadIdx.x;
+  const int nc = s->nc;
+  const NodeEnt cur = s->cur;
+  const uint32_t* list = w.lists + ((size_t)tree * 2 + cur.buf) * d.n + cur.start;
+  const bool bayes = rule_is_bayes(g.rule), unit = rule_unit_time(g.rule), strat = rule_is_stratified(g.rule);
+  double beta = 0.0;
+  if (bayes) beta = g.alpha / (((double)cur.m + (double)cur.E) / cur.rtsum);
+  const int Kloop = strat ? d.K : 1;
+  NodeCtx c{d, g, w, m, list, tree, bayes, unit, strat, beta, Kloop};
+
+  // segment boundaries of the strata inside this node's (row-sorted) entry list
+  if (strat) {
+    for (int k = tid; k <= d.K + 1; k += kThreads) {
+      uint32_t key = d.sb[k];
+      uint32_t lo = 0, hi = cur.len;
+      while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if ((list[mid] & kRowMask) < key) lo = mid + 1; else hi = mid;
+      }
+      m.segpos[k] = lo;
+    }
+  } else if (tid == 0) {
+    m.segpos[0] = 0; m.segpos[1] = 0; m.segpos[2] = cur.len;
+  }
+  for (int i = tid; i < nc * kHistBins; i += kThreads) { m.sL[i] = 0.0; m.sR[i] = 0.0; }
+  for (int i = tid; i < nc * 8; i += kThreads) m.pres[i] = 0u;
+  if (tid < nc) m.statP[tid] = 0.0;
+  if (tid == 0) { s->have = 0; s->bestDelta = 0.0; s->bestCand = -1; s->bestCode = 0; s->cutsSeen = 0; }
+  __syncthreads();
+
+  bool anyHist = false, anySort = false;
+  for (int ci = 0; ci < nc; ci++) { if (s->candHist[ci]) anyHist = true; else anySort = true; }
+
+  if (anyHist) {
+    for (int k = 1; k <= Kloop; k++) {
+      const uint32_t s0 = m.segpos[k], s1 = m.segpos[k + 1];
+      if (s0 == s1) continue;
+      for (uint32_t i = s0 + tid; i < s1; i += kThreads) {
+        const uint32_t ent = list[i];
+        const uint32_t row = ent & kRowMask, mult = (ent >> kRowBits) + 1u;
+        const uint32_t e = d.ev[row];
+        const double ft = unit ? 0.0 : (double)mult * d.rt[row];
+        for (int ci = 0; ci < nc; ci++) {
+          if (!s->candHist[ci]) continue;
+          const uint32_t code = load_code(s->candPtr[ci], s->candW[ci], row);
+          const int idx = ci * kHistBins + (int)code;
+          atomicAdd(&m.hN[idx], mult);
+          if (e) atomicAdd(&m.hE[idx], mult);
+          if (!unit) {
+            atomicAdd(&m.hT[idx], ft);
+            if (e) atomicAdd(&m.hW[idx], ft);
+          }
+        }
+      }
+      __syncthreads();
+      flush_stratum(c, nc);
+      __syncthreads();
+    }
+  }
+  if (anySort) stratum_totals(c, cur.len);
+
+  for (int ci = 0; ci < nc; ci++) {
+    if (s->candHist[ci]) {
+      if (warp_id() == 0) track_hist(c, ci);
+      __syncthreads();
+    } else {
+      sort_candidate(c, ci, cur.len);
+    }
+  }
+  __syncthreads();
+}
+
+// ---- thread 0: draw the node's candidate covariates (step 1) ---------------------------------
+__device__ inline void draw_candidates(const DevData& d, const GrowParams& g, GrowShared* s) {
+  int size = 0;
+  for (int k = 0; k < d.p; k++)
+    if ((s->perm[k >> 5] >> (k & 31)) & 1u) s->pool[size++] = (uint16_t)k;     // ascending (rf.c:8209-8213)
+  int count = 0, nc = 0;
+  while (count < g.mtry && size > 0) {
+    count++;
+    uint32_t slot = ran1_index(s->rng, (uint32_t)size);                          // in [1, size]
+    int cov = s->pool[slot - 1];
+    s->pool[slot - 1] = s->pool[size - 1];                                       // swap-remove (rf.c:8306)
+    size--;
+    s->candCov[nc] = cov;
+    s->candD[nc] = d.D[cov];
+    s->candW[nc] = d.width[cov];
+    s->candPtr[nc] = d.codes[cov];
+    s->candHist[nc] = d.D[cov] <= kHistBins;
+    nc++;
+  }
+  s->nc = nc;
+}
+
+__device__ inline bool append_record(const GrowWork& w, GrowShared* s, int tree, uint32_t nodeID, uint32_t parm,
+                                     uint32_t a, uint32_t b, double stat, uint32_t parentRec, uint32_t* outIdx) {
+  uint32_t q = s->nodeCount;
+  if ((q % kRecChunk) == 0) {
+    uint32_t ch = q / kRecChunk;
+    uint32_t id = atomicAdd(w.poolCursor, 1u);
+    if (id >= w.poolChunks || ch >= w.maxChunksPerTree) { atomicExch(w.status, 1); s->abort = 1; return false; }
+    w.ctab[(size_t)tree * w.maxChunksPerTree + ch] = id;
+  }
+  uint32_t cidx = w.ctab[(size_t)tree * w.maxChunksPerTree + q / kRecChunk];
+  size_t at = (size_t)cidx * kRecChunk + (q % kRecChunk);
+  w.pool[at] = Rec{nodeID, parm, a, b};
+  w.statPool[at] = stat;
+  if (parentRec != kNone) rec_ptr(w, tree, parentRec)->b = q;
+  s->nodeCount = q + 1;
+  *outIdx = q;
+  return true;
+}
+
+extern "C" __global__ void __launch_bounds__(kThreads, 2)
+rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GrowSmem m = carve(smem_raw, g.ncmax, d.K);
+  GrowShared* s = m.s;
+  const int tid = threadIdx.x;
+  const int tree = blockIdx.x;
+  const int n = d.n;
+  uint32_t* listA = w.lists + (size_t)tree * 2 * n;
+  const uint16_t* cnt = w.cnt + (size_t)tree * w.cntStride;
+
+  // ---- clean histograms (flushes keep them clean afterwards) ----
+  for (int i = tid; i < g.ncmax * kHistBins; i += kThreads) { m.hN[i] = 0; m.hE[i] = 0; m.hT[i] = 0.0; m.hW[i] = 0.0; }
+  if (tid == 0) {
+    ran1_seed(s->rng, w.seedB[tree]);
+    s->nodeCount = 0; s->leafCount = 1; s->sp = 0; s->candCount = 0; s->algoBytes = 0; s->abort = 0;
+  }
+  for (int k = tid; k < 32; k += kThreads) {
+    uint32_t msk = 0;
+    for (int b = 0; b < 32; b++) if (k * 32 + b < d.p) msk |= (1u << b);
+    s->perm[k] = msk;
+  }
+  __syncthreads();
+
+  // ---- root: in-bag entry list in internal row order from the bootstrap counts (rf.c:492-627) ----
+  {
+    uint32_t base = 0;
+    unsigned long long ne = 0; double rts = 0.0;
+    const uint32_t ntiles = ((uint32_t)n + kThreads - 1) / kThreads;
+    for (uint32_t t = 0; t < ntiles; t++) {
+      uint32_t i = t * kThreads + tid;
+      uint32_t cval = (i < (uint32_t)n) ? cnt[i] : 0u;
+      uint32_t nent = (cval + kMaxMult - 1) / kMaxMult;
+      unsigned long long tot;
+      unsigned long long inc = block_incl_scan<unsigned long long>((unsigned long long)nent, s->scrU, tot);
+      uint32_t pos = base + (uint32_t)(inc - nent);
+      uint32_t left = cval;
+      for (uint32_t q = 0; q < nent; q++) {
+        uint32_t mu = left > kMaxMult ? kMaxMult : left;
+        listA[pos + q] = ((mu - 1u) << kRowBits) | i;
+        left -= mu;
+      }
+      if (cval) {
+        ne += ((unsigned long long)cval << 32) | (unsigned long long)(d.ev[i] ? cval : 0u);
+        rts += (double)cval * d.rt[i];
+      }
+      base += (uint32_t)tot;
+      __syncthreads();
+    }
+    unsigned long long tne = block_sum<unsigned long long>(ne, s->scrU);
+    double trt = block_sum<double>(rts, s->scrD);
+    if (tid == 0) {
+      s->cur.start = 0; s->cur.len = base; s->cur.m = (uint32_t)(tne >> 32); s->cur.E = (uint32_t)(tne & 0xffffffffu);
+      s->cur.rtsum = trt; s->cur.nodeID = 1; s->cur.parentRec = kNone; s->cur.depth = 0; s->cur.buf = 0;
+      s->algoBytes += 4ull * (unsigned long long)w.bootSize[tree];
+    }
+    __syncthreads();
+  }
+
+  const bool bayes = rule_is_bayes(g.rule);
+  // ---- depth-first growth (rf.c:21460-21792) ----
+  while (true) {
+    __syncthreads();
+    if (s->abort) break;
+    const NodeEnt cur = s->cur;
+    // node gate (rf.c:15354-15371) and purity (rf.c:6391-6416): both classes present
+    bool attempt = (cur.m >= 2u * (uint32_t)g.nodesize) && (g.nodedepth < 0 || cur.depth < (uint32_t)g.nodedepth);
+    if (attempt) {
+      double mm = (double)cur.m, ee = (double)cur.E;
+      double mean = (mm + ee) / mm;
+      double var = ((mm - ee) * (mean - 1.0) * (mean - 1.0) + ee * (mean - 2.0) * (mean - 2.0)) / mm;
+      attempt = var > kEpsilon;
+    }
+    if (w.sinkDelta) attempt = true;                       // single-node scoring mode: no gate
+    if (tid == 0) { s->nc = 0; s->have = 0; }
+    __syncthreads();
+    if (attempt) {
+      if (tid == 0) {
+        draw_candidates(d, g, s);
+        s->algoBytes += (unsigned long long)cur.m * (12ull * (unsigned long long)s->nc + 20ull);
+      }
+      __syncthreads();
+      if (s->nc > 0) score_node(d, g, w, m, tree);
+    }
+    __syncthreads();
+    if (w.sinkDelta) {                                     // emit-only mode stops after the root
+      if (tid == 0) *w.sinkCount = s->cutsSeen;
+      break;
+    }
+    const bool split = attempt && s->have;
+    if (!split) {
+      if (tid == 0) {
+        uint32_t q;
+        append_record(w, s, tree, cur.nodeID, 0u, cur.E, cur.m, nan(""), cur.parentRec, &q);
+        if (!s->abort) {
+          if (s->sp == 0) {
+            s->abort = 2;                                   // finished
+          } else {
+            s->sp--;
+            s->cur = w.stack[(size_t)tree * kStackCap + s->sp];
+          }
+        }
+      }
+      __syncthreads();
+      if (s->abort == 2) break;
+      if (!s->abort) {
+        const uint32_t* sp = w.stackPerm + ((size_t)tree * kStackCap + s->sp) * g.pw;
+        for (int k = tid; k < g.pw; k += kThreads) s->perm[k] = sp[k];
+      }
+      continue;
+    }
+
+    // ---- split: record, partition, push right, descend left ----
+    const int bc = s->bestCand;
+    const uint32_t bcode = s->bestCode;
+    const void* ptr = s->candPtr[bc]; const int wd = s->candW[bc]; const int cov = s->candCov[bc];
+    const uint32_t* src = w.lists + ((size_t)tree * 2 + cur.buf) * n + cur.start;
+    uint32_t* dst = w.lists + ((size_t)tree * 2 + (cur.buf ^ 1u)) * n + cur.start;
+    // pass 1: sizes of the left child
+    unsigned long long cL = 0, neL = 0; double rtL = 0.0, rtR = 0.0;
+    for (uint32_t i = tid; i < cur.len; i += kThreads) {
+      uint32_t ent = src[i];
+      uint32_t row = ent & kRowMask, mult = (ent >> kRowBits) + 1u;
+      bool left = load_code(ptr, wd, row) <= bcode;          // LEFT iff cut - x >= 0 (rf.c:15194)
+      uint32_t e = d.ev[row];
+      if (left) { cL++; neL += ((unsigned long long)mult << 32) | (unsigned long long)(e ? mult : 0u); }
+      if (bayes) { double v = (double)mult * d.rt[row]; if (left) rtL += v; else rtR += v; }
+    }
+    const uint32_t nL = (uint32_t)block_sum<unsigned long long>(cL, s->scrU);
+    const unsigned long long tneL = block_sum<unsigned long long>(neL, s->scrU);
+    double trtL = 0.0, trtR = 0.0;
+    if (bayes) { trtL = block_sum<double>(rtL, s->scrD); trtR = block_sum<double>(rtR, s->scrD); }
+    // pass 2: stable scatter
+    {
+      uint32_t baseL = 0, baseR = 0;
+      const uint32_t ntiles = (cur.len + kThreads - 1) / kThreads;
+      for (uint32_t t = 0; t < ntiles; t++) {
+        uint32_t i = t * kThreads + tid;
+        bool valid = i < cur.len;
+        uint32_t ent = valid ? src[i] : 0u;
+        bool left = valid && (load_code(ptr, wd, ent & kRowMask) <= bcode);
+        unsigned long long tot;
+        unsigned long long inc = block_incl_scan<unsigned long long>(left ? 1ull : 0ull, s->scrU, tot);
+        uint32_t before = (uint32_t)inc - (left ? 1u : 0u);
+        if (valid) {
+          if (left) dst[baseL + before] = ent;
+          else dst[nL + baseR + ((uint32_t)tid - before)] = ent;
+        }
+        uint32_t nvalid = min((uint32_t)kThreads, cur.len - t * kThreads);
+        baseL += (uint32_t)tot;
+        baseR += nvalid - (uint32_t)tot;
+        __syncthreads();
+      }
+    }
+    if (tid == 0) {
+      uint32_t q;
+      append_record(w, s, tree, cur.nodeID, (uint32_t)cov + 1u, bcode, kNone, s->bestDelta, cur.parentRec, &q);
+      s->algoBytes += 16ull * (unsigned long long)cur.m;
+      if (!s->abort) {
+        if (s->sp >= (uint32_t)kStackCap) { atomicExch(w.status, 2); s->abort = 1; }
+        else {
+          s->leafCount++;
+          NodeEnt r;
+          r.start = cur.start + nL; r.len = cur.len - nL;
+          r.m = cur.m - (uint32_t)(tneL >> 32); r.E = cur.E - (uint32_t)(tneL & 0xffffffffu);
+          r.rtsum = trtR; r.nodeID = s->leafCount; r.parentRec = q; r.depth = cur.depth + 1; r.buf = cur.buf ^ 1u;
+          w.stack[(size_t)tree * kStackCap + s->sp] = r;
+          NodeEnt l;
+          l.start = cur.start; l.len = nL; l.m = (uint32_t)(tneL >> 32); l.E = (uint32_t)(tneL & 0xffffffffu);
+          l.rtsum = trtL; l.nodeID = cur.nodeID; l.parentRec = kNone; l.depth = cur.depth + 1; l.buf = cur.buf ^ 1u;
+          s->cur = l;
+        }
+      }
+    }
+    __syncthreads();
+    if (!s->abort) {
+      // children inherit the parent's (possibly updated) permissible mask (rf.c:10725-10727)
+      uint32_t* sp = w.stackPerm + ((size_t)tree * kStackCap + s->sp) * g.pw;
+      for (int k = tid; k < g.pw; k += kThreads) sp[k] = s->perm[k];
+      __syncthreads();
+      if (tid == 0) s->sp++;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    w.nodeCount[tree] = s->nodeCount;
+    w.leafCount[tree] = s->leafCount;
+    w.candCount[tree] = s->candCount;
+    w.algoBytes[tree] = s->algoBytes;
+  }
+}
+
+}  // namespace rfslam

@@ -1,0 +1,70 @@
+// internal.h -- structures shared by the translation units of librfslam_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+
+#include "../../include/rfslam_b200.h"
+#include "common.cuh"
+
+namespace rfslam {
+
+// Device view of the resident CPIU table.  Rows are held in INTERNAL order = sorted by
+// (stratum, original row): every stratum is one contiguous row range, so a node's in-bag list
+// (kept sorted by internal row) is stratum-major and per-stratum histograms need only D bins.
+struct DevData {
+  int n, p, K;                    // rows, covariates, largest stratum id
+  const uint32_t* perm;           // [n] internal -> original row
+  const uint32_t* inv;            // [n] original -> internal row
+  const uint32_t* sb;             // [K+2] stratum k owns internal rows [sb[k], sb[k+1]); sb[0] = sb[1] = 0
+  const uint8_t*  ev;             // [n] 1 = event (response code 2)
+  const double*   rt;             // [n] risk time
+  const uint16_t* strat;          // [n] stratum id (redundant with sb; used by the sorted-walk path)
+  const void* const* codes;       // [p] rank-coded column, internal order, `width[c]` bytes per row
+  const uint8_t*  width;          // [p] 1 / 2 / 4
+  const int*      D;              // [p] number of distinct values
+  const double* const* uniq;      // [p] the distinct values, ascending: cut value = uniq[c][code]
+};
+
+}  // namespace rfslam
+
+// The opaque handle of the C-ABI.
+struct rfslam_dataset {
+  int device = 0;
+  int n = 0, p = 0, K = 0;
+  rfslam::DevData dev{};
+  std::vector<int> D;             // host mirrors
+  std::vector<uint8_t> width;
+  std::vector<void*> allocs;      // everything to cudaFree
+  std::vector<void*> codes_h;     // device pointers per column
+  std::vector<double*> uniq_h;
+  int64_t bytes = 0;
+  int max_D = 0;
+};
+
+namespace rfslam {
+
+struct GrowConfig {
+  int rule;            // 1..6
+  int mtry, nodesize, nodedepth;
+  double alpha;        // 1 / k_for_alpha^2
+  int ntree;           // forest size (seeds depend on it, rf.c:6677-6692)
+  int seed;
+  bool by_user;
+  bool want_membership;
+  bool want_membr_lists;
+  bool finalize;
+};
+
+int  dataset_build(const rfslam_grow_args* a, rfslam_dataset** out);
+void dataset_free(rfslam_dataset* ds);
+int  grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out* out);
+int  predict_forest(const rfslam_predict_args* a, rfslam_predict_out* out);
+int  score_node_impl(int rule, double k_for_alpha, int m, const double* x, const double* response,
+                     const int32_t* stratum, const double* risk_time, double* cut_value, double* delta,
+                     int32_t* n_cuts, int device);
+int  bootstrap_counts_impl(int seed, int ntree, int n, int tree, int32_t* counts, int device);
+int  validate_grow_args(const rfslam_grow_args* a, GrowConfig* cfg);
+void chain_seeds(int seed, int ntree, std::vector<int>& seedA, std::vector<int>& seedB);
+
+}  // namespace rfslam

@@ -1,0 +1,223 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+``rfsrc()`` mirrors the argument names, defaults and option packing of the reference's R entry
+point for the RF-SLAM configuration (/root/reference/R/rfsrc.R:1026-1067, :1360-1379, :1509-1652)
+and returns the native output list under the reference's own names (randomForestSRC.c:9-79);
+``predict_rfsrc()`` mirrors R/generic.predict.rfsrc.R:437-534.  Both go through the C-ABI
+(include/rfslam_b200.h) -- the same calls a cgo/JNI/.Call binding would make.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import ForestOut, GrowArgs, PredictArgs, PredictOut, _pd, _pi
+
+SPLITRULES = {f"poisson.split{k}": k for k in range(1, 7)}
+
+
+def _dp(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(_pd)
+
+
+def _ip(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(_pi)
+
+
+def _take(ptr, count, dtype):
+    if not ptr or count == 0:
+        return np.zeros(0, dtype) if ptr else None
+    return np.ctypeslib.as_array(ptr, shape=(count,)).astype(dtype, copy=True)
+
+
+class _Packed:
+    """GrowArgs plus the numpy buffers it points into (kept alive for the call)."""
+
+    def __init__(self, x, y, risk_time, stratifier, *, splitrule, ntree, mtry, nodesize, nodedepth, seed, k_for_alpha,
+                 membership, samp, sampsize, split_wt, device, tree_first, tree_step, finalize, nsplit=0, xvar_types=None):
+        x = np.ascontiguousarray(x, np.float64)
+        assert x.ndim == 2, "x must be [p, n]: p contiguous columns of n (randomForestSRC.c:22190)"
+        p, n = x.shape
+        if isinstance(splitrule, str):
+            if splitrule not in SPLITRULES:
+                raise ValueError(f"splitrule {splitrule!r}: only {sorted(SPLITRULES)} are on the accelerated path")
+            rule = SPLITRULES[splitrule]
+        else:
+            rule = int(splitrule)
+        slot = rule + 1                                           # R/rfsrc.R:1360-1379 "poisson.splitN" -> "custom(N+1)"
+        if mtry is None:
+            mtry = int(math.ceil(math.sqrt(p)))                   # R/data.utilities.R:391-405
+        if risk_time is None:
+            risk_time = np.ones(n)                                # R/rfsrc.R:1509
+        if stratifier is None:
+            stratifier = np.ones(n, np.int32)                     # R/rfsrc.R:1510
+        self.keep = dict(
+            x=x, y=np.ascontiguousarray(y, np.float64), rt=np.ascontiguousarray(risk_time, np.float64),
+            st=np.ascontiguousarray(stratifier, np.int32), rlev=np.array([2], np.int32), xlev=np.zeros(p, np.int32),
+            cat=np.ones(p, np.int32), catw=np.array([1.0]), tofix=np.zeros(1, np.int32), cw=np.ones(n), yw=np.array([1.0]),
+            xw=np.ones(p), sw=np.ascontiguousarray(np.ones(p) if split_wt is None else split_wt, np.float64))
+        k = self.keep
+        a = GrowArgs()
+        a.trace_flag = 0
+        a.seed = int(seed)
+        a.opt_low = (1 << 5) + (1 << 2)                           # forest + perf (R/utilities.R:89-103, :260-263)
+        a.opt_high = 256 * (slot - 1) + (1 << 16)                 # split.cust bits + terminal.qualts (R/utilities.R:403-459)
+        if membership:
+            a.opt_high |= (1 << 6)                                # R/utilities.R:333-348
+        if samp is not None:
+            a.opt_low |= (1 << 19) + (1 << 20)                    # bootstrap = "by.user" (R/utilities.R:43-45)
+            k["samp"] = np.ascontiguousarray(samp, np.int32)
+            assert k["samp"].shape == (ntree, n)
+            a.bootstrap = _ip(k["samp"])
+            k["bs"] = k["samp"].sum(axis=1).astype(np.int32)
+        else:
+            k["bs"] = np.full(ntree, n if sampsize is None else int(sampsize), np.int32)
+        a.split_rule = 16
+        a.nsplit = int(nsplit)
+        a.mtry = int(mtry); a.htry = 0; a.ytry = 1
+        a.node_size = int(nodesize); a.node_depth = int(nodedepth)
+        a.cr_weight_size = 0
+        a.ntree = int(ntree); a.observation_size = n; a.y_size = 1
+        self._rtype = b"C"; a.r_type = self._rtype
+        a.r_levels = _ip(k["rlev"]); a.r_data = _dp(k["y"])
+        a.x_size = p
+        self._xtype = ("".join(xvar_types) if xvar_types is not None else "R" * p).encode(); a.x_type = self._xtype
+        a.x_levels = _ip(k["xlev"])
+        a.risk_time = _dp(k["rt"]); a.stratifier = _ip(k["st"]); a.max_strat = int(k["st"].max())
+        a.var_categories = _ip(k["cat"]); a.category_weights = _dp(k["catw"]); a.n_categories = 1
+        a.to_fix = _ip(k["tofix"]); a.n_to_fix = 0
+        a.k_for_alpha = float(k_for_alpha)
+        a.max_bootstrap_size = int(k["bs"].max()); a.bootstrap_size = _ip(k["bs"])
+        a.case_weight = _dp(k["cw"]); a.x_split_stat_weight = _dp(k["sw"]); a.y_weight = _dp(k["yw"]); a.x_weight = _dp(k["xw"])
+        a.x_data = _dp(k["x"])
+        a.time_interest_size = 0; a.n_impute = 1; a.perf_block = int(ntree); a.num_threads = -1
+        a.device = int(device); a.tree_first = int(tree_first); a.tree_step = int(tree_step)
+        a.finalize_ensembles = 1 if finalize else 0
+        self.args = a
+        self.n, self.p = n, p
+
+
+def _unpack_forest(o: ForestOut) -> Dict[str, np.ndarray]:
+    n, T, NN, NL = o.n, o.ntree, o.total_nodes, o.total_leaves
+    res = {
+        "tree_ids": _take(o.tree_ids, T, np.int32),
+        "treeID": _take(o.treeID, NN, np.int32), "nodeID": _take(o.nodeID, NN, np.int32),
+        "parmID": _take(o.parmID, NN, np.int32), "contPT": _take(o.contPT, NN, np.float64),
+        "mwcpSZ": _take(o.mwcpSZ, NN, np.int32), "splitStat": _take(o.splitStat, NN, np.float64),
+        "leafCount": _take(o.leafCount, T, np.int32), "seed": _take(o.seed, T, np.int32),
+        "tnRCNT": _take(o.tnRCNT, NL, np.int32), "tnACNT": _take(o.tnACNT, NL, np.int32),
+        "tnCLAS": _take(o.tnCLAS, 2 * NL, np.int32),
+        "oobEnsbCLS": _take(o.oobEnsbCLS, 2 * n, np.float64), "allEnsbCLS": _take(o.allEnsbCLS, 2 * n, np.float64),
+        "oobEnsbDen": _take(o.oobEnsbDen, n, np.uint32), "allEnsbDen": _take(o.allEnsbDen, n, np.uint32),
+        "split_candidates": int(o.split_candidates), "algorithmic_bytes": int(o.algorithmic_bytes),
+        "grow_kernel_ms": float(o.grow_kernel_ms), "total_device_ms": float(o.total_device_ms),
+    }
+    if o.nodeMembership:
+        res["nodeMembership"] = _take(o.nodeMembership, T * n, np.int32)
+        res["bootMembership"] = _take(o.bootMembership, T * n, np.int32)
+    return res
+
+
+class ResidentCpiu:
+    """The CPIU table uploaded and rank-coded once, resident in HBM (rfslam_b200_dataset_create)."""
+
+    def __init__(self, x, y, risk_time=None, stratifier=None, *, device: int = -1):
+        self._pk = _Packed(x, y, risk_time, stratifier, splitrule=4, ntree=1, mtry=1, nodesize=1, nodedepth=-1, seed=-1,
+                           k_for_alpha=2.0, membership=False, samp=None, sampsize=None, split_wt=None, device=device,
+                           tree_first=0, tree_step=0, finalize=True)
+        self.handle = C.c_void_p()
+        capi.check(capi.lib().rfslam_b200_dataset_create(C.byref(self._pk.args), C.byref(self.handle)))
+        self.n, self.p = self._pk.n, self._pk.p
+        self.device = device
+
+    @property
+    def hbm_bytes(self) -> int:
+        return int(capi.lib().rfslam_b200_dataset_bytes(self.handle))
+
+    def close(self):
+        if self.handle:
+            capi.lib().rfslam_b200_dataset_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def grow(self, *, splitrule="poisson.split4", ntree=500, mtry=None, nodesize=5, nodedepth=-1, seed=-12345,
+             k_for_alpha=2.0, membership=False, samp=None, sampsize=None, split_wt=None, tree_first=0, tree_step=0,
+             finalize=True) -> Dict[str, np.ndarray]:
+        k = self._pk.keep
+        pk = _Packed(k["x"], k["y"], k["rt"], k["st"], splitrule=splitrule, ntree=ntree, mtry=mtry, nodesize=nodesize,
+                     nodedepth=nodedepth, seed=seed, k_for_alpha=k_for_alpha, membership=membership, samp=samp,
+                     sampsize=sampsize, split_wt=split_wt, device=self.device, tree_first=tree_first, tree_step=tree_step,
+                     finalize=finalize)
+        out = ForestOut()
+        capi.check(capi.lib().rfslam_b200_grow_resident(self.handle, C.byref(pk.args), C.byref(out)))
+        res = _unpack_forest(out)
+        capi.lib().rfslam_b200_free_forest(C.byref(out))
+        return res
+
+
+def rfsrc(x, y, risk_time=None, stratifier=None, *, splitrule="poisson.split4", ntree=500, mtry=None, nodesize=5,
+          nodedepth=-1, seed=-12345, k_for_alpha=2.0, membership=False, samp=None, sampsize=None, split_wt=None,
+          device=-1, tree_first=0, tree_step=0, finalize=True, nsplit=0, xvar_types=None) -> Dict[str, np.ndarray]:
+    """Grow an RF-SLAM forest from HOST arrays through rfslam_b200_grow (upload + grow + download).
+
+    x [p, n] float64 (p contiguous columns), y response codes 1.0 / 2.0, risk_time [n], stratifier [n]
+    (interval number >= 1); defaults follow R/rfsrc.R:1026-1067 (k_for_alpha = 2, nodedepth unlimited,
+    mtry = ceil(sqrt(p)), bootstrap by.root unless ``samp`` is given)."""
+    pk = _Packed(x, y, risk_time, stratifier, splitrule=splitrule, ntree=ntree, mtry=mtry, nodesize=nodesize,
+                 nodedepth=nodedepth, seed=seed, k_for_alpha=k_for_alpha, membership=membership, samp=samp, sampsize=sampsize,
+                 split_wt=split_wt, device=device, tree_first=tree_first, tree_step=tree_step, finalize=finalize, nsplit=nsplit,
+                 xvar_types=xvar_types)
+    out = ForestOut()
+    capi.check(capi.lib().rfslam_b200_grow(C.byref(pk.args), C.byref(out)))
+    res = _unpack_forest(out)
+    capi.lib().rfslam_b200_free_forest(C.byref(out))
+    return res
+
+
+def predict_rfsrc(forest: Dict[str, np.ndarray], fx, *, membership=True, device=-1, finalize=True) -> Dict[str, np.ndarray]:
+    """Held-out prediction of a forest in the reference's wire format (rfslam_b200_predict)."""
+    fx = np.ascontiguousarray(fx, np.float64)
+    p, m = fx.shape
+    keep = {k: np.ascontiguousarray(forest[k], np.int32) for k in ("treeID", "nodeID", "parmID", "leafCount", "tnCLAS")}
+    keep["contPT"] = np.ascontiguousarray(forest["contPT"], np.float64)
+    a = PredictArgs()
+    a.ntree = int(keep["leafCount"].size); a.x_size = p; a.total_nodes = int(keep["treeID"].size)
+    a.treeID = _ip(keep["treeID"]); a.nodeID = _ip(keep["nodeID"]); a.parmID = _ip(keep["parmID"]); a.contPT = _dp(keep["contPT"])
+    a.leafCount = _ip(keep["leafCount"]); a.tnCLAS = _ip(keep["tnCLAS"])
+    a.fobservation_size = m; a.fx_data = _dp(fx); a.want_membership = 1 if membership else 0
+    a.device = device; a.finalize_ensembles = 1 if finalize else 0
+    out = PredictOut()
+    capi.check(capi.lib().rfslam_b200_predict(C.byref(a), C.byref(out)))
+    res = {"allEnsbCLS": _take(out.allEnsbCLS, 2 * m, np.float64), "allEnsbDen": _take(out.allEnsbDen, m, np.uint32),
+           "kernel_ms": float(out.kernel_ms)}
+    if out.nodeMembership:
+        res["nodeMembership"] = _take(out.nodeMembership, a.ntree * m, np.int32)
+    capi.lib().rfslam_b200_free_predict(C.byref(out))
+    return res
+
+
+def score_node(rule: int, k_for_alpha: float, x, response, stratum, risk_time, *, device=-1):
+    """Delta for every cutpoint of one covariate in one node (rfslam_b200_score_node): what the
+    reference obtains from one customFunction call per cut (randomForestSRC.c:13404-13529)."""
+    x = np.ascontiguousarray(x, np.float64); r = np.ascontiguousarray(response, np.float64)
+    s = np.ascontiguousarray(stratum, np.int32); t = np.ascontiguousarray(risk_time, np.float64)
+    m = x.size
+    cut = np.zeros(m, np.float64); delta = np.zeros(m, np.float64); nc = C.c_int32(0)
+    capi.check(capi.lib().rfslam_b200_score_node(int(rule), float(k_for_alpha), m, _dp(x), _dp(r), _ip(s), _dp(t),
+                                                 _dp(cut), _dp(delta), C.byref(nc), device))
+    return cut[: nc.value].copy(), delta[: nc.value].copy()
+
+
+def bootstrap_counts(seed: int, ntree: int, n: int, tree: int, *, device=-1) -> np.ndarray:
+    out = np.zeros(n, np.int32)
+    capi.check(capi.lib().rfslam_b200_bootstrap_counts(seed, ntree, n, tree, _ip(out), device))
+    return out

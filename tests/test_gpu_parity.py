@@ -1,0 +1,151 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C-ABI,
+against the committed golden outputs of the unmodified reference and against the oracle port on
+fresh seeded inputs.  Bars (north_star): in-bag counts / node membership / topology bit-exact;
+split variable and cutpoint identical; hazards (ensembles) within 1e-6 relative."""
+import os
+
+import numpy as np
+import pytest
+
+import rfslam_b200
+from oracle import port
+from rfslam_b200.synth import make_cpiu
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _golden_names():
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return [os.path.basename(f) for f in parity.golden_files(here)]
+
+
+def test_library_sees_a_gpu():
+    from rfslam_b200 import capi
+    assert capi.lib().rfslam_b200_device_count() >= 1
+
+
+def test_bootstrap_counts_bit_exact(golden_dir):
+    g = parity.load_golden(os.path.join(golden_dir, "grow_r4_q64.npz"))
+    q = parity.golden_params(g)
+    for b in range(q["ntree"]):
+        got = rfslam_b200.bootstrap_counts(q["seed"], q["ntree"], q["n"], b + 1)
+        np.testing.assert_array_equal(got, g["ref_bootMembership"][b * q["n"]:(b + 1) * q["n"]])
+
+
+def test_score_node_matches_plugin_kat(golden_dir):
+    """One-cut nodes built from the reference plugin's own known answers (x = 0 on the LEFT rows)."""
+    z = np.load(os.path.join(golden_dir, "plugin_kat.npz"))
+    for i in range(int(z["count"][0])):
+        memb = z[f"memb_{i}"]
+        x = np.where(memb == 1, 0.0, 1.0)
+        for rule in range(1, 7):
+            cut, delta = rfslam_b200.score_node(rule, float(z[f"kfa_{i}"][0]), x, z[f"resp_{i}"],
+                                                z[f"strat_{i}"].astype(np.int32), z[f"rt_{i}"])
+            assert cut.size == 1 and cut[0] == 0.0
+            want = z[f"stat_{i}"][rule - 1]
+            assert delta[0] == pytest.approx(want, rel=1e-9, abs=1e-9), (i, rule, delta[0], want)
+
+
+@pytest.mark.parametrize("levels", [8, 200, 0])
+@pytest.mark.parametrize("rule", [1, 2, 3, 4, 5, 6])
+def test_score_node_every_cut_matches_oracle(rule, levels):
+    """Histogram path (<= 256 distinct values) and sorted-walk path (continuous) against one oracle
+    plugin evaluation per cut."""
+    d = make_cpiu(700, 3, levels=levels, seed=77 + rule)
+    x = d.x[2] if levels else d.x[0] + 1e-3 * np.arange(d.n)
+    cut, delta = rfslam_b200.score_node(rule, 2.0, x, d.y, d.strat, d.rt)
+    vals = np.unique(x)
+    np.testing.assert_array_equal(cut, vals[:-1])
+    for k in range(0, cut.size, max(1, cut.size // 60)):
+        memb = (x <= cut[k]).astype(np.int8)
+        want = port.poisson_stat(rule, 2.0, memb, d.y, d.strat.astype(np.float64), d.rt)
+        assert delta[k] == pytest.approx(want, rel=1e-9, abs=1e-9), (rule, levels, k)
+
+
+@pytest.mark.parametrize("name", _golden_names())
+def test_grow_matches_reference_golden(golden_dir, name):
+    g = parity.load_golden(os.path.join(golden_dir, name))
+    q = parity.golden_params(g)
+    got = rfslam_b200.rfsrc(g["x"], g["y"], g["rt"], g["strat"], splitrule=q["rule"], ntree=q["ntree"],
+                            nodesize=q["nodesize"], mtry=q["mtry"], seed=q["seed"], samp=g.get("samp"), membership=True)
+    parity.assert_forest_equal(got, parity.golden_ref_forest(g), q["n"], q["ntree"], label=name)
+
+
+@pytest.mark.parametrize("name", ["grow_r4_q64.npz", "grow_r1_cont.npz", "grow_r4_byuser.npz"])
+def test_predict_matches_reference_golden(golden_dir, name):
+    g = parity.load_golden(os.path.join(golden_dir, name))
+    q = parity.golden_params(g)
+    f = rfslam_b200.rfsrc(g["x"], g["y"], g["rt"], g["strat"], splitrule=q["rule"], ntree=q["ntree"],
+                          nodesize=q["nodesize"], mtry=q["mtry"], seed=q["seed"], samp=g.get("samp"))
+    pr = rfslam_b200.predict_rfsrc(f, g["fx"])
+    np.testing.assert_array_equal(pr["nodeMembership"], g["pred_nodeMembership"])
+    np.testing.assert_allclose(pr["allEnsbCLS"], g["pred_allEnsbCLS"], rtol=parity.HAZARD_RTOL)
+
+
+@pytest.mark.parametrize("rule,n,p,levels,nodesize,seed,dseed", [
+    (4, 6000, 14, 64, 5, -31337, 601), (1, 5000, 10, 0, 10, -2, 602), (5, 3000, 6, 8, 1, -987654, 603),
+    (3, 4000, 13, 256, 4, -800000, 604), (2, 3500, 9, 0, 20, -55, 605), (6, 4500, 20, 32, 7, -66, 606)])
+def test_grow_matches_oracle_fresh_seeds(rule, n, p, levels, nodesize, seed, dseed):
+    d = make_cpiu(n, p, levels=levels, seed=dseed)
+    ntree = 6
+    want = port.grow(d.x, d.y, d.rt, d.strat, rule=rule, ntree=ntree, nodesize=nodesize, seed=seed)
+    got = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, splitrule=rule, ntree=ntree, nodesize=nodesize, seed=seed, membership=True)
+    parity.assert_forest_equal(got, want, n, ntree, label="fresh")
+    assert got["split_candidates"] == int(want["candidates"][0])
+
+
+def test_empty_and_degenerate_nodes():
+    """No events at all -> every tree is a stump; a constant covariate is never chosen."""
+    d = make_cpiu(600, 4, levels=16, seed=9)
+    y = np.ones(d.n)
+    got = rfslam_b200.rfsrc(d.x, y, d.rt, d.strat, ntree=3, nodesize=2)
+    np.testing.assert_array_equal(got["leafCount"], [1, 1, 1])
+    x = d.x.copy(); x[1] = 3.25
+    want = port.grow(x, d.y, d.rt, d.strat, rule=4, ntree=4, nodesize=3, seed=-9)
+    got = rfslam_b200.rfsrc(x, d.y, d.rt, d.strat, splitrule=4, ntree=4, nodesize=3, seed=-9, membership=True)
+    parity.assert_forest_equal(got, want, d.n, 4, label="constant-column")
+    assert not np.any(got["parmID"] == 2)
+
+
+def test_tree_sharding_is_invariant():
+    """Tree b is identical whichever shard grows it, and partial ensembles add up."""
+    d = make_cpiu(3000, 8, levels=32, seed=10)
+    full = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=6, seed=-4, finalize=False)
+    parts = [rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=6, seed=-4, tree_first=r + 1, tree_step=2, finalize=False) for r in range(2)]
+    for r, pt in enumerate(parts):
+        np.testing.assert_array_equal(pt["tree_ids"], np.arange(r + 1, 7, 2))
+        for b in pt["tree_ids"]:
+            for k in ("nodeID", "parmID"):
+                np.testing.assert_array_equal(parity.split_tree(pt, b)[k], parity.split_tree(full, b)[k])
+    np.testing.assert_allclose(parts[0]["allEnsbCLS"] + parts[1]["allEnsbCLS"], full["allEnsbCLS"], rtol=1e-12)
+    np.testing.assert_array_equal(parts[0]["oobEnsbDen"] + parts[1]["oobEnsbDen"], full["oobEnsbDen"])
+
+
+def test_resident_dataset_and_determinism():
+    d = make_cpiu(20000, 12, levels=64, seed=11)
+    ds = rfslam_b200.ResidentCpiu(d.x, d.y, d.rt, d.strat)
+    a = ds.grow(ntree=8, nodesize=20, seed=-3)
+    b = ds.grow(ntree=8, nodesize=20, seed=-3)
+    for k in ("treeID", "nodeID", "parmID", "contPT", "tnRCNT", "tnACNT"):
+        np.testing.assert_array_equal(a[k], b[k])
+    c = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=8, nodesize=20, seed=-3)
+    np.testing.assert_array_equal(a["parmID"], c["parmID"])
+    # structural invariants that hold at any size
+    assert a["total_device_ms"] > 0 and a["split_candidates"] > 0
+    for t in range(8):
+        tr = parity.split_tree(a, t + 1)
+        assert tr["nodeID"].size == 2 * a["leafCount"][t] - 1
+    assert a["tnRCNT"].sum() == 8 * d.n           # every in-bag draw lands in exactly one leaf
+    assert a["tnACNT"].sum() == 8 * d.n           # every row reaches exactly one leaf per tree
+    ds.close()
+
+
+def test_unsupported_inputs_fail_loudly():
+    d = make_cpiu(300, 3, levels=8, seed=12)
+    with pytest.raises(rfslam_b200.RfslamError):
+        rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=2, seed=5)            # seed must be < 0
+    with pytest.raises(rfslam_b200.RfslamError):
+        rfslam_b200.rfsrc(d.x, d.y + 1.0, d.rt, d.strat, ntree=2)              # response codes outside {1, 2}
+    with pytest.raises(rfslam_b200.RfslamError):
+        rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=2, nsplit=3)          # random cut subsets: not accelerated

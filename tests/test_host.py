@@ -1,0 +1,69 @@
+"""CPU suite for the host side: the C-ABI library loads, exports every symbol the header declares,
+mirrors the reference's slot registry, and refuses to compute without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import rfslam_b200
+from rfslam_b200 import capi
+from rfslam_b200.synth import make_cpiu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "rfslam_b200.h")).read()
+    declared = set(re.findall(r"\b(rfslam_b200_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(capi.SYMBOLS)
+    L = ctypes.CDLL(capi.LIB_PATH)
+    for s in declared:
+        assert hasattr(L, s), s
+
+
+def test_slot_registry_mirrors_reference():
+    # splitCustom.c:47-62: poissonSplitN sits in CLAS_FAM slot N+1; slot 1 is the stock example rule
+    L = capi.lib()
+    L.rfslam_b200_register_defaults()
+    assert [L.rfslam_b200_rule_of_slot(0, s) for s in range(1, 9)] == [0, 1, 2, 3, 4, 5, 6, 0]
+    assert L.rfslam_b200_rule_of_slot(1, 2) == 0          # regression slots abort in the reference too
+    assert L.rfslam_b200_register_this(4, 0, 9) == 0
+    assert L.rfslam_b200_rule_of_slot(0, 9) == 4
+    assert L.rfslam_b200_register_this(4, 1, 9) != 0
+    L.rfslam_b200_register_defaults()
+    assert L.rfslam_b200_rule_of_slot(0, 9) == 0
+
+
+def test_struct_layout_matches_header_sizes():
+    # the ctypes mirrors must have the C layout: pointer-sized alignment, no stray fields
+    assert ctypes.sizeof(capi.GrowArgs) % 8 == 0
+    assert capi.GrowArgs.x_data.offset % 8 == 0
+    assert ctypes.sizeof(capi.ForestOut) == 4 + 4 + 8 + 8 + 20 * 8 + 8 + 8 + 8 + 8
+
+
+@pytest.mark.skipif(capi.lib().rfslam_b200_device_count() > 0, reason="a GPU is present")
+def test_no_cpu_fallback():
+    d = make_cpiu(200, 3, levels=8, seed=1)
+    with pytest.raises(rfslam_b200.RfslamError) as e:
+        rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=2)
+    assert e.value.code == 2
+
+
+def test_argument_validation_precedes_device_work():
+    d = make_cpiu(200, 3, levels=8, seed=1)
+    with pytest.raises(rfslam_b200.RfslamError) as e:
+        rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=2, seed=7)
+    assert e.value.code == 1 and "seed" in str(e.value).lower()
+    with pytest.raises(ValueError):
+        rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=2, splitrule="gini")
+
+
+def test_synth_is_deterministic_and_shaped():
+    a = make_cpiu(5000, 9, levels=64)
+    b = make_cpiu(5000, 9, levels=64)
+    assert a.x.shape == (9, 5000) and np.array_equal(a.x, b.x) and np.array_equal(a.y, b.y)
+    assert set(np.unique(a.y)) <= {1.0, 2.0} and a.strat.min() >= 1 and a.strat.max() <= 16 and (a.rt > 0).all()
+    assert 0.01 < (a.y == 2).mean() < 0.15
+    assert max(np.unique(c).size for c in a.x) <= 64
