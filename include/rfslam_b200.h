@@ -209,6 +209,11 @@ int  rfslam_b200_score_node(int rule, double k_for_alpha, int m, const double *x
 /* Chain-A replay only (rf.c:529-533): in-bag counts of tree `tree` (1-based) of an ntree forest. */
 int  rfslam_b200_bootstrap_counts(int seed, int ntree, int n, int tree, int32_t *counts /* [n] */, int device);
 
+/* Diagnostics: with RFSLAM_PROFILE set in the environment the tree kernel accumulates clock64()
+   cycles per phase (slots 0..11), per node-size class log2(entries) (slots 16..47) and node counts
+   per class pair (slots 48..63), summed over the trees of the last grow call. Returns slots written. */
+int  rfslam_b200_last_profile(uint64_t *slots, int capacity);
+
 const char *rfslam_b200_last_error(void);
 const char *rfslam_b200_version(void);
 int  rfslam_b200_device_count(void);

@@ -1,0 +1,24 @@
+import time, sys, numpy as np
+sys.path.insert(0, '.')
+import rfslam_b200
+from rfslam_b200.synth import make_cpiu
+n, p, L = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+ntree = int(sys.argv[4]); nodesize = int(sys.argv[5])
+t=time.time(); d = make_cpiu(n, p, levels=L); print("gen", time.time()-t, "events", (d.y==2).mean(), "D", [int(np.unique(c[:100000]).size) for c in d.x][:12], flush=True)
+t=time.time(); ds = rfslam_b200.ResidentCpiu(d.x, d.y, d.rt, d.strat); print("resident", time.time()-t, ds.hbm_bytes/1e6, "MB", flush=True)
+for rep in range(2):
+    t=time.time(); f = ds.grow(ntree=ntree, nodesize=nodesize, seed=-12345); dt=time.time()-t
+    print(f"grow wall {dt:.3f}s kernel {f['grow_kernel_ms']:.1f}ms total_dev {f['total_device_ms']:.1f}ms trees/s(kernel) {ntree/(f['grow_kernel_ms']/1e3):.1f} nodes {f['treeID'].size} cand {f['split_candidates']} cand/s {f['split_candidates']/(f['grow_kernel_ms']/1e3):.3e} algoGB {f['algorithmic_bytes']/1e9:.2f} GB/s {f['algorithmic_bytes']/1e9/(f['grow_kernel_ms']/1e3):.1f}", flush=True)
+import ctypes as C
+from rfslam_b200 import capi
+buf = (C.c_uint64*64)()
+k = capi.lib().rfslam_b200_last_profile(buf, 64)
+if k:
+    names = ["root","gate+draw","segpos+zero","hist","flush","strat_tot","track","sortcand","part_count","part_scatter","leaf","split_book"]
+    tot = sum(buf[i] for i in range(12))
+    print("phase cycles (sum over trees), total %.3e" % tot)
+    for i,nm in enumerate(names): print(f"  {nm:14s} {buf[i]:.3e} {100*buf[i]/max(tot,1):5.1f}%")
+    print("node time by log2(len):")
+    for c in range(0,28): 
+        if buf[16+c]: print(f"  2^{c}: {buf[16+c]:.3e} {100*buf[16+c]/max(tot,1):5.1f}%")
+    print("node counts by class pair:", [int(buf[48+i]) for i in range(14)])

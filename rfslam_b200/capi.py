@@ -68,7 +68,7 @@ SYMBOLS = [
     "rfslam_b200_dataset_destroy", "rfslam_b200_dataset_bytes", "rfslam_b200_predict", "rfslam_b200_free_predict",
     "rfslam_b200_rule_of_slot", "rfslam_b200_register_this", "rfslam_b200_register_defaults",
     "rfslam_b200_score_node", "rfslam_b200_bootstrap_counts", "rfslam_b200_last_error", "rfslam_b200_version",
-    "rfslam_b200_device_count",
+    "rfslam_b200_device_count", "rfslam_b200_last_profile",
 ]
 
 _lib = None
@@ -107,6 +107,7 @@ def lib():
         L.rfslam_b200_last_error.restype = C.c_char_p; L.rfslam_b200_last_error.argtypes = []
         L.rfslam_b200_version.restype = C.c_char_p; L.rfslam_b200_version.argtypes = []
         L.rfslam_b200_device_count.restype = C.c_int; L.rfslam_b200_device_count.argtypes = []
+        L.rfslam_b200_last_profile.restype = C.c_int; L.rfslam_b200_last_profile.argtypes = [C.POINTER(C.c_uint64), C.c_int]
         _lib = L
     return _lib
 

@@ -8,6 +8,8 @@
 
 namespace rfslam {
 
+extern std::vector<unsigned long long> g_last_profile;
+
 static thread_local char g_err[1024] = "";
 
 void set_error(const char* fmt, ...) {
@@ -115,6 +117,12 @@ int rfslam_b200_score_node(int rule, double k_for_alpha, int m, const double* x,
                            int32_t* n_cuts, int device) {
   if (!x || !response || !stratum || !risk_time || !cut_value || !delta || !n_cuts) { set_error("null arguments"); return RFSLAM_EINVAL; }
   return score_node_impl(rule, k_for_alpha, m, x, response, stratum, risk_time, cut_value, delta, n_cuts, device);
+}
+
+int rfslam_b200_last_profile(uint64_t* slots, int capacity) {
+  int k = 0;
+  for (; k < capacity && k < (int)g_last_profile.size(); k++) slots[k] = g_last_profile[k];
+  return k;
 }
 
 int rfslam_b200_bootstrap_counts(int seed, int ntree, int n, int tree, int32_t* counts, int device) {

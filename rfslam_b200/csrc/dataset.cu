@@ -240,7 +240,23 @@ int dataset_build(const rfslam_grow_args* a, rfslam_dataset** out) {
       RF_CUDA(cudaMemcpy(d_width, ds->width.data(), (size_t)p, cudaMemcpyHostToDevice));
       RF_CUDA(cudaMemcpy(d_D, ds->D.data(), (size_t)p * sizeof(int), cudaMemcpyHostToDevice));
 
+      // dominant risk time: the modal value of a sample (any value is correct; the mode is fastest)
+      double rt_mode = a->risk_time[0];
+      {
+        std::vector<double> smp;
+        const int step = std::max(1, n / 65536);
+        for (int i = 0; i < n; i += step) smp.push_back(a->risk_time[i]);
+        std::sort(smp.begin(), smp.end());
+        size_t bestLen = 0;
+        for (size_t i = 0; i < smp.size();) {
+          size_t j = i;
+          while (j < smp.size() && smp[j] == smp[i]) j++;
+          if (j - i > bestLen) { bestLen = j - i; rt_mode = smp[i]; }
+          i = j;
+        }
+      }
       DevData& d = ds->dev;
+      d.rt_mode = rt_mode;
       d.n = n; d.p = p; d.K = ds->K;
       d.perm = perm; d.inv = inv; d.sb = sb; d.ev = ev; d.rt = rt; d.strat = strat;
       d.codes = (const void* const*)d_codes; d.width = d_width; d.D = d_D; d.uniq = (const double* const*)d_uniq;

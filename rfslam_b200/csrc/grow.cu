@@ -25,6 +25,8 @@ void chain_seeds(int seed, int ntree, std::vector<int>& seedA, std::vector<int>&
     }
 }
 
+std::vector<unsigned long long> g_last_profile;
+
 namespace {
 
 // K1a: chain-A replay, one warp per tree with lane 0 walking the (inherently sequential)
@@ -295,6 +297,9 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     d_cand.alloc(B); d_algo.alloc(B); d_nodeOff.alloc(B + 1); d_leafOff.alloc(B + 1);
     const uint32_t maxChunksPerTree = (uint32_t)((worstNodes + kRecChunk - 1) / kRecChunk) + 1;
     d_ctab.alloc((size_t)B * maxChunksPerTree);
+    const bool profile = getenv("RFSLAM_PROFILE") != nullptr;
+    DevBuf<unsigned long long> d_prof;
+    if (profile) { d_prof.alloc((size_t)B * kProfSlots); g_last_profile.assign(kProfSlots, 0ull); }
 
     for (int b0 = 0; b0 < T; b0 += B) {
       const int nb = std::min(B, T - b0);
@@ -336,6 +341,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         w.pool = d_pool.p; w.statPool = d_statPool.p; w.poolChunks = (uint32_t)poolChunks; w.poolCursor = d_cursor.p;
         w.ctab = d_ctab.p; w.maxChunksPerTree = maxChunksPerTree; w.nodeCount = d_nodeCount.p; w.leafCount = d_leafCount.p;
         w.candCount = d_cand.p; w.algoBytes = d_algo.p; w.status = d_status.p;
+        w.prof = profile ? d_prof.p : nullptr;
         DevData dd = ds->dev;
         RF_CUDA(cudaEventRecord(ev1));
         rfslam_grow_kernel<<<nb, kThreads, smem>>>(dd, g, w);
@@ -350,6 +356,11 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         }
         if (status == 2) { set_error("tree deeper than %d pending nodes", kStackCap); throw CudaFail{RFSLAM_ENOSUP}; }
 
+        if (profile) {
+          std::vector<unsigned long long> hp((size_t)nb * kProfSlots);
+          RF_CUDA(cudaMemcpy(hp.data(), d_prof.p, hp.size() * 8, cudaMemcpyDeviceToHost));
+          for (int t = 0; t < nb; t++) for (int k = 0; k < kProfSlots; k++) if (k != 12 && k != 13) g_last_profile[k] += hp[(size_t)t * kProfSlots + k];
+        }
         // ---- offsets, compaction, traversal ----
         std::vector<uint32_t> hNodes(nb), hLeaves(nb);
         std::vector<unsigned long long> hCand(nb), hAlgo(nb), nodeOff(nb + 1, 0), leafOff(nb + 1, 0);

@@ -45,6 +45,8 @@ struct NodeEnt {        // a pending node of the DFS
 };
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr int kSmallMax = 512;      // nodes with <= this many entries are scored entirely out of shared memory
+constexpr int kProfSlots = 64;   // 0..15 phases, 16..47 node time by log2(len), 48..63 node count by log2(len)/2
 
 struct GrowParams {
   int rule, mtry, nodesize, nodedepth;
@@ -75,6 +77,7 @@ struct GrowWork {
   unsigned long long* candCount; // [ntrees]
   unsigned long long* algoBytes; // [ntrees]
   int* status;                   // 0 ok, 1 record pool exhausted, 2 DFS stack overflow
+  unsigned long long* prof;      // optional [ntrees][kProfSlots] clock64 sums per phase / node-size class
   // single-node scoring mode (rfslam_b200_score_node): emit every cut instead of tracking
   double* sinkCut; double* sinkDelta; int* sinkCount;
 };
@@ -96,15 +99,24 @@ struct GrowShared {
   int cutsSeen;
   // scratch for block reductions / scans
   double scrD[kWarps]; unsigned long long scrU[kWarps]; int scrI[kWarps];
-  // sorted-walk tile
-  double tileTL[kThreads]; double tileTR[kThreads]; double tileDelta[kThreads];
-  uint32_t tileKey[kThreads]; uint8_t tileCut[kThreads];
-  uint32_t radixBase[256];
   uint32_t nodeCount, leafCount, sp;
   unsigned long long candCount, algoBytes;
   int abort;
   int ptotReady;
+  int nAct; double statPnode; int isSmall; int poolSize;
+  int trkMaxBin[kMaxCand]; double trkMax[kMaxCand]; int trkClean[kMaxCand]; int trkNp[kMaxCand]; int trkLast[kMaxCand];
+  unsigned long long prof[kProfSlots];
+  long long tmark;
 };
+
+#define RF_PROF(slot)                                                                  \
+  do {                                                                                 \
+    if (w.prof && threadIdx.x == 0) {                                                  \
+      long long now__ = clock64();                                                     \
+      s->prof[slot] += (unsigned long long)(now__ - s->tmark);                         \
+      s->tmark = now__;                                                                \
+    }                                                                                  \
+  } while (0)
 
 __device__ __forceinline__ Rec* rec_ptr(const GrowWork& w, int tree, uint32_t q) {
   uint32_t c = w.ctab[(size_t)tree * w.maxChunksPerTree + q / kRecChunk];
@@ -129,9 +141,13 @@ __device__ __forceinline__ int block_incl_scan_max(int v, int* scratch) {
 // dynamic shared memory carve-up
 struct GrowSmem {
   double *sL, *sR, *hT, *hW, *statP;
-  uint32_t *hN, *hE, *pres;
+  uint32_t *hN, *hE, *hNx, *hEx, *pres;
+  // sorted-walk tile arrays (alias the small-node staging: the two paths never overlap in time)
+  double *tileTL, *tileTR, *tileDelta; uint32_t *tileKey, *radixBase; uint8_t* tileCut;
   uint32_t *segpos, *PN, *PE, *cN, *cE;
   double *PT, *PW, *cT, *cW, *cTL, *cTR;
+  // small-node staging: the node's entries and everything scoring needs about them
+  uint32_t* smEnt; double* smT; uint8_t *smMult, *smE, *smS, *smCodes;
   GrowShared* s;
 };
 
@@ -140,10 +156,11 @@ __host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K) {
   size_t b = 0;
   b += (size_t)ncmax * kHistBins * 8 * 4;      // sL sR hT hW
   b += (size_t)ncmax * 8;                      // statP
-  b += (size_t)ncmax * kHistBins * 4 * 2;      // hN hE
+  b += (size_t)ncmax * kHistBins * 4 * 4;      // hN hE hNx hEx
   b += (size_t)ncmax * 8 * 4;                  // pres
   b += KS * 8 * 6;                             // PT PW cT cW cTL cTR
   b += KS * 4 * 5;                             // segpos PN PE cN cE
+  b += (size_t)kSmallMax * (8 + 4 + 3 + (size_t)ncmax) + 16;  // small-node staging (>= the 8.5 KB of sorted-walk tiles aliased onto it)
   b = (b + 15) & ~(size_t)15;
   b += sizeof(GrowShared);
   return b + 16;
@@ -162,8 +179,23 @@ __device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K) {
   uint32_t* u = (uint32_t*)d;
   m.hN = u; u += (size_t)ncmax * kHistBins;
   m.hE = u; u += (size_t)ncmax * kHistBins;
+  m.hNx = u; u += (size_t)ncmax * kHistBins;
+  m.hEx = u; u += (size_t)ncmax * kHistBins;
   m.pres = u; u += (size_t)ncmax * 8;
   m.segpos = u; u += KS; m.PN = u; u += KS; m.PE = u; u += KS; m.cN = u; u += KS; m.cE = u; u += KS;
+  {
+    uintptr_t al = ((uintptr_t)u + 7) & ~(uintptr_t)7;
+    u = (uint32_t*)al;
+    m.tileTL = (double*)u; m.tileTR = m.tileTL + kThreads; m.tileDelta = m.tileTR + kThreads;
+    m.tileKey = (uint32_t*)(m.tileDelta + kThreads); m.radixBase = m.tileKey + kThreads; m.tileCut = (uint8_t*)(m.radixBase + 256);
+  }
+  m.smEnt = u; u += kSmallMax;
+  uint8_t* b8 = (uint8_t*)u;
+  m.smMult = b8; b8 += kSmallMax; m.smE = b8; b8 += kSmallMax; m.smS = b8; b8 += kSmallMax;
+  m.smCodes = b8; b8 += (size_t)kSmallMax * ncmax;
+  uintptr_t pt = ((uintptr_t)b8 + 7) & ~(uintptr_t)7;
+  m.smT = (double*)pt;
+  u = (uint32_t*)(m.smT + kSmallMax);
   uintptr_t p = ((uintptr_t)u + 15) & ~(uintptr_t)15;
   m.s = (GrowShared*)p;
   return m;
@@ -207,7 +239,71 @@ struct NodeCtx {
   int Kloop;
 };
 
-// ---- per-stratum flush of the joint histograms (step 3) -------------------------------------
+// one in-bag entry into one candidate's histogram: native 32-bit shared atomics for the counts;
+// the f64 exposure sums (CAS loops in shared memory on sm_100a) only see rows whose risk time
+// differs from the table's dominant value t0 -- in CPIU data that is the last interval of a person.
+__device__ __forceinline__ void hist_add(const GrowSmem& m, int idx, uint32_t mult, uint32_t e, bool unit, bool isT0, double ft) {
+  atomicAdd(&m.hN[idx], mult);
+  if (e) atomicAdd(&m.hE[idx], mult);
+  if (!unit && !isT0) {
+    atomicAdd(&m.hNx[idx], mult);
+    atomicAdd(&m.hT[idx], ft);
+    if (e) { atomicAdd(&m.hEx[idx], mult); atomicAdd(&m.hW[idx], ft); }
+  }
+}
+
+// ---- per-stratum flush of one candidate's histogram (step 3), executed by one warp ----------
+// tN/tE/tT/tW are the stratum's totals in this node; the histogram is left clean.
+__device__ __forceinline__ void flush_candidate(const NodeCtx& c, int ci, uint32_t tN, uint32_t tE, double tT, double tW,
+                                                double termP, bool updatePres) {
+  GrowSmem& m = c.m;
+  GrowShared* s = m.s;
+  const int lane = lane_id();
+  const int Dc = s->candD[ci];
+  const int nch = (Dc + 31) >> 5;
+  uint32_t* hN = m.hN + ci * kHistBins; uint32_t* hE = m.hE + ci * kHistBins;
+  uint32_t* hNx = m.hNx + ci * kHistBins; uint32_t* hEx = m.hEx + ci * kHistBins;
+  double* hT = m.hT + ci * kHistBins;   double* hW = m.hW + ci * kHistBins;
+  const double t0 = c.d.rt_mode;
+  const bool active = tE > 0;
+  uint32_t cN = 0, cE = 0; double cT = 0.0, cW = 0.0;     // carries (warp-uniform)
+  double cTL = 0.0, cTR = termP;
+  for (int ch = 0; ch < nch; ch++) {
+    int bin = (ch << 5) + lane;
+    uint32_t vN = 0, vE = 0; double vT = 0.0, vW = 0.0;
+    if (bin < Dc) {
+      vN = hN[bin]; vE = hE[bin];
+      if (!c.unit) {                                               // exposure = t0 * (rows at the dominant risk time) + the rest
+        vT = t0 * (double)(vN - hNx[bin]) + hT[bin];
+        vW = t0 * (double)(vE - hEx[bin]) + hW[bin];
+      }
+      hN[bin] = 0; hE[bin] = 0; hNx[bin] = 0; hEx[bin] = 0; hT[bin] = 0.0; hW[bin] = 0.0;   // leave the histogram clean
+    }
+    unsigned own = __ballot_sync(0xffffffffu, vN > 0);
+    if (updatePres && lane == 0 && own) m.pres[ci * 8 + ch] |= own;
+    if (!active) continue;
+    if (c.unit) { vT = (double)vN; vW = (double)vE; }
+    uint32_t iN = warp_incl_scan(vN) + cN, iE = warp_incl_scan(vE) + cE;
+    double iT = warp_incl_scan(vT) + cT, iW = warp_incl_scan(vW) + cW;
+    double tL = 0.0, tR = 0.0;
+    if (vN > 0) {
+      tL = side_term(c.bayes, (double)iE, (double)iN, iT, iW, c.g.alpha, c.beta);
+      tR = side_term(c.bayes, (double)(tE - iE), (double)(tN - iN), tT - iT, tW - iW, c.g.alpha, c.beta);
+    }
+    // fill-forward from the nearest lane <= me that holds rows of this stratum
+    unsigned le = own & (0xffffffffu >> (31 - lane));
+    int src = le ? (31 - __clz(le)) : -1;
+    double fL = __shfl_sync(0xffffffffu, tL, src < 0 ? 0 : src);
+    double fR = __shfl_sync(0xffffffffu, tR, src < 0 ? 0 : src);
+    if (src < 0) { fL = cTL; fR = cTR; }
+    if (bin < Dc) { m.sL[ci * kHistBins + bin] += fL; m.sR[ci * kHistBins + bin] += fR; }
+    cN = __shfl_sync(0xffffffffu, iN, 31); cE = __shfl_sync(0xffffffffu, iE, 31);
+    cT = __shfl_sync(0xffffffffu, iT, 31); cW = __shfl_sync(0xffffffffu, iW, 31);
+    cTL = __shfl_sync(0xffffffffu, fL, 31); cTR = __shfl_sync(0xffffffffu, fR, 31);
+  }
+}
+
+// large-node variant: totals come from the histogram itself
 __device__ inline void flush_stratum(const NodeCtx& c, int nc) {
   GrowSmem& m = c.m;
   GrowShared* s = m.s;
@@ -216,60 +312,38 @@ __device__ inline void flush_stratum(const NodeCtx& c, int nc) {
     if (!s->candHist[ci]) continue;
     const int Dc = s->candD[ci];
     const int nch = (Dc + 31) >> 5;
-    uint32_t* hN = m.hN + ci * kHistBins; uint32_t* hE = m.hE + ci * kHistBins;
-    double* hT = m.hT + ci * kHistBins;   double* hW = m.hW + ci * kHistBins;
-    // stratum totals
+    const uint32_t* hN = m.hN + ci * kHistBins; const uint32_t* hE = m.hE + ci * kHistBins;
+    const uint32_t* hNx = m.hNx + ci * kHistBins; const uint32_t* hEx = m.hEx + ci * kHistBins;
+    const double* hT = m.hT + ci * kHistBins;   const double* hW = m.hW + ci * kHistBins;
+    const double t0 = c.d.rt_mode;
     uint32_t tN = 0, tE = 0; double tT = 0.0, tW = 0.0;
     for (int ch = 0; ch < nch; ch++) {
       int bin = (ch << 5) + lane;
-      if (bin < Dc) { tN += hN[bin]; tE += hE[bin]; if (!c.unit) { tT += hT[bin]; tW += hW[bin]; } }
+      if (bin < Dc) {
+        tN += hN[bin]; tE += hE[bin];
+        if (!c.unit) { tT += t0 * (double)(hN[bin] - hNx[bin]) + hT[bin]; tW += t0 * (double)(hE[bin] - hEx[bin]) + hW[bin]; }
+      }
     }
     tN = warp_sum(tN); tE = warp_sum(tE);
     if (c.unit) { tT = (double)tN; tW = (double)tE; } else { tT = warp_sum(tT); tW = warp_sum(tW); }
     if (tN == 0) continue;
-    const bool active = tE > 0;
     double termP = 0.0;
-    if (active) {
+    if (tE > 0) {
       termP = side_term(c.bayes, (double)tE, (double)tN, tT, tW, c.g.alpha, c.beta);
       if (lane == 0) m.statP[ci] += termP;
     }
-    uint32_t cN = 0, cE = 0; double cT = 0.0, cW = 0.0;     // carries (warp-uniform)
-    double cTL = 0.0, cTR = termP;
-    for (int ch = 0; ch < nch; ch++) {
-      int bin = (ch << 5) + lane;
-      uint32_t vN = 0, vE = 0; double vT = 0.0, vW = 0.0;
-      if (bin < Dc) {
-        vN = hN[bin]; vE = hE[bin];
-        if (!c.unit) { vT = hT[bin]; vW = hW[bin]; }
-        hN[bin] = 0; hE[bin] = 0; hT[bin] = 0.0; hW[bin] = 0.0;      // leave the histogram clean
-      }
-      unsigned own = __ballot_sync(0xffffffffu, vN > 0);
-      if (lane == 0 && own) m.pres[ci * 8 + ch] |= own;
-      if (!active) continue;
-      if (c.unit) { vT = (double)vN; vW = (double)vE; }
-      uint32_t iN = warp_incl_scan(vN) + cN, iE = warp_incl_scan(vE) + cE;
-      double iT = warp_incl_scan(vT) + cT, iW = warp_incl_scan(vW) + cW;
-      double tL = 0.0, tR = 0.0;
-      if (vN > 0) {
-        tL = side_term(c.bayes, (double)iE, (double)iN, iT, iW, c.g.alpha, c.beta);
-        tR = side_term(c.bayes, (double)(tE - iE), (double)(tN - iN), tT - iT, tW - iW, c.g.alpha, c.beta);
-      }
-      // fill-forward from the nearest lane <= me that holds rows of this stratum
-      unsigned le = own & (0xffffffffu >> (31 - lane));
-      int src = le ? (31 - __clz(le)) : -1;
-      double fL = __shfl_sync(0xffffffffu, tL, src < 0 ? 0 : src);
-      double fR = __shfl_sync(0xffffffffu, tR, src < 0 ? 0 : src);
-      if (src < 0) { fL = cTL; fR = cTR; }
-      if (bin < Dc) { m.sL[ci * kHistBins + bin] += fL; m.sR[ci * kHistBins + bin] += fR; }
-      cN = __shfl_sync(0xffffffffu, iN, 31); cE = __shfl_sync(0xffffffffu, iE, 31);
-      cT = __shfl_sync(0xffffffffu, iT, 31); cW = __shfl_sync(0xffffffffu, iW, 31);
-      cTL = __shfl_sync(0xffffffffu, fL, 31); cTR = __shfl_sync(0xffffffffu, fR, 31);
-    }
+    flush_candidate(c, ci, tN, tE, tT, tW, termP, true);
   }
 }
 
-// ---- tracker over one histogram candidate (warp 0 only) -------------------------------------
-__device__ inline void track_hist(const NodeCtx& c, int ci) {
+// ---- tracker (step 4): exact replay of updateMaximumSplit (rf.c:15471-15551) ------------------
+// The tracker can only ever select strict prefix-max records, so when no cut BEFORE the first
+// occurrence of a candidate's maximum M lies within EPSILON of M, the candidate's final selection
+// is (M, first position) if M beats the incoming best by more than EPSILON and nothing otherwise.
+// track_summary (run by the warp that scored the candidate, all candidates in parallel) reduces a
+// candidate to {#cuts, M, position, "needs the exact walk"}; track_combine (warp 0) then replays
+// the candidates in draw order, walking the exact sequential chain only for near-ties and NaN.
+__device__ inline void track_summary(const NodeCtx& c, int ci) {
   GrowSmem& m = c.m;
   GrowShared* s = m.s;
   const int lane = lane_id();
@@ -280,20 +354,60 @@ __device__ inline void track_hist(const NodeCtx& c, int ci) {
   int last = word ? (lane * 32 + 31 - __clz(word)) : -1;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  if (np < 2) { if (lane == 0) { s->trkNp[ci] = np; s->trkClean[ci] = 1; } return; }
   const int cov = s->candCov[ci];
-  if (np < 2) {                       // constant in this node: not permissible below (rf.c:15004-15007)
-    if (lane == 0) s->perm[cov >> 5] &= ~(1u << (cov & 31));
-    return;
-  }
   const double wgt = c.g.split_weight ? c.g.split_weight[cov] : 1.0;
   const double statP = m.statP[ci];
+  double M = -INFINITY; int pos = 0x7fffffff; bool anyNan = false;
+  for (int ch = 0; ch < nch; ch++) {
+    int bin = (ch << 5) + lane;
+    uint32_t wd = m.pres[ci * 8 + ch];
+    bool present = ((wd >> lane) & 1u) && bin != last;
+    if (present) {
+      double val = (m.sL[ci * kHistBins + bin] + m.sR[ci * kHistBins + bin] - statP) * wgt;
+      m.sL[ci * kHistBins + bin] = val;                     // keep delta for the combine / exact walk
+      if (val != val) anyNan = true;
+      if (val > M) { M = val; pos = bin; }
+    }
+  }
+  anyNan = __any_sync(0xffffffffu, anyNan);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double oM = __shfl_xor_sync(0xffffffffu, M, o); int oP = __shfl_xor_sync(0xffffffffu, pos, o);
+    if (oM > M || (oM == M && oP < pos)) { M = oM; pos = oP; }
+  }
+  bool near = false;                                        // an earlier cut within EPSILON of the maximum?
+  if (!anyNan) {
+    for (int ch = 0; ch <= (pos >> 5); ch++) {
+      int bin = (ch << 5) + lane;
+      uint32_t wd = m.pres[ci * 8 + ch];
+      bool present = ((wd >> lane) & 1u) && bin != last && bin < pos;
+      if (present && !((M - m.sL[ci * kHistBins + bin]) > kEpsilon)) near = true;
+    }
+    near = __any_sync(0xffffffffu, near);
+  }
+  if (lane == 0) {
+    s->trkNp[ci] = np; s->trkMax[ci] = M; s->trkMaxBin[ci] = pos; s->trkClean[ci] = (!anyNan && !near) ? 1 : 0;
+    s->trkLast[ci] = last;
+  }
+}
+
+// exact chain walk of one candidate (warp 0); sL holds the deltas (track_summary)
+__device__ inline void track_exact(const NodeCtx& c, int ci) {
+  GrowSmem& m = c.m;
+  GrowShared* s = m.s;
+  const int lane = lane_id();
+  const int Dc = s->candD[ci];
+  const int nch = (Dc + 31) >> 5;
+  const int last = s->trkLast[ci];
+  const int cov = s->candCov[ci];
   int have = s->have; double best = s->bestDelta; int bestBin = -1;
   int emitted = s->cutsSeen;
   for (int ch = 0; ch < nch; ch++) {
     int bin = (ch << 5) + lane;
     uint32_t wd = m.pres[ci * 8 + ch];
     bool present = ((wd >> lane) & 1u) && bin != last;
-    double val = present ? (m.sL[ci * kHistBins + bin] + m.sR[ci * kHistBins + bin] - statP) * wgt : 0.0;
+    double val = present ? m.sL[ci * kHistBins + bin] : 0.0;
     if (c.w.sinkDelta) {
       unsigned pm = __ballot_sync(0xffffffffu, present);
       if (present) {
@@ -308,26 +422,49 @@ __device__ inline void track_hist(const NodeCtx& c, int ci) {
     if (sel >= 0) bestBin = (ch << 5) + sel;
   }
   if (lane == 0) {
-    s->candCount += (unsigned long long)(np - 1);
     s->cutsSeen = emitted;
     if (bestBin >= 0) { s->have = 1; s->bestDelta = best; s->bestCand = ci; s->bestCode = (uint32_t)bestBin; }
   }
+  __syncwarp();
+}
+
+// warp 0: one histogram candidate, in draw order
+__device__ inline void track_combine_one(const NodeCtx& c, int ci) {
+  GrowShared* s = c.m.s;
+  const int lane = lane_id();
+  const int np = s->trkNp[ci];
+  const int cov = s->candCov[ci];
+  if (np < 2) {                       // constant in this node: not permissible below (rf.c:15004-15007)
+    if (lane == 0) s->perm[cov >> 5] &= ~(1u << (cov & 31));
+    __syncwarp();
+    return;
+  }
+  if (lane == 0) s->candCount += (unsigned long long)(np - 1);
+  if (s->trkClean[ci] && !c.w.sinkDelta) {
+    if (lane == 0) {
+      const double M = s->trkMax[ci];
+      if (!s->have || (M - s->bestDelta) > kEpsilon) { s->have = 1; s->bestDelta = M; s->bestCand = ci; s->bestCode = (uint32_t)s->trkMaxBin[ci]; }
+    }
+    __syncwarp();
+    return;
+  }
+  track_exact(c, ci);
 }
 
 // ---- sorted-walk path for covariates with more than kHistBins distinct values ----------------
 __device__ inline void radix_pass(const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout,
-                                  uint32_t len, int shift, GrowShared* s) {
+                                  uint32_t len, int shift, GrowShared* s, uint32_t* rbase) {
   const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
   __syncthreads();
-  s->radixBase[tid] = 0;
+  rbase[tid] = 0;
   __syncthreads();
-  for (uint32_t i = tid; i < len; i += kThreads) atomicAdd(&s->radixBase[(kin[i] >> shift) & 255u], 1u);
+  for (uint32_t i = tid; i < len; i += kThreads) atomicAdd(&rbase[(kin[i] >> shift) & 255u], 1u);
   __syncthreads();
-  uint32_t cnt = s->radixBase[tid];
+  uint32_t cnt = rbase[tid];
   unsigned long long tot;
   unsigned long long inc = block_incl_scan<unsigned long long>((unsigned long long)cnt, s->scrU, tot);
   __syncthreads();
-  s->radixBase[tid] = (uint32_t)(inc - cnt);
+  rbase[tid] = (uint32_t)(inc - cnt);
   __syncthreads();
   const uint32_t ntiles = (len + kThreads - 1) / kThreads;
   for (uint32_t t = 0; t < ntiles; t++) {
@@ -341,9 +478,9 @@ __device__ inline void radix_pass(const uint32_t* kin, const uint32_t* vin, uint
       if (wid == wv) {
         unsigned peers = __match_any_sync(0xffffffffu, dgt);
         uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-        if (valid) pos = s->radixBase[dgt] + rank;
+        if (valid) pos = rbase[dgt] + rank;
         __syncwarp();
-        if (valid && rank == 0) s->radixBase[dgt] += __popc(peers);
+        if (valid && rank == 0) rbase[dgt] += __popc(peers);
       }
       __syncthreads();
     }
@@ -397,7 +534,7 @@ __device__ inline void sort_candidate(const NodeCtx& c, int ci, uint32_t len) {
   int npass = (bits + 7) >> 3;
   uint32_t *ks = kA, *vs = vA, *kd = kB, *vd = vB;
   for (int ps = 0; ps < npass; ps++) {
-    radix_pass(ks, vs, kd, vd, len, 8 * ps, s);
+    radix_pass(ks, vs, kd, vd, len, 8 * ps, s, m.radixBase);
     uint32_t* t1 = ks; ks = kd; kd = t1;
     uint32_t* t2 = vs; vs = vd; vd = t2;
   }
@@ -443,13 +580,13 @@ __device__ inline void sort_candidate(const NodeCtx& c, int ci, uint32_t len) {
       uint32_t LN = (uint32_t)(ine >> 32) + m.cN[a], LE = (uint32_t)(ine & 0xffffffffu) + m.cE[a];
       double LT = iT + m.cT[a], LW = iW + m.cW[a];
       if (f) {
-        s->tileTL[tid] = side_term(c.bayes, (double)LE, (double)LN, LT, LW, c.g.alpha, c.beta);
-        s->tileTR[tid] = side_term(c.bayes, (double)(m.PE[a] - LE), (double)(m.PN[a] - LN), m.PT[a] - LT, m.PW[a] - LW, c.g.alpha, c.beta);
+        m.tileTL[tid] = side_term(c.bayes, (double)LE, (double)LN, LT, LW, c.g.alpha, c.beta);
+        m.tileTR[tid] = side_term(c.bayes, (double)(m.PE[a] - LE), (double)(m.PN[a] - LN), m.PT[a] - LT, m.PW[a] - LW, c.g.alpha, c.beta);
       }
       int src = block_incl_scan_max(f ? tid : -1, s->scrI);
       __syncthreads();
-      double myL = (src >= 0) ? s->tileTL[src] : m.cTL[a];
-      double myR = (src >= 0) ? s->tileTR[src] : m.cTR[a];
+      double myL = (src >= 0) ? m.tileTL[src] : m.cTL[a];
+      double myR = (src >= 0) ? m.tileTR[src] : m.cTR[a];
       if (cut) { accL += myL; accR += myR; }
       __syncthreads();
       if (tid == kThreads - 1) {
@@ -457,26 +594,26 @@ __device__ inline void sort_candidate(const NodeCtx& c, int ci, uint32_t len) {
       }
       __syncthreads();
     }
-    s->tileDelta[tid] = cut ? (accL + accR - statP) * wgt : 0.0;
-    s->tileCut[tid] = cut ? 1 : 0;
-    s->tileKey[tid] = key;
+    m.tileDelta[tid] = cut ? (accL + accR - statP) * wgt : 0.0;
+    m.tileCut[tid] = cut ? 1 : 0;
+    m.tileKey[tid] = key;
     __syncthreads();
     if (wid == 0) {
       for (int ch = 0; ch < kWarps; ch++) {
         int q = (ch << 5) + lane;
-        bool present = s->tileCut[q] != 0;
-        double val = s->tileDelta[q];
+        bool present = m.tileCut[q] != 0;
+        double val = m.tileDelta[q];
         unsigned pm = __ballot_sync(0xffffffffu, present);
         if (c.w.sinkDelta && present) {
           int k = emitted + __popc(pm & ((1u << lane) - 1u));
           c.w.sinkDelta[k] = val;
-          c.w.sinkCut[k] = c.d.uniq[cov][s->tileKey[q]];
+          c.w.sinkCut[k] = c.d.uniq[cov][m.tileKey[q]];
         }
         emitted += __popc(pm);
         totalCuts += __popc(pm);
         int sel;
         track_chunk(present, val, have, best, sel);
-        if (sel >= 0) { bestKey = s->tileKey[(ch << 5) + sel]; gotBest = 1; }
+        if (sel >= 0) { bestKey = m.tileKey[(ch << 5) + sel]; gotBest = 1; }
       }
     }
     __syncthreads();
@@ -493,6 +630,139 @@ __device__ inline void sort_candidate(const NodeCtx& c, int ci, uint32_t len) {
   __syncthreads();
 }
 
+// ---- small nodes (<= kSmallMax entries, histogram candidates only) ---------------------------
+// One batched prefetch brings the node's entries, their event / risk time / stratum and the codes
+// of every candidate into shared memory (a single exposed memory latency instead of one per
+// stratum); after that every warp scores its own candidate with warp-level synchronisation only,
+// visiting just the strata that contain events in this node (all other cells contribute exactly 0
+// to every rule, see side_term) -- their rows matter only for which cuts exist (presence bits).
+__device__ inline void score_small(NodeCtx& c) {
+  GrowSmem& m = c.m;
+  GrowShared* s = m.s;
+  const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+  const int nc = s->nc;
+  const uint32_t len = s->cur.len;
+  const DevData& d = c.d;
+  const GrowWork& w = c.w;
+  // segpos = first entry of a stratum, cN = one past its last entry (both 0 when absent)
+  for (int k = tid; k <= c.Kloop + 1; k += kThreads) { m.segpos[k] = 0; m.cN[k] = 0; }
+  for (int i = tid; i < nc * 8; i += kThreads) m.pres[i] = 0u;
+  if (tid == 0) { s->have = 0; s->bestDelta = 0.0; s->bestCand = -1; s->bestCode = 0; s->cutsSeen = 0; }
+  __syncthreads();
+  RF_PROF(2);
+  {
+    // every global load of the node is issued before the first shared-memory store, for both of
+    // this thread's entries, so the whole prefetch exposes two dependent latencies (entry -> row data)
+    static_assert(kSmallMax == 2 * kThreads, "prefetch is unrolled for two entries per thread");
+    uint32_t ent[2], ev2[2] = {0u, 0u}, st2[2] = {0u, 0u}; double tv2[2] = {0.0, 0.0};
+    uint32_t pk[2][kMaxCand / 4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};   // byte codes, four per register
+#pragma unroll
+    for (int u = 0; u < 2; u++) { const uint32_t j = tid + u * kThreads; ent[u] = j < len ? c.list[j] : 0u; }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const uint32_t j = tid + u * kThreads;
+      const uint32_t row = ent[u] & kRowMask;
+      if (j < len) {
+        ev2[u] = d.ev[row]; tv2[u] = d.rt[row]; st2[u] = c.strat ? (uint32_t)d.strat[row] - 1u : 0u;
+#pragma unroll
+        for (int ci = 0; ci < kMaxCand; ci++)
+          if (ci < nc) pk[u][ci >> 2] |= load_code(s->candPtr[ci], s->candW[ci], row) << (8 * (ci & 3));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const uint32_t j = tid + u * kThreads;
+      if (j < len) {
+        m.smEnt[j] = ent[u];
+        m.smMult[j] = (uint8_t)((ent[u] >> kRowBits) + 1u);
+        m.smE[j] = (uint8_t)ev2[u];
+        m.smT[j] = tv2[u];
+        m.smS[j] = (uint8_t)st2[u];
+#pragma unroll
+        for (int ci = 0; ci < kMaxCand; ci++)
+          if (ci < nc) {
+            const uint32_t code = (pk[u][ci >> 2] >> (8 * (ci & 3))) & 255u;
+            m.smCodes[ci * kSmallMax + j] = (uint8_t)code;
+            atomicOr(&m.pres[ci * 8 + (code >> 5)], 1u << (code & 31u));
+          }
+      }
+    }
+  }
+  __syncthreads();
+  RF_PROF(3);
+  for (uint32_t j = tid; j < len; j += kThreads) {
+    const int sj = m.smS[j] + 1;
+    if (j == 0 || m.smS[j - 1] + 1 != sj) m.segpos[sj] = j;
+    if (j == len - 1 || m.smS[j + 1] + 1 != sj) m.cN[sj] = j + 1;
+  }
+  __syncthreads();
+  // per-stratum totals, one warp per stratum
+  for (int a = 1 + wid; a <= c.Kloop; a += kWarps) {
+    const uint32_t b0 = m.segpos[a], b1 = m.cN[a];
+    uint32_t tN = 0, tE = 0; double tT = 0.0, tW = 0.0;
+    for (uint32_t i = b0 + lane; i < b1; i += 32) {
+      const uint32_t mu = m.smMult[i];
+      const double ft = c.unit ? (double)mu : (double)mu * m.smT[i];
+      tN += mu; tT += ft;
+      if (m.smE[i]) { tE += mu; tW += ft; }
+    }
+    tN = warp_sum(tN); tE = warp_sum(tE); tT = warp_sum(tT); tW = warp_sum(tW);
+    if (lane == 0) {
+      m.PN[a] = tN; m.PE[a] = tE; m.PT[a] = tT; m.PW[a] = tW;
+      m.cTR[a] = (tE > 0) ? side_term(c.bayes, (double)tE, (double)tN, tT, tW, c.g.alpha, c.beta) : 0.0;
+    }
+  }
+  __syncthreads();
+  // ascending list of the strata that contain events (kept in cE[]) and the parent statistic
+  if (wid == 0) {
+    int nAct = 0;
+    for (int base = 0; base < c.Kloop; base += 32) {
+      const int a = base + lane + 1;
+      const bool act = a <= c.Kloop && m.PE[a] > 0;
+      const unsigned bm = __ballot_sync(0xffffffffu, act);
+      if (act) m.cE[nAct + __popc(bm & ((1u << lane) - 1u))] = (uint32_t)a;
+      nAct += __popc(bm);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      double sp = 0.0;
+      for (int ia = 0; ia < nAct; ia++) sp += m.cTR[m.cE[ia]];
+      s->nAct = nAct; s->statPnode = sp;
+    }
+  }
+  __syncthreads();
+  RF_PROF(5);
+  const int nAct = s->nAct;
+  for (int ci = wid; ci < nc; ci += kWarps) {
+    const int Dc = s->candD[ci];
+    for (int b = lane; b < Dc; b += 32) { m.sL[ci * kHistBins + b] = 0.0; m.sR[ci * kHistBins + b] = 0.0; }
+    const uint8_t* cptr = m.smCodes + ci * kSmallMax;
+    __syncwarp();
+    for (int ia = 0; ia < nAct; ia++) {
+      const int a = (int)m.cE[ia];
+      const uint32_t b0 = m.segpos[a], b1 = m.cN[a];
+      for (uint32_t i = b0 + lane; i < b1; i += 32) {
+        const int idx = ci * kHistBins + (int)cptr[i];
+        const uint32_t mu = m.smMult[i];
+        const double tv = m.smT[i];
+        hist_add(m, idx, mu, m.smE[i], c.unit, tv == d.rt_mode, (double)mu * tv);
+      }
+      __syncwarp();
+      flush_candidate(c, ci, m.PN[a], m.PE[a], m.PT[a], m.PW[a], m.cTR[a], false);
+      __syncwarp();
+    }
+    if (lane == 0) m.statP[ci] = s->statPnode;
+    __syncwarp();
+    track_summary(c, ci);
+  }
+  __syncthreads();
+  RF_PROF(4);
+  if (wid == 0)
+    for (int ci = 0; ci < nc; ci++) track_combine_one(c, ci);
+  __syncthreads();
+  RF_PROF(6);
+}
+
 // ---- score all drawn candidates of the current node (steps 2-4) ------------------------------
 __device__ inline void score_node(const DevData& d, const GrowParams& g, const GrowWork& w, GrowSmem& m, int tree) {
   GrowShared* s = m.s;
@@ -505,6 +775,14 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
   if (bayes) beta = g.alpha / (((double)cur.m + (double)cur.E) / cur.rtsum);
   const int Kloop = strat ? d.K : 1;
   NodeCtx c{d, g, w, m, list, tree, bayes, unit, strat, beta, Kloop};
+
+  bool allHist = true;
+  for (int ci = 0; ci < nc; ci++) if (!s->candHist[ci]) allHist = false;
+  if (allHist && cur.len <= (uint32_t)kSmallMax) {
+    if (tid == 0) s->isSmall = 1;
+    score_small(c);
+    return;
+  }
 
   // segment boundaries of the strata inside this node's (row-sorted) entry list
   if (strat) {
@@ -525,44 +803,55 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
   if (tid < nc) m.statP[tid] = 0.0;
   if (tid == 0) { s->have = 0; s->bestDelta = 0.0; s->bestCand = -1; s->bestCode = 0; s->cutsSeen = 0; }
   __syncthreads();
+  RF_PROF(2);
 
   bool anyHist = false, anySort = false;
   for (int ci = 0; ci < nc; ci++) { if (s->candHist[ci]) anyHist = true; else anySort = true; }
 
   if (anyHist) {
+    unsigned hmask = 0u;
+    for (int ci = 0; ci < nc; ci++) if (s->candHist[ci]) hmask |= 1u << ci;
     for (int k = 1; k <= Kloop; k++) {
       const uint32_t s0 = m.segpos[k], s1 = m.segpos[k + 1];
       if (s0 == s1) continue;
       for (uint32_t i = s0 + tid; i < s1; i += kThreads) {
         const uint32_t ent = list[i];
         const uint32_t row = ent & kRowMask, mult = (ent >> kRowBits) + 1u;
+        // issue every gather of this entry before the first shared-memory atomic
         const uint32_t e = d.ev[row];
-        const double ft = unit ? 0.0 : (double)mult * d.rt[row];
-        for (int ci = 0; ci < nc; ci++) {
-          if (!s->candHist[ci]) continue;
-          const uint32_t code = load_code(s->candPtr[ci], s->candW[ci], row);
-          const int idx = ci * kHistBins + (int)code;
-          atomicAdd(&m.hN[idx], mult);
-          if (e) atomicAdd(&m.hE[idx], mult);
-          if (!unit) {
-            atomicAdd(&m.hT[idx], ft);
-            if (e) atomicAdd(&m.hW[idx], ft);
-          }
-        }
+        const double tv = unit ? 0.0 : d.rt[row];
+        uint32_t pk[kMaxCand / 4] = {0u, 0u, 0u, 0u};              // histogram codes are bytes: four per register
+#pragma unroll
+        for (int ci = 0; ci < kMaxCand; ci++)
+          if (ci < nc && ((hmask >> ci) & 1u))
+            pk[ci >> 2] |= load_code(s->candPtr[ci], s->candW[ci], row) << (8 * (ci & 3));
+        const bool isT0 = tv == d.rt_mode;
+        const double ft = (double)mult * tv;
+#pragma unroll
+        for (int ci = 0; ci < kMaxCand; ci++)
+          if (ci < nc && ((hmask >> ci) & 1u))
+            hist_add(m, ci * kHistBins + (int)((pk[ci >> 2] >> (8 * (ci & 3))) & 255u), mult, e, unit, isT0, ft);
       }
       __syncthreads();
+      RF_PROF(3);
       flush_stratum(c, nc);
       __syncthreads();
+      RF_PROF(4);
     }
   }
-  if (anySort) stratum_totals(c, cur.len);
+  if (anySort) { stratum_totals(c, cur.len); RF_PROF(5); }
+  for (int ci = warp_id(); ci < nc; ci += kWarps)
+    if (s->candHist[ci]) track_summary(c, ci);
+  __syncthreads();
 
   for (int ci = 0; ci < nc; ci++) {
     if (s->candHist[ci]) {
-      if (warp_id() == 0) track_hist(c, ci);
+      if (warp_id() == 0) track_combine_one(c, ci);
       __syncthreads();
+      RF_PROF(6);
     } else {
       sort_candidate(c, ci, cur.len);
+      RF_PROF(7);
     }
   }
   __syncthreads();
@@ -570,9 +859,7 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
 
 // ---- thread 0: draw the node's candidate covariates (step 1) ---------------------------------
 __device__ inline void draw_candidates(const DevData& d, const GrowParams& g, GrowShared* s) {
-  int size = 0;
-  for (int k = 0; k < d.p; k++)
-    if ((s->perm[k >> 5] >> (k & 31)) & 1u) s->pool[size++] = (uint16_t)k;     // ascending (rf.c:8209-8213)
+  int size = s->poolSize;                                                         // built by warp 0, ascending (rf.c:8209-8213)
   int count = 0, nc = 0;
   while (count < g.mtry && size > 0) {
     count++;
@@ -581,10 +868,6 @@ __device__ inline void draw_candidates(const DevData& d, const GrowParams& g, Gr
     s->pool[slot - 1] = s->pool[size - 1];                                       // swap-remove (rf.c:8306)
     size--;
     s->candCov[nc] = cov;
-    s->candD[nc] = d.D[cov];
-    s->candW[nc] = d.width[cov];
-    s->candPtr[nc] = d.codes[cov];
-    s->candHist[nc] = d.D[cov] <= kHistBins;
     nc++;
   }
   s->nc = nc;
@@ -621,8 +904,10 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
   const uint16_t* cnt = w.cnt + (size_t)tree * w.cntStride;
 
   // ---- clean histograms (flushes keep them clean afterwards) ----
-  for (int i = tid; i < g.ncmax * kHistBins; i += kThreads) { m.hN[i] = 0; m.hE[i] = 0; m.hT[i] = 0.0; m.hW[i] = 0.0; }
+  for (int i = tid; i < g.ncmax * kHistBins; i += kThreads) { m.hN[i] = 0; m.hE[i] = 0; m.hNx[i] = 0; m.hEx[i] = 0; m.hT[i] = 0.0; m.hW[i] = 0.0; }
   if (tid == 0) {
+    for (int k = 0; k < kProfSlots; k++) s->prof[k] = 0;
+    s->tmark = clock64();
     ran1_seed(s->rng, w.seedB[tree]);
     s->nodeCount = 0; s->leafCount = 1; s->sp = 0; s->candCount = 0; s->algoBytes = 0; s->abort = 0;
   }
@@ -667,6 +952,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     }
     __syncthreads();
   }
+  RF_PROF(0);
 
   const bool bayes = rule_is_bayes(g.rule);
   // ---- depth-first growth (rf.c:21460-21792) ----
@@ -674,6 +960,14 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     __syncthreads();
     if (s->abort) break;
     const NodeEnt cur = s->cur;
+    if (w.prof && tid == 0) {
+      long long now = clock64();
+      if (s->prof[13]) s->prof[16 + s->prof[12]] += (unsigned long long)now - s->prof[13];
+      int cls = 31 - __clz(cur.len | 1u);
+      s->prof[48 + (cls >> 1)] += 1ull;
+      s->prof[12] = (unsigned long long)cls;
+      s->prof[13] = (unsigned long long)now;
+    }
     // node gate (rf.c:15354-15371) and purity (rf.c:6391-6416): both classes present
     bool attempt = (cur.m >= 2u * (uint32_t)g.nodesize) && (g.nodedepth < 0 || cur.depth < (uint32_t)g.nodedepth);
     if (attempt) {
@@ -686,11 +980,31 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     if (tid == 0) { s->nc = 0; s->have = 0; }
     __syncthreads();
     if (attempt) {
+      if (warp_id() == 0) {                                // permissible covariates, ascending, by ballot compaction
+        int size = 0;
+        for (int base = 0; base < d.p; base += 32) {
+          const int k = base + lane_id();
+          const bool ok = k < d.p && ((s->perm[base >> 5] >> lane_id()) & 1u);
+          const unsigned bm = __ballot_sync(0xffffffffu, ok);
+          if (ok) s->pool[size + __popc(bm & ((1u << lane_id()) - 1u))] = (uint16_t)k;
+          size += __popc(bm);
+        }
+        if (lane_id() == 0) s->poolSize = size;
+        __syncwarp();
+      }
       if (tid == 0) {
         draw_candidates(d, g, s);
         s->algoBytes += (unsigned long long)cur.m * (12ull * (unsigned long long)s->nc + 20ull);
       }
       __syncthreads();
+      if (tid < s->nc) {                                   // candidate metadata: one parallel round of loads
+        const int cov = s->candCov[tid];
+        const int Dv = d.D[cov];
+        s->candD[tid] = Dv; s->candW[tid] = d.width[cov]; s->candPtr[tid] = d.codes[cov]; s->candHist[tid] = Dv <= kHistBins;
+      }
+      if (tid == 0) s->isSmall = 0;
+      __syncthreads();
+      RF_PROF(1);
       if (s->nc > 0) score_node(d, g, w, m, tree);
     }
     __syncthreads();
@@ -713,6 +1027,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
         }
       }
       __syncthreads();
+      RF_PROF(10);
       if (s->abort == 2) break;
       if (!s->abort) {
         const uint32_t* sp = w.stackPerm + ((size_t)tree * kStackCap + s->sp) * g.pw;
@@ -727,20 +1042,31 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     const void* ptr = s->candPtr[bc]; const int wd = s->candW[bc]; const int cov = s->candCov[bc];
     const uint32_t* src = w.lists + ((size_t)tree * 2 + cur.buf) * n + cur.start;
     uint32_t* dst = w.lists + ((size_t)tree * 2 + (cur.buf ^ 1u)) * n + cur.start;
+    const bool small = s->isSmall != 0;
+    const uint8_t* cptr = m.smCodes + bc * kSmallMax;
     // pass 1: sizes of the left child
     unsigned long long cL = 0, neL = 0; double rtL = 0.0, rtR = 0.0;
     for (uint32_t i = tid; i < cur.len; i += kThreads) {
-      uint32_t ent = src[i];
-      uint32_t row = ent & kRowMask, mult = (ent >> kRowBits) + 1u;
-      bool left = load_code(ptr, wd, row) <= bcode;          // LEFT iff cut - x >= 0 (rf.c:15194)
-      uint32_t e = d.ev[row];
+      uint32_t ent, e; bool left; double rtv = 0.0;
+      if (small) {
+        ent = m.smEnt[i]; left = cptr[i] <= bcode; e = m.smE[i];
+        if (bayes) rtv = m.smT[i];
+      } else {
+        ent = src[i];
+        const uint32_t row = ent & kRowMask;
+        left = load_code(ptr, wd, row) <= bcode;             // LEFT iff cut - x >= 0 (rf.c:15194)
+        e = d.ev[row];
+        if (bayes) rtv = d.rt[row];
+      }
+      const uint32_t mult = (ent >> kRowBits) + 1u;
       if (left) { cL++; neL += ((unsigned long long)mult << 32) | (unsigned long long)(e ? mult : 0u); }
-      if (bayes) { double v = (double)mult * d.rt[row]; if (left) rtL += v; else rtR += v; }
+      if (bayes) { double v = (double)mult * rtv; if (left) rtL += v; else rtR += v; }
     }
     const uint32_t nL = (uint32_t)block_sum<unsigned long long>(cL, s->scrU);
     const unsigned long long tneL = block_sum<unsigned long long>(neL, s->scrU);
     double trtL = 0.0, trtR = 0.0;
     if (bayes) { trtL = block_sum<double>(rtL, s->scrD); trtR = block_sum<double>(rtR, s->scrD); }
+    RF_PROF(8);
     // pass 2: stable scatter
     {
       uint32_t baseL = 0, baseR = 0;
@@ -748,8 +1074,11 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
       for (uint32_t t = 0; t < ntiles; t++) {
         uint32_t i = t * kThreads + tid;
         bool valid = i < cur.len;
-        uint32_t ent = valid ? src[i] : 0u;
-        bool left = valid && (load_code(ptr, wd, ent & kRowMask) <= bcode);
+        uint32_t ent = 0u; bool left = false;
+        if (valid) {
+          if (small) { ent = m.smEnt[i]; left = cptr[i] <= bcode; }
+          else { ent = src[i]; left = load_code(ptr, wd, ent & kRowMask) <= bcode; }
+        }
         unsigned long long tot;
         unsigned long long inc = block_incl_scan<unsigned long long>(left ? 1ull : 0ull, s->scrU, tot);
         uint32_t before = (uint32_t)inc - (left ? 1u : 0u);
@@ -763,6 +1092,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
         __syncthreads();
       }
     }
+    RF_PROF(9);
     if (tid == 0) {
       uint32_t q;
       append_record(w, s, tree, cur.nodeID, (uint32_t)cov + 1u, bcode, kNone, s->bestDelta, cur.parentRec, &q);
@@ -791,9 +1121,11 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
       __syncthreads();
       if (tid == 0) s->sp++;
     }
+    RF_PROF(11);
   }
   __syncthreads();
   if (tid == 0) {
+    if (w.prof) for (int k = 0; k < kProfSlots; k++) w.prof[(size_t)tree * kProfSlots + k] = s->prof[k];
     w.nodeCount[tree] = s->nodeCount;
     w.leafCount[tree] = s->leafCount;
     w.candCount[tree] = s->candCount;

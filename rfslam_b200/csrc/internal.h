@@ -24,6 +24,7 @@ struct DevData {
   const uint8_t*  width;          // [p] 1 / 2 / 4
   const int*      D;              // [p] number of distinct values
   const double* const* uniq;      // [p] the distinct values, ascending: cut value = uniq[c][code]
+  double rt_mode;                 // the table's dominant risk time (exposure = rt_mode * count + exceptions)
 };
 
 }  // namespace rfslam
