@@ -14,8 +14,8 @@ from rfslam_b200 import capi
 buf = (C.c_uint64*64)()
 k = capi.lib().rfslam_b200_last_profile(buf, 64)
 if k:
-    names = ["root","gate+draw","segpos+zero","hist","flush","strat_tot","track","sortcand","part_count","part_scatter","leaf","split_book"]
-    tot = sum(buf[i] for i in range(12))
+    names = ["root","gate+draw","segpos+zero","hist","flush","strat_tot","track","sortcand","part_count","part_scatter","leaf","split_book","x","x","small_list","x15"]
+    tot = sum(buf[i] for i in list(range(12))+[14,15])
     print("phase cycles (sum over trees), total %.3e" % tot)
     for i,nm in enumerate(names): print(f"  {nm:14s} {buf[i]:.3e} {100*buf[i]/max(tot,1):5.1f}%")
     print("node time by log2(len):")

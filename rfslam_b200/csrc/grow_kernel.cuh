@@ -650,41 +650,65 @@ __device__ inline void score_small(NodeCtx& c) {
   if (tid == 0) { s->have = 0; s->bestDelta = 0.0; s->bestCand = -1; s->bestCode = 0; s->cutsSeen = 0; }
   __syncthreads();
   RF_PROF(2);
+  for (uint32_t j = tid; j < len; j += kThreads) {
+    const uint32_t ent = c.list[j];
+    m.smEnt[j] = ent;
+    m.smMult[j] = (uint8_t)((ent >> kRowBits) + 1u);
+  }
+  __syncthreads();
+  RF_PROF(14);
+  // one warp per column (nc candidate code columns + event, risk time, stratum); each lane keeps
+  // four gathers in flight before it touches shared memory again
   {
-    // every global load of the node is issued before the first shared-memory store, for both of
-    // this thread's entries, so the whole prefetch exposes two dependent latencies (entry -> row data)
-    static_assert(kSmallMax == 2 * kThreads, "prefetch is unrolled for two entries per thread");
-    uint32_t ent[2], ev2[2] = {0u, 0u}, st2[2] = {0u, 0u}; double tv2[2] = {0.0, 0.0};
-    uint32_t pk[2][kMaxCand / 4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};   // byte codes, four per register
+    const int ncols = nc + 3;
+    for (int col = wid; col < ncols; col += kWarps) {
+      if (col < nc) {
+        const uint8_t* __restrict__ ptr = (const uint8_t*)s->candPtr[col];
+        const int nwords = (s->candD[col] + 31) >> 5;
+        uint32_t acc = 0u;                                   // lane w accumulates presence word w
+        for (uint32_t j0 = 0; j0 < len; j0 += 128) {
+          uint32_t v[4];
 #pragma unroll
-    for (int u = 0; u < 2; u++) { const uint32_t j = tid + u * kThreads; ent[u] = j < len ? c.list[j] : 0u; }
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const uint32_t j = tid + u * kThreads;
-      const uint32_t row = ent[u] & kRowMask;
-      if (j < len) {
-        ev2[u] = d.ev[row]; tv2[u] = d.rt[row]; st2[u] = c.strat ? (uint32_t)d.strat[row] - 1u : 0u;
-#pragma unroll
-        for (int ci = 0; ci < kMaxCand; ci++)
-          if (ci < nc) pk[u][ci >> 2] |= load_code(s->candPtr[ci], s->candW[ci], row) << (8 * (ci & 3));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const uint32_t j = tid + u * kThreads;
-      if (j < len) {
-        m.smEnt[j] = ent[u];
-        m.smMult[j] = (uint8_t)((ent[u] >> kRowBits) + 1u);
-        m.smE[j] = (uint8_t)ev2[u];
-        m.smT[j] = tv2[u];
-        m.smS[j] = (uint8_t)st2[u];
-#pragma unroll
-        for (int ci = 0; ci < kMaxCand; ci++)
-          if (ci < nc) {
-            const uint32_t code = (pk[u][ci >> 2] >> (8 * (ci & 3))) & 255u;
-            m.smCodes[ci * kSmallMax + j] = (uint8_t)code;
-            atomicOr(&m.pres[ci * 8 + (code >> 5)], 1u << (code & 31u));
+          for (int k = 0; k < 4; k++) {
+            const uint32_t j = j0 + k * 32 + lane;
+            v[k] = (j < len) ? (uint32_t)ptr[m.smEnt[j] & kRowMask] : 0xFFFFu;
           }
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const uint32_t j = j0 + k * 32 + lane;
+            if (j < len) m.smCodes[col * kSmallMax + j] = (uint8_t)v[k];
+            for (int wd2 = 0; wd2 < nwords; wd2++) {
+              const uint32_t bits = ((v[k] >> 5) == (uint32_t)wd2) ? (1u << (v[k] & 31u)) : 0u;
+              const uint32_t red = __reduce_or_sync(0xffffffffu, bits);
+              if (lane == wd2) acc |= red;
+            }
+          }
+        }
+        if (lane < nwords) m.pres[col * 8 + lane] = acc;
+      } else if (col == nc) {
+        for (uint32_t j0 = 0; j0 < len; j0 += 128) {
+          uint32_t v[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) { const uint32_t j = j0 + k * 32 + lane; v[k] = (j < len) ? (uint32_t)d.ev[m.smEnt[j] & kRowMask] : 0u; }
+#pragma unroll
+          for (int k = 0; k < 4; k++) { const uint32_t j = j0 + k * 32 + lane; if (j < len) m.smE[j] = (uint8_t)v[k]; }
+        }
+      } else if (col == nc + 1) {
+        for (uint32_t j0 = 0; j0 < len; j0 += 128) {
+          double v[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) { const uint32_t j = j0 + k * 32 + lane; v[k] = (j < len) ? d.rt[m.smEnt[j] & kRowMask] : 0.0; }
+#pragma unroll
+          for (int k = 0; k < 4; k++) { const uint32_t j = j0 + k * 32 + lane; if (j < len) m.smT[j] = v[k]; }
+        }
+      } else {
+        for (uint32_t j0 = 0; j0 < len; j0 += 128) {
+          uint32_t v[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) { const uint32_t j = j0 + k * 32 + lane; v[k] = (j < len && c.strat) ? (uint32_t)d.strat[m.smEnt[j] & kRowMask] - 1u : 0u; }
+#pragma unroll
+          for (int k = 0; k < 4; k++) { const uint32_t j = j0 + k * 32 + lane; if (j < len) m.smS[j] = (uint8_t)v[k]; }
+        }
       }
     }
   }
@@ -811,6 +835,9 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
   if (anyHist) {
     unsigned hmask = 0u;
     for (int ci = 0; ci < nc; ci++) if (s->candHist[ci]) hmask |= 1u << ci;
+    const uint8_t* __restrict__ hptr[kMaxCand];
+#pragma unroll
+    for (int ci = 0; ci < kMaxCand; ci++) hptr[ci] = (ci < nc) ? (const uint8_t*)s->candPtr[ci] : nullptr;
     for (int k = 1; k <= Kloop; k++) {
       const uint32_t s0 = m.segpos[k], s1 = m.segpos[k + 1];
       if (s0 == s1) continue;
@@ -820,17 +847,24 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
         // issue every gather of this entry before the first shared-memory atomic
         const uint32_t e = d.ev[row];
         const double tv = unit ? 0.0 : d.rt[row];
-        uint32_t pk[kMaxCand / 4] = {0u, 0u, 0u, 0u};              // histogram codes are bytes: four per register
-#pragma unroll
-        for (int ci = 0; ci < kMaxCand; ci++)
-          if (ci < nc && ((hmask >> ci) & 1u))
-            pk[ci >> 2] |= load_code(s->candPtr[ci], s->candW[ci], row) << (8 * (ci & 3));
         const bool isT0 = tv == d.rt_mode;
         const double ft = (double)mult * tv;
 #pragma unroll
-        for (int ci = 0; ci < kMaxCand; ci++)
-          if (ci < nc && ((hmask >> ci) & 1u))
-            hist_add(m, ci * kHistBins + (int)((pk[ci >> 2] >> (8 * (ci & 3))) & 255u), mult, e, unit, isT0, ft);
+        for (int half = 0; half < kMaxCand; half += 8) {
+          if (half < nc) {
+            uint32_t raw[8];                                       // histogram candidates are byte-coded
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              const int ci = half + q;
+              raw[q] = (ci < nc && ((hmask >> ci) & 1u)) ? (uint32_t)hptr[ci][row] : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              const int ci = half + q;
+              if (ci < nc && ((hmask >> ci) & 1u)) hist_add(m, ci * kHistBins + (int)raw[q], mult, e, unit, isT0, ft);
+            }
+          }
+        }
       }
       __syncthreads();
       RF_PROF(3);
