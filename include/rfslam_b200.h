@@ -132,6 +132,7 @@ typedef struct rfslam_forest_out {
   int64_t   algorithmic_bytes; /* sum over attempted nodes of B_score + B_part + 4n per tree */
   double    grow_kernel_ms;    /* device time of the tree-growing kernel(s), CUDA events */
   double    total_device_ms;   /* device time of the whole call incl. bootstrap and ensembles */
+  int64_t   kernel_launches;   /* kernels of this library launched by the call */
 } rfslam_forest_out;
 
 int  rfslam_b200_grow(const rfslam_grow_args *args, rfslam_forest_out *out);

@@ -103,6 +103,7 @@ T* dalloc(rfslam_dataset* ds, size_t count, bool resident = true) {
 void dataset_free(rfslam_dataset* ds) {
   if (!ds) return;
   cudaSetDevice(ds->device);
+  ds->pool.release_all();
   for (void* p : ds->allocs) cudaFree(p);
   delete ds;
 }

@@ -101,9 +101,11 @@ __global__ void membership_kernel(DevData d, int ntrees, const unsigned long lon
                                   const int32_t* nodeID, const int32_t* parmID, const uint32_t* code, const uint32_t* right,
                                   const int32_t* tnRCNT, const int32_t* tnCLAS, const uint16_t* cnt,
                                   int32_t* tnACNT, double* allNum, double* oobNum, uint32_t* allDen, uint32_t* oobDen,
-                                  int32_t* nodeMembership, int32_t* bootMembership, int batchFirst, size_t cntStride) {
+                                  int32_t* nodeMembership, int32_t* bootMembership, int batchFirst, size_t cntStride,
+                                  unsigned long long* pathSum) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d.n) return;
+  unsigned long long steps = 0;
+  if (i < d.n) {
   const uint32_t orig = d.perm[i];
   double a1 = 0.0, a2 = 0.0, o1 = 0.0, o2 = 0.0; uint32_t od = 0;
   for (int t = 0; t < ntrees; t++) {
@@ -113,6 +115,7 @@ __global__ void membership_kernel(DevData d, int ntrees, const unsigned long lon
     while ((pm = parmID[q]) != 0) {
       uint32_t cd = load_code(d.codes[pm - 1], d.width[pm - 1], (uint32_t)i);
       q = (cd <= code[q]) ? q + 1 : off + right[q];
+      steps++;
     }
     const int leaf = nodeID[q];
     const unsigned long long li = leafOff[t] + (unsigned long long)leaf - 1ull;
@@ -127,6 +130,10 @@ __global__ void membership_kernel(DevData d, int ntrees, const unsigned long lon
   }
   allNum[orig] += a1; allNum[(size_t)d.n + orig] += a2; allDen[orig] += (uint32_t)ntrees;
   oobNum[orig] += o1; oobNum[(size_t)d.n + orig] += o2; oobDen[orig] += od;
+  }
+  // every internal node on a row's path routes that row once: sum of path lengths = sum over split nodes of their all-row size
+  steps = warp_sum(steps);
+  if ((threadIdx.x & 31) == 0) atomicAdd(pathSum, steps);
 }
 
 __global__ void finalize_kernel(double* num, const uint32_t* den, int n) {
@@ -137,16 +144,22 @@ __global__ void finalize_kernel(double* num, const uint32_t* den, int n) {
   }
 }
 
+// device scratch; with a pool (the resident dataset's) buffers are recycled across grow calls
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t count = 0;
+  WsPool* pool = nullptr;
+  DevBuf() {}
+  explicit DevBuf(WsPool* pl) : pool(pl) {}
   void alloc(size_t c) {
     count = c;
-    RF_CUDA(cudaMalloc((void**)&p, std::max<size_t>(c, 1) * sizeof(T)));
+    size_t bytes = std::max<size_t>(c, 1) * sizeof(T);
+    if (pool) { p = (T*)pool->get(bytes); if (!p) { set_error("out of device memory (%zu bytes)", bytes); throw CudaFail{RFSLAM_ENOMEM}; } }
+    else RF_CUDA(cudaMalloc((void**)&p, bytes));
   }
-  void zero() { RF_CUDA(cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T))); }
-  ~DevBuf() { if (p) cudaFree(p); }
+  void zero() { RF_CUDA(cudaMemsetAsync(p, 0, std::max<size_t>(count, 1) * sizeof(T))); }
+  ~DevBuf() { if (p) { if (pool) pool->put(p); else cudaFree(p); } }
 };
 
 template <typename T>
@@ -206,6 +219,25 @@ int validate_grow_args(const rfslam_grow_args* a, GrowConfig* cfg) {
   return RFSLAM_OK;
 }
 
+namespace {
+// growable host array handed to the caller (malloc'd; the C-ABI frees it with free())
+template <typename T>
+struct HostOut {
+  T* p = nullptr; size_t n = 0, cap = 0;
+  T* grow(size_t add) {
+    if (n + add > cap) {
+      cap = std::max<size_t>(n + add, cap * 2);
+      T* q = (T*)realloc(p, std::max<size_t>(cap, 1) * sizeof(T));
+      if (!q) { set_error("out of host memory"); throw CudaFail{RFSLAM_ENOMEM}; }
+      p = q;
+    }
+    T* at = p + n; n += add; return at;
+  }
+  T* release() { if (!p) p = (T*)malloc(sizeof(T)); T* q = p; p = nullptr; return q; }
+  ~HostOut() { free(p); }
+};
+}  // namespace
+
 int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out* out) {
   memset(out, 0, sizeof(*out));
   GrowConfig cfg;
@@ -213,6 +245,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
   if (rc) return rc;
   if (a->observation_size != ds->n || a->x_size != ds->p) { set_error("arguments do not match the resident dataset"); return RFSLAM_EINVAL; }
   const int n = ds->n, p = ds->p;
+  WsPool* pool = &ds->pool;
   try {
     RF_CUDA(cudaSetDevice(ds->device));
     // ---- which trees does this process grow? (tree b -> rank (b-1) mod G) ----
@@ -220,6 +253,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     int first = a->tree_first > 0 ? a->tree_first : 1, step = a->tree_step > 0 ? a->tree_step : 1;
     for (int b = first; b <= cfg.ntree; b += step) ids.push_back(b);
     const int T = (int)ids.size();
+    if (T == 0) { set_error("this shard holds no trees (tree_first %d > ntree %d)", first, cfg.ntree); return RFSLAM_EINVAL; }
     std::vector<int> seedA, seedB;
     chain_seeds(cfg.seed, cfg.ntree, seedA, seedB);
     std::vector<int> bootSize(T);
@@ -242,7 +276,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     g.rule = cfg.rule; g.mtry = cfg.mtry; g.nodesize = cfg.nodesize; g.nodedepth = cfg.nodedepth; g.alpha = cfg.alpha;
     g.pw = (p + 31) / 32; g.ncmax = std::min(cfg.mtry, kMaxCand);
     g.has_sort = ds->max_D > kHistBins;
-    DevBuf<double> d_sw;
+    DevBuf<double> d_sw(pool);
     if (a->x_split_stat_weight) {
       bool allOne = true;
       for (int i = 0; i < p; i++) if (a->x_split_stat_weight[i] != 1.0) allOne = false;
@@ -258,34 +292,38 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     // ---- batch size from free memory ----
     size_t freeB = 0, totalB = 0;
     RF_CUDA(cudaMemGetInfo(&freeB, &totalB));
+    freeB += pool->idle_bytes();
     const size_t perTree = (size_t)n * (8 + 2 + (g.has_sort ? 16 : 0)) + (cfg.by_user ? 0 : (size_t)maxBoot * 4)
                          + (size_t)kStackCap * (sizeof(NodeEnt) + (size_t)g.pw * 4) + 4096;
     const size_t worstNodes = 2ull * (size_t)std::min(n, maxBoot) + 1;
     size_t estNodes = std::min<size_t>(worstNodes, 4ull * (size_t)maxBoot / (size_t)std::max(1, cfg.nodesize) + 256);
     size_t budget = (size_t)(0.80 * (double)freeB);
     size_t fixed = (size_t)n * (16 + 16 + 8) + (64u << 20);
-    int B = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, (budget > fixed ? budget - fixed : 0) / (perTree + estNodes * 48)));
+    int B = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, (budget > fixed ? budget - fixed : 0) / (perTree + estNodes * 72)));
     if (const char* e = getenv("RFSLAM_TREES_PER_BATCH")) { int v = atoi(e); if (v > 0) B = std::min(T, v); }
 
     // ---- persistent accumulators ----
-    DevBuf<double> d_allNum, d_oobNum; DevBuf<uint32_t> d_allDen, d_oobDen;
+    DevBuf<double> d_allNum(pool), d_oobNum(pool); DevBuf<uint32_t> d_allDen(pool), d_oobDen(pool);
     d_allNum.alloc(2 * (size_t)n); d_oobNum.alloc(2 * (size_t)n); d_allDen.alloc(n); d_oobDen.alloc(n);
     d_allNum.zero(); d_oobNum.zero(); d_allDen.zero(); d_oobDen.zero();
-    DevBuf<int32_t> d_nodeMemb, d_bootMemb;
+    DevBuf<int32_t> d_nodeMemb(pool), d_bootMemb(pool);
     if (cfg.want_membership) { d_nodeMemb.alloc((size_t)T * n); d_bootMemb.alloc((size_t)T * n); }
+    DevBuf<unsigned long long> d_pathSum(pool);
+    d_pathSum.alloc(1); d_pathSum.zero();
 
-    std::vector<int32_t> h_treeID, h_nodeID, h_parmID, h_leafCount(T), h_seed(T), h_tnRCNT, h_tnACNT, h_tnCLAS;
-    std::vector<double> h_contPT, h_stat;
-    long long totalCand = 0, totalAlgo = 0;
+    HostOut<int32_t> h_treeID, h_nodeID, h_parmID, h_tnRCNT, h_tnACNT, h_tnCLAS;
+    HostOut<double> h_contPT, h_stat;
+    std::vector<int32_t> h_leafCount(T), h_seed(T);
+    long long totalCand = 0, totalAlgo = 0, launches = 0;
     float growMs = 0.f, totalMs = 0.f;
     cudaEvent_t ev0, ev1, ev2, ev3;
     RF_CUDA(cudaEventCreate(&ev0)); RF_CUDA(cudaEventCreate(&ev1)); RF_CUDA(cudaEventCreate(&ev2)); RF_CUDA(cudaEventCreate(&ev3));
 
     // ---- per-batch buffers ----
-    DevBuf<uint32_t> d_lists, d_sort, d_draws, d_stackPerm, d_ctab, d_nodeCount, d_leafCount, d_cursor;
-    DevBuf<uint16_t> d_cnt; DevBuf<NodeEnt> d_stack; DevBuf<int> d_seedA, d_seedB, d_boot, d_ids, d_status;
-    DevBuf<unsigned long long> d_cand, d_algo, d_nodeOff, d_leafOff;
-    DevBuf<int32_t> d_samp;
+    DevBuf<uint32_t> d_lists(pool), d_sort(pool), d_draws(pool), d_stackPerm(pool), d_ctab(pool), d_nodeCount(pool), d_leafCount(pool), d_cursor(pool);
+    DevBuf<uint16_t> d_cnt(pool); DevBuf<NodeEnt> d_stack(pool); DevBuf<int> d_seedA(pool), d_seedB(pool), d_boot(pool), d_ids(pool), d_status(pool);
+    DevBuf<unsigned long long> d_cand(pool), d_algo(pool), d_nodeOff(pool), d_leafOff(pool);
+    DevBuf<int32_t> d_samp(pool);
     const size_t cntStride = ((size_t)n + 1) & ~(size_t)1;         // u16 count rows stay 4-byte aligned
     d_lists.alloc((size_t)B * 2 * n);
     if (g.has_sort) d_sort.alloc((size_t)B * 4 * n);
@@ -298,7 +336,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     const uint32_t maxChunksPerTree = (uint32_t)((worstNodes + kRecChunk - 1) / kRecChunk) + 1;
     d_ctab.alloc((size_t)B * maxChunksPerTree);
     const bool profile = getenv("RFSLAM_PROFILE") != nullptr;
-    DevBuf<unsigned long long> d_prof;
+    DevBuf<unsigned long long> d_prof(pool);
     if (profile) { d_prof.alloc((size_t)B * kProfSlots); g_last_profile.assign(kProfSlots, 0ull); }
 
     for (int b0 = 0; b0 < T; b0 += B) {
@@ -312,7 +350,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
 
       size_t poolChunks = std::max<size_t>((size_t)nb * 2, (estNodes * nb + kRecChunk - 1) / kRecChunk + nb);
       for (int attempt = 0;; attempt++) {
-        DevBuf<Rec> d_pool; DevBuf<double> d_statPool;
+        DevBuf<Rec> d_pool(pool); DevBuf<double> d_statPool(pool);
         d_pool.alloc(poolChunks * kRecChunk); d_statPool.alloc(poolChunks * kRecChunk);
         RF_CUDA(cudaEventRecord(ev0));
         // K1: bootstrap
@@ -323,6 +361,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
           for (int t = 0; t < nb; t++) {
             RF_CUDA(cudaMemcpy(d_samp.p, a->bootstrap + (size_t)(hid[t] - 1) * n, (size_t)n * 4, cudaMemcpyHostToDevice));
             user_count_kernel<<<(n + 255) / 256, 256>>>(d_samp.p, ds->dev.perm, d_cnt.p + (size_t)t * cntStride, n, d_bad);
+            launches++;
           }
           int bad = 0;
           RF_CUDA(cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost));
@@ -331,10 +370,11 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
           bootstrap_draw_kernel<<<nb, 32>>>(d_seedA.p, d_boot.p, d_draws.p, (size_t)maxBoot, n);
           dim3 gc((unsigned)std::min<size_t>(((size_t)maxBoot + 255) / 256, 1024), (unsigned)nb);
           bag_count_kernel<<<gc, 256>>>(d_draws.p, (size_t)maxBoot, d_boot.p, ds->dev.inv, (uint32_t*)d_cnt.p, cntStride / 2);
+          launches += 2;
         }
         RF_CUDA(cudaGetLastError());
         // K2: grow
-        RF_CUDA(cudaMemset(d_cursor.p, 0, 4)); RF_CUDA(cudaMemset(d_status.p, 0, 4));
+        RF_CUDA(cudaMemsetAsync(d_cursor.p, 0, 4)); RF_CUDA(cudaMemsetAsync(d_status.p, 0, 4));
         GrowWork w{};
         w.ntrees = nb; w.seedB = d_seedB.p; w.bootSize = d_boot.p; w.lists = d_lists.p; w.cnt = d_cnt.p; w.cntStride = cntStride;
         w.sortbuf = g.has_sort ? d_sort.p : nullptr; w.stack = d_stack.p; w.stackPerm = d_stackPerm.p;
@@ -342,9 +382,9 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         w.ctab = d_ctab.p; w.maxChunksPerTree = maxChunksPerTree; w.nodeCount = d_nodeCount.p; w.leafCount = d_leafCount.p;
         w.candCount = d_cand.p; w.algoBytes = d_algo.p; w.status = d_status.p;
         w.prof = profile ? d_prof.p : nullptr;
-        DevData dd = ds->dev;
         RF_CUDA(cudaEventRecord(ev1));
-        rfslam_grow_kernel<<<nb, kThreads, smem>>>(dd, g, w);
+        rfslam_grow_kernel<<<nb, kThreads, smem>>>(ds->dev, g, w);
+        launches++;
         RF_CUDA(cudaEventRecord(ev2));
         RF_CUDA(cudaGetLastError());
         int status = 0;
@@ -355,7 +395,6 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
           continue;                                            // deterministic: simply regrow the batch
         }
         if (status == 2) { set_error("tree deeper than %d pending nodes", kStackCap); throw CudaFail{RFSLAM_ENOSUP}; }
-
         if (profile) {
           std::vector<unsigned long long> hp((size_t)nb * kProfSlots);
           RF_CUDA(cudaMemcpy(hp.data(), d_prof.p, hp.size() * 8, cudaMemcpyDeviceToHost));
@@ -377,7 +416,8 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         RF_CUDA(cudaMemcpy(d_nodeOff.p, nodeOff.data(), (nb + 1) * 8, cudaMemcpyHostToDevice));
         RF_CUDA(cudaMemcpy(d_leafOff.p, leafOff.data(), (nb + 1) * 8, cudaMemcpyHostToDevice));
         const size_t NN = nodeOff[nb], NL = leafOff[nb];
-        DevBuf<int32_t> f_tree, f_node, f_parm, f_rcnt, f_acnt, f_clas; DevBuf<double> f_cont, f_stat; DevBuf<uint32_t> f_code, f_right;
+        DevBuf<int32_t> f_tree(pool), f_node(pool), f_parm(pool), f_rcnt(pool), f_acnt(pool), f_clas(pool);
+        DevBuf<double> f_cont(pool), f_stat(pool); DevBuf<uint32_t> f_code(pool), f_right(pool);
         f_tree.alloc(NN); f_node.alloc(NN); f_parm.alloc(NN); f_cont.alloc(NN); f_stat.alloc(NN); f_code.alloc(NN); f_right.alloc(NN);
         f_rcnt.alloc(NL); f_acnt.alloc(NL); f_clas.alloc(2 * NL); f_acnt.zero();
         uint32_t maxNodes = *std::max_element(hNodes.begin(), hNodes.end());
@@ -386,40 +426,23 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
                                     f_code.p, f_right.p, f_rcnt.p, f_clas.p);
         membership_kernel<<<(n + 127) / 128, 128>>>(ds->dev, nb, d_nodeOff.p, d_leafOff.p, f_node.p, f_parm.p, f_code.p, f_right.p,
                                                     f_rcnt.p, f_clas.p, d_cnt.p, f_acnt.p, d_allNum.p, d_oobNum.p, d_allDen.p, d_oobDen.p,
-                                                    d_nodeMemb.p, d_bootMemb.p, b0, cntStride);
+                                                    d_nodeMemb.p, d_bootMemb.p, b0, cntStride, d_pathSum.p);
+        launches += 2;
         RF_CUDA(cudaEventRecord(ev3));
         RF_CUDA(cudaGetLastError());
         RF_CUDA(cudaEventSynchronize(ev3));
         float ms = 0.f;
         RF_CUDA(cudaEventElapsedTime(&ms, ev1, ev2)); growMs += ms;
         RF_CUDA(cudaEventElapsedTime(&ms, ev0, ev3)); totalMs += ms;
-
-        // ---- append to host output ----
-        size_t o0 = h_treeID.size(), l0 = h_tnRCNT.size();
-        h_treeID.resize(o0 + NN); h_nodeID.resize(o0 + NN); h_parmID.resize(o0 + NN); h_contPT.resize(o0 + NN); h_stat.resize(o0 + NN);
-        h_tnRCNT.resize(l0 + NL); h_tnACNT.resize(l0 + NL); h_tnCLAS.resize(2 * (l0 + NL));
-        RF_CUDA(cudaMemcpy(h_treeID.data() + o0, f_tree.p, NN * 4, cudaMemcpyDeviceToHost));
-        RF_CUDA(cudaMemcpy(h_nodeID.data() + o0, f_node.p, NN * 4, cudaMemcpyDeviceToHost));
-        RF_CUDA(cudaMemcpy(h_parmID.data() + o0, f_parm.p, NN * 4, cudaMemcpyDeviceToHost));
-        RF_CUDA(cudaMemcpy(h_contPT.data() + o0, f_cont.p, NN * 8, cudaMemcpyDeviceToHost));
-        RF_CUDA(cudaMemcpy(h_stat.data() + o0, f_stat.p, NN * 8, cudaMemcpyDeviceToHost));
-        RF_CUDA(cudaMemcpy(h_tnRCNT.data() + l0, f_rcnt.p, NL * 4, cudaMemcpyDeviceToHost));
-        RF_CUDA(cudaMemcpy(h_tnACNT.data() + l0, f_acnt.p, NL * 4, cudaMemcpyDeviceToHost));
-        RF_CUDA(cudaMemcpy(h_tnCLAS.data() + 2 * l0, f_clas.p, 2 * NL * 4, cudaMemcpyDeviceToHost));
-        // B_part's all-row term: 16 bytes per row of every split node
-        {
-          std::vector<uint32_t> hr(NN);
-          RF_CUDA(cudaMemcpy(hr.data(), f_right.p, NN * 4, cudaMemcpyDeviceToHost));
-          std::vector<long long> acc(NN);
-          for (int t = 0; t < nb; t++) {
-            size_t off = nodeOff[t];
-            for (long long q = (long long)hNodes[t] - 1; q >= 0; q--) {
-              size_t at = off + (size_t)q;
-              if (h_parmID[o0 + at] == 0) acc[at] = h_tnACNT[l0 + leafOff[t] + (size_t)h_nodeID[o0 + at] - 1];
-              else { acc[at] = acc[at + 1] + acc[off + hr[at]]; totalAlgo += 16ll * acc[at]; }
-            }
-          }
-        }
+        // ---- straight into the caller's arrays ----
+        RF_CUDA(cudaMemcpy(h_treeID.grow(NN), f_tree.p, NN * 4, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_nodeID.grow(NN), f_node.p, NN * 4, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_parmID.grow(NN), f_parm.p, NN * 4, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_contPT.grow(NN), f_cont.p, NN * 8, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_stat.grow(NN), f_stat.p, NN * 8, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_tnRCNT.grow(NL), f_rcnt.p, NL * 4, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_tnACNT.grow(NL), f_acnt.p, NL * 4, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_tnCLAS.grow(2 * NL), f_clas.p, 2 * NL * 4, cudaMemcpyDeviceToHost));
         break;
       }
     }
@@ -427,22 +450,24 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     if (cfg.finalize) {
       finalize_kernel<<<(n + 255) / 256, 256>>>(d_allNum.p, d_allDen.p, n);
       finalize_kernel<<<(n + 255) / 256, 256>>>(d_oobNum.p, d_oobDen.p, n);
+      launches += 2;
       RF_CUDA(cudaGetLastError());
     }
     cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2); cudaEventDestroy(ev3);
+    unsigned long long pathSum = 0;
+    RF_CUDA(cudaMemcpy(&pathSum, d_pathSum.p, 8, cudaMemcpyDeviceToHost));
+    totalAlgo += 16ll * (long long)pathSum;                      // B_part's all-row term
 
     // ---- hand over ----
-    auto give_i = [](const std::vector<int32_t>& v) { int32_t* q = (int32_t*)malloc(std::max<size_t>(v.size(), 1) * 4); memcpy(q, v.data(), v.size() * 4); return q; };
-    auto give_d = [](const std::vector<double>& v) { double* q = (double*)malloc(std::max<size_t>(v.size(), 1) * 8); memcpy(q, v.data(), v.size() * 8); return q; };
     out->ntree = T; out->n = n;
-    out->total_nodes = (int64_t)h_treeID.size(); out->total_leaves = (int64_t)h_tnRCNT.size();
-    std::vector<int32_t> idv(ids.begin(), ids.end());
-    out->tree_ids = give_i(idv);
-    out->treeID = give_i(h_treeID); out->nodeID = give_i(h_nodeID); out->parmID = give_i(h_parmID);
-    out->contPT = give_d(h_contPT); out->splitStat = give_d(h_stat);
-    out->mwcpSZ = (int32_t*)calloc(std::max<size_t>(h_treeID.size(), 1), 4);
-    out->leafCount = give_i(h_leafCount); out->seed = give_i(h_seed);
-    out->tnRCNT = give_i(h_tnRCNT); out->tnACNT = give_i(h_tnACNT); out->tnCLAS = give_i(h_tnCLAS);
+    out->total_nodes = (int64_t)h_treeID.n; out->total_leaves = (int64_t)h_tnRCNT.n;
+    out->tree_ids = (int32_t*)malloc((size_t)T * 4); memcpy(out->tree_ids, ids.data(), (size_t)T * 4);
+    out->mwcpSZ = (int32_t*)calloc(std::max<size_t>(h_treeID.n, 1), 4);
+    out->treeID = h_treeID.release(); out->nodeID = h_nodeID.release(); out->parmID = h_parmID.release();
+    out->contPT = h_contPT.release(); out->splitStat = h_stat.release();
+    out->leafCount = (int32_t*)malloc((size_t)T * 4); memcpy(out->leafCount, h_leafCount.data(), (size_t)T * 4);
+    out->seed = (int32_t*)malloc((size_t)T * 4); memcpy(out->seed, h_seed.data(), (size_t)T * 4);
+    out->tnRCNT = h_tnRCNT.release(); out->tnACNT = h_tnACNT.release(); out->tnCLAS = h_tnCLAS.release();
     out->oobEnsbCLS = host_copy(d_oobNum.p, 2 * (size_t)n); out->allEnsbCLS = host_copy(d_allNum.p, 2 * (size_t)n);
     out->oobEnsbDen = host_copy(d_oobDen.p, (size_t)n); out->allEnsbDen = host_copy(d_allDen.p, (size_t)n);
     if (cfg.want_membership) {
@@ -450,7 +475,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
       out->bootMembership = host_copy(d_bootMemb.p, (size_t)T * n);
     }
     out->split_candidates = totalCand; out->algorithmic_bytes = totalAlgo;
-    out->grow_kernel_ms = growMs; out->total_device_ms = totalMs;
+    out->grow_kernel_ms = growMs; out->total_device_ms = totalMs; out->kernel_launches = launches;
   } catch (CudaFail f) {
     rfslam_b200_free_forest(out);
     return f.code;

@@ -29,6 +29,37 @@ struct DevData {
 
 }  // namespace rfslam
 
+namespace rfslam {
+// recycles device scratch across grow calls on a resident dataset (cudaMalloc / cudaFree of
+// multi-GB buffers would otherwise be paid on every call)
+struct WsPool {
+  struct Blk { void* p; size_t bytes; bool used; };
+  std::vector<Blk> blks;
+  void* get(size_t bytes) {
+    int best = -1;
+    for (size_t i = 0; i < blks.size(); i++)
+      if (!blks[i].used && blks[i].bytes >= bytes && blks[i].bytes <= 2 * bytes + (1u << 20) && (best < 0 || blks[i].bytes < blks[best].bytes)) best = (int)i;
+    if (best >= 0) { blks[best].used = true; return blks[best].p; }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      trim();                                   // drop idle blocks and retry once
+      if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    blks.push_back({p, bytes, true});
+    return p;
+  }
+  void put(void* p) { for (auto& b : blks) if (b.p == p) { b.used = false; return; } }
+  size_t idle_bytes() const { size_t s = 0; for (auto& b : blks) if (!b.used) s += b.bytes; return s; }
+  void trim() {
+    std::vector<Blk> keep;
+    for (auto& b : blks) { if (b.used) keep.push_back(b); else cudaFree(b.p); }
+    blks.swap(keep);
+  }
+  void release_all() { for (auto& b : blks) cudaFree(b.p); blks.clear(); }
+};
+}  // namespace rfslam
+
 // The opaque handle of the C-ABI.
 struct rfslam_dataset {
   int device = 0;
@@ -41,6 +72,7 @@ struct rfslam_dataset {
   std::vector<double*> uniq_h;
   int64_t bytes = 0;
   int max_D = 0;
+  rfslam::WsPool pool;            // scratch recycled across grow calls
 };
 
 namespace rfslam {

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import weakref
 from typing import Dict, Optional, Sequence
 
 import numpy as np
@@ -28,10 +29,31 @@ def _ip(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(_pi)
 
 
+_libc = C.CDLL(None)
+_libc.free.argtypes = [C.c_void_p]
+_libc.free.restype = None
+
+
 def _take(ptr, count, dtype):
     if not ptr or count == 0:
         return np.zeros(0, dtype) if ptr else None
     return np.ctypeslib.as_array(ptr, shape=(count,)).astype(dtype, copy=True)
+
+
+def _own(struct, field, count, dtype):
+    """Adopt a callee-malloc'd output array without copying: the struct's pointer is cleared (so
+    rfslam_b200_free_* skips it) and free() runs when the numpy array is collected."""
+    ptr = getattr(struct, field)
+    if not ptr:
+        return None
+    if count == 0:
+        return np.zeros(0, dtype)
+    addr = C.cast(ptr, C.c_void_p).value
+    arr = np.ctypeslib.as_array(ptr, shape=(count,))
+    assert arr.dtype == np.dtype(dtype), (field, arr.dtype, dtype)
+    setattr(struct, field, type(ptr)())
+    weakref.finalize(arr, _libc.free, addr)
+    return arr
 
 
 class _Packed:
@@ -104,21 +126,22 @@ class _Packed:
 def _unpack_forest(o: ForestOut) -> Dict[str, np.ndarray]:
     n, T, NN, NL = o.n, o.ntree, o.total_nodes, o.total_leaves
     res = {
-        "tree_ids": _take(o.tree_ids, T, np.int32),
-        "treeID": _take(o.treeID, NN, np.int32), "nodeID": _take(o.nodeID, NN, np.int32),
-        "parmID": _take(o.parmID, NN, np.int32), "contPT": _take(o.contPT, NN, np.float64),
-        "mwcpSZ": _take(o.mwcpSZ, NN, np.int32), "splitStat": _take(o.splitStat, NN, np.float64),
-        "leafCount": _take(o.leafCount, T, np.int32), "seed": _take(o.seed, T, np.int32),
-        "tnRCNT": _take(o.tnRCNT, NL, np.int32), "tnACNT": _take(o.tnACNT, NL, np.int32),
-        "tnCLAS": _take(o.tnCLAS, 2 * NL, np.int32),
-        "oobEnsbCLS": _take(o.oobEnsbCLS, 2 * n, np.float64), "allEnsbCLS": _take(o.allEnsbCLS, 2 * n, np.float64),
-        "oobEnsbDen": _take(o.oobEnsbDen, n, np.uint32), "allEnsbDen": _take(o.allEnsbDen, n, np.uint32),
+        "tree_ids": _own(o, "tree_ids", T, np.int32),
+        "treeID": _own(o, "treeID", NN, np.int32), "nodeID": _own(o, "nodeID", NN, np.int32),
+        "parmID": _own(o, "parmID", NN, np.int32), "contPT": _own(o, "contPT", NN, np.float64),
+        "mwcpSZ": _own(o, "mwcpSZ", NN, np.int32), "splitStat": _own(o, "splitStat", NN, np.float64),
+        "leafCount": _own(o, "leafCount", T, np.int32), "seed": _own(o, "seed", T, np.int32),
+        "tnRCNT": _own(o, "tnRCNT", NL, np.int32), "tnACNT": _own(o, "tnACNT", NL, np.int32),
+        "tnCLAS": _own(o, "tnCLAS", 2 * NL, np.int32),
+        "oobEnsbCLS": _own(o, "oobEnsbCLS", 2 * n, np.float64), "allEnsbCLS": _own(o, "allEnsbCLS", 2 * n, np.float64),
+        "oobEnsbDen": _own(o, "oobEnsbDen", n, np.uint32), "allEnsbDen": _own(o, "allEnsbDen", n, np.uint32),
         "split_candidates": int(o.split_candidates), "algorithmic_bytes": int(o.algorithmic_bytes),
         "grow_kernel_ms": float(o.grow_kernel_ms), "total_device_ms": float(o.total_device_ms),
+        "kernel_launches": int(o.kernel_launches),
     }
     if o.nodeMembership:
-        res["nodeMembership"] = _take(o.nodeMembership, T * n, np.int32)
-        res["bootMembership"] = _take(o.bootMembership, T * n, np.int32)
+        res["nodeMembership"] = _own(o, "nodeMembership", T * n, np.int32)
+        res["bootMembership"] = _own(o, "bootMembership", T * n, np.int32)
     return res
 
 
