@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librfslam_b200.so")
+LIB_PATH = os.environ.get("RFSLAM_LIB", os.path.join(HERE, "librfslam_b200.so"))
 
 _pd = C.POINTER(C.c_double)
 _pi = C.POINTER(C.c_int32)

@@ -25,6 +25,10 @@
 #include "common.cuh"
 #include "internal.h"
 
+#ifndef RF_ASSUME
+#define RF_ASSUME 19   // bits 4 and 8 (the staging / tile region) miscompute on nvcc 12.9 when assumed shared: left generic
+#endif
+
 namespace rfslam {
 
 struct Rec {            // one forest record (pre-order); 16 bytes
@@ -198,6 +202,24 @@ __device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K) {
   u = (uint32_t*)(m.smT + kSmallMax);
   uintptr_t p = ((uintptr_t)u + 15) & ~(uintptr_t)15;
   m.s = (GrowShared*)p;
+  // tell the compiler these all live in shared memory (LDS/STS/ATOMS instead of generic LD/ST)
+#define RF_SH(x) __builtin_assume(__isShared(x))
+#if RF_ASSUME & 1
+  RF_SH(m.sL); RF_SH(m.sR); RF_SH(m.hT); RF_SH(m.hW); RF_SH(m.statP); RF_SH(m.hN); RF_SH(m.hE); RF_SH(m.hNx); RF_SH(m.hEx); RF_SH(m.pres);
+#endif
+#if RF_ASSUME & 2
+  RF_SH(m.segpos); RF_SH(m.PN); RF_SH(m.PE); RF_SH(m.cN); RF_SH(m.cE); RF_SH(m.PT); RF_SH(m.PW); RF_SH(m.cT); RF_SH(m.cW); RF_SH(m.cTL); RF_SH(m.cTR);
+#endif
+#if RF_ASSUME & 4
+  RF_SH(m.smEnt); RF_SH(m.smT); RF_SH(m.smMult); RF_SH(m.smE); RF_SH(m.smS); RF_SH(m.smCodes);
+#endif
+#if RF_ASSUME & 8
+  RF_SH(m.tileTL); RF_SH(m.tileTR); RF_SH(m.tileDelta); RF_SH(m.tileKey); RF_SH(m.radixBase); RF_SH(m.tileCut);
+#endif
+#if RF_ASSUME & 16
+  RF_SH(m.s);
+#endif
+#undef RF_SH
   return m;
 }
 
