@@ -79,6 +79,39 @@ __host__ __device__ inline float ran1_next(Ran1& s) {
   return t;
 }
 
+// The initialisation branch of ran1_generic taken on its own (rf.c:6082-6096): running it right
+// after seeding changes nothing, and lets later draws skip the test.
+__host__ __device__ inline void ran1_init(Ran1& s) {
+  if (s.idum <= 0 || s.iy == 0) {
+    s.idum = (-(s.idum) < 1) ? 1 : -(s.idum);
+    for (int j = 39; j >= 0; j--) {
+      s.idum = ran1_step(s.idum);
+      if (j < 32) s.iv[j] = s.idum;
+    }
+    s.iy = s.iv[1];
+  }
+}
+
+// 16807^k mod (2^31 - 1), k = 1..16: the Park-Miller state k steps ahead is (kJump[k-1] * idum) mod M,
+// bit-identical to k Schrage steps (both are exact modular products)
+__device__ __constant__ const uint32_t kJump[16] = {16807u, 282475249u, 1622650073u, 984943658u, 1144108930u, 470211272u,
+  101027544u, 1457850878u, 1458777923u, 2007237709u, 823564440u, 1115438165u, 1784484492u, 74243042u, 114807987u, 1137522503u};
+
+__host__ __device__ inline int ran1_mulmod(uint32_t a, uint32_t v) {
+  unsigned long long p = (unsigned long long)a * (unsigned long long)v;
+  unsigned long long r = (p & 0x7FFFFFFFull) + (p >> 31);
+  r = (r & 0x7FFFFFFFull) + (r >> 31);
+  if (r >= 0x7FFFFFFFull) r -= 0x7FFFFFFFull;
+  return (int)r;
+}
+
+__host__ __device__ inline float ran1_float(int iy) {
+  float t = (float)((1.0 / 2147483647.0) * (double)iy);
+  const double rnmx = 1.0 - 1.2e-7;
+  if ((double)t > rnmx) return (float)rnmx;
+  return t;
+}
+
 // draw k in [1, size]: (uint) ceil(ran1 * (size * 1.0))  (rf.c:531, rf.c:8380)
 __host__ __device__ inline uint32_t ran1_index(Ran1& s, uint32_t size) {
   return (uint32_t)ceil((double)ran1_next(s) * ((double)size * 1.0));
@@ -105,6 +138,21 @@ __host__ __device__ inline double side_term(bool bayes, double E, double N, doub
   double mu = W / T;
   if (mu == 0.0) return 0.0;
   return (E * log(mu)) - (N * mu);
+}
+
+// Branch-free form of side_term for code that evaluates several terms back to back (the two
+// sides of two chunks): the four logs form independent dependency chains the scheduler can overlap.
+__host__ __device__ inline double side_term_nb(bool bayes, double E, double N, double T, double W, double alpha, double beta) {
+  if (bayes) {
+    const double lam = (E + alpha) / (beta + T);
+    const double r = E * log(lam);
+    return (E == 0.0) ? 0.0 : r;
+  }
+  const double mu0 = (T != 0.0) ? W / T : 0.0;
+  const bool ok = (E != 0.0) && (mu0 != 0.0);
+  const double mu = ok ? mu0 : 1.0;
+  const double r = (E * log(mu)) - (N * mu);
+  return ok ? r : 0.0;
 }
 
 #ifdef __CUDACC__

@@ -91,7 +91,6 @@ struct GrowShared {
   Ran1 rng;
   NodeEnt cur;
   uint32_t perm[32];                 // permissible covariates of the current node (p <= 1024)
-  uint16_t pool[1024];
   int nc;
   int candCov[kMaxCand];
   int candD[kMaxCand];
@@ -148,6 +147,7 @@ struct GrowSmem {
   uint32_t *hN, *hE, *hNx, *hEx, *pres;
   // sorted-walk tile arrays (alias the small-node staging: the two paths never overlap in time)
   double *tileTL, *tileTR, *tileDelta; uint32_t *tileKey, *radixBase; uint8_t* tileCut;
+  uint16_t* pool;                    // permissible-covariate pool of the draw step (same aliasing: used between nodes only)
   uint32_t *segpos, *PN, *PE, *cN, *cE;
   double *PT, *PW, *cT, *cW, *cTL, *cTR;
   // small-node staging: the node's entries and everything scoring needs about them
@@ -192,6 +192,7 @@ __device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K) {
     u = (uint32_t*)al;
     m.tileTL = (double*)u; m.tileTR = m.tileTL + kThreads; m.tileDelta = m.tileTR + kThreads;
     m.tileKey = (uint32_t*)(m.tileDelta + kThreads); m.radixBase = m.tileKey + kThreads; m.tileCut = (uint8_t*)(m.radixBase + 256);
+    m.pool = (uint16_t*)u;
   }
   m.smEnt = u; u += kSmallMax;
   uint8_t* b8 = (uint8_t*)u;
@@ -471,6 +472,37 @@ __device__ inline void track_combine_one(const NodeCtx& c, int ci) {
     return;
   }
   track_exact(c, ci);
+}
+
+// warp 0, nodes whose candidates are all histogram candidates: lane = candidate; the draw-order
+// replay of the tracker is a short register loop, the exact walk only runs for near-ties / NaN
+__device__ inline void track_combine_all(const NodeCtx& c, int nc) {
+  GrowShared* s = c.m.s;
+  const int lane = lane_id();
+  const bool mine = lane < nc;
+  const int np = mine ? s->trkNp[lane] : 0;
+  const bool clean = mine ? (s->trkClean[lane] != 0) : true;
+  if (c.w.sinkDelta || __any_sync(0xffffffffu, mine && np >= 2 && !clean)) {
+    for (int ci = 0; ci < nc; ci++) track_combine_one(c, ci);
+    return;
+  }
+  if (mine && np < 2) {                                   // constant in this node (rf.c:15004-15007)
+    const int cov = s->candCov[lane];
+    atomicAnd(&s->perm[cov >> 5], ~(1u << (cov & 31)));
+  }
+  const int cuts = warp_sum(np >= 2 ? np - 1 : 0);
+  const double M = mine ? s->trkMax[lane] : 0.0;
+  int have = s->have; double best = s->bestDelta; int bc = -1;
+  for (int ci = 0; ci < nc; ci++) {
+    const double Mi = __shfl_sync(0xffffffffu, M, ci);
+    const int npi = __shfl_sync(0xffffffffu, np, ci);
+    if (npi >= 2 && (!have || (Mi - best) > kEpsilon)) { have = 1; best = Mi; bc = ci; }
+  }
+  if (lane == 0) {
+    s->candCount += (unsigned long long)cuts;
+    if (bc >= 0) { s->have = 1; s->bestDelta = best; s->bestCand = bc; s->bestCode = (uint32_t)s->trkMaxBin[bc]; }
+  }
+  __syncwarp();
 }
 
 // ---- sorted-walk path for covariates with more than kHistBins distinct values ----------------
@@ -803,8 +835,7 @@ __device__ inline void score_small(NodeCtx& c) {
   }
   __syncthreads();
   RF_PROF(4);
-  if (wid == 0)
-    for (int ci = 0; ci < nc; ci++) track_combine_one(c, ci);
+  if (wid == 0) track_combine_all(c, nc);
   __syncthreads();
   RF_PROF(6);
 }
@@ -900,6 +931,12 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
     if (s->candHist[ci]) track_summary(c, ci);
   __syncthreads();
 
+  if (!anySort) {
+    if (warp_id() == 0) track_combine_all(c, nc);
+    __syncthreads();
+    RF_PROF(6);
+    return;
+  }
   for (int ci = 0; ci < nc; ci++) {
     if (s->candHist[ci]) {
       if (warp_id() == 0) track_combine_one(c, ci);
@@ -914,19 +951,43 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
 }
 
 // ---- thread 0: draw the node's candidate covariates (step 1) ---------------------------------
-__device__ inline void draw_candidates(const DevData& d, const GrowParams& g, GrowShared* s) {
-  int size = s->poolSize;                                                         // built by warp 0, ascending (rf.c:8209-8213)
-  int count = 0, nc = 0;
-  while (count < g.mtry && size > 0) {
-    count++;
-    uint32_t slot = ran1_index(s->rng, (uint32_t)size);                          // in [1, size]
-    int cov = s->pool[slot - 1];
-    s->pool[slot - 1] = s->pool[size - 1];                                       // swap-remove (rf.c:8306)
-    size--;
-    s->candCov[nc] = cov;
-    nc++;
+// ---- warp 0: draw the node's candidate covariates (step 1) -----------------------------------
+// min(mtry, pool) draws without replacement, slot = ceil(ran1B * size), swap-remove
+// (rf.c:8378-8381, rf.c:8305-8307).  The Park-Miller states of all draws are produced at once by
+// jump-ahead (lane k: k+1 steps), only the Bays-Durham table walk and the swap-remove are serial.
+__device__ inline void draw_candidates(const DevData& d, const GrowParams& g, GrowShared* s, GrowSmem& m) {
+  const int lane = lane_id();
+  const int size0 = s->poolSize;                                                  // built just before, ascending (rf.c:8209-8213)
+  const int nd = min(g.mtry, size0);
+  if (nd > 0) {
+    const int idum0 = s->rng.idum;
+    const int myIdum = (lane < nd) ? ran1_mulmod(kJump[lane], (uint32_t)idum0) : 0;
+    int iy = s->rng.iy, myIy = 0;
+    for (int k = 0; k < nd; k++) {
+      const int idk = __shfl_sync(0xffffffffu, myIdum, k);
+      const int j = iy / 67108864;
+      const int niy = s->rng.iv[j];
+      __syncwarp();
+      if (lane == 0) s->rng.iv[j] = idk;
+      __syncwarp();
+      iy = niy;
+      if (lane == k) myIy = niy;
+    }
+    if (lane == 0) s->rng.iy = iy;
+    const int lastIdum = __shfl_sync(0xffffffffu, myIdum, nd - 1);
+    if (lane == 0) s->rng.idum = lastIdum;
+    uint32_t slot = 0;
+    if (lane < nd) slot = (uint32_t)ceil((double)ran1_float(myIy) * ((double)(size0 - lane) * 1.0));   // in [1, size]
+    for (int k = 0; k < nd; k++) {
+      const uint32_t sl = __shfl_sync(0xffffffffu, slot, k);
+      const int cov = m.pool[sl - 1];
+      const int tail = m.pool[size0 - 1 - k];
+      __syncwarp();
+      if (lane == 0) { m.pool[sl - 1] = (uint16_t)tail; s->candCov[k] = cov; }            // swap-remove (rf.c:8306)
+      __syncwarp();
+    }
   }
-  s->nc = nc;
+  if (lane == 0) s->nc = nd;
 }
 
 __device__ inline bool append_record(const GrowWork& w, GrowShared* s, int tree, uint32_t nodeID, uint32_t parm,
@@ -965,6 +1026,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     for (int k = 0; k < kProfSlots; k++) s->prof[k] = 0;
     s->tmark = clock64();
     ran1_seed(s->rng, w.seedB[tree]);
+    ran1_init(s->rng);
     s->nodeCount = 0; s->leafCount = 1; s->sp = 0; s->candCount = 0; s->algoBytes = 0; s->abort = 0;
   }
   for (int k = tid; k < 32; k += kThreads) {
@@ -1042,15 +1104,13 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
           const int k = base + lane_id();
           const bool ok = k < d.p && ((s->perm[base >> 5] >> lane_id()) & 1u);
           const unsigned bm = __ballot_sync(0xffffffffu, ok);
-          if (ok) s->pool[size + __popc(bm & ((1u << lane_id()) - 1u))] = (uint16_t)k;
+          if (ok) m.pool[size + __popc(bm & ((1u << lane_id()) - 1u))] = (uint16_t)k;
           size += __popc(bm);
         }
         if (lane_id() == 0) s->poolSize = size;
         __syncwarp();
-      }
-      if (tid == 0) {
-        draw_candidates(d, g, s);
-        s->algoBytes += (unsigned long long)cur.m * (12ull * (unsigned long long)s->nc + 20ull);
+        draw_candidates(d, g, s, m);
+        if (lane_id() == 0) s->algoBytes += (unsigned long long)cur.m * (12ull * (unsigned long long)s->nc + 20ull);
       }
       __syncthreads();
       if (tid < s->nc) {                                   // candidate metadata: one parallel round of loads
@@ -1100,27 +1160,54 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     uint32_t* dst = w.lists + ((size_t)tree * 2 + (cur.buf ^ 1u)) * n + cur.start;
     const bool small = s->isSmall != 0;
     const uint8_t* cptr = m.smCodes + bc * kSmallMax;
+    uint32_t nL; unsigned long long tneL; double trtL = 0.0, trtR = 0.0;
+    if (small) {
+      // the node is staged in shared memory: thread t owns entries 2t and 2t+1, one block scan of a
+      // packed (left entries | left rows << 16 | left events << 40) word gives sizes and positions
+      static_assert(kSmallMax == 2 * kThreads, "two staged entries per thread");
+      unsigned long long my = 0ull; bool lf[2] = {false, false}; uint32_t en[2] = {0u, 0u};
+      double rtL = 0.0, rtR = 0.0;
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const uint32_t i = 2u * tid + u;
+        if (i < cur.len) {
+          en[u] = m.smEnt[i];
+          lf[u] = cptr[i] <= bcode;                               // LEFT iff cut - x >= 0 (rf.c:15194)
+          const unsigned long long mult = (en[u] >> kRowBits) + 1u;
+          if (lf[u]) my += 1ull | (mult << 16) | ((m.smE[i] ? mult : 0ull) << 40);
+          if (bayes) { const double v = (double)mult * m.smT[i]; if (lf[u]) rtL += v; else rtR += v; }
+        }
+      }
+      unsigned long long tot;
+      const unsigned long long inc = block_incl_scan<unsigned long long>(my, s->scrU, tot);
+      nL = (uint32_t)(tot & 0xFFFFull);
+      tneL = (((tot >> 16) & 0xFFFFFFull) << 32) | (tot >> 40);
+      if (bayes) { trtL = block_sum<double>(rtL, s->scrD); trtR = block_sum<double>(rtR, s->scrD); }
+      RF_PROF(8);
+      uint32_t before = (uint32_t)((inc - my) & 0xFFFFull);
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const uint32_t i = 2u * tid + u;
+        if (i < cur.len) {
+          if (lf[u]) { dst[before] = en[u]; before++; }
+          else dst[nL + (i - before)] = en[u];
+        }
+      }
+      __syncthreads();
+    } else {
     // pass 1: sizes of the left child
     unsigned long long cL = 0, neL = 0; double rtL = 0.0, rtR = 0.0;
     for (uint32_t i = tid; i < cur.len; i += kThreads) {
-      uint32_t ent, e; bool left; double rtv = 0.0;
-      if (small) {
-        ent = m.smEnt[i]; left = cptr[i] <= bcode; e = m.smE[i];
-        if (bayes) rtv = m.smT[i];
-      } else {
-        ent = src[i];
-        const uint32_t row = ent & kRowMask;
-        left = load_code(ptr, wd, row) <= bcode;             // LEFT iff cut - x >= 0 (rf.c:15194)
-        e = d.ev[row];
-        if (bayes) rtv = d.rt[row];
-      }
+      const uint32_t ent = src[i];
+      const uint32_t row = ent & kRowMask;
+      const bool left = load_code(ptr, wd, row) <= bcode;          // LEFT iff cut - x >= 0 (rf.c:15194)
+      const uint32_t e = d.ev[row];
       const uint32_t mult = (ent >> kRowBits) + 1u;
       if (left) { cL++; neL += ((unsigned long long)mult << 32) | (unsigned long long)(e ? mult : 0u); }
-      if (bayes) { double v = (double)mult * rtv; if (left) rtL += v; else rtR += v; }
+      if (bayes) { double v = (double)mult * d.rt[row]; if (left) rtL += v; else rtR += v; }
     }
-    const uint32_t nL = (uint32_t)block_sum<unsigned long long>(cL, s->scrU);
-    const unsigned long long tneL = block_sum<unsigned long long>(neL, s->scrU);
-    double trtL = 0.0, trtR = 0.0;
+    nL = (uint32_t)block_sum<unsigned long long>(cL, s->scrU);
+    tneL = block_sum<unsigned long long>(neL, s->scrU);
     if (bayes) { trtL = block_sum<double>(rtL, s->scrD); trtR = block_sum<double>(rtR, s->scrD); }
     RF_PROF(8);
     // pass 2: stable scatter
@@ -1131,10 +1218,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
         uint32_t i = t * kThreads + tid;
         bool valid = i < cur.len;
         uint32_t ent = 0u; bool left = false;
-        if (valid) {
-          if (small) { ent = m.smEnt[i]; left = cptr[i] <= bcode; }
-          else { ent = src[i]; left = load_code(ptr, wd, ent & kRowMask) <= bcode; }
-        }
+        if (valid) { ent = src[i]; left = load_code(ptr, wd, ent & kRowMask) <= bcode; }
         unsigned long long tot;
         unsigned long long inc = block_incl_scan<unsigned long long>(left ? 1ull : 0ull, s->scrU, tot);
         uint32_t before = (uint32_t)inc - (left ? 1u : 0u);
@@ -1147,6 +1231,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
         baseR += nvalid - (uint32_t)tot;
         __syncthreads();
       }
+    }
     }
     RF_PROF(9);
     if (tid == 0) {
