@@ -200,11 +200,10 @@ def main():
         f = ds.grow(splitrule=cfg["rule"], ntree=forest_ntree, nodesize=cfg["nodesize"], seed=cfg["seed"], k_for_alpha=cfg["k_for_alpha"],
                     tree_first=rank + 1, tree_step=world, finalize=(world == 1))
         if dist is not None:
-            # the one exchange of the path: sum the ensemble numerators / denominators (rf.c:944-949)
-            # and tell rank 0 every shard's forest size (the arrays themselves stay sharded by tree)
-            num = torch.from_numpy(np.concatenate([f["oobEnsbCLS"], f["allEnsbCLS"]])).cuda()
-            den = torch.from_numpy(np.concatenate([f["oobEnsbDen"], f["allEnsbDen"]]).astype(np.int64)).cuda()
-            dist.all_reduce(num); dist.all_reduce(den)
+            # the one exchange of the path: sum the ensemble numerators / denominators over ranks
+            # (rf.c:944-949) and tell every rank the shards' forest sizes; the records stay sharded by tree
+            from rfslam_b200 import shard
+            f = shard.allreduce_ensembles(f, device="cuda")
             sizes = torch.tensor([f["treeID"].size, int(f["leafCount"].sum())], device="cuda")
             gathered = [torch.zeros_like(sizes) for _ in range(world)]
             dist.all_gather(gathered, sizes)

@@ -160,7 +160,13 @@ __host__ __device__ inline double side_term_nb(bool bayes, double E, double N, d
 // warp / block primitives
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
-__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+// Virtual warp / thread ids.  The tree kernel gives warp 0 / thread 0 all the serial work of a node
+// (draws, tracker combine, records).  Hardware warp w issues on scheduler w % 4, so with several CTAs
+// per SM every CTA's serial warp would pile onto scheduler 0; rotating the numbering per CTA spreads
+// them (CTAs b and b + 148 share an SM under the round-robin placement and get different rotations).
+__device__ __forceinline__ int warp_rot() { return (int)((blockIdx.x * 5u + (blockIdx.x / 148u) * 3u) & (unsigned)(kWarps - 1)); }
+__device__ __forceinline__ int warp_id() { return (int)(((threadIdx.x >> 5) + (unsigned)warp_rot()) & (unsigned)(kWarps - 1)); }
+__device__ __forceinline__ int vtid() { return (warp_id() << 5) | (int)(threadIdx.x & 31); }
 
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {

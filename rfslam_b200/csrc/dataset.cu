@@ -207,6 +207,7 @@ int dataset_build(const rfslam_grow_args* a, rfslam_dataset** out) {
         int D = (int)last + 1;
         ds->D[c] = D;
         ds->max_D = std::max(ds->max_D, D);
+        if (D <= kHistBins) while (ds->hist_bins < D) ds->hist_bins *= 2;
         double* uniq = dalloc<double>(ds, D);
         ds->uniq_h[c] = uniq;
         if (D <= 256) {

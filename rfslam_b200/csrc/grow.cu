@@ -276,6 +276,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     g.rule = cfg.rule; g.mtry = cfg.mtry; g.nodesize = cfg.nodesize; g.nodedepth = cfg.nodedepth; g.alpha = cfg.alpha;
     g.pw = (p + 31) / 32; g.ncmax = std::min(cfg.mtry, kMaxCand);
     g.has_sort = ds->max_D > kHistBins;
+    g.hbins = ds->hist_bins;
     DevBuf<double> d_sw(pool);
     if (a->x_split_stat_weight) {
       bool allOne = true;
@@ -286,7 +287,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         g.split_weight = d_sw.p;
       }
     }
-    const size_t smem = grow_smem_bytes(g.ncmax, ds->K);
+    const size_t smem = grow_smem_bytes(g.ncmax, ds->K, g.hbins);
     RF_CUDA(cudaFuncSetAttribute(rfslam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     // ---- batch size from free memory ----
@@ -503,8 +504,8 @@ int score_node_impl(int rule, double k_for_alpha, int m, const double* x, const 
     const int n = m;
     GrowParams g{};
     g.rule = rule; g.mtry = 1; g.nodesize = 1; g.nodedepth = -1; g.alpha = 1.0 / (k_for_alpha * k_for_alpha);
-    g.pw = 1; g.ncmax = 1; g.has_sort = ds->max_D > kHistBins;
-    const size_t smem = grow_smem_bytes(g.ncmax, ds->K);
+    g.pw = 1; g.ncmax = 1; g.has_sort = ds->max_D > kHistBins; g.hbins = ds->hist_bins;
+    const size_t smem = grow_smem_bytes(g.ncmax, ds->K, g.hbins);
     RF_CUDA(cudaFuncSetAttribute(rfslam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DevBuf<uint32_t> d_lists, d_sort, d_stackPerm, d_ctab, d_nodeCount, d_leafCount, d_cursor;
     DevBuf<uint16_t> d_cnt; DevBuf<NodeEnt> d_stack; DevBuf<int> d_seedB, d_boot, d_status, d_sinkCount;

@@ -59,6 +59,7 @@ struct GrowParams {
   int pw;                        // words of a permissible-covariate mask
   int ncmax;                     // min(mtry, kMaxCand)
   int has_sort;                  // any covariate with D > kHistBins
+  int hbins;                     // histogram stride (see GrowSmem::hb)
 };
 
 struct GrowWork {
@@ -114,7 +115,7 @@ struct GrowShared {
 
 #define RF_PROF(slot)                                                                  \
   do {                                                                                 \
-    if (w.prof && threadIdx.x == 0) {                                                  \
+    if (w.prof && vtid() == 0) {                                                  \
       long long now__ = clock64();                                                     \
       s->prof[slot] += (unsigned long long)(now__ - s->tmark);                         \
       s->tmark = now__;                                                                \
@@ -153,14 +154,15 @@ struct GrowSmem {
   // small-node staging: the node's entries and everything scoring needs about them
   uint32_t* smEnt; double* smT; uint8_t *smMult, *smE, *smS, *smCodes;
   GrowShared* s;
+  int hb;                            // bins per candidate histogram: pow2 >= the widest byte-coded column, 32..256
 };
 
-__host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K) {
+__host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K, int hb) {
   size_t KS = (size_t)K + 2;
   size_t b = 0;
-  b += (size_t)ncmax * kHistBins * 8 * 4;      // sL sR hT hW
+  b += (size_t)ncmax * hb * 8 * 4;             // sL sR hT hW
   b += (size_t)ncmax * 8;                      // statP
-  b += (size_t)ncmax * kHistBins * 4 * 4;      // hN hE hNx hEx
+  b += (size_t)ncmax * hb * 4 * 4;             // hN hE hNx hEx
   b += (size_t)ncmax * 8 * 4;                  // pres
   b += KS * 8 * 6;                             // PT PW cT cW cTL cTR
   b += KS * 4 * 5;                             // segpos PN PE cN cE
@@ -170,21 +172,22 @@ __host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K) {
   return b + 16;
 }
 
-__device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K) {
+__device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb) {
   GrowSmem m;
+  m.hb = hb;
   size_t KS = (size_t)K + 2;
   double* d = (double*)raw;
-  m.sL = d; d += (size_t)ncmax * kHistBins;
-  m.sR = d; d += (size_t)ncmax * kHistBins;
-  m.hT = d; d += (size_t)ncmax * kHistBins;
-  m.hW = d; d += (size_t)ncmax * kHistBins;
+  m.sL = d; d += (size_t)ncmax * hb;
+  m.sR = d; d += (size_t)ncmax * hb;
+  m.hT = d; d += (size_t)ncmax * hb;
+  m.hW = d; d += (size_t)ncmax * hb;
   m.statP = d; d += ncmax;
   m.PT = d; d += KS; m.PW = d; d += KS; m.cT = d; d += KS; m.cW = d; d += KS; m.cTL = d; d += KS; m.cTR = d; d += KS;
   uint32_t* u = (uint32_t*)d;
-  m.hN = u; u += (size_t)ncmax * kHistBins;
-  m.hE = u; u += (size_t)ncmax * kHistBins;
-  m.hNx = u; u += (size_t)ncmax * kHistBins;
-  m.hEx = u; u += (size_t)ncmax * kHistBins;
+  m.hN = u; u += (size_t)ncmax * hb;
+  m.hE = u; u += (size_t)ncmax * hb;
+  m.hNx = u; u += (size_t)ncmax * hb;
+  m.hEx = u; u += (size_t)ncmax * hb;
   m.pres = u; u += (size_t)ncmax * 8;
   m.segpos = u; u += KS; m.PN = u; u += KS; m.PE = u; u += KS; m.cN = u; u += KS; m.cE = u; u += KS;
   {
@@ -284,9 +287,9 @@ __device__ __forceinline__ void flush_candidate(const NodeCtx& c, int ci, uint32
   const int lane = lane_id();
   const int Dc = s->candD[ci];
   const int nch = (Dc + 31) >> 5;
-  uint32_t* hN = m.hN + ci * kHistBins; uint32_t* hE = m.hE + ci * kHistBins;
-  uint32_t* hNx = m.hNx + ci * kHistBins; uint32_t* hEx = m.hEx + ci * kHistBins;
-  double* hT = m.hT + ci * kHistBins;   double* hW = m.hW + ci * kHistBins;
+  uint32_t* hN = m.hN + ci * m.hb; uint32_t* hE = m.hE + ci * m.hb;
+  uint32_t* hNx = m.hNx + ci * m.hb; uint32_t* hEx = m.hEx + ci * m.hb;
+  double* hT = m.hT + ci * m.hb;   double* hW = m.hW + ci * m.hb;
   const double t0 = c.d.rt_mode;
   const bool active = tE > 0;
   uint32_t cN = 0, cE = 0; double cT = 0.0, cW = 0.0;     // carries (warp-uniform)
@@ -319,7 +322,7 @@ __device__ __forceinline__ void flush_candidate(const NodeCtx& c, int ci, uint32
     double fL = __shfl_sync(0xffffffffu, tL, src < 0 ? 0 : src);
     double fR = __shfl_sync(0xffffffffu, tR, src < 0 ? 0 : src);
     if (src < 0) { fL = cTL; fR = cTR; }
-    if (bin < Dc) { m.sL[ci * kHistBins + bin] += fL; m.sR[ci * kHistBins + bin] += fR; }
+    if (bin < Dc) { m.sL[ci * m.hb + bin] += fL; m.sR[ci * m.hb + bin] += fR; }
     cN = __shfl_sync(0xffffffffu, iN, 31); cE = __shfl_sync(0xffffffffu, iE, 31);
     cT = __shfl_sync(0xffffffffu, iT, 31); cW = __shfl_sync(0xffffffffu, iW, 31);
     cTL = __shfl_sync(0xffffffffu, fL, 31); cTR = __shfl_sync(0xffffffffu, fR, 31);
@@ -335,9 +338,9 @@ __device__ inline void flush_stratum(const NodeCtx& c, int nc) {
     if (!s->candHist[ci]) continue;
     const int Dc = s->candD[ci];
     const int nch = (Dc + 31) >> 5;
-    const uint32_t* hN = m.hN + ci * kHistBins; const uint32_t* hE = m.hE + ci * kHistBins;
-    const uint32_t* hNx = m.hNx + ci * kHistBins; const uint32_t* hEx = m.hEx + ci * kHistBins;
-    const double* hT = m.hT + ci * kHistBins;   const double* hW = m.hW + ci * kHistBins;
+    const uint32_t* hN = m.hN + ci * m.hb; const uint32_t* hE = m.hE + ci * m.hb;
+    const uint32_t* hNx = m.hNx + ci * m.hb; const uint32_t* hEx = m.hEx + ci * m.hb;
+    const double* hT = m.hT + ci * m.hb;   const double* hW = m.hW + ci * m.hb;
     const double t0 = c.d.rt_mode;
     uint32_t tN = 0, tE = 0; double tT = 0.0, tW = 0.0;
     for (int ch = 0; ch < nch; ch++) {
@@ -387,8 +390,8 @@ __device__ inline void track_summary(const NodeCtx& c, int ci) {
     uint32_t wd = m.pres[ci * 8 + ch];
     bool present = ((wd >> lane) & 1u) && bin != last;
     if (present) {
-      double val = (m.sL[ci * kHistBins + bin] + m.sR[ci * kHistBins + bin] - statP) * wgt;
-      m.sL[ci * kHistBins + bin] = val;                     // keep delta for the combine / exact walk
+      double val = (m.sL[ci * m.hb + bin] + m.sR[ci * m.hb + bin] - statP) * wgt;
+      m.sL[ci * m.hb + bin] = val;                     // keep delta for the combine / exact walk
       if (val != val) anyNan = true;
       if (val > M) { M = val; pos = bin; }
     }
@@ -405,7 +408,7 @@ __device__ inline void track_summary(const NodeCtx& c, int ci) {
       int bin = (ch << 5) + lane;
       uint32_t wd = m.pres[ci * 8 + ch];
       bool present = ((wd >> lane) & 1u) && bin != last && bin < pos;
-      if (present && !((M - m.sL[ci * kHistBins + bin]) > kEpsilon)) near = true;
+      if (present && !((M - m.sL[ci * m.hb + bin]) > kEpsilon)) near = true;
     }
     near = __any_sync(0xffffffffu, near);
   }
@@ -430,7 +433,7 @@ __device__ inline void track_exact(const NodeCtx& c, int ci) {
     int bin = (ch << 5) + lane;
     uint32_t wd = m.pres[ci * 8 + ch];
     bool present = ((wd >> lane) & 1u) && bin != last;
-    double val = present ? m.sL[ci * kHistBins + bin] : 0.0;
+    double val = present ? m.sL[ci * m.hb + bin] : 0.0;
     if (c.w.sinkDelta) {
       unsigned pm = __ballot_sync(0xffffffffu, present);
       if (present) {
@@ -508,7 +511,7 @@ __device__ inline void track_combine_all(const NodeCtx& c, int nc) {
 // ---- sorted-walk path for covariates with more than kHistBins distinct values ----------------
 __device__ inline void radix_pass(const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout,
                                   uint32_t len, int shift, GrowShared* s, uint32_t* rbase) {
-  const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+  const int tid = vtid(), lane = lane_id(), wid = warp_id();
   __syncthreads();
   rbase[tid] = 0;
   __syncthreads();
@@ -550,7 +553,7 @@ __device__ inline void stratum_totals(const NodeCtx& c, uint32_t len) {
   for (int k = 1; k <= c.Kloop; k++) {
     uint32_t s0 = m.segpos[k], s1 = m.segpos[k + 1];
     unsigned long long ne = 0; double vT = 0.0, vW = 0.0;
-    for (uint32_t i = s0 + threadIdx.x; i < s1; i += kThreads) {
+    for (uint32_t i = s0 + vtid(); i < s1; i += kThreads) {
       uint32_t ent = c.list[i];
       uint32_t row = ent & kRowMask, mult = (ent >> kRowBits) + 1u;
       uint32_t e = c.d.ev[row];
@@ -562,7 +565,7 @@ __device__ inline void stratum_totals(const NodeCtx& c, uint32_t len) {
     unsigned long long tne = block_sum<unsigned long long>(ne, s->scrU);
     double tT = block_sum<double>(vT, s->scrD);
     double tW = block_sum<double>(vW, s->scrD);
-    if (threadIdx.x == 0) {
+    if (vtid() == 0) {
       m.PN[k] = (uint32_t)(tne >> 32); m.PE[k] = (uint32_t)(tne & 0xffffffffu);
       m.PT[k] = tT; m.PW[k] = tW;
     }
@@ -574,7 +577,7 @@ __device__ inline void stratum_totals(const NodeCtx& c, uint32_t len) {
 __device__ inline void sort_candidate(const NodeCtx& c, int ci, uint32_t len) {
   GrowSmem& m = c.m;
   GrowShared* s = m.s;
-  const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+  const int tid = vtid(), lane = lane_id(), wid = warp_id();
   const int n = c.d.n;
   uint32_t* kA = c.w.sortbuf + (size_t)c.tree * 4 * n;
   uint32_t* kB = kA + n; uint32_t* vA = kB + n; uint32_t* vB = vA + n;
@@ -693,7 +696,7 @@ __device__ inline void sort_candidate(const NodeCtx& c, int ci, uint32_t len) {
 __device__ inline void score_small(NodeCtx& c) {
   GrowSmem& m = c.m;
   GrowShared* s = m.s;
-  const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+  const int tid = vtid(), lane = lane_id(), wid = warp_id();
   const int nc = s->nc;
   const uint32_t len = s->cur.len;
   const DevData& d = c.d;
@@ -813,14 +816,14 @@ __device__ inline void score_small(NodeCtx& c) {
   const int nAct = s->nAct;
   for (int ci = wid; ci < nc; ci += kWarps) {
     const int Dc = s->candD[ci];
-    for (int b = lane; b < Dc; b += 32) { m.sL[ci * kHistBins + b] = 0.0; m.sR[ci * kHistBins + b] = 0.0; }
+    for (int b = lane; b < Dc; b += 32) { m.sL[ci * m.hb + b] = 0.0; m.sR[ci * m.hb + b] = 0.0; }
     const uint8_t* cptr = m.smCodes + ci * kSmallMax;
     __syncwarp();
     for (int ia = 0; ia < nAct; ia++) {
       const int a = (int)m.cE[ia];
       const uint32_t b0 = m.segpos[a], b1 = m.cN[a];
       for (uint32_t i = b0 + lane; i < b1; i += 32) {
-        const int idx = ci * kHistBins + (int)cptr[i];
+        const int idx = ci * m.hb + (int)cptr[i];
         const uint32_t mu = m.smMult[i];
         const double tv = m.smT[i];
         hist_add(m, idx, mu, m.smE[i], c.unit, tv == d.rt_mode, (double)mu * tv);
@@ -843,7 +846,7 @@ __device__ inline void score_small(NodeCtx& c) {
 // ---- score all drawn candidates of the current node (steps 2-4) ------------------------------
 __device__ inline void score_node(const DevData& d, const GrowParams& g, const GrowWork& w, GrowSmem& m, int tree) {
   GrowShared* s = m.s;
-  const int tid = threadIdx.x;
+  const int tid = vtid();
   const int nc = s->nc;
   const NodeEnt cur = s->cur;
   const uint32_t* list = w.lists + ((size_t)tree * 2 + cur.buf) * d.n + cur.start;
@@ -875,7 +878,7 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
   } else if (tid == 0) {
     m.segpos[0] = 0; m.segpos[1] = 0; m.segpos[2] = cur.len;
   }
-  for (int i = tid; i < nc * kHistBins; i += kThreads) { m.sL[i] = 0.0; m.sR[i] = 0.0; }
+  for (int i = tid; i < nc * m.hb; i += kThreads) { m.sL[i] = 0.0; m.sR[i] = 0.0; }
   for (int i = tid; i < nc * 8; i += kThreads) m.pres[i] = 0u;
   if (tid < nc) m.statP[tid] = 0.0;
   if (tid == 0) { s->have = 0; s->bestDelta = 0.0; s->bestCand = -1; s->bestCode = 0; s->cutsSeen = 0; }
@@ -914,7 +917,7 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
 #pragma unroll
             for (int q = 0; q < 8; q++) {
               const int ci = half + q;
-              if (ci < nc && ((hmask >> ci) & 1u)) hist_add(m, ci * kHistBins + (int)raw[q], mult, e, unit, isT0, ft);
+              if (ci < nc && ((hmask >> ci) & 1u)) hist_add(m, ci * m.hb + (int)raw[q], mult, e, unit, isT0, ft);
             }
           }
         }
@@ -1009,19 +1012,22 @@ __device__ inline bool append_record(const GrowWork& w, GrowShared* s, int tree,
   return true;
 }
 
-extern "C" __global__ void __launch_bounds__(kThreads, 2)
+#ifndef RF_MIN_CTAS
+#define RF_MIN_CTAS 2
+#endif
+extern "C" __global__ void __launch_bounds__(kThreads, RF_MIN_CTAS)
 rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  GrowSmem m = carve(smem_raw, g.ncmax, d.K);
+  GrowSmem m = carve(smem_raw, g.ncmax, d.K, g.hbins);
   GrowShared* s = m.s;
-  const int tid = threadIdx.x;
+  const int tid = vtid();
   const int tree = blockIdx.x;
   const int n = d.n;
   uint32_t* listA = w.lists + (size_t)tree * 2 * n;
   const uint16_t* cnt = w.cnt + (size_t)tree * w.cntStride;
 
   // ---- clean histograms (flushes keep them clean afterwards) ----
-  for (int i = tid; i < g.ncmax * kHistBins; i += kThreads) { m.hN[i] = 0; m.hE[i] = 0; m.hNx[i] = 0; m.hEx[i] = 0; m.hT[i] = 0.0; m.hW[i] = 0.0; }
+  for (int i = tid; i < g.ncmax * m.hb; i += kThreads) { m.hN[i] = 0; m.hE[i] = 0; m.hNx[i] = 0; m.hEx[i] = 0; m.hT[i] = 0.0; m.hW[i] = 0.0; }
   if (tid == 0) {
     for (int k = 0; k < kProfSlots; k++) s->prof[k] = 0;
     s->tmark = clock64();

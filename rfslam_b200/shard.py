@@ -1,0 +1,78 @@
+"""Tree sharding across GPUs: one process per GPU, rank r grows trees
+r+1, r+1+G, ... of the SAME ntree-tree forest (chain seeds are derived for all ntree trees on
+every rank, randomForestSRC.c:6664-6692, so tree b is identical for any G).  Nothing is exchanged
+while trees grow; afterwards the ensemble numerators / denominators are summed
+(randomForestSRC.c:944-949 does the same under per-row locks) and, if wanted, the variable-length
+forest records are gathered to rank 0.  Works with any torch.distributed backend (NCCL on the
+GPUs, gloo in the CPU tests)."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+
+FOREST_KEYS = ("treeID", "nodeID", "parmID", "contPT", "mwcpSZ")
+LEAF_KEYS = ("tnRCNT", "tnACNT")
+
+
+def shard_tree_ids(rank: int, world: int, ntree: int) -> np.ndarray:
+    """1-based ids of the trees rank `rank` grows: tree b -> rank (b - 1) mod world."""
+    return np.arange(rank + 1, ntree + 1, world, dtype=np.int32)
+
+
+def allreduce_ensembles(f: Dict[str, np.ndarray], *, device=None, group=None) -> Dict[str, np.ndarray]:
+    """Sum the per-shard ensemble sums over ranks and finish them (randomForestSRC.c:8113-8125:
+    numerator / denominator where the denominator is non-zero, 0 otherwise)."""
+    import torch
+    import torch.distributed as dist
+    n = f["allEnsbDen"].size
+    num = torch.from_numpy(np.concatenate([f["oobEnsbCLS"], f["allEnsbCLS"]]).astype(np.float64))
+    den = torch.from_numpy(np.concatenate([f["oobEnsbDen"], f["allEnsbDen"]]).astype(np.int64))
+    if device is not None:
+        num, den = num.to(device), den.to(device)
+    dist.all_reduce(num, group=group)
+    dist.all_reduce(den, group=group)
+    num, den = num.cpu().numpy(), den.cpu().numpy()
+    out = dict(f)
+    for k, (lo, dlo) in {"oobEnsbCLS": (0, 0), "allEnsbCLS": (2 * n, n)}.items():
+        d = den[dlo:dlo + n].astype(np.float64)
+        v = num[lo:lo + 2 * n].reshape(2, n)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            out[k] = np.where(d > 0, v / np.where(d > 0, d, 1.0), 0.0).reshape(-1)
+    out["oobEnsbDen"] = den[:n].astype(np.uint32)
+    out["allEnsbDen"] = den[n:].astype(np.uint32)
+    return out
+
+
+def gather_forest(f: Dict[str, np.ndarray], *, dst: int = 0, group=None) -> Optional[Dict[str, np.ndarray]]:
+    """Gather the shards' forest records to rank `dst` and put the trees in ascending treeID order
+    (records of one tree stay contiguous and in pre-order, randomForestSRC.c:10735-10806)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    payload = {k: f[k] for k in FOREST_KEYS + LEAF_KEYS + ("tnCLAS", "leafCount", "seed", "tree_ids")}
+    gathered: List[Optional[dict]] = [None] * world if rank == dst else None
+    dist.gather_object(payload, gathered, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return merge_shards(gathered)
+
+
+def merge_shards(parts: List[Dict[str, np.ndarray]]) -> Dict[str, np.ndarray]:
+    trees = []
+    for p in parts:
+        noff = np.concatenate([[0], np.cumsum(2 * p["leafCount"].astype(np.int64) - 1)])
+        loff = np.concatenate([[0], np.cumsum(p["leafCount"].astype(np.int64))])
+        for t, b in enumerate(p["tree_ids"]):
+            trees.append((int(b), p, t, noff, loff))
+    trees.sort(key=lambda x: x[0])
+    out: Dict[str, List[np.ndarray]] = {k: [] for k in FOREST_KEYS + LEAF_KEYS + ("tnCLAS", "leafCount", "seed", "tree_ids")}
+    for b, p, t, noff, loff in trees:
+        for k in FOREST_KEYS:
+            out[k].append(p[k][noff[t]:noff[t + 1]])
+        for k in LEAF_KEYS:
+            out[k].append(p[k][loff[t]:loff[t + 1]])
+        out["tnCLAS"].append(p["tnCLAS"][2 * loff[t]:2 * loff[t + 1]])
+        out["leafCount"].append(p["leafCount"][t:t + 1]); out["seed"].append(p["seed"][t:t + 1])
+        out["tree_ids"].append(np.array([b], np.int32))
+    return {k: np.concatenate(v) if v else np.zeros(0) for k, v in out.items()}
