@@ -29,6 +29,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# torchrun exports OMP_NUM_THREADS=1; the reference arm / CPU baseline (OpenMP over trees,
+# randomForestSRC.c:7082-7087) must see every host core, so set it before libgomp is loaded
+os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
 
 WORKLOAD = dict(n=1_000_000, p=50, levels=64, ntree=500, nodesize=20, rule=4, seed=-12345, k_for_alpha=2.0)
 
@@ -160,8 +163,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=0, help="override rows (debug)")
-    ap.add_argument("--ntree", type=int, default=0, help="override trees per GPU (debug)")
+    ap.add_argument("--rows", type=int, default=0, help="override rows (debug; not --n: torchrun abbreviates it to --nnodes)")
+    ap.add_argument("--trees", type=int, default=0, help="override trees per GPU (debug)")
     ap.add_argument("--ref-sample-n", type=int, default=100_000)
     ap.add_argument("--ref-ntree", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -173,10 +176,10 @@ def main():
     import rfslam_b200
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = dict(WORKLOAD)
-    if args.n:
-        cfg["n"] = args.n
-    if args.ntree:
-        cfg["ntree"] = args.ntree
+    if args.rows:
+        cfg["n"] = args.rows
+    if args.trees:
+        cfg["ntree"] = args.trees
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: rfslam_b200 has no CPU fallback")
     torch.cuda.set_device(local)

@@ -244,6 +244,11 @@ int dataset_build(const rfslam_grow_args* a, rfslam_dataset** out) {
 
       // dominant risk time: the modal value of a sample (any value is correct; the mode is fastest)
       double rt_mode = a->risk_time[0];
+      for (int i = 0; i < n; i++) {
+        const double t = a->risk_time[i];
+        if (t < 0.0) { set_error("negative risk time at row %d", i + 1); throw CudaFail{RFSLAM_EINVAL}; }
+        if (t > ds->max_rt) ds->max_rt = t;
+      }
       {
         std::vector<double> smp;
         const int step = std::max(1, n / 65536);

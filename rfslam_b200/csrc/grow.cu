@@ -2,6 +2,7 @@
 // tree kernel: chain-A bootstrap replay (K1), record compaction, and the row-parallel traversal
 // that yields node membership, all-row leaf counts and the OOB / full ensembles (K4/K5).
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -277,6 +278,12 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     g.pw = (p + 31) / 32; g.ncmax = std::min(cfg.mtry, kMaxCand);
     g.has_sort = ds->max_D > kHistBins;
     g.hbins = ds->hist_bins;
+    {   // fixed-point scale of the exposure accumulators: the largest power of two that keeps
+        // (bootstrap size) * (max risk time) below 2^62
+      int ex = 0;
+      frexp(std::max((double)maxBoot * std::max(ds->max_rt, 1e-300), 1.0), &ex);
+      g.tscale = ldexp(1.0, 62 - ex); g.tinv = ldexp(1.0, ex - 62);
+    }
     DevBuf<double> d_sw(pool);
     if (a->x_split_stat_weight) {
       bool allOne = true;
@@ -505,6 +512,7 @@ int score_node_impl(int rule, double k_for_alpha, int m, const double* x, const 
     GrowParams g{};
     g.rule = rule; g.mtry = 1; g.nodesize = 1; g.nodedepth = -1; g.alpha = 1.0 / (k_for_alpha * k_for_alpha);
     g.pw = 1; g.ncmax = 1; g.has_sort = ds->max_D > kHistBins; g.hbins = ds->hist_bins;
+    { int ex = 0; frexp(std::max((double)m * std::max(ds->max_rt, 1e-300), 1.0), &ex); g.tscale = ldexp(1.0, 62 - ex); g.tinv = ldexp(1.0, ex - 62); }
     const size_t smem = grow_smem_bytes(g.ncmax, ds->K, g.hbins);
     RF_CUDA(cudaFuncSetAttribute(rfslam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DevBuf<uint32_t> d_lists, d_sort, d_stackPerm, d_ctab, d_nodeCount, d_leafCount, d_cursor;

@@ -60,6 +60,7 @@ struct GrowParams {
   int ncmax;                     // min(mtry, kMaxCand)
   int has_sort;                  // any covariate with D > kHistBins
   int hbins;                     // histogram stride (see GrowSmem::hb)
+  double tscale, tinv;           // 2^S and 2^-S of the fixed-point exposure accumulators (see hist_add)
 };
 
 struct GrowWork {
@@ -265,16 +266,31 @@ struct NodeCtx {
   int Kloop;
 };
 
-// one in-bag entry into one candidate's histogram: native 32-bit shared atomics for the counts;
-// the f64 exposure sums (CAS loops in shared memory on sm_100a) only see rows whose risk time
-// differs from the table's dominant value t0 -- in CPIU data that is the last interval of a person.
-__device__ __forceinline__ void hist_add(const GrowSmem& m, int idx, uint32_t mult, uint32_t e, bool unit, bool isT0, double ft) {
+// one in-bag entry into one candidate's histogram: native 32-bit shared atomics only.
+// f64 (and 64-bit) shared atomics are CAS loops on sm_100a (ATOMS.CAST.SPIN) and were the top stall
+// of the kernel, so (a) exposure is kept as rt_mode * (N - Nx) + Tx: only rows whose risk time
+// differs from the table's dominant value t0 (in CPIU data: the last interval of a person) touch
+// the exposure accumulators at all, and (b) those accumulate in 64-bit fixed point (resolution
+// 2^-S, S = 62 - ceil(log2(bootstrap size * max risk time)), 2^-43 at 1M rows) as two native 32-bit
+// adds: the low word's returned old value tells this add whether IT caused the carry.
+__device__ __forceinline__ void fixed_add(double* acc, unsigned long long x) {
+  uint32_t* w32 = (uint32_t*)acc;
+  const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 32);
+  const uint32_t old = atomicAdd(&w32[0], xl);
+  const uint32_t hi = xh + (((uint32_t)(old + xl) < old) ? 1u : 0u);
+  if (hi) atomicAdd(&w32[1], hi);
+}
+__device__ __forceinline__ double fixed_get(const double* acc, double tinv) {
+  return (double)(*(const unsigned long long*)acc) * tinv;
+}
+
+__device__ __forceinline__ void hist_add(const GrowSmem& m, int idx, uint32_t mult, uint32_t e, bool unit, bool isT0, unsigned long long fx) {
   atomicAdd(&m.hN[idx], mult);
   if (e) atomicAdd(&m.hE[idx], mult);
   if (!unit && !isT0) {
     atomicAdd(&m.hNx[idx], mult);
-    atomicAdd(&m.hT[idx], ft);
-    if (e) { atomicAdd(&m.hEx[idx], mult); atomicAdd(&m.hW[idx], ft); }
+    fixed_add(&m.hT[idx], fx);
+    if (e) { atomicAdd(&m.hEx[idx], mult); fixed_add(&m.hW[idx], fx); }
   }
 }
 
@@ -300,8 +316,8 @@ __device__ __forceinline__ void flush_candidate(const NodeCtx& c, int ci, uint32
     if (bin < Dc) {
       vN = hN[bin]; vE = hE[bin];
       if (!c.unit) {                                               // exposure = t0 * (rows at the dominant risk time) + the rest
-        vT = t0 * (double)(vN - hNx[bin]) + hT[bin];
-        vW = t0 * (double)(vE - hEx[bin]) + hW[bin];
+        vT = t0 * (double)(vN - hNx[bin]) + fixed_get(&hT[bin], c.g.tinv);
+        vW = t0 * (double)(vE - hEx[bin]) + fixed_get(&hW[bin], c.g.tinv);
       }
       hN[bin] = 0; hE[bin] = 0; hNx[bin] = 0; hEx[bin] = 0; hT[bin] = 0.0; hW[bin] = 0.0;   // leave the histogram clean
     }
@@ -347,7 +363,7 @@ __device__ inline void flush_stratum(const NodeCtx& c, int nc) {
       int bin = (ch << 5) + lane;
       if (bin < Dc) {
         tN += hN[bin]; tE += hE[bin];
-        if (!c.unit) { tT += t0 * (double)(hN[bin] - hNx[bin]) + hT[bin]; tW += t0 * (double)(hE[bin] - hEx[bin]) + hW[bin]; }
+        if (!c.unit) { tT += t0 * (double)(hN[bin] - hNx[bin]) + fixed_get(&hT[bin], c.g.tinv); tW += t0 * (double)(hE[bin] - hEx[bin]) + fixed_get(&hW[bin], c.g.tinv); }
       }
     }
     tN = warp_sum(tN); tE = warp_sum(tE);
@@ -826,7 +842,7 @@ __device__ inline void score_small(NodeCtx& c) {
         const int idx = ci * m.hb + (int)cptr[i];
         const uint32_t mu = m.smMult[i];
         const double tv = m.smT[i];
-        hist_add(m, idx, mu, m.smE[i], c.unit, tv == d.rt_mode, (double)mu * tv);
+        hist_add(m, idx, mu, m.smE[i], c.unit, tv == d.rt_mode, (unsigned long long)__double2ll_rn(tv * c.g.tscale) * (unsigned long long)mu);
       }
       __syncwarp();
       flush_candidate(c, ci, m.PN[a], m.PE[a], m.PT[a], m.PW[a], m.cTR[a], false);
@@ -904,7 +920,7 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
         const uint32_t e = d.ev[row];
         const double tv = unit ? 0.0 : d.rt[row];
         const bool isT0 = tv == d.rt_mode;
-        const double ft = (double)mult * tv;
+        const unsigned long long ft = (unsigned long long)__double2ll_rn(tv * g.tscale) * (unsigned long long)mult;
 #pragma unroll
         for (int half = 0; half < kMaxCand; half += 8) {
           if (half < nc) {
@@ -1201,16 +1217,31 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
       }
       __syncthreads();
     } else {
+    // Four consecutive entries per thread in both passes: the four list loads, then the four
+    // dependent code gathers, are in flight together (the kernel is latency-bound, not HBM-bound).
     // pass 1: sizes of the left child
     unsigned long long cL = 0, neL = 0; double rtL = 0.0, rtR = 0.0;
-    for (uint32_t i = tid; i < cur.len; i += kThreads) {
-      const uint32_t ent = src[i];
-      const uint32_t row = ent & kRowMask;
-      const bool left = load_code(ptr, wd, row) <= bcode;          // LEFT iff cut - x >= 0 (rf.c:15194)
-      const uint32_t e = d.ev[row];
-      const uint32_t mult = (ent >> kRowBits) + 1u;
-      if (left) { cL++; neL += ((unsigned long long)mult << 32) | (unsigned long long)(e ? mult : 0u); }
-      if (bayes) { double v = (double)mult * d.rt[row]; if (left) rtL += v; else rtR += v; }
+    for (uint32_t base = 0; base < cur.len; base += 4u * kThreads) {
+      uint32_t ent[4]; uint32_t cd[4]; uint32_t ev4[4]; double rt4[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const uint32_t i = base + 4u * tid + u; ent[u] = (i < cur.len) ? src[i] : 0xFFFFFFFFu; }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const bool valid = ent[u] != 0xFFFFFFFFu;
+        const uint32_t row = ent[u] & kRowMask;
+        cd[u] = valid ? load_code(ptr, wd, row) : 0xFFFFFFFFu;
+        ev4[u] = valid ? (uint32_t)d.ev[row] : 0u;
+        rt4[u] = (valid && bayes) ? d.rt[row] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (ent[u] != 0xFFFFFFFFu) {
+          const bool left = cd[u] <= bcode;                        // LEFT iff cut - x >= 0 (rf.c:15194)
+          const uint32_t mult = (ent[u] >> kRowBits) + 1u;
+          if (left) { cL++; neL += ((unsigned long long)mult << 32) | (unsigned long long)(ev4[u] ? mult : 0u); }
+          if (bayes) { const double v = (double)mult * rt4[u]; if (left) rtL += v; else rtR += v; }
+        }
+      }
     }
     nL = (uint32_t)block_sum<unsigned long long>(cL, s->scrU);
     tneL = block_sum<unsigned long long>(neL, s->scrU);
@@ -1219,20 +1250,26 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     // pass 2: stable scatter
     {
       uint32_t baseL = 0, baseR = 0;
-      const uint32_t ntiles = (cur.len + kThreads - 1) / kThreads;
-      for (uint32_t t = 0; t < ntiles; t++) {
-        uint32_t i = t * kThreads + tid;
-        bool valid = i < cur.len;
-        uint32_t ent = 0u; bool left = false;
-        if (valid) { ent = src[i]; left = load_code(ptr, wd, ent & kRowMask) <= bcode; }
+      for (uint32_t base = 0; base < cur.len; base += 4u * kThreads) {
+        uint32_t ent[4]; uint32_t cd[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const uint32_t i = base + 4u * tid + u; ent[u] = (i < cur.len) ? src[i] : 0xFFFFFFFFu; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) cd[u] = (ent[u] != 0xFFFFFFFFu) ? load_code(ptr, wd, ent[u] & kRowMask) : 0xFFFFFFFFu;
+        uint32_t mine = 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) mine += (ent[u] != 0xFFFFFFFFu && cd[u] <= bcode) ? 1u : 0u;
         unsigned long long tot;
-        unsigned long long inc = block_incl_scan<unsigned long long>(left ? 1ull : 0ull, s->scrU, tot);
-        uint32_t before = (uint32_t)inc - (left ? 1u : 0u);
-        if (valid) {
-          if (left) dst[baseL + before] = ent;
-          else dst[nL + baseR + ((uint32_t)tid - before)] = ent;
+        const unsigned long long inc = block_incl_scan<unsigned long long>((unsigned long long)mine, s->scrU, tot);
+        uint32_t before = (uint32_t)inc - mine;                     // left entries of this tile before mine
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (ent[u] != 0xFFFFFFFFu) {
+            if (cd[u] <= bcode) { dst[baseL + before] = ent[u]; before++; }
+            else dst[nL + baseR + (4u * tid + u - before)] = ent[u];
+          }
         }
-        uint32_t nvalid = min((uint32_t)kThreads, cur.len - t * kThreads);
+        const uint32_t nvalid = min(4u * kThreads, cur.len - base);
         baseL += (uint32_t)tot;
         baseR += nvalid - (uint32_t)tot;
         __syncthreads();

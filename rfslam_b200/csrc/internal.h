@@ -72,6 +72,7 @@ struct rfslam_dataset {
   std::vector<double*> uniq_h;
   int64_t bytes = 0;
   int max_D = 0;
+  double max_rt = 0.0;            // largest risk time (scale of the fixed-point exposure sums)
   int hist_bins = 32;             // pow2 >= the widest column with <= 256 distinct values
   rfslam::WsPool pool;            // scratch recycled across grow calls
 };
