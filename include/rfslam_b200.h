@@ -97,6 +97,7 @@ typedef struct rfslam_grow_args {
   int32_t        tree_step;           /*   (1-based ids; 0/0 = all).  Seeds are derived for all ntree */
                                       /*   trees on every rank, so tree b is identical for any sharding. */
   int32_t        finalize_ensembles;  /* 1: divide by the denominators (single process); 0: return sums */
+  int32_t        want_split_stat;     /* 1: also return splitStat (the winning delta per node) */
 } rfslam_grow_args;
 
 /* The reference's named output list for the class family (rf.c:9-79), sized by the
@@ -113,7 +114,7 @@ typedef struct rfslam_forest_out {
   int32_t  *parmID;            /* [total_nodes] 0 = terminal */
   double   *contPT;            /* [total_nodes] NA_REAL at terminals */
   int32_t  *mwcpSZ;            /* [total_nodes] all 0 (no factor splits on this path) */
-  double   *splitStat;         /* [total_nodes] winning delta (NaN at terminals); not a reference output */
+  double   *splitStat;         /* [total_nodes] winning delta (NaN at terminals) when want_split_stat, else NULL */
   int32_t  *leafCount;         /* [ntree] */
   int32_t  *seed;              /* [ntree] chain-A seed, as forest$seed */
   int32_t  *tnRCNT;            /* [total_leaves] in-bag count per leaf, by tree then leaf id */

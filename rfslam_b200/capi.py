@@ -33,6 +33,7 @@ class GrowArgs(C.Structure):
         ("time_interest_size", C.c_int32), ("time_interest", _pd),
         ("n_impute", C.c_int32), ("perf_block", C.c_int32), ("num_threads", C.c_int32),
         ("device", C.c_int32), ("tree_first", C.c_int32), ("tree_step", C.c_int32), ("finalize_ensembles", C.c_int32),
+        ("want_split_stat", C.c_int32),
     ]
 
 

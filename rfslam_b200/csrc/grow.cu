@@ -324,8 +324,12 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     std::vector<int32_t> h_leafCount(T), h_seed(T);
     long long totalCand = 0, totalAlgo = 0, launches = 0;
     float growMs = 0.f, totalMs = 0.f;
-    cudaEvent_t ev0, ev1, ev2, ev3;
+    cudaEvent_t ev0, ev1, ev2, ev3, evC;
     RF_CUDA(cudaEventCreate(&ev0)); RF_CUDA(cudaEventCreate(&ev1)); RF_CUDA(cudaEventCreate(&ev2)); RF_CUDA(cudaEventCreate(&ev3));
+    RF_CUDA(cudaEventCreateWithFlags(&evC, cudaEventDisableTiming));
+    cudaStream_t copyStream;                                     // forest records go home while the traversal kernel runs
+    RF_CUDA(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
+    const bool wantStat = a->want_split_stat != 0;
 
     // ---- per-batch buffers ----
     DevBuf<uint32_t> d_lists(pool), d_sort(pool), d_draws(pool), d_stackPerm(pool), d_ctab(pool), d_nodeCount(pool), d_leafCount(pool), d_cursor(pool);
@@ -432,25 +436,29 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         dim3 gk((unsigned)std::min<uint32_t>((maxNodes + 255) / 256, 2048), (unsigned)nb);
         compact_kernel<<<gk, 256>>>(w, ds->dev, d_ids.p, d_nodeOff.p, d_leafOff.p, f_tree.p, f_node.p, f_parm.p, f_cont.p, f_stat.p,
                                     f_code.p, f_right.p, f_rcnt.p, f_clas.p);
+        RF_CUDA(cudaEventRecord(evC));
         membership_kernel<<<(n + 127) / 128, 128>>>(ds->dev, nb, d_nodeOff.p, d_leafOff.p, f_node.p, f_parm.p, f_code.p, f_right.p,
                                                     f_rcnt.p, f_clas.p, d_cnt.p, f_acnt.p, d_allNum.p, d_oobNum.p, d_allDen.p, d_oobDen.p,
                                                     d_nodeMemb.p, d_bootMemb.p, b0, cntStride, d_pathSum.p);
         launches += 2;
         RF_CUDA(cudaEventRecord(ev3));
         RF_CUDA(cudaGetLastError());
+        // ---- straight into the caller's arrays: the forest records are final after compaction, so
+        // their copies overlap the traversal kernel on a second stream ----
+        RF_CUDA(cudaStreamWaitEvent(copyStream, evC, 0));
+        RF_CUDA(cudaMemcpyAsync(h_treeID.grow(NN), f_tree.p, NN * 4, cudaMemcpyDeviceToHost, copyStream));
+        RF_CUDA(cudaMemcpyAsync(h_nodeID.grow(NN), f_node.p, NN * 4, cudaMemcpyDeviceToHost, copyStream));
+        RF_CUDA(cudaMemcpyAsync(h_parmID.grow(NN), f_parm.p, NN * 4, cudaMemcpyDeviceToHost, copyStream));
+        RF_CUDA(cudaMemcpyAsync(h_contPT.grow(NN), f_cont.p, NN * 8, cudaMemcpyDeviceToHost, copyStream));
+        if (wantStat) RF_CUDA(cudaMemcpyAsync(h_stat.grow(NN), f_stat.p, NN * 8, cudaMemcpyDeviceToHost, copyStream));
+        RF_CUDA(cudaMemcpyAsync(h_tnRCNT.grow(NL), f_rcnt.p, NL * 4, cudaMemcpyDeviceToHost, copyStream));
+        RF_CUDA(cudaMemcpyAsync(h_tnCLAS.grow(2 * NL), f_clas.p, 2 * NL * 4, cudaMemcpyDeviceToHost, copyStream));
+        RF_CUDA(cudaStreamSynchronize(copyStream));
         RF_CUDA(cudaEventSynchronize(ev3));
         float ms = 0.f;
         RF_CUDA(cudaEventElapsedTime(&ms, ev1, ev2)); growMs += ms;
         RF_CUDA(cudaEventElapsedTime(&ms, ev0, ev3)); totalMs += ms;
-        // ---- straight into the caller's arrays ----
-        RF_CUDA(cudaMemcpy(h_treeID.grow(NN), f_tree.p, NN * 4, cudaMemcpyDeviceToHost));
-        RF_CUDA(cudaMemcpy(h_nodeID.grow(NN), f_node.p, NN * 4, cudaMemcpyDeviceToHost));
-        RF_CUDA(cudaMemcpy(h_parmID.grow(NN), f_parm.p, NN * 4, cudaMemcpyDeviceToHost));
-        RF_CUDA(cudaMemcpy(h_contPT.grow(NN), f_cont.p, NN * 8, cudaMemcpyDeviceToHost));
-        RF_CUDA(cudaMemcpy(h_stat.grow(NN), f_stat.p, NN * 8, cudaMemcpyDeviceToHost));
-        RF_CUDA(cudaMemcpy(h_tnRCNT.grow(NL), f_rcnt.p, NL * 4, cudaMemcpyDeviceToHost));
         RF_CUDA(cudaMemcpy(h_tnACNT.grow(NL), f_acnt.p, NL * 4, cudaMemcpyDeviceToHost));
-        RF_CUDA(cudaMemcpy(h_tnCLAS.grow(2 * NL), f_clas.p, 2 * NL * 4, cudaMemcpyDeviceToHost));
         break;
       }
     }
@@ -461,7 +469,8 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
       launches += 2;
       RF_CUDA(cudaGetLastError());
     }
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2); cudaEventDestroy(ev3);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2); cudaEventDestroy(ev3); cudaEventDestroy(evC);
+    cudaStreamDestroy(copyStream);
     unsigned long long pathSum = 0;
     RF_CUDA(cudaMemcpy(&pathSum, d_pathSum.p, 8, cudaMemcpyDeviceToHost));
     totalAlgo += 16ll * (long long)pathSum;                      // B_part's all-row term
@@ -472,7 +481,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     out->tree_ids = (int32_t*)malloc((size_t)T * 4); memcpy(out->tree_ids, ids.data(), (size_t)T * 4);
     out->mwcpSZ = (int32_t*)calloc(std::max<size_t>(h_treeID.n, 1), 4);
     out->treeID = h_treeID.release(); out->nodeID = h_nodeID.release(); out->parmID = h_parmID.release();
-    out->contPT = h_contPT.release(); out->splitStat = h_stat.release();
+    out->contPT = h_contPT.release(); out->splitStat = wantStat ? h_stat.release() : nullptr;
     out->leafCount = (int32_t*)malloc((size_t)T * 4); memcpy(out->leafCount, h_leafCount.data(), (size_t)T * 4);
     out->seed = (int32_t*)malloc((size_t)T * 4); memcpy(out->seed, h_seed.data(), (size_t)T * 4);
     out->tnRCNT = h_tnRCNT.release(); out->tnACNT = h_tnACNT.release(); out->tnCLAS = h_tnCLAS.release();
