@@ -156,14 +156,19 @@ struct GrowSmem {
   uint32_t* smEnt; double* smT; uint8_t *smMult, *smE, *smS, *smCodes;
   GrowShared* s;
   int hb;                            // bins per candidate histogram: pow2 >= the widest byte-coded column, 32..256
+  int hs;                            // stratum slots per candidate histogram (large nodes accumulate hs strata per pass)
 };
 
+__host__ __device__ inline int hist_slots(int hb) { int g = 256 / hb; return g < 1 ? 1 : (g > 4 ? 4 : g); }
+
 __host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K, int hb) {
+  const size_t hs = (size_t)hist_slots(hb);
   size_t KS = (size_t)K + 2;
   size_t b = 0;
-  b += (size_t)ncmax * hb * 8 * 4;             // sL sR hT hW
+  b += (size_t)ncmax * hb * 8 * 2;             // sL sR
+  b += (size_t)ncmax * hb * hs * 8 * 2;        // hT hW
   b += (size_t)ncmax * 8;                      // statP
-  b += (size_t)ncmax * hb * 4 * 4;             // hN hE hNx hEx
+  b += (size_t)ncmax * hb * hs * 4 * 4;        // hN hE hNx hEx
   b += (size_t)ncmax * 8 * 4;                  // pres
   b += KS * 8 * 6;                             // PT PW cT cW cTL cTR
   b += KS * 4 * 5;                             // segpos PN PE cN cE
@@ -176,19 +181,21 @@ __host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K, int hb) {
 __device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb) {
   GrowSmem m;
   m.hb = hb;
+  m.hs = hist_slots(hb);
+  const size_t hsz = (size_t)ncmax * hb * m.hs;
   size_t KS = (size_t)K + 2;
   double* d = (double*)raw;
   m.sL = d; d += (size_t)ncmax * hb;
   m.sR = d; d += (size_t)ncmax * hb;
-  m.hT = d; d += (size_t)ncmax * hb;
-  m.hW = d; d += (size_t)ncmax * hb;
+  m.hT = d; d += hsz;
+  m.hW = d; d += hsz;
   m.statP = d; d += ncmax;
   m.PT = d; d += KS; m.PW = d; d += KS; m.cT = d; d += KS; m.cW = d; d += KS; m.cTL = d; d += KS; m.cTR = d; d += KS;
   uint32_t* u = (uint32_t*)d;
-  m.hN = u; u += (size_t)ncmax * hb;
-  m.hE = u; u += (size_t)ncmax * hb;
-  m.hNx = u; u += (size_t)ncmax * hb;
-  m.hEx = u; u += (size_t)ncmax * hb;
+  m.hN = u; u += hsz;
+  m.hE = u; u += hsz;
+  m.hNx = u; u += hsz;
+  m.hEx = u; u += hsz;
   m.pres = u; u += (size_t)ncmax * 8;
   m.segpos = u; u += KS; m.PN = u; u += KS; m.PE = u; u += KS; m.cN = u; u += KS; m.cE = u; u += KS;
   {
@@ -296,16 +303,17 @@ __device__ __forceinline__ void hist_add(const GrowSmem& m, int idx, uint32_t mu
 
 // ---- per-stratum flush of one candidate's histogram (step 3), executed by one warp ----------
 // tN/tE/tT/tW are the stratum's totals in this node; the histogram is left clean.
-__device__ __forceinline__ void flush_candidate(const NodeCtx& c, int ci, uint32_t tN, uint32_t tE, double tT, double tW,
+__device__ __forceinline__ void flush_candidate(const NodeCtx& c, int ci, int slot, uint32_t tN, uint32_t tE, double tT, double tW,
                                                 double termP, bool updatePres) {
   GrowSmem& m = c.m;
   GrowShared* s = m.s;
   const int lane = lane_id();
   const int Dc = s->candD[ci];
   const int nch = (Dc + 31) >> 5;
-  uint32_t* hN = m.hN + ci * m.hb; uint32_t* hE = m.hE + ci * m.hb;
-  uint32_t* hNx = m.hNx + ci * m.hb; uint32_t* hEx = m.hEx + ci * m.hb;
-  double* hT = m.hT + ci * m.hb;   double* hW = m.hW + ci * m.hb;
+  const int ho = (ci * m.hs + slot) * m.hb;
+  uint32_t* hN = m.hN + ho; uint32_t* hE = m.hE + ho;
+  uint32_t* hNx = m.hNx + ho; uint32_t* hEx = m.hEx + ho;
+  double* hT = m.hT + ho;   double* hW = m.hW + ho;
   const double t0 = c.d.rt_mode;
   const bool active = tE > 0;
   uint32_t cN = 0, cE = 0; double cT = 0.0, cW = 0.0;     // carries (warp-uniform)
@@ -345,8 +353,9 @@ __device__ __forceinline__ void flush_candidate(const NodeCtx& c, int ci, uint32
   }
 }
 
-// large-node variant: totals come from the histogram itself
-__device__ inline void flush_stratum(const NodeCtx& c, int nc) {
+// large-node variant: totals come from the histogram itself; `nslots` strata were accumulated in
+// this pass (slot q = stratum k0 + q) and are flushed in ascending order
+__device__ inline void flush_stratum(const NodeCtx& c, int nc, int nslots) {
   GrowSmem& m = c.m;
   GrowShared* s = m.s;
   const int lane = lane_id();
@@ -354,27 +363,30 @@ __device__ inline void flush_stratum(const NodeCtx& c, int nc) {
     if (!s->candHist[ci]) continue;
     const int Dc = s->candD[ci];
     const int nch = (Dc + 31) >> 5;
-    const uint32_t* hN = m.hN + ci * m.hb; const uint32_t* hE = m.hE + ci * m.hb;
-    const uint32_t* hNx = m.hNx + ci * m.hb; const uint32_t* hEx = m.hEx + ci * m.hb;
-    const double* hT = m.hT + ci * m.hb;   const double* hW = m.hW + ci * m.hb;
     const double t0 = c.d.rt_mode;
-    uint32_t tN = 0, tE = 0; double tT = 0.0, tW = 0.0;
-    for (int ch = 0; ch < nch; ch++) {
-      int bin = (ch << 5) + lane;
-      if (bin < Dc) {
-        tN += hN[bin]; tE += hE[bin];
-        if (!c.unit) { tT += t0 * (double)(hN[bin] - hNx[bin]) + fixed_get(&hT[bin], c.g.tinv); tW += t0 * (double)(hE[bin] - hEx[bin]) + fixed_get(&hW[bin], c.g.tinv); }
+    for (int slot = 0; slot < nslots; slot++) {
+      const int ho = (ci * m.hs + slot) * m.hb;
+      const uint32_t* hN = m.hN + ho; const uint32_t* hE = m.hE + ho;
+      const uint32_t* hNx = m.hNx + ho; const uint32_t* hEx = m.hEx + ho;
+      const double* hT = m.hT + ho;   const double* hW = m.hW + ho;
+      uint32_t tN = 0, tE = 0; double tT = 0.0, tW = 0.0;
+      for (int ch = 0; ch < nch; ch++) {
+        int bin = (ch << 5) + lane;
+        if (bin < Dc) {
+          tN += hN[bin]; tE += hE[bin];
+          if (!c.unit) { tT += t0 * (double)(hN[bin] - hNx[bin]) + fixed_get(&hT[bin], c.g.tinv); tW += t0 * (double)(hE[bin] - hEx[bin]) + fixed_get(&hW[bin], c.g.tinv); }
+        }
       }
+      tN = warp_sum(tN); tE = warp_sum(tE);
+      if (c.unit) { tT = (double)tN; tW = (double)tE; } else { tT = warp_sum(tT); tW = warp_sum(tW); }
+      if (tN == 0) continue;
+      double termP = 0.0;
+      if (tE > 0) {
+        termP = side_term(c.bayes, (double)tE, (double)tN, tT, tW, c.g.alpha, c.beta);
+        if (lane == 0) m.statP[ci] += termP;
+      }
+      flush_candidate(c, ci, slot, tN, tE, tT, tW, termP, true);
     }
-    tN = warp_sum(tN); tE = warp_sum(tE);
-    if (c.unit) { tT = (double)tN; tW = (double)tE; } else { tT = warp_sum(tT); tW = warp_sum(tW); }
-    if (tN == 0) continue;
-    double termP = 0.0;
-    if (tE > 0) {
-      termP = side_term(c.bayes, (double)tE, (double)tN, tT, tW, c.g.alpha, c.beta);
-      if (lane == 0) m.statP[ci] += termP;
-    }
-    flush_candidate(c, ci, tN, tE, tT, tW, termP, true);
   }
 }
 
@@ -839,13 +851,13 @@ __device__ inline void score_small(NodeCtx& c) {
       const int a = (int)m.cE[ia];
       const uint32_t b0 = m.segpos[a], b1 = m.cN[a];
       for (uint32_t i = b0 + lane; i < b1; i += 32) {
-        const int idx = ci * m.hb + (int)cptr[i];
+        const int idx = ci * m.hs * m.hb + (int)cptr[i];
         const uint32_t mu = m.smMult[i];
         const double tv = m.smT[i];
         hist_add(m, idx, mu, m.smE[i], c.unit, tv == d.rt_mode, (unsigned long long)__double2ll_rn(tv * c.g.tscale) * (unsigned long long)mu);
       }
       __syncwarp();
-      flush_candidate(c, ci, m.PN[a], m.PE[a], m.PT[a], m.PW[a], m.cTR[a], false);
+      flush_candidate(c, ci, 0, m.PN[a], m.PE[a], m.PT[a], m.PW[a], m.cTR[a], false);
       __syncwarp();
     }
     if (lane == 0) m.statP[ci] = s->statPnode;
@@ -910,15 +922,23 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
     const uint8_t* __restrict__ hptr[kMaxCand];
 #pragma unroll
     for (int ci = 0; ci < kMaxCand; ci++) hptr[ci] = (ci < nc) ? (const uint8_t*)s->candPtr[ci] : nullptr;
-    for (int k = 1; k <= Kloop; k++) {
-      const uint32_t s0 = m.segpos[k], s1 = m.segpos[k + 1];
+    const int hstride = m.hs * m.hb;
+    for (int k0 = 1; k0 <= Kloop; k0 += m.hs) {
+      // one pass accumulates the next hs strata (a contiguous entry range: the list is stratum-major),
+      // slot = stratum - k0, so the dependent gathers of a mid-size node are exposed once per hs strata
+      const int ns = min(m.hs, Kloop - k0 + 1);
+      const uint32_t s0 = m.segpos[k0], s1 = m.segpos[k0 + ns];
       if (s0 == s1) continue;
+      uint32_t bnd[3];
+#pragma unroll
+      for (int q = 0; q < 3; q++) bnd[q] = (q + 1 < ns) ? m.segpos[k0 + q + 1] : 0xFFFFFFFFu;
       for (uint32_t i = s0 + tid; i < s1; i += kThreads) {
         const uint32_t ent = list[i];
         const uint32_t row = ent & kRowMask, mult = (ent >> kRowBits) + 1u;
         // issue every gather of this entry before the first shared-memory atomic
         const uint32_t e = d.ev[row];
         const double tv = unit ? 0.0 : d.rt[row];
+        const int slotOff = ((i >= bnd[0]) + (i >= bnd[1]) + (i >= bnd[2])) * m.hb;
         const bool isT0 = tv == d.rt_mode;
         const unsigned long long ft = (unsigned long long)__double2ll_rn(tv * g.tscale) * (unsigned long long)mult;
 #pragma unroll
@@ -933,14 +953,14 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
 #pragma unroll
             for (int q = 0; q < 8; q++) {
               const int ci = half + q;
-              if (ci < nc && ((hmask >> ci) & 1u)) hist_add(m, ci * m.hb + (int)raw[q], mult, e, unit, isT0, ft);
+              if (ci < nc && ((hmask >> ci) & 1u)) hist_add(m, ci * hstride + slotOff + (int)raw[q], mult, e, unit, isT0, ft);
             }
           }
         }
       }
       __syncthreads();
       RF_PROF(3);
-      flush_stratum(c, nc);
+      flush_stratum(c, nc, ns);
       __syncthreads();
       RF_PROF(4);
     }
@@ -1043,7 +1063,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
   const uint16_t* cnt = w.cnt + (size_t)tree * w.cntStride;
 
   // ---- clean histograms (flushes keep them clean afterwards) ----
-  for (int i = tid; i < g.ncmax * m.hb; i += kThreads) { m.hN[i] = 0; m.hE[i] = 0; m.hNx[i] = 0; m.hEx[i] = 0; m.hT[i] = 0.0; m.hW[i] = 0.0; }
+  for (int i = tid; i < g.ncmax * m.hb * m.hs; i += kThreads) { m.hN[i] = 0; m.hE[i] = 0; m.hNx[i] = 0; m.hEx[i] = 0; m.hT[i] = 0.0; m.hW[i] = 0.0; }
   if (tid == 0) {
     for (int k = 0; k < kProfSlots; k++) s->prof[k] = 0;
     s->tmark = clock64();
