@@ -11,8 +11,8 @@ for rep in range(2):
     print(f"grow wall {dt:.3f}s kernel {f['grow_kernel_ms']:.1f}ms total_dev {f['total_device_ms']:.1f}ms trees/s(kernel) {ntree/(f['grow_kernel_ms']/1e3):.1f} nodes {f['treeID'].size} cand {f['split_candidates']} cand/s {f['split_candidates']/(f['grow_kernel_ms']/1e3):.3e} algoGB {f['algorithmic_bytes']/1e9:.2f} GB/s {f['algorithmic_bytes']/1e9/(f['grow_kernel_ms']/1e3):.1f}", flush=True)
 import ctypes as C
 from rfslam_b200 import capi
-buf = (C.c_uint64*64)()
-k = capi.lib().rfslam_b200_last_profile(buf, 64)
+buf = (C.c_uint64*96)()
+k = capi.lib().rfslam_b200_last_profile(buf, 96)
 if k:
     names = ["root","gate+draw","segpos+zero","hist","flush","strat_tot","track","sortcand","part_count","part_scatter","leaf","split_book","x","x","small_list","x15"]
     tot = sum(buf[i] for i in list(range(12))+[14,15])
@@ -22,3 +22,9 @@ if k:
     for c in range(0,28): 
         if buf[16+c]: print(f"  2^{c}: {buf[16+c]:.3e} {100*buf[16+c]/max(tot,1):5.1f}%")
     print("node counts by class pair:", [int(buf[48+i]) for i in range(14)])
+
+if k >= 80:
+    tots = sum(buf[64+i] for i in list(range(12))+[14,15])
+    print("phases for nodes with < 64 entries: total %.3e (%.1f%% of all)" % (tots, 100*tots/max(tot,1)))
+    for i,nm in enumerate(names):
+        if buf[64+i]: print(f"  {nm:14s} {buf[64+i]:.3e} {100*buf[64+i]/max(tots,1):5.1f}%")

@@ -26,7 +26,10 @@ struct CudaFail { int code; };
 // ------------------------------------------------------------------------------------------
 // constants of the path
 // ------------------------------------------------------------------------------------------
-constexpr int      kThreads     = 256;          // CTA size of the tree kernel
+#ifndef RF_THREADS
+#define RF_THREADS 256
+#endif
+constexpr int      kThreads     = RF_THREADS;   // CTA size of the tree kernel (128 or 256)
 constexpr int      kWarps       = kThreads / 32;
 constexpr int      kHistBins    = 256;          // covariates with <= 256 distinct values score by histogram
 constexpr int      kMaxCand     = 16;           // mtry limit of the joint histogram pass

@@ -50,7 +50,7 @@ struct NodeEnt {        // a pending node of the DFS
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr int kSmallMax = 512;      // nodes with <= this many entries are scored entirely out of shared memory
-constexpr int kProfSlots = 64;   // 0..15 phases, 16..47 node time by log2(len), 48..63 node count by log2(len)/2
+constexpr int kProfSlots = 96;   // 64..79: the phase slots again, restricted to nodes with < 64 entries   // 0..15 phases, 16..47 node time by log2(len), 48..63 node count by log2(len)/2
 
 struct GrowParams {
   int rule, mtry, nodesize, nodedepth;
@@ -109,6 +109,8 @@ struct GrowShared {
   int abort;
   int ptotReady;
   int nAct; double statPnode; int isSmall; int poolSize;
+  // sparse evaluation of small nodes: the rows of the strata that contain events (<= 32), stratum-ascending
+  int nActRows; uint16_t actRow[32]; uint8_t actIa[32]; uint8_t actOff[34];
   int trkMaxBin[kMaxCand]; double trkMax[kMaxCand]; int trkClean[kMaxCand]; int trkNp[kMaxCand]; int trkLast[kMaxCand];
   unsigned long long prof[kProfSlots];
   long long tmark;
@@ -119,6 +121,7 @@ struct GrowShared {
     if (w.prof && vtid() == 0) {                                                  \
       long long now__ = clock64();                                                     \
       s->prof[slot] += (unsigned long long)(now__ - s->tmark);                         \
+      if (s->cur.len < 64u) s->prof[64 + (slot)] += (unsigned long long)(now__ - s->tmark); \
       s->tmark = now__;                                                                \
     }                                                                                  \
   } while (0)
@@ -159,7 +162,10 @@ struct GrowSmem {
   int hs;                            // stratum slots per candidate histogram (large nodes accumulate hs strata per pass)
 };
 
-__host__ __device__ inline int hist_slots(int hb) { int g = 256 / hb; return g < 1 ? 1 : (g > 4 ? 4 : g); }
+#ifndef RF_MAX_SLOTS
+#define RF_MAX_SLOTS 4
+#endif
+__host__ __device__ inline int hist_slots(int hb) { int g = 256 / hb; return g < 1 ? 1 : (g > RF_MAX_SLOTS ? RF_MAX_SLOTS : g); }
 
 __host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K, int hb) {
   const size_t hs = (size_t)hist_slots(hb);
@@ -541,15 +547,18 @@ __device__ inline void radix_pass(const uint32_t* kin, const uint32_t* vin, uint
                                   uint32_t len, int shift, GrowShared* s, uint32_t* rbase) {
   const int tid = vtid(), lane = lane_id(), wid = warp_id();
   __syncthreads();
-  rbase[tid] = 0;
+  constexpr int kDigPer = 256 / kThreads;                // digits owned by one thread (consecutive)
+  for (int q = 0; q < kDigPer; q++) rbase[tid * kDigPer + q] = 0;
   __syncthreads();
   for (uint32_t i = tid; i < len; i += kThreads) atomicAdd(&rbase[(kin[i] >> shift) & 255u], 1u);
   __syncthreads();
-  uint32_t cnt = rbase[tid];
+  uint32_t cnt[kDigPer]; uint32_t mine = 0;
+  for (int q = 0; q < kDigPer; q++) { cnt[q] = rbase[tid * kDigPer + q]; mine += cnt[q]; }
   unsigned long long tot;
-  unsigned long long inc = block_incl_scan<unsigned long long>((unsigned long long)cnt, s->scrU, tot);
+  unsigned long long inc = block_incl_scan<unsigned long long>((unsigned long long)mine, s->scrU, tot);
   __syncthreads();
-  rbase[tid] = (uint32_t)(inc - cnt);
+  uint32_t run = (uint32_t)(inc - mine);
+  for (int q = 0; q < kDigPer; q++) { rbase[tid * kDigPer + q] = run; run += cnt[q]; }
   __syncthreads();
   const uint32_t ntiles = (len + kThreads - 1) / kThreads;
   for (uint32_t t = 0; t < ntiles; t++) {
@@ -715,6 +724,101 @@ __device__ inline void sort_candidate(const NodeCtx& c, int ci, uint32_t len) {
   __syncthreads();
 }
 
+// ---- sparse evaluation of one candidate in a small node -------------------------------------
+// Only strata that contain events contribute to any rule (side_term), and a stratum's left/right
+// terms change only at the codes of ITS OWN rows.  So delta, as a function of the cut, is piecewise
+// constant with breakpoints at the codes of the (few) rows of the event strata; the tracker only
+// ever selects the first cut of a piece.  With lane = one such row (<= 32 of them) the warp
+// evaluates every piece at once: own-stratum prefix by a shuffle loop, both sides' terms for all
+// lanes in one go (two overlapped log chains instead of one chain per stratum and chunk), then the
+// in-order sum over strata at every breakpoint.  Produces the same summary track_summary does.
+__device__ inline void sparse_candidate(const NodeCtx& c, int ci) {
+  GrowSmem& m = c.m;
+  GrowShared* s = m.s;
+  const int lane = lane_id();
+  const int nR = s->nActRows, nAct = s->nAct;
+  const uint8_t* cptr = m.smCodes + ci * kSmallMax;
+  // presence summary (which cuts exist): #present codes, lowest and highest present code
+  uint32_t word = (lane < 8) ? m.pres[ci * 8 + lane] : 0u;
+  int np = warp_sum((int)__popc(word));
+  int last = word ? (lane * 32 + 31 - __clz(word)) : -1;
+  int first = word ? (lane * 32 + __ffs(word) - 1) : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { last = max(last, __shfl_xor_sync(0xffffffffu, last, o)); first = min(first, __shfl_xor_sync(0xffffffffu, first, o)); }
+  if (np < 2) { if (lane == 0) { s->trkNp[ci] = np; s->trkClean[ci] = 1; } return; }
+  const int cov = s->candCov[ci];
+  const double wgt = c.g.split_weight ? c.g.split_weight[cov] : 1.0;
+  const double statP = s->statPnode;
+  // lane -> one row of an event stratum
+  int code = 0x7fff, ia = -1; uint32_t mu = 0, e = 0; double ft = 0.0;
+  if (lane < nR) {
+    const int j = s->actRow[lane];
+    code = cptr[j]; ia = s->actIa[lane]; mu = m.smMult[j]; e = m.smE[j];
+    ft = c.unit ? (double)mu : (double)mu * m.smT[j];
+  }
+  // own-stratum left sums at this row's code: rows of the same stratum with code <= mine
+  uint32_t LN = 0, LE = 0; double LT = 0.0, LW = 0.0;
+  const int lo = (ia >= 0) ? s->actOff[ia] : 0, hi = (ia >= 0) ? s->actOff[ia + 1] : 0;
+  int maxr = hi - lo;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) maxr = max(maxr, __shfl_xor_sync(0xffffffffu, maxr, o));
+  for (int k = 0; k < maxr; k++) {
+    const int src = min(lo + k, 31);
+    const int ck = __shfl_sync(0xffffffffu, code, src);
+    const uint32_t mk = __shfl_sync(0xffffffffu, mu, src), ek = __shfl_sync(0xffffffffu, e, src);
+    const double fk = __shfl_sync(0xffffffffu, ft, src);
+    if (lo + k < hi && ck <= code) { LN += mk; LT += fk; if (ek) { LE += mk; LW += fk; } }
+  }
+  double tL = 0.0, tR = 0.0;
+  if (ia >= 0) {
+    const int a = (int)m.cE[ia];
+    tL = side_term_nb(c.bayes, (double)LE, (double)LN, LT, LW, c.g.alpha, c.beta);
+    tR = side_term_nb(c.bayes, (double)(m.PE[a] - LE), (double)(m.PN[a] - LN), m.PT[a] - LT, m.PW[a] - LW, c.g.alpha, c.beta);
+  }
+  // evaluation points: every row's code (lanes < nR) and the lowest present code (lane nR, the
+  // piece below the first breakpoint); delta = sum over event strata, ascending, of that stratum's
+  // terms at its last breakpoint <= the cut (none: left 0, right = the stratum's parent term)
+  const int q = (lane < nR) ? code : ((lane == nR) ? first : 0x7fff);
+  double accL = 0.0, accR = 0.0;
+  for (int a2 = 0; a2 < nAct; a2++) {
+    const int l2 = s->actOff[a2], h2 = s->actOff[a2 + 1];
+    int bestc = -1; double bl = 0.0, br = m.cTR[m.cE[a2]];
+    for (int k = l2; k < h2; k++) {
+      const int ck = __shfl_sync(0xffffffffu, code, k);
+      const double tlk = __shfl_sync(0xffffffffu, tL, k), trk = __shfl_sync(0xffffffffu, tR, k);
+      if (ck <= q && ck >= bestc) { bestc = ck; bl = tlk; br = trk; }
+    }
+    accL += bl; accR += br;
+  }
+  const double delta = (accL + accR - statP) * wgt;
+  const bool valid = (lane <= nR) && q != last && q <= 0xff;
+  // summary: maximum, its first code, and whether an earlier piece lies within EPSILON of it
+  double M = valid ? delta : -INFINITY; int pos = valid ? q : 0x7fffffff;
+  bool anyNan = __any_sync(0xffffffffu, valid && delta != delta);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oM = __shfl_xor_sync(0xffffffffu, M, o); const int oP = __shfl_xor_sync(0xffffffffu, pos, o);
+    if (oM > M || (oM == M && oP < pos)) { M = oM; pos = oP; }
+  }
+  const bool near = __any_sync(0xffffffffu, valid && q < pos && !((M - delta) > kEpsilon));
+  const bool clean = !anyNan && !near && !c.w.sinkDelta;
+  if (!clean) {
+    // rare: hand the exact walk the full delta-per-present-code array it expects (track_exact)
+    const int Dc = s->candD[ci];
+    for (int b = lane; b < ((Dc + 31) & ~31); b += 32) {
+      int bestc = -1; double dv = 0.0;
+      for (int k = 0; k <= nR && k < 32; k++) {
+        const int qk = __shfl_sync(0xffffffffu, q, k); const double dk = __shfl_sync(0xffffffffu, delta, k);
+        if (qk <= b && qk >= bestc) { bestc = qk; dv = dk; }
+      }
+      if (b < Dc) m.sL[ci * m.hb + b] = dv;
+    }
+  }
+  if (lane == 0) {
+    s->trkNp[ci] = np; s->trkMax[ci] = M; s->trkMaxBin[ci] = pos; s->trkClean[ci] = clean ? 1 : 0; s->trkLast[ci] = last;
+  }
+}
+
 // ---- small nodes (<= kSmallMax entries, histogram candidates only) ---------------------------
 // One batched prefetch brings the node's entries, their event / risk time / stratum and the codes
 // of every candidate into shared memory (a single exposed memory latency instead of one per
@@ -838,11 +942,26 @@ __device__ inline void score_small(NodeCtx& c) {
       for (int ia = 0; ia < nAct; ia++) sp += m.cTR[m.cE[ia]];
       s->nAct = nAct; s->statPnode = sp;
     }
+    // rows of the event strata, stratum-ascending; <= 31 of them enables the sparse evaluation
+    int nrows = 0x7fffffff;
+    if (nAct <= 32) {
+      const int a = (lane < nAct) ? (int)m.cE[lane] : 0;
+      const int r = (lane < nAct) ? (int)(m.cN[a] - m.segpos[a]) : 0;
+      const int inc = warp_incl_scan(r);
+      nrows = __shfl_sync(0xffffffffu, inc, 31);
+      if (nrows <= 31) {
+        if (lane < nAct) { s->actOff[lane] = (uint8_t)(inc - r); for (int k = 0; k < r; k++) { s->actRow[inc - r + k] = (uint16_t)(m.segpos[a] + k); s->actIa[inc - r + k] = (uint8_t)lane; } }
+        if (lane == 0) s->actOff[nAct] = (uint8_t)nrows;
+      }
+    }
+    if (lane == 0) s->nActRows = (nrows <= 31) ? nrows : -1;
   }
   __syncthreads();
   RF_PROF(5);
   const int nAct = s->nAct;
+  const bool sparse = s->nActRows >= 0;
   for (int ci = wid; ci < nc; ci += kWarps) {
+    if (sparse) { sparse_candidate(c, ci); continue; }
     const int Dc = s->candD[ci];
     for (int b = lane; b < Dc; b += 32) { m.sL[ci * m.hb + b] = 0.0; m.sR[ci * m.hb + b] = 0.0; }
     const uint8_t* cptr = m.smCodes + ci * kSmallMax;
@@ -1206,12 +1325,14 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     if (small) {
       // the node is staged in shared memory: thread t owns entries 2t and 2t+1, one block scan of a
       // packed (left entries | left rows << 16 | left events << 40) word gives sizes and positions
-      static_assert(kSmallMax == 2 * kThreads, "two staged entries per thread");
-      unsigned long long my = 0ull; bool lf[2] = {false, false}; uint32_t en[2] = {0u, 0u};
+      constexpr int kEpt = kSmallMax / kThreads;               // staged entries per thread (consecutive)
+      static_assert(kSmallMax % kThreads == 0 && kEpt <= 4, "staged entries per thread");
+      unsigned long long my = 0ull; bool lf[kEpt]; uint32_t en[kEpt];
       double rtL = 0.0, rtR = 0.0;
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
-        const uint32_t i = 2u * tid + u;
+      for (int u = 0; u < kEpt; u++) {
+        const uint32_t i = (uint32_t)kEpt * tid + u;
+        lf[u] = false; en[u] = 0u;
         if (i < cur.len) {
           en[u] = m.smEnt[i];
           lf[u] = cptr[i] <= bcode;                               // LEFT iff cut - x >= 0 (rf.c:15194)
@@ -1228,8 +1349,8 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
       RF_PROF(8);
       uint32_t before = (uint32_t)((inc - my) & 0xFFFFull);
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
-        const uint32_t i = 2u * tid + u;
+      for (int u = 0; u < kEpt; u++) {
+        const uint32_t i = (uint32_t)kEpt * tid + u;
         if (i < cur.len) {
           if (lf[u]) { dst[before] = en[u]; before++; }
           else dst[nL + (i - before)] = en[u];
