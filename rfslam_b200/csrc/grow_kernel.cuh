@@ -1249,12 +1249,10 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     }
     // node gate (rf.c:15354-15371) and purity (rf.c:6391-6416): both classes present
     bool attempt = (cur.m >= 2u * (uint32_t)g.nodesize) && (g.nodedepth < 0 || cur.depth < (uint32_t)g.nodedepth);
-    if (attempt) {
-      double mm = (double)cur.m, ee = (double)cur.E;
-      double mean = (mm + ee) / mm;
-      double var = ((mm - ee) * (mean - 1.0) * (mean - 1.0) + ee * (mean - 2.0) * (mean - 2.0)) / mm;
-      attempt = var > kEpsilon;
-    }
+    // purity (rf.c:6391-6416): the variance of the response codes is (E/m)(1 - E/m) >= (1/m)(1 - 1/m),
+    // i.e. > 1.4e-8 for any m < 2^26 whenever both classes are present, and exactly 0 otherwise --
+    // so "variance > EPSILON" is the integer test 0 < E < m
+    if (attempt) attempt = cur.E > 0u && cur.E < cur.m;
     if (w.sinkDelta) attempt = true;                       // single-node scoring mode: no gate
     if (tid == 0) { s->nc = 0; s->have = 0; }
     __syncthreads();
