@@ -98,6 +98,7 @@ typedef struct rfslam_grow_args {
                                       /*   trees on every rank, so tree b is identical for any sharding. */
   int32_t        finalize_ensembles;  /* 1: divide by the denominators (single process); 0: return sums */
   int32_t        want_split_stat;     /* 1: also return splitStat (the winning delta per node) */
+  int32_t        want_member_lists;   /* 1 (with RFSLAM_OPTH_MEMB_OUTG): also return rmbr/ambrMembership, 8 bytes x n x ntree */
 } rfslam_grow_args;
 
 /* The reference's named output list for the class family (rf.c:9-79), sized by the
@@ -134,6 +135,7 @@ typedef struct rfslam_forest_out {
   double    grow_kernel_ms;    /* device time of the tree-growing kernel(s), CUDA events */
   double    total_device_ms;   /* device time of the whole call incl. bootstrap and ensembles */
   int64_t   kernel_launches;   /* kernels of this library launched by the call */
+  int64_t   rmbr_stride;       /* row stride of rmbrMembership (= maxBootstrapSize, rf.c:18296) */
 } rfslam_forest_out;
 
 int  rfslam_b200_grow(const rfslam_grow_args *args, rfslam_forest_out *out);

@@ -33,7 +33,7 @@ class GrowArgs(C.Structure):
         ("time_interest_size", C.c_int32), ("time_interest", _pd),
         ("n_impute", C.c_int32), ("perf_block", C.c_int32), ("num_threads", C.c_int32),
         ("device", C.c_int32), ("tree_first", C.c_int32), ("tree_step", C.c_int32), ("finalize_ensembles", C.c_int32),
-        ("want_split_stat", C.c_int32),
+        ("want_split_stat", C.c_int32), ("want_member_lists", C.c_int32),
     ]
 
 
@@ -45,7 +45,7 @@ class ForestOut(C.Structure):
         ("nodeMembership", _pi), ("bootMembership", _pi), ("rmbrMembership", _pi), ("ambrMembership", _pi),
         ("oobEnsbCLS", _pd), ("allEnsbCLS", _pd), ("oobEnsbDen", _pu), ("allEnsbDen", _pu),
         ("split_candidates", C.c_int64), ("algorithmic_bytes", C.c_int64),
-        ("grow_kernel_ms", C.c_double), ("total_device_ms", C.c_double), ("kernel_launches", C.c_int64),
+        ("grow_kernel_ms", C.c_double), ("total_device_ms", C.c_double), ("kernel_launches", C.c_int64), ("rmbr_stride", C.c_int64),
     ]
 
 

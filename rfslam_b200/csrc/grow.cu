@@ -1,6 +1,8 @@
 // grow.cu -- host orchestration of forest growth plus the supporting kernels either side of the
 // tree kernel: chain-A bootstrap replay (K1), record compaction, and the row-parallel traversal
 // that yields node membership, all-row leaf counts and the OOB / full ensembles (K4/K5).
+#include <cub/cub.cuh>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -137,6 +139,38 @@ __global__ void membership_kernel(DevData d, int ntrees, const unsigned long lon
   if ((threadIdx.x & 31) == 0) atomicAdd(pathSum, steps);
 }
 
+// ---- rmbrMembership / ambrMembership (rf.c:797-803, rf.c:7602-7607): row ids grouped by leaf in the
+// order leaves are reached by the DFS, draw order (in-bag) / ascending row order (all rows) inside a leaf.
+// Built after the fact from node membership: leaf rank = position of the terminal record in pre-order,
+// then a stable sort of the draws / of all rows by the rank of their leaf.
+__global__ void leaf_flag_kernel(const int32_t* parmID, uint32_t* flag, size_t NN) {
+  size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < NN) flag[q] = parmID[q] == 0 ? 1u : 0u;
+}
+__global__ void leaf_rank_kernel(const int32_t* parmID, const int32_t* nodeID, const uint32_t* exscan, const unsigned long long* nodeOff,
+                                 const unsigned long long* leafOff, int ntrees, uint32_t* leafRank) {
+  const int t = blockIdx.y;
+  const unsigned long long off = nodeOff[t], end = nodeOff[t + 1];
+  for (unsigned long long q = off + blockIdx.x * blockDim.x + threadIdx.x; q < end; q += (unsigned long long)gridDim.x * blockDim.x)
+    if (parmID[q] == 0) leafRank[leafOff[t] + (unsigned long long)nodeID[q] - 1ull] = exscan[q] - exscan[off];
+  (void)ntrees;
+}
+// keys for the stable sort: rank of the leaf that original row r fell into (vals = r + 1, the 1-based id R sees)
+__global__ void member_keys_kernel(const uint32_t* rows, int count, const int32_t* nodeMembT, const uint32_t* leafRankT,
+                                   uint32_t* keys, uint32_t* vals) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < count) {
+    const uint32_t r = rows ? rows[j] : (uint32_t)j;
+    keys[j] = leafRankT[nodeMembT[r] - 1];
+    vals[j] = r + 1u;
+  }
+}
+// by.user bootstrap: the in-bag list is every row repeated count times, ascending (rf.c:520-526)
+__global__ void expand_counts_kernel(const int32_t* cnt, const uint32_t* exscan, int n, uint32_t* rows) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const uint32_t o = exscan[i]; for (int k = 0; k < cnt[i]; k++) rows[o + k] = (uint32_t)i; }
+}
+
 __global__ void finalize_kernel(double* num, const uint32_t* den, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
@@ -214,7 +248,7 @@ int validate_grow_args(const rfslam_grow_args* a, GrowConfig* cfg) {
   cfg->alpha = 1.0 / (a->k_for_alpha * a->k_for_alpha);
   cfg->ntree = a->ntree; cfg->seed = a->seed; cfg->by_user = t1 && t2;
   cfg->want_membership = (a->opt_high & RFSLAM_OPTH_MEMB_USER) != 0;
-  cfg->want_membr_lists = false;
+  cfg->want_membr_lists = (a->opt_high & RFSLAM_OPTH_MEMB_OUTG) != 0 && a->want_member_lists != 0;
   cfg->finalize = a->finalize_ensembles != 0;
   if (cfg->by_user && !a->bootstrap) { set_error("bootstrap = by.user needs the samp matrix"); return RFSLAM_EINVAL; }
   return RFSLAM_OK;
@@ -315,7 +349,10 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     d_allNum.alloc(2 * (size_t)n); d_oobNum.alloc(2 * (size_t)n); d_allDen.alloc(n); d_oobDen.alloc(n);
     d_allNum.zero(); d_oobNum.zero(); d_allDen.zero(); d_oobDen.zero();
     DevBuf<int32_t> d_nodeMemb(pool), d_bootMemb(pool);
-    if (cfg.want_membership) { d_nodeMemb.alloc((size_t)T * n); d_bootMemb.alloc((size_t)T * n); }
+    if (cfg.want_membership || cfg.want_membr_lists) { d_nodeMemb.alloc((size_t)T * n); d_bootMemb.alloc((size_t)T * n); }
+    DevBuf<int32_t> d_rmbr(pool), d_ambr(pool);
+    const size_t rmbrStride = (size_t)std::max(a->max_bootstrap_size, maxBoot);
+    if (cfg.want_membr_lists) { d_rmbr.alloc((size_t)T * rmbrStride); d_ambr.alloc((size_t)T * n); d_rmbr.zero(); d_ambr.zero(); }
     DevBuf<unsigned long long> d_pathSum(pool);
     d_pathSum.alloc(1); d_pathSum.zero();
 
@@ -459,6 +496,47 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         RF_CUDA(cudaEventElapsedTime(&ms, ev1, ev2)); growMs += ms;
         RF_CUDA(cudaEventElapsedTime(&ms, ev0, ev3)); totalMs += ms;
         RF_CUDA(cudaMemcpy(h_tnACNT.grow(NL), f_acnt.p, NL * 4, cudaMemcpyDeviceToHost));
+        if (cfg.want_membr_lists) {
+          DevBuf<uint32_t> d_flag(pool), d_scan(pool), d_lrank(pool), d_k1(pool), d_k2(pool), d_v1(pool), d_v2(pool), d_rows(pool);
+          d_flag.alloc(NN); d_scan.alloc(std::max<size_t>(NN, (size_t)n)); d_lrank.alloc(NL);
+          const size_t mcap = std::max<size_t>((size_t)n, (size_t)maxBoot);
+          d_k1.alloc(mcap); d_k2.alloc(mcap); d_v1.alloc(mcap); d_v2.alloc(mcap);
+          if (cfg.by_user) d_rows.alloc(mcap);
+          size_t tb = 0, tb2 = 0;
+          cub::DeviceScan::ExclusiveSum(nullptr, tb, d_flag.p, d_scan.p, (int)std::max<size_t>(NN, (size_t)n));
+          cub::DeviceRadixSort::SortPairs(nullptr, tb2, d_k1.p, d_k2.p, d_v1.p, d_v2.p, (int)mcap);
+          DevBuf<unsigned char> d_tmp(pool);
+          d_tmp.alloc(std::max(tb, tb2));
+          size_t tbytes = std::max(tb, tb2);
+          leaf_flag_kernel<<<(unsigned)((NN + 255) / 256), 256>>>(f_parm.p, d_flag.p, NN);
+          RF_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, tbytes, d_flag.p, d_scan.p, (int)NN));
+          dim3 gl((unsigned)std::min<uint32_t>((maxNodes + 255) / 256, 2048), (unsigned)nb);
+          leaf_rank_kernel<<<gl, 256>>>(f_parm.p, f_node.p, d_scan.p, d_nodeOff.p, d_leafOff.p, nb, d_lrank.p);
+          for (int t = 0; t < nb; t++) {
+            const int32_t* memb = d_nodeMemb.p + (size_t)(b0 + t) * n;
+            const uint32_t* lr = d_lrank.p + leafOff[t];
+            int bits = 1; while ((1u << bits) < hLeaves[t]) bits++;
+            // all rows, ascending row order inside a leaf
+            member_keys_kernel<<<(n + 255) / 256, 256>>>(nullptr, n, memb, lr, d_k1.p, d_v1.p);
+            tbytes = std::max(tb, tb2);
+            RF_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tbytes, d_k1.p, d_k2.p, d_v1.p, (uint32_t*)(d_ambr.p + (size_t)(b0 + t) * n), n, 0, bits));
+            // in-bag rows, draw order inside a leaf
+            const uint32_t* rows; const int bs = hbs[t];
+            if (cfg.by_user) {
+              RF_CUDA(cudaMemcpy(d_samp.p, a->bootstrap + (size_t)(hid[t] - 1) * n, (size_t)n * 4, cudaMemcpyHostToDevice));
+              tbytes = std::max(tb, tb2);
+              RF_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, tbytes, (const uint32_t*)d_samp.p, d_scan.p, n));
+              expand_counts_kernel<<<(n + 255) / 256, 256>>>(d_samp.p, d_scan.p, n, d_rows.p);
+              rows = d_rows.p;
+            } else {
+              rows = d_draws.p + (size_t)t * maxBoot;
+            }
+            member_keys_kernel<<<(bs + 255) / 256, 256>>>(rows, bs, memb, lr, d_k1.p, d_v1.p);
+            tbytes = std::max(tb, tb2);
+            RF_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tbytes, d_k1.p, d_k2.p, d_v1.p, (uint32_t*)(d_rmbr.p + (size_t)(b0 + t) * rmbrStride), bs, 0, bits));
+          }
+          RF_CUDA(cudaDeviceSynchronize());
+        }
         break;
       }
     }
@@ -490,6 +568,11 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     if (cfg.want_membership) {
       out->nodeMembership = host_copy(d_nodeMemb.p, (size_t)T * n);
       out->bootMembership = host_copy(d_bootMemb.p, (size_t)T * n);
+    }
+    if (cfg.want_membr_lists) {
+      out->rmbrMembership = host_copy(d_rmbr.p, (size_t)T * rmbrStride);
+      out->ambrMembership = host_copy(d_ambr.p, (size_t)T * n);
+      out->rmbr_stride = (int64_t)rmbrStride;
     }
     out->split_candidates = totalCand; out->algorithmic_bytes = totalAlgo;
     out->grow_kernel_ms = growMs; out->total_device_ms = totalMs; out->kernel_launches = launches;

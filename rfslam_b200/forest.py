@@ -61,7 +61,7 @@ class _Packed:
 
     def __init__(self, x, y, risk_time, stratifier, *, splitrule, ntree, mtry, nodesize, nodedepth, seed, k_for_alpha,
                  membership, samp, sampsize, split_wt, device, tree_first, tree_step, finalize, nsplit=0, xvar_types=None,
-                 split_stat=False):
+                 split_stat=False, member_lists=False):
         x = np.ascontiguousarray(x, np.float64)
         assert x.ndim == 2, "x must be [p, n]: p contiguous columns of n (randomForestSRC.c:22190)"
         p, n = x.shape
@@ -121,6 +121,7 @@ class _Packed:
         a.device = int(device); a.tree_first = int(tree_first); a.tree_step = int(tree_step)
         a.finalize_ensembles = 1 if finalize else 0
         a.want_split_stat = 1 if split_stat else 0
+        a.want_member_lists = 1 if member_lists else 0
         self.args = a
         self.n, self.p = n, p
 
@@ -141,6 +142,9 @@ def _unpack_forest(o: ForestOut) -> Dict[str, np.ndarray]:
         "grow_kernel_ms": float(o.grow_kernel_ms), "total_device_ms": float(o.total_device_ms),
         "kernel_launches": int(o.kernel_launches),
     }
+    if o.rmbrMembership:
+        res["rmbrMembership"] = _own(o, "rmbrMembership", T * int(o.rmbr_stride), np.int32)
+        res["ambrMembership"] = _own(o, "ambrMembership", T * n, np.int32)
     if o.nodeMembership:
         res["nodeMembership"] = _own(o, "nodeMembership", T * n, np.int32)
         res["bootMembership"] = _own(o, "bootMembership", T * n, np.int32)
@@ -176,12 +180,12 @@ class ResidentCpiu:
 
     def grow(self, *, splitrule="poisson.split4", ntree=500, mtry=None, nodesize=5, nodedepth=-1, seed=-12345,
              k_for_alpha=2.0, membership=False, samp=None, sampsize=None, split_wt=None, tree_first=0, tree_step=0,
-             finalize=True, split_stat=False) -> Dict[str, np.ndarray]:
+             finalize=True, split_stat=False, member_lists=False) -> Dict[str, np.ndarray]:
         k = self._pk.keep
         pk = _Packed(k["x"], k["y"], k["rt"], k["st"], splitrule=splitrule, ntree=ntree, mtry=mtry, nodesize=nodesize,
                      nodedepth=nodedepth, seed=seed, k_for_alpha=k_for_alpha, membership=membership, samp=samp,
                      sampsize=sampsize, split_wt=split_wt, device=self.device, tree_first=tree_first, tree_step=tree_step,
-                     finalize=finalize, split_stat=split_stat)
+                     finalize=finalize, split_stat=split_stat, member_lists=member_lists)
         out = ForestOut()
         capi.check(capi.lib().rfslam_b200_grow_resident(self.handle, C.byref(pk.args), C.byref(out)))
         res = _unpack_forest(out)
@@ -191,7 +195,8 @@ class ResidentCpiu:
 
 def rfsrc(x, y, risk_time=None, stratifier=None, *, splitrule="poisson.split4", ntree=500, mtry=None, nodesize=5,
           nodedepth=-1, seed=-12345, k_for_alpha=2.0, membership=False, samp=None, sampsize=None, split_wt=None,
-          device=-1, tree_first=0, tree_step=0, finalize=True, nsplit=0, xvar_types=None, split_stat=False) -> Dict[str, np.ndarray]:
+          device=-1, tree_first=0, tree_step=0, finalize=True, nsplit=0, xvar_types=None, split_stat=False,
+          member_lists=False) -> Dict[str, np.ndarray]:
     """Grow an RF-SLAM forest from HOST arrays through rfslam_b200_grow (upload + grow + download).
 
     x [p, n] float64 (p contiguous columns), y response codes 1.0 / 2.0, risk_time [n], stratifier [n]
@@ -200,7 +205,7 @@ def rfsrc(x, y, risk_time=None, stratifier=None, *, splitrule="poisson.split4", 
     pk = _Packed(x, y, risk_time, stratifier, splitrule=splitrule, ntree=ntree, mtry=mtry, nodesize=nodesize,
                  nodedepth=nodedepth, seed=seed, k_for_alpha=k_for_alpha, membership=membership, samp=samp, sampsize=sampsize,
                  split_wt=split_wt, device=device, tree_first=tree_first, tree_step=tree_step, finalize=finalize, nsplit=nsplit,
-                 xvar_types=xvar_types, split_stat=split_stat)
+                 xvar_types=xvar_types, split_stat=split_stat, member_lists=member_lists)
     out = ForestOut()
     capi.check(capi.lib().rfslam_b200_grow(C.byref(pk.args), C.byref(out)))
     res = _unpack_forest(out)

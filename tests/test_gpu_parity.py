@@ -68,8 +68,9 @@ def test_grow_matches_reference_golden(golden_dir, name):
     g = parity.load_golden(os.path.join(golden_dir, name))
     q = parity.golden_params(g)
     got = rfslam_b200.rfsrc(g["x"], g["y"], g["rt"], g["strat"], splitrule=q["rule"], ntree=q["ntree"],
-                            nodesize=q["nodesize"], mtry=q["mtry"], seed=q["seed"], samp=g.get("samp"), membership=True)
-    parity.assert_forest_equal(got, parity.golden_ref_forest(g), q["n"], q["ntree"], label=name)
+                            nodesize=q["nodesize"], mtry=q["mtry"], seed=q["seed"], samp=g.get("samp"), membership=True,
+                            member_lists=True)
+    parity.assert_forest_equal(got, parity.golden_ref_forest(g), q["n"], q["ntree"], check_membr_lists=True, label=name)
 
 
 @pytest.mark.parametrize("name", ["grow_r4_q64.npz", "grow_r1_cont.npz", "grow_r4_byuser.npz"])
