@@ -130,7 +130,8 @@ def grow(x: np.ndarray, y: np.ndarray, risk_time: np.ndarray, stratifier: np.nda
          nodedepth: int = -1, seed: int = -12345, k_for_alpha: float = 2.0,
          membership: bool = True, nthreads: int = -1, samp: Optional[np.ndarray] = None,
          nsplit: int = 0, split_weight: Optional[np.ndarray] = None,
-         xtype: Optional[Sequence[str]] = None, xlevels: Optional[np.ndarray] = None
+         xtype: Optional[Sequence[str]] = None, xlevels: Optional[np.ndarray] = None,
+         var_categories: Optional[np.ndarray] = None, category_weights: Optional[np.ndarray] = None
          ) -> Dict[str, np.ndarray]:
     """Run the reference's rfsrcGrow.  ``x`` is [p, n] float64 (p contiguous columns of n), ``y``
     the response codes in {1.0, 2.0}.  ``samp`` ([ntree, n] int32 in-bag counts) selects
@@ -162,6 +163,9 @@ def grow(x: np.ndarray, y: np.ndarray, risk_time: np.ndarray, stratifier: np.nda
         xlevels = np.zeros(p, np.int32)
     if split_weight is None:
         split_weight = np.ones(p)
+    if var_categories is None:
+        var_categories = np.ones(p, np.int32); category_weights = np.array([1.0])
+    ncat = int(np.unique(var_categories).size)
     args = [
         P.i(0), P.i(seed), P.i(opt_low), P.i(opt_high),
         P.i(16),                    # splitRule = custom (randomForestSRC.h:189)
@@ -172,7 +176,7 @@ def grow(x: np.ndarray, y: np.ndarray, risk_time: np.ndarray, stratifier: np.nda
         P.i(p), P.s(list(xtype)), P.i(xlevels),
         P.d(np.asarray(risk_time, np.float64)), P.i(np.asarray(stratifier, np.int32)),
         P.i(int(np.max(stratifier))),
-        P.i(np.ones(p, np.int32)), P.d(1.0), P.i(1),      # varCategories, categoryWeights, nCategories
+        P.i(np.asarray(var_categories, np.int32)), P.d(np.asarray(category_weights, np.float64)), P.i(ncat),   # varCategories, categoryWeights, nCategories
         P.i(np.zeros(0, np.int32)), P.i(0),               # toFix, nToFix
         P.d(k_for_alpha), P.i(max_boot), P.i(boot_sizes), samp_arg,
         P.d(np.ones(n)), P.d(np.asarray(split_weight, np.float64)), P.d(1.0), P.d(np.ones(p)),

@@ -227,8 +227,20 @@ int validate_grow_args(const rfslam_grow_args* a, GrowConfig* cfg) {
   if (a->x_size > 1024) { set_error("xSize %d exceeds 1024 covariates", a->x_size); return RFSLAM_ENOSUP; }
   if (a->node_size < 1) { set_error("nodeSize must be >= 1"); return RFSLAM_EINVAL; }
   if (a->n_impute > 1) { set_error("multiple imputation is outside the accelerated path"); return RFSLAM_ENOSUP; }
+  // Variable categories (rf.c:14887-15014) only bound how many FAILED draws one call of
+  // selectRandomCovariates may make: ceil(mtry * weight) per category, categories tried in turn.
+  // Which covariate is drawn never depends on them: the sampler is chosen once from the incoming
+  // xWeight (uniform -> RF_WGHT_UNIFORM, rf.c:19110-19114) and the uniform sampler ignores the
+  // per-category RF_xWeight rewrites (rf.c:8378-8381).  As long as the per-call budget cannot bind
+  // before mtry does, the draws are those of the single-category path.
   if (a->n_categories > 1 || (a->n_categories == 1 && a->category_weights && a->category_weights[0] != 1.0)) {
-    set_error("variable categories: only the default single category of weight 1 is accelerated"); return RFSLAM_ENOSUP;
+    if (!a->category_weights) { set_error("categoryWeights missing"); return RFSLAM_EINVAL; }
+    long budget = 0;
+    for (int k = 0; k < a->n_categories; k++) budget += (long)ceil((double)a->mtry * a->category_weights[k]);
+    if (budget < a->mtry) {
+      set_error("category weights give a per-call draw budget of %ld < mtry = %d: that truncation is outside the accelerated path", budget, a->mtry);
+      return RFSLAM_ENOSUP;
+    }
   }
   if (a->n_to_fix > 0) { set_error("fixed_during_bootstrap covariates are outside the accelerated path"); return RFSLAM_ENOSUP; }
   if (a->opt_high & 0x1000u) { set_error("sampling without replacement is outside the accelerated path"); return RFSLAM_ENOSUP; }

@@ -61,7 +61,7 @@ class _Packed:
 
     def __init__(self, x, y, risk_time, stratifier, *, splitrule, ntree, mtry, nodesize, nodedepth, seed, k_for_alpha,
                  membership, samp, sampsize, split_wt, device, tree_first, tree_step, finalize, nsplit=0, xvar_types=None,
-                 split_stat=False, member_lists=False):
+                 split_stat=False, member_lists=False, var_categories=None, category_weights=None):
         x = np.ascontiguousarray(x, np.float64)
         assert x.ndim == 2, "x must be [p, n]: p contiguous columns of n (randomForestSRC.c:22190)"
         p, n = x.shape
@@ -81,7 +81,8 @@ class _Packed:
         self.keep = dict(
             x=x, y=np.ascontiguousarray(y, np.float64), rt=np.ascontiguousarray(risk_time, np.float64),
             st=np.ascontiguousarray(stratifier, np.int32), rlev=np.array([2], np.int32), xlev=np.zeros(p, np.int32),
-            cat=np.ones(p, np.int32), catw=np.array([1.0]), tofix=np.zeros(1, np.int32), cw=np.ones(n), yw=np.array([1.0]),
+            cat=np.ones(p, np.int32) if var_categories is None else np.ascontiguousarray(var_categories, np.int32),
+            catw=np.array([1.0]) if category_weights is None else np.ascontiguousarray(category_weights, np.float64), tofix=np.zeros(1, np.int32), cw=np.ones(n), yw=np.array([1.0]),
             xw=np.ones(p), sw=np.ascontiguousarray(np.ones(p) if split_wt is None else split_wt, np.float64))
         k = self.keep
         a = GrowArgs()
@@ -111,7 +112,7 @@ class _Packed:
         self._xtype = ("".join(xvar_types) if xvar_types is not None else "R" * p).encode(); a.x_type = self._xtype
         a.x_levels = _ip(k["xlev"])
         a.risk_time = _dp(k["rt"]); a.stratifier = _ip(k["st"]); a.max_strat = int(k["st"].max())
-        a.var_categories = _ip(k["cat"]); a.category_weights = _dp(k["catw"]); a.n_categories = 1
+        a.var_categories = _ip(k["cat"]); a.category_weights = _dp(k["catw"]); a.n_categories = int(np.unique(k["cat"]).size)
         a.to_fix = _ip(k["tofix"]); a.n_to_fix = 0
         a.k_for_alpha = float(k_for_alpha)
         a.max_bootstrap_size = int(k["bs"].max()); a.bootstrap_size = _ip(k["bs"])
@@ -196,7 +197,7 @@ class ResidentCpiu:
 def rfsrc(x, y, risk_time=None, stratifier=None, *, splitrule="poisson.split4", ntree=500, mtry=None, nodesize=5,
           nodedepth=-1, seed=-12345, k_for_alpha=2.0, membership=False, samp=None, sampsize=None, split_wt=None,
           device=-1, tree_first=0, tree_step=0, finalize=True, nsplit=0, xvar_types=None, split_stat=False,
-          member_lists=False) -> Dict[str, np.ndarray]:
+          member_lists=False, var_categories=None, category_weights=None) -> Dict[str, np.ndarray]:
     """Grow an RF-SLAM forest from HOST arrays through rfslam_b200_grow (upload + grow + download).
 
     x [p, n] float64 (p contiguous columns), y response codes 1.0 / 2.0, risk_time [n], stratifier [n]
@@ -205,7 +206,8 @@ def rfsrc(x, y, risk_time=None, stratifier=None, *, splitrule="poisson.split4", 
     pk = _Packed(x, y, risk_time, stratifier, splitrule=splitrule, ntree=ntree, mtry=mtry, nodesize=nodesize,
                  nodedepth=nodedepth, seed=seed, k_for_alpha=k_for_alpha, membership=membership, samp=samp, sampsize=sampsize,
                  split_wt=split_wt, device=device, tree_first=tree_first, tree_step=tree_step, finalize=finalize, nsplit=nsplit,
-                 xvar_types=xvar_types, split_stat=split_stat, member_lists=member_lists)
+                 xvar_types=xvar_types, split_stat=split_stat, member_lists=member_lists, var_categories=var_categories,
+                 category_weights=category_weights)
     out = ForestOut()
     capi.check(capi.lib().rfslam_b200_grow(C.byref(pk.args), C.byref(out)))
     res = _unpack_forest(out)

@@ -150,3 +150,17 @@ def test_unsupported_inputs_fail_loudly():
         rfslam_b200.rfsrc(d.x, d.y + 1.0, d.rt, d.strat, ntree=2)              # response codes outside {1, 2}
     with pytest.raises(rfslam_b200.RfslamError):
         rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=2, nsplit=3)          # random cut subsets: not accelerated
+
+
+def test_variable_categories_accepted():
+    """rfSLAM's structured-covariate arguments (R/rfsrc.R:1529-1585): inert for the draws (see
+    tests/test_oracle.py::test_reference_variable_categories_do_not_change_the_draws), so the forest is unchanged."""
+    d = make_cpiu(1500, 9, levels=32, seed=72)
+    base = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=3, nodesize=5, seed=-21)
+    cats = np.array([1, 2, 3, 1, 2, 3, 1, 2, 3], np.int32)
+    other = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=3, nodesize=5, seed=-21, var_categories=cats,
+                              category_weights=np.array([0.5, 0.25, 0.25]))
+    np.testing.assert_array_equal(base["parmID"], other["parmID"])
+    with pytest.raises(rfslam_b200.RfslamError):
+        rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=3, nodesize=5, seed=-21, mtry=9, var_categories=cats,
+                          category_weights=np.array([0.1, 0.1, 0.1]))

@@ -98,3 +98,21 @@ def test_port_matches_live_reference(rule, n, p, levels, nodesize, seed, dseed):
         t[k] = t[k][order]
     got = port.grow(d.x, d.y, d.rt, d.strat, rule=rule, ntree=ntree, nodesize=nodesize, seed=seed)
     parity.assert_forest_equal(got, t, n, ntree, check_membr_lists=True, label="live")
+
+
+@pytest.mark.skipif(not refdriver.available(), reason="oracle/_ref not built (no /root/reference here)")
+def test_reference_variable_categories_do_not_change_the_draws():
+    """Pins the claim behind accepting nCategories > 1 on the device path (randomForestSRC.c:14887-15014):
+    under uniform xvar.wt the category loop never changes which covariates are drawn."""
+    d = make_cpiu(1200, 9, levels=32, seed=71)
+    base = refdriver.grow(d.x, d.y, d.rt, d.strat, rule=4, ntree=4, nodesize=5, seed=-19)
+    cats = np.array([1, 2, 3, 1, 2, 3, 1, 2, 3], np.int32)
+    for w in ([0.5, 0.25, 0.25], [1 / 3, 1 / 3, 1 / 3], [0.8, 0.1, 0.1]):
+        other = refdriver.grow(d.x, d.y, d.rt, d.strat, rule=4, ntree=4, nodesize=5, seed=-19, var_categories=cats,
+                               category_weights=np.array(w))
+        a, b = refdriver.trim_forest(base, d.n), refdriver.trim_forest(other, d.n)
+        ta, tb = refdriver.per_tree(a), refdriver.per_tree(b)
+        for k in ta:
+            np.testing.assert_array_equal(ta[k]["parmID"], tb[k]["parmID"])
+            np.testing.assert_array_equal(ta[k]["nodeID"], tb[k]["nodeID"])
+        np.testing.assert_array_equal(base["nodeMembership"], other["nodeMembership"])
