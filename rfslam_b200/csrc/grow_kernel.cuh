@@ -1051,8 +1051,10 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
       uint32_t bnd[3];
 #pragma unroll
       for (int q = 0; q < 3; q++) bnd[q] = (q + 1 < ns) ? m.segpos[k0 + q + 1] : 0xFFFFFFFFu;
+      uint32_t entNext = (s0 + tid < s1) ? list[s0 + tid] : 0u;
       for (uint32_t i = s0 + tid; i < s1; i += kThreads) {
-        const uint32_t ent = list[i];
+        const uint32_t ent = entNext;
+        if (i + kThreads < s1) entNext = list[i + kThreads];       // software pipelining: next entry's load overlaps this entry's gathers
         const uint32_t row = ent & kRowMask, mult = (ent >> kRowBits) + 1u;
         // issue every gather of this entry before the first shared-memory atomic
         const uint32_t e = d.ev[row];
