@@ -1,8 +1,15 @@
-import sys; sys.path.insert(0,'.')
-import numpy as np, rfslam_b200
+import time, sys, numpy as np
+sys.path.insert(0, '.')
+import rfslam_b200
 from rfslam_b200.synth import make_cpiu
-from oracle import port
-d = make_cpiu(4000, 9, levels=64, seed=3)
-got = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, splitrule=4, ntree=4, nodesize=5, seed=-11, membership=True)
-want = port.grow(d.x, d.y, d.rt, d.strat, rule=4, ntree=4, nodesize=5, seed=-11)
-print("parm equal", np.array_equal(got["parmID"], want["parmID"]), got["treeID"].size)
+n, p, L = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+nodesize = int(sys.argv[4])
+d = make_cpiu(n, p, levels=L)
+print("K", int(d.strat.max()), flush=True)
+ds = rfslam_b200.ResidentCpiu(d.x, d.y, d.rt, d.strat)
+for ntree in [int(a) for a in sys.argv[5:]]:
+    best = 1e30
+    for rep in range(2):
+        f = ds.grow(ntree=ntree, nodesize=nodesize, seed=-12345)
+        best = min(best, f['grow_kernel_ms'])
+    print(f"ntree {ntree} kernel {best:.1f} ms  trees/s {ntree/best*1e3:.1f}", flush=True)

@@ -110,7 +110,7 @@ struct GrowShared {
   int ptotReady;
   int nAct; double statPnode; int isSmall; int poolSize;
   // sparse evaluation of small nodes: the rows of the strata that contain events (<= 32), stratum-ascending
-  int nActRows; uint16_t actRow[32]; uint8_t actIa[32]; uint8_t actOff[34];
+  uint32_t evMask[8];                // small nodes: strata that contain events
   int trkMaxBin[kMaxCand]; double trkMax[kMaxCand]; int trkClean[kMaxCand]; int trkNp[kMaxCand]; int trkLast[kMaxCand];
   unsigned long long prof[kProfSlots];
   long long tmark;
@@ -146,6 +146,9 @@ __device__ __forceinline__ int block_incl_scan_max(int v, int* scratch) {
   return max(v, off);
 }
 
+// one staged entry of a small node (score_small): multiplicity * risk time, multiplicity, event | (stratum - 1) << 8
+struct __align__(16) SmallRec { double mrt; uint32_t mult; uint32_t es; };
+
 // dynamic shared memory carve-up
 struct GrowSmem {
   double *sL, *sR, *hT, *hW, *statP;
@@ -156,7 +159,7 @@ struct GrowSmem {
   uint32_t *segpos, *PN, *PE, *cN, *cE;
   double *PT, *PW, *cT, *cW, *cTL, *cTR;
   // small-node staging: the node's entries and everything scoring needs about them
-  uint32_t* smEnt; double* smT; uint8_t *smMult, *smE, *smS, *smCodes;
+  uint32_t* smEnt; SmallRec* smRec; uint8_t* smCodes;
   GrowShared* s;
   int hb;                            // bins per candidate histogram: pow2 >= the widest byte-coded column, 32..256
   int hs;                            // stratum slots per candidate histogram (large nodes accumulate hs strata per pass)
@@ -178,7 +181,7 @@ __host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K, int hb) {
   b += (size_t)ncmax * 8 * 4;                  // pres
   b += KS * 8 * 6;                             // PT PW cT cW cTL cTR
   b += KS * 4 * 5;                             // segpos PN PE cN cE
-  b += (size_t)kSmallMax * (8 + 4 + 3 + (size_t)ncmax) + 16;  // small-node staging (>= the 8.5 KB of sorted-walk tiles aliased onto it)
+  b += (size_t)kSmallMax * (16 + 4 + (size_t)ncmax) + 32;  // small-node staging (>= the 8.5 KB of sorted-walk tiles aliased onto it)
   b = (b + 15) & ~(size_t)15;
   b += sizeof(GrowShared);
   return b + 16;
@@ -211,13 +214,14 @@ __device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb) {
     m.tileKey = (uint32_t*)(m.tileDelta + kThreads); m.radixBase = m.tileKey + kThreads; m.tileCut = (uint8_t*)(m.radixBase + 256);
     m.pool = (uint16_t*)u;
   }
+  {
+    uintptr_t al = ((uintptr_t)u + 15) & ~(uintptr_t)15;
+    m.smRec = (SmallRec*)al;
+    u = (uint32_t*)(al + (size_t)kSmallMax * 16);
+  }
   m.smEnt = u; u += kSmallMax;
-  uint8_t* b8 = (uint8_t*)u;
-  m.smMult = b8; b8 += kSmallMax; m.smE = b8; b8 += kSmallMax; m.smS = b8; b8 += kSmallMax;
-  m.smCodes = b8; b8 += (size_t)kSmallMax * ncmax;
-  uintptr_t pt = ((uintptr_t)b8 + 7) & ~(uintptr_t)7;
-  m.smT = (double*)pt;
-  u = (uint32_t*)(m.smT + kSmallMax);
+  m.smCodes = (uint8_t*)u;
+  u = (uint32_t*)(m.smCodes + (size_t)kSmallMax * ncmax);
   uintptr_t p = ((uintptr_t)u + 15) & ~(uintptr_t)15;
   m.s = (GrowShared*)p;
   // tell the compiler these all live in shared memory (LDS/STS/ATOMS instead of generic LD/ST)
@@ -229,7 +233,7 @@ __device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb) {
   RF_SH(m.segpos); RF_SH(m.PN); RF_SH(m.PE); RF_SH(m.cN); RF_SH(m.cE); RF_SH(m.PT); RF_SH(m.PW); RF_SH(m.cT); RF_SH(m.cW); RF_SH(m.cTL); RF_SH(m.cTR);
 #endif
 #if RF_ASSUME & 4
-  RF_SH(m.smEnt); RF_SH(m.smT); RF_SH(m.smMult); RF_SH(m.smE); RF_SH(m.smS); RF_SH(m.smCodes);
+  RF_SH(m.smEnt); RF_SH(m.smRec); RF_SH(m.smCodes);
 #endif
 #if RF_ASSUME & 8
   RF_SH(m.tileTL); RF_SH(m.tileTR); RF_SH(m.tileDelta); RF_SH(m.tileKey); RF_SH(m.radixBase); RF_SH(m.tileCut);
@@ -724,107 +728,79 @@ __device__ inline void sort_candidate(const NodeCtx& c, int ci, uint32_t len) {
   __syncthreads();
 }
 
-// ---- sparse evaluation of one candidate in a small node -------------------------------------
-// Only strata that contain events contribute to any rule (side_term), and a stratum's left/right
-// terms change only at the codes of ITS OWN rows.  So delta, as a function of the cut, is piecewise
-// constant with breakpoints at the codes of the (few) rows of the event strata; the tracker only
-// ever selects the first cut of a piece.  With lane = one such row (<= 32 of them) the warp
-// evaluates every piece at once: own-stratum prefix by a shuffle loop, both sides' terms for all
-// lanes in one go (two overlapped log chains instead of one chain per stratum and chunk), then the
-// in-order sum over strata at every breakpoint.  Produces the same summary track_summary does.
-__device__ inline void sparse_candidate(const NodeCtx& c, int ci) {
+// ---- small nodes (<= kSmallMax entries, histogram candidates only) ---------------------------
+// The node is staged in shared memory once -- per entry a 16-byte record (multiplicity * risk time,
+// multiplicity, event, stratum) and one code byte per candidate -- with every gather of an entry in
+// flight together.  Then warp ci scores candidate ci on its own: LANE = CUT (code lane and lane + 32
+// of the current 64-code window), and the warp streams the node's records in list order, which is
+// stratum-major.  Every lane keeps the left sums of its own cut; when the stratum changes the rule's
+// terms of the finished stratum are added (strata without events contribute exactly 0 to every rule,
+// see side_term, and are skipped).  This is the same sum the histogram + prefix-scan + fill-forward
+// of the large-node path produces, with no atomics, no per-stratum synchronisation and a loop body of
+// a few dozen instructions -- the kernel is instruction-fetch bound on its once-per-node code
+// (stall_no_instruction was the top stall at two CTAs per SM), so small code is the optimisation.
+__device__ inline void small_candidate(const NodeCtx& c, int ci, uint32_t len) {
   GrowSmem& m = c.m;
   GrowShared* s = m.s;
   const int lane = lane_id();
-  const int nR = s->nActRows, nAct = s->nAct;
-  const uint8_t* cptr = m.smCodes + ci * kSmallMax;
-  // presence summary (which cuts exist): #present codes, lowest and highest present code
-  uint32_t word = (lane < 8) ? m.pres[ci * 8 + lane] : 0u;
-  int np = warp_sum((int)__popc(word));
-  int last = word ? (lane * 32 + 31 - __clz(word)) : -1;
-  int first = word ? (lane * 32 + __ffs(word) - 1) : 0x7fffffff;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { last = max(last, __shfl_xor_sync(0xffffffffu, last, o)); first = min(first, __shfl_xor_sync(0xffffffffu, first, o)); }
-  if (np < 2) { if (lane == 0) { s->trkNp[ci] = np; s->trkClean[ci] = 1; } return; }
-  const int cov = s->candCov[ci];
-  const double wgt = c.g.split_weight ? c.g.split_weight[cov] : 1.0;
-  const double statP = s->statPnode;
-  // lane -> one row of an event stratum
-  int code = 0x7fff, ia = -1; uint32_t mu = 0, e = 0; double ft = 0.0;
-  if (lane < nR) {
-    const int j = s->actRow[lane];
-    code = cptr[j]; ia = s->actIa[lane]; mu = m.smMult[j]; e = m.smE[j];
-    ft = c.unit ? (double)mu : (double)mu * m.smT[j];
-  }
-  // own-stratum left sums at this row's code: rows of the same stratum with code <= mine
-  uint32_t LN = 0, LE = 0; double LT = 0.0, LW = 0.0;
-  const int lo = (ia >= 0) ? s->actOff[ia] : 0, hi = (ia >= 0) ? s->actOff[ia + 1] : 0;
-  int maxr = hi - lo;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) maxr = max(maxr, __shfl_xor_sync(0xffffffffu, maxr, o));
-  for (int k = 0; k < maxr; k++) {
-    const int src = min(lo + k, 31);
-    const int ck = __shfl_sync(0xffffffffu, code, src);
-    const uint32_t mk = __shfl_sync(0xffffffffu, mu, src), ek = __shfl_sync(0xffffffffu, e, src);
-    const double fk = __shfl_sync(0xffffffffu, ft, src);
-    if (lo + k < hi && ck <= code) { LN += mk; LT += fk; if (ek) { LE += mk; LW += fk; } }
-  }
-  double tL = 0.0, tR = 0.0;
-  if (ia >= 0) {
-    const int a = (int)m.cE[ia];
-    tL = side_term_nb(c.bayes, (double)LE, (double)LN, LT, LW, c.g.alpha, c.beta);
-    tR = side_term_nb(c.bayes, (double)(m.PE[a] - LE), (double)(m.PN[a] - LN), m.PT[a] - LT, m.PW[a] - LW, c.g.alpha, c.beta);
-  }
-  // evaluation points: every row's code (lanes < nR) and the lowest present code (lane nR, the
-  // piece below the first breakpoint); delta = sum over event strata, ascending, of that stratum's
-  // terms at its last breakpoint <= the cut (none: left 0, right = the stratum's parent term)
-  const int q = (lane < nR) ? code : ((lane == nR) ? first : 0x7fff);
-  double accL = 0.0, accR = 0.0;
-  for (int a2 = 0; a2 < nAct; a2++) {
-    const int l2 = s->actOff[a2], h2 = s->actOff[a2 + 1];
-    int bestc = -1; double bl = 0.0, br = m.cTR[m.cE[a2]];
-    for (int k = l2; k < h2; k++) {
-      const int ck = __shfl_sync(0xffffffffu, code, k);
-      const double tlk = __shfl_sync(0xffffffffu, tL, k), trk = __shfl_sync(0xffffffffu, tR, k);
-      if (ck <= q && ck >= bestc) { bestc = ck; bl = tlk; br = trk; }
-    }
-    accL += bl; accR += br;
-  }
-  const double delta = (accL + accR - statP) * wgt;
-  const bool valid = (lane <= nR) && q != last && q <= 0xff;
-  // summary: maximum, its first code, and whether an earlier piece lies within EPSILON of it
-  double M = valid ? delta : -INFINITY; int pos = valid ? q : 0x7fffffff;
-  bool anyNan = __any_sync(0xffffffffu, valid && delta != delta);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double oM = __shfl_xor_sync(0xffffffffu, M, o); const int oP = __shfl_xor_sync(0xffffffffu, pos, o);
-    if (oM > M || (oM == M && oP < pos)) { M = oM; pos = oP; }
-  }
-  const bool near = __any_sync(0xffffffffu, valid && q < pos && !((M - delta) > kEpsilon));
-  const bool clean = !anyNan && !near && !c.w.sinkDelta;
-  if (!clean) {
-    // rare: hand the exact walk the full delta-per-present-code array it expects (track_exact)
-    const int Dc = s->candD[ci];
-    for (int b = lane; b < ((Dc + 31) & ~31); b += 32) {
-      int bestc = -1; double dv = 0.0;
-      for (int k = 0; k <= nR && k < 32; k++) {
-        const int qk = __shfl_sync(0xffffffffu, q, k); const double dk = __shfl_sync(0xffffffffu, delta, k);
-        if (qk <= b && qk >= bestc) { bestc = qk; dv = dk; }
+  const int Dc = s->candD[ci];
+  const SmallRec* __restrict__ rec = m.smRec;
+  const uint8_t* __restrict__ cptr = m.smCodes + ci * kSmallMax;
+  const int nw = (c.Kloop + 31) >> 5;
+  double statP = 0.0;
+  if (lane < 8) m.pres[ci * 8 + lane] = 0u;
+  __syncwarp();
+  for (int base = 0; base < Dc; base += 64) {
+    const uint32_t b0 = (uint32_t)(base + lane), b1 = b0 + 32u;
+    const bool two = Dc > base + 32;
+    double accL0 = 0.0, accR0 = 0.0, accL1 = 0.0, accR1 = 0.0;
+    statP = 0.0;
+    {                                                              // which codes of this window occur in the node (the cuts that exist)
+      uint32_t plo = 0u, phi = 0u;
+      for (uint32_t i = (uint32_t)lane; i < len; i += 32u) {
+        const uint32_t rel = (uint32_t)cptr[i] - (uint32_t)base;
+        if (rel < 32u) plo |= 1u << rel; else if (rel < 64u) phi |= 1u << (rel - 32u);
       }
-      if (b < Dc) m.sL[ci * m.hb + b] = dv;
+      plo = __reduce_or_sync(0xffffffffu, plo); phi = __reduce_or_sync(0xffffffffu, phi);
+      if (lane == 0) { m.pres[ci * 8 + (base >> 5)] = plo; if (two) m.pres[ci * 8 + (base >> 5) + 1] = phi; }
     }
+    for (int w8 = 0; w8 < nw; w8++) {
+      uint32_t word = s->evMask[w8];
+      while (word) {                                               // strata with events, ascending (warp-uniform)
+        const int sidx = (w8 << 5) + __ffs(word) - 1;
+        word &= word - 1u;
+        const uint32_t r0 = m.segpos[sidx], r1 = m.cN[sidx];
+        uint32_t TN = 0, TE = 0, LN0 = 0, LE0 = 0, LN1 = 0, LE1 = 0;
+        double TT = 0.0, TW = 0.0, LT0 = 0.0, LW0 = 0.0, LT1 = 0.0, LW1 = 0.0;
+#pragma unroll 4
+        for (uint32_t i = r0; i < r1; i++) {
+          const SmallRec r = rec[i];
+          const uint32_t code = cptr[i];
+          const uint32_t mu = r.mult;
+          const double ft = c.unit ? (double)mu : r.mrt;
+          const bool ev = (r.es & 1u) != 0u;
+          const bool l0 = code <= b0, l1 = code <= b1;
+          const uint32_t me = ev ? mu : 0u; const double fe = ev ? ft : 0.0;
+          TN += mu; TT += ft; TE += me; TW += fe;
+          LN0 += l0 ? mu : 0u; LT0 += l0 ? ft : 0.0; LE0 += l0 ? me : 0u; LW0 += l0 ? fe : 0.0;
+          LN1 += l1 ? mu : 0u; LT1 += l1 ? ft : 0.0; LE1 += l1 ? me : 0u; LW1 += l1 ? fe : 0.0;
+        }
+        statP += side_term_nb(c.bayes, (double)TE, (double)TN, TT, TW, c.g.alpha, c.beta);
+        accL0 += side_term_nb(c.bayes, (double)LE0, (double)LN0, LT0, LW0, c.g.alpha, c.beta);
+        accR0 += side_term_nb(c.bayes, (double)(TE - LE0), (double)(TN - LN0), TT - LT0, TW - LW0, c.g.alpha, c.beta);
+        if (two) {
+          accL1 += side_term_nb(c.bayes, (double)LE1, (double)LN1, LT1, LW1, c.g.alpha, c.beta);
+          accR1 += side_term_nb(c.bayes, (double)(TE - LE1), (double)(TN - LN1), TT - LT1, TW - LW1, c.g.alpha, c.beta);
+        }
+      }
+    }
+    if (b0 < (uint32_t)Dc) { m.sL[ci * m.hb + b0] = accL0; m.sR[ci * m.hb + b0] = accR0; }
+    if (b1 < (uint32_t)Dc) { m.sL[ci * m.hb + b1] = accL1; m.sR[ci * m.hb + b1] = accR1; }
   }
-  if (lane == 0) {
-    s->trkNp[ci] = np; s->trkMax[ci] = M; s->trkMaxBin[ci] = pos; s->trkClean[ci] = clean ? 1 : 0; s->trkLast[ci] = last;
-  }
+  if (lane == 0) m.statP[ci] = statP;
+  __syncwarp();
 }
 
-// ---- small nodes (<= kSmallMax entries, histogram candidates only) ---------------------------
-// One batched prefetch brings the node's entries, their event / risk time / stratum and the codes
-// of every candidate into shared memory (a single exposed memory latency instead of one per
-// stratum); after that every warp scores its own candidate with warp-level synchronisation only,
-// visiting just the strata that contain events in this node (all other cells contribute exactly 0
-// to every rule, see side_term) -- their rows matter only for which cuts exist (presence bits).
 __device__ inline void score_small(NodeCtx& c) {
   GrowSmem& m = c.m;
   GrowShared* s = m.s;
@@ -833,154 +809,50 @@ __device__ inline void score_small(NodeCtx& c) {
   const uint32_t len = s->cur.len;
   const DevData& d = c.d;
   const GrowWork& w = c.w;
-  // segpos = first entry of a stratum, cN = one past its last entry (both 0 when absent)
-  for (int k = tid; k <= c.Kloop + 1; k += kThreads) { m.segpos[k] = 0; m.cN[k] = 0; }
-  for (int i = tid; i < nc * 8; i += kThreads) m.pres[i] = 0u;
+  if (tid < 8) s->evMask[tid] = 0u;
   if (tid == 0) { s->have = 0; s->bestDelta = 0.0; s->bestCand = -1; s->bestCode = 0; s->cutsSeen = 0; }
   __syncthreads();
   RF_PROF(2);
-  for (uint32_t j = tid; j < len; j += kThreads) {
-    const uint32_t ent = c.list[j];
-    m.smEnt[j] = ent;
-    m.smMult[j] = (uint8_t)((ent >> kRowBits) + 1u);
-  }
-  __syncthreads();
-  RF_PROF(14);
-  // one warp per column (nc candidate code columns + event, risk time, stratum); each lane keeps
-  // four gathers in flight before it touches shared memory again
-  {
-    const int ncols = nc + 3;
-    for (int col = wid; col < ncols; col += kWarps) {
-      if (col < nc) {
-        const uint8_t* __restrict__ ptr = (const uint8_t*)s->candPtr[col];
-        const int nwords = (s->candD[col] + 31) >> 5;
-        uint32_t acc = 0u;                                   // lane w accumulates presence word w
-        for (uint32_t j0 = 0; j0 < len; j0 += 128) {
-          uint32_t v[4];
+  // stage: one thread per entry, all of an entry's gathers issued before the first shared-memory store
+  for (uint32_t j0 = (uint32_t)(tid - lane); j0 < len; j0 += kThreads) {
+    const uint32_t j = j0 + lane;
+    const bool valid = j < len;
+    const uint32_t ent = valid ? c.list[j] : 0u;
+    const uint32_t row = ent & kRowMask, mult = (ent >> kRowBits) + 1u;
+    const uint32_t e = d.ev[row];
+    const double tv = d.rt[row];
+    const uint32_t sidx = c.strat ? (uint32_t)d.strat[row] - 1u : 0u;
+    // the stratum of the entry before this warp's first / after its last one (segment boundaries)
+    uint32_t edgeS = 0xFFFFFFFFu;
+    if (c.strat) {
+      if (lane == 0 && j > 0u) edgeS = (uint32_t)d.strat[c.list[j - 1u] & kRowMask] - 1u;
+      if (lane == 31 && j + 1u < len) edgeS = (uint32_t)d.strat[c.list[j + 1u] & kRowMask] - 1u;
+    }
+    for (int half = 0; half < nc; half += 8) {
+      uint32_t raw[8];
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const uint32_t j = j0 + k * 32 + lane;
-            v[k] = (j < len) ? (uint32_t)ptr[m.smEnt[j] & kRowMask] : 0xFFFFu;
-          }
+      for (int q = 0; q < 8; q++) raw[q] = (half + q < nc) ? (uint32_t)((const uint8_t*)s->candPtr[half + q])[row] : 0u;
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const uint32_t j = j0 + k * 32 + lane;
-            if (j < len) m.smCodes[col * kSmallMax + j] = (uint8_t)v[k];
-            for (int wd2 = 0; wd2 < nwords; wd2++) {
-              const uint32_t bits = ((v[k] >> 5) == (uint32_t)wd2) ? (1u << (v[k] & 31u)) : 0u;
-              const uint32_t red = __reduce_or_sync(0xffffffffu, bits);
-              if (lane == wd2) acc |= red;
-            }
-          }
-        }
-        if (lane < nwords) m.pres[col * 8 + lane] = acc;
-      } else if (col == nc) {
-        for (uint32_t j0 = 0; j0 < len; j0 += 128) {
-          uint32_t v[4];
-#pragma unroll
-          for (int k = 0; k < 4; k++) { const uint32_t j = j0 + k * 32 + lane; v[k] = (j < len) ? (uint32_t)d.ev[m.smEnt[j] & kRowMask] : 0u; }
-#pragma unroll
-          for (int k = 0; k < 4; k++) { const uint32_t j = j0 + k * 32 + lane; if (j < len) m.smE[j] = (uint8_t)v[k]; }
-        }
-      } else if (col == nc + 1) {
-        for (uint32_t j0 = 0; j0 < len; j0 += 128) {
-          double v[4];
-#pragma unroll
-          for (int k = 0; k < 4; k++) { const uint32_t j = j0 + k * 32 + lane; v[k] = (j < len) ? d.rt[m.smEnt[j] & kRowMask] : 0.0; }
-#pragma unroll
-          for (int k = 0; k < 4; k++) { const uint32_t j = j0 + k * 32 + lane; if (j < len) m.smT[j] = v[k]; }
-        }
-      } else {
-        for (uint32_t j0 = 0; j0 < len; j0 += 128) {
-          uint32_t v[4];
-#pragma unroll
-          for (int k = 0; k < 4; k++) { const uint32_t j = j0 + k * 32 + lane; v[k] = (j < len && c.strat) ? (uint32_t)d.strat[m.smEnt[j] & kRowMask] - 1u : 0u; }
-#pragma unroll
-          for (int k = 0; k < 4; k++) { const uint32_t j = j0 + k * 32 + lane; if (j < len) m.smS[j] = (uint8_t)v[k]; }
-        }
-      }
+      for (int q = 0; q < 8; q++)
+        if (valid && half + q < nc) m.smCodes[(half + q) * kSmallMax + j] = (uint8_t)raw[q];
+    }
+    uint32_t prevS = __shfl_up_sync(0xffffffffu, sidx, 1), nextS = __shfl_down_sync(0xffffffffu, sidx, 1);
+    if (lane == 0) prevS = (j > 0u && !c.strat) ? 0u : edgeS;
+    if (lane == 31) nextS = (j + 1u < len && !c.strat) ? 0u : edgeS;
+    if (j + 1u >= len) nextS = 0xFFFFFFFFu;
+    if (valid) {
+      m.smEnt[j] = ent;
+      SmallRec r; r.mrt = (double)mult * tv; r.mult = mult; r.es = (e ? 1u : 0u) | (sidx << 8);
+      m.smRec[j] = r;
+      if (prevS != sidx) m.segpos[sidx] = j;
+      if (nextS != sidx) m.cN[sidx] = j + 1u;
+      if (e) atomicOr(&s->evMask[sidx >> 5], 1u << (sidx & 31u));
     }
   }
   __syncthreads();
   RF_PROF(3);
-  for (uint32_t j = tid; j < len; j += kThreads) {
-    const int sj = m.smS[j] + 1;
-    if (j == 0 || m.smS[j - 1] + 1 != sj) m.segpos[sj] = j;
-    if (j == len - 1 || m.smS[j + 1] + 1 != sj) m.cN[sj] = j + 1;
-  }
-  __syncthreads();
-  // per-stratum totals, one warp per stratum
-  for (int a = 1 + wid; a <= c.Kloop; a += kWarps) {
-    const uint32_t b0 = m.segpos[a], b1 = m.cN[a];
-    uint32_t tN = 0, tE = 0; double tT = 0.0, tW = 0.0;
-    for (uint32_t i = b0 + lane; i < b1; i += 32) {
-      const uint32_t mu = m.smMult[i];
-      const double ft = c.unit ? (double)mu : (double)mu * m.smT[i];
-      tN += mu; tT += ft;
-      if (m.smE[i]) { tE += mu; tW += ft; }
-    }
-    tN = warp_sum(tN); tE = warp_sum(tE); tT = warp_sum(tT); tW = warp_sum(tW);
-    if (lane == 0) {
-      m.PN[a] = tN; m.PE[a] = tE; m.PT[a] = tT; m.PW[a] = tW;
-      m.cTR[a] = (tE > 0) ? side_term(c.bayes, (double)tE, (double)tN, tT, tW, c.g.alpha, c.beta) : 0.0;
-    }
-  }
-  __syncthreads();
-  // ascending list of the strata that contain events (kept in cE[]) and the parent statistic
-  if (wid == 0) {
-    int nAct = 0;
-    for (int base = 0; base < c.Kloop; base += 32) {
-      const int a = base + lane + 1;
-      const bool act = a <= c.Kloop && m.PE[a] > 0;
-      const unsigned bm = __ballot_sync(0xffffffffu, act);
-      if (act) m.cE[nAct + __popc(bm & ((1u << lane) - 1u))] = (uint32_t)a;
-      nAct += __popc(bm);
-    }
-    __syncwarp();
-    if (lane == 0) {
-      double sp = 0.0;
-      for (int ia = 0; ia < nAct; ia++) sp += m.cTR[m.cE[ia]];
-      s->nAct = nAct; s->statPnode = sp;
-    }
-    // rows of the event strata, stratum-ascending; <= 31 of them enables the sparse evaluation
-    int nrows = 0x7fffffff;
-    if (nAct <= 32) {
-      const int a = (lane < nAct) ? (int)m.cE[lane] : 0;
-      const int r = (lane < nAct) ? (int)(m.cN[a] - m.segpos[a]) : 0;
-      const int inc = warp_incl_scan(r);
-      nrows = __shfl_sync(0xffffffffu, inc, 31);
-      if (nrows <= 31) {
-        if (lane < nAct) { s->actOff[lane] = (uint8_t)(inc - r); for (int k = 0; k < r; k++) { s->actRow[inc - r + k] = (uint16_t)(m.segpos[a] + k); s->actIa[inc - r + k] = (uint8_t)lane; } }
-        if (lane == 0) s->actOff[nAct] = (uint8_t)nrows;
-      }
-    }
-    if (lane == 0) s->nActRows = (nrows <= 31) ? nrows : -1;
-  }
-  __syncthreads();
-  RF_PROF(5);
-  const int nAct = s->nAct;
-  const bool sparse = s->nActRows >= 0;
   for (int ci = wid; ci < nc; ci += kWarps) {
-    if (sparse) { sparse_candidate(c, ci); continue; }
-    const int Dc = s->candD[ci];
-    for (int b = lane; b < Dc; b += 32) { m.sL[ci * m.hb + b] = 0.0; m.sR[ci * m.hb + b] = 0.0; }
-    const uint8_t* cptr = m.smCodes + ci * kSmallMax;
-    __syncwarp();
-    for (int ia = 0; ia < nAct; ia++) {
-      const int a = (int)m.cE[ia];
-      const uint32_t b0 = m.segpos[a], b1 = m.cN[a];
-      for (uint32_t i = b0 + lane; i < b1; i += 32) {
-        const int idx = ci * m.hs * m.hb + (int)cptr[i];
-        const uint32_t mu = m.smMult[i];
-        const double tv = m.smT[i];
-        hist_add(m, idx, mu, m.smE[i], c.unit, tv == d.rt_mode, (unsigned long long)__double2ll_rn(tv * c.g.tscale) * (unsigned long long)mu);
-      }
-      __syncwarp();
-      flush_candidate(c, ci, 0, m.PN[a], m.PE[a], m.PT[a], m.PW[a], m.cTR[a], false);
-      __syncwarp();
-    }
-    if (lane == 0) m.statP[ci] = s->statPnode;
-    __syncwarp();
+    small_candidate(c, ci, len);
     track_summary(c, ci);
   }
   __syncthreads();
@@ -1337,8 +1209,9 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
           en[u] = m.smEnt[i];
           lf[u] = cptr[i] <= bcode;                               // LEFT iff cut - x >= 0 (rf.c:15194)
           const unsigned long long mult = (en[u] >> kRowBits) + 1u;
-          if (lf[u]) my += 1ull | (mult << 16) | ((m.smE[i] ? mult : 0ull) << 40);
-          if (bayes) { const double v = (double)mult * m.smT[i]; if (lf[u]) rtL += v; else rtR += v; }
+          const SmallRec r = m.smRec[i];
+          if (lf[u]) my += 1ull | (mult << 16) | (((r.es & 1u) ? mult : 0ull) << 40);
+          if (bayes) { if (lf[u]) rtL += r.mrt; else rtR += r.mrt; }
         }
       }
       unsigned long long tot;
