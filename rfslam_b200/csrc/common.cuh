@@ -131,21 +131,15 @@ __host__ __device__ inline bool rule_unit_time(int rule)     { return rule == 3 
 
 // E, N: event / row counts; T: exposure; W: sum of event * exposure.  Zero-event cells contribute
 // exactly 0 under every rule (Bayes: 0 * log(.), sc.c:761; raw: mu = 0 is skipped, sc.c:1282).
-__host__ __device__ inline double side_term(bool bayes, double E, double N, double T, double W, double alpha, double beta) {
-  if (E == 0.0) return 0.0;
-  if (bayes) {
-    double lam = (E + alpha) / (beta + T);
-    return E * log(lam);
-  }
-  if (T == 0.0) return 0.0;
-  double mu = W / T;
-  if (mu == 0.0) return 0.0;
-  return (E * log(mu)) - (N * mu);
-}
-
-// Branch-free form of side_term for code that evaluates several terms back to back (the two
-// sides of two chunks): the four logs form independent dependency chains the scheduler can overlap.
-__host__ __device__ inline double side_term_nb(bool bayes, double E, double N, double T, double W, double alpha, double beta) {
+// Branch-free form of side_term.  On the device this is ONE out-of-line function: the tree kernel is
+// instruction-fetch bound on its once-per-node code, and every inlined copy of the FP64 divide + log
+// sequence is ~120 instructions.
+#ifdef __CUDACC__
+static __device__ __noinline__
+#else
+inline
+#endif
+double side_term_nb(bool bayes, double E, double N, double T, double W, double alpha, double beta) {
   if (bayes) {
     const double lam = (E + alpha) / (beta + T);
     const double r = E * log(lam);
@@ -156,6 +150,23 @@ __host__ __device__ inline double side_term_nb(bool bayes, double E, double N, d
   const double mu = ok ? mu0 : 1.0;
   const double r = (E * log(mu)) - (N * mu);
   return ok ? r : 0.0;
+}
+
+
+__host__ __device__ inline double side_term(bool bayes, double E, double N, double T, double W, double alpha, double beta) {
+#ifdef __CUDA_ARCH__
+  return side_term_nb(bayes, E, N, T, W, alpha, beta);
+#else
+  if (E == 0.0) return 0.0;
+  if (bayes) {
+    double lam = (E + alpha) / (beta + T);
+    return E * log(lam);
+  }
+  if (T == 0.0) return 0.0;
+  double mu = W / T;
+  if (mu == 0.0) return 0.0;
+  return (E * log(mu)) - (N * mu);
+#endif
 }
 
 #ifdef __CUDACC__
