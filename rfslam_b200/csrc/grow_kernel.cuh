@@ -108,7 +108,7 @@ struct GrowShared {
   unsigned long long candCount, algoBytes;
   int abort;
   int ptotReady;
-  int nAct; double statPnode; int isSmall; int poolSize;
+  int needSlow; int isSmall; int poolSize;
   // sparse evaluation of small nodes: the rows of the strata that contain events (<= 32), stratum-ascending
   uint32_t evMask[8];                // small nodes: strata that contain events
   int trkMaxBin[kMaxCand]; double trkMax[kMaxCand]; int trkClean[kMaxCand]; int trkNp[kMaxCand]; int trkLast[kMaxCand];
@@ -423,6 +423,7 @@ __device__ inline void track_summary(const NodeCtx& c, int ci) {
   const double wgt = c.g.split_weight ? c.g.split_weight[cov] : 1.0;
   const double statP = m.statP[ci];
   double M = -INFINITY; int pos = 0x7fffffff; bool anyNan = false;
+#pragma unroll 1
   for (int ch = 0; ch < nch; ch++) {
     int bin = (ch << 5) + lane;
     uint32_t wd = m.pres[ci * 8 + ch];
@@ -442,6 +443,7 @@ __device__ inline void track_summary(const NodeCtx& c, int ci) {
   }
   bool near = false;                                        // an earlier cut within EPSILON of the maximum?
   if (!anyNan) {
+#pragma unroll 1
     for (int ch = 0; ch <= (pos >> 5); ch++) {
       int bin = (ch << 5) + lane;
       uint32_t wd = m.pres[ci * 8 + ch];
@@ -467,6 +469,7 @@ __device__ inline void track_exact(const NodeCtx& c, int ci) {
   const int cov = s->candCov[ci];
   int have = s->have; double best = s->bestDelta; int bestBin = -1;
   int emitted = s->cutsSeen;
+#pragma unroll 1
   for (int ch = 0; ch < nch; ch++) {
     int bin = (ch << 5) + lane;
     uint32_t wd = m.pres[ci * 8 + ch];
@@ -523,10 +526,9 @@ __device__ inline void track_combine_all(const NodeCtx& c, int nc) {
   const bool mine = lane < nc;
   const int np = mine ? s->trkNp[lane] : 0;
   const bool clean = mine ? (s->trkClean[lane] != 0) : true;
-  if (c.w.sinkDelta || __any_sync(0xffffffffu, mine && np >= 2 && !clean)) {
-    for (int ci = 0; ci < nc; ci++) track_combine_one(c, ci);
-    return;
-  }
+  const bool slow = c.w.sinkDelta || __any_sync(0xffffffffu, mine && np >= 2 && !clean);
+  if (lane == 0) s->needSlow = slow ? 1 : 0;              // near-ties / NaN / emit mode: the caller walks the candidates one by one
+  if (slow) return;
   if (mine && np < 2) {                                   // constant in this node (rf.c:15004-15007)
     const int cov = s->candCov[lane];
     atomicAnd(&s->perm[cov >> 5], ~(1u << (cov & 31)));
@@ -534,6 +536,7 @@ __device__ inline void track_combine_all(const NodeCtx& c, int nc) {
   const int cuts = warp_sum(np >= 2 ? np - 1 : 0);
   const double M = mine ? s->trkMax[lane] : 0.0;
   int have = s->have; double best = s->bestDelta; int bc = -1;
+#pragma unroll 1
   for (int ci = 0; ci < nc; ci++) {
     const double Mi = __shfl_sync(0xffffffffu, M, ci);
     const int npi = __shfl_sync(0xffffffffu, np, ci);
@@ -851,15 +854,7 @@ __device__ inline void score_small(NodeCtx& c) {
   }
   __syncthreads();
   RF_PROF(3);
-  for (int ci = wid; ci < nc; ci += kWarps) {
-    small_candidate(c, ci, len);
-    track_summary(c, ci);
-  }
-  __syncthreads();
-  RF_PROF(4);
-  if (wid == 0) track_combine_all(c, nc);
-  __syncthreads();
-  RF_PROF(6);
+  for (int ci = wid; ci < nc; ci += kWarps) small_candidate(c, ci, len);   // the same warp summarises ci next (score_node)
 }
 
 // ---- score all drawn candidates of the current node (steps 2-4) ------------------------------
@@ -877,12 +872,13 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
 
   bool allHist = true;
   for (int ci = 0; ci < nc; ci++) if (!s->candHist[ci]) allHist = false;
-  if (allHist && cur.len <= (uint32_t)kSmallMax) {
+  const bool small = allHist && cur.len <= (uint32_t)kSmallMax;
+  bool anyHist = false, anySort = false;
+  for (int ci = 0; ci < nc; ci++) { if (s->candHist[ci]) anyHist = true; else anySort = true; }
+  if (small) {
     if (tid == 0) s->isSmall = 1;
     score_small(c);
-    return;
-  }
-
+  } else {
   // segment boundaries of the strata inside this node's (row-sorted) entry list
   if (strat) {
     for (int k = tid; k <= d.K + 1; k += kThreads) {
@@ -903,9 +899,6 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
   if (tid == 0) { s->have = 0; s->bestDelta = 0.0; s->bestCand = -1; s->bestCode = 0; s->cutsSeen = 0; }
   __syncthreads();
   RF_PROF(2);
-
-  bool anyHist = false, anySort = false;
-  for (int ci = 0; ci < nc; ci++) { if (s->candHist[ci]) anyHist = true; else anySort = true; }
 
   if (anyHist) {
     unsigned hmask = 0u;
@@ -959,16 +952,21 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
     }
   }
   if (anySort) { stratum_totals(c, cur.len); RF_PROF(5); }
+  }
+  // shared tail: warp ci summarises candidate ci (the warp that scored it), then warp 0 replays the
+  // tracker in draw order
   for (int ci = warp_id(); ci < nc; ci += kWarps)
     if (s->candHist[ci]) track_summary(c, ci);
   __syncthreads();
+  RF_PROF(4);
 
   if (!anySort) {
     if (warp_id() == 0) track_combine_all(c, nc);
     __syncthreads();
     RF_PROF(6);
-    return;
+    if (!s->needSlow) return;
   }
+#pragma unroll 1
   for (int ci = 0; ci < nc; ci++) {
     if (s->candHist[ci]) {
       if (warp_id() == 0) track_combine_one(c, ci);
@@ -995,6 +993,7 @@ __device__ inline void draw_candidates(const DevData& d, const GrowParams& g, Gr
     const int idum0 = s->rng.idum;
     const int myIdum = (lane < nd) ? ran1_mulmod(kJump[lane], (uint32_t)idum0) : 0;
     int iy = s->rng.iy, myIy = 0;
+#pragma unroll 1
     for (int k = 0; k < nd; k++) {
       const int idk = __shfl_sync(0xffffffffu, myIdum, k);
       const int j = iy / 67108864;
@@ -1010,6 +1009,7 @@ __device__ inline void draw_candidates(const DevData& d, const GrowParams& g, Gr
     if (lane == 0) s->rng.idum = lastIdum;
     uint32_t slot = 0;
     if (lane < nd) slot = (uint32_t)ceil((double)ran1_float(myIy) * ((double)(size0 - lane) * 1.0));   // in [1, size]
+#pragma unroll 1
     for (int k = 0; k < nd; k++) {
       const uint32_t sl = __shfl_sync(0xffffffffu, slot, k);
       const int cov = m.pool[sl - 1];
@@ -1133,6 +1133,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     if (attempt) {
       if (warp_id() == 0) {                                // permissible covariates, ascending, by ballot compaction
         int size = 0;
+#pragma unroll 1
         for (int base = 0; base < d.p; base += 32) {
           const int k = base + lane_id();
           const bool ok = k < d.p && ((s->perm[base >> 5] >> lane_id()) & 1u);
@@ -1180,6 +1181,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
       if (s->abort == 2) break;
       if (!s->abort) {
         const uint32_t* sp = w.stackPerm + ((size_t)tree * kStackCap + s->sp) * g.pw;
+#pragma unroll 1
         for (int k = tid; k < g.pw; k += kThreads) s->perm[k] = sp[k];
       }
       continue;
@@ -1315,6 +1317,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     if (!s->abort) {
       // children inherit the parent's (possibly updated) permissible mask (rf.c:10725-10727)
       uint32_t* sp = w.stackPerm + ((size_t)tree * kStackCap + s->sp) * g.pw;
+#pragma unroll 1
       for (int k = tid; k < g.pw; k += kThreads) sp[k] = s->perm[k];
       __syncthreads();
       if (tid == 0) s->sp++;
