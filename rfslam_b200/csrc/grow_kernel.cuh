@@ -108,7 +108,7 @@ struct GrowShared {
   unsigned long long candCount, algoBytes;
   int abort;
   int ptotReady;
-  int needSlow; int isSmall; int poolSize;
+  int needSlow; int isSmall; int poolSize; int histDirty;
   // sparse evaluation of small nodes: the rows of the strata that contain events (<= 32), stratum-ascending
   uint32_t evMask[8];                // small nodes: strata that contain events
   int trkMaxBin[kMaxCand]; double trkMax[kMaxCand]; int trkClean[kMaxCand]; int trkNp[kMaxCand]; int trkLast[kMaxCand];
@@ -804,6 +804,130 @@ __device__ inline void small_candidate(const NodeCtx& c, int ci, uint32_t len) {
   __syncwarp();
 }
 
+// LANE = ROW variant for nodes whose event strata are all short (<= 32 rows each; the usual case under
+// the stratified rules).  The FP64 divide + log of the rule terms is what the candidate warps contend
+// for, and a stratum's terms only change at the codes of its own rows: so the terms are evaluated once
+// per ROW of an event stratum (32 rows per batch: two term evaluations for the whole batch, against
+// three to five per stratum with lane = cut), written to a per-stratum table, and each cut then adds,
+// stratum by stratum, the entry of the largest code <= the cut (fill-forward by bit search).  The
+// rows holding their stratum's largest code have "left = everything", i.e. their left term IS the
+// stratum's parent term.  Tables live in this candidate's slice of the (idle) large-node histograms.
+__device__ inline void small_candidate_rows(const NodeCtx& c, int ci, uint32_t len) {
+  GrowSmem& m = c.m;
+  GrowShared* s = m.s;
+  const int lane = lane_id();
+  const int Dc = s->candD[ci];
+  const int nwords = (Dc + 31) >> 5;
+  const SmallRec* __restrict__ rec = m.smRec;
+  const uint8_t* __restrict__ cptr = m.smCodes + ci * kSmallMax;
+  const int nw = (c.Kloop + 31) >> 5;
+  const int G = m.hs;                                              // table slots = strata per group
+  double* tabL = m.hT + (size_t)ci * m.hs * m.hb;
+  double* tabR = m.hW + (size_t)ci * m.hs * m.hb;
+  uint32_t* mk = m.hN + (size_t)ci * m.hs * m.hb;                  // [slot][8] codes that have rows in the slot's stratum
+  if (lane < 8) m.pres[ci * 8 + lane] = 0u;
+  for (int b = lane; b < Dc; b += 32) { m.sL[ci * m.hb + b] = 0.0; m.sR[ci * m.hb + b] = 0.0; }
+  __syncwarp();
+#pragma unroll 1
+  for (int base = 0; base < Dc; base += 64) {                      // which codes occur in the node (the cuts that exist)
+    uint32_t plo = 0u, phi = 0u;
+    for (uint32_t i = (uint32_t)lane; i < len; i += 32u) {
+      const uint32_t rel = (uint32_t)cptr[i] - (uint32_t)base;
+      if (rel < 32u) plo |= 1u << rel; else if (rel < 64u) phi |= 1u << (rel - 32u);
+    }
+    plo = __reduce_or_sync(0xffffffffu, plo); phi = __reduce_or_sync(0xffffffffu, phi);
+    if (lane == 0) { m.pres[ci * 8 + (base >> 5)] = plo; if (Dc > base + 32) m.pres[ci * 8 + (base >> 5) + 1] = phi; }
+  }
+  double statP = 0.0;
+  int w8 = 0; uint32_t word = s->evMask[0];
+#pragma unroll 1
+  while (true) {
+    // next group of up to G strata with events, ascending
+    uint32_t r0[RF_MAX_SLOTS], r1[RF_MAX_SLOTS]; double tP[RF_MAX_SLOTS];
+    int ng = 0;
+#pragma unroll
+    for (int q = 0; q < RF_MAX_SLOTS; q++) {
+      r0[q] = 0u; r1[q] = 0u; tP[q] = 0.0;
+      if (q < G) {
+        while (!word && ++w8 < nw) word = s->evMask[w8];
+        if (word) {
+          const int sidx = (w8 << 5) + __ffs(word) - 1;
+          word &= word - 1u;
+          r0[q] = m.segpos[sidx]; r1[q] = m.cN[sidx]; ng = q + 1;
+        }
+      }
+    }
+    if (ng == 0) break;
+    if (lane < G * 8) mk[lane] = 0u;
+    __syncwarp();
+    uint32_t R = 0;
+#pragma unroll
+    for (int q = 0; q < RF_MAX_SLOTS; q++) R += r1[q] - r0[q];
+#pragma unroll 1
+    for (uint32_t bb = 0; bb < R; bb += 32u) {
+      const uint32_t idx = bb + (uint32_t)lane;
+      int myG = -1; uint32_t myJ = 0u, lo = 0u, hi = 0u, cum = 0u;
+#pragma unroll
+      for (int q = 0; q < RF_MAX_SLOTS; q++) {
+        const uint32_t sz = r1[q] - r0[q];
+        if (myG < 0 && idx < cum + sz) { myG = q; myJ = r0[q] + (idx - cum); lo = r0[q]; hi = r1[q]; }
+        cum += sz;
+      }
+      const uint32_t myCode = (myG >= 0) ? (uint32_t)cptr[myJ] : 0u;
+      uint32_t TN = 0, TE = 0, LN = 0, LE = 0;
+      double TT = 0.0, TW = 0.0, LT = 0.0, LW = 0.0;
+      for (uint32_t k = lo; k < hi; k++) {                          // my stratum's rows (<= 32)
+        const SmallRec r = rec[k];
+        const uint32_t mu = r.mult;
+        const double ft = c.unit ? (double)mu : r.mrt;
+        const bool ev = (r.es & 1u) != 0u;
+        const bool le = (uint32_t)cptr[k] <= myCode;
+        const uint32_t me = ev ? mu : 0u; const double fe = ev ? ft : 0.0;
+        TN += mu; TT += ft; TE += me; TW += fe;
+        LN += le ? mu : 0u; LT += le ? ft : 0.0; LE += le ? me : 0u; LW += le ? fe : 0.0;
+      }
+      const double tL = side_term_nb(c.bayes, (double)LE, (double)LN, LT, LW, c.g.alpha, c.beta);
+      const double tR = side_term_nb(c.bayes, (double)(TE - LE), (double)(TN - LN), TT - LT, TW - LW, c.g.alpha, c.beta);
+      if (myG >= 0) {
+        tabL[myG * m.hb + (int)myCode] = tL; tabR[myG * m.hb + (int)myCode] = tR;
+        atomicOr(&mk[myG * 8 + (int)(myCode >> 5)], 1u << (myCode & 31u));
+      }
+#pragma unroll
+      for (int q = 0; q < RF_MAX_SLOTS; q++) {
+        const unsigned bal = __ballot_sync(0xffffffffu, myG == q && LN == TN);
+        if (bal) tP[q] = __shfl_sync(0xffffffffu, tL, __ffs(bal) - 1);
+      }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int wq = 0; wq < nwords; wq++) {                          // lane = cut: add this group's strata in ascending order
+      const int q = (wq << 5) + lane;
+      if (q < Dc) {
+        double aL = m.sL[ci * m.hb + q], aR = m.sR[ci * m.hb + q];
+#pragma unroll
+        for (int g2 = 0; g2 < RF_MAX_SLOTS; g2++) {
+          if (g2 < ng) {
+            int src = -1;
+            for (int w2 = wq; w2 >= 0 && src < 0; w2--) {
+              uint32_t mw = mk[g2 * 8 + w2];
+              if (w2 == wq) mw &= 0xFFFFFFFFu >> (31 - lane);
+              if (mw) src = (w2 << 5) + 31 - __clz(mw);
+            }
+            if (src >= 0) { aL += tabL[g2 * m.hb + src]; aR += tabR[g2 * m.hb + src]; }
+            else aR += tP[g2];
+          }
+        }
+        m.sL[ci * m.hb + q] = aL; m.sR[ci * m.hb + q] = aR;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < RF_MAX_SLOTS; q++) if (q < ng) statP += tP[q];
+    __syncwarp();
+  }
+  if (lane == 0) m.statP[ci] = statP;
+  __syncwarp();
+}
+
 __device__ inline void score_small(NodeCtx& c) {
   GrowSmem& m = c.m;
   GrowShared* s = m.s;
@@ -854,7 +978,18 @@ __device__ inline void score_small(NodeCtx& c) {
   }
   __syncthreads();
   RF_PROF(3);
-  for (int ci = wid; ci < nc; ci += kWarps) small_candidate(c, ci, len);   // the same warp summarises ci next (score_node)
+  // longest event stratum of the node decides the evaluation scheme (warp-uniform, same for every warp)
+  uint32_t maxSeg = 0;
+  for (int w8 = 0; w8 < ((c.Kloop + 31) >> 5); w8++) {
+    uint32_t word = s->evMask[w8];
+    while (word) { const int sidx = (w8 << 5) + __ffs(word) - 1; word &= word - 1u; maxSeg = max(maxSeg, m.cN[sidx] - m.segpos[sidx]); }
+  }
+  if (maxSeg <= 32u) {
+    if (tid == 0) s->histDirty = 1;                                  // the tables live in the large-node histograms
+    for (int ci = wid; ci < nc; ci += kWarps) small_candidate_rows(c, ci, len);
+  } else {
+    for (int ci = wid; ci < nc; ci += kWarps) small_candidate(c, ci, len);   // the same warp summarises ci next (score_node)
+  }
 }
 
 // ---- score all drawn candidates of the current node (steps 2-4) ------------------------------
@@ -893,11 +1028,15 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
   } else if (tid == 0) {
     m.segpos[0] = 0; m.segpos[1] = 0; m.segpos[2] = cur.len;
   }
+  if (s->histDirty) {                                                // small nodes kept tables in the histograms since the last large node
+    for (int i = tid; i < g.ncmax * m.hb * m.hs; i += kThreads) { m.hN[i] = 0; m.hT[i] = 0.0; m.hW[i] = 0.0; }
+  }
   for (int i = tid; i < nc * m.hb; i += kThreads) { m.sL[i] = 0.0; m.sR[i] = 0.0; }
   for (int i = tid; i < nc * 8; i += kThreads) m.pres[i] = 0u;
   if (tid < nc) m.statP[tid] = 0.0;
   if (tid == 0) { s->have = 0; s->bestDelta = 0.0; s->bestCand = -1; s->bestCode = 0; s->cutsSeen = 0; }
   __syncthreads();
+  if (tid == 0) s->histDirty = 0;                                    // (every thread has read the flag above)
   RF_PROF(2);
 
   if (anyHist) {
@@ -1062,7 +1201,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     s->tmark = clock64();
     ran1_seed(s->rng, w.seedB[tree]);
     ran1_init(s->rng);
-    s->nodeCount = 0; s->leafCount = 1; s->sp = 0; s->candCount = 0; s->algoBytes = 0; s->abort = 0;
+    s->nodeCount = 0; s->leafCount = 1; s->sp = 0; s->candCount = 0; s->algoBytes = 0; s->abort = 0; s->histDirty = 0;
   }
   for (int k = tid; k < 32; k += kThreads) {
     uint32_t msk = 0;
