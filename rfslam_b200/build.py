@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("RFSLAM_LIB", os.path.join(HERE, "librfslam_b200.so"))
-SOURCES = ["api.cu", "dataset.cu", "grow.cu", "predict.cu"]
+SOURCES = ["api.cu", "dataset.cu", "grow.cu", "predict.cu", "hostpool.cu"]
 HEADERS = ["common.cuh", "internal.h", "grow_kernel.cuh", os.path.join("..", "..", "include", "rfslam_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

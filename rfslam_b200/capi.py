@@ -69,7 +69,7 @@ SYMBOLS = [
     "rfslam_b200_dataset_destroy", "rfslam_b200_dataset_bytes", "rfslam_b200_predict", "rfslam_b200_free_predict",
     "rfslam_b200_rule_of_slot", "rfslam_b200_register_this", "rfslam_b200_register_defaults",
     "rfslam_b200_score_node", "rfslam_b200_bootstrap_counts", "rfslam_b200_last_error", "rfslam_b200_version",
-    "rfslam_b200_device_count", "rfslam_b200_last_profile",
+    "rfslam_b200_device_count", "rfslam_b200_last_profile", "rfslam_b200_free_array", "rfslam_b200_host_pool_trim",
 ]
 
 _lib = None
@@ -109,6 +109,8 @@ def lib():
         L.rfslam_b200_version.restype = C.c_char_p; L.rfslam_b200_version.argtypes = []
         L.rfslam_b200_device_count.restype = C.c_int; L.rfslam_b200_device_count.argtypes = []
         L.rfslam_b200_last_profile.restype = C.c_int; L.rfslam_b200_last_profile.argtypes = [C.POINTER(C.c_uint64), C.c_int]
+        L.rfslam_b200_free_array.restype = None; L.rfslam_b200_free_array.argtypes = [vp]
+        L.rfslam_b200_host_pool_trim.restype = None; L.rfslam_b200_host_pool_trim.argtypes = []
         _lib = L
     return _lib
 

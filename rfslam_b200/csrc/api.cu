@@ -94,12 +94,15 @@ int rfslam_b200_grow(const rfslam_grow_args* args, rfslam_forest_out* out) {
 
 void rfslam_b200_free_forest(rfslam_forest_out* o) {
   if (!o) return;
-  free(o->tree_ids); free(o->treeID); free(o->nodeID); free(o->parmID); free(o->contPT); free(o->mwcpSZ); free(o->splitStat);
-  free(o->leafCount); free(o->seed); free(o->tnRCNT); free(o->tnACNT); free(o->tnCLAS);
-  free(o->nodeMembership); free(o->bootMembership); free(o->rmbrMembership); free(o->ambrMembership);
-  free(o->oobEnsbCLS); free(o->allEnsbCLS); free(o->oobEnsbDen); free(o->allEnsbDen);
+  void* arrays[] = {o->tree_ids, o->treeID, o->nodeID, o->parmID, o->contPT, o->mwcpSZ, o->splitStat, o->leafCount, o->seed,
+                    o->tnRCNT, o->tnACNT, o->tnCLAS, o->nodeMembership, o->bootMembership, o->rmbrMembership, o->ambrMembership,
+                    o->oobEnsbCLS, o->allEnsbCLS, o->oobEnsbDen, o->allEnsbDen};
+  for (void* p : arrays) host_free(p);
   memset(o, 0, sizeof(*o));
 }
+
+void rfslam_b200_free_array(void* p) { host_free(p); }
+void rfslam_b200_host_pool_trim(void) { host_pool_trim(); }
 
 int rfslam_b200_predict(const rfslam_predict_args* args, rfslam_predict_out* out) {
   if (!args || !out) { set_error("null arguments"); return RFSLAM_EINVAL; }
@@ -108,7 +111,7 @@ int rfslam_b200_predict(const rfslam_predict_args* args, rfslam_predict_out* out
 
 void rfslam_b200_free_predict(rfslam_predict_out* o) {
   if (!o) return;
-  free(o->allEnsbCLS); free(o->allEnsbDen); free(o->nodeMembership);
+  host_free(o->allEnsbCLS); host_free(o->allEnsbDen); host_free(o->nodeMembership);
   memset(o, 0, sizeof(*o));
 }
 

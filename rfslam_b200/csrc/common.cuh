@@ -95,10 +95,12 @@ __host__ __device__ inline void ran1_init(Ran1& s) {
   }
 }
 
-// 16807^k mod (2^31 - 1), k = 1..16: the Park-Miller state k steps ahead is (kJump[k-1] * idum) mod M,
+// 16807^k mod (2^31 - 1), k = 1..32: the Park-Miller state k steps ahead is (kJump[k-1] * idum) mod M,
 // bit-identical to k Schrage steps (both are exact modular products)
-__device__ __constant__ const uint32_t kJump[16] = {16807u, 282475249u, 1622650073u, 984943658u, 1144108930u, 470211272u,
-  101027544u, 1457850878u, 1458777923u, 2007237709u, 823564440u, 1115438165u, 1784484492u, 74243042u, 114807987u, 1137522503u};
+__device__ __constant__ const uint32_t kJump[32] = {16807u, 282475249u, 1622650073u, 984943658u, 1144108930u, 470211272u,
+  101027544u, 1457850878u, 1458777923u, 2007237709u, 823564440u, 1115438165u, 1784484492u, 74243042u, 114807987u, 1137522503u,
+  1441282327u, 16531729u, 823378840u, 143542612u, 896544303u, 1474833169u, 1264817709u, 1998097157u, 1817129560u, 1131570933u,
+  197493099u, 1404280278u, 893351816u, 1505795335u, 1954899097u, 1636807826u};
 
 __host__ __device__ inline int ran1_mulmod(uint32_t a, uint32_t v) {
   unsigned long long p = (unsigned long long)a * (unsigned long long)v;

@@ -32,16 +32,33 @@ std::vector<unsigned long long> g_last_profile;
 
 namespace {
 
-// K1a: chain-A replay, one warp per tree with lane 0 walking the (inherently sequential)
-// Bays-Durham shuffle; trees run concurrently on different SMs.  draws are 0-based original rows.
+// K1a: chain-A replay (rf.c:492-627), one warp per tree, 32 draws per round.  The Park-Miller states of
+// a round come from jump-ahead (lane k: k + 1 steps); the Bays-Durham table lives in registers (lane j
+// holds iv[j]) so the inherently sequential shuffle walk is two warp shuffles per draw; the float ->
+// row index conversion and the stores are lane-parallel and coalesced.  draws are 0-based original rows.
 __global__ void bootstrap_draw_kernel(const int* seedA, const int* bootSize, uint32_t* draws, size_t stride, int n) {
   __shared__ Ran1 rng;
-  const int t = blockIdx.x;
-  if (threadIdx.x != 0) return;
-  ran1_seed(rng, seedA[t]);
+  const int t = blockIdx.x, lane = threadIdx.x;
+  if (lane == 0) { ran1_seed(rng, seedA[t]); ran1_init(rng); }
+  __syncwarp();
+  int ivReg = rng.iv[lane], iy = rng.iy, idum = rng.idum;
   uint32_t* out = draws + (size_t)t * stride;
   const int bs = bootSize[t];
-  for (int i = 0; i < bs; i++) out[i] = ran1_index(rng, (uint32_t)n) - 1u;     // rf.c:531
+  for (int base = 0; base < bs; base += 32) {
+    const int cnt = min(32, bs - base);
+    const int myIdum = ran1_mulmod(kJump[lane], (uint32_t)idum);
+    int myIy = 0;
+    for (int k = 0; k < cnt; k++) {
+      const int j = iy / 67108864;
+      const int idk = __shfl_sync(0xffffffffu, myIdum, k);
+      const int niy = __shfl_sync(0xffffffffu, ivReg, j);
+      if (lane == j) ivReg = idk;
+      iy = niy;
+      if (lane == k) myIy = niy;
+    }
+    idum = __shfl_sync(0xffffffffu, myIdum, cnt - 1);
+    if (lane < cnt) out[base + lane] = (uint32_t)ceil((double)ran1_float(myIy) * ((double)n * 1.0)) - 1u;     // rf.c:531
+  }
 }
 
 // K1b: in-bag multiplicity per INTERNAL row (u16 packed two per word, native 32-bit atomics)
@@ -199,7 +216,7 @@ struct DevBuf {
 
 template <typename T>
 T* host_copy(const T* dev, size_t count) {
-  T* h = (T*)malloc(std::max<size_t>(count, 1) * sizeof(T));
+  T* h = (T*)host_alloc(std::max<size_t>(count, 1) * sizeof(T));
   if (!h) { set_error("out of host memory"); throw CudaFail{RFSLAM_ENOMEM}; }
   if (count) RF_CUDA(cudaMemcpy(h, dev, count * sizeof(T), cudaMemcpyDeviceToHost));
   return h;
@@ -267,21 +284,22 @@ int validate_grow_args(const rfslam_grow_args* a, GrowConfig* cfg) {
 }
 
 namespace {
-// growable host array handed to the caller (malloc'd; the C-ABI frees it with free())
+// growable host array handed to the caller (pool block, see hostpool.cu; released by rfslam_b200_free_forest)
 template <typename T>
 struct HostOut {
   T* p = nullptr; size_t n = 0, cap = 0;
-  T* grow(size_t add) {
-    if (n + add > cap) {
-      cap = std::max<size_t>(n + add, cap * 2);
-      T* q = (T*)realloc(p, std::max<size_t>(cap, 1) * sizeof(T));
-      if (!q) { set_error("out of host memory"); throw CudaFail{RFSLAM_ENOMEM}; }
-      p = q;
-    }
-    T* at = p + n; n += add; return at;
+  void reserve(size_t want) {
+    if (want <= cap) return;
+    const size_t ncap = std::max<size_t>(want, cap * 2);
+    T* q = (T*)host_alloc(std::max<size_t>(ncap, 1) * sizeof(T));
+    if (!q) { set_error("out of host memory"); throw CudaFail{RFSLAM_ENOMEM}; }
+    if (n) memcpy(q, p, n * sizeof(T));
+    host_free(p);
+    p = q; cap = ncap;
   }
-  T* release() { if (!p) p = (T*)malloc(sizeof(T)); T* q = p; p = nullptr; return q; }
-  ~HostOut() { free(p); }
+  T* grow(size_t add) { reserve(n + add); T* at = p + n; n += add; return at; }
+  T* release() { if (!p) p = (T*)host_alloc(sizeof(T)); T* q = p; p = nullptr; return q; }
+  ~HostOut() { host_free(p); }
 };
 }  // namespace
 
@@ -568,12 +586,12 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     // ---- hand over ----
     out->ntree = T; out->n = n;
     out->total_nodes = (int64_t)h_treeID.n; out->total_leaves = (int64_t)h_tnRCNT.n;
-    out->tree_ids = (int32_t*)malloc((size_t)T * 4); memcpy(out->tree_ids, ids.data(), (size_t)T * 4);
-    out->mwcpSZ = (int32_t*)calloc(std::max<size_t>(h_treeID.n, 1), 4);
+    out->tree_ids = (int32_t*)host_alloc((size_t)T * 4); memcpy(out->tree_ids, ids.data(), (size_t)T * 4);
+    out->mwcpSZ = (int32_t*)host_calloc(std::max<size_t>(h_treeID.n, 1) * 4);
     out->treeID = h_treeID.release(); out->nodeID = h_nodeID.release(); out->parmID = h_parmID.release();
     out->contPT = h_contPT.release(); out->splitStat = wantStat ? h_stat.release() : nullptr;
-    out->leafCount = (int32_t*)malloc((size_t)T * 4); memcpy(out->leafCount, h_leafCount.data(), (size_t)T * 4);
-    out->seed = (int32_t*)malloc((size_t)T * 4); memcpy(out->seed, h_seed.data(), (size_t)T * 4);
+    out->leafCount = (int32_t*)host_alloc((size_t)T * 4); memcpy(out->leafCount, h_leafCount.data(), (size_t)T * 4);
+    out->seed = (int32_t*)host_alloc((size_t)T * 4); memcpy(out->seed, h_seed.data(), (size_t)T * 4);
     out->tnRCNT = h_tnRCNT.release(); out->tnACNT = h_tnACNT.release(); out->tnCLAS = h_tnCLAS.release();
     out->oobEnsbCLS = host_copy(d_oobNum.p, 2 * (size_t)n); out->allEnsbCLS = host_copy(d_allNum.p, 2 * (size_t)n);
     out->oobEnsbDen = host_copy(d_oobDen.p, (size_t)n); out->allEnsbDen = host_copy(d_allDen.p, (size_t)n);

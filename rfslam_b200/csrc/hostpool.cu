@@ -1,0 +1,90 @@
+// hostpool.cu -- page-locked, recycled host memory for the arrays the C-ABI hands to the caller.
+//
+// A 500-tree forest on 1M rows is ~1 GB of records (randomForestSRC.c:9-79 lists them).  Fresh
+// malloc'd pages cost a page fault + kernel zeroing per 4 KB and pageable device-to-host copies are
+// staged through the driver's bounce buffers; together that was ~0.4 s per rfslam_b200_grow call,
+// a fifth of the step.  Blocks come from cudaHostAlloc instead and go back to a free list when the
+// caller releases the forest (rfslam_b200_free_forest / rfslam_b200_free_array), so a second call
+// of similar size touches no new pages and its copies run at PCIe speed, asynchronously.
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include "common.cuh"
+#include "internal.h"
+
+namespace rfslam {
+namespace {
+std::mutex g_mu;
+std::unordered_map<void*, size_t> g_owned;          // every live pool block (handed out or idle) -> capacity
+std::multimap<size_t, void*> g_idle;                // capacity -> idle block
+size_t g_idleBytes = 0;
+
+constexpr size_t kSmall = 1u << 16;                 // below this plain malloc is used (free() releases it)
+
+size_t idle_cap() {
+  static size_t cap = [] {
+    const char* e = getenv("RFSLAM_HOST_POOL_MB");
+    return (size_t)(e ? atoll(e) : 8192) << 20;
+  }();
+  return cap;
+}
+
+size_t round_cap(size_t bytes) {                    // eighth-of-an-octave size classes, 2 MB granularity
+  size_t p2 = 1; while ((p2 << 1) <= bytes) p2 <<= 1;
+  size_t step = std::max<size_t>(p2 >> 3, (size_t)2 << 20);
+  return (bytes + step - 1) / step * step;
+}
+}  // namespace
+
+void* host_alloc(size_t bytes) {
+  if (bytes < kSmall) return malloc(std::max<size_t>(bytes, 1));
+  const size_t cap = round_cap(bytes);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_idle.lower_bound(cap);
+    if (it != g_idle.end() && it->first < 2 * cap) {
+      void* p = it->second; g_idleBytes -= it->first; g_idle.erase(it);
+      return p;
+    }
+  }
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();                              // not page-lockable right now: pageable memory still works
+    return malloc(bytes);
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_owned[p] = cap;
+  return p;
+}
+
+void* host_calloc(size_t bytes) {
+  void* p = host_alloc(bytes);
+  if (p) memset(p, 0, bytes);
+  return p;
+}
+
+void host_free(void* p) {
+  if (!p) return;
+  size_t cap = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_owned.find(p);
+    if (it == g_owned.end()) { cap = 0; }
+    else {
+      cap = it->second;
+      if (g_idleBytes + cap <= idle_cap()) { g_idle.emplace(cap, p); g_idleBytes += cap; return; }
+      g_owned.erase(it);
+    }
+  }
+  if (cap) cudaFreeHost(p); else free(p);
+}
+
+void host_pool_trim() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& kv : g_idle) { g_owned.erase(kv.second); cudaFreeHost(kv.second); }
+  g_idle.clear(); g_idleBytes = 0;
+}
+
+}  // namespace rfslam

@@ -102,4 +102,10 @@ int  bootstrap_counts_impl(int seed, int ntree, int n, int tree, int32_t* counts
 int  validate_grow_args(const rfslam_grow_args* a, GrowConfig* cfg);
 void chain_seeds(int seed, int ntree, std::vector<int>& seedA, std::vector<int>& seedB);
 
+// hostpool.cu: recycled page-locked memory for the arrays handed to the caller
+void* host_alloc(size_t bytes);
+void* host_calloc(size_t bytes);
+void  host_free(void* p);      // pool blocks return to the pool, anything else goes to free()
+void  host_pool_trim();
+
 }  // namespace rfslam

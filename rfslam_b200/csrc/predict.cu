@@ -113,12 +113,12 @@ int predict_forest(const rfslam_predict_args* a, rfslam_predict_out* out) {
     RF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     out->m = m; out->ntree = ntree; out->kernel_ms = ms;
-    out->allEnsbCLS = (double*)malloc((size_t)2 * m * 8);
-    out->allEnsbDen = (uint32_t*)malloc((size_t)m * 4);
+    out->allEnsbCLS = (double*)host_alloc((size_t)2 * m * 8);
+    out->allEnsbDen = (uint32_t*)host_alloc((size_t)m * 4);
     RF_CUDA(cudaMemcpy(out->allEnsbCLS, b_ens.p, (size_t)2 * m * 8, cudaMemcpyDeviceToHost));
     RF_CUDA(cudaMemcpy(out->allEnsbDen, b_den.p, (size_t)m * 4, cudaMemcpyDeviceToHost));
     if (a->want_membership) {
-      out->nodeMembership = (int32_t*)malloc((size_t)ntree * m * 4);
+      out->nodeMembership = (int32_t*)host_alloc((size_t)ntree * m * 4);
       RF_CUDA(cudaMemcpy(out->nodeMembership, b_memb.p, (size_t)ntree * m * 4, cudaMemcpyDeviceToHost));
     }
   } catch (CudaFail f) {

@@ -29,9 +29,6 @@ def _ip(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(_pi)
 
 
-_libc = C.CDLL(None)
-_libc.free.argtypes = [C.c_void_p]
-_libc.free.restype = None
 
 
 def _take(ptr, count, dtype):
@@ -41,8 +38,9 @@ def _take(ptr, count, dtype):
 
 
 def _own(struct, field, count, dtype):
-    """Adopt a callee-malloc'd output array without copying: the struct's pointer is cleared (so
-    rfslam_b200_free_* skips it) and free() runs when the numpy array is collected."""
+    """Adopt a callee-owned output array without copying: the struct's pointer is cleared (so
+    rfslam_b200_free_* skips it) and rfslam_b200_free_array returns the block to the library's
+    page-locked pool when the numpy array is collected."""
     ptr = getattr(struct, field)
     if not ptr:
         return None
@@ -52,7 +50,7 @@ def _own(struct, field, count, dtype):
     arr = np.ctypeslib.as_array(ptr, shape=(count,))
     assert arr.dtype == np.dtype(dtype), (field, arr.dtype, dtype)
     setattr(struct, field, type(ptr)())
-    weakref.finalize(arr, _libc.free, addr)
+    weakref.finalize(arr, capi.lib().rfslam_b200_free_array, addr)
     return arr
 
 
