@@ -142,7 +142,8 @@ int  rfslam_b200_grow(const rfslam_grow_args *args, rfslam_forest_out *out);
 void rfslam_b200_free_forest(rfslam_forest_out *out);
 /* Output arrays are page-locked blocks recycled across calls (the R stub copies them into R vectors and
    frees the struct; a binding that adopts single arrays instead releases each with free_array, never
-   with free()).  host_pool_trim returns the idle blocks to the OS (cap: RFSLAM_HOST_POOL_MB, default 8192). */
+   with free()).  host_pool_trim returns the idle blocks to the OS (cap: RFSLAM_HOST_POOL_MB, default 8192) and
+   frees the device scratch rfslam_b200_grow keeps between calls. */
 void rfslam_b200_free_array(void *array);
 void rfslam_b200_host_pool_trim(void);
 

@@ -1,4 +1,7 @@
 // api.cu -- the extern "C" surface declared in include/rfslam_b200.h.
+#include <chrono>
+#include <map>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -35,6 +38,9 @@ static void ensure_defaults() {
 }  // namespace rfslam
 
 using namespace rfslam;
+
+static std::mutex g_scratchMu;
+static std::map<int, WsPool> g_scratch;      // per device: idle scratch blocks kept between rfslam_b200_grow calls
 
 extern "C" {
 
@@ -84,11 +90,30 @@ int rfslam_b200_grow(const rfslam_grow_args* args, rfslam_forest_out* out) {
   GrowConfig cfg;
   int rc = validate_grow_args(args, &cfg);
   if (rc) return rc;
+  const bool timing = getenv("RFSLAM_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   rfslam_dataset* ds = nullptr;
   rc = dataset_build(args, &ds);
   if (rc) return rc;
+  {   // device scratch of the previous call on this device (several GB of entry lists and stacks):
+      // cudaMalloc / cudaFree of it cost up to 0.6 s per call
+    std::lock_guard<std::mutex> lk(g_scratchMu);
+    auto& cache = g_scratch[ds->device];
+    for (auto& b : cache.blks) ds->pool.blks.push_back(b);
+    cache.blks.clear();
+  }
+  const double t1 = now();
   rc = grow_forest(ds, args, out);
+  const double t2 = now();
+  {
+    std::lock_guard<std::mutex> lk(g_scratchMu);
+    auto& cache = g_scratch[ds->device];
+    for (auto& b : ds->pool.blks) { b.used = false; cache.blks.push_back(b); }
+    ds->pool.blks.clear();
+  }
   dataset_free(ds);
+  if (timing) fprintf(stderr, "[rfslam_b200_grow] dataset %.1f ms, grow %.1f ms, release %.1f ms\n", t1 - t0, t2 - t1, now() - t2);
   return rc;
 }
 
@@ -102,7 +127,11 @@ void rfslam_b200_free_forest(rfslam_forest_out* o) {
 }
 
 void rfslam_b200_free_array(void* p) { host_free(p); }
-void rfslam_b200_host_pool_trim(void) { host_pool_trim(); }
+void rfslam_b200_host_pool_trim(void) {
+  host_pool_trim();
+  std::lock_guard<std::mutex> lk(g_scratchMu);
+  for (auto& kv : g_scratch) { cudaSetDevice(kv.first); kv.second.release_all(); }
+}
 
 int rfslam_b200_predict(const rfslam_predict_args* args, rfslam_predict_out* out) {
   if (!args || !out) { set_error("null arguments"); return RFSLAM_EINVAL; }
