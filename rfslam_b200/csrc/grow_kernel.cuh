@@ -168,6 +168,9 @@ struct GrowSmem {
 #ifndef RF_MAX_SLOTS
 #define RF_MAX_SLOTS 4
 #endif
+#ifndef RF_ROWS_MAXSEG
+#define RF_ROWS_MAXSEG 64   // small nodes: longest event stratum for which the lane = row evaluation is used
+#endif
 __host__ __device__ inline int hist_slots(int hb) { int g = 256 / hb; return g < 1 ? 1 : (g > RF_MAX_SLOTS ? RF_MAX_SLOTS : g); }
 
 __host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K, int hb) {
@@ -734,85 +737,77 @@ __device__ inline void sort_candidate(const NodeCtx& c, int ci, uint32_t len) {
 // ---- small nodes (<= kSmallMax entries, histogram candidates only) ---------------------------
 // The node is staged in shared memory once -- per entry a 16-byte record (multiplicity * risk time,
 // multiplicity, event, stratum) and one code byte per candidate -- with every gather of an entry in
-// flight together.  Then warp ci scores candidate ci on its own: LANE = CUT (code lane and lane + 32
-// of the current 64-code window), and the warp streams the node's records in list order, which is
-// stratum-major.  Every lane keeps the left sums of its own cut; when the stratum changes the rule's
-// terms of the finished stratum are added (strata without events contribute exactly 0 to every rule,
-// see side_term, and are skipped).  This is the same sum the histogram + prefix-scan + fill-forward
-// of the large-node path produces, with no atomics, no per-stratum synchronisation and a loop body of
-// a few dozen instructions -- the kernel is instruction-fetch bound on its once-per-node code
-// (stall_no_instruction was the top stall at two CTAs per SM), so small code is the optimisation.
-__device__ inline void small_candidate(const NodeCtx& c, int ci, uint32_t len) {
+// flight together.  Then warp ci scores candidate ci on its own, with warp-level synchronisation only
+// and no atomics, visiting just the strata that contain events in this node (every other cell
+// contributes exactly 0 to every rule, see side_term; their rows matter only for which cuts exist).
+// The kernel was instruction-fetch bound on its once-per-node code (stall_no_instruction was the top
+// stall at two CTAs per SM) and, inside this function, bound by the FP64 divide + log of the rule
+// terms, so it is organised to be small and to evaluate as few terms as possible:
+//
+//  * short strata (<= RF_ROWS_MAXSEG rows, the usual case under the stratified rules): LANE = ROW.
+//    A stratum's terms only change at the codes of its own rows, so they are evaluated once per row of
+//    an event stratum (32 rows per batch, two term evaluations for the whole batch), written to a
+//    per-stratum table, and each cut then adds, stratum by stratum, the entry of the largest code <=
+//    the cut (fill-forward by bit search).  Rows holding their stratum's largest code have "left =
+//    everything": their left term IS the stratum's parent term.  Tables live in this candidate's
+//    slice of the (idle) large-node histograms, G = hs strata per group.
+//  * long strata: LANE = CUT.  The warp streams the stratum's records, every lane keeps the left sums
+//    of its own cut(s) of the current 64-code window, three to five terms per stratum and window.
+//
+// Either way a cut's left / right statistics are the sums over strata in ascending order, exactly
+// what the histogram + prefix-scan + fill-forward of the large-node path produces.
+template <bool TWO>
+__device__ __forceinline__ void stream_rows(const SmallRec* __restrict__ rec, const uint8_t* __restrict__ cptr, uint32_t r0, uint32_t r1,
+                                            bool unit, uint32_t b0, uint32_t b1, uint32_t& TN, uint32_t& TE, double& TT, double& TW,
+                                            uint32_t& LN0, uint32_t& LE0, double& LT0, double& LW0,
+                                            uint32_t& LN1, uint32_t& LE1, double& LT1, double& LW1) {
+#pragma unroll 4
+  for (uint32_t i = r0; i < r1; i++) {
+    const SmallRec r = rec[i];
+    const uint32_t code = cptr[i];
+    const uint32_t mu = r.mult;
+    const double ft = unit ? (double)mu : r.mrt;
+    const bool ev = (r.es & 1u) != 0u;
+    const uint32_t me = ev ? mu : 0u; const double fe = ev ? ft : 0.0;
+    TN += mu; TT += ft; TE += me; TW += fe;
+    const bool l0 = code <= b0;
+    LN0 += l0 ? mu : 0u; LT0 += l0 ? ft : 0.0; LE0 += l0 ? me : 0u; LW0 += l0 ? fe : 0.0;
+    if (TWO) {
+      const bool l1 = code <= b1;
+      LN1 += l1 ? mu : 0u; LT1 += l1 ? ft : 0.0; LE1 += l1 ? me : 0u; LW1 += l1 ? fe : 0.0;
+    }
+  }
+}
+
+// one long stratum, lane = cut; adds its terms to sL / sR and returns its parent term
+__device__ inline double stream_stratum(const NodeCtx& c, int ci, int Dc, uint32_t r0, uint32_t r1) {
   GrowSmem& m = c.m;
-  GrowShared* s = m.s;
   const int lane = lane_id();
-  const int Dc = s->candD[ci];
   const SmallRec* __restrict__ rec = m.smRec;
   const uint8_t* __restrict__ cptr = m.smCodes + ci * kSmallMax;
-  const int nw = (c.Kloop + 31) >> 5;
-  double statP = 0.0;
-  if (lane < 8) m.pres[ci * 8 + lane] = 0u;
-  __syncwarp();
+  double tP = 0.0;
+#pragma unroll 1
   for (int base = 0; base < Dc; base += 64) {
     const uint32_t b0 = (uint32_t)(base + lane), b1 = b0 + 32u;
     const bool two = Dc > base + 32;
-    double accL0 = 0.0, accR0 = 0.0, accL1 = 0.0, accR1 = 0.0;
-    statP = 0.0;
-    {                                                              // which codes of this window occur in the node (the cuts that exist)
-      uint32_t plo = 0u, phi = 0u;
-      for (uint32_t i = (uint32_t)lane; i < len; i += 32u) {
-        const uint32_t rel = (uint32_t)cptr[i] - (uint32_t)base;
-        if (rel < 32u) plo |= 1u << rel; else if (rel < 64u) phi |= 1u << (rel - 32u);
-      }
-      plo = __reduce_or_sync(0xffffffffu, plo); phi = __reduce_or_sync(0xffffffffu, phi);
-      if (lane == 0) { m.pres[ci * 8 + (base >> 5)] = plo; if (two) m.pres[ci * 8 + (base >> 5) + 1] = phi; }
+    uint32_t TN = 0, TE = 0, LN0 = 0, LE0 = 0, LN1 = 0, LE1 = 0;
+    double TT = 0.0, TW = 0.0, LT0 = 0.0, LW0 = 0.0, LT1 = 0.0, LW1 = 0.0;
+    if (two) stream_rows<true>(rec, cptr, r0, r1, c.unit, b0, b1, TN, TE, TT, TW, LN0, LE0, LT0, LW0, LN1, LE1, LT1, LW1);
+    else stream_rows<false>(rec, cptr, r0, r1, c.unit, b0, b1, TN, TE, TT, TW, LN0, LE0, LT0, LW0, LN1, LE1, LT1, LW1);
+    if (base == 0) tP = side_term_nb(c.bayes, (double)TE, (double)TN, TT, TW, c.g.alpha, c.beta);
+    const double tL0 = side_term_nb(c.bayes, (double)LE0, (double)LN0, LT0, LW0, c.g.alpha, c.beta);
+    const double tR0 = side_term_nb(c.bayes, (double)(TE - LE0), (double)(TN - LN0), TT - LT0, TW - LW0, c.g.alpha, c.beta);
+    if (b0 < (uint32_t)Dc) { m.sL[ci * m.hb + b0] += tL0; m.sR[ci * m.hb + b0] += tR0; }
+    if (two) {
+      const double tL1 = side_term_nb(c.bayes, (double)LE1, (double)LN1, LT1, LW1, c.g.alpha, c.beta);
+      const double tR1 = side_term_nb(c.bayes, (double)(TE - LE1), (double)(TN - LN1), TT - LT1, TW - LW1, c.g.alpha, c.beta);
+      if (b1 < (uint32_t)Dc) { m.sL[ci * m.hb + b1] += tL1; m.sR[ci * m.hb + b1] += tR1; }
     }
-    for (int w8 = 0; w8 < nw; w8++) {
-      uint32_t word = s->evMask[w8];
-      while (word) {                                               // strata with events, ascending (warp-uniform)
-        const int sidx = (w8 << 5) + __ffs(word) - 1;
-        word &= word - 1u;
-        const uint32_t r0 = m.segpos[sidx], r1 = m.cN[sidx];
-        uint32_t TN = 0, TE = 0, LN0 = 0, LE0 = 0, LN1 = 0, LE1 = 0;
-        double TT = 0.0, TW = 0.0, LT0 = 0.0, LW0 = 0.0, LT1 = 0.0, LW1 = 0.0;
-#pragma unroll 4
-        for (uint32_t i = r0; i < r1; i++) {
-          const SmallRec r = rec[i];
-          const uint32_t code = cptr[i];
-          const uint32_t mu = r.mult;
-          const double ft = c.unit ? (double)mu : r.mrt;
-          const bool ev = (r.es & 1u) != 0u;
-          const bool l0 = code <= b0, l1 = code <= b1;
-          const uint32_t me = ev ? mu : 0u; const double fe = ev ? ft : 0.0;
-          TN += mu; TT += ft; TE += me; TW += fe;
-          LN0 += l0 ? mu : 0u; LT0 += l0 ? ft : 0.0; LE0 += l0 ? me : 0u; LW0 += l0 ? fe : 0.0;
-          LN1 += l1 ? mu : 0u; LT1 += l1 ? ft : 0.0; LE1 += l1 ? me : 0u; LW1 += l1 ? fe : 0.0;
-        }
-        statP += side_term_nb(c.bayes, (double)TE, (double)TN, TT, TW, c.g.alpha, c.beta);
-        accL0 += side_term_nb(c.bayes, (double)LE0, (double)LN0, LT0, LW0, c.g.alpha, c.beta);
-        accR0 += side_term_nb(c.bayes, (double)(TE - LE0), (double)(TN - LN0), TT - LT0, TW - LW0, c.g.alpha, c.beta);
-        if (two) {
-          accL1 += side_term_nb(c.bayes, (double)LE1, (double)LN1, LT1, LW1, c.g.alpha, c.beta);
-          accR1 += side_term_nb(c.bayes, (double)(TE - LE1), (double)(TN - LN1), TT - LT1, TW - LW1, c.g.alpha, c.beta);
-        }
-      }
-    }
-    if (b0 < (uint32_t)Dc) { m.sL[ci * m.hb + b0] = accL0; m.sR[ci * m.hb + b0] = accR0; }
-    if (b1 < (uint32_t)Dc) { m.sL[ci * m.hb + b1] = accL1; m.sR[ci * m.hb + b1] = accR1; }
   }
-  if (lane == 0) m.statP[ci] = statP;
-  __syncwarp();
+  return tP;
 }
 
-// LANE = ROW variant for nodes whose event strata are all short (<= 32 rows each; the usual case under
-// the stratified rules).  The FP64 divide + log of the rule terms is what the candidate warps contend
-// for, and a stratum's terms only change at the codes of its own rows: so the terms are evaluated once
-// per ROW of an event stratum (32 rows per batch: two term evaluations for the whole batch, against
-// three to five per stratum with lane = cut), written to a per-stratum table, and each cut then adds,
-// stratum by stratum, the entry of the largest code <= the cut (fill-forward by bit search).  The
-// rows holding their stratum's largest code have "left = everything", i.e. their left term IS the
-// stratum's parent term.  Tables live in this candidate's slice of the (idle) large-node histograms.
-__device__ inline void small_candidate_rows(const NodeCtx& c, int ci, uint32_t len) {
+__device__ inline void small_candidate(const NodeCtx& c, int ci, uint32_t len) {
   GrowSmem& m = c.m;
   GrowShared* s = m.s;
   const int lane = lane_id();
@@ -840,24 +835,28 @@ __device__ inline void small_candidate_rows(const NodeCtx& c, int ci, uint32_t l
   }
   double statP = 0.0;
   int w8 = 0; uint32_t word = s->evMask[0];
+  uint32_t bigR0 = 0u, bigR1 = 0u;                                 // a long stratum met while collecting a group: handled after it
 #pragma unroll 1
   while (true) {
-    // next group of up to G strata with events, ascending
+    // next group: up to G short strata with events, ascending; a long stratum ends the group
     uint32_t r0[RF_MAX_SLOTS], r1[RF_MAX_SLOTS]; double tP[RF_MAX_SLOTS];
     int ng = 0;
 #pragma unroll
     for (int q = 0; q < RF_MAX_SLOTS; q++) {
       r0[q] = 0u; r1[q] = 0u; tP[q] = 0.0;
-      if (q < G) {
+      if (q < G && bigR1 == 0u) {
         while (!word && ++w8 < nw) word = s->evMask[w8];
         if (word) {
           const int sidx = (w8 << 5) + __ffs(word) - 1;
           word &= word - 1u;
-          r0[q] = m.segpos[sidx]; r1[q] = m.cN[sidx]; ng = q + 1;
+          const uint32_t a0 = m.segpos[sidx], a1 = m.cN[sidx];
+          if (a1 - a0 > (uint32_t)RF_ROWS_MAXSEG) { bigR0 = a0; bigR1 = a1; }
+          else { r0[q] = a0; r1[q] = a1; ng = q + 1; }
         }
       }
     }
-    if (ng == 0) break;
+    if (ng == 0 && bigR1 == 0u) break;
+    if (ng > 0) {
     if (lane < G * 8) mk[lane] = 0u;
     __syncwarp();
     uint32_t R = 0;
@@ -876,7 +875,7 @@ __device__ inline void small_candidate_rows(const NodeCtx& c, int ci, uint32_t l
       const uint32_t myCode = (myG >= 0) ? (uint32_t)cptr[myJ] : 0u;
       uint32_t TN = 0, TE = 0, LN = 0, LE = 0;
       double TT = 0.0, TW = 0.0, LT = 0.0, LW = 0.0;
-      for (uint32_t k = lo; k < hi; k++) {                          // my stratum's rows (<= 32)
+      for (uint32_t k = lo; k < hi; k++) {                          // my stratum's rows
         const SmallRec r = rec[k];
         const uint32_t mu = r.mult;
         const double ft = c.unit ? (double)mu : r.mrt;
@@ -923,6 +922,12 @@ __device__ inline void small_candidate_rows(const NodeCtx& c, int ci, uint32_t l
 #pragma unroll
     for (int q = 0; q < RF_MAX_SLOTS; q++) if (q < ng) statP += tP[q];
     __syncwarp();
+    }
+    if (bigR1 != 0u) {
+      statP += stream_stratum(c, ci, Dc, bigR0, bigR1);
+      bigR0 = 0u; bigR1 = 0u;
+      __syncwarp();
+    }
   }
   if (lane == 0) m.statP[ci] = statP;
   __syncwarp();
@@ -978,18 +983,8 @@ __device__ inline void score_small(NodeCtx& c) {
   }
   __syncthreads();
   RF_PROF(3);
-  // longest event stratum of the node decides the evaluation scheme (warp-uniform, same for every warp)
-  uint32_t maxSeg = 0;
-  for (int w8 = 0; w8 < ((c.Kloop + 31) >> 5); w8++) {
-    uint32_t word = s->evMask[w8];
-    while (word) { const int sidx = (w8 << 5) + __ffs(word) - 1; word &= word - 1u; maxSeg = max(maxSeg, m.cN[sidx] - m.segpos[sidx]); }
-  }
-  if (maxSeg <= 32u) {
-    if (tid == 0) s->histDirty = 1;                                  // the tables live in the large-node histograms
-    for (int ci = wid; ci < nc; ci += kWarps) small_candidate_rows(c, ci, len);
-  } else {
-    for (int ci = wid; ci < nc; ci += kWarps) small_candidate(c, ci, len);   // the same warp summarises ci next (score_node)
-  }
+  if (tid == 0) s->histDirty = 1;                                    // the candidates keep tables in the large-node histograms
+  for (int ci = wid; ci < nc; ci += kWarps) small_candidate(c, ci, len);   // the same warp summarises ci next (score_node)
 }
 
 // ---- score all drawn candidates of the current node (steps 2-4) ------------------------------
