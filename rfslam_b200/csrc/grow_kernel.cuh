@@ -941,10 +941,6 @@ __device__ inline void score_small(NodeCtx& c) {
   const uint32_t len = s->cur.len;
   const DevData& d = c.d;
   const GrowWork& w = c.w;
-  if (tid < 8) s->evMask[tid] = 0u;
-  if (tid == 0) { s->have = 0; s->bestDelta = 0.0; s->bestCand = -1; s->bestCode = 0; s->cutsSeen = 0; }
-  __syncthreads();
-  RF_PROF(2);
   // stage: one thread per entry, all of an entry's gathers issued before the first shared-memory store
   for (uint32_t j0 = (uint32_t)(tid - lane); j0 < len; j0 += kThreads) {
     const uint32_t j = j0 + lane;
@@ -1262,63 +1258,68 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     // so "variance > EPSILON" is the integer test 0 < E < m
     if (attempt) attempt = cur.E > 0u && cur.E < cur.m;
     if (w.sinkDelta) attempt = true;                       // single-node scoring mode: no gate
-    if (tid == 0) { s->nc = 0; s->have = 0; }
-    __syncthreads();
-    if (attempt) {
-      if (warp_id() == 0) {                                // permissible covariates, ascending, by ballot compaction
+    // One serial section per node, run by warp 0 between two block barriers: tracker reset, the draws
+    // and the candidate metadata (a barrier + phase boundary costs ~1k cycles on a node that has a few
+    // dozen rows; there used to be five of them before the first gather).
+    if (warp_id() == 0) {
+      const int lane = lane_id();
+      if (lane == 0) { s->nc = 0; s->have = 0; s->isSmall = 0; s->bestDelta = 0.0; s->bestCand = -1; s->bestCode = 0; s->cutsSeen = 0; }
+      if (lane < 8) s->evMask[lane] = 0u;
+      __syncwarp();
+      if (attempt) {                                       // permissible covariates, ascending, by ballot compaction
         int size = 0;
 #pragma unroll 1
         for (int base = 0; base < d.p; base += 32) {
-          const int k = base + lane_id();
-          const bool ok = k < d.p && ((s->perm[base >> 5] >> lane_id()) & 1u);
+          const int k = base + lane;
+          const bool ok = k < d.p && ((s->perm[base >> 5] >> lane) & 1u);
           const unsigned bm = __ballot_sync(0xffffffffu, ok);
-          if (ok) m.pool[size + __popc(bm & ((1u << lane_id()) - 1u))] = (uint16_t)k;
+          if (ok) m.pool[size + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)k;
           size += __popc(bm);
         }
-        if (lane_id() == 0) s->poolSize = size;
+        if (lane == 0) s->poolSize = size;
         __syncwarp();
         draw_candidates(d, g, s, m);
-        if (lane_id() == 0) s->algoBytes += (unsigned long long)cur.m * (12ull * (unsigned long long)s->nc + 20ull);
+        __syncwarp();
+        const int ncd = s->nc;
+        if (lane == 0) s->algoBytes += (unsigned long long)cur.m * (12ull * (unsigned long long)ncd + 20ull);
+        if (lane < ncd) {                                  // candidate metadata: one parallel round of loads
+          const int cov = s->candCov[lane];
+          const int Dv = d.D[cov];
+          s->candD[lane] = Dv; s->candW[lane] = d.width[cov]; s->candPtr[lane] = d.codes[cov]; s->candHist[lane] = Dv <= kHistBins;
+        }
       }
-      __syncthreads();
-      if (tid < s->nc) {                                   // candidate metadata: one parallel round of loads
-        const int cov = s->candCov[tid];
-        const int Dv = d.D[cov];
-        s->candD[tid] = Dv; s->candW[tid] = d.width[cov]; s->candPtr[tid] = d.codes[cov]; s->candHist[tid] = Dv <= kHistBins;
-      }
-      if (tid == 0) s->isSmall = 0;
-      __syncthreads();
-      RF_PROF(1);
-      if (s->nc > 0) score_node(d, g, w, m, tree);
     }
     __syncthreads();
+    RF_PROF(1);
+    if (attempt && s->nc > 0) score_node(d, g, w, m, tree);   // ends with a block barrier
     if (w.sinkDelta) {                                     // emit-only mode stops after the root
       if (tid == 0) *w.sinkCount = s->cutsSeen;
       break;
     }
     const bool split = attempt && s->have;
     if (!split) {
-      if (tid == 0) {
-        uint32_t q;
-        append_record(w, s, tree, cur.nodeID, 0u, cur.E, cur.m, nan(""), cur.parentRec, &q);
-        if (!s->abort) {
-          if (s->sp == 0) {
-            s->abort = 2;                                   // finished
-          } else {
-            s->sp--;
-            s->cur = w.stack[(size_t)tree * kStackCap + s->sp];
+      if (warp_id() == 0) {
+        if (lane_id() == 0) {
+          uint32_t q;
+          append_record(w, s, tree, cur.nodeID, 0u, cur.E, cur.m, nan(""), cur.parentRec, &q);
+          if (!s->abort) {
+            if (s->sp == 0) {
+              s->abort = 2;                                 // finished
+            } else {
+              s->sp--;
+              s->cur = w.stack[(size_t)tree * kStackCap + s->sp];
+            }
           }
         }
-      }
-      __syncthreads();
-      RF_PROF(10);
-      if (s->abort == 2) break;
-      if (!s->abort) {
-        const uint32_t* sp = w.stackPerm + ((size_t)tree * kStackCap + s->sp) * g.pw;
+        __syncwarp();
+        if (!s->abort) {
+          const uint32_t* sp = w.stackPerm + ((size_t)tree * kStackCap + s->sp) * g.pw;
 #pragma unroll 1
-        for (int k = tid; k < g.pw; k += kThreads) s->perm[k] = sp[k];
+          for (int k = lane_id(); k < g.pw; k += 32) s->perm[k] = sp[k];
+        }
       }
-      continue;
+      RF_PROF(10);
+      continue;                                             // the loop-top barrier publishes cur / perm / abort
     }
 
     // ---- split: record, partition, push right, descend left ----
@@ -1365,7 +1366,6 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
           else dst[nL + (i - before)] = en[u];
         }
       }
-      __syncthreads();
     } else {
     // Four consecutive entries per thread in both passes: the four list loads, then the four
     // dependent code gathers, are in flight together (the kernel is latency-bound, not HBM-bound).
@@ -1427,34 +1427,36 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     }
     }
     RF_PROF(9);
-    if (tid == 0) {
-      uint32_t q;
-      append_record(w, s, tree, cur.nodeID, (uint32_t)cov + 1u, bcode, kNone, s->bestDelta, cur.parentRec, &q);
-      s->algoBytes += 16ull * (unsigned long long)cur.m;
-      if (!s->abort) {
-        if (s->sp >= (uint32_t)kStackCap) { atomicExch(w.status, 2); s->abort = 1; }
-        else {
-          s->leafCount++;
-          NodeEnt r;
-          r.start = cur.start + nL; r.len = cur.len - nL;
-          r.m = cur.m - (uint32_t)(tneL >> 32); r.E = cur.E - (uint32_t)(tneL & 0xffffffffu);
-          r.rtsum = trtR; r.nodeID = s->leafCount; r.parentRec = q; r.depth = cur.depth + 1; r.buf = cur.buf ^ 1u;
-          w.stack[(size_t)tree * kStackCap + s->sp] = r;
-          NodeEnt l;
-          l.start = cur.start; l.len = nL; l.m = (uint32_t)(tneL >> 32); l.E = (uint32_t)(tneL & 0xffffffffu);
-          l.rtsum = trtL; l.nodeID = cur.nodeID; l.parentRec = kNone; l.depth = cur.depth + 1; l.buf = cur.buf ^ 1u;
-          s->cur = l;
+    if (warp_id() == 0) {
+      if (lane_id() == 0) {
+        uint32_t q;
+        append_record(w, s, tree, cur.nodeID, (uint32_t)cov + 1u, bcode, kNone, s->bestDelta, cur.parentRec, &q);
+        s->algoBytes += 16ull * (unsigned long long)cur.m;
+        if (!s->abort) {
+          if (s->sp >= (uint32_t)kStackCap) { atomicExch(w.status, 2); s->abort = 1; }
+          else {
+            s->leafCount++;
+            NodeEnt r;
+            r.start = cur.start + nL; r.len = cur.len - nL;
+            r.m = cur.m - (uint32_t)(tneL >> 32); r.E = cur.E - (uint32_t)(tneL & 0xffffffffu);
+            r.rtsum = trtR; r.nodeID = s->leafCount; r.parentRec = q; r.depth = cur.depth + 1; r.buf = cur.buf ^ 1u;
+            w.stack[(size_t)tree * kStackCap + s->sp] = r;
+            NodeEnt l;
+            l.start = cur.start; l.len = nL; l.m = (uint32_t)(tneL >> 32); l.E = (uint32_t)(tneL & 0xffffffffu);
+            l.rtsum = trtL; l.nodeID = cur.nodeID; l.parentRec = kNone; l.depth = cur.depth + 1; l.buf = cur.buf ^ 1u;
+            s->cur = l;
+          }
         }
       }
-    }
-    __syncthreads();
-    if (!s->abort) {
-      // children inherit the parent's (possibly updated) permissible mask (rf.c:10725-10727)
-      uint32_t* sp = w.stackPerm + ((size_t)tree * kStackCap + s->sp) * g.pw;
+      __syncwarp();
+      if (!s->abort) {
+        // children inherit the parent's (possibly updated) permissible mask (rf.c:10725-10727)
+        uint32_t* sp = w.stackPerm + ((size_t)tree * kStackCap + s->sp) * g.pw;
 #pragma unroll 1
-      for (int k = tid; k < g.pw; k += kThreads) sp[k] = s->perm[k];
-      __syncthreads();
-      if (tid == 0) s->sp++;
+        for (int k = lane_id(); k < g.pw; k += 32) sp[k] = s->perm[k];
+        __syncwarp();
+        if (lane_id() == 0) s->sp++;
+      }
     }
     RF_PROF(11);
   }
