@@ -34,6 +34,7 @@ extern "C" {
 #define RFSLAM_ENOMEM    4
 
 /* option bits the path understands; same values as the reference (rf.h:108-158) */
+#define RFSLAM_OPT_PERF        0x00000004u   /* optLow: performance of the OOB ensemble (rf.h:110) */
 #define RFSLAM_OPT_BOOT_TYP1   0x00080000u   /* optLow  (by.user = TYP1|TYP2, rf.c:520) */
 #define RFSLAM_OPT_BOOT_TYP2   0x00100000u
 #define RFSLAM_OPTH_MEMB_USER  0x00000040u   /* optHigh: return nodeMembership / bootMembership */
@@ -136,6 +137,11 @@ typedef struct rfslam_forest_out {
   double    total_device_ms;   /* device time of the whole call incl. bootstrap and ensembles */
   int64_t   kernel_launches;   /* kernels of this library launched by the call */
   int64_t   rmbr_stride;       /* row stride of rmbrMembership (= maxBootstrapSize, rf.c:18296) */
+  /* perfClas (rf.c:25, rf.c:17454): [ntree][1 + 2] OOB misclassification rate of the forest and per class
+     (getClassificationIndex rf.c:1067, getConditionalClassificationIndex rf.c:1025).  Present when opt_low has
+     RFSLAM_OPT_PERF and the call finalizes the ensembles of the whole forest; only the last row is filled
+     (perfBlock = ntree, rf.c:8155), the others hold NA_REAL as in the reference. */
+  double   *perfClas;
 } rfslam_forest_out;
 
 int  rfslam_b200_grow(const rfslam_grow_args *args, rfslam_forest_out *out);

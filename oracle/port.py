@@ -109,6 +109,16 @@ def grow(x, y, rt, strat, *, rule=4, ntree=4, mtry=None, nodesize=5, nodedepth=-
         "oobEnsbCLS": _arr(o.oobEns, 2 * n, np.float64), "allEnsbCLS": _arr(o.allEns, 2 * n, np.float64),
         "candidates": np.array([o.candidates], np.int64),
     }
+    # perfClas [ntree][3]: NA_REAL rows except the last (perfBlock = ntree, randomForestSRC.c:8155)
+    na = np.array([0x7FF00000000007A2], np.uint64).view(np.float64)[0]
+    perf = np.full(ntree * 3, na, np.float64)
+    last = np.zeros(3, np.float64)
+    oob_den = _arr(o.oobDen, n, np.int32)
+    L.orc_perf_clas.restype = None
+    L.orc_perf_clas.argtypes = [C.c_int, _pd, _pd, _pi, C.c_double, _pd]
+    L.orc_perf_clas(n, _dp(y), _dp(res["oobEnsbCLS"]), _ip(oob_den), C.c_double(na), _dp(last))
+    perf[-3:] = last
+    res["perfClas"] = perf
     L.orc_free(op)
     return res
 

@@ -459,6 +459,29 @@ void orc_free(orc_out *o) {
   free(o);
 }
 
+/* perfClas of the finalized OOB ensemble (default performance of the class family):
+   out[0] = getClassificationIndex (randomForestSRC.c:1067-1095) over getMaxVote (randomForestSRC.c:1175-1218:
+   the last class whose probability is >= the running maximum wins, i.e. class 2 on a tie);
+   out[1..2] = getConditionalClassificationIndex (randomForestSRC.c:1025-1066): correct OOB votes of the class
+   over ALL rows of the class.  na = the caller's NA_REAL.  y in {1.0, 2.0}; ens = [2][n] class-major. */
+void orc_perf_clas(int n, const double *y, const double *ens, const int *den, double na, double *out) {
+  double correct = 0.0, cpv[3] = {0.0, 0.0, 0.0};
+  unsigned cum = 0, count[3] = {0, 0, 0};
+  for (int i = 0; i < n; i++) {
+    count[(unsigned) y[i]]++;
+    if (den[i] != 0) {
+      double maxValue = 0.0, maxClass = 0.0;
+      for (int k = 1; k <= 2; k++)
+        if (maxValue <= ens[(size_t)(k - 1) * n + i]) { maxValue = ens[(size_t)(k - 1) * n + i]; maxClass = (double) k; }
+      cum++;
+      if (y[i] == maxClass) { correct += 1.0; cpv[(unsigned) y[i]] += 1.0; }
+    }
+  }
+  if (cum == 0) { out[0] = out[1] = out[2] = na; return; }
+  out[0] = 1.0 - correct / (double) cum;
+  for (int k = 1; k <= 2; k++) out[k] = count[k] ? 1.0 - cpv[k] / (double) count[k] : na;
+}
+
 /* bootstrap-only entry (chain A replay) for the in-bag parity tests */
 void orc_bootstrap(int seed, int ntree, int n, int tree /* 0-based */, int *draws /* [n], 1-based row ids */) {
   int *seedA = malloc(ntree * sizeof(int)), *seedB = malloc(ntree * sizeof(int));

@@ -41,6 +41,7 @@ void     orc_chain_seeds(int seed, int ntree, int *seedA, int *seedB);
 void     orc_chain_seeds_restore(int ntree, int *seedB);
 void     orc_bootstrap(int seed, int ntree, int n, int tree, int *draws);
 void     orc_ran1_stream(int seed, int count, float *out);
+void     orc_perf_clas(int n, const double *y, const double *ens, const int *den, double na, double *out);
 
 #ifdef __cplusplus
 }

@@ -45,7 +45,7 @@ class ForestOut(C.Structure):
         ("nodeMembership", _pi), ("bootMembership", _pi), ("rmbrMembership", _pi), ("ambrMembership", _pi),
         ("oobEnsbCLS", _pd), ("allEnsbCLS", _pd), ("oobEnsbDen", _pu), ("allEnsbDen", _pu),
         ("split_candidates", C.c_int64), ("algorithmic_bytes", C.c_int64),
-        ("grow_kernel_ms", C.c_double), ("total_device_ms", C.c_double), ("kernel_launches", C.c_int64), ("rmbr_stride", C.c_int64),
+        ("grow_kernel_ms", C.c_double), ("total_device_ms", C.c_double), ("kernel_launches", C.c_int64), ("rmbr_stride", C.c_int64), ("perfClas", _pd),
     ]
 
 

@@ -121,7 +121,7 @@ void rfslam_b200_free_forest(rfslam_forest_out* o) {
   if (!o) return;
   void* arrays[] = {o->tree_ids, o->treeID, o->nodeID, o->parmID, o->contPT, o->mwcpSZ, o->splitStat, o->leafCount, o->seed,
                     o->tnRCNT, o->tnACNT, o->tnCLAS, o->nodeMembership, o->bootMembership, o->rmbrMembership, o->ambrMembership,
-                    o->oobEnsbCLS, o->allEnsbCLS, o->oobEnsbDen, o->allEnsbDen};
+                    o->oobEnsbCLS, o->allEnsbCLS, o->oobEnsbDen, o->allEnsbDen, o->perfClas};
   for (void* p : arrays) host_free(p);
   memset(o, 0, sizeof(*o));
 }

@@ -196,6 +196,29 @@ __global__ void finalize_kernel(double* num, const uint32_t* den, int n) {
   }
 }
 
+// perfClas (rf.c:7954-8010 default branch): votes of the finalized OOB ensemble.  getMaxVote (rf.c:1175)
+// keeps the LAST class whose probability is >= the running maximum, i.e. class 2 on a tie; the
+// classification index counts rows with an OOB prediction (rf.c:1067), the conditional index divides by
+// ALL rows of the class (rf.c:1025-1066).  acc = {rows class 1, rows class 2, rows with OOB, correct 1, correct 2}
+__global__ void perf_kernel(const double* oob, const uint32_t* den, const uint8_t* ev, const uint32_t* inv, int n,
+                            unsigned long long* acc) {
+  unsigned long long c0 = 0, c1 = 0, cum = 0, ok0 = 0, ok1 = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int cls = ev[inv[i]] ? 1 : 0;
+    if (cls) c1++; else c0++;
+    if (den[i] != 0u) {
+      cum++;
+      const double p1 = oob[i], p2 = oob[(size_t)n + i];
+      const int vote = (p1 <= p2) ? 1 : 0;
+      if (vote == cls) { if (cls) ok1++; else ok0++; }
+    }
+  }
+  c0 = warp_sum(c0); c1 = warp_sum(c1); cum = warp_sum(cum); ok0 = warp_sum(ok0); ok1 = warp_sum(ok1);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&acc[0], c0); atomicAdd(&acc[1], c1); atomicAdd(&acc[2], cum); atomicAdd(&acc[3], ok0); atomicAdd(&acc[4], ok1);
+  }
+}
+
 // device scratch; with a pool (the resident dataset's) buffers are recycled across grow calls
 template <typename T>
 struct DevBuf {
@@ -577,6 +600,25 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
       launches += 2;
       RF_CUDA(cudaGetLastError());
     }
+    // perfClas: only for a whole, finalized forest (a shard's ensembles are partial sums)
+    double* h_perf = nullptr;
+    if (cfg.finalize && (a->opt_low & RFSLAM_OPT_PERF) && T == cfg.ntree) {
+      DevBuf<unsigned long long> d_acc(pool);
+      d_acc.alloc(5); d_acc.zero();
+      perf_kernel<<<296, 256>>>(d_oobNum.p, d_oobDen.p, ds->dev.ev, ds->dev.inv, n, d_acc.p);
+      launches++;
+      unsigned long long acc[5];
+      RF_CUDA(cudaMemcpy(acc, d_acc.p, sizeof acc, cudaMemcpyDeviceToHost));
+      h_perf = (double*)host_alloc((size_t)T * 3 * sizeof(double));
+      const double na = rfslam_na_real();
+      for (size_t k = 0; k < (size_t)T * 3; k++) h_perf[k] = na;
+      double* last = h_perf + (size_t)(T - 1) * 3;                // serialTreeID == ntree (rf.c:8155)
+      if (acc[2] != 0) {
+        last[0] = 1.0 - (double)(acc[3] + acc[4]) / (double)acc[2];
+        if (acc[0]) last[1] = 1.0 - (double)acc[3] / (double)acc[0];
+        if (acc[1]) last[2] = 1.0 - (double)acc[4] / (double)acc[1];
+      }
+    }
     cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2); cudaEventDestroy(ev3); cudaEventDestroy(evC);
     cudaStreamDestroy(copyStream);
     unsigned long long pathSum = 0;
@@ -604,6 +646,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
       out->ambrMembership = host_copy(d_ambr.p, (size_t)T * n);
       out->rmbr_stride = (int64_t)rmbrStride;
     }
+    out->perfClas = h_perf;
     out->split_candidates = totalCand; out->algorithmic_bytes = totalAlgo;
     out->grow_kernel_ms = growMs; out->total_device_ms = totalMs; out->kernel_launches = launches;
   } catch (CudaFail f) {

@@ -1,5 +1,6 @@
 // internal.h -- structures shared by the translation units of librfslam_b200.so (not part of the ABI).
 #pragma once
+#include <string.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <vector>
@@ -101,6 +102,9 @@ int  score_node_impl(int rule, double k_for_alpha, int m, const double* x, const
 int  bootstrap_counts_impl(int seed, int ntree, int n, int tree, int32_t* counts, int device);
 int  validate_grow_args(const rfslam_grow_args* a, GrowConfig* cfg);
 void chain_seeds(int seed, int ntree, std::vector<int>& seedA, std::vector<int>& seedB);
+
+// R's NA_real_: the NaN with payload 1954 (arithmetic NaN is a different bit pattern)
+inline double rfslam_na_real() { const unsigned long long b = 0x7FF00000000007A2ull; double d; memcpy(&d, &b, 8); return d; }
 
 // hostpool.cu: recycled page-locked memory for the arrays handed to the caller
 void* host_alloc(size_t bytes);

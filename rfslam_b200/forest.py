@@ -147,6 +147,8 @@ def _unpack_forest(o: ForestOut) -> Dict[str, np.ndarray]:
     if o.nodeMembership:
         res["nodeMembership"] = _own(o, "nodeMembership", T * n, np.int32)
         res["bootMembership"] = _own(o, "bootMembership", T * n, np.int32)
+    if o.perfClas:
+        res["perfClas"] = _own(o, "perfClas", T * 3, np.float64)
     return res
 
 

@@ -64,7 +64,7 @@ def main():
             save["samp"] = samp
         for k in ("oobEnsbCLS", "allEnsbCLS", "leafCount", "seed", "nodeMembership", "bootMembership",
                   "treeID", "nodeID", "parmID", "contPT", "mwcpSZ", "tnRCNT", "tnACNT",
-                  "rmbrMembership", "ambrMembership"):
+                  "rmbrMembership", "ambrMembership", "perfClas"):
             save["ref_" + k] = t[k]
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **save)
         print(name, "nodes", t["treeID"].size, "bytes", os.path.getsize(os.path.join(OUT, name + ".npz")))

@@ -59,6 +59,9 @@ def assert_forest_equal(got: Dict[str, np.ndarray], ref: Dict[str, np.ndarray], 
         np.testing.assert_array_equal(np.isnan(a), np.isnan(r), err_msg=f"{label} {k} NA pattern")
         ok = ~np.isnan(r)
         np.testing.assert_allclose(a[ok], r[ok], rtol=HAZARD_RTOL, atol=0, err_msg=f"{label} {k}")
+    if "perfClas" in ref and "perfClas" in got:
+        # OOB misclassification rates: ratios of integer counts, exact; NA_REAL (payload 1954) elsewhere
+        np.testing.assert_array_equal(got["perfClas"].view(np.uint64), ref["perfClas"].view(np.uint64), err_msg=label + " perfClas")
     if check_membr_lists:
         np.testing.assert_array_equal(got["rmbrMembership"][: ref["rmbrMembership"].size], ref["rmbrMembership"], err_msg=label + " rmbr")
         np.testing.assert_array_equal(got["ambrMembership"], ref["ambrMembership"], err_msg=label + " ambr")

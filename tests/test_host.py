@@ -40,7 +40,7 @@ def test_struct_layout_matches_header_sizes():
     # the ctypes mirrors must have the C layout: pointer-sized alignment, no stray fields
     assert ctypes.sizeof(capi.GrowArgs) % 8 == 0
     assert capi.GrowArgs.x_data.offset % 8 == 0
-    assert ctypes.sizeof(capi.ForestOut) == 4 + 4 + 8 + 8 + 20 * 8 + 8 + 8 + 8 + 8 + 8 + 8
+    assert ctypes.sizeof(capi.ForestOut) == 4 + 4 + 8 + 8 + 20 * 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8   # ... + perfClas
 
 
 @pytest.mark.skipif(capi.lib().rfslam_b200_device_count() > 0, reason="a GPU is present")
