@@ -383,6 +383,15 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     }
     const size_t smem = grow_smem_bytes(g.ncmax, ds->K, g.hbins);
     RF_CUDA(cudaFuncSetAttribute(rfslam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int residentCtas = 0; long long quantumCycles = 0;
+    {
+      int perSm = 0, dev = 0; cudaDeviceProp prop;
+      RF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, rfslam_grow_kernel, kThreads, smem));
+      RF_CUDA(cudaGetDevice(&dev)); RF_CUDA(cudaGetDeviceProperties(&prop, dev));
+      residentCtas = std::max(1, perSm) * prop.multiProcessorCount;
+      const char* q = getenv("RFSLAM_QUANTUM_MS");
+      quantumCycles = (long long)((q ? atof(q) : 10.0) * (double)prop.clockRate);      // clockRate is in kHz = cycles per ms
+    }
 
     // ---- batch size from free memory ----
     size_t freeB = 0, totalB = 0;
@@ -484,8 +493,19 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         w.ctab = d_ctab.p; w.maxChunksPerTree = maxChunksPerTree; w.nodeCount = d_nodeCount.p; w.leafCount = d_leafCount.p;
         w.candCount = d_cand.p; w.algoBytes = d_algo.p; w.status = d_status.p;
         w.prof = profile ? d_prof.p : nullptr;
+        // more trees than resident CTAs: the grid is the resident CTAs and trees are time-sliced
+        int gridTrees = nb;
+        DevBuf<int> d_tstate(pool); DevBuf<unsigned char> d_saved(pool);
+        if (nb > residentCtas && !getenv("RFSLAM_NO_SLICING")) {
+          d_tstate.alloc((size_t)nb + 2); d_tstate.zero();
+          d_saved.alloc((size_t)nb * sizeof(GrowShared));
+          RF_CUDA(cudaMemcpyAsync(d_tstate.p + nb, &nb, 4, cudaMemcpyHostToDevice));     // waiting = nb; ticket = 0
+          w.treeState = d_tstate.p; w.waiting = d_tstate.p + nb; w.ticket = (unsigned*)(d_tstate.p + nb + 1);
+          w.saved = d_saved.p; w.quantum = quantumCycles;
+          gridTrees = residentCtas;
+        }
         RF_CUDA(cudaEventRecord(ev1));
-        rfslam_grow_kernel<<<nb, kThreads, smem>>>(ds->dev, g, w);
+        rfslam_grow_kernel<<<gridTrees, kThreads, smem>>>(ds->dev, g, w);
         launches++;
         RF_CUDA(cudaEventRecord(ev2));
         RF_CUDA(cudaGetLastError());

@@ -86,6 +86,12 @@ struct GrowWork {
   unsigned long long* prof;      // optional [ntrees][kProfSlots] clock64 sums per phase / node-size class
   // single-node scoring mode (rfslam_b200_score_node): emit every cut instead of tracking
   double* sinkCut; double* sinkDelta; int* sinkCount;
+  // time slicing (batches with more trees than resident CTAs): see rfslam_grow_kernel
+  int* treeState;                // [ntrees] 0 fresh, 1 suspended, 2 running, 3 done; nullptr = one CTA per tree, no slicing
+  int* waiting;                  // trees that are fresh or suspended
+  unsigned* ticket;              // round-robin cursor
+  unsigned char* saved;          // [ntrees][sizeof(GrowShared)] state of suspended trees
+  long long quantum;             // cycles a CTA works on a tree before it offers the slot to a waiting tree
 };
 
 // fixed-size part of the CTA's shared memory
@@ -114,6 +120,7 @@ struct GrowShared {
   int trkMaxBin[kMaxCand]; double trkMax[kMaxCand]; int trkClean[kMaxCand]; int trkNp[kMaxCand]; int trkLast[kMaxCand];
   unsigned long long prof[kProfSlots];
   long long tmark;
+  long long sliceStart; int curTree; int fresh;
 };
 
 #define RF_PROF(slot)                                                                  \
@@ -1180,19 +1187,46 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
   GrowSmem m = carve(smem_raw, g.ncmax, d.K, g.hbins);
   GrowShared* s = m.s;
   const int tid = vtid();
-  const int tree = blockIdx.x;
   const int n = d.n;
-  uint32_t* listA = w.lists + (size_t)tree * 2 * n;
-  const uint16_t* cnt = w.cnt + (size_t)tree * w.cntStride;
+  const bool sliced = w.treeState != nullptr;
 
   // ---- clean histograms (flushes keep them clean afterwards) ----
   for (int i = tid; i < g.ncmax * m.hb * m.hs; i += kThreads) { m.hN[i] = 0; m.hE[i] = 0; m.hNx[i] = 0; m.hEx[i] = 0; m.hT[i] = 0.0; m.hW[i] = 0.0; }
+
+  // Time slicing.  A batch with more trees than resident CTAs (500 trees, 296 slots) used to run as a
+  // full wave and a partial one: 1.61 s against 1.43 s for a balanced load, and a tree cannot be split
+  // (chain B).  But a tree's whole state between two nodes is GrowShared (2 KB: RNG, current node,
+  // permissible mask, counters) plus what already lives in global memory, so the grid is the resident
+  // CTAs and every CTA works on a tree for a quantum, parks it and takes the next waiting one: all trees
+  // advance at the same rate and finish together.  Results do not depend on the schedule.
+  while (true) {
+  if (tid == 0) {
+    int t = -1, fresh = 0;
+    if (!sliced) { t = (int)blockIdx.x; fresh = 1; }
+    else {
+      while (atomicAdd(w.waiting, 0) > 0) {
+        const unsigned k = atomicAdd(w.ticket, 1u) % (unsigned)w.ntrees;
+        const int old = atomicCAS(&w.treeState[k], 0, 2);
+        if (old == 0) { t = (int)k; fresh = 1; atomicSub(w.waiting, 1); break; }
+        if (old == 1 && atomicCAS(&w.treeState[k], 1, 2) == 1) { t = (int)k; atomicSub(w.waiting, 1); break; }
+      }
+    }
+    s->curTree = t; s->fresh = fresh;
+  }
+  __syncthreads();
+  const int tree = s->curTree;
+  if (tree < 0) break;
+  __threadfence();                                                   // acquire: what the previous owner of this tree wrote
+  uint32_t* listA = w.lists + (size_t)tree * 2 * n;
+  const uint16_t* cnt = w.cnt + (size_t)tree * w.cntStride;
+  if (s->fresh) {
   if (tid == 0) {
     for (int k = 0; k < kProfSlots; k++) s->prof[k] = 0;
     s->tmark = clock64();
     ran1_seed(s->rng, w.seedB[tree]);
     ran1_init(s->rng);
-    s->nodeCount = 0; s->leafCount = 1; s->sp = 0; s->candCount = 0; s->algoBytes = 0; s->abort = 0; s->histDirty = 0;
+    s->nodeCount = 0; s->leafCount = 1; s->sp = 0; s->candCount = 0; s->algoBytes = 0; s->abort = 0;
+    s->histDirty = sliced ? 1 : 0;                                  // another tree's small nodes may have used the histograms
   }
   for (int k = tid; k < 32; k += kThreads) {
     uint32_t msk = 0;
@@ -1236,10 +1270,21 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     __syncthreads();
   }
   RF_PROF(0);
+  } else {
+    // resume a parked tree
+    const uint32_t* src32 = (const uint32_t*)(w.saved + (size_t)tree * sizeof(GrowShared));
+    uint32_t* dst32 = (uint32_t*)s;
+    for (int k = tid; k < (int)(sizeof(GrowShared) / 4); k += kThreads) dst32[k] = __ldcg(src32 + k);
+    __syncthreads();
+    if (tid == 0) { s->curTree = tree; s->fresh = 0; s->abort = 0; s->histDirty = 1; s->tmark = clock64(); s->prof[13] = 0; }
+    __syncthreads();
+  }
+  if (tid == 0) s->sliceStart = clock64();
 
   const bool bayes = rule_is_bayes(g.rule);
   // ---- depth-first growth (rf.c:21460-21792) ----
   while (true) {
+    if (sliced && tid == 0 && !s->abort && clock64() - s->sliceStart > w.quantum && atomicAdd(w.waiting, 0) > 0) s->abort = 3;   // park
     __syncthreads();
     if (s->abort) break;
     const NodeEnt cur = s->cur;
@@ -1461,12 +1506,27 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     RF_PROF(11);
   }
   __syncthreads();
+  if (s->abort == 3) {
+    // park: state to global, then publish (every thread's writes of this slice are fenced first)
+    uint32_t* dst32 = (uint32_t*)(w.saved + (size_t)tree * sizeof(GrowShared));
+    const uint32_t* src32 = (const uint32_t*)s;
+    for (int k = tid; k < (int)(sizeof(GrowShared) / 4); k += kThreads) dst32[k] = src32[k];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) { atomicExch(&w.treeState[tree], 1); atomicAdd(w.waiting, 1); }
+    __syncthreads();
+    continue;
+  }
   if (tid == 0) {
     if (w.prof) for (int k = 0; k < kProfSlots; k++) w.prof[(size_t)tree * kProfSlots + k] = s->prof[k];
     w.nodeCount[tree] = s->nodeCount;
     w.leafCount[tree] = s->leafCount;
     w.candCount[tree] = s->candCount;
     w.algoBytes[tree] = s->algoBytes;
+    if (sliced) atomicExch(&w.treeState[tree], 3);
+  }
+  __syncthreads();
+  if (!sliced) break;
   }
 }
 
