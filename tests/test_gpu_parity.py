@@ -164,3 +164,45 @@ def test_variable_categories_accepted():
     with pytest.raises(rfslam_b200.RfslamError):
         rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=3, nodesize=5, seed=-21, mtry=9, var_categories=cats,
                           category_weights=np.array([0.1, 0.1, 0.1]))
+
+
+def test_time_slicing_does_not_change_the_forest(monkeypatch):
+    # more trees than resident CTAs: trees are parked and resumed by other CTAs (grow_kernel.cuh);
+    # the forest must be the one grown with one CTA per tree from start to finish, and match the oracle
+    d = make_cpiu(3000, 8, levels=32, seed=21)
+    ntree = 700
+    monkeypatch.setenv("RFSLAM_QUANTUM_MS", "0.05")              # many switches per tree
+    a = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=ntree, nodesize=5, seed=-9, membership=True)
+    monkeypatch.setenv("RFSLAM_NO_SLICING", "1")
+    b = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=ntree, nodesize=5, seed=-9, membership=True)
+    for k in ("treeID", "nodeID", "parmID", "leafCount", "tnRCNT", "tnACNT", "nodeMembership", "bootMembership"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    np.testing.assert_array_equal(a["contPT"].view(np.uint64), b["contPT"].view(np.uint64))
+    np.testing.assert_array_equal(a["oobEnsbCLS"], b["oobEnsbCLS"])
+    want = port.grow(d.x, d.y, d.rt, d.strat, rule=4, ntree=ntree, nodesize=5, seed=-9)
+    parity.assert_forest_equal(a, want, d.n, ntree, label="sliced")
+
+
+def test_full_size_properties():
+    # BASELINE configs[1] rows x covariates (1M x 50, 64 levels), more trees than resident CTAs:
+    # size-independent properties -- every draw and every row lands in exactly one leaf, records are
+    # a full binary tree in pre-order, the time-sliced schedule and tree sharding do not change a tree
+    d = make_cpiu(1_000_000, 50, levels=64)
+    ds = rfslam_b200.ResidentCpiu(d.x, d.y, d.rt, d.strat)
+    ntree = 304
+    a = ds.grow(ntree=ntree, nodesize=20, seed=-12345)
+    assert a["tnRCNT"].sum() == ntree * d.n and a["tnACNT"].sum() == ntree * d.n
+    assert a["treeID"].size == int((2 * a["leafCount"].astype(np.int64) - 1).sum())
+    assert int((a["parmID"] == 0).sum()) == int(a["leafCount"].sum())
+    assert np.all(a["tnRCNT"] >= 1) and np.all(a["oobEnsbDen"] <= ntree)
+    ens = a["allEnsbCLS"].reshape(2, -1)
+    np.testing.assert_allclose(ens.sum(axis=0), 1.0, rtol=1e-12)             # class proportions of a row sum to one
+    assert 0.0 <= a["perfClas"][-3] <= 1.0 and np.isnan(a["perfClas"][:-3]).all()
+    # the same trees from a shard that holds every 38th tree (8 trees: one CTA each, no slicing)
+    part = ds.grow(ntree=ntree, nodesize=20, seed=-12345, tree_first=5, tree_step=38, finalize=False)
+    for j, b in enumerate(range(5, ntree + 1, 38)):
+        full_t, part_t = parity.split_tree(a, b), parity.split_tree(part, b)
+        for k in ("nodeID", "parmID"):
+            np.testing.assert_array_equal(full_t[k], part_t[k], err_msg=f"tree {b} {k}")
+        np.testing.assert_array_equal(full_t["contPT"].view(np.uint64), part_t["contPT"].view(np.uint64))
+    ds.close()
