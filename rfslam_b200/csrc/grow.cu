@@ -88,7 +88,7 @@ __global__ void user_count_kernel(const int32_t* samp, const uint32_t* perm, uin
 __global__ void compact_kernel(GrowWork w, DevData d, const int* treeIds, const unsigned long long* nodeOff,
                                const unsigned long long* leafOff,
                                int32_t* treeID, int32_t* nodeID, int32_t* parmID, double* contPT, double* splitStat,
-                               uint32_t* code, uint32_t* right, int32_t* tnRCNT, int32_t* tnCLAS) {
+                               uint4* rec4, int32_t* tnRCNT, int32_t* tnCLAS) {
   const int t = blockIdx.y;
   const uint32_t cntN = w.nodeCount[t];
   const unsigned long long off = nodeOff[t], loff = leafOff[t];
@@ -101,12 +101,12 @@ __global__ void compact_kernel(GrowWork w, DevData d, const int* treeIds, const 
     nodeID[off + q] = (int32_t)r.nodeID;
     parmID[off + q] = (int32_t)r.parm;
     splitStat[off + q] = w.statPool[at];
+    // the traversal kernels read ONE 16-byte record per visited node: {covariate + 1, cut code, right child, node id}
+    rec4[off + q] = r.parm ? make_uint4(r.parm, r.a, r.b, r.nodeID) : make_uint4(0u, 0u, 0u, r.nodeID);
     if (r.parm) {
       contPT[off + q] = d.uniq[r.parm - 1][r.a];
-      code[off + q] = r.a; right[off + q] = r.b;
     } else {
       contPT[off + q] = na;
-      code[off + q] = 0; right[off + q] = 0;
       tnRCNT[loff + r.nodeID - 1] = (int32_t)r.b;
       tnCLAS[2 * (loff + r.nodeID - 1)] = (int32_t)(r.b - r.a);
       tnCLAS[2 * (loff + r.nodeID - 1) + 1] = (int32_t)r.a;
@@ -118,7 +118,7 @@ __global__ void compact_kernel(GrowWork w, DevData d, const int* treeIds, const 
 // LEFT iff code <= cut code  <=>  cut - x >= 0), accumulating the class proportions of the leaf
 // (rf.c:928-962) into the full ensemble and, when the row is out of bag, the OOB ensemble.
 __global__ void membership_kernel(DevData d, int ntrees, const unsigned long long* nodeOff, const unsigned long long* leafOff,
-                                  const int32_t* nodeID, const int32_t* parmID, const uint32_t* code, const uint32_t* right,
+                                  const uint4* __restrict__ rec4,
                                   const int32_t* tnRCNT, const int32_t* tnCLAS, const uint16_t* cnt,
                                   int32_t* tnACNT, double* allNum, double* oobNum, uint32_t* allDen, uint32_t* oobDen,
                                   int32_t* nodeMembership, int32_t* bootMembership, int batchFirst, size_t cntStride,
@@ -131,13 +131,14 @@ __global__ void membership_kernel(DevData d, int ntrees, const unsigned long lon
   for (int t = 0; t < ntrees; t++) {
     const unsigned long long off = nodeOff[t];
     unsigned long long q = off;
-    int pm;
-    while ((pm = parmID[q]) != 0) {
-      uint32_t cd = load_code(d.codes[pm - 1], d.width[pm - 1], (uint32_t)i);
-      q = (cd <= code[q]) ? q + 1 : off + right[q];
+    uint4 r = rec4[q];
+    while (r.x != 0u) {
+      const uint32_t cd = load_code(d.codes[r.x - 1u], d.width[r.x - 1u], (uint32_t)i);
+      q = (cd <= r.y) ? q + 1 : off + r.z;
+      r = rec4[q];
       steps++;
     }
-    const int leaf = nodeID[q];
+    const int leaf = (int)r.w;
     const unsigned long long li = leafOff[t] + (unsigned long long)leaf - 1ull;
     const double rc = (double)tnRCNT[li];
     const double p1 = (double)tnCLAS[2 * li] / rc, p2 = (double)tnCLAS[2 * li + 1] / rc;
@@ -403,7 +404,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     size_t estNodes = std::min<size_t>(worstNodes, 4ull * (size_t)maxBoot / (size_t)std::max(1, cfg.nodesize) + 256);
     size_t budget = (size_t)(0.80 * (double)freeB);
     size_t fixed = (size_t)n * (16 + 16 + 8) + (64u << 20);
-    int B = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, (budget > fixed ? budget - fixed : 0) / (perTree + estNodes * 72)));
+    int B = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, (budget > fixed ? budget - fixed : 0) / (perTree + estNodes * 80)));
     if (const char* e = getenv("RFSLAM_TREES_PER_BATCH")) { int v = atoi(e); if (v > 0) B = std::min(T, v); }
 
     // ---- persistent accumulators ----
@@ -539,15 +540,15 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         RF_CUDA(cudaMemcpy(d_leafOff.p, leafOff.data(), (nb + 1) * 8, cudaMemcpyHostToDevice));
         const size_t NN = nodeOff[nb], NL = leafOff[nb];
         DevBuf<int32_t> f_tree(pool), f_node(pool), f_parm(pool), f_rcnt(pool), f_acnt(pool), f_clas(pool);
-        DevBuf<double> f_cont(pool), f_stat(pool); DevBuf<uint32_t> f_code(pool), f_right(pool);
-        f_tree.alloc(NN); f_node.alloc(NN); f_parm.alloc(NN); f_cont.alloc(NN); f_stat.alloc(NN); f_code.alloc(NN); f_right.alloc(NN);
+        DevBuf<double> f_cont(pool), f_stat(pool); DevBuf<uint4> f_rec4(pool);
+        f_tree.alloc(NN); f_node.alloc(NN); f_parm.alloc(NN); f_cont.alloc(NN); f_stat.alloc(NN); f_rec4.alloc(NN);
         f_rcnt.alloc(NL); f_acnt.alloc(NL); f_clas.alloc(2 * NL); f_acnt.zero();
         uint32_t maxNodes = *std::max_element(hNodes.begin(), hNodes.end());
         dim3 gk((unsigned)std::min<uint32_t>((maxNodes + 255) / 256, 2048), (unsigned)nb);
         compact_kernel<<<gk, 256>>>(w, ds->dev, d_ids.p, d_nodeOff.p, d_leafOff.p, f_tree.p, f_node.p, f_parm.p, f_cont.p, f_stat.p,
-                                    f_code.p, f_right.p, f_rcnt.p, f_clas.p);
+                                    f_rec4.p, f_rcnt.p, f_clas.p);
         RF_CUDA(cudaEventRecord(evC));
-        membership_kernel<<<(n + 127) / 128, 128>>>(ds->dev, nb, d_nodeOff.p, d_leafOff.p, f_node.p, f_parm.p, f_code.p, f_right.p,
+        membership_kernel<<<(n + 127) / 128, 128>>>(ds->dev, nb, d_nodeOff.p, d_leafOff.p, f_rec4.p,
                                                     f_rcnt.p, f_clas.p, d_cnt.p, f_acnt.p, d_allNum.p, d_oobNum.p, d_allDen.p, d_oobDen.p,
                                                     d_nodeMemb.p, d_bootMemb.p, b0, cntStride, d_pathSum.p);
         launches += 2;
