@@ -1,5 +1,6 @@
-import time, sys, numpy as np
-sys.path.insert(0, '.')
+"""Phase profile of the tree kernel: RFSLAM_PROFILE=1 python tools/phase_profile.py <rows> <covariates> <levels> <ntree> <nodesize>"""
+import os, time, sys, numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
 import rfslam_b200
 from rfslam_b200.synth import make_cpiu
 n, p, L = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
