@@ -152,6 +152,18 @@ def run_reference_arm(args):
     return 0
 
 
+def ncu_traffic(cfg):
+    """DRAM bytes of one tree-kernel launch from the committed `ncu --set full` capture of this workload
+    (profiles/ncu_traffic_r01.json); None for any other workload (nothing is measured under a profiler here)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
+        wl = t["workload"]
+        same = all(int(wl[k]) == int(cfg[k]) for k in ("n", "p", "ntree", "levels", "nodesize", "rule"))
+        return float(t["dram_bytes_per_launch"]) if same else None
+    except Exception:
+        return None
+
+
 def workload_name(cfg):
     return (f"BASELINE configs[1]: {cfg['n']} CPIUs x {cfg['p']} covariates (mode Q, {cfg['levels']} levels), ntree={cfg['ntree']} per GPU, "
             f"mtry=ceil(sqrt(p)), nodesize={cfg['nodesize']}, poisson.split{cfg['rule']}, bootstrap by.root, seed {cfg['seed']}")
@@ -282,7 +294,7 @@ def main():
         "gpu_launches": int(f["kernel_launches"]) * args.steps,
         "roofline": {"bound": "hbm", "kernel": "rfslam_grow_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_total / world, "kernel_ms": kern_mean,
-                     "traffic": None},
+                     "traffic": ncu_traffic(cfg), "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum)"},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
