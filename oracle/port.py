@@ -24,7 +24,7 @@ class OrcArgs(C.Structure):
     _fields_ = [(k, C.c_int) for k in ("n", "p", "ntree", "mtry", "nodesize", "nodedepth", "rule", "seed", "max_boot")] + [
         ("k_for_alpha", C.c_double),
         ("x", _pd), ("y", _pd), ("rt", _pd), ("strat", _pi), ("samp", _pi), ("boot_size", _pi),
-        ("split_weight", _pd), ("tree_seeds", _pi)]
+        ("split_weight", _pd), ("tree_seeds", _pi), ("nsplit", C.c_int)]
 
 
 class OrcOut(C.Structure):
@@ -72,7 +72,7 @@ def _arr(ptr, n, dtype):
 
 
 def grow(x, y, rt, strat, *, rule=4, ntree=4, mtry=None, nodesize=5, nodedepth=-1, seed=-12345,
-         k_for_alpha=2.0, samp=None, split_weight=None, tree_seeds=None) -> Dict[str, np.ndarray]:
+         k_for_alpha=2.0, samp=None, split_weight=None, tree_seeds=None, nsplit=0) -> Dict[str, np.ndarray]:
     L = lib()
     p, n = x.shape
     x = np.ascontiguousarray(x, np.float64); y = np.ascontiguousarray(y, np.float64)
@@ -82,6 +82,7 @@ def grow(x, y, rt, strat, *, rule=4, ntree=4, mtry=None, nodesize=5, nodedepth=-
     a = OrcArgs()
     a.n, a.p, a.ntree, a.mtry, a.nodesize, a.nodedepth, a.rule, a.seed = n, p, ntree, mtry, nodesize, nodedepth, rule, seed
     a.k_for_alpha = k_for_alpha
+    a.nsplit = int(nsplit)
     a.x, a.y, a.rt, a.strat = _dp(x), _dp(y), _dp(rt), _ip(strat)
     keep = [x, y, rt, strat]
     a.max_boot = n

@@ -217,7 +217,24 @@ static int score_covariate(tree_ctx *c, int cov, const int *rep, int m,
     c->gend[D - 1] = i + 1;
   }
   if (D < 2) return D;
-  c->candidates += D - 1;
+  /* nsplit > 0 (stackAndConstructSplitVector, randomForestSRC.c:14533-14564): with more than nsplit distinct values,
+     nsplit of the D - 1 cut positions are drawn from chain B without replacement (swap-remove over 1..D-1,
+     slot = ceil(ran1B * size)) and evaluated in ascending order; otherwise every position is a cut */
+  char *sel = NULL;
+  if (a->nsplit > 0 && D > a->nsplit) {
+    sel = calloc(D, 1);
+    int *swor = malloc((size_t) D * sizeof(int)); int sz = D - 1;
+    for (int j = 1; j <= sz; j++) swor[j] = j;
+    for (int j = 1; j <= a->nsplit; j++) {
+      int idx = (int) ceil((double) orc_ran1(&c->chainB) * (sz * 1.0));
+      sel[swor[idx] - 1] = 1;
+      swor[idx] = swor[sz]; sz--;
+    }
+    free(swor);
+    c->candidates += a->nsplit;
+  } else {
+    c->candidates += D - 1;
+  }
 
   int K = 1;
   if (rule_stratified(rule)) { K = 0; for (int i = 0; i < m; i++) if (a->strat[rep[i]] > K) K = a->strat[rep[i]]; }
@@ -250,12 +267,14 @@ static int score_covariate(tree_ctx *c, int cov, const int *rep, int m,
 #undef ADD_ROW
   double w = a->split_weight ? a->split_weight[cov] : 1.0;
   for (int g = 0; g < D - 1; g++) {
+    if (sel && !sel[g]) continue;
     double delta = (c->statL[g] + c->statR[g] - statP) * w;
     int flag;
     if (!*have_best) flag = 1;
     else flag = (delta - *best_delta) > 1.0e-9;
     if (flag) { *have_best = 1; *best_delta = delta; *best_cov = cov; *best_cut = c->gval[g]; }
   }
+  free(sel);
   return D;
 }
 

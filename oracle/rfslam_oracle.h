@@ -16,6 +16,7 @@ typedef struct {
   const int    *boot_size;    /* [ntree] or NULL (= n) */
   const double *split_weight; /* [p] or NULL */
   const int    *tree_seeds;   /* [ntree] chain-A seeds (restore) or NULL (grow) */
+  int           nsplit;       /* 0 = every distinct value but the last is a cut; > 0: at most nsplit random cuts per covariate */
 } orc_args;
 
 typedef struct {

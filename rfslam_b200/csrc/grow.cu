@@ -261,7 +261,8 @@ int validate_grow_args(const rfslam_grow_args* a, GrowConfig* cfg) {
   int slot = (int)((a->opt_high & RFSLAM_OPTH_SPLT_CUST) >> 8) + 1;
   int rule = rfslam_b200_rule_of_slot(RFSLAM_CLAS_FAM, slot);
   if (rule < 1) { set_error("custom split slot %d has no device rule (only the six Poisson rules are accelerated; no CPU fallback)", slot); return RFSLAM_ENOSUP; }
-  if (a->nsplit != 0) { set_error("nsplit = %d: random cutpoint subsets are outside the accelerated path (SURVEY 8f-2)", a->nsplit); return RFSLAM_ENOSUP; }
+  if (a->nsplit < 0) { set_error("nsplit = %d must be >= 0 (R/data.utilities.R:483-488)", a->nsplit); return RFSLAM_EINVAL; }
+  cfg->nsplit = a->nsplit;
   if (a->htry != 0) { set_error("htry must be 0 (rf.c:6490-6494)"); return RFSLAM_EINVAL; }
   if (a->mtry < 1 || a->mtry > a->x_size) { set_error("mtry must be in [1, xSize]"); return RFSLAM_EINVAL; }
   if (a->mtry > kMaxCand) { set_error("mtry %d exceeds the %d candidates scored jointly per node", a->mtry, kMaxCand); return RFSLAM_ENOSUP; }
@@ -366,6 +367,11 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     g.pw = (p + 31) / 32; g.ncmax = std::min(cfg.mtry, kMaxCand);
     g.has_sort = ds->max_D > kHistBins;
     g.hbins = ds->hist_bins;
+    g.nsplit = cfg.nsplit;
+    if (cfg.nsplit > 0 && ds->max_D > kHistBins) {
+      set_error("nsplit = %d with a covariate of %d distinct values: random cut subsets are accelerated for covariates of at most %d distinct values", cfg.nsplit, ds->max_D, kHistBins);
+      return RFSLAM_ENOSUP;
+    }
     {   // fixed-point scale of the exposure accumulators: the largest power of two that keeps
         // (bootstrap size) * (max risk time) below 2^62
       int ex = 0;

@@ -61,6 +61,7 @@ struct GrowParams {
   int has_sort;                  // any covariate with D > kHistBins
   int hbins;                     // histogram stride (see GrowSmem::hb)
   double tscale, tinv;           // 2^S and 2^-S of the fixed-point exposure accumulators (see hist_add)
+  int nsplit;                    // > 0: at most nsplit randomly drawn cuts per covariate (rf.c:14533-14564)
 };
 
 struct GrowWork {
@@ -121,6 +122,8 @@ struct GrowShared {
   unsigned long long prof[kProfSlots];
   long long tmark;
   long long sliceStart; int curTree; int fresh;
+  // nsplit > 0: the cuts drawn for each candidate (bit = code), scratch of the draw, cuts per candidate
+  uint32_t cutMask[kMaxCand][8]; uint32_t rankSel[8]; uint8_t swor[256]; int trkCuts[kMaxCand];
 };
 
 #define RF_PROF(slot)                                                                  \
@@ -428,15 +431,18 @@ __device__ inline void track_summary(const NodeCtx& c, int ci) {
   int last = word ? (lane * 32 + 31 - __clz(word)) : -1;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-  if (np < 2) { if (lane == 0) { s->trkNp[ci] = np; s->trkClean[ci] = 1; } return; }
+  if (np < 2) { if (lane == 0) { s->trkNp[ci] = np; s->trkClean[ci] = 1; s->trkCuts[ci] = 0; } return; }
   const int cov = s->candCov[ci];
   const double wgt = c.g.split_weight ? c.g.split_weight[cov] : 1.0;
   const double statP = m.statP[ci];
+  const uint32_t* cm = c.g.nsplit > 0 ? s->cutMask[ci] : nullptr;    // drawn cut subset (nsplit > 0)
+  int ncuts = np - 1;
+  if (cm) ncuts = warp_sum((lane < 8) ? (int)__popc(cm[lane]) : 0);
   double M = -INFINITY; int pos = 0x7fffffff; bool anyNan = false;
 #pragma unroll 1
   for (int ch = 0; ch < nch; ch++) {
     int bin = (ch << 5) + lane;
-    uint32_t wd = m.pres[ci * 8 + ch];
+    uint32_t wd = cm ? cm[ch] : m.pres[ci * 8 + ch];
     bool present = ((wd >> lane) & 1u) && bin != last;
     if (present) {
       double val = (m.sL[ci * m.hb + bin] + m.sR[ci * m.hb + bin] - statP) * wgt;
@@ -456,7 +462,7 @@ __device__ inline void track_summary(const NodeCtx& c, int ci) {
 #pragma unroll 1
     for (int ch = 0; ch <= (pos >> 5); ch++) {
       int bin = (ch << 5) + lane;
-      uint32_t wd = m.pres[ci * 8 + ch];
+      uint32_t wd = cm ? cm[ch] : m.pres[ci * 8 + ch];
       bool present = ((wd >> lane) & 1u) && bin != last && bin < pos;
       if (present && !((M - m.sL[ci * m.hb + bin]) > kEpsilon)) near = true;
     }
@@ -464,6 +470,7 @@ __device__ inline void track_summary(const NodeCtx& c, int ci) {
   }
   if (lane == 0) {
     s->trkNp[ci] = np; s->trkMax[ci] = M; s->trkMaxBin[ci] = pos; s->trkClean[ci] = (!anyNan && !near) ? 1 : 0;
+    s->trkCuts[ci] = ncuts;
     s->trkLast[ci] = last;
   }
 }
@@ -479,10 +486,11 @@ __device__ inline void track_exact(const NodeCtx& c, int ci) {
   const int cov = s->candCov[ci];
   int have = s->have; double best = s->bestDelta; int bestBin = -1;
   int emitted = s->cutsSeen;
+  const uint32_t* cm = c.g.nsplit > 0 ? s->cutMask[ci] : nullptr;
 #pragma unroll 1
   for (int ch = 0; ch < nch; ch++) {
     int bin = (ch << 5) + lane;
-    uint32_t wd = m.pres[ci * 8 + ch];
+    uint32_t wd = cm ? cm[ch] : m.pres[ci * 8 + ch];
     bool present = ((wd >> lane) & 1u) && bin != last;
     double val = present ? m.sL[ci * m.hb + bin] : 0.0;
     if (c.w.sinkDelta) {
@@ -516,7 +524,7 @@ __device__ inline void track_combine_one(const NodeCtx& c, int ci) {
     __syncwarp();
     return;
   }
-  if (lane == 0) s->candCount += (unsigned long long)(np - 1);
+  if (lane == 0) s->candCount += (unsigned long long)s->trkCuts[ci];
   if (s->trkClean[ci] && !c.w.sinkDelta) {
     if (lane == 0) {
       const double M = s->trkMax[ci];
@@ -543,7 +551,7 @@ __device__ inline void track_combine_all(const NodeCtx& c, int nc) {
     const int cov = s->candCov[lane];
     atomicAnd(&s->perm[cov >> 5], ~(1u << (cov & 31)));
   }
-  const int cuts = warp_sum(np >= 2 ? np - 1 : 0);
+  const int cuts = warp_sum((mine && np >= 2) ? s->trkCuts[lane] : 0);
   const double M = mine ? s->trkMax[lane] : 0.0;
   int have = s->have; double best = s->bestDelta; int bc = -1;
 #pragma unroll 1
@@ -1159,6 +1167,92 @@ __device__ inline void draw_candidates(const DevData& d, const GrowParams& g, Gr
   if (lane == 0) s->nc = nd;
 }
 
+// ---- nsplit > 0: the whole CTA draws the node's candidates one at a time ------------------------
+// stackAndConstructSplitVector (rf.c:14533-14564) draws a covariate's cuts from chain B right after the
+// covariate itself, and how many it draws depends on the number of distinct values the covariate has in
+// THIS node (all D - 1 positions when D <= nsplit, else nsplit of them without replacement).  So the
+// chain position of candidate k + 1 is only known once candidate k's values have been looked at: per
+// candidate, one pass of the CTA over the node's entries collects which codes occur, then thread 0 draws
+// the cut ranks (swap-remove over 1..D-1, slot = ceil(ran1B * size)) and turns them into a code mask the
+// tracker uses in place of "every present code but the last".
+__device__ inline void node_prologue_nsplit(const DevData& d, const GrowParams& g, GrowShared* s, GrowSmem& m,
+                                            const uint32_t* list, uint32_t len, uint32_t mInBag) {
+  const int tid = vtid(), lane = lane_id();
+  if (warp_id() == 0) {
+    if (lane == 0) { s->nc = 0; s->have = 0; s->isSmall = 0; s->bestDelta = 0.0; s->bestCand = -1; s->bestCode = 0; s->cutsSeen = 0; }
+    if (lane < 8) s->evMask[lane] = 0u;
+    int size = 0;
+#pragma unroll 1
+    for (int base = 0; base < d.p; base += 32) {
+      const int k = base + lane;
+      const bool ok = k < d.p && ((s->perm[base >> 5] >> lane) & 1u);
+      const unsigned bm = __ballot_sync(0xffffffffu, ok);
+      if (ok) m.pool[size + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)k;
+      size += __popc(bm);
+    }
+    if (lane == 0) s->poolSize = size;
+  }
+  __syncthreads();
+  const int size0 = s->poolSize;
+  const int nd = min(g.mtry, size0);
+#pragma unroll 1
+  for (int k = 0; k < nd; k++) {
+    if (tid == 0) {                                                  // the covariate (rf.c:8378-8381, rf.c:8305-8307)
+      const uint32_t sl = ran1_index(s->rng, (uint32_t)(size0 - k));
+      const int cov = m.pool[sl - 1];
+      m.pool[sl - 1] = m.pool[size0 - 1 - k];
+      const int Dv = d.D[cov];
+      s->candCov[k] = cov; s->candD[k] = Dv; s->candW[k] = d.width[cov]; s->candPtr[k] = d.codes[cov]; s->candHist[k] = Dv <= kHistBins;
+    }
+    if (tid < 8) { m.pres[k * 8 + tid] = 0u; s->cutMask[k][tid] = 0u; s->rankSel[tid] = 0u; }
+    __syncthreads();
+    {                                                                // which codes occur in the node
+      const uint8_t* __restrict__ ptr = (const uint8_t*)s->candPtr[k];
+      uint32_t acc0 = 0u, acc1 = 0u;
+      for (uint32_t i = (uint32_t)tid; i < len; i += kThreads) {
+        const uint32_t code = ptr[list[i] & kRowMask];
+        if (code < 32u) acc0 |= 1u << code;
+        else if (code < 64u) acc1 |= 1u << (code - 32u);
+        else atomicOr(&m.pres[k * 8 + (int)(code >> 5)], 1u << (code & 31u));
+      }
+      acc0 = __reduce_or_sync(0xffffffffu, acc0); acc1 = __reduce_or_sync(0xffffffffu, acc1);
+      if (lane == 0) { if (acc0) atomicOr(&m.pres[k * 8], acc0); if (acc1) atomicOr(&m.pres[k * 8 + 1], acc1); }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int np = 0, last = -1;
+      for (int wq = 0; wq < 8; wq++) { const uint32_t wd = m.pres[k * 8 + wq]; np += __popc(wd); if (wd) last = (wq << 5) + 31 - __clz(wd); }
+      if (np >= 2) {
+        if (np > g.nsplit) {
+          int sz = np - 1;
+          for (int j = 0; j < sz; j++) s->swor[j] = (uint8_t)j;      // ranks 0 .. D-2 of the distinct values (the last is never a cut)
+          for (int j = 0; j < g.nsplit; j++) {
+            const uint32_t idx = ran1_index(s->rng, (uint32_t)sz);
+            const int r = s->swor[idx - 1];
+            s->rankSel[r >> 5] |= 1u << (r & 31);
+            s->swor[idx - 1] = s->swor[sz - 1]; sz--;
+          }
+          int rank = 0;
+          for (int wq = 0; wq < 8; wq++) {
+            uint32_t wd = m.pres[k * 8 + wq], out = 0u;
+            while (wd) {
+              const int b = __ffs(wd) - 1; wd &= wd - 1u;
+              if ((s->rankSel[rank >> 5] >> (rank & 31)) & 1u) out |= 1u << b;
+              rank++;
+            }
+            s->cutMask[k][wq] = out;
+          }
+        } else {
+          for (int wq = 0; wq < 8; wq++) s->cutMask[k][wq] = m.pres[k * 8 + wq];
+          s->cutMask[k][last >> 5] &= ~(1u << (last & 31));
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) { s->nc = nd; s->algoBytes += (unsigned long long)mInBag * (12ull * (unsigned long long)nd + 20ull); }
+}
+
 __device__ inline bool append_record(const GrowWork& w, GrowShared* s, int tree, uint32_t nodeID, uint32_t parm,
                                      uint32_t a, uint32_t b, double stat, uint32_t parentRec, uint32_t* outIdx) {
   uint32_t q = s->nodeCount;
@@ -1306,7 +1400,9 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     // One serial section per node, run by warp 0 between two block barriers: tracker reset, the draws
     // and the candidate metadata (a barrier + phase boundary costs ~1k cycles on a node that has a few
     // dozen rows; there used to be five of them before the first gather).
-    if (warp_id() == 0) {
+    if (g.nsplit > 0 && attempt) {
+      node_prologue_nsplit(d, g, s, m, w.lists + ((size_t)tree * 2 + cur.buf) * n + cur.start, cur.len, cur.m);
+    } else if (warp_id() == 0) {
       const int lane = lane_id();
       if (lane == 0) { s->nc = 0; s->have = 0; s->isSmall = 0; s->bestDelta = 0.0; s->bestCand = -1; s->bestCode = 0; s->cutsSeen = 0; }
       if (lane < 8) s->evMask[lane] = 0u;

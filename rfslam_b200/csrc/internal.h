@@ -84,6 +84,7 @@ struct GrowConfig {
   int rule;            // 1..6
   int mtry, nodesize, nodedepth;
   double alpha;        // 1 / k_for_alpha^2
+  int nsplit;          // 0 = every cut; > 0 = at most nsplit random cuts per covariate
   int ntree;           // forest size (seeds depend on it, rf.c:6677-6692)
   int seed;
   bool by_user;

@@ -41,24 +41,29 @@ GROW_CASES = [
     ("grow_r4_byuser", 1800, 10, 32, 4, 5, 5, None, -99, 13, True),
     ("grow_r4_q256_big", 12000, 20, 256, 4, 4, 20, None, -4242, 14, False),
     ("grow_r1_mtry1", 900, 6, 16, 1, 8, 2, 1, -5, 15, False),
+    # nsplit > 0 (12th field): random cut subsets, rf.c:14533-14564
+    ("grow_r4_q64_nsplit5", 1500, 9, 64, 4, 6, 5, None, -12345, 20260101, False, 5),
+    ("grow_r1_q256_nsplit10", 6000, 12, 256, 1, 4, 10, None, -4242, 16, False, 10),
 ]
 
 
 def main():
-    for (name, n, p, levels, rule, ntree, nodesize, mtry, seed, dseed, byuser) in GROW_CASES:
+    for case in GROW_CASES:
+        (name, n, p, levels, rule, ntree, nodesize, mtry, seed, dseed, byuser) = case[:11]
+        nsplit = case[11] if len(case) > 11 else 0
         d = make_cpiu(n, p, levels=levels, seed=dseed)
         samp = None
         if byuser:
             rng = np.random.default_rng(dseed + 1)
             samp = rng.multinomial(int(0.8 * n), np.full(n, 1.0 / n), size=ntree).astype(np.int32)
         r = rd.grow(d.x, d.y, d.rt, d.strat, rule=rule, ntree=ntree, nodesize=nodesize, mtry=mtry,
-                    seed=seed, samp=samp)
+                    seed=seed, samp=samp, nsplit=nsplit)
         t = canon(r, n)
         dt = make_cpiu(max(200, n // 3), p, levels=levels, seed=dseed + 1000)
         pr = rd.predict(d.x, d.y, t, dt.x, samp=samp, nodesize=nodesize)
         save = dict(
             x=d.x, y=d.y, rt=d.rt, strat=d.strat,
-            params=np.array([n, p, levels, rule, ntree, nodesize, -1 if mtry is None else mtry, seed, dseed, int(byuser)], np.int64),
+            params=np.array([n, p, levels, rule, ntree, nodesize, -1 if mtry is None else mtry, seed, dseed, int(byuser)] + ([nsplit] if nsplit else []), np.int64),
             fx=dt.x, pred_allEnsbCLS=pr["allEnsbCLS"], pred_nodeMembership=pr["nodeMembership"])
         if samp is not None:
             save["samp"] = samp

@@ -27,9 +27,11 @@ def golden_files(golden_dir: str) -> List[str]:
 
 
 def golden_params(g) -> dict:
-    n, p, levels, rule, ntree, nodesize, mtry, seed, dseed, byuser = [int(v) for v in g["params"]]
+    vals = [int(v) for v in g["params"]]
+    n, p, levels, rule, ntree, nodesize, mtry, seed, dseed, byuser = vals[:10]
+    nsplit = vals[10] if len(vals) > 10 else 0
     return dict(n=n, p=p, levels=levels, rule=rule, ntree=ntree, nodesize=nodesize,
-                mtry=None if mtry < 0 else mtry, seed=seed, dseed=dseed, byuser=bool(byuser))
+                mtry=None if mtry < 0 else mtry, seed=seed, dseed=dseed, byuser=bool(byuser), nsplit=nsplit)
 
 
 def split_tree(f: Dict[str, np.ndarray], b: int):

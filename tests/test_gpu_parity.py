@@ -69,7 +69,7 @@ def test_grow_matches_reference_golden(golden_dir, name):
     q = parity.golden_params(g)
     got = rfslam_b200.rfsrc(g["x"], g["y"], g["rt"], g["strat"], splitrule=q["rule"], ntree=q["ntree"],
                             nodesize=q["nodesize"], mtry=q["mtry"], seed=q["seed"], samp=g.get("samp"), membership=True,
-                            member_lists=True)
+                            member_lists=True, nsplit=q["nsplit"])
     parity.assert_forest_equal(got, parity.golden_ref_forest(g), q["n"], q["ntree"], check_membr_lists=True, label=name)
 
 
@@ -148,8 +148,9 @@ def test_unsupported_inputs_fail_loudly():
         rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=2, seed=5)            # seed must be < 0
     with pytest.raises(rfslam_b200.RfslamError):
         rfslam_b200.rfsrc(d.x, d.y + 1.0, d.rt, d.strat, ntree=2)              # response codes outside {1, 2}
+    dc = make_cpiu(2000, 3, levels=0, seed=12)                                   # continuous: > 256 distinct values
     with pytest.raises(rfslam_b200.RfslamError):
-        rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=2, nsplit=3)          # random cut subsets: not accelerated
+        rfslam_b200.rfsrc(dc.x, dc.y, dc.rt, dc.strat, ntree=2, nsplit=3)      # random cut subsets of such a covariate: not accelerated
 
 
 def test_variable_categories_accepted():
@@ -206,3 +207,17 @@ def test_full_size_properties():
             np.testing.assert_array_equal(full_t[k], part_t[k], err_msg=f"tree {b} {k}")
         np.testing.assert_array_equal(full_t["contPT"].view(np.uint64), part_t["contPT"].view(np.uint64))
     ds.close()
+
+
+@pytest.mark.parametrize("rule,n,p,levels,nsplit,nodesize,seed,dseed", [
+    (4, 4000, 9, 64, 5, 5, -12345, 701), (1, 3000, 8, 32, 3, 3, -7, 702), (6, 2500, 12, 256, 10, 5, -99, 703),
+    (2, 3000, 6, 16, 1, 2, -31, 704), (4, 20000, 10, 64, 2, 20, -5, 705)])
+def test_nsplit_random_cut_subsets_match_oracle(rule, n, p, levels, nsplit, nodesize, seed, dseed):
+    # nsplit > 0 (rf.c:14533-14564): cut draws interleave with covariate draws in chain B and depend on the
+    # number of distinct values in the node; the oracle's nsplit is pinned against the live reference (test_oracle)
+    d = make_cpiu(n, p, levels=levels, seed=dseed)
+    ntree = 5
+    got = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, splitrule=rule, ntree=ntree, nodesize=nodesize, seed=seed, nsplit=nsplit, membership=True)
+    want = port.grow(d.x, d.y, d.rt, d.strat, rule=rule, ntree=ntree, nodesize=nodesize, seed=seed, nsplit=nsplit)
+    parity.assert_forest_equal(got, want, d.n, ntree, label=f"nsplit={nsplit}")
+    assert got["split_candidates"] == int(want["candidates"][0])

@@ -21,7 +21,7 @@ def _golden_names():
 def test_port_matches_golden_grow(golden_dir, name):
     g = parity.load_golden(os.path.join(golden_dir, name))
     q = parity.golden_params(g)
-    got = port.grow(g["x"], g["y"], g["rt"], g["strat"], rule=q["rule"], ntree=q["ntree"], nodesize=q["nodesize"],
+    got = port.grow(g["x"], g["y"], g["rt"], g["strat"], rule=q["rule"], ntree=q["ntree"], nodesize=q["nodesize"], nsplit=q["nsplit"],
                     mtry=q["mtry"], seed=q["seed"], samp=g.get("samp"))
     parity.assert_forest_equal(got, parity.golden_ref_forest(g), q["n"], q["ntree"], check_membr_lists=True, label=name)
 
@@ -98,6 +98,23 @@ def test_port_matches_live_reference(rule, n, p, levels, nodesize, seed, dseed):
         t[k] = t[k][order]
     got = port.grow(d.x, d.y, d.rt, d.strat, rule=rule, ntree=ntree, nodesize=nodesize, seed=seed)
     parity.assert_forest_equal(got, t, n, ntree, check_membr_lists=True, label="live")
+
+
+@pytest.mark.skipif(not refdriver.available(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("rule,n,p,levels,nsplit,nodesize,seed,dseed", [
+    (4, 1500, 9, 64, 5, 5, -12345, 105), (1, 2000, 8, 32, 3, 5, -7, 103), (4, 1200, 6, 0, 10, 5, -31, 110),
+    (6, 1800, 10, 16, 1, 5, -99, 101)])
+def test_port_nsplit_matches_live_reference(rule, n, p, levels, nsplit, nodesize, seed, dseed):
+    # random cut subsets (randomForestSRC.c:14533-14564), continuous covariates included
+    d = make_cpiu(n, p, levels=levels, seed=dseed)
+    ntree = 5
+    r = refdriver.grow(d.x, d.y, d.rt, d.strat, rule=rule, ntree=ntree, nodesize=nodesize, seed=seed, nsplit=nsplit)
+    t = refdriver.trim_forest(r, n)
+    order = np.argsort(t["treeID"], kind="stable")
+    for k in ("treeID", "nodeID", "parmID", "contPT", "mwcpSZ"):
+        t[k] = t[k][order]
+    got = port.grow(d.x, d.y, d.rt, d.strat, rule=rule, ntree=ntree, nodesize=nodesize, seed=seed, nsplit=nsplit)
+    parity.assert_forest_equal(got, t, n, ntree, check_membr_lists=True, label=f"live nsplit={nsplit}")
 
 
 @pytest.mark.skipif(not refdriver.available(), reason="oracle/_ref not built (no /root/reference here)")
