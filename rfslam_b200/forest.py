@@ -59,7 +59,7 @@ class _Packed:
 
     def __init__(self, x, y, risk_time, stratifier, *, splitrule, ntree, mtry, nodesize, nodedepth, seed, k_for_alpha,
                  membership, samp, sampsize, split_wt, device, tree_first, tree_step, finalize, nsplit=0, xvar_types=None,
-                 split_stat=False, member_lists=False, var_categories=None, category_weights=None):
+                 split_stat=False, member_lists=False, var_categories=None, category_weights=None, bootstrap=None):
         x = np.ascontiguousarray(x, np.float64)
         assert x.ndim == 2, "x must be [p, n]: p contiguous columns of n (randomForestSRC.c:22190)"
         p, n = x.shape
@@ -90,6 +90,8 @@ class _Packed:
         a.opt_high = 256 * (slot - 1) + (1 << 16)                 # split.cust bits + terminal.qualts (R/utilities.R:403-459)
         if membership:
             a.opt_high |= (1 << 6)                                # R/utilities.R:333-348
+        if bootstrap not in (None, "by.root", "by.user"):
+            raise ValueError(f"bootstrap {bootstrap!r}: only by.root and by.user (samp) are on the accelerated path")
         if samp is not None:
             a.opt_low |= (1 << 19) + (1 << 20)                    # bootstrap = "by.user" (R/utilities.R:43-45)
             k["samp"] = np.ascontiguousarray(samp, np.int32)
@@ -181,12 +183,12 @@ class ResidentCpiu:
 
     def grow(self, *, splitrule="poisson.split4", ntree=500, mtry=None, nodesize=5, nodedepth=-1, seed=-12345,
              k_for_alpha=2.0, membership=False, samp=None, sampsize=None, split_wt=None, tree_first=0, tree_step=0,
-             finalize=True, split_stat=False, member_lists=False) -> Dict[str, np.ndarray]:
+             finalize=True, split_stat=False, member_lists=False, nsplit=0, bootstrap=None) -> Dict[str, np.ndarray]:
         k = self._pk.keep
         pk = _Packed(k["x"], k["y"], k["rt"], k["st"], splitrule=splitrule, ntree=ntree, mtry=mtry, nodesize=nodesize,
                      nodedepth=nodedepth, seed=seed, k_for_alpha=k_for_alpha, membership=membership, samp=samp,
                      sampsize=sampsize, split_wt=split_wt, device=self.device, tree_first=tree_first, tree_step=tree_step,
-                     finalize=finalize, split_stat=split_stat, member_lists=member_lists)
+                     finalize=finalize, split_stat=split_stat, member_lists=member_lists, nsplit=nsplit, bootstrap=bootstrap)
         out = ForestOut()
         capi.check(capi.lib().rfslam_b200_grow_resident(self.handle, C.byref(pk.args), C.byref(out)))
         res = _unpack_forest(out)
@@ -197,17 +199,17 @@ class ResidentCpiu:
 def rfsrc(x, y, risk_time=None, stratifier=None, *, splitrule="poisson.split4", ntree=500, mtry=None, nodesize=5,
           nodedepth=-1, seed=-12345, k_for_alpha=2.0, membership=False, samp=None, sampsize=None, split_wt=None,
           device=-1, tree_first=0, tree_step=0, finalize=True, nsplit=0, xvar_types=None, split_stat=False,
-          member_lists=False, var_categories=None, category_weights=None) -> Dict[str, np.ndarray]:
+          member_lists=False, var_categories=None, category_weights=None, bootstrap=None) -> Dict[str, np.ndarray]:
     """Grow an RF-SLAM forest from HOST arrays through rfslam_b200_grow (upload + grow + download).
 
     x [p, n] float64 (p contiguous columns), y response codes 1.0 / 2.0, risk_time [n], stratifier [n]
     (interval number >= 1); defaults follow R/rfsrc.R:1026-1067 (k_for_alpha = 2, nodedepth unlimited,
-    mtry = ceil(sqrt(p)), bootstrap by.root unless ``samp`` is given)."""
+    mtry = ceil(sqrt(p)), bootstrap by.root unless ``samp`` is given (by.user))."""
     pk = _Packed(x, y, risk_time, stratifier, splitrule=splitrule, ntree=ntree, mtry=mtry, nodesize=nodesize,
                  nodedepth=nodedepth, seed=seed, k_for_alpha=k_for_alpha, membership=membership, samp=samp, sampsize=sampsize,
                  split_wt=split_wt, device=device, tree_first=tree_first, tree_step=tree_step, finalize=finalize, nsplit=nsplit,
                  xvar_types=xvar_types, split_stat=split_stat, member_lists=member_lists, var_categories=var_categories,
-                 category_weights=category_weights)
+                 category_weights=category_weights, bootstrap=bootstrap)
     out = ForestOut()
     capi.check(capi.lib().rfslam_b200_grow(C.byref(pk.args), C.byref(out)))
     res = _unpack_forest(out)
