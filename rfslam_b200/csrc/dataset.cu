@@ -208,6 +208,7 @@ int dataset_build(const rfslam_grow_args* a, rfslam_dataset** out) {
         ds->D[c] = D;
         ds->max_D = std::max(ds->max_D, D);
         if (D <= kHistBins) while (ds->hist_bins < D) ds->hist_bins *= 2;
+        else ds->hist_bins = kHistBins;            // small nodes re-rank such a column locally: up to 256 ranks per node
         double* uniq = dalloc<double>(ds, D);
         ds->uniq_h[c] = uniq;
         if (D <= 256) {

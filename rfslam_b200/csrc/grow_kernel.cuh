@@ -49,7 +49,8 @@ struct NodeEnt {        // a pending node of the DFS
 };
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;
-constexpr int kSmallMax = 512;      // nodes with <= this many entries are scored entirely out of shared memory
+constexpr int kSmallMax = 512;
+constexpr int kLocalMax = 256;      // small nodes up to this many entries also take covariates with > 256 distinct values (local ranks)      // nodes with <= this many entries are scored entirely out of shared memory
 constexpr int kProfSlots = 96;   // 64..79: the phase slots again, restricted to nodes with < 64 entries   // 0..15 phases, 16..47 node time by log2(len), 48..63 node count by log2(len)/2
 
 struct GrowParams {
@@ -124,6 +125,8 @@ struct GrowShared {
   long long sliceStart; int curTree; int fresh;
   // nsplit > 0: the cuts drawn for each candidate (bit = code), scratch of the draw, cuts per candidate
   uint32_t cutMask[kMaxCand][8]; uint32_t rankSel[8]; uint8_t swor[256]; int trkCuts[kMaxCand];
+  uint8_t candLocal[kMaxCand];       // candidate re-ranked locally by this node (its codes in shared memory are node-local ranks)
+  uint32_t bestWide;                 // the winning cut of a locally re-ranked candidate as a table-wide code
 };
 
 #define RF_PROF(slot)                                                                  \
@@ -822,6 +825,58 @@ __device__ inline double stream_stratum(const NodeCtx& c, int ci, int Dc, uint32
   return tP;
 }
 
+// A covariate with more than 256 distinct values in the table has at most len <= kLocalMax of them in a
+// small node: the candidate's warp gathers the node's wide codes (<= 8 per lane), ranks them among the
+// node's distinct values by all-pairs comparison through warp shuffles (len * len / 32 compares), and
+// writes the ranks as the node-local byte codes the rest of the small path works on.  The winning rank is
+// turned back into a table-wide code by the split path (every entry with that rank holds the same code).
+__device__ inline void local_rank_candidate(GrowShared* s, const uint32_t* smEnt, uint8_t* cptr, int ci, uint32_t len) {
+  const int lane = lane_id();
+  const void* ptr = s->candPtr[ci]; const int wd = s->candW[ci];
+  uint32_t wv[kLocalMax / 32];
+#pragma unroll
+  for (int r = 0; r < kLocalMax / 32; r++) {
+    const uint32_t j = (uint32_t)(r * 32 + lane);
+    wv[r] = (j < len) ? load_code(ptr, wd, smEnt[j] & kRowMask) : 0xFFFFFFFFu;
+  }
+  // first[r]: no earlier entry holds the same value; rank[r]: distinct values below mine
+  uint32_t firstMask = 0u;
+  uint32_t rank[kLocalMax / 32];
+#pragma unroll
+  for (int r = 0; r < kLocalMax / 32; r++) rank[r] = 0u;
+  const int nr = (int)((len + 31u) >> 5);
+#pragma unroll
+  for (int rk = 0; rk < kLocalMax / 32; rk++) {
+    if (rk < nr) {
+#pragma unroll 1
+      for (int src = 0; src < 32; src++) {
+        const uint32_t k = (uint32_t)(rk * 32 + src);
+        if (k >= len) break;                                          // warp-uniform
+        const uint32_t wk = __shfl_sync(0xffffffffu, wv[rk], src);
+        // is entry k the first occurrence of its value?  (any earlier entry equal to it)
+        bool dup = false;
+#pragma unroll
+        for (int r = 0; r < kLocalMax / 32; r++) dup |= (wv[r] == wk) && ((uint32_t)(r * 32 + lane) < k);
+        const bool isFirst = !__any_sync(0xffffffffu, dup);
+        if (isFirst) {
+#pragma unroll
+          for (int r = 0; r < kLocalMax / 32; r++) rank[r] += (wk < wv[r]) ? 1u : 0u;
+          if (lane == src) firstMask |= 1u << rk;
+        }
+      }
+    }
+  }
+  int np = __popc(firstMask);
+  np = warp_sum(np);
+#pragma unroll
+  for (int r = 0; r < kLocalMax / 32; r++) {
+    const uint32_t j = (uint32_t)(r * 32 + lane);
+    if (j < len) cptr[j] = (uint8_t)rank[r];
+  }
+  if (lane == 0) { s->candD[ci] = np; s->candHist[ci] = 1; s->candLocal[ci] = 1; }   // node-local cardinality / byte codes from here on
+  __syncwarp();
+}
+
 __device__ inline void small_candidate(const NodeCtx& c, int ci, uint32_t len) {
   GrowSmem& m = c.m;
   GrowShared* s = m.s;
@@ -995,6 +1050,10 @@ __device__ inline void score_small(NodeCtx& c) {
   __syncthreads();
   RF_PROF(3);
   if (tid == 0) s->histDirty = 1;                                    // the candidates keep tables in the large-node histograms
+  if (m.hb >= kLocalMax) {                                          // only tables with a covariate of > 256 distinct values get here
+    for (int ci = wid; ci < nc; ci += kWarps)
+      if (!s->candHist[ci]) local_rank_candidate(s, m.smEnt, m.smCodes + ci * kSmallMax, ci, len);
+  }
   for (int ci = wid; ci < nc; ci += kWarps) small_candidate(c, ci, len);   // the same warp summarises ci next (score_node)
 }
 
@@ -1013,12 +1072,14 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
 
   bool allHist = true;
   for (int ci = 0; ci < nc; ci++) if (!s->candHist[ci]) allHist = false;
-  const bool small = allHist && cur.len <= (uint32_t)kSmallMax;
+  const bool small = (allHist && cur.len <= (uint32_t)kSmallMax) ||
+                     (cur.len <= (uint32_t)kLocalMax && m.hb >= kLocalMax && !w.sinkDelta && g.nsplit == 0);
   bool anyHist = false, anySort = false;
   for (int ci = 0; ci < nc; ci++) { if (s->candHist[ci]) anyHist = true; else anySort = true; }
   if (small) {
     if (tid == 0) s->isSmall = 1;
     score_small(c);
+    anySort = false;                                                 // wide covariates were re-ranked locally (local_rank_candidate)
   } else {
   // segment boundaries of the strata inside this node's (row-sorted) entry list
   if (strat) {
@@ -1426,7 +1487,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
         if (lane < ncd) {                                  // candidate metadata: one parallel round of loads
           const int cov = s->candCov[lane];
           const int Dv = d.D[cov];
-          s->candD[lane] = Dv; s->candW[lane] = d.width[cov]; s->candPtr[lane] = d.codes[cov]; s->candHist[lane] = Dv <= kHistBins;
+          s->candD[lane] = Dv; s->candW[lane] = d.width[cov]; s->candPtr[lane] = d.codes[cov]; s->candHist[lane] = Dv <= kHistBins; s->candLocal[lane] = 0;
         }
       }
     }
@@ -1470,6 +1531,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     const uint32_t* src = w.lists + ((size_t)tree * 2 + cur.buf) * n + cur.start;
     uint32_t* dst = w.lists + ((size_t)tree * 2 + (cur.buf ^ 1u)) * n + cur.start;
     const bool small = s->isSmall != 0;
+    const bool localCut = small && s->candLocal[bc] != 0;
     const uint8_t* cptr = m.smCodes + bc * kSmallMax;
     uint32_t nL; unsigned long long tneL; double trtL = 0.0, trtR = 0.0;
     if (small) {
@@ -1486,6 +1548,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
         if (i < cur.len) {
           en[u] = m.smEnt[i];
           lf[u] = cptr[i] <= bcode;                               // LEFT iff cut - x >= 0 (rf.c:15194)
+          if (localCut && cptr[i] == bcode) s->bestWide = load_code(ptr, wd, en[u] & kRowMask);   // same value from every such entry
           const unsigned long long mult = (en[u] >> kRowBits) + 1u;
           const SmallRec r = m.smRec[i];
           if (lf[u]) my += 1ull | (mult << 16) | (((r.es & 1u) ? mult : 0ull) << 40);
@@ -1571,7 +1634,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     if (warp_id() == 0) {
       if (lane_id() == 0) {
         uint32_t q;
-        append_record(w, s, tree, cur.nodeID, (uint32_t)cov + 1u, bcode, kNone, s->bestDelta, cur.parentRec, &q);
+        append_record(w, s, tree, cur.nodeID, (uint32_t)cov + 1u, localCut ? s->bestWide : bcode, kNone, s->bestDelta, cur.parentRec, &q);
         s->algoBytes += 16ull * (unsigned long long)cur.m;
         if (!s->abort) {
           if (s->sp >= (uint32_t)kStackCap) { atomicExch(w.status, 2); s->abort = 1; }
