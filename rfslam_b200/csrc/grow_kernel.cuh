@@ -31,6 +31,14 @@
 
 namespace rfslam {
 
+// RF_CHECK builds (RFSLAM_NVCC_EXTRA=-DRF_CHECK): device-side sanity checks of the entry lists and the DFS state
+// (compute-sanitizer is not available on the test boxes); a violation prints once and traps.
+#ifdef RF_CHECK
+#define RF_ASSERT(cond, ...) do { if (!(cond)) { printf("RF_CHECK " __VA_ARGS__); __trap(); } } while (0)
+#else
+#define RF_ASSERT(cond, ...) do { } while (0)
+#endif
+
 struct Rec {            // one forest record (pre-order); 16 bytes
   uint32_t nodeID;
   uint32_t parm;        // covariate + 1, 0 = terminal
@@ -1016,6 +1024,7 @@ __device__ inline void score_small(NodeCtx& c) {
     const uint32_t j = j0 + lane;
     const bool valid = j < len;
     const uint32_t ent = valid ? c.list[j] : 0u;
+    RF_ASSERT((ent & kRowMask) < (uint32_t)d.n, "small staging: tree %d entry %u/%u = %08x (start %u buf %u node %u)\n", c.tree, j, len, ent, s->cur.start, s->cur.buf, s->cur.nodeID);
     const uint32_t row = ent & kRowMask, mult = (ent >> kRowBits) + 1u;
     const uint32_t e = d.ev[row];
     const double tv = d.rt[row];
@@ -1125,6 +1134,7 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
       uint32_t entNext = (s0 + tid < s1) ? list[s0 + tid] : 0u;
       for (uint32_t i = s0 + tid; i < s1; i += kThreads) {
         const uint32_t ent = entNext;
+        RF_ASSERT((ent & kRowMask) < (uint32_t)d.n, "large pass: tree %d entry %u = %08x (len %u start %u buf %u)\n", tree, i, ent, cur.len, cur.start, cur.buf);
         if (i + kThreads < s1) entNext = list[i + kThreads];       // software pipelining: next entry's load overlaps this entry's gathers
         const uint32_t row = ent & kRowMask, mult = (ent >> kRowBits) + 1u;
         // issue every gather of this entry before the first shared-memory atomic
@@ -1443,6 +1453,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     __syncthreads();
     if (s->abort) break;
     const NodeEnt cur = s->cur;
+    RF_ASSERT(cur.start + cur.len <= (uint32_t)n && cur.len >= 1u && cur.buf <= 1u && s->sp <= (uint32_t)kStackCap, "node state: tree %d start %u len %u buf %u sp %u nodeID %u\n", tree, cur.start, cur.len, cur.buf, s->sp, cur.nodeID);
     if (w.prof && tid == 0) {
       long long now = clock64();
       if (s->prof[13]) s->prof[16 + s->prof[12]] += (unsigned long long)now - s->prof[13];
