@@ -14,22 +14,26 @@ namespace rfslam {
 
 namespace {
 
+// one visited node = one 16-byte load: cut value, covariate + 1 (0 = terminal), right child (internal) or leaf id (terminal)
+struct __align__(16) PredRec { double cont; uint32_t parm; uint32_t link; };
+
 // one thread per test row; trees are walked in order so the sum is reproducible
 __global__ void predict_kernel(int ntree, int m, const unsigned long long* nodeOff, const unsigned long long* leafOff,
-                               const int32_t* nodeID, const int32_t* parmID, const double* contPT, const uint32_t* right,
-                               const int32_t* tnCLAS, const double* fx, double* ens, uint32_t* den, int32_t* membership) {
+                               const PredRec* __restrict__ rec, const int32_t* tnCLAS, const double* __restrict__ fx,
+                               double* ens, uint32_t* den, int32_t* membership) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   double a1 = 0.0, a2 = 0.0;
   for (int t = 0; t < ntree; t++) {
     const unsigned long long off = nodeOff[t];
     unsigned long long q = off;
-    int pm;
-    while ((pm = parmID[q]) != 0) {
-      double xv = fx[(size_t)(pm - 1) * m + i];
-      q = ((contPT[q] - xv) >= 0.0) ? q + 1 : off + right[q];
+    PredRec r = rec[q];
+    while (r.parm != 0u) {
+      const double xv = fx[(size_t)(r.parm - 1u) * m + i];
+      q = ((r.cont - xv) >= 0.0) ? q + 1 : off + r.link;          // LEFT iff cut - x >= 0 (rf.c:10610)
+      r = rec[q];
     }
-    const int leaf = nodeID[q];
+    const int leaf = (int)r.link;
     const unsigned long long li = leafOff[t] + (unsigned long long)leaf - 1ull;
     const double c1 = (double)tnCLAS[2 * li], c2 = (double)tnCLAS[2 * li + 1];
     const double rc = c1 + c2;
@@ -87,13 +91,15 @@ int predict_forest(const rfslam_predict_args* a, rfslam_predict_out* out) {
   try {
     if (a->device >= 0) RF_CUDA(cudaSetDevice(a->device));
     const size_t NL = (size_t)leafOff[ntree];
-    Buf b_noff, b_loff, b_node, b_parm, b_cont, b_right, b_clas, b_fx, b_ens, b_den, b_memb;
+    Buf b_noff, b_loff, b_rec, b_clas, b_fx, b_ens, b_den, b_memb;
+    std::vector<PredRec> recs((size_t)NN);
+    for (int64_t q = 0; q < NN; q++) {
+      const uint32_t pm = (uint32_t)a->parmID[q];
+      recs[(size_t)q] = PredRec{pm ? a->contPT[q] : 0.0, pm, pm ? right[(size_t)q] : (uint32_t)a->nodeID[q]};
+    }
     RF_CUDA(cudaMemcpy(b_noff.alloc((ntree + 1) * 8), nodeOff.data(), (ntree + 1) * 8, cudaMemcpyHostToDevice));
     RF_CUDA(cudaMemcpy(b_loff.alloc((ntree + 1) * 8), leafOff.data(), (ntree + 1) * 8, cudaMemcpyHostToDevice));
-    RF_CUDA(cudaMemcpy(b_node.alloc(NN * 4), a->nodeID, NN * 4, cudaMemcpyHostToDevice));
-    RF_CUDA(cudaMemcpy(b_parm.alloc(NN * 4), a->parmID, NN * 4, cudaMemcpyHostToDevice));
-    RF_CUDA(cudaMemcpy(b_cont.alloc(NN * 8), a->contPT, NN * 8, cudaMemcpyHostToDevice));
-    RF_CUDA(cudaMemcpy(b_right.alloc(NN * 4), right.data(), NN * 4, cudaMemcpyHostToDevice));
+    RF_CUDA(cudaMemcpy(b_rec.alloc((size_t)NN * sizeof(PredRec)), recs.data(), (size_t)NN * sizeof(PredRec), cudaMemcpyHostToDevice));
     RF_CUDA(cudaMemcpy(b_clas.alloc(NL * 8), a->tnCLAS, NL * 8, cudaMemcpyHostToDevice));
     RF_CUDA(cudaMemcpy(b_fx.alloc((size_t)p * m * 8), a->fx_data, (size_t)p * m * 8, cudaMemcpyHostToDevice));
     b_ens.alloc((size_t)2 * m * 8); b_den.alloc((size_t)m * 4);
@@ -102,8 +108,7 @@ int predict_forest(const rfslam_predict_args* a, rfslam_predict_out* out) {
     RF_CUDA(cudaEventCreate(&e0)); RF_CUDA(cudaEventCreate(&e1));
     RF_CUDA(cudaEventRecord(e0));
     predict_kernel<<<(m + 127) / 128, 128>>>(ntree, m, (const unsigned long long*)b_noff.p, (const unsigned long long*)b_loff.p,
-                                             (const int32_t*)b_node.p, (const int32_t*)b_parm.p, (const double*)b_cont.p,
-                                             (const uint32_t*)b_right.p, (const int32_t*)b_clas.p, (const double*)b_fx.p,
+                                             (const PredRec*)b_rec.p, (const int32_t*)b_clas.p, (const double*)b_fx.p,
                                              (double*)b_ens.p, (uint32_t*)b_den.p, (int32_t*)b_memb.p);
     if (a->finalize_ensembles) finalize_pred_kernel<<<(m + 255) / 256, 256>>>((double*)b_ens.p, (const uint32_t*)b_den.p, m);
     RF_CUDA(cudaEventRecord(e1));
