@@ -52,7 +52,8 @@ typedef struct rfslam_grow_args {
   uint32_t       opt_low;
   uint32_t       opt_high;
   int32_t        split_rule;          /* 16 = custom (rf.h:189) */
-  int32_t        nsplit;              /* 0 = every distinct value is a cut */
+  int32_t        nsplit;              /* 0 = every distinct value but the last is a cut; > 0 = at most nsplit random cuts per covariate
+                                         (rf.c:14533-14564; accelerated for covariates of <= 256 distinct values) */
   int32_t        mtry;
   int32_t        htry;                /* must be 0 (rf.c:6490-6494) */
   int32_t        ytry;

@@ -9,18 +9,23 @@
 //
 // Per attempted node the CTA does (reference functions replaced in brackets):
 //   1. draw <= mtry covariates without replacement          [selectRandomCovariates rf.c:14793]
-//   2. ONE pass over the node's in-bag entries, stratum segment by stratum segment, building
-//      per-(candidate, code) sufficient statistics for all candidates at once in shared memory
-//      [the per-cut regather rf.c:13455-13465 + the O(m) passes of poissonSplitN sc.c:710-747]
-//   3. per stratum: prefix sums over codes, the rule's term at every code where the stratum has
-//      rows, fill-forward, accumulate into per-cut left/right statistics in ascending stratum
-//      order [sc.c:751-764 / sc.c:1262-1290]
-//   4. sequential epsilon-hysteresis tracker over candidates in draw order and cuts in ascending
-//      order, exact and parallel via warp ballots           [updateMaximumSplit rf.c:15471]
-//   5. stable partition of the entry list into the two children [forkAndUpdate rf.c:10568,
+//      (nsplit > 0: candidate by candidate, each followed by its cut draws, rf.c:14533-14564)
+//   2. sufficient statistics of every (candidate, cut):
+//      - node of <= 512 entries (97 % of nodes): the node is staged in shared memory and warp ci scores
+//        candidate ci alone -- rule terms once per row of an event stratum (lane = row) or per cut
+//        (lane = cut) for long strata; covariates with > 256 distinct values are re-ranked locally
+//      - larger node: passes over the entries, up to four strata per pass, per-(candidate, code)
+//        histograms in shared memory with native 32-bit atomics, then per stratum prefix sums over
+//        codes, the rule's term at every code where the stratum has rows, fill-forward
+//      [the per-cut regather rf.c:13455-13465 + the O(m) passes of poissonSplitN sc.c:710-747,
+//       sc.c:751-764 / sc.c:1262-1290]; ascending stratum order as in the reference
+//   3. sequential epsilon-hysteresis tracker over candidates in draw order and cuts in ascending
+//      order, exact and parallel via per-candidate summaries    [updateMaximumSplit rf.c:15471]
+//   4. stable partition of the entry list into the two children [forkAndUpdate rf.c:10568,
 //      rf.c:21653-21663]
-// Covariates with more than 256 distinct values take the sorted-walk path instead of 2-3: the
-// CTA radix-sorts the node's codes in global scratch and walks the sorted order with block scans.
+// Covariates with more than 256 distinct values in nodes above 256 entries take the sorted-walk path:
+// the CTA radix-sorts the node's codes in global scratch and walks the sorted order with block scans.
+// Batches with more trees than resident CTAs are time-sliced (see rfslam_grow_kernel).
 #pragma once
 #include "common.cuh"
 #include "internal.h"
@@ -123,7 +128,6 @@ struct GrowShared {
   uint32_t nodeCount, leafCount, sp;
   unsigned long long candCount, algoBytes;
   int abort;
-  int ptotReady;
   int needSlow; int isSmall; int poolSize; int histDirty;
   // sparse evaluation of small nodes: the rows of the strata that contain events (<= 32), stratum-ascending
   uint32_t evMask[8];                // small nodes: strata that contain events
