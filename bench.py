@@ -277,37 +277,59 @@ def main():
     def e2e_step():
         return rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, splitrule=cfg["rule"], ntree=forest_ntree, nodesize=cfg["nodesize"], seed=cfg["seed"],
                                  k_for_alpha=cfg["k_for_alpha"], device=local, tree_first=rank + 1, tree_step=world, finalize=(world == 1))
+    # No collective inside or after this leg: a device fault in one rank must not hang the others (the
+    # one collective of the path, the ensemble all-reduce, is part of the resident step above).  Ranks
+    # start together, time their own calls, and hand rank 0 their mean through a file; the job's e2e
+    # time is the max over ranks.
     e2e_note = None
+    h2d = d.x.nbytes + d.y.nbytes + d.rt.nbytes + d.strat.nbytes
+    d2h = 0
+    barrier()
     try:
         e2e_times = []
         fe = None
         for it in range(2 + max(1, min(args.steps, 2))):         # two untimed calls: page-locked output blocks and device scratch get recycled from the third on
             fe = None                                            # the caller drops the previous forest before asking for the next
             flush.fill_(1)
-            barrier()
+            torch.cuda.synchronize()
             t0 = time.perf_counter()
             fe = e2e_step()
-            barrier()
+            torch.cuda.synchronize()
             if it > 1:
                 e2e_times.append(time.perf_counter() - t0)
         e2e_s = float(np.mean(e2e_times))
-        h2d = d.x.nbytes + d.y.nbytes + d.rt.nbytes + d.strat.nbytes
         d2h = sum(int(v.nbytes) for v in fe.values() if isinstance(v, np.ndarray))
-    except Exception as e:                                       # a CUDA fault poisons this process: measure the leg in a fresh one
-        if world > 1:
-            raise
-        e2e_note = f"in-process e2e leg failed ({type(e).__name__}: {str(e)[:160]}); measured in a fresh process"
+    except Exception as e:                                       # a CUDA fault poisons this process
+        e2e_s = None
+        e2e_note = f"in-process e2e leg failed on rank {rank} ({type(e).__name__}: {str(e)[:160]})"
         sys.stderr.write("[bench] " + e2e_note + "\n")
-        cmd = [sys.executable, os.path.abspath(__file__), "--e2e-only", "--steps", str(args.steps), "--warmup", str(args.warmup), "--no-cpu-baseline"]
-        if args.rows: cmd += ["--rows", str(args.rows)]
-        if args.trees: cmd += ["--trees", str(args.trees)]
-        outp = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
-        child = json.loads(outp.stdout.strip().split("\n")[-1])
-        e2e_s, h2d, d2h = child["e2e_s"], child["h2d"], child["d2h"]
-    if dist is not None:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        if world == 1:                                           # measure the leg in a fresh process
+            cmd = [sys.executable, os.path.abspath(__file__), "--e2e-only", "--steps", str(args.steps), "--warmup", str(args.warmup), "--no-cpu-baseline"]
+            if args.rows: cmd += ["--rows", str(args.rows)]
+            if args.trees: cmd += ["--trees", str(args.trees)]
+            outp = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+            child = json.loads(outp.stdout.strip().split("\n")[-1])
+            e2e_s, h2d, d2h = child["e2e_s"], child["h2d"], child["d2h"]
+            e2e_note += "; measured in a fresh process"
+    if world > 1:
+        tag = os.environ.get("MASTER_PORT", "0") + "_" + os.environ.get("TORCHELASTIC_RUN_ID", "x")
+        mine = os.path.join("/tmp", f"rfslam_bench_e2e_{tag}_{rank}.json")
+        with open(mine + ".tmp", "w") as fh:
+            json.dump({"e2e_s": e2e_s, "d2h": int(d2h), "note": e2e_note}, fh)
+        os.replace(mine + ".tmp", mine)
+        if rank == 0:
+            got, deadline = {}, time.time() + 900
+            while len(got) < world and time.time() < deadline:
+                for r in range(world):
+                    fn = os.path.join("/tmp", f"rfslam_bench_e2e_{tag}_{r}.json")
+                    if r not in got and os.path.exists(fn):
+                        got[r] = json.load(open(fn)); os.remove(fn)
+                time.sleep(0.05)
+            ok = [v["e2e_s"] for v in got.values() if v.get("e2e_s")]
+            notes = [v["note"] for v in got.values() if v.get("note")] + ([f"{world - len(got)} rank(s) did not report"] if len(got) < world else [])
+            e2e_s = max(ok) if ok else None
+            d2h = max([v["d2h"] for v in got.values()] + [0])
+            e2e_note = "; ".join(notes) if notes else None
 
     trees_total = cfg["ntree"] * world
     peak, peak_src = measured_peak_gbs()
@@ -320,7 +342,8 @@ def main():
         "split_candidates_per_sec": cand_total / step_s,
         "device_ms_per_step": dev_mean, "grow_kernel_ms_per_step": kern_mean, "forest_nodes": nodes_total,
         "clocks": clocks,
-        "e2e": dict({"value": trees_total / e2e_s, "unit": "trees/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s},
+        "e2e": dict({"value": (trees_total / e2e_s) if e2e_s else None, "unit": "trees/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                     "ms_per_step": (1e3 * e2e_s) if e2e_s else None},
                     **({"note": e2e_note} if e2e_note else {})),
         "gpu_launches": int(f["kernel_launches"]) * args.steps,
         "roofline": {"bound": "hbm", "kernel": "rfslam_grow_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -342,9 +365,10 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": "trees/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
     if rank == 0:
         print(json.dumps(line))
+    sys.stdout.flush(); sys.stderr.flush()
+    if dist is not None or e2e_note:
+        os._exit(0)              # no collective teardown: a rank whose context faulted in the e2e leg must not hang the rest
     ds.close()
-    if dist is not None:
-        dist.destroy_process_group()
     return 0
 
 
