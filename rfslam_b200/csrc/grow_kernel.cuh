@@ -1213,17 +1213,17 @@ __device__ inline void draw_candidates(const DevData& d, const GrowParams& g, Gr
     const int idum0 = s->rng.idum;
     const int myIdum = (lane < nd) ? ran1_mulmod(kJump[lane], (uint32_t)idum0) : 0;
     int iy = s->rng.iy, myIy = 0;
+    int ivReg = s->rng.iv[lane];                                                  // the Bays-Durham table, one entry per lane
 #pragma unroll 1
     for (int k = 0; k < nd; k++) {
       const int idk = __shfl_sync(0xffffffffu, myIdum, k);
       const int j = iy / 67108864;
-      const int niy = s->rng.iv[j];
-      __syncwarp();
-      if (lane == 0) s->rng.iv[j] = idk;
-      __syncwarp();
+      const int niy = __shfl_sync(0xffffffffu, ivReg, j);
+      if (lane == j) ivReg = idk;
       iy = niy;
       if (lane == k) myIy = niy;
     }
+    s->rng.iv[lane] = ivReg;
     if (lane == 0) s->rng.iy = iy;
     const int lastIdum = __shfl_sync(0xffffffffu, myIdum, nd - 1);
     if (lane == 0) s->rng.idum = lastIdum;
