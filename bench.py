@@ -49,8 +49,8 @@ def measured_peak_gbs():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
-    def __init__(self, index: int):
-        self.index = index
+    def __init__(self, index):
+        self.index = index                       # one GPU index or a comma-separated list (one sampler for the whole job)
         self.rows = []
         self.proc = None
 
@@ -245,7 +245,8 @@ def main():
     def timed_resident(count, sample_clocks=False):
         dev_ms, kern_ms, walls = [], [], []
         last = None
-        sampler = ClockSampler(local) if sample_clocks else None
+        # one sampler for the whole job (rank 0, all of the job's GPUs): N polling nvidia-smi processes contend on the driver
+        sampler = ClockSampler(",".join(str(i) for i in range(world))) if (sample_clocks and rank == 0) else None
         if sampler:
             sampler.start()
         for _ in range(count):

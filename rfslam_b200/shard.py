@@ -26,21 +26,20 @@ def allreduce_ensembles(f: Dict[str, np.ndarray], *, device=None, group=None) ->
     import torch
     import torch.distributed as dist
     n = f["allEnsbDen"].size
-    num = torch.from_numpy(np.concatenate([f["oobEnsbCLS"], f["allEnsbCLS"]]).astype(np.float64))
-    den = torch.from_numpy(np.concatenate([f["oobEnsbDen"], f["allEnsbDen"]]).astype(np.int64))
-    if device is not None:
-        num, den = num.to(device), den.to(device)
+    dev = device if device is not None else "cpu"
+    # the arrays are page-locked (hostpool.cu): four straight copies, everything else on the device
+    num = torch.cat([torch.from_numpy(np.ascontiguousarray(f[k], np.float64)).to(dev, non_blocking=True) for k in ("oobEnsbCLS", "allEnsbCLS")])
+    den = torch.cat([torch.from_numpy(np.ascontiguousarray(f[k]).view(np.int32)).to(dev, non_blocking=True) for k in ("oobEnsbDen", "allEnsbDen")])
     dist.all_reduce(num, group=group)
     dist.all_reduce(den, group=group)
-    num, den = num.cpu().numpy(), den.cpu().numpy()
     out = dict(f)
     for k, (lo, dlo) in {"oobEnsbCLS": (0, 0), "allEnsbCLS": (2 * n, n)}.items():
-        d = den[dlo:dlo + n].astype(np.float64)
-        v = num[lo:lo + 2 * n].reshape(2, n)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            out[k] = np.where(d > 0, v / np.where(d > 0, d, 1.0), 0.0).reshape(-1)
-    out["oobEnsbDen"] = den[:n].astype(np.uint32)
-    out["allEnsbDen"] = den[n:].astype(np.uint32)
+        d = den[dlo:dlo + n].to(torch.float64)
+        v = num[lo:lo + 2 * n].view(2, n)
+        out[k] = torch.where(d > 0, v / torch.where(d > 0, d, torch.ones_like(d)), torch.zeros_like(v)).reshape(-1).cpu().numpy()
+    den_h = den.cpu().numpy().view(np.uint32)
+    out["oobEnsbDen"] = den_h[:n].copy()
+    out["allEnsbDen"] = den_h[n:].copy()
     return out
 
 
