@@ -93,15 +93,22 @@ int rfslam_b200_grow(const rfslam_grow_args* args, rfslam_forest_out* out) {
   const bool timing = getenv("RFSLAM_TIMING") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t0 = now();
-  rfslam_dataset* ds = nullptr;
-  rc = dataset_build(args, &ds);
-  if (rc) return rc;
-  {   // device scratch of the previous call on this device (several GB of entry lists and stacks):
-      // cudaMalloc / cudaFree of it cost up to 0.6 s per call
+  // device memory of the previous call on this device (several GB of entry lists and stacks, the rank-coded
+  // table): cudaMalloc / cudaFree of it cost up to 0.6 s per call, and contend between the ranks of a node
+  WsPool seed;
+  {
+    int dev = 0;
+    if (args->device >= 0) dev = args->device; else cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lk(g_scratchMu);
-    auto& cache = g_scratch[ds->device];
-    for (auto& b : cache.blks) ds->pool.blks.push_back(b);
-    cache.blks.clear();
+    auto& cache = g_scratch[dev];
+    seed.blks.swap(cache.blks);
+  }
+  rfslam_dataset* ds = nullptr;
+  rc = dataset_build(args, &ds, &seed);
+  if (rc) {                                   // dataset_build released what it had adopted; anything left goes back
+    std::lock_guard<std::mutex> lk(g_scratchMu);
+    for (auto& b : seed.blks) g_scratch[args->device >= 0 ? args->device : 0].blks.push_back(b);
+    return rc;
   }
   const double t1 = now();
   rc = grow_forest(ds, args, out);

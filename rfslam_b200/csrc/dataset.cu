@@ -89,11 +89,13 @@ __global__ void scatter_codes_kernel(const double* sorted, const uint32_t* sorte
   }
 }
 
+// every device array of a dataset comes from its pool: rfslam_b200_grow seeds the pool with the blocks of
+// the previous call (api.cu), so a second call of the same shape makes no cudaMalloc / cudaFree at all
 template <typename T>
 T* dalloc(rfslam_dataset* ds, size_t count, bool resident = true) {
-  void* p = nullptr;
-  RF_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
-  ds->allocs.push_back(p);
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  void* p = ds->pool.get(bytes);
+  if (!p) { set_error("out of device memory (%zu bytes)", bytes); throw CudaFail{RFSLAM_ENOMEM}; }
   if (resident) ds->bytes += (int64_t)(count * sizeof(T));
   return (T*)p;
 }
@@ -108,7 +110,7 @@ void dataset_free(rfslam_dataset* ds) {
   delete ds;
 }
 
-int dataset_build(const rfslam_grow_args* a, rfslam_dataset** out) {
+int dataset_build(const rfslam_grow_args* a, rfslam_dataset** out, WsPool* seed) {
   *out = nullptr;
   const int n = a->observation_size, p = a->x_size;
   if (n < 2 || p < 1) { set_error("observationSize must be >= 2 and xSize >= 1"); return RFSLAM_EINVAL; }
@@ -125,28 +127,22 @@ int dataset_build(const rfslam_grow_args* a, rfslam_dataset** out) {
   try {
     if (a->device >= 0) RF_CUDA(cudaSetDevice(a->device));
     RF_CUDA(cudaGetDevice(&ds->device));
+    if (seed) { for (auto& b : seed->blks) { b.used = false; ds->pool.blks.push_back(b); } seed->blks.clear(); }
     ds->n = n; ds->p = p;
     const int T = 256, G = (n + T - 1) / T;
 
-    int* d_bad = nullptr;
-    RF_CUDA(cudaMalloc(&d_bad, sizeof(int)));
+    int* d_bad = dalloc<int>(ds, 1, false);
     RF_CUDA(cudaMemset(d_bad, 0, sizeof(int)));
 
     // ---- transient buffers -------------------------------------------------------------
-    int32_t* d_strat_in; double *d_col, *d_keys, *d_keys_sorted, *d_y, *d_rt_in;
-    uint32_t *d_iota, *d_rows_sorted, *d_u32a, *d_u32b;
-    RF_CUDA(cudaMalloc(&d_strat_in, (size_t)n * 4));
-    RF_CUDA(cudaMalloc(&d_col, (size_t)n * 8));
-    RF_CUDA(cudaMalloc(&d_keys, (size_t)n * 8));
-    RF_CUDA(cudaMalloc(&d_keys_sorted, (size_t)n * 8));
-    RF_CUDA(cudaMalloc(&d_y, (size_t)n * 8));
-    RF_CUDA(cudaMalloc(&d_rt_in, (size_t)n * 8));
-    RF_CUDA(cudaMalloc(&d_iota, (size_t)n * 4));
-    RF_CUDA(cudaMalloc(&d_rows_sorted, (size_t)n * 4));
-    RF_CUDA(cudaMalloc(&d_u32a, (size_t)n * 4));
-    RF_CUDA(cudaMalloc(&d_u32b, (size_t)n * 4));
+    int32_t* d_strat_in = dalloc<int32_t>(ds, n, false);
+    double* d_col = dalloc<double>(ds, n, false); double* d_keys = dalloc<double>(ds, n, false);
+    double* d_keys_sorted = dalloc<double>(ds, n, false); double* d_y = dalloc<double>(ds, n, false);
+    double* d_rt_in = dalloc<double>(ds, n, false);
+    uint32_t* d_iota = dalloc<uint32_t>(ds, n, false); uint32_t* d_rows_sorted = dalloc<uint32_t>(ds, n, false);
+    uint32_t* d_u32a = dalloc<uint32_t>(ds, n, false); uint32_t* d_u32b = dalloc<uint32_t>(ds, n, false);
     std::vector<void*> transient = {d_strat_in, d_col, d_keys, d_keys_sorted, d_y, d_rt_in, d_iota, d_rows_sorted, d_u32a, d_u32b, d_bad};
-    auto free_transient = [&]() { for (void* q : transient) cudaFree(q); transient.clear(); };
+    auto free_transient = [&]() { RF_CUDA(cudaDeviceSynchronize()); for (void* q : transient) ds->pool.put(q); transient.clear(); };
 
     size_t tmp_bytes = 0, tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, n);
@@ -155,8 +151,7 @@ int dataset_build(const rfslam_grow_args* a, rfslam_dataset** out) {
     tmp_bytes = std::max(tmp_bytes, tb);
     cub::DeviceScan::InclusiveSum(nullptr, tb, (const uint32_t*)nullptr, (uint32_t*)nullptr, n);
     tmp_bytes = std::max(tmp_bytes, tb);
-    void* d_tmp = nullptr;
-    RF_CUDA(cudaMalloc(&d_tmp, tmp_bytes));
+    void* d_tmp = dalloc<unsigned char>(ds, tmp_bytes, false);
     transient.push_back(d_tmp);
 
     try {

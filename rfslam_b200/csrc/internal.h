@@ -93,7 +93,7 @@ struct GrowConfig {
   bool finalize;
 };
 
-int  dataset_build(const rfslam_grow_args* a, rfslam_dataset** out);
+int  dataset_build(const rfslam_grow_args* a, rfslam_dataset** out, WsPool* seed = nullptr);
 void dataset_free(rfslam_dataset* ds);
 int  grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out* out);
 int  predict_forest(const rfslam_predict_args* a, rfslam_predict_out* out);
