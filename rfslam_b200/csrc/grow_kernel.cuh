@@ -1384,11 +1384,13 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
   }
   __syncthreads();
   const int tree = s->curTree;
+  const bool isFresh = s->fresh != 0;
   if (tree < 0) break;
+  __syncthreads();                                                   // every thread holds the pick in registers: the restore below overwrites GrowShared (curTree, fresh included)
   __threadfence();                                                   // acquire: what the previous owner of this tree wrote
   uint32_t* listA = w.lists + (size_t)tree * 2 * n;
   const uint16_t* cnt = w.cnt + (size_t)tree * w.cntStride;
-  if (s->fresh) {
+  if (isFresh) {
   if (tid == 0) {
     for (int k = 0; k < kProfSlots; k++) s->prof[k] = 0;
     s->tmark = clock64();
