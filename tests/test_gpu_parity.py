@@ -221,3 +221,16 @@ def test_nsplit_random_cut_subsets_match_oracle(rule, n, p, levels, nsplit, node
     want = port.grow(d.x, d.y, d.rt, d.strat, rule=rule, ntree=ntree, nodesize=nodesize, seed=seed, nsplit=nsplit)
     parity.assert_forest_equal(got, want, d.n, ntree, label=f"nsplit={nsplit}")
     assert got["split_candidates"] == int(want["candidates"][0])
+
+
+def test_time_slicing_is_stable_over_many_calls(monkeypatch):
+    # regression: resuming a parked tree raced with the pick (a thread could take the "fresh tree" branch
+    # while its CTA restored) -- about one illegal address per 200 sliced calls; tools/slice_stress.py runs more
+    d = make_cpiu(4000, 10, levels=32, seed=23)
+    monkeypatch.setenv("RFSLAM_QUANTUM_MS", "0.02")
+    first = None
+    for rep in range(40):
+        f = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=600, nodesize=3, seed=-4)
+        key = (f["treeID"].size, int(f["parmID"].astype(np.int64).sum()), int(f["tnRCNT"].astype(np.int64).sum()))
+        first = first or key
+        assert key == first, rep
