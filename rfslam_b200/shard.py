@@ -43,6 +43,29 @@ def allreduce_ensembles(f: Dict[str, np.ndarray], *, device=None, group=None) ->
     return out
 
 
+def perf_clas(y: np.ndarray, oob_ens: np.ndarray, oob_den: np.ndarray, ntree: int) -> np.ndarray:
+    """perfClas of a whole forest from its (all-reduced, finalized) OOB ensemble: what rfslam_b200_grow returns
+    when it grows every tree itself (perf_kernel in grow.cu).  [ntree][3], NA_REAL except the last row =
+    misclassification rate over rows with an OOB prediction (randomForestSRC.c:1067-1095, votes as in
+    getMaxVote randomForestSRC.c:1175-1218: class 2 wins a tie) and per class over ALL rows of the class
+    (randomForestSRC.c:1025-1066)."""
+    na = np.array([0x7FF00000000007A2], np.uint64).view(np.float64)[0]
+    out = np.full(ntree * 3, na, np.float64)
+    n = oob_den.size
+    p = np.asarray(oob_ens, np.float64).reshape(2, n)
+    cls = np.asarray(y).astype(np.int64)                     # 1 / 2
+    has = np.asarray(oob_den) != 0
+    vote = np.where(p[0] <= p[1], 2, 1)
+    correct = has & (vote == cls)
+    if has.any():
+        out[-3] = 1.0 - float(correct.sum()) / float(has.sum())
+        for k in (1, 2):
+            cnt = int((cls == k).sum())
+            if cnt:
+                out[-3 + k] = 1.0 - float((correct & (cls == k)).sum()) / float(cnt)
+    return out
+
+
 def gather_forest(f: Dict[str, np.ndarray], *, dst: int = 0, group=None) -> Optional[Dict[str, np.ndarray]]:
     """Gather the shards' forest records to rank `dst` and put the trees in ascending treeID order
     (records of one tree stay contiguous and in pre-order, randomForestSRC.c:10735-10806)."""

@@ -50,6 +50,9 @@ def _worker(rank, world, portno, q):
     merged = shard.allreduce_ensembles(part)
     forest = shard.gather_forest(part, dst=0)
     ok = np.allclose(merged["allEnsbCLS"], full["allEnsbCLS"], rtol=1e-12) and np.allclose(merged["oobEnsbCLS"], full["oobEnsbCLS"], rtol=1e-12)
+    # the forest's perfClas from the reduced ensemble = the oracle's (and the reference's) on the unsharded forest
+    perf = shard.perf_clas(d.y, merged["oobEnsbCLS"], merged["oobEnsbDen"], ntree)
+    ok = ok and np.array_equal(perf.view(np.uint64), full["perfClas"].view(np.uint64))
     if rank == 0:
         for k in shard.FOREST_KEYS + shard.LEAF_KEYS + ("leafCount", "seed"):
             a, b = forest[k], full[k]
