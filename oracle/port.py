@@ -72,7 +72,7 @@ def _arr(ptr, n, dtype):
 
 
 def grow(x, y, rt, strat, *, rule=4, ntree=4, mtry=None, nodesize=5, nodedepth=-1, seed=-12345,
-         k_for_alpha=2.0, samp=None, split_weight=None, tree_seeds=None, nsplit=0) -> Dict[str, np.ndarray]:
+         k_for_alpha=2.0, samp=None, split_weight=None, tree_seeds=None, nsplit=0, sampsize=None) -> Dict[str, np.ndarray]:
     L = lib()
     p, n = x.shape
     x = np.ascontiguousarray(x, np.float64); y = np.ascontiguousarray(y, np.float64)
@@ -89,6 +89,9 @@ def grow(x, y, rt, strat, *, rule=4, ntree=4, mtry=None, nodesize=5, nodedepth=-
     if samp is not None:
         samp = np.ascontiguousarray(samp, np.int32); keep.append(samp)
         a.samp = _ip(samp); a.max_boot = int(samp.sum(axis=1).max())
+    if sampsize is not None and samp is None:
+        bs = np.full(ntree, int(sampsize), np.int32); keep.append(bs)
+        a.boot_size = _ip(bs); a.max_boot = int(sampsize)
     if split_weight is not None:
         sw = np.ascontiguousarray(split_weight, np.float64); keep.append(sw); a.split_weight = _dp(sw)
     if tree_seeds is not None:

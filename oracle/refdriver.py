@@ -131,11 +131,16 @@ def grow(x: np.ndarray, y: np.ndarray, risk_time: np.ndarray, stratifier: np.nda
          membership: bool = True, nthreads: int = -1, samp: Optional[np.ndarray] = None,
          nsplit: int = 0, split_weight: Optional[np.ndarray] = None,
          xtype: Optional[Sequence[str]] = None, xlevels: Optional[np.ndarray] = None,
-         var_categories: Optional[np.ndarray] = None, category_weights: Optional[np.ndarray] = None
-         ) -> Dict[str, np.ndarray]:
+         var_categories: Optional[np.ndarray] = None, category_weights: Optional[np.ndarray] = None,
+         statistics: bool = False, sampsize: Optional[int] = None) -> Dict[str, np.ndarray]:
     """Run the reference's rfsrcGrow.  ``x`` is [p, n] float64 (p contiguous columns of n), ``y``
     the response codes in {1.0, 2.0}.  ``samp`` ([ntree, n] int32 in-bag counts) selects
-    bootstrap="by.user" (R/utilities.R:43-45 -> bits 2^19+2^20)."""
+    bootstrap="by.user" (R/utilities.R:43-45 -> bits 2^19+2^20).  ``statistics`` sets OPT_NODE_STAT
+    (randomForestSRC.h:133, R statistics = TRUE): per node the covariates tried and the best statistic of
+    each come back as ``mtryID`` / ``mtryST`` [node][mtry] (randomForestSRC.c:15553-15575; ``spltST`` itself is
+    never filled on the custom-rule path of this fork).  They are appended under their own critical section
+    (randomForestSRC.c:20948-20962), so they line up with ``treeID`` only when ``nthreads == 1``;
+    trim_forest() turns them into ``splitStat`` = the statistic of the covariate the node split on."""
     L = lib()
     p, n = x.shape
     x = np.ascontiguousarray(x, dtype=np.float64)
@@ -146,6 +151,9 @@ def grow(x: np.ndarray, y: np.ndarray, risk_time: np.ndarray, stratifier: np.nda
     opt_high = 256 * (split_slot(rule) - 1) + (1 << 16)
     if membership:
         opt_high += (1 << 6)
+    if statistics:
+        assert nthreads == 1, "spltST is only in tree order with one thread"
+        opt_low += 0x08000000
     if samp is not None:
         opt_low += (1 << 19) + (1 << 20)
         samp = np.ascontiguousarray(samp, dtype=np.int32)
@@ -154,8 +162,8 @@ def grow(x: np.ndarray, y: np.ndarray, risk_time: np.ndarray, stratifier: np.nda
         max_boot = int(boot_sizes.max())
         samp_arg = P.i_alias(samp.reshape(-1))
     else:
-        boot_sizes = np.full(ntree, n, np.int32)
-        max_boot = n
+        boot_sizes = np.full(ntree, n if sampsize is None else int(sampsize), np.int32)
+        max_boot = int(boot_sizes.max())
         samp_arg = P.i(np.zeros(0, np.int32))
     if xtype is None:
         xtype = ["R"] * p
@@ -208,6 +216,15 @@ def trim_forest(res: Dict[str, np.ndarray], n: int) -> Dict[str, np.ndarray]:
     out = dict(res)
     for k in ("treeID", "nodeID", "parmID", "contPT", "mwcpSZ"):
         out[k] = res[k][:total]
+    if "mtryST" in res and res["mtryST"].size:
+        mtry = res["mtryST"].size // res["spltST"].size
+        ids = res["mtryID"].reshape(-1, mtry)[:total]
+        st = res["mtryST"].reshape(-1, mtry)[:total]
+        hit = ids == out["parmID"][:, None]
+        stat = np.full(total, np.nan)
+        rows = hit.any(axis=1) & (out["parmID"] > 0)
+        stat[rows] = st[rows, hit[rows].argmax(axis=1)]
+        out["splitStat"] = stat
     stride = int(res["_maxBootstrapSize"][0]) - 2 * (int(res["_nodesize"][0]) - 1)
     for k in ("tnRCNT", "tnACNT"):
         if k in res:

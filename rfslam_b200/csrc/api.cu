@@ -26,8 +26,10 @@ void set_error(const char* fmt, ...) {
 // registrations of sc.c:47-62 (poissonSplitN in CLAS_FAM slot N+1)
 static int g_rule_table[4][16];
 static bool g_rule_init = false;
+static std::mutex g_ruleMu;                   // the registry may be read by concurrent grow calls
 
 static void ensure_defaults() {
+  std::lock_guard<std::mutex> lk(g_ruleMu);
   if (!g_rule_init) {
     memset(g_rule_table, 0, sizeof g_rule_table);
     for (int r = 1; r <= 6; r++) g_rule_table[RFSLAM_CLAS_FAM][r] = r;      // slot r+1 -> index r
@@ -53,20 +55,21 @@ int rfslam_b200_device_count(void) {
   return n;
 }
 
-void rfslam_b200_register_defaults(void) { g_rule_init = false; ensure_defaults(); }
+void rfslam_b200_register_defaults(void) { { std::lock_guard<std::mutex> lk(g_ruleMu); g_rule_init = false; } ensure_defaults(); }
 
 int rfslam_b200_register_this(int rule, int family, int slot) {
   ensure_defaults();
   if (family < 0 || family > 3 || slot < 1 || slot > 16) { set_error("family must be 0..3 and slot 1..16 (rf.c:8856-8866)"); return RFSLAM_EINVAL; }
   if (rule < 0 || rule > 6) { set_error("only the six Poisson rules have device implementations"); return RFSLAM_ENOSUP; }
   if (rule != 0 && family != RFSLAM_CLAS_FAM) { set_error("the Poisson rules are classification-family rules (sc.c:47-62)"); return RFSLAM_ENOSUP; }
-  g_rule_table[family][slot - 1] = rule;
+  { std::lock_guard<std::mutex> lk(g_ruleMu); g_rule_table[family][slot - 1] = rule; }
   return RFSLAM_OK;
 }
 
 int rfslam_b200_rule_of_slot(int family, int slot) {
   ensure_defaults();
   if (family < 0 || family > 3 || slot < 1 || slot > 16) return 0;
+  std::lock_guard<std::mutex> lk(g_ruleMu);
   return g_rule_table[family][slot - 1];
 }
 
@@ -96,8 +99,8 @@ int rfslam_b200_grow(const rfslam_grow_args* args, rfslam_forest_out* out) {
   // device memory of the previous call on this device (several GB of entry lists and stacks, the rank-coded
   // table): cudaMalloc / cudaFree of it cost up to 0.6 s per call, and contend between the ranks of a node
   WsPool seed;
+  int dev = 0;
   {
-    int dev = 0;
     if (args->device >= 0) dev = args->device; else cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lk(g_scratchMu);
     auto& cache = g_scratch[dev];
@@ -107,7 +110,7 @@ int rfslam_b200_grow(const rfslam_grow_args* args, rfslam_forest_out* out) {
   rc = dataset_build(args, &ds, &seed);
   if (rc) {                                   // dataset_build released what it had adopted; anything left goes back
     std::lock_guard<std::mutex> lk(g_scratchMu);
-    for (auto& b : seed.blks) g_scratch[args->device >= 0 ? args->device : 0].blks.push_back(b);
+    for (auto& b : seed.blks) g_scratch[dev].blks.push_back(b);      // back to the device they were taken from
     return rc;
   }
   const double t1 = now();

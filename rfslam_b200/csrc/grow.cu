@@ -392,19 +392,27 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     RF_CUDA(cudaFuncSetAttribute(rfslam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int residentCtas = 0; long long quantumCycles = 0;
     {
-      int perSm = 0, dev = 0; cudaDeviceProp prop;
+      int perSm = 0, dev = 0, sms = 0, khz = 0;
       RF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, rfslam_grow_kernel, kThreads, smem));
-      RF_CUDA(cudaGetDevice(&dev)); RF_CUDA(cudaGetDeviceProperties(&prop, dev));
-      residentCtas = std::max(1, perSm) * prop.multiProcessorCount;
+      RF_CUDA(cudaGetDevice(&dev));
+      RF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      RF_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));                  // kHz = cycles per ms
+      residentCtas = std::max(1, perSm) * sms;
       const char* q = getenv("RFSLAM_QUANTUM_MS");
-      quantumCycles = (long long)((q ? atof(q) : 10.0) * (double)prop.clockRate);      // clockRate is in kHz = cycles per ms
+      quantumCycles = (long long)((q ? atof(q) : 10.0) * (double)khz);
     }
 
     // ---- batch size from free memory ----
     size_t freeB = 0, totalB = 0;
     RF_CUDA(cudaMemGetInfo(&freeB, &totalB));
     freeB += pool->idle_bytes();
-    const size_t perTree = (size_t)n * (8 + 2 + (g.has_sort ? 16 : 0)) + (cfg.by_user ? 0 : (size_t)maxBoot * 4)
+    // entries of a tree: a row drawn c times folds into ceil(c / kMaxMult) <= 1 + c / kMaxMult entries
+    const size_t listStride = (size_t)std::min(n, maxBoot) + (size_t)maxBoot / kMaxMult + 1;
+    if (!cfg.by_user && maxBoot > 65535) {                         // u16 in-bag counts: refuse samples under which a row could plausibly exceed them
+      const double mean = (double)maxBoot / (double)n;
+      if (mean + 12.0 * sqrt(mean) + 50.0 > 65535.0) { set_error("sampsize %d over %d rows would overflow the 16-bit in-bag counts", maxBoot, n); return RFSLAM_ENOSUP; }
+    }
+    const size_t perTree = listStride * (8 + (g.has_sort ? 16 : 0)) + (size_t)n * 2 + (cfg.by_user ? 0 : (size_t)maxBoot * 4)
                          + (size_t)kStackCap * (sizeof(NodeEnt) + (size_t)g.pw * 4) + 4096;
     const size_t worstNodes = 2ull * (size_t)std::min(n, maxBoot) + 1;
     size_t estNodes = std::min<size_t>(worstNodes, 4ull * (size_t)maxBoot / (size_t)std::max(1, cfg.nodesize) + 256);
@@ -430,11 +438,17 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     std::vector<int32_t> h_leafCount(T), h_seed(T);
     long long totalCand = 0, totalAlgo = 0, launches = 0;
     float growMs = 0.f, totalMs = 0.f;
-    cudaEvent_t ev0, ev1, ev2, ev3, evC;
-    RF_CUDA(cudaEventCreate(&ev0)); RF_CUDA(cudaEventCreate(&ev1)); RF_CUDA(cudaEventCreate(&ev2)); RF_CUDA(cudaEventCreate(&ev3));
-    RF_CUDA(cudaEventCreateWithFlags(&evC, cudaEventDisableTiming));
-    cudaStream_t copyStream;                                     // forest records go home while the traversal kernel runs
-    RF_CUDA(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
+    // events and the copy stream are released on every exit path; the stream is drained first, so no copy can
+    // still target a page-locked output block when the HostOut destructors (declared above) hand it back
+    struct Sync {
+      cudaEvent_t e[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; cudaStream_t st = nullptr;
+      ~Sync() { if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); } for (auto x : e) if (x) cudaEventDestroy(x); }
+    } sync;
+    for (int k = 0; k < 4; k++) RF_CUDA(cudaEventCreate(&sync.e[k]));
+    RF_CUDA(cudaEventCreateWithFlags(&sync.e[4], cudaEventDisableTiming));
+    RF_CUDA(cudaStreamCreateWithFlags(&sync.st, cudaStreamNonBlocking));   // forest records go home while the traversal kernel runs
+    cudaEvent_t ev0 = sync.e[0], ev1 = sync.e[1], ev2 = sync.e[2], ev3 = sync.e[3], evC = sync.e[4];
+    cudaStream_t copyStream = sync.st;
     const bool wantStat = a->want_split_stat != 0;
 
     // ---- per-batch buffers ----
@@ -443,8 +457,8 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     DevBuf<unsigned long long> d_cand(pool), d_algo(pool), d_nodeOff(pool), d_leafOff(pool);
     DevBuf<int32_t> d_samp(pool);
     const size_t cntStride = ((size_t)n + 1) & ~(size_t)1;         // u16 count rows stay 4-byte aligned
-    d_lists.alloc((size_t)B * 2 * n);
-    if (g.has_sort) d_sort.alloc((size_t)B * 4 * n);
+    d_lists.alloc((size_t)B * 2 * listStride);
+    if (g.has_sort) d_sort.alloc((size_t)B * 4 * listStride);
     if (!cfg.by_user) d_draws.alloc((size_t)B * maxBoot); else d_samp.alloc(n);
     d_cnt.alloc((size_t)B * cntStride);
     d_stack.alloc((size_t)B * kStackCap); d_stackPerm.alloc((size_t)B * kStackCap * g.pw);
@@ -494,7 +508,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         // K2: grow
         RF_CUDA(cudaMemsetAsync(d_cursor.p, 0, 4)); RF_CUDA(cudaMemsetAsync(d_status.p, 0, 4));
         GrowWork w{};
-        w.ntrees = nb; w.seedB = d_seedB.p; w.bootSize = d_boot.p; w.lists = d_lists.p; w.cnt = d_cnt.p; w.cntStride = cntStride;
+        w.ntrees = nb; w.seedB = d_seedB.p; w.bootSize = d_boot.p; w.lists = d_lists.p; w.listStride = listStride; w.cnt = d_cnt.p; w.cntStride = cntStride;
         w.sortbuf = g.has_sort ? d_sort.p : nullptr; w.stack = d_stack.p; w.stackPerm = d_stackPerm.p;
         w.pool = d_pool.p; w.statPool = d_statPool.p; w.poolChunks = (uint32_t)poolChunks; w.poolCursor = d_cursor.p;
         w.ctab = d_ctab.p; w.maxChunksPerTree = maxChunksPerTree; w.nodeCount = d_nodeCount.p; w.leafCount = d_leafCount.p;
@@ -646,8 +660,6 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         if (acc[1]) last[2] = 1.0 - (double)acc[4] / (double)acc[1];
       }
     }
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2); cudaEventDestroy(ev3); cudaEventDestroy(evC);
-    cudaStreamDestroy(copyStream);
     unsigned long long pathSum = 0;
     RF_CUDA(cudaMemcpy(&pathSum, d_pathSum.p, 8, cudaMemcpyDeviceToHost));
     totalAlgo += 16ll * (long long)pathSum;                      // B_part's all-row term
@@ -723,7 +735,7 @@ int score_node_impl(int rule, double k_for_alpha, int m, const double* x, const 
     RF_CUDA(cudaMemcpy(d_boot.p, &bs, 4, cudaMemcpyHostToDevice));
     d_cursor.zero(); d_status.zero(); d_sinkCount.zero();
     GrowWork w{};
-    w.ntrees = 1; w.seedB = d_seedB.p; w.bootSize = d_boot.p; w.lists = d_lists.p; w.cnt = d_cnt.p; w.cntStride = cntStride;
+    w.ntrees = 1; w.seedB = d_seedB.p; w.bootSize = d_boot.p; w.lists = d_lists.p; w.listStride = (size_t)n; w.cnt = d_cnt.p; w.cntStride = cntStride;
     w.sortbuf = g.has_sort ? d_sort.p : nullptr; w.stack = d_stack.p; w.stackPerm = d_stackPerm.p;
     w.pool = d_pool.p; w.statPool = d_statPool.p; w.poolChunks = 2; w.poolCursor = d_cursor.p; w.ctab = d_ctab.p; w.maxChunksPerTree = 4;
     w.nodeCount = d_nodeCount.p; w.leafCount = d_leafCount.p; w.candCount = d_cand.p; w.algoBytes = d_algo.p; w.status = d_status.p;

@@ -82,10 +82,11 @@ struct GrowWork {
   int ntrees;
   const int* seedB;              // [ntrees]
   const int* bootSize;           // [ntrees] sum of in-bag counts
-  uint32_t* lists;               // [ntrees][2][n]
+  uint32_t* lists;               // [ntrees][2][listStride]
+  size_t listStride;             // entries a tree can hold: min(n, bootstrap size) + bootstrap size / kMaxMult + 1
   const uint16_t* cnt;           // [ntrees][cntStride] in-bag count per internal row
   size_t cntStride;
-  uint32_t* sortbuf;             // [ntrees][4][n] or nullptr
+  uint32_t* sortbuf;             // [ntrees][4][listStride] or nullptr
   NodeEnt* stack;                // [ntrees][kStackCap]
   uint32_t* stackPerm;           // [ntrees][kStackCap][pw]
   Rec* pool; double* statPool;   // [poolChunks * kRecChunk]
@@ -655,7 +656,7 @@ __device__ inline void sort_candidate(const NodeCtx& c, int ci, uint32_t len) {
   GrowSmem& m = c.m;
   GrowShared* s = m.s;
   const int tid = vtid(), lane = lane_id(), wid = warp_id();
-  const int n = c.d.n;
+  const size_t n = c.w.listStride;
   uint32_t* kA = c.w.sortbuf + (size_t)c.tree * 4 * n;
   uint32_t* kB = kA + n; uint32_t* vA = kB + n; uint32_t* vB = vA + n;
   const void* ptr = s->candPtr[ci]; const int wd = s->candW[ci]; const int Dc = s->candD[ci]; const int cov = s->candCov[ci];
@@ -1076,7 +1077,7 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
   const int tid = vtid();
   const int nc = s->nc;
   const NodeEnt cur = s->cur;
-  const uint32_t* list = w.lists + ((size_t)tree * 2 + cur.buf) * d.n + cur.start;
+  const uint32_t* list = w.lists + ((size_t)tree * 2 + cur.buf) * w.listStride + cur.start;
   const bool bayes = rule_is_bayes(g.rule), unit = rule_unit_time(g.rule), strat = rule_is_stratified(g.rule);
   double beta = 0.0;
   if (bayes) beta = g.alpha / (((double)cur.m + (double)cur.E) / cur.rtsum);
@@ -1388,7 +1389,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
   if (tree < 0) break;
   __syncthreads();                                                   // every thread holds the pick in registers: the restore below overwrites GrowShared (curTree, fresh included)
   __threadfence();                                                   // acquire: what the previous owner of this tree wrote
-  uint32_t* listA = w.lists + (size_t)tree * 2 * n;
+  uint32_t* listA = w.lists + (size_t)tree * 2 * w.listStride;
   const uint16_t* cnt = w.cnt + (size_t)tree * w.cntStride;
   if (isFresh) {
   if (tid == 0) {
@@ -1459,7 +1460,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     __syncthreads();
     if (s->abort) break;
     const NodeEnt cur = s->cur;
-    RF_ASSERT(cur.start + cur.len <= (uint32_t)n && cur.len >= 1u && cur.buf <= 1u && s->sp <= (uint32_t)kStackCap, "node state: tree %d start %u len %u buf %u sp %u nodeID %u\n", tree, cur.start, cur.len, cur.buf, s->sp, cur.nodeID);
+    RF_ASSERT((size_t)cur.start + cur.len <= w.listStride && cur.len >= 1u && cur.buf <= 1u && s->sp <= (uint32_t)kStackCap, "node state: tree %d start %u len %u buf %u sp %u nodeID %u\n", tree, cur.start, cur.len, cur.buf, s->sp, cur.nodeID);
     if (w.prof && tid == 0) {
       long long now = clock64();
       if (s->prof[13]) s->prof[16 + s->prof[12]] += (unsigned long long)now - s->prof[13];
@@ -1479,7 +1480,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     // and the candidate metadata (a barrier + phase boundary costs ~1k cycles on a node that has a few
     // dozen rows; there used to be five of them before the first gather).
     if (g.nsplit > 0 && attempt) {
-      node_prologue_nsplit(d, g, s, m, w.lists + ((size_t)tree * 2 + cur.buf) * n + cur.start, cur.len, cur.m);
+      node_prologue_nsplit(d, g, s, m, w.lists + ((size_t)tree * 2 + cur.buf) * w.listStride + cur.start, cur.len, cur.m);
     } else if (warp_id() == 0) {
       const int lane = lane_id();
       if (lane == 0) { s->nc = 0; s->have = 0; s->isSmall = 0; s->bestDelta = 0.0; s->bestCand = -1; s->bestCode = 0; s->cutsSeen = 0; }
@@ -1545,8 +1546,8 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     const int bc = s->bestCand;
     const uint32_t bcode = s->bestCode;
     const void* ptr = s->candPtr[bc]; const int wd = s->candW[bc]; const int cov = s->candCov[bc];
-    const uint32_t* src = w.lists + ((size_t)tree * 2 + cur.buf) * n + cur.start;
-    uint32_t* dst = w.lists + ((size_t)tree * 2 + (cur.buf ^ 1u)) * n + cur.start;
+    const uint32_t* src = w.lists + ((size_t)tree * 2 + cur.buf) * w.listStride + cur.start;
+    uint32_t* dst = w.lists + ((size_t)tree * 2 + (cur.buf ^ 1u)) * w.listStride + cur.start;
     const bool small = s->isSmall != 0;
     const bool localCut = small && s->candLocal[bc] != 0;
     const uint8_t* cptr = m.smCodes + bc * kSmallMax;

@@ -83,6 +83,12 @@ class _Packed:
             catw=np.array([1.0]) if category_weights is None else np.ascontiguousarray(category_weights, np.float64), tofix=np.zeros(1, np.int32), cw=np.ones(n), yw=np.array([1.0]),
             xw=np.ones(p), sw=np.ascontiguousarray(np.ones(p) if split_wt is None else split_wt, np.float64))
         k = self.keep
+        # the C side reads n (per row) / p (per covariate) elements from each of these: check before it does
+        for name, want in (("y", n), ("rt", n), ("st", n), ("cat", p), ("sw", p)):
+            if k[name].shape != (want,):
+                raise ValueError(f"{name}: expected {want} elements for x of shape [p={p}, n={n}], got shape {k[name].shape}")
+        if k["catw"].ndim != 1 or k["catw"].size < int(k["cat"].max()):
+            raise ValueError("category_weights must hold one weight per variable category")
         a = GrowArgs()
         a.trace_flag = 0
         a.seed = int(seed)
@@ -127,7 +133,7 @@ class _Packed:
         self.n, self.p = n, p
 
 
-def _unpack_forest(o: ForestOut) -> Dict[str, np.ndarray]:
+def _unpack_forest(o: ForestOut, finalized: bool = True) -> Dict[str, np.ndarray]:
     n, T, NN, NL = o.n, o.ntree, o.total_nodes, o.total_leaves
     res = {
         "tree_ids": _own(o, "tree_ids", T, np.int32),
@@ -142,6 +148,7 @@ def _unpack_forest(o: ForestOut) -> Dict[str, np.ndarray]:
         "split_candidates": int(o.split_candidates), "algorithmic_bytes": int(o.algorithmic_bytes),
         "grow_kernel_ms": float(o.grow_kernel_ms), "total_device_ms": float(o.total_device_ms),
         "kernel_launches": int(o.kernel_launches),
+        "finalized": bool(finalized),             # False: oob/allEnsbCLS are the shard's sums (see shard.allreduce_ensembles)
     }
     if o.rmbrMembership:
         res["rmbrMembership"] = _own(o, "rmbrMembership", T * int(o.rmbr_stride), np.int32)
@@ -191,7 +198,7 @@ class ResidentCpiu:
                      finalize=finalize, split_stat=split_stat, member_lists=member_lists, nsplit=nsplit, bootstrap=bootstrap)
         out = ForestOut()
         capi.check(capi.lib().rfslam_b200_grow_resident(self.handle, C.byref(pk.args), C.byref(out)))
-        res = _unpack_forest(out)
+        res = _unpack_forest(out, finalize)
         capi.lib().rfslam_b200_free_forest(C.byref(out))
         return res
 
@@ -212,7 +219,7 @@ def rfsrc(x, y, risk_time=None, stratifier=None, *, splitrule="poisson.split4", 
                  category_weights=category_weights, bootstrap=bootstrap)
     out = ForestOut()
     capi.check(capi.lib().rfslam_b200_grow(C.byref(pk.args), C.byref(out)))
-    res = _unpack_forest(out)
+    res = _unpack_forest(out, finalize)
     capi.lib().rfslam_b200_free_forest(C.byref(out))
     return res
 

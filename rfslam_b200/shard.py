@@ -25,6 +25,8 @@ def allreduce_ensembles(f: Dict[str, np.ndarray], *, device=None, group=None) ->
     numerator / denominator where the denominator is non-zero, 0 otherwise)."""
     import torch
     import torch.distributed as dist
+    if f.get("finalized", False):
+        raise ValueError("allreduce_ensembles needs the shards' SUMS: grow them with finalize=False")
     n = f["allEnsbDen"].size
     dev = device if device is not None else "cpu"
     # the arrays are page-locked (hostpool.cu): four straight copies, everything else on the device

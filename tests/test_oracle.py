@@ -133,3 +133,91 @@ def test_reference_variable_categories_do_not_change_the_draws():
             np.testing.assert_array_equal(ta[k]["parmID"], tb[k]["parmID"])
             np.testing.assert_array_equal(ta[k]["nodeID"], tb[k]["nodeID"])
         np.testing.assert_array_equal(base["nodeMembership"], other["nodeMembership"])
+
+
+# ---- arguments the first round left untested: each pinned against the live reference -----------------
+def _wide_strata(d, K):
+    """Re-stratify a synthetic table into K strata (the reference allocates per-stratum arrays of K + 1)."""
+    rng = np.random.default_rng(5)
+    return rng.integers(1, K + 1, d.n).astype(np.int32)
+
+
+UNTESTED_ARG_CASES = [
+    dict(tag="split_weight", rule=4, kw=dict(), split_weight=True),
+    dict(tag="nodedepth3", rule=4, kw=dict(nodedepth=3)),
+    dict(tag="nodedepth0", rule=1, kw=dict(nodedepth=0)),
+    dict(tag="sampsize", rule=4, kw=dict(sampsize=900)),
+    dict(tag="sampsize_bayes", rule=2, kw=dict(sampsize=1400)),
+    dict(tag="strata40", rule=4, kw=dict(), strata=40),
+    dict(tag="strata40_bayes", rule=1, kw=dict(), strata=40),
+    dict(tag="byuser_r1", rule=1, kw=dict(), byuser=True),
+    dict(tag="byuser_r2", rule=2, kw=dict(), byuser=True),
+    dict(tag="byuser_r3", rule=3, kw=dict(), byuser=True),
+]
+
+
+def untested_arg_inputs(case, n=1600, p=9):
+    d = make_cpiu(n, p, levels=32, seed=900 + len(case["tag"]))
+    kw = dict(case["kw"])
+    if case.get("strata"):
+        d.strat = _wide_strata(d, case["strata"])
+    if case.get("split_weight"):
+        kw["split_weight"] = np.linspace(0.25, 2.0, p)
+    if case.get("byuser"):
+        rng = np.random.default_rng(17)
+        samp = rng.multinomial(n, np.full(n, 1.0 / n), size=4).astype(np.int32)
+        samp[:, 0] = 70                                           # one row drawn more often than an entry's multiplicity field holds (64)
+        kw["samp"] = samp
+    return d, kw
+
+
+@pytest.mark.skipif(not refdriver.available(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("case", UNTESTED_ARG_CASES, ids=[c["tag"] for c in UNTESTED_ARG_CASES])
+def test_port_matches_live_reference_other_arguments(case):
+    d, kw = untested_arg_inputs(case)
+    t = parity.live_reference_forest(d, rule=case["rule"], ntree=4, nodesize=5, seed=-77, **kw)
+    got = port.grow(d.x, d.y, d.rt, d.strat, rule=case["rule"], ntree=4, nodesize=5, seed=-77, **kw)
+    parity.assert_forest_equal(got, t, d.n, 4, check_membr_lists=not case.get("byuser") and "sampsize" not in case["kw"], label=case["tag"])
+
+
+@pytest.mark.skipif(not refdriver.available(), reason="oracle/_ref not built (no /root/reference here)")
+def test_port_split_statistic_matches_reference_node_statistics():
+    """The winning statistic per node (what the tie-aware comparison of tests/parity.py rests on):
+    the port's splitStat against the reference's own mtryST of the chosen covariate (OPT_NODE_STAT)."""
+    d = make_cpiu(4000, 10, levels=64, seed=31)
+    for rule in (1, 4):
+        t = parity.live_reference_forest(d, statistics=True, rule=rule, ntree=3, nodesize=5, seed=-7)
+        w = port.grow(d.x, d.y, d.rt, d.strat, rule=rule, ntree=3, nodesize=5, seed=-7)
+        parity.assert_forest_equal(w, t, d.n, 3, label="stat")
+        m = w["parmID"] != 0
+        np.testing.assert_allclose(w["splitStat"][m], t["splitStat"][m], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.skipif(not refdriver.available(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("rule", [1, 4])
+def test_port_matches_live_reference_zero_risk_time(rule):
+    """Degenerate exposure: every risk time 0.  The Bayes rules then produce inf - inf = NaN deltas; the
+    reference's tracker takes the FIRST delta of a node whatever it is (deltaMax starts as NA,
+    randomForestSRC.c:15497-15499) and nothing ever beats a NaN."""
+    d = make_cpiu(900, 5, levels=16, seed=41)
+    d.rt = np.zeros(d.n)
+    t = parity.live_reference_forest(d, rule=rule, ntree=3, nodesize=5, seed=-3)
+    got = port.grow(d.x, d.y, d.rt, d.strat, rule=rule, ntree=3, nodesize=5, seed=-3)
+    parity.assert_forest_equal(got, t, d.n, 3, label="zero-rt")
+
+
+def test_tie_aware_comparison_accepts_ties_only():
+    d = make_cpiu(1500, 6, levels=16, seed=51)
+    a = port.grow(d.x, d.y, d.rt, d.strat, rule=4, ntree=3, nodesize=5, seed=-5)
+    b = {k: v.copy() for k, v in a.items()}
+    assert parity.assert_forest_equal(a, b, d.n, 3, tie_aware=True) == {"ties": 0, "trees_compared": 3}
+    # move the cutpoint of the second tree's root: a tie when the statistics agree, a failure when they do not
+    k = int(np.nonzero(b["treeID"] == 2)[0][0])
+    b["contPT"][k] = b["contPT"][k] + 1.0
+    res = parity.assert_forest_equal(a, b, d.n, 3, tie_aware=True)
+    assert res == {"ties": 1, "trees_compared": 2}
+    with pytest.raises(AssertionError):
+        parity.assert_forest_equal(a, b, d.n, 3)
+    b["splitStat"][k] = b["splitStat"][k] * (1.0 + 1e-6)
+    with pytest.raises(AssertionError, match="not a tie"):
+        parity.assert_forest_equal(a, b, d.n, 3, tie_aware=True)
