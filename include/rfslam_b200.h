@@ -116,7 +116,7 @@ typedef struct rfslam_forest_out {
   int32_t  *nodeID;            /* [total_nodes] */
   int32_t  *parmID;            /* [total_nodes] 0 = terminal */
   double   *contPT;            /* [total_nodes] NA_REAL at terminals */
-  int32_t  *mwcpSZ;            /* [total_nodes] all 0 (no factor splits on this path) */
+  int32_t  *mwcpSZ;            /* [total_nodes] words of the factor split of the node, 0 for a numeric split or a leaf (rf.c:10773) */
   double   *splitStat;         /* [total_nodes] winning delta (NaN at terminals) when want_split_stat, else NULL */
   int32_t  *leafCount;         /* [ntree] */
   int32_t  *seed;              /* [ntree] chain-A seed, as forest$seed */
@@ -143,6 +143,11 @@ typedef struct rfslam_forest_out {
      RFSLAM_OPT_PERF and the call finalizes the ensembles of the whole forest; only the last row is filled
      (perfBlock = ntree, rf.c:8155), the others hold NA_REAL as in the reference. */
   double   *perfClas;
+  /* factor (MWCP) splits (rf.c:1416-1616, rf.c:10773-10788): the left-daughter level sets of all factor splits,
+     32 levels per word, words of a node in ascending order, nodes in the forest's record order */
+  int32_t  *mwcpPT;            /* [mwcp_total] or NULL when the forest has no factor split */
+  int32_t  *mwcpCT;            /* [ntree] words per tree */
+  int64_t   mwcp_total;
 } rfslam_forest_out;
 
 int  rfslam_b200_grow(const rfslam_grow_args *args, rfslam_forest_out *out);
@@ -165,33 +170,92 @@ int64_t rfslam_b200_dataset_bytes(const rfslam_dataset *ds);
 
 /* ---------------------------------------------------------------- predict --------------------- */
 
-/* The subset of rfsrcPredict's 58 arguments the class path reads (rf.c:22219-22279): a forest in
-   the wire format of rf.c:10735-10806 plus held-out covariates.  Leaf class counts replace the
-   reference's "drop the training rows again" step (rf.c:3687-3747, rf.c:755-858). */
+/* Mirrors the 58 .Call arguments of rfsrcPredict in their order (rf.c:22219-22279, R side
+   R/generic.predict.rfsrc.R:437-532); list arguments are flattened (hc_zero = parmID / contPT / mwcpSZ / mwcpPT;
+   hc_one .. hc_mwcpPT exist only for htry > 0, which the path refuses; partial = its seven elements).
+   Mode as in the reference (rf.c:22361): fobservation_size > 0 predicts the held-out rows fx_data, otherwise the
+   call RESTORES the forest on its training rows x_data (OOB and full ensembles, perfClas).
+   Leaf class counts: taken from tnCLAS when it is passed (OPT_TERM_INCG, per tree leafCount x 2 as R stores it);
+   otherwise rebuilt the way restoreNodeMembership does (rf.c:3446-3900, rf.c:755-858): the bootstrap is replayed
+   from forest$seed (rf.c:7046-7050) or taken from `bootstrap` (by.user) and the training rows are routed down
+   every tree. */
 typedef struct rfslam_predict_args {
+  int32_t        trace_flag;
+  int32_t        seed;
+  uint32_t       opt_low;
+  uint32_t       opt_high;
   int32_t        ntree;
+  int32_t        observation_size;  /* n training rows */
+  int32_t        y_size;
+  const char    *r_type;
+  const int32_t *r_levels;
+  const double  *r_data;            /* [n] training response codes 1.0 / 2.0 */
   int32_t        x_size;            /* p */
-  int64_t        total_nodes;
-  const int32_t *treeID;            /* [total_nodes] trees contiguous, records pre-order */
+  const char    *x_type;
+  const int32_t *x_levels;
+  const double  *x_data;            /* [p][n] training covariates */
+  double         k_for_alpha;
+  int32_t        max_bootstrap_size;
+  const int32_t *bootstrap_size;    /* [ntree] */
+  const int32_t *bootstrap;         /* [ntree][n] when by.user */
+  const double  *case_weight;
+  int32_t        time_interest_size;
+  const double  *time_interest;
+  int32_t        total_node_count;  /* records in the forest arrays */
+  const int32_t *forest_seed;       /* [ntree] forest$seed: chain-A seeds (rf.c:7046-7050) */
+  int32_t        htry;              /* must be 0 */
+  const int32_t *treeID;            /* [total_node_count] records of one tree contiguous, pre-order */
   const int32_t *nodeID;
-  const int32_t *parmID;
-  const double  *contPT;
-  const int32_t *leafCount;         /* [ntree] in the order trees appear in treeID */
-  const int32_t *tnCLAS;            /* [total_leaves][2] by tree (same order) then leaf id */
-  int32_t        fobservation_size; /* m_test */
-  const double  *fx_data;           /* [p][m_test] */
-  int32_t        want_membership;   /* 1: fill nodeMembership */
-  int32_t        device;
-  int32_t        finalize_ensembles;
+  const int32_t *parmID;            /* hc_zero[[1]] */
+  const double  *contPT;            /* hc_zero[[2]] */
+  const int32_t *mwcpSZ;            /* hc_zero[[3]] */
+  const int32_t *mwcpPT;            /* hc_zero[[4]] or NULL */
+  const int32_t *tnRMBR;            /* forest$nativeArrayTNDS, as returned by grow */
+  const int32_t *tnAMBR;
+  const int32_t *tnRCNT;            /* concatenated per tree id, leafCount[b] entries each */
+  const int32_t *tnACNT;
+  const double  *tnSURV, *tnMORT, *tnNLSN, *tnCSHZ, *tnCIFN, *tnREGR;   /* other families: unused */
+  const int32_t *tnCLAS;            /* concatenated per tree id, leafCount[b] x 2 (non-event, event) */
+  const int32_t *r_target;
+  int32_t        r_target_count;
+  int32_t        ptn_count;         /* must be 0 (pruning) */
+  int32_t        intr_predictor_size;
+  const int32_t *intr_predictor;
+  int32_t        partial_type, partial_xvar, partial_length;   /* partial[[1..3]]; partial plots are outside the path */
+  int32_t        sobservation_size;
+  const int32_t *sobservation_indv;
+  int32_t        fobservation_size; /* m held-out rows; 0 = restore mode */
+  int32_t        fr_size;
+  const double  *fr_data;
+  const double  *fx_data;           /* [p][m] */
+  int32_t        perf_block;
+  int32_t        num_threads;       /* ignored */
+
+  /* --- build-specific knobs (no reference counterpart) --- */
+  int64_t        tnCLAS_len;        /* elements in tnCLAS (a SEXP carries its length, a pointer does not); 0 = absent */
+  int64_t        mwcp_total;        /* elements in mwcpPT */
+  int32_t        device;            /* CUDA device ordinal; < 0 = current */
+  int32_t        finalize_ensembles;/* 1: divide by the denominators; 0: return sums (tree-sharded forests) */
+  int32_t        frow_first;        /* row sharding: this process handles held-out rows [frow_first, frow_first + frow_count) */
+  int32_t        frow_count;        /*   of fx_data (0 = all); outputs are sized by the shard.  Forest replicated, no collective. */
 } rfslam_predict_args;
 
 typedef struct rfslam_predict_out {
-  int32_t   m;
+  int32_t   m;                 /* rows in the outputs: the shard's held-out rows, or n in restore mode */
   int32_t   ntree;
-  double   *allEnsbCLS;       /* [2][m] */
-  uint32_t *allEnsbDen;       /* [m] */
-  int32_t  *nodeMembership;   /* [ntree][m] or NULL */
-  double    kernel_ms;
+  double   *allEnsbCLS;        /* [2][m] */
+  uint32_t *allEnsbDen;        /* [m] */
+  double   *oobEnsbCLS;        /* [2][n] restore mode only */
+  uint32_t *oobEnsbDen;        /* [n] restore mode only */
+  double   *perfClas;          /* [ntree][3] restore mode with OPT_PERF, as rfslam_forest_out.perfClas */
+  int32_t  *leafCount;         /* [ntree] by tree id */
+  int32_t  *nodeMembership;    /* [ntree][m] by tree id, with OPT_MEMB_USER, else NULL */
+  int32_t  *bootMembership;    /* [ntree][n] in-bag counts of the training rows (replayed), with OPT_MEMB_USER */
+  double    kernel_ms;         /* device time of the routing kernels (CUDA events) */
+  double    total_device_ms;   /* device time of the whole call incl. uploads */
+  int64_t   kernel_launches;
+  int64_t   row_tree_visits;   /* (row, tree) pairs routed */
+  int64_t   node_visits;       /* records read while routing (sum of path lengths) */
 } rfslam_predict_out;
 
 int  rfslam_b200_predict(const rfslam_predict_args *args, rfslam_predict_out *out);
@@ -212,6 +276,31 @@ int  rfslam_b200_rule_of_slot(int family, int slot);
 /* re-map a slot to one of the six device rules (what registerThis does for function pointers) */
 int  rfslam_b200_register_this(int rule, int family, int slot);
 void rfslam_b200_register_defaults(void);
+
+/* The reference's own plugin symbols, with its exact signatures (src/splitCustom.h:24-44, :246-330;
+   src/splitCustom.c:23-67; src/randomForestSRC.c:8856-8866), so that code written against splitCustom.h
+   links against this library unchanged.  Arrays are 1-BASED as in the reference (rf.c:13455-13482):
+   membership[1..n] (LEFT = 1), response[1..n] in {1, 2}, feature[1][1..n] = stratum, feature[2][1..n] = risk
+   time; time / event / eventTime are unused (NULL).  poissonSplitN evaluates the statistic of that ONE cut on
+   the device.  registerThis maps a slot to the device rule when func is one of the six symbols below; any
+   other pointer is a CPU rule with no device implementation: the slot is marked foreign and a grow call that
+   selects it fails with RFSLAM_ENOSUP. */
+typedef double (*rfslam_custom_function)(unsigned int n, double k_for_alpha, char *membership, double *time, double *event,
+                                         unsigned int eventTypeSize, unsigned int eventTimeSize, double *eventTime,
+                                         double *response, double mean, double variance, unsigned int maxLevel,
+                                         double **feature, unsigned int featureCount);
+#define RFSLAM_DECLARE_PLUGIN(name)                                                                              \
+  double name(unsigned int n, double k_for_alpha, char *membership, double *time, double *event,                \
+              unsigned int eventTypeSize, unsigned int eventTimeSize, double *eventTime, double *response,      \
+              double mean, double variance, unsigned int maxLevel, double **feature, unsigned int featureCount)
+RFSLAM_DECLARE_PLUGIN(poissonSplit1);   /* sc.c:639-783   Bayes, stratified */
+RFSLAM_DECLARE_PLUGIN(poissonSplit2);   /* sc.c:814-943   Bayes, unstratified */
+RFSLAM_DECLARE_PLUGIN(poissonSplit3);   /* sc.c:975-1120  Bayes, stratified, unit exposure */
+RFSLAM_DECLARE_PLUGIN(poissonSplit4);   /* sc.c:1151-1314 raw rate, stratified */
+RFSLAM_DECLARE_PLUGIN(poissonSplit5);   /* sc.c:1346-1491 raw rate, unstratified */
+RFSLAM_DECLARE_PLUGIN(poissonSplit6);   /* sc.c:1524-1687 raw rate, stratified, unit exposure */
+void registerThis(rfslam_custom_function func, unsigned int family, unsigned int slot);   /* rf.c:8856-8866 */
+void registerCustomFunctions(void);                                                        /* sc.c:23-67 */
 
 /* Score every cutpoint of ONE covariate in ONE node on the device: the work of the reference's
    per-cut loop rf.c:13404-13529 (virtuallySplitNode + gather + plugin call).

@@ -57,6 +57,8 @@ void   error(const char *fmt, ...);     /* longjmps back to fr_guard() */
 #define NUMERIC_POINTER(x)   REAL(x)
 #define INTEGER_POINTER(x)   INTEGER(x)
 #define CHARACTER_POINTER(x) ((SEXP *) ((x)->data))
+#define length(x)          ((int) ((x)->len))
+#define LENGTH(x)          ((int) ((x)->len))
 #define PROTECT(x)         (x)
 #define UNPROTECT(n)       ((void) (n))
 

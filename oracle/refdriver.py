@@ -19,22 +19,25 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(_HERE, "_ref", "librfslam_ref.so")
+# the PRODUCT's rfsrcGrow / rfsrcPredict (rfslam_b200/csrc/r_shim.c over librfslam_b200.so) compiled against the same
+# fake-R boxes (`make -C oracle rshim`): the same packer below drives it when impl="b200"
+SHIM_SO = os.path.join(_HERE, "_ref", "librfslam_b200_rshim.so")
 
-_lib = None
+_libs = {}
 
 
-def available() -> bool:
-    return os.path.exists(REF_SO)
+def available(impl: str = "ref") -> bool:
+    return os.path.exists(REF_SO if impl == "ref" else SHIM_SO)
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if not available():
+def lib(impl: str = "ref"):
+    if impl not in _libs:
+        if not available(impl):
             raise RuntimeError(
                 "oracle/_ref/librfslam_ref.so is missing: run `make -C oracle ref` in a container "
-                "that has /root/reference (the GPU box only uses the prebuilt file)")
-        L = C.CDLL(REF_SO, mode=C.RTLD_LOCAL)
+                "that has /root/reference (the GPU box only uses the prebuilt file)" if impl == "ref" else
+                "oracle/_ref/librfslam_b200_rshim.so is missing: run `make -C oracle rshim`")
+        L = C.CDLL(REF_SO if impl == "ref" else SHIM_SO, mode=C.RTLD_LOCAL)
         vp = C.c_void_p
         L.fr_int.restype = vp; L.fr_int.argtypes = [vp, C.c_long]
         L.fr_real.restype = vp; L.fr_real.argtypes = [vp, C.c_long]
@@ -52,15 +55,15 @@ def lib():
         L.fr_release_all.restype = None; L.fr_release_all.argtypes = []
         L.fr_guard_call.restype = vp
         L.fr_guard_call.argtypes = [vp, C.c_int, C.POINTER(vp), C.c_char_p, C.c_int]
-        _lib = L
-    return _lib
+        _libs[impl] = L
+    return _libs[impl]
 
 
 class _Packer:
     """Keeps the numpy buffers alive for the duration of one call."""
 
-    def __init__(self):
-        self.L = lib()
+    def __init__(self, impl: str = "ref"):
+        self.L = lib(impl)
         self.keep = []
 
     def i(self, v) -> int:
@@ -132,7 +135,7 @@ def grow(x: np.ndarray, y: np.ndarray, risk_time: np.ndarray, stratifier: np.nda
          nsplit: int = 0, split_weight: Optional[np.ndarray] = None,
          xtype: Optional[Sequence[str]] = None, xlevels: Optional[np.ndarray] = None,
          var_categories: Optional[np.ndarray] = None, category_weights: Optional[np.ndarray] = None,
-         statistics: bool = False, sampsize: Optional[int] = None) -> Dict[str, np.ndarray]:
+         statistics: bool = False, sampsize: Optional[int] = None, impl: str = "ref", quants: bool = False) -> Dict[str, np.ndarray]:
     """Run the reference's rfsrcGrow.  ``x`` is [p, n] float64 (p contiguous columns of n), ``y``
     the response codes in {1.0, 2.0}.  ``samp`` ([ntree, n] int32 in-bag counts) selects
     bootstrap="by.user" (R/utilities.R:43-45 -> bits 2^19+2^20).  ``statistics`` sets OPT_NODE_STAT
@@ -141,14 +144,16 @@ def grow(x: np.ndarray, y: np.ndarray, risk_time: np.ndarray, stratifier: np.nda
     never filled on the custom-rule path of this fork).  They are appended under their own critical section
     (randomForestSRC.c:20948-20962), so they line up with ``treeID`` only when ``nthreads == 1``;
     trim_forest() turns them into ``splitStat`` = the statistic of the covariate the node split on."""
-    L = lib()
+    L = lib(impl)
     p, n = x.shape
     x = np.ascontiguousarray(x, dtype=np.float64)
     if mtry is None:
         mtry = int(np.ceil(np.sqrt(p)))        # R/data.utilities.R:391-405
-    P = _Packer()
+    P = _Packer(impl)
     opt_low = (1 << 5) + (1 << 2)              # forest + perf (SURVEY app. C)
     opt_high = 256 * (split_slot(rule) - 1) + (1 << 16)
+    if quants:
+        opt_high += (1 << 18)                  # terminal.quants outgoing: tnCLAS (R/utilities.R:462-483)
     if membership:
         opt_high += (1 << 6)
     if statistics:
@@ -198,7 +203,7 @@ def grow(x: np.ndarray, y: np.ndarray, risk_time: np.ndarray, stratifier: np.nda
     out = L.fr_guard_call(fn, 44, arr, msg, 2048)
     if not out:
         L.fr_release_all()
-        raise RuntimeError("reference rfsrcGrow failed: " + msg.value.decode(errors="replace"))
+        raise RuntimeError(f"rfsrcGrow ({impl}) failed: " + msg.value.decode(errors="replace"))
     res = _unpack(L, out)
     L.fr_release_all()
     res["_maxBootstrapSize"] = np.array([max_boot], np.int64)
@@ -251,16 +256,18 @@ def per_tree(res: Dict[str, np.ndarray]) -> Dict[int, Dict[str, np.ndarray]]:
 
 def predict(x: np.ndarray, y: np.ndarray, forest: Dict[str, np.ndarray], fx: Optional[np.ndarray], *,
             k_for_alpha: float = 2.0, membership: bool = True, samp: Optional[np.ndarray] = None,
-            nodesize: int = 5) -> Dict[str, np.ndarray]:
+            nodesize: int = 5, impl: str = "ref", quants: bool = False) -> Dict[str, np.ndarray]:
     """Run the reference's rfsrcPredict on a (trimmed) grow output.  ``fx`` [p, m_test] selects
     RF_PRED; ``fx=None`` is restore mode (RF_REST) (randomForestSRC.c:22361)."""
-    L = lib()
+    L = lib(impl)
     p, n = x.shape
     x = np.ascontiguousarray(x, dtype=np.float64)
     ntree = forest["leafCount"].size
-    P = _Packer()
+    P = _Packer(impl)
     opt_low = (1 << 5) + (1 << 2)
     opt_high = (1 << 17)
+    if quants:
+        opt_high += (1 << 19)                  # terminal.quants incoming: tnCLAS is passed (R/utilities.R:462-483)
     if membership:
         opt_high += (1 << 6)
     if samp is not None:
@@ -296,7 +303,7 @@ def predict(x: np.ndarray, y: np.ndarray, forest: Dict[str, np.ndarray], fx: Opt
         P.i(forest["rmbrMembership"]), P.i(forest["ambrMembership"]),
         P.i(forest["tnRCNT"]), P.i(forest["tnACNT"]),
         z_d(), z_d(), z_d(), z_d(), z_d(), z_d(),
-        P.i(forest["tnCLAS"]) if "tnCLAS" in forest else z_i(),
+        P.i(forest["tnCLAS"]) if (quants and "tnCLAS" in forest) else z_i(),
         P.i(1), P.i(1), P.i(0),
         P.i(0), z_i(), partial, P.i(0), z_i(),
         P.i(m_test), P.i(0), z_d(), fx_arg, P.i(ntree), P.i(-1),
@@ -308,7 +315,7 @@ def predict(x: np.ndarray, y: np.ndarray, forest: Dict[str, np.ndarray], fx: Opt
     out = L.fr_guard_call(fn, 58, arr, msg, 2048)
     if not out:
         L.fr_release_all()
-        raise RuntimeError("reference rfsrcPredict failed: " + msg.value.decode(errors="replace"))
+        raise RuntimeError(f"rfsrcPredict ({impl}) failed: " + msg.value.decode(errors="replace"))
     res = _unpack(L, out)
     L.fr_release_all()
     return res

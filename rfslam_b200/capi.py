@@ -46,21 +46,39 @@ class ForestOut(C.Structure):
         ("oobEnsbCLS", _pd), ("allEnsbCLS", _pd), ("oobEnsbDen", _pu), ("allEnsbDen", _pu),
         ("split_candidates", C.c_int64), ("algorithmic_bytes", C.c_int64),
         ("grow_kernel_ms", C.c_double), ("total_device_ms", C.c_double), ("kernel_launches", C.c_int64), ("rmbr_stride", C.c_int64), ("perfClas", _pd),
+        ("mwcpPT", _pi), ("mwcpCT", _pi), ("mwcp_total", C.c_int64),
     ]
 
 
 class PredictArgs(C.Structure):
+    """Mirrors rfslam_predict_args: the 58 rfsrcPredict arguments in order, lists flattened, then the build knobs."""
     _fields_ = [
-        ("ntree", C.c_int32), ("x_size", C.c_int32), ("total_nodes", C.c_int64),
-        ("treeID", _pi), ("nodeID", _pi), ("parmID", _pi), ("contPT", _pd), ("leafCount", _pi), ("tnCLAS", _pi),
-        ("fobservation_size", C.c_int32), ("fx_data", _pd), ("want_membership", C.c_int32),
-        ("device", C.c_int32), ("finalize_ensembles", C.c_int32),
+        ("trace_flag", C.c_int32), ("seed", C.c_int32), ("opt_low", C.c_uint32), ("opt_high", C.c_uint32),
+        ("ntree", C.c_int32), ("observation_size", C.c_int32), ("y_size", C.c_int32),
+        ("r_type", C.c_char_p), ("r_levels", _pi), ("r_data", _pd),
+        ("x_size", C.c_int32), ("x_type", C.c_char_p), ("x_levels", _pi), ("x_data", _pd),
+        ("k_for_alpha", C.c_double), ("max_bootstrap_size", C.c_int32), ("bootstrap_size", _pi), ("bootstrap", _pi),
+        ("case_weight", _pd), ("time_interest_size", C.c_int32), ("time_interest", _pd),
+        ("total_node_count", C.c_int32), ("forest_seed", _pi), ("htry", C.c_int32),
+        ("treeID", _pi), ("nodeID", _pi), ("parmID", _pi), ("contPT", _pd), ("mwcpSZ", _pi), ("mwcpPT", _pi),
+        ("tnRMBR", _pi), ("tnAMBR", _pi), ("tnRCNT", _pi), ("tnACNT", _pi),
+        ("tnSURV", _pd), ("tnMORT", _pd), ("tnNLSN", _pd), ("tnCSHZ", _pd), ("tnCIFN", _pd), ("tnREGR", _pd),
+        ("tnCLAS", _pi), ("r_target", _pi), ("r_target_count", C.c_int32), ("ptn_count", C.c_int32),
+        ("intr_predictor_size", C.c_int32), ("intr_predictor", _pi),
+        ("partial_type", C.c_int32), ("partial_xvar", C.c_int32), ("partial_length", C.c_int32),
+        ("sobservation_size", C.c_int32), ("sobservation_indv", _pi),
+        ("fobservation_size", C.c_int32), ("fr_size", C.c_int32), ("fr_data", _pd), ("fx_data", _pd),
+        ("perf_block", C.c_int32), ("num_threads", C.c_int32),
+        ("tnCLAS_len", C.c_int64), ("mwcp_total", C.c_int64), ("device", C.c_int32), ("finalize_ensembles", C.c_int32),
+        ("frow_first", C.c_int32), ("frow_count", C.c_int32),
     ]
 
 
 class PredictOut(C.Structure):
     _fields_ = [("m", C.c_int32), ("ntree", C.c_int32), ("allEnsbCLS", _pd), ("allEnsbDen", _pu),
-                ("nodeMembership", _pi), ("kernel_ms", C.c_double)]
+                ("oobEnsbCLS", _pd), ("oobEnsbDen", _pu), ("perfClas", _pd), ("leafCount", _pi),
+                ("nodeMembership", _pi), ("bootMembership", _pi), ("kernel_ms", C.c_double), ("total_device_ms", C.c_double),
+                ("kernel_launches", C.c_int64), ("row_tree_visits", C.c_int64), ("node_visits", C.c_int64)]
 
 
 # every symbol include/rfslam_b200.h declares (tests check the library exports exactly these)
@@ -71,6 +89,10 @@ SYMBOLS = [
     "rfslam_b200_score_node", "rfslam_b200_bootstrap_counts", "rfslam_b200_last_error", "rfslam_b200_version",
     "rfslam_b200_device_count", "rfslam_b200_last_profile", "rfslam_b200_free_array", "rfslam_b200_host_pool_trim",
 ]
+# the reference's own plugin symbols, exported with its signatures (src/splitCustom.h:24-44, src/splitCustom.c:23-67)
+REFERENCE_SYMBOLS = ["registerThis", "registerCustomFunctions"] + [f"poissonSplit{k}" for k in range(1, 7)]
+CUSTOM_FUNCTION = C.CFUNCTYPE(C.c_double, C.c_uint, C.c_double, C.c_char_p, _pd, _pd, C.c_uint, C.c_uint, _pd, _pd, C.c_double, C.c_double,
+                              C.c_uint, C.POINTER(_pd), C.c_uint)
 
 _lib = None
 
@@ -111,6 +133,12 @@ def lib():
         L.rfslam_b200_last_profile.restype = C.c_int; L.rfslam_b200_last_profile.argtypes = [C.POINTER(C.c_uint64), C.c_int]
         L.rfslam_b200_free_array.restype = None; L.rfslam_b200_free_array.argtypes = [vp]
         L.rfslam_b200_host_pool_trim.restype = None; L.rfslam_b200_host_pool_trim.argtypes = []
+        L.registerThis.restype = None; L.registerThis.argtypes = [C.c_void_p, C.c_uint, C.c_uint]
+        L.registerCustomFunctions.restype = None; L.registerCustomFunctions.argtypes = []
+        for k in range(1, 7):
+            f = getattr(L, f"poissonSplit{k}")
+            f.restype = C.c_double
+            f.argtypes = [C.c_uint, C.c_double, C.c_void_p, _pd, _pd, C.c_uint, C.c_uint, _pd, C.c_void_p, C.c_double, C.c_double, C.c_uint, C.c_void_p, C.c_uint]
         _lib = L
     return _lib
 

@@ -22,21 +22,6 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-// family x slot -> device rule; the reference's customFunctionArray[4][16] (rf.c:486) with the
-// registrations of sc.c:47-62 (poissonSplitN in CLAS_FAM slot N+1)
-static int g_rule_table[4][16];
-static bool g_rule_init = false;
-static std::mutex g_ruleMu;                   // the registry may be read by concurrent grow calls
-
-static void ensure_defaults() {
-  std::lock_guard<std::mutex> lk(g_ruleMu);
-  if (!g_rule_init) {
-    memset(g_rule_table, 0, sizeof g_rule_table);
-    for (int r = 1; r <= 6; r++) g_rule_table[RFSLAM_CLAS_FAM][r] = r;      // slot r+1 -> index r
-    g_rule_init = true;
-  }
-}
-
 }  // namespace rfslam
 
 using namespace rfslam;
@@ -55,22 +40,20 @@ int rfslam_b200_device_count(void) {
   return n;
 }
 
-void rfslam_b200_register_defaults(void) { { std::lock_guard<std::mutex> lk(g_ruleMu); g_rule_init = false; } ensure_defaults(); }
+void rfslam_b200_register_defaults(void) { reset_rule_defaults(); }
 
 int rfslam_b200_register_this(int rule, int family, int slot) {
-  ensure_defaults();
   if (family < 0 || family > 3 || slot < 1 || slot > 16) { set_error("family must be 0..3 and slot 1..16 (rf.c:8856-8866)"); return RFSLAM_EINVAL; }
   if (rule < 0 || rule > 6) { set_error("only the six Poisson rules have device implementations"); return RFSLAM_ENOSUP; }
   if (rule != 0 && family != RFSLAM_CLAS_FAM) { set_error("the Poisson rules are classification-family rules (sc.c:47-62)"); return RFSLAM_ENOSUP; }
-  { std::lock_guard<std::mutex> lk(g_ruleMu); g_rule_table[family][slot - 1] = rule; }
+  rule_table_set(family, slot, rule);
   return RFSLAM_OK;
 }
 
 int rfslam_b200_rule_of_slot(int family, int slot) {
-  ensure_defaults();
   if (family < 0 || family > 3 || slot < 1 || slot > 16) return 0;
-  std::lock_guard<std::mutex> lk(g_ruleMu);
-  return g_rule_table[family][slot - 1];
+  const int r = rule_table_get(family, slot);
+  return r > 0 ? r : 0;                       // empty and foreign (user-supplied CPU rule) slots have no device rule
 }
 
 int rfslam_b200_dataset_create(const rfslam_grow_args* args, rfslam_dataset** ds) {
@@ -131,7 +114,7 @@ void rfslam_b200_free_forest(rfslam_forest_out* o) {
   if (!o) return;
   void* arrays[] = {o->tree_ids, o->treeID, o->nodeID, o->parmID, o->contPT, o->mwcpSZ, o->splitStat, o->leafCount, o->seed,
                     o->tnRCNT, o->tnACNT, o->tnCLAS, o->nodeMembership, o->bootMembership, o->rmbrMembership, o->ambrMembership,
-                    o->oobEnsbCLS, o->allEnsbCLS, o->oobEnsbDen, o->allEnsbDen, o->perfClas};
+                    o->oobEnsbCLS, o->allEnsbCLS, o->oobEnsbDen, o->allEnsbDen, o->perfClas, o->mwcpPT, o->mwcpCT};
   for (void* p : arrays) host_free(p);
   memset(o, 0, sizeof(*o));
 }
@@ -150,7 +133,8 @@ int rfslam_b200_predict(const rfslam_predict_args* args, rfslam_predict_out* out
 
 void rfslam_b200_free_predict(rfslam_predict_out* o) {
   if (!o) return;
-  host_free(o->allEnsbCLS); host_free(o->allEnsbDen); host_free(o->nodeMembership);
+  void* arrays[] = {o->allEnsbCLS, o->allEnsbDen, o->oobEnsbCLS, o->oobEnsbDen, o->perfClas, o->leafCount, o->nodeMembership, o->bootMembership};
+  for (void* p : arrays) host_free(p);
   memset(o, 0, sizeof(*o));
 }
 

@@ -248,6 +248,10 @@ T* host_copy(const T* dev, size_t count) {
 
 }  // namespace
 
+void launch_bootstrap_draw(const int* d_seedA, const int* d_bootSize, uint32_t* d_draws, size_t stride, int n, int ntrees) {
+  bootstrap_draw_kernel<<<ntrees, 32>>>(d_seedA, d_bootSize, d_draws, stride, n);
+}
+
 int validate_grow_args(const rfslam_grow_args* a, GrowConfig* cfg) {
   if (!a) { set_error("null arguments"); return RFSLAM_EINVAL; }
   if (a->seed >= 0) { set_error("Random seed must be less than zero (rf.c:6454)"); return RFSLAM_EINVAL; }
@@ -260,7 +264,11 @@ int validate_grow_args(const rfslam_grow_args* a, GrowConfig* cfg) {
   if (a->split_rule != 16) { set_error("splitRule %d is not the custom rule (16): no device implementation", a->split_rule); return RFSLAM_ENOSUP; }
   int slot = (int)((a->opt_high & RFSLAM_OPTH_SPLT_CUST) >> 8) + 1;
   int rule = rfslam_b200_rule_of_slot(RFSLAM_CLAS_FAM, slot);
-  if (rule < 1) { set_error("custom split slot %d has no device rule (only the six Poisson rules are accelerated; no CPU fallback)", slot); return RFSLAM_ENOSUP; }
+  if (rule < 1) {
+    if (rule_slot_is_foreign(RFSLAM_CLAS_FAM, slot)) set_error("custom split slot %d holds a user-supplied CPU function (registerThis): it has no device implementation and there is no CPU fallback", slot);
+    else set_error("custom split slot %d has no device rule (only the six Poisson rules are accelerated; no CPU fallback)", slot);
+    return RFSLAM_ENOSUP;
+  }
   if (a->nsplit < 0) { set_error("nsplit = %d must be >= 0 (R/data.utilities.R:483-488)", a->nsplit); return RFSLAM_EINVAL; }
   cfg->nsplit = a->nsplit;
   if (a->htry != 0) { set_error("htry must be 0 (rf.c:6490-6494)"); return RFSLAM_EINVAL; }
@@ -669,6 +677,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     out->total_nodes = (int64_t)h_treeID.n; out->total_leaves = (int64_t)h_tnRCNT.n;
     out->tree_ids = (int32_t*)host_alloc((size_t)T * 4); memcpy(out->tree_ids, ids.data(), (size_t)T * 4);
     out->mwcpSZ = (int32_t*)host_calloc(std::max<size_t>(h_treeID.n, 1) * 4);
+    out->mwcpCT = (int32_t*)host_calloc((size_t)T * 4); out->mwcpPT = nullptr; out->mwcp_total = 0;
     out->treeID = h_treeID.release(); out->nodeID = h_nodeID.release(); out->parmID = h_parmID.release();
     out->contPT = h_contPT.release(); out->splitStat = wantStat ? h_stat.release() : nullptr;
     out->leafCount = (int32_t*)host_alloc((size_t)T * 4); memcpy(out->leafCount, h_leafCount.data(), (size_t)T * 4);

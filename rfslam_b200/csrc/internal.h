@@ -103,6 +103,15 @@ int  score_node_impl(int rule, double k_for_alpha, int m, const double* x, const
 int  bootstrap_counts_impl(int seed, int ntree, int n, int tree, int32_t* counts, int device);
 int  validate_grow_args(const rfslam_grow_args* a, GrowConfig* cfg);
 void chain_seeds(int seed, int ntree, std::vector<int>& seedA, std::vector<int>& seedB);
+// chain-A replay of `ntrees` trees (grow.cu bootstrap_draw_kernel): draws[t][0..bootSize[t]) = 0-based original rows
+void launch_bootstrap_draw(const int* d_seedA, const int* d_bootSize, uint32_t* d_draws, size_t stride, int n, int ntrees);
+
+// plugin.cu: family x slot -> device rule (the reference's customFunctionArray[4][16], rf.c:486)
+void ensure_rule_defaults();
+void reset_rule_defaults();
+int  rule_table_get(int family, int slot);            // 1..6 device rule, 0 empty, -1 foreign (user-supplied CPU function)
+void rule_table_set(int family, int slot, int rule);
+bool rule_slot_is_foreign(int family, int slot);
 
 // R's NA_real_: the NaN with payload 1954 (arithmetic NaN is a different bit pattern)
 inline double rfslam_na_real() { const unsigned long long b = 0x7FF00000000007A2ull; double d; memcpy(&d, &b, 8); return d; }

@@ -140,6 +140,8 @@ def _unpack_forest(o: ForestOut, finalized: bool = True) -> Dict[str, np.ndarray
         "treeID": _own(o, "treeID", NN, np.int32), "nodeID": _own(o, "nodeID", NN, np.int32),
         "parmID": _own(o, "parmID", NN, np.int32), "contPT": _own(o, "contPT", NN, np.float64),
         "mwcpSZ": _own(o, "mwcpSZ", NN, np.int32), "splitStat": _own(o, "splitStat", NN, np.float64),
+        "mwcpPT": _own(o, "mwcpPT", int(o.mwcp_total), np.int32) if o.mwcpPT else np.zeros(0, np.int32),
+        "mwcpCT": _own(o, "mwcpCT", T, np.int32),
         "leafCount": _own(o, "leafCount", T, np.int32), "seed": _own(o, "seed", T, np.int32),
         "tnRCNT": _own(o, "tnRCNT", NL, np.int32), "tnACNT": _own(o, "tnACNT", NL, np.int32),
         "tnCLAS": _own(o, "tnCLAS", 2 * NL, np.int32),
@@ -224,24 +226,86 @@ def rfsrc(x, y, risk_time=None, stratifier=None, *, splitrule="poisson.split4", 
     return res
 
 
-def predict_rfsrc(forest: Dict[str, np.ndarray], fx, *, membership=True, device=-1, finalize=True) -> Dict[str, np.ndarray]:
-    """Held-out prediction of a forest in the reference's wire format (rfslam_b200_predict)."""
-    fx = np.ascontiguousarray(fx, np.float64)
-    p, m = fx.shape
-    keep = {k: np.ascontiguousarray(forest[k], np.int32) for k in ("treeID", "nodeID", "parmID", "leafCount", "tnCLAS")}
+def predict_rfsrc(forest: Dict[str, np.ndarray], fx=None, *, x=None, y=None, membership=True, device=-1, finalize=True,
+                  samp=None, sampsize=None, use_tnclas=True, frow_first=0, frow_count=0, perf=True) -> Dict[str, np.ndarray]:
+    """rfsrcPredict through the C-ABI (rfslam_b200_predict), mirroring R/generic.predict.rfsrc.R:437-534.
+
+    ``forest`` is a grow result (the reference's wire format).  ``fx`` [p, m] predicts held-out rows; ``fx=None``
+    RESTORES the forest on its training rows ``x`` / ``y`` (OOB + full ensembles, perfClas).  The leaf class counts
+    come from ``forest["tnCLAS"]`` when present (and ``use_tnclas``), else they are rebuilt from the training rows
+    with the bootstrap replayed from ``forest["seed"]`` (or ``samp``).  ``frow_first`` / ``frow_count`` select this
+    process' shard of the held-out rows (forest replicated, no collective)."""
+    keep = {k: np.ascontiguousarray(forest[k], np.int32) for k in ("treeID", "nodeID", "parmID", "seed")}
     keep["contPT"] = np.ascontiguousarray(forest["contPT"], np.float64)
+    keep["mwcpSZ"] = np.ascontiguousarray(forest["mwcpSZ"], np.int32) if "mwcpSZ" in forest else np.zeros(keep["treeID"].size, np.int32)
+    ntree = int(keep["seed"].size)
     a = PredictArgs()
-    a.ntree = int(keep["leafCount"].size); a.x_size = p; a.total_nodes = int(keep["treeID"].size)
+    a.trace_flag = 0; a.seed = -1
+    a.opt_low = ((1 << 2) if perf else 0) + (1 << 5)
+    a.opt_high = (1 << 17)
+    if membership:
+        a.opt_high |= (1 << 6)
+    a.ntree = ntree; a.y_size = 1
+    rtype = b"C"; a.r_type = rtype
+    keep["rlev"] = np.array([2], np.int32); a.r_levels = _ip(keep["rlev"])
+    if fx is not None:
+        fx = np.ascontiguousarray(fx, np.float64)
+        p, m = fx.shape
+    else:
+        if x is None or y is None:
+            raise ValueError("restore mode (fx=None) needs the training x and y")
+        p, m = np.asarray(x).shape[0], 0
+    if x is not None:
+        keep["x"] = np.ascontiguousarray(x, np.float64); keep["y"] = np.ascontiguousarray(y, np.float64)
+        if keep["x"].shape[0] != p or keep["y"].shape != (keep["x"].shape[1],):
+            raise ValueError("training x must be [p, n] and y [n]")
+        n = keep["x"].shape[1]
+        a.x_data = _dp(keep["x"]); a.r_data = _dp(keep["y"])
+    else:
+        n = int(forest["allEnsbDen"].size) if "allEnsbDen" in forest else 1
+    a.observation_size = n; a.x_size = p
+    xtype = b"R" * p; a.x_type = xtype
+    keep["xlev"] = np.zeros(p, np.int32); a.x_levels = _ip(keep["xlev"])
+    a.k_for_alpha = 2.0
+    if samp is not None:
+        a.opt_low |= (1 << 19) + (1 << 20)
+        keep["samp"] = np.ascontiguousarray(samp, np.int32)
+        assert keep["samp"].shape == (ntree, n)
+        a.bootstrap = _ip(keep["samp"]); keep["bs"] = keep["samp"].sum(axis=1).astype(np.int32)
+    else:
+        keep["bs"] = np.full(ntree, n if sampsize is None else int(sampsize), np.int32)
+    a.max_bootstrap_size = int(keep["bs"].max()); a.bootstrap_size = _ip(keep["bs"])
+    a.total_node_count = int(keep["treeID"].size); a.forest_seed = _ip(keep["seed"]); a.htry = 0
     a.treeID = _ip(keep["treeID"]); a.nodeID = _ip(keep["nodeID"]); a.parmID = _ip(keep["parmID"]); a.contPT = _dp(keep["contPT"])
-    a.leafCount = _ip(keep["leafCount"]); a.tnCLAS = _ip(keep["tnCLAS"])
-    a.fobservation_size = m; a.fx_data = _dp(fx); a.want_membership = 1 if membership else 0
-    a.device = device; a.finalize_ensembles = 1 if finalize else 0
+    a.mwcpSZ = _ip(keep["mwcpSZ"])
+    for k, f in (("tnRCNT", "tnRCNT"), ("tnACNT", "tnACNT"), ("rmbrMembership", "tnRMBR"), ("ambrMembership", "tnAMBR")):
+        if k in forest and forest[k] is not None:
+            keep[f] = np.ascontiguousarray(forest[k], np.int32); setattr(a, f, _ip(keep[f]))
+    if use_tnclas and forest.get("tnCLAS") is not None:
+        keep["tnCLAS"] = np.ascontiguousarray(forest["tnCLAS"], np.int32)
+        a.tnCLAS = _ip(keep["tnCLAS"]); a.tnCLAS_len = int(keep["tnCLAS"].size); a.opt_high |= (1 << 19)
+    keep["rtarget"] = np.array([1], np.int32); a.r_target = _ip(keep["rtarget"]); a.r_target_count = 1
+    a.fobservation_size = m
+    if fx is not None:
+        a.fx_data = _dp(fx)
+    a.perf_block = ntree; a.num_threads = -1
+    a.device = int(device); a.finalize_ensembles = 1 if finalize else 0
+    a.frow_first = int(frow_first); a.frow_count = int(frow_count)
     out = PredictOut()
     capi.check(capi.lib().rfslam_b200_predict(C.byref(a), C.byref(out)))
-    res = {"allEnsbCLS": _take(out.allEnsbCLS, 2 * m, np.float64), "allEnsbDen": _take(out.allEnsbDen, m, np.uint32),
-           "kernel_ms": float(out.kernel_ms)}
+    M = int(out.m)
+    res = {"allEnsbCLS": _take(out.allEnsbCLS, 2 * M, np.float64), "allEnsbDen": _take(out.allEnsbDen, M, np.uint32),
+           "leafCount": _take(out.leafCount, ntree, np.int32), "kernel_ms": float(out.kernel_ms),
+           "total_device_ms": float(out.total_device_ms), "kernel_launches": int(out.kernel_launches),
+           "row_tree_visits": int(out.row_tree_visits), "node_visits": int(out.node_visits), "finalized": bool(finalize)}
+    if out.oobEnsbCLS:
+        res["oobEnsbCLS"] = _take(out.oobEnsbCLS, 2 * M, np.float64); res["oobEnsbDen"] = _take(out.oobEnsbDen, M, np.uint32)
+    if out.perfClas:
+        res["perfClas"] = _take(out.perfClas, 3 * ntree, np.float64)
     if out.nodeMembership:
-        res["nodeMembership"] = _take(out.nodeMembership, a.ntree * m, np.int32)
+        res["nodeMembership"] = _take(out.nodeMembership, ntree * M, np.int32)
+    if out.bootMembership:
+        res["bootMembership"] = _take(out.bootMembership, ntree * n, np.int32)
     capi.lib().rfslam_b200_free_predict(C.byref(out))
     return res
 

@@ -145,3 +145,89 @@ def quantise(x: np.ndarray, levels: int) -> np.ndarray:
         b = np.minimum(np.floor((col - lo) / w), levels - 1)
         out[j] = lo + (b + 0.5) * w
     return out
+
+
+def make_cpiu_torch(n: int, p: int, *, levels: int = 64, seed: int = DATA_SEED, interval: float = 0.5, max_k: int = 16,
+                    event_rate: float = 0.05, device: str = "cuda") -> Cpiu:
+    """The same schema as make_cpiu generated with torch on ``device`` (a `torch.Generator` stream, so the VALUES
+    differ from the numpy generator's): for tables too large to synthesise on the host within a benchmark's
+    budget (10M x 100 takes minutes in numpy, about a second on the GPU).  Returns host arrays."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    f64 = torch.float64
+    U = lambda *s: torch.rand(*s, generator=g, device=device, dtype=f64)
+    N = lambda *s: torch.randn(*s, generator=g, device=device, dtype=f64)
+    beta = (N(p) * 0.35) * (U(p) < 0.5)
+    persons = int(n / (0.5 * max_k) * 1.6) + 64
+    while True:
+        F = interval + U(persons) * (interval * max_k - interval)
+        k = torch.clamp(torch.ceil(F / interval).to(torch.int64), max=max_k)
+        start = torch.zeros(persons + 1, dtype=torch.int64, device=device)
+        start[1:] = torch.cumsum(k, 0)
+        rows = int(start[-1])
+        pid = torch.repeat_interleave(torch.arange(persons, device=device), k)
+        first = start[pid]
+        intn = torch.arange(rows, device=device) - first + 1
+        rt = torch.full((rows,), interval, dtype=f64, device=device)
+        rem = F - interval * (k - 1).to(f64)
+        rt[start[1:] - 1] = torch.where(rem > 0, rem, torch.full_like(rem, interval))
+        nb, nt = (p + 2) // 3, (p + 1) // 3
+        x = torch.empty((p, rows), dtype=f64, device=device)
+        eta = torch.zeros(rows, dtype=f64, device=device)
+        for j in range(p):
+            if j < nb:                                             # baseline: constant within person
+                kind = j % 4
+                if kind == 0:
+                    v = 60.0 + 12.0 * N(persons)
+                elif kind == 1:
+                    v = (U(persons) < 0.5).to(f64)
+                elif kind == 2:
+                    v = (U(persons) < 0.2).to(f64)
+                else:
+                    v = torch.floor(U(persons) * 6.0)
+                col = v[pid]
+            elif j < nb + nt:                                      # time-varying: random walk with carry-forward
+                persist = 1 + ((j - nb) % 3)
+                step = 0.35 * N(rows)
+                step[((intn - 1) % persist != 0) | (intn == 1)] = 0.0
+                cs = torch.cumsum(step, 0)
+                col = N(persons)[pid] + (cs - cs[first])
+            else:                                                  # counts / elapsed time: non-decreasing within person
+                jj = j - nb - nt
+                if jj % 2 == 0:
+                    inc = torch.poisson(torch.full((rows,), 0.3, dtype=f64, device=device), generator=g)
+                    inc[intn == 1] = 0.0
+                    cs = torch.cumsum(inc, 0)
+                    col = cs - cs[first]
+                else:
+                    col = (intn - 1).to(f64) * interval + torch.floor(U(persons) * 3.0)[pid] * interval
+            x[j] = col
+            if float(beta[j]) != 0.0:
+                sd = col.std(unbiased=False)
+                eta += beta[j] * (col - col.mean()) / (sd if float(sd) > 0 else 1.0)
+        eta /= max(1.0, float(torch.count_nonzero(beta)) ** 0.5)
+        lam = torch.exp(torch.log(torch.tensor(event_rate / interval, dtype=f64, device=device)) + eta - 0.5 * eta.var(unbiased=False))
+        ev = U(rows) < (1.0 - torch.exp(-lam * rt))
+        cs = torch.cumsum(ev.to(torch.int64), 0)
+        before = cs - ev.to(torch.int64)
+        keep = (before - before[first]) == 0                        # rows up to and including the person's first event
+        idx = torch.nonzero(keep).squeeze(1)
+        if idx.numel() >= n:
+            idx = idx[:n]
+            break
+        persons = int(persons * 1.3)
+    if levels and levels > 0:
+        for j in range(p):
+            col = x[j, idx]
+            lo, hi = float(col.min()), float(col.max())
+            if hi > lo and torch.unique(col).numel() > levels:
+                w = (hi - lo) / levels
+                b = torch.clamp(torch.floor((col - lo) / w), max=levels - 1)
+                x[j, idx] = lo + (b + 0.5) * w
+    xh = torch.empty((p, n), dtype=f64, pin_memory=(device != "cpu"))
+    for j in range(p):
+        xh[j].copy_(x[j, idx])
+    out = Cpiu(x=xh.numpy(), y=(1.0 + ev[idx].to(f64)).cpu().numpy(), rt=rt[idx].cpu().numpy(),
+               strat=intn[idx].to(torch.int32).cpu().numpy(), person=pid[idx].to(torch.int32).cpu().numpy())
+    return out

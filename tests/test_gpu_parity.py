@@ -84,6 +84,60 @@ def test_predict_matches_reference_golden(golden_dir, name):
     np.testing.assert_allclose(pr["allEnsbCLS"], g["pred_allEnsbCLS"], rtol=parity.HAZARD_RTOL)
 
 
+def test_restore_and_sharded_predict():
+    """Restore mode (fx = None: the forest on its own training rows, rf.c:22361) reproduces the grow call's ensembles
+    and perfClas; leaf class counts rebuilt from forest$seed equal the tnCLAS the grow call returned; held-out rows
+    sharded over processes (forest replicated, no collective) concatenate to the unsharded result."""
+    d = make_cpiu(5000, 10, levels=64, seed=91)
+    f = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, splitrule=4, ntree=7, nodesize=5, seed=-17, membership=True)
+    r = rfslam_b200.predict_rfsrc(f, None, x=d.x, y=d.y, use_tnclas=False)
+    for k in ("oobEnsbCLS", "allEnsbCLS"):
+        np.testing.assert_allclose(r[k], f[k], rtol=1e-12, atol=0, err_msg=k)
+    np.testing.assert_array_equal(r["perfClas"].view(np.uint64), f["perfClas"].view(np.uint64))
+    np.testing.assert_array_equal(r["nodeMembership"], f["nodeMembership"])
+    np.testing.assert_array_equal(r["bootMembership"], f["bootMembership"])
+    np.testing.assert_array_equal(r["leafCount"], f["leafCount"])
+    fx = make_cpiu(3001, 10, levels=64, seed=92).x
+    a = rfslam_b200.predict_rfsrc(f, fx)                                         # tnCLAS passed
+    b = rfslam_b200.predict_rfsrc(f, fx, x=d.x, y=d.y, use_tnclas=False)          # rebuilt from the training rows
+    np.testing.assert_array_equal(a["allEnsbCLS"], b["allEnsbCLS"])
+    np.testing.assert_array_equal(a["nodeMembership"], b["nodeMembership"])
+    ens, memb = port.predict(f, fx)
+    np.testing.assert_array_equal(a["nodeMembership"], memb)
+    np.testing.assert_allclose(a["allEnsbCLS"], ens, rtol=parity.HAZARD_RTOL)
+    parts = [rfslam_b200.predict_rfsrc(f, fx, frow_first=lo, frow_count=cnt, membership=False) for lo, cnt in ((0, 1000), (1000, 1500), (2500, 501))]
+    cat = np.concatenate([q["allEnsbCLS"].reshape(2, -1) for q in parts], axis=1).reshape(-1)
+    np.testing.assert_array_equal(cat, a["allEnsbCLS"])
+    assert a["node_visits"] > 0 and a["row_tree_visits"] == 7 * 3001
+    # small tiles: several uploads per sweep, both buffers in use
+    os.environ["RFSLAM_PREDICT_TILE_ROWS"] = "512"
+    try:
+        c = rfslam_b200.predict_rfsrc(f, fx)
+    finally:
+        del os.environ["RFSLAM_PREDICT_TILE_ROWS"]
+    np.testing.assert_array_equal(c["allEnsbCLS"], a["allEnsbCLS"])
+    np.testing.assert_array_equal(c["nodeMembership"], a["nodeMembership"])
+
+
+def test_plugin_symbols_match_reference_known_answers(golden_dir):
+    """poissonSplit1..6 with the reference's own signature (splitCustom.h:24-44), 1-based arrays, against the
+    statistics the reference's plugin returned for the same memberships (tests/golden/plugin_kat.npz)."""
+    import ctypes as C
+    from rfslam_b200 import capi
+    L = capi.lib()
+    z = np.load(os.path.join(golden_dir, "plugin_kat.npz"))
+    for i in range(int(z["count"][0])):
+        memb = np.concatenate([[0], z[f"memb_{i}"]]).astype(np.int8)
+        resp = np.concatenate([[0.0], z[f"resp_{i}"]]); strat = np.concatenate([[0.0], z[f"strat_{i}"].astype(np.float64)])
+        rt = np.concatenate([[0.0], z[f"rt_{i}"]])
+        feat = (C.c_void_p * 3)(None, strat.ctypes.data, rt.ctypes.data)
+        for rule in range(1, 7):
+            got = getattr(L, f"poissonSplit{rule}")(memb.size - 1, float(z[f"kfa_{i}"][0]), memb.ctypes.data, None, None, 0, 0, None,
+                                                     resp.ctypes.data, 0.0, 0.0, 2, C.addressof(feat), 2)
+            want = z[f"stat_{i}"][rule - 1]
+            assert got == pytest.approx(want, rel=1e-9, abs=1e-9), (i, rule, got, want)
+
+
 @pytest.mark.parametrize("rule,n,p,levels,nodesize,seed,dseed", [
     (4, 6000, 14, 64, 5, -31337, 601), (1, 5000, 10, 0, 10, -2, 602), (5, 3000, 6, 8, 1, -987654, 603),
     (3, 4000, 13, 256, 4, -800000, 604), (2, 3500, 9, 0, 20, -55, 605), (6, 4500, 20, 32, 7, -66, 606)])

@@ -21,6 +21,41 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(capi.LIB_PATH)
     for s in declared:
         assert hasattr(L, s), s
+    # the reference's plugin symbols are exported under their own names (splitCustom.h:24-44, splitCustom.c:23-67)
+    for s in capi.REFERENCE_SYMBOLS:
+        assert re.search(r"\b" + s + r"\b", hdr), s
+        assert hasattr(L, s), s
+
+
+def test_register_this_maps_function_pointers_like_the_reference():
+    # registerThis(&poissonSplitN, CLAS_FAM, slot) (splitCustom.c:47-62): the six known pointers select device rules,
+    # any other function pointer is a CPU rule -> the slot is foreign and a grow that selects it is refused
+    L = capi.lib()
+    L.rfslam_b200_register_defaults()
+    addr = lambda k: ctypes.cast(getattr(L, f"poissonSplit{k}"), ctypes.c_void_p).value
+    L.registerThis(addr(4), 0, 9)
+    assert L.rfslam_b200_rule_of_slot(0, 9) == 4
+    L.registerThis(addr(2), 0, 9)
+    assert L.rfslam_b200_rule_of_slot(0, 9) == 2
+
+    @capi.CUSTOM_FUNCTION
+    def user_rule(*a):
+        return 0.0
+    L.registerThis(ctypes.cast(user_rule, ctypes.c_void_p).value, 0, 10)
+    assert L.rfslam_b200_rule_of_slot(0, 10) == 0
+    d = make_cpiu(200, 3, levels=8, seed=1)
+    pk = rfslam_b200.forest._Packed(d.x, d.y, d.rt, d.strat, splitrule=4, ntree=2, mtry=None, nodesize=5, nodedepth=-1, seed=-3,
+                                    k_for_alpha=2.0, membership=False, samp=None, sampsize=None, split_wt=None, device=-1,
+                                    tree_first=0, tree_step=0, finalize=True)
+    pk.args.opt_high = (pk.args.opt_high & ~0x0F00) | (256 * (10 - 1))
+    out = capi.ForestOut()
+    rc = L.rfslam_b200_grow(ctypes.byref(pk.args), ctypes.byref(out))
+    assert rc == 3 and b"user-supplied" in L.rfslam_b200_last_error()
+    L.registerThis(addr(4), 1, 9)                    # a Poisson rule in the regression family: no device rule there
+    assert L.rfslam_b200_rule_of_slot(1, 9) == 0
+    L.rfslam_b200_register_defaults()
+    L.registerCustomFunctions()
+    assert [L.rfslam_b200_rule_of_slot(0, s) for s in range(1, 9)] == [0, 1, 2, 3, 4, 5, 6, 0]
 
 
 def test_slot_registry_mirrors_reference():
@@ -40,7 +75,7 @@ def test_struct_layout_matches_header_sizes():
     # the ctypes mirrors must have the C layout: pointer-sized alignment, no stray fields
     assert ctypes.sizeof(capi.GrowArgs) % 8 == 0
     assert capi.GrowArgs.x_data.offset % 8 == 0
-    assert ctypes.sizeof(capi.ForestOut) == 4 + 4 + 8 + 8 + 20 * 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8   # ... + perfClas
+    assert ctypes.sizeof(capi.ForestOut) == 4 + 4 + 8 + 8 + 20 * 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8   # ... + perfClas, mwcpPT, mwcpCT, mwcp_total
 
 
 @pytest.mark.skipif(capi.lib().rfslam_b200_device_count() > 0, reason="a GPU is present")

@@ -1,0 +1,84 @@
+"""The drop-in boundary under test: the product's `.Call` entry points
+(rfslam_b200/csrc/r_shim.c: SEXP rfsrcGrow(44) / SEXP rfsrcPredict(58) over librfslam_b200.so) and the
+UNMODIFIED reference, both compiled against the same stand-in R API (oracle/fake_r) and driven by ONE
+argument packer (oracle/refdriver.py) -- what comes back must be the same named list."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from oracle import refdriver
+from rfslam_b200 import capi
+from rfslam_b200.synth import make_cpiu
+from tests import parity
+
+needs_shim = pytest.mark.skipif(not refdriver.available("b200"), reason="oracle/_ref/librfslam_b200_rshim.so not built (make -C oracle rshim)")
+needs_ref = pytest.mark.skipif(not refdriver.available("ref"), reason="oracle/_ref/librfslam_ref.so not present")
+
+
+@needs_shim
+def test_shim_exports_the_reference_call_symbols():
+    L = ctypes.CDLL(refdriver.SHIM_SO, mode=ctypes.RTLD_LOCAL)
+    for s in ("rfsrcGrow", "rfsrcPredict"):                  # src/R_init_randomForestSRC.c:26-31
+        assert hasattr(L, s), s
+
+
+@needs_shim
+@pytest.mark.skipif(capi.lib().rfslam_b200_device_count() > 0, reason="a GPU is present")
+def test_shim_turns_library_errors_into_r_errors():
+    d = make_cpiu(300, 4, levels=8, seed=2)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        refdriver.grow(d.x, d.y, d.rt, d.strat, rule=4, ntree=2, impl="b200")
+
+
+def _sorted_by_tree(t):
+    order = np.argsort(t["treeID"], kind="stable")
+    out = dict(t)
+    for k in ("treeID", "nodeID", "parmID", "contPT", "mwcpSZ"):
+        out[k] = t[k][order]
+    return out
+
+
+CASES = [dict(rule=4, levels=32, kw=dict()), dict(rule=1, levels=0, kw=dict()), dict(rule=5, levels=16, kw=dict(byuser=True)),
+         dict(rule=4, levels=64, kw=dict(quants=True))]
+
+
+@pytest.mark.gpu
+@needs_shim
+@needs_ref
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"r{c['rule']}L{c['levels']}" + "".join(c["kw"]))
+def test_both_libraries_return_the_same_named_lists(case):
+    d = make_cpiu(3000, 9, levels=case["levels"], seed=77)
+    ntree, nodesize = 5, 5
+    kw = dict(rule=case["rule"], ntree=ntree, nodesize=nodesize, seed=-4242, membership=True, quants=bool(case["kw"].get("quants")))
+    if case["kw"].get("byuser"):
+        kw["samp"] = np.random.default_rng(3).multinomial(d.n, np.full(d.n, 1.0 / d.n), size=ntree).astype(np.int32)
+    ref = refdriver.grow(d.x, d.y, d.rt, d.strat, impl="ref", **kw)
+    got = refdriver.grow(d.x, d.y, d.rt, d.strat, impl="b200", **kw)
+    # same names in the same order (what R indexes by name and, around "treeID", by position: R/rfsrc.R:1766)
+    assert [k for k in got if not k.startswith("_")] == [k for k in ref if not k.startswith("_")]
+    # per-leaf arrays come at the reference's stride, so ONE trimming routine (R/rfsrc.R:1771-1861) serves both
+    assert got["tnRCNT"].size == ref["tnRCNT"].size and got["tnACNT"].size == ref["tnACNT"].size
+    tg, tr = _sorted_by_tree(refdriver.trim_forest(got, d.n)), _sorted_by_tree(refdriver.trim_forest(ref, d.n))
+    parity.assert_forest_equal(tg, tr, d.n, ntree, check_membr_lists=True, label="rshim")
+    np.testing.assert_array_equal(got["mwcpCT"], ref["mwcpCT"])
+    assert got["mwcpPT"].size == ref["mwcpPT"].size == 0
+    if kw["quants"]:
+        np.testing.assert_array_equal(tg["tnCLAS"], tr["tnCLAS"])
+
+    # predict and restore through the 58-argument entry, forest = what R would keep from EITHER grow call
+    fx = make_cpiu(700, 9, levels=case["levels"], seed=78).x
+    for forest in (tr, tg):
+        for mode_fx in (fx, None):
+            pkw = dict(nodesize=nodesize, samp=kw.get("samp"), quants=kw["quants"])
+            pr = refdriver.predict(d.x, d.y, forest, mode_fx, impl="ref", **pkw)
+            pg = refdriver.predict(d.x, d.y, forest, mode_fx, impl="b200", **pkw)
+            assert list(pg) == list(pr)
+            for k in pr:
+                if pr[k].dtype.kind == "i":
+                    np.testing.assert_array_equal(pg[k], pr[k], err_msg=k)
+                else:
+                    np.testing.assert_array_equal(np.isnan(pg[k]), np.isnan(pr[k]), err_msg=k)
+                    ok = ~np.isnan(pr[k])
+                    np.testing.assert_allclose(pg[k][ok], pr[k][ok], rtol=parity.HAZARD_RTOL, atol=0, err_msg=k)

@@ -1,13 +1,16 @@
-"""Phase profile of the tree kernel: RFSLAM_PROFILE=1 python tools/phase_profile.py <rows> <covariates> <levels> <ntree> <nodesize>"""
+"""Phase profile of the tree kernel: RFSLAM_PROFILE=1 python tools/phase_profile.py <rows> <covariates> <levels> <ntree> <nodesize> [torch] [reps]
+("torch": synthesise the table on the GPU -- for 10M x 100, where the numpy generator takes minutes)"""
 import os, time, sys, numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
 import rfslam_b200
-from rfslam_b200.synth import make_cpiu
+from rfslam_b200.synth import make_cpiu, make_cpiu_torch
+if len(sys.argv) > 6 and sys.argv[6] == "torch": make_cpiu = make_cpiu_torch
+reps = int(sys.argv[7]) if len(sys.argv) > 7 else 2
 n, p, L = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 ntree = int(sys.argv[4]); nodesize = int(sys.argv[5])
 t=time.time(); d = make_cpiu(n, p, levels=L); print("gen", time.time()-t, "events", (d.y==2).mean(), "D", [int(np.unique(c[:100000]).size) for c in d.x][:12], flush=True)
 t=time.time(); ds = rfslam_b200.ResidentCpiu(d.x, d.y, d.rt, d.strat); print("resident", time.time()-t, ds.hbm_bytes/1e6, "MB", flush=True)
-for rep in range(2):
+for rep in range(reps):
     t=time.time(); f = ds.grow(ntree=ntree, nodesize=nodesize, seed=-12345); dt=time.time()-t
     print(f"grow wall {dt:.3f}s kernel {f['grow_kernel_ms']:.1f}ms total_dev {f['total_device_ms']:.1f}ms trees/s(kernel) {ntree/(f['grow_kernel_ms']/1e3):.1f} nodes {f['treeID'].size} cand {f['split_candidates']} cand/s {f['split_candidates']/(f['grow_kernel_ms']/1e3):.3e} algoGB {f['algorithmic_bytes']/1e9:.2f} GB/s {f['algorithmic_bytes']/1e9/(f['grow_kernel_ms']/1e3):.1f}", flush=True)
 import ctypes as C
