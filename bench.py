@@ -6,13 +6,19 @@ reference's own CPU implementation on the box's host cores.
   python bench.py --gpus N --steps K --warmup W            (N = 1: plain python)
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
 
-One step = one pass of the hot path over the workload: grow the whole forest (bootstrap replay,
-split scoring, partition, leaf estimates, OOB / full ensembles) from the CPIU table resident in HBM.
-Workload at N = 1 is BASELINE.json configs[1]: 1M CPIUs x 50 covariates, ntree = 500,
-mtry = ceil(sqrt(p)) = 8, nodesize = 20, rule poisson.split4, cardinality mode Q (64 levels).
-At N > 1 every rank holds a replica of the table and grows 500 trees of a 500*N-tree forest
-(weak scaling; trees are independent, no collective during growth); one NCCL all-reduce of the
-ensemble sums and a gather of the forest sizes close the step.
+One step = one pass of the hot path over the workload: grow the whole forest (bootstrap replay, split
+scoring, partition, leaf estimates, OOB / full ensembles) from the CPIU table resident in HBM.
+Workload at N = 1 is BASELINE.json configs[1]: 1M CPIUs x 50 covariates, ntree = 500, mtry = ceil(sqrt(p)) = 8,
+nodesize = 20, rule poisson.split4, cardinality mode Q (64 levels).  At N > 1 every rank holds a replica of
+the table and grows 500 trees of a 500*N-tree forest (weak scaling; trees are independent, no collective
+during growth); the step ends with the path's one exchange, inside the library and on device buffers:
+an NCCL all-reduce of the ensemble sums and an NCCL gather of the forest records to rank 0.
+
+Two more records ride on the same JSON line:
+  c3      BASELINE configs[2], the north-star target: ONE 1000-tree forest on 10M CPIUs x 100 covariates
+          (mtry 10), its trees sharded over the N ranks (strong scaling: total work fixed), one timed step
+  predict BASELINE configs[4] scaled to the box: rfsrcPredict of the step's forest on held-out rows sharded
+          over the N ranks (forest replicated, no collective), row.trees/s and the B_pred roofline
 """
 from __future__ import annotations
 
@@ -34,6 +40,8 @@ if ROOT not in sys.path:
 os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
 
 WORKLOAD = dict(n=1_000_000, p=50, levels=64, ntree=500, nodesize=20, rule=4, seed=-12345, k_for_alpha=2.0)
+C3 = dict(n=10_000_000, p=100, levels=64, ntree=1000, nodesize=20, rule=4, seed=-12345, k_for_alpha=2.0)
+REF_SAMPLE_N = 200_000           # rows of the bounded sample the reference arm / cpu_baseline grow (25 calls must fit a few minutes)
 
 
 def measured_peak_gbs():
@@ -96,7 +104,7 @@ def make_data(cfg):
     return make_cpiu(cfg["n"], cfg["p"], levels=cfg["levels"])
 
 
-def cpu_reference_sample(cfg, *, sample_n: int, ntree: int, threads: int):
+def cpu_reference_sample(cfg, *, sample_n: int, ntree: int, threads: int, membership: bool = False):
     """The reference's own OpenMP CPU path (oracle/_ref, the unmodified reference compiled against
     the fake-R shim) on a bounded sample of the same synthetic workload."""
     from oracle import refdriver
@@ -104,17 +112,9 @@ def cpu_reference_sample(cfg, *, sample_n: int, ntree: int, threads: int):
     d = make_cpiu(sample_n, cfg["p"], levels=cfg["levels"])
     t0 = time.perf_counter()
     r = refdriver.grow(d.x, d.y, d.rt, d.strat, rule=cfg["rule"], ntree=ntree, nodesize=cfg["nodesize"], seed=cfg["seed"],
-                       k_for_alpha=cfg["k_for_alpha"], membership=False, nthreads=threads)
+                       k_for_alpha=cfg["k_for_alpha"], membership=membership, nthreads=threads)
     dt = time.perf_counter() - t0
     return d, r, dt
-
-
-def count_candidates_gpu(d, cfg, ntree):
-    """Split candidates of the sample forest: identical trees => identical count, taken from the device path."""
-    import rfslam_b200
-    f = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, splitrule=cfg["rule"], ntree=ntree, nodesize=cfg["nodesize"], seed=cfg["seed"],
-                          k_for_alpha=cfg["k_for_alpha"])
-    return int(f["split_candidates"])
 
 
 def run_reference_arm(args):
@@ -139,7 +139,8 @@ def run_reference_arm(args):
     sample = (f"unmodified reference (randomForestSRC.c + splitCustom.c, gcc -O2 -fopenmp) on a bounded sample of the workload: "
               f"n={sample_n} of {cfg['n']} CPIUs x p={cfg['p']}, L={cfg['levels']} levels, ntree={ntree} (>= 1 tree per core), "
               f"nodesize={cfg['nodesize']}, poisson.split{cfg['rule']}; the reference allocates ~64*n*ntree bytes and is "
-              f"O(m * #distinct) per covariate, so the full n=1e6 x ntree=500 point is out of its reach (BASELINE.md 3)")
+              f"O(m * #distinct) per covariate, so the full n=1e6 x ntree=500 point is out of its reach (BASELINE.md 3); "
+              f"the GPU arm's cpu_baseline.same_job times the device path on exactly this job")
     line = {
         "impl": "reference", "metric": "trees_per_sec", "value": value, "unit": "trees/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -152,14 +153,12 @@ def run_reference_arm(args):
     return 0
 
 
-def ncu_traffic(cfg):
-    """DRAM bytes of one tree-kernel launch from the committed `ncu --set full` capture of this workload
-    (profiles/ncu_traffic_r01.json); None for any other workload (nothing is measured under a profiler here)."""
+def ncu_traffic(name):
+    """DRAM bytes of one tree-kernel launch of a workload from the committed `ncu --set full` capture of it
+    (profiles/ncu_traffic_r02.json); nothing is measured under a profiler here."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
-        wl = t["workload"]
-        same = all(int(wl[k]) == int(cfg[k]) for k in ("n", "p", "ntree", "levels", "nodesize", "rule"))
-        return float(t["dram_bytes_per_launch"]) if same else None
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")))
+        return float(t[name]["dram_bytes_per_launch"])
     except Exception:
         return None
 
@@ -177,16 +176,21 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=0, help="override rows (debug; not --n: torchrun abbreviates it to --nnodes)")
     ap.add_argument("--trees", type=int, default=0, help="override trees per GPU (debug)")
-    ap.add_argument("--ref-sample-n", type=int, default=100_000)
+    ap.add_argument("--ref-sample-n", type=int, default=REF_SAMPLE_N)
     ap.add_argument("--ref-ntree", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-only", action="store_true", help="internal: measure only the host-buffer leg and print {e2e_s, h2d, d2h}")
+    ap.add_argument("--no-c3", action="store_true", help="skip the configs[2] record (10M x 100, 1000 trees)")
+    ap.add_argument("--c3-rows", type=int, default=0)
+    ap.add_argument("--c3-trees", type=int, default=0)
+    ap.add_argument("--no-predict", action="store_true", help="skip the rfsrcPredict record")
+    ap.add_argument("--predict-rows", type=int, default=2_000_000, help="held-out rows per job for the predict record")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
 
     import torch
     import rfslam_b200
+    from rfslam_b200 import capi, shard
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = dict(WORKLOAD)
     if args.rows:
@@ -197,30 +201,16 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: rfslam_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dist = None
+    comm = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        comm = shard.Comm.from_torch(local)                      # the library's own NCCL communicator (csrc/comm.cu)
 
     d = make_data(cfg)
     n, p = d.n, d.p
     forest_ntree = cfg["ntree"] * world                      # weak scaling: every rank grows cfg.ntree trees
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
-    if args.e2e_only:                                        # child of a failed in-process e2e leg (see below)
-        times = []
-        fe = None
-        for it in range(2 + max(1, min(args.steps, 2))):
-            fe = None
-            flush.fill_(1)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            fe = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, splitrule=cfg["rule"], ntree=forest_ntree, nodesize=cfg["nodesize"], seed=cfg["seed"],
-                                   k_for_alpha=cfg["k_for_alpha"], device=local)
-            torch.cuda.synchronize()
-            if it > 1:
-                times.append(time.perf_counter() - t0)
-        print(json.dumps({"e2e_s": float(np.mean(times)), "h2d": int(d.x.nbytes + d.y.nbytes + d.rt.nbytes + d.strat.nbytes),
-                          "d2h": int(sum(int(v.nbytes) for v in fe.values() if isinstance(v, np.ndarray)))}))
-        return 0
     ds = rfslam_b200.ResidentCpiu(d.x, d.y, d.rt, d.strat, device=local)
 
     def barrier():
@@ -228,19 +218,25 @@ def main():
         if dist is not None:
             dist.barrier()
 
+    def max_over_ranks(vals):
+        if dist is None:
+            return [float(v) for v in vals]
+        t = torch.tensor(vals, device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def sum_over_ranks(vals):
+        if dist is None:
+            return [float(v) for v in vals]
+        t = torch.tensor(vals, device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
     def one_step():
-        f = ds.grow(splitrule=cfg["rule"], ntree=forest_ntree, nodesize=cfg["nodesize"], seed=cfg["seed"], k_for_alpha=cfg["k_for_alpha"],
-                    tree_first=rank + 1, tree_step=world, finalize=(world == 1))
-        if dist is not None:
-            # the one exchange of the path: sum the ensemble numerators / denominators over ranks
-            # (rf.c:944-949) and tell every rank the shards' forest sizes; the records stay sharded by tree
-            from rfslam_b200 import shard
-            f = shard.allreduce_ensembles(f, device="cuda")
-            sizes = torch.tensor([f["treeID"].size, int(f["leafCount"].sum())], device="cuda")
-            gathered = [torch.zeros_like(sizes) for _ in range(world)]
-            dist.all_gather(gathered, sizes)
-            torch.cuda.synchronize()
-        return f
+        # N > 1: the all-reduce of the ensemble sums and the gather of the forest records to rank 0 happen inside
+        # the call, on device buffers (comm); every rank returns the whole forest's ensembles, rank 0 its records
+        return ds.grow(splitrule=cfg["rule"], ntree=forest_ntree, nodesize=cfg["nodesize"], seed=cfg["seed"], k_for_alpha=cfg["k_for_alpha"],
+                       tree_first=rank + 1, tree_step=world, finalize=True, comm=comm, gather_forest=True)
 
     def timed_resident(count, sample_clocks=False):
         dev_ms, kern_ms, walls = [], [], []
@@ -250,6 +246,7 @@ def main():
         if sampler:
             sampler.start()
         for _ in range(count):
+            last = None                                      # drop the previous forest: its page-locked blocks are reused
             flush.fill_(1)
             barrier()
             t0 = time.perf_counter()
@@ -262,114 +259,167 @@ def main():
 
     timed_resident(args.warmup)
     walls, dev_ms, kern_ms, f, clocks = timed_resident(args.steps, sample_clocks=True)
-    step_s = float(np.mean(walls))
-    if dist is not None:
-        t = torch.tensor([step_s, float(np.mean(kern_ms)), float(np.mean(dev_ms))], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_s, kern_mean, dev_mean = [float(v) for v in t.tolist()]
-        tot = torch.tensor([f["split_candidates"], f["algorithmic_bytes"], f["treeID"].size], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tot)
-        cand_total, algo_total, nodes_total = [float(v) for v in tot.tolist()]
-    else:
-        kern_mean, dev_mean = float(np.mean(kern_ms)), float(np.mean(dev_ms))
-        cand_total, algo_total, nodes_total = float(f["split_candidates"]), float(f["algorithmic_bytes"]), float(f["treeID"].size)
+    step_s, kern_mean, dev_mean, memb_ms, boot_ms, coll_ms = max_over_ranks(
+        [float(np.mean(walls)), float(np.mean(kern_ms)), float(np.mean(dev_ms)), f["membership_kernel_ms"], f["bootstrap_ms"], f["collective_ms"]])
+    cand_total, algo_grow, algo_memb, algo_boot = sum_over_ranks(
+        [f["split_candidates"], f["grow_kernel_algorithmic_bytes"], f["membership_algorithmic_bytes"], f["bootstrap_algorithmic_bytes"]])
+    nodes_total = float(f["treeID"].size) if world == 1 else sum_over_ranks([float(f["treeID"].size)])[0]     # rank 0 holds the gathered forest
+    launches_step = int(f["kernel_launches"])
 
-    # ---- e2e: the same forest through the public host-buffer call (upload + rank-code + grow + download) ----
+    # ---- e2e: the same forest through the public host-buffer call (upload + rank-code + grow + exchange + download).
+    # A device fault here is a failed benchmark: nothing is caught.
     def e2e_step():
         return rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, splitrule=cfg["rule"], ntree=forest_ntree, nodesize=cfg["nodesize"], seed=cfg["seed"],
-                                 k_for_alpha=cfg["k_for_alpha"], device=local, tree_first=rank + 1, tree_step=world, finalize=(world == 1))
-    # No collective inside or after this leg: a device fault in one rank must not hang the others (the
-    # one collective of the path, the ensemble all-reduce, is part of the resident step above).  Ranks
-    # start together, time their own calls, and hand rank 0 their mean through a file; the job's e2e
-    # time is the max over ranks.
-    e2e_note = None
+                                 k_for_alpha=cfg["k_for_alpha"], device=local, tree_first=rank + 1, tree_step=world, finalize=True,
+                                 comm=comm, gather_forest=True)
     h2d = d.x.nbytes + d.y.nbytes + d.rt.nbytes + d.strat.nbytes
-    d2h = 0
-    barrier()
-    try:
-        e2e_times = []
-        fe = None
-        for it in range(2 + max(1, min(args.steps, 2))):         # two untimed calls: page-locked output blocks and device scratch get recycled from the third on
-            fe = None                                            # the caller drops the previous forest before asking for the next
-            flush.fill_(1)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            fe = e2e_step()
-            torch.cuda.synchronize()
-            if it > 1:
-                e2e_times.append(time.perf_counter() - t0)
-        e2e_s = float(np.mean(e2e_times))
-        d2h = sum(int(v.nbytes) for v in fe.values() if isinstance(v, np.ndarray))
-    except Exception as e:                                       # a CUDA fault poisons this process
-        e2e_s = None
-        e2e_note = f"in-process e2e leg failed on rank {rank} ({type(e).__name__}: {str(e)[:160]})"
-        sys.stderr.write("[bench] " + e2e_note + "\n")
-        if world == 1:                                           # measure the leg in a fresh process
-            cmd = [sys.executable, os.path.abspath(__file__), "--e2e-only", "--steps", str(args.steps), "--warmup", str(args.warmup), "--no-cpu-baseline"]
-            if args.rows: cmd += ["--rows", str(args.rows)]
-            if args.trees: cmd += ["--trees", str(args.trees)]
-            outp = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
-            child = json.loads(outp.stdout.strip().split("\n")[-1])
-            e2e_s, h2d, d2h = child["e2e_s"], child["h2d"], child["d2h"]
-            e2e_note += "; measured in a fresh process"
-    if world > 1:
-        tag = os.environ.get("MASTER_PORT", "0") + "_" + os.environ.get("TORCHELASTIC_RUN_ID", "x")
-        mine = os.path.join("/tmp", f"rfslam_bench_e2e_{tag}_{rank}.json")
-        with open(mine + ".tmp", "w") as fh:
-            json.dump({"e2e_s": e2e_s, "d2h": int(d2h), "note": e2e_note}, fh)
-        os.replace(mine + ".tmp", mine)
-        if rank == 0:
-            got, deadline = {}, time.time() + 900
-            while len(got) < world and time.time() < deadline:
-                for r in range(world):
-                    fn = os.path.join("/tmp", f"rfslam_bench_e2e_{tag}_{r}.json")
-                    if r not in got and os.path.exists(fn):
-                        got[r] = json.load(open(fn)); os.remove(fn)
-                time.sleep(0.05)
-            ok = [v["e2e_s"] for v in got.values() if v.get("e2e_s")]
-            notes = [v["note"] for v in got.values() if v.get("note")] + ([f"{world - len(got)} rank(s) did not report"] if len(got) < world else [])
-            e2e_s = max(ok) if ok else None
-            d2h = max([v["d2h"] for v in got.values()] + [0])
-            e2e_note = "; ".join(notes) if notes else None
+    e2e_times = []
+    fe = None
+    for it in range(2 + max(5, min(args.steps, 10))):        # two untimed calls: page-locked output blocks and device scratch get recycled from the third on
+        fe = None                                            # the caller drops the previous forest before asking for the next
+        flush.fill_(1)
+        barrier()
+        t0 = time.perf_counter()
+        fe = e2e_step()
+        barrier()
+        if it > 1:
+            e2e_times.append(time.perf_counter() - t0)
+    e2e_s = max_over_ranks([float(np.mean(e2e_times))])[0]
+    d2h = max_over_ranks([float(sum(int(v.nbytes) for v in fe.values() if isinstance(v, np.ndarray)))])[0]
+    fe = None
 
     trees_total = cfg["ntree"] * world
     peak, peak_src = measured_peak_gbs()
-    achieved = (algo_total / world) / 1e9 / (kern_mean / 1e3)        # per GPU, the tree kernel of one launch
+    achieved = (algo_grow / world) / 1e9 / (kern_mean / 1e3)        # per GPU, the tree kernel of one launch: its own bytes / its own time
     line = {
         "metric": "trees_per_sec", "value": trees_total / step_s, "unit": "trees/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(cfg), "n": n, "p": p, "ntree_total": trees_total, "l2": "256 MB flush buffer written between timed steps",
-                   "parallelism": f"tree-sharded x{world}"},
+                   "parallelism": f"tree-sharded x{world}" + ("; NCCL all-reduce of the ensemble sums + gather of the forest records to rank 0 inside the step" if world > 1 else "")},
         "split_candidates_per_sec": cand_total / step_s,
         "device_ms_per_step": dev_mean, "grow_kernel_ms_per_step": kern_mean, "forest_nodes": nodes_total,
         "clocks": clocks,
-        "e2e": dict({"value": (trees_total / e2e_s) if e2e_s else None, "unit": "trees/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                     "ms_per_step": (1e3 * e2e_s) if e2e_s else None},
-                    **({"note": e2e_note} if e2e_note else {})),
-        "gpu_launches": int(f["kernel_launches"]) * args.steps,
+        "e2e": {"value": trees_total / e2e_s, "unit": "trees/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * e2e_s, "timed_calls": len(e2e_times)},
+        "gpu_launches": launches_step * args.steps,
         "roofline": {"bound": "hbm", "kernel": "rfslam_grow_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_total / world, "kernel_ms": kern_mean,
-                     "traffic": ncu_traffic(cfg), "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum)"},
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_grow / world, "kernel_ms": kern_mean,
+                     "traffic": ncu_traffic("configs1"), "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                     "other_kernels": [
+                         {"kernel": "membership_kernel", "algorithmic_bytes_per_step": algo_memb / world, "ms": memb_ms,
+                          "achieved": (algo_memb / world) / 1e9 / max(memb_ms / 1e3, 1e-9)},
+                         {"kernel": "bootstrap_draw_kernel + bag_count_kernel", "algorithmic_bytes_per_step": algo_boot / world, "ms": boot_ms,
+                          "achieved": (algo_boot / world) / 1e9 / max(boot_ms / 1e3, 1e-9)}]},
     }
+    if comm is not None:
+        line["comm"] = dict(comm.collectives(), collective_ms_per_step=coll_ms, nccl_version=int(capi.lib().rfslam_b200_nccl_version()))
+
+    # ---- predict record: rfsrcPredict of the step's forest, held-out rows sharded over the ranks ----
+    if not args.no_predict:
+        from rfslam_b200.synth import make_cpiu_torch
+        # forest replicated: at N > 1 every rank grows the same cfg.ntree-tree forest for this record (trees are
+        # deterministic, so the replicas are identical); the held-out rows are what is sharded
+        fp = f if world == 1 else ds.grow(splitrule=cfg["rule"], ntree=cfg["ntree"], nodesize=cfg["nodesize"], seed=cfg["seed"], k_for_alpha=cfg["k_for_alpha"])
+        m_total = args.predict_rows
+        fx = make_cpiu_torch(m_total, cfg["p"], levels=cfg["levels"], seed=20260102, device=f"cuda:{local}").x
+        lo = rank * (m_total // world)
+        cnt = (m_total // world) if rank < world - 1 else m_total - lo
+        pr = None
+        ptimes = []
+        for it in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            pr = rfslam_b200.predict_rfsrc(fp, fx, membership=False, device=local, frow_first=lo, frow_count=cnt)
+            barrier()
+            ptimes.append(time.perf_counter() - t0)
+        p_s, p_kern = max_over_ranks([float(np.mean(ptimes[1:])), pr["kernel_ms"]])
+        visits, rowtrees = sum_over_ranks([pr["node_visits"], pr["row_tree_visits"]])
+        pbytes = 24.0 * visits + 8.0 * rowtrees                  # B_pred = d * (8 + 16) + 8 per (row, tree)
+        line["predict"] = {"metric": "row_trees_per_sec", "value": rowtrees / p_s, "rows": m_total, "trees": int(fp["leafCount"].size),
+                           "ms_per_call": 1e3 * p_s, "route_kernel_ms": p_kern, "mean_depth": visits / max(rowtrees, 1.0),
+                           "h2d_bytes_per_call": int(fx.nbytes // world + sum(int(fp[k].nbytes) for k in ("treeID", "nodeID", "parmID", "contPT", "tnCLAS"))),
+                           "roofline": {"bound": "hbm", "kernel": "route_kernel", "achieved": pbytes / world / 1e9 / max(p_kern / 1e3, 1e-9), "peak": peak,
+                                        "unit": "GB/s", "frac": pbytes / world / 1e9 / max(p_kern / 1e3, 1e-9) / peak, "algorithmic_bytes_per_call": pbytes / world},
+                           "sharding": f"held-out rows split over {world} rank(s), forest replicated, no collective"}
+        del fx, pr, fp
+
+    # ---- cpu baseline (rank 0, N = 1): the unmodified reference on a bounded sample, and the SAME job on the device ----
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            cores = os.cpu_count() or 1
-            nt = max(cores, 8)
-            sd, _, dt = cpu_reference_sample(cfg, sample_n=args.ref_sample_n, ntree=nt, threads=-1)
-            cands = count_candidates_gpu(sd, cfg, nt)
-            line["cpu_baseline"] = {
-                "value": nt / dt, "unit": "trees/s", "cores": cores, "kind": "reference",
-                "split_candidates_per_sec": cands / dt,
-                "sample": (f"unmodified reference C (OpenMP, {cores} host threads) on n={args.ref_sample_n} of {cfg['n']} CPIUs x p={cfg['p']}, "
-                           f"L={cfg['levels']}, ntree={nt}, nodesize={cfg['nodesize']}, poisson.split{cfg['rule']}: {dt:.1f} s")}
-        except Exception as e:   # the baseline is a reported figure, never the product path
-            line["cpu_baseline"] = {"value": None, "unit": "trees/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+        from tests import parity
+        from oracle import refdriver
+        cores = os.cpu_count() or 1
+        nt = max(cores, 8)
+        sd, ref, dt = cpu_reference_sample(cfg, sample_n=args.ref_sample_n, ntree=nt, threads=-1, membership=True)
+        same = None
+        gts = []
+        for it in range(3):
+            t0 = time.perf_counter()
+            same = rfslam_b200.rfsrc(sd.x, sd.y, sd.rt, sd.strat, splitrule=cfg["rule"], ntree=nt, nodesize=cfg["nodesize"], seed=cfg["seed"],
+                                     k_for_alpha=cfg["k_for_alpha"], membership=True, split_stat=True)
+            gts.append(time.perf_counter() - t0)
+        # outside every timed region: the two forests of this sample must be the same forest
+        rt = refdriver.trim_forest(ref, sd.n)
+        order = np.argsort(rt["treeID"], kind="stable")
+        for k in ("treeID", "nodeID", "parmID", "contPT", "mwcpSZ"):
+            rt[k] = rt[k][order]
+        from oracle import port
+        chk = parity.assert_forest_equal(same, rt, sd.n, nt, label="bench sample", tie_aware=True,
+                                         ref_stat=lambda: port.grow(sd.x, sd.y, sd.rt, sd.strat, rule=cfg["rule"], ntree=nt, nodesize=cfg["nodesize"], seed=cfg["seed"]))
+        g_s = float(np.min(gts[1:]))
+        line["cpu_baseline"] = {
+            "value": nt / dt, "unit": "trees/s", "cores": cores, "kind": "reference",
+            "split_candidates_per_sec": int(same["split_candidates"]) / dt,
+            "sample": (f"unmodified reference C (OpenMP, {cores} host threads) on n={args.ref_sample_n} of {cfg['n']} CPIUs x p={cfg['p']}, "
+                       f"L={cfg['levels']}, ntree={nt}, nodesize={cfg['nodesize']}, poisson.split{cfg['rule']}: {dt:.1f} s"),
+            "same_job": {"what": "the device path through rfslam_b200.rfsrc() from host buffers on exactly this sample and ntree",
+                         "value": nt / g_s, "unit": "trees/s", "ms": 1e3 * g_s, "ratio": (nt / g_s) / (nt / dt),
+                         "forest_identical": True, "ties": chk["ties"], "trees_compared": chk["trees_compared"]}}
+        del sd, ref, same
+
+    # ---- c3: BASELINE configs[2], ONE forest of C3.ntree trees sharded over the ranks (strong scaling) ----
+    if not args.no_c3:
+        from rfslam_b200.synth import make_cpiu_torch
+        c3 = dict(C3)
+        if args.c3_rows:
+            c3["n"] = args.c3_rows
+        if args.c3_trees:
+            c3["ntree"] = args.c3_trees
+        ds.close()
+        del ds, d, f
+        flush = None
+        torch.cuda.empty_cache()
+        capi.lib().rfslam_b200_host_pool_trim()
+        d3 = make_cpiu_torch(c3["n"], c3["p"], levels=c3["levels"], device=f"cuda:{local}")
+        torch.cuda.empty_cache()
+        ds3 = rfslam_b200.ResidentCpiu(d3.x, d3.y, d3.rt, d3.strat, device=local)
+        barrier()
+        t0 = time.perf_counter()
+        f3 = ds3.grow(splitrule=c3["rule"], ntree=c3["ntree"], nodesize=c3["nodesize"], seed=c3["seed"], k_for_alpha=c3["k_for_alpha"],
+                      tree_first=rank + 1, tree_step=world, finalize=True, comm=comm, gather_forest=False)
+        barrier()
+        c3_s = time.perf_counter() - t0
+        c3_s, c3_kern = max_over_ranks([c3_s, f3["grow_kernel_ms"]])
+        c3_algo, c3_cand, c3_nodes = sum_over_ranks([f3["grow_kernel_algorithmic_bytes"], f3["split_candidates"], float(f3["treeID"].size)])
+        a3 = (c3_algo / world) / 1e9 / (c3_kern / 1e3)
+        line["c3"] = {"workload": (f"BASELINE configs[2]: {c3['n']} CPIUs x {c3['p']} covariates (mode Q, {c3['levels']} levels, generated on the device), "
+                                   f"ONE forest of ntree={c3['ntree']} sharded over {world} GPU(s), mtry=ceil(sqrt(p))=10, nodesize={c3['nodesize']}, poisson.split{c3['rule']}"),
+                      "scaling": "strong", "trees": c3["ntree"], "trees_per_gpu": len(range(rank + 1, c3["ntree"] + 1, world)), "steps": 1, "warmup": 0,
+                      "value": c3["ntree"] / c3_s, "unit": "trees/s", "ms_per_step": 1e3 * c3_s, "grow_kernel_ms": c3_kern,
+                      "split_candidates_per_sec": c3_cand / c3_s, "forest_nodes": c3_nodes, "table_bytes_hbm": int(ds3.hbm_bytes),
+                      "roofline": {"bound": "hbm", "kernel": "rfslam_grow_kernel", "achieved": a3, "peak": peak, "unit": "GB/s", "frac": a3 / peak,
+                                   "algorithmic_bytes_per_launch": c3_algo / world, "traffic": ncu_traffic("configs2"),
+                                   "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum)"}}
+        line["gpu_launches"] += int(f3["kernel_launches"])
+        ds3.close()
+
     if rank == 0:
         print(json.dumps(line))
     sys.stdout.flush(); sys.stderr.flush()
-    if dist is not None or e2e_note:
-        os._exit(0)              # no collective teardown: a rank whose context faulted in the e2e leg must not hang the rest
-    ds.close()
+    if comm is not None:
+        comm.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 

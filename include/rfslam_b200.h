@@ -46,6 +46,7 @@ extern "C" {
 /* Mirrors the 44 .Call arguments of rfsrcGrow in their order (rf.c:22110-22155); scalars by value,
    vectors as pointers.  Fields the Poisson class path never reads are kept so that a binding can
    forward every argument; they are validated, not ignored (see rfslam_b200_grow). */
+struct rfslam_comm;
 typedef struct rfslam_grow_args {
   int32_t        trace_flag;
   int32_t        seed;                /* must be < 0 (rf.c:6454) */
@@ -101,6 +102,11 @@ typedef struct rfslam_grow_args {
   int32_t        finalize_ensembles;  /* 1: divide by the denominators (single process); 0: return sums */
   int32_t        want_split_stat;     /* 1: also return splitStat (the winning delta per node) */
   int32_t        want_member_lists;   /* 1 (with RFSLAM_OPTH_MEMB_OUTG): also return rmbr/ambrMembership, 8 bytes x n x ntree */
+  struct rfslam_comm *comm;           /* tree-sharded forest over several GPUs (rfslam_b200_comm_init): the ensemble sums are
+                                         all-reduced ON THE DEVICE before they are finalized and sent home, so every rank returns the
+                                         whole forest's oob/allEnsbCLS (and perfClas); NULL = this process is the whole job */
+  int32_t        gather_forest;       /* with comm: 1 = gather the shards' forest records to rank 0 over NCCL and return the whole
+                                         forest there in ascending treeID order (other ranks return no records); 0 = records stay sharded */
 } rfslam_grow_args;
 
 /* The reference's named output list for the class family (rf.c:9-79), sized by the
@@ -133,7 +139,7 @@ typedef struct rfslam_forest_out {
   uint32_t *allEnsbDen;        /* [n] */
   /* measurement */
   int64_t   split_candidates;  /* (node, covariate, cutpoint) triples scored */
-  int64_t   algorithmic_bytes; /* sum over attempted nodes of B_score + B_part + 4n per tree */
+  int64_t   algorithmic_bytes; /* sum over attempted nodes of B_score + B_part + 4n per tree = the three below */
   double    grow_kernel_ms;    /* device time of the tree-growing kernel(s), CUDA events */
   double    total_device_ms;   /* device time of the whole call incl. bootstrap and ensembles */
   int64_t   kernel_launches;   /* kernels of this library launched by the call */
@@ -148,6 +154,15 @@ typedef struct rfslam_forest_out {
   int32_t  *mwcpPT;            /* [mwcp_total] or NULL when the forest has no factor split */
   int32_t  *mwcpCT;            /* [ntree] words per tree */
   int64_t   mwcp_total;
+  /* algorithmic bytes and device time kernel by kernel: the tree kernel owns B_score and the in-bag
+     half of B_part, the traversal kernel the all-row half (16 B per row per split node on its path), the
+     bootstrap replay the 4 B per draw */
+  int64_t   grow_kernel_algorithmic_bytes;
+  int64_t   membership_algorithmic_bytes;
+  int64_t   bootstrap_algorithmic_bytes;
+  double    membership_kernel_ms;
+  double    bootstrap_ms;
+  double    collective_ms;     /* all-reduce (+ gather) through comm, host clock around the device work */
 } rfslam_forest_out;
 
 int  rfslam_b200_grow(const rfslam_grow_args *args, rfslam_forest_out *out);
@@ -158,6 +173,23 @@ void rfslam_b200_free_forest(rfslam_forest_out *out);
    frees the device scratch rfslam_b200_grow keeps between calls. */
 void rfslam_b200_free_array(void *array);
 void rfslam_b200_host_pool_trim(void);
+
+/* ---------------------------------------------------------------- multi-GPU ------------------- */
+/* One process per GPU; rank r grows trees r+1, r+1+world, ... (tree_first = rank + 1, tree_step = world) of the same
+   ntree-tree forest with a full replica of the table -- nothing is exchanged while trees grow (rf.c:7082-7087).  The
+   communicator (NCCL, bound at run time) carries the one exchange after growth: the all-reduce of the ensemble sums
+   (rf.c:944-949) and, on request, the gather of the forest records to rank 0 (rf.c:20938-20946).  The 128-byte id
+   made by rank 0 travels to the other ranks by whatever the host program has (torch.distributed, MPI, a file). */
+typedef struct rfslam_comm rfslam_comm;
+#define RFSLAM_COMM_ID_BYTES 128
+int  rfslam_b200_comm_unique_id(void *id, int bytes);
+int  rfslam_b200_comm_init(rfslam_comm **comm, int rank, int world, const void *id, int device);
+void rfslam_b200_comm_destroy(rfslam_comm *comm);
+int  rfslam_b200_comm_rank(const rfslam_comm *comm);
+int  rfslam_b200_comm_world(const rfslam_comm *comm);
+/* collectives issued so far through this communicator (returns their sum) */
+int64_t rfslam_b200_comm_collectives(const rfslam_comm *comm, int64_t *allreduces, int64_t *gathers);
+int  rfslam_b200_nccl_version(void);
 
 /* Resident variant: upload + rank-code the CPIU table once, grow many forests from HBM.
    rfslam_b200_grow() == dataset_create + grow_resident + dataset_destroy. */

@@ -34,6 +34,7 @@ class GrowArgs(C.Structure):
         ("n_impute", C.c_int32), ("perf_block", C.c_int32), ("num_threads", C.c_int32),
         ("device", C.c_int32), ("tree_first", C.c_int32), ("tree_step", C.c_int32), ("finalize_ensembles", C.c_int32),
         ("want_split_stat", C.c_int32), ("want_member_lists", C.c_int32),
+        ("comm", C.c_void_p), ("gather_forest", C.c_int32),
     ]
 
 
@@ -47,6 +48,8 @@ class ForestOut(C.Structure):
         ("split_candidates", C.c_int64), ("algorithmic_bytes", C.c_int64),
         ("grow_kernel_ms", C.c_double), ("total_device_ms", C.c_double), ("kernel_launches", C.c_int64), ("rmbr_stride", C.c_int64), ("perfClas", _pd),
         ("mwcpPT", _pi), ("mwcpCT", _pi), ("mwcp_total", C.c_int64),
+        ("grow_kernel_algorithmic_bytes", C.c_int64), ("membership_algorithmic_bytes", C.c_int64), ("bootstrap_algorithmic_bytes", C.c_int64),
+        ("membership_kernel_ms", C.c_double), ("bootstrap_ms", C.c_double), ("collective_ms", C.c_double),
     ]
 
 
@@ -88,6 +91,8 @@ SYMBOLS = [
     "rfslam_b200_rule_of_slot", "rfslam_b200_register_this", "rfslam_b200_register_defaults",
     "rfslam_b200_score_node", "rfslam_b200_bootstrap_counts", "rfslam_b200_last_error", "rfslam_b200_version",
     "rfslam_b200_device_count", "rfslam_b200_last_profile", "rfslam_b200_free_array", "rfslam_b200_host_pool_trim",
+    "rfslam_b200_comm_unique_id", "rfslam_b200_comm_init", "rfslam_b200_comm_destroy", "rfslam_b200_comm_rank",
+    "rfslam_b200_comm_world", "rfslam_b200_comm_collectives", "rfslam_b200_nccl_version",
 ]
 # the reference's own plugin symbols, exported with its signatures (src/splitCustom.h:24-44, src/splitCustom.c:23-67)
 REFERENCE_SYMBOLS = ["registerThis", "registerCustomFunctions"] + [f"poissonSplit{k}" for k in range(1, 7)]
@@ -133,6 +138,13 @@ def lib():
         L.rfslam_b200_last_profile.restype = C.c_int; L.rfslam_b200_last_profile.argtypes = [C.POINTER(C.c_uint64), C.c_int]
         L.rfslam_b200_free_array.restype = None; L.rfslam_b200_free_array.argtypes = [vp]
         L.rfslam_b200_host_pool_trim.restype = None; L.rfslam_b200_host_pool_trim.argtypes = []
+        L.rfslam_b200_comm_unique_id.restype = C.c_int; L.rfslam_b200_comm_unique_id.argtypes = [vp, C.c_int]
+        L.rfslam_b200_comm_init.restype = C.c_int; L.rfslam_b200_comm_init.argtypes = [C.POINTER(vp), C.c_int, C.c_int, vp, C.c_int]
+        L.rfslam_b200_comm_destroy.restype = None; L.rfslam_b200_comm_destroy.argtypes = [vp]
+        L.rfslam_b200_comm_rank.restype = C.c_int; L.rfslam_b200_comm_rank.argtypes = [vp]
+        L.rfslam_b200_comm_world.restype = C.c_int; L.rfslam_b200_comm_world.argtypes = [vp]
+        L.rfslam_b200_comm_collectives.restype = C.c_int64; L.rfslam_b200_comm_collectives.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.rfslam_b200_nccl_version.restype = C.c_int; L.rfslam_b200_nccl_version.argtypes = []
         L.registerThis.restype = None; L.registerThis.argtypes = [C.c_void_p, C.c_uint, C.c_uint]
         L.registerCustomFunctions.restype = None; L.registerCustomFunctions.argtypes = []
         for k in range(1, 7):

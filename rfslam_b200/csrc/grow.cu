@@ -4,6 +4,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -313,6 +314,10 @@ int validate_grow_args(const rfslam_grow_args* a, GrowConfig* cfg) {
   cfg->want_membr_lists = (a->opt_high & RFSLAM_OPTH_MEMB_OUTG) != 0 && a->want_member_lists != 0;
   cfg->finalize = a->finalize_ensembles != 0;
   if (cfg->by_user && !a->bootstrap) { set_error("bootstrap = by.user needs the samp matrix"); return RFSLAM_EINVAL; }
+  if (a->comm && a->gather_forest && (cfg->want_membership || cfg->want_membr_lists)) {
+    set_error("per-row membership outputs stay with the shard that grew the tree: ask for them without gather_forest");
+    return RFSLAM_ENOSUP;
+  }
   return RFSLAM_OK;
 }
 
@@ -428,6 +433,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     size_t fixed = (size_t)n * (16 + 16 + 8) + (64u << 20);
     int B = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, (budget > fixed ? budget - fixed : 0) / (perTree + estNodes * 80)));
     if (const char* e = getenv("RFSLAM_TREES_PER_BATCH")) { int v = atoi(e); if (v > 0) B = std::min(T, v); }
+    B = (T + (T + B - 1) / B - 1) / ((T + B - 1) / B);             // equal batches: 1000 trees with room for 900 run as 500 + 500, not 900 + 100
 
     // ---- persistent accumulators ----
     DevBuf<double> d_allNum(pool), d_oobNum(pool); DevBuf<uint32_t> d_allDen(pool), d_oobDen(pool);
@@ -445,7 +451,30 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     HostOut<double> h_contPT, h_stat;
     std::vector<int32_t> h_leafCount(T), h_seed(T);
     long long totalCand = 0, totalAlgo = 0, launches = 0;
-    float growMs = 0.f, totalMs = 0.f;
+    float growMs = 0.f, totalMs = 0.f, membMs = 0.f, bootMs = 0.f;
+    long long bootDraws = 0;
+    rfslam_comm* comm = (a->comm && comm_world(a->comm) > 1) ? a->comm : nullptr;
+    const bool gather = comm && a->gather_forest != 0;
+    // gathering: the shard's records stay on the device (appended batch by batch) instead of going home
+    struct Acc {
+      WsPool* pool; void* p = nullptr; size_t used = 0, cap = 0;
+      explicit Acc(WsPool* pl) : pool(pl) {}
+      ~Acc() { if (p) pool->put(p); }
+      void append(const void* src, size_t bytes, size_t hint) {
+        if (used + bytes > cap) {
+          const size_t ncap = std::max<size_t>({used + bytes, 2 * cap, hint});
+          void* q = pool->get(ncap);
+          if (!q) { set_error("out of device memory (%zu bytes)", ncap); throw CudaFail{RFSLAM_ENOMEM}; }
+          if (used) RF_CUDA(cudaMemcpyAsync(q, p, used, cudaMemcpyDeviceToDevice));
+          RF_CUDA(cudaDeviceSynchronize());
+          if (p) pool->put(p);
+          p = q; cap = ncap;
+        }
+        if (bytes) RF_CUDA(cudaMemcpyAsync((char*)p + used, src, bytes, cudaMemcpyDeviceToDevice));
+        used += bytes;
+      }
+    };
+    Acc g_tree(pool), g_node(pool), g_parm(pool), g_cont(pool), g_stat(pool), g_rcnt(pool), g_acnt(pool), g_clas(pool);
     // events and the copy stream are released on every exit path; the stream is drained first, so no copy can
     // still target a page-locked output block when the HostOut destructors (declared above) hand it back
     struct Sync {
@@ -456,6 +485,8 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     RF_CUDA(cudaEventCreateWithFlags(&sync.e[4], cudaEventDisableTiming));
     RF_CUDA(cudaStreamCreateWithFlags(&sync.st, cudaStreamNonBlocking));   // forest records go home while the traversal kernel runs
     cudaEvent_t ev0 = sync.e[0], ev1 = sync.e[1], ev2 = sync.e[2], ev3 = sync.e[3], evC = sync.e[4];
+    struct Ev2 { cudaEvent_t a = nullptr, b = nullptr; ~Ev2() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } evM;
+    RF_CUDA(cudaEventCreate(&evM.a)); RF_CUDA(cudaEventCreate(&evM.b));
     cudaStream_t copyStream = sync.st;
     const bool wantStat = a->want_split_stat != 0;
 
@@ -560,7 +591,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         RF_CUDA(cudaMemcpy(hAlgo.data(), d_algo.p, nb * 8, cudaMemcpyDeviceToHost));
         for (int t = 0; t < nb; t++) {
           nodeOff[t + 1] = nodeOff[t] + hNodes[t]; leafOff[t + 1] = leafOff[t] + hLeaves[t];
-          totalCand += (long long)hCand[t]; totalAlgo += (long long)hAlgo[t];
+          totalCand += (long long)hCand[t]; totalAlgo += (long long)hAlgo[t]; bootDraws += (long long)hbs[t];
           h_leafCount[b0 + t] = (int32_t)hLeaves[t];
           if (hNodes[t] != 2 * hLeaves[t] - 1) { set_error("internal: tree %d has %u records for %u leaves", hid[t], hNodes[t], hLeaves[t]); throw CudaFail{RFSLAM_EINVAL}; }
         }
@@ -576,12 +607,23 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         compact_kernel<<<gk, 256>>>(w, ds->dev, d_ids.p, d_nodeOff.p, d_leafOff.p, f_tree.p, f_node.p, f_parm.p, f_cont.p, f_stat.p,
                                     f_rec4.p, f_rcnt.p, f_clas.p);
         RF_CUDA(cudaEventRecord(evC));
+        RF_CUDA(cudaEventRecord(evM.a));
         membership_kernel<<<(n + 127) / 128, 128>>>(ds->dev, nb, d_nodeOff.p, d_leafOff.p, f_rec4.p,
                                                     f_rcnt.p, f_clas.p, d_cnt.p, f_acnt.p, d_allNum.p, d_oobNum.p, d_allDen.p, d_oobDen.p,
                                                     d_nodeMemb.p, d_bootMemb.p, b0, cntStride, d_pathSum.p);
         launches += 2;
+        RF_CUDA(cudaEventRecord(evM.b));
         RF_CUDA(cudaEventRecord(ev3));
         RF_CUDA(cudaGetLastError());
+        if (gather) {
+          const size_t hintN = (size_t)(estNodes * T), hintL = hintN / 2 + T;
+          g_tree.append(f_tree.p, NN * 4, hintN * 4); g_node.append(f_node.p, NN * 4, hintN * 4); g_parm.append(f_parm.p, NN * 4, hintN * 4);
+          g_cont.append(f_cont.p, NN * 8, hintN * 8);
+          if (wantStat) g_stat.append(f_stat.p, NN * 8, hintN * 8);
+          g_rcnt.append(f_rcnt.p, NL * 4, hintL * 4); g_acnt.append(f_acnt.p, NL * 4, hintL * 4); g_clas.append(f_clas.p, 2 * NL * 4, hintL * 8);
+          RF_CUDA(cudaEventSynchronize(ev3));
+          RF_CUDA(cudaDeviceSynchronize());
+        } else {
         // ---- straight into the caller's arrays: the forest records are final after compaction, so
         // their copies overlap the traversal kernel on a second stream ----
         RF_CUDA(cudaStreamWaitEvent(copyStream, evC, 0));
@@ -594,10 +636,13 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         RF_CUDA(cudaMemcpyAsync(h_tnCLAS.grow(2 * NL), f_clas.p, 2 * NL * 4, cudaMemcpyDeviceToHost, copyStream));
         RF_CUDA(cudaStreamSynchronize(copyStream));
         RF_CUDA(cudaEventSynchronize(ev3));
+        RF_CUDA(cudaMemcpy(h_tnACNT.grow(NL), f_acnt.p, NL * 4, cudaMemcpyDeviceToHost));
+        }
         float ms = 0.f;
         RF_CUDA(cudaEventElapsedTime(&ms, ev1, ev2)); growMs += ms;
         RF_CUDA(cudaEventElapsedTime(&ms, ev0, ev3)); totalMs += ms;
-        RF_CUDA(cudaMemcpy(h_tnACNT.grow(NL), f_acnt.p, NL * 4, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaEventElapsedTime(&ms, ev0, ev1)); bootMs += ms;
+        RF_CUDA(cudaEventElapsedTime(&ms, evM.a, evM.b)); membMs += ms;
         if (cfg.want_membr_lists) {
           DevBuf<uint32_t> d_flag(pool), d_scan(pool), d_lrank(pool), d_k1(pool), d_k2(pool), d_v1(pool), d_v2(pool), d_rows(pool);
           d_flag.alloc(NN); d_scan.alloc(std::max<size_t>(NN, (size_t)n)); d_lrank.alloc(NL);
@@ -643,6 +688,23 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
       }
     }
 
+    // ---- the one exchange of a tree-sharded forest: sum the ensemble accumulators over ranks, on the device ----
+    bool wholeForest = T == cfg.ntree;
+    double collMs = 0.0;
+    auto wall = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    if (comm) {
+      const double t0 = wall();
+      comm_allreduce_ensembles(comm, d_allNum.p, d_oobNum.p, d_allDen.p, d_oobDen.p, n);
+      DevBuf<unsigned long long> d_cntT(pool);
+      d_cntT.alloc(1);
+      const unsigned long long mine = (unsigned long long)T;
+      RF_CUDA(cudaMemcpy(d_cntT.p, &mine, 8, cudaMemcpyHostToDevice));
+      comm_allreduce_sum_u64(comm, d_cntT.p, 1);
+      unsigned long long all = 0;
+      RF_CUDA(cudaMemcpy(&all, d_cntT.p, 8, cudaMemcpyDeviceToHost));
+      wholeForest = all == (unsigned long long)cfg.ntree;      // the ranks of this communicator hold every tree exactly once
+      collMs += wall() - t0;
+    }
     if (cfg.finalize) {
       finalize_kernel<<<(n + 255) / 256, 256>>>(d_allNum.p, d_allDen.p, n);
       finalize_kernel<<<(n + 255) / 256, 256>>>(d_oobNum.p, d_oobDen.p, n);
@@ -651,17 +713,18 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     }
     // perfClas: only for a whole, finalized forest (a shard's ensembles are partial sums)
     double* h_perf = nullptr;
-    if (cfg.finalize && (a->opt_low & RFSLAM_OPT_PERF) && T == cfg.ntree) {
+    if (cfg.finalize && (a->opt_low & RFSLAM_OPT_PERF) && wholeForest) {
       DevBuf<unsigned long long> d_acc(pool);
       d_acc.alloc(5); d_acc.zero();
       perf_kernel<<<296, 256>>>(d_oobNum.p, d_oobDen.p, ds->dev.ev, ds->dev.inv, n, d_acc.p);
       launches++;
       unsigned long long acc[5];
       RF_CUDA(cudaMemcpy(acc, d_acc.p, sizeof acc, cudaMemcpyDeviceToHost));
-      h_perf = (double*)host_alloc((size_t)T * 3 * sizeof(double));
+      const size_t PT = (size_t)cfg.ntree;                         // [ntree][3]; a rank of a sharded forest returns the whole forest's table too
+      h_perf = (double*)host_alloc(PT * 3 * sizeof(double));
       const double na = rfslam_na_real();
-      for (size_t k = 0; k < (size_t)T * 3; k++) h_perf[k] = na;
-      double* last = h_perf + (size_t)(T - 1) * 3;                // serialTreeID == ntree (rf.c:8155)
+      for (size_t k = 0; k < PT * 3; k++) h_perf[k] = na;
+      double* last = h_perf + (PT - 1) * 3;                       // serialTreeID == ntree (rf.c:8155)
       if (acc[2] != 0) {
         last[0] = 1.0 - (double)(acc[3] + acc[4]) / (double)acc[2];
         if (acc[0]) last[1] = 1.0 - (double)acc[3] / (double)acc[0];
@@ -670,18 +733,58 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     }
     unsigned long long pathSum = 0;
     RF_CUDA(cudaMemcpy(&pathSum, d_pathSum.p, 8, cudaMemcpyDeviceToHost));
-    totalAlgo += 16ll * (long long)pathSum;                      // B_part's all-row term
+    const long long growAlgo = totalAlgo;                        // B_score + the in-bag half of B_part: the tree kernel's own
+    const long long membAlgo = 16ll * (long long)pathSum;        // B_part's all-row term: the traversal kernel routes those rows
+    const long long bootAlgo = 4ll * bootDraws;                  // 4 B per bootstrap draw written
+    totalAlgo = growAlgo + membAlgo + bootAlgo;
+
+    // ---- gather the shards' records to rank 0 (NCCL send / recv over NVLink, then a device merge into tree order) ----
+    std::vector<int32_t> allLeaf;
+    if (gather) {
+      const double t0 = wall();
+      RF_CUDA(cudaDeviceSynchronize());
+      comm_allgather_leaf_counts(comm, h_leafCount, cfg.ntree, allLeaf);
+      std::vector<long long> nodeUnits(cfg.ntree), leafUnits(cfg.ntree);
+      for (int b = 0; b < cfg.ntree; b++) { leafUnits[b] = allLeaf[b]; nodeUnits[b] = 2ll * allLeaf[b] - 1; }
+      long long NNall = 0, NLall = 0;
+      for (int b = 0; b < cfg.ntree; b++) { NNall += nodeUnits[b]; NLall += leafUnits[b]; }
+      struct Dev { void* p = nullptr; ~Dev() { if (p) cudaFree(p); } };
+      Dev m_tree, m_node, m_parm, m_cont, m_stat, m_rcnt, m_acnt, m_clas;
+      m_tree.p = comm_gather_i32(comm, (const int32_t*)g_tree.p, nodeUnits, 1);
+      m_node.p = comm_gather_i32(comm, (const int32_t*)g_node.p, nodeUnits, 1);
+      m_parm.p = comm_gather_i32(comm, (const int32_t*)g_parm.p, nodeUnits, 1);
+      m_cont.p = comm_gather_f64(comm, (const double*)g_cont.p, nodeUnits, 1);
+      if (wantStat) m_stat.p = comm_gather_f64(comm, (const double*)g_stat.p, nodeUnits, 1);
+      m_rcnt.p = comm_gather_i32(comm, (const int32_t*)g_rcnt.p, leafUnits, 1);
+      m_acnt.p = comm_gather_i32(comm, (const int32_t*)g_acnt.p, leafUnits, 1);
+      m_clas.p = comm_gather_i32(comm, (const int32_t*)g_clas.p, leafUnits, 2);
+      collMs += wall() - t0;
+      if (comm_rank(comm) == 0) {
+        RF_CUDA(cudaMemcpy(h_treeID.grow((size_t)NNall), m_tree.p, (size_t)NNall * 4, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_nodeID.grow((size_t)NNall), m_node.p, (size_t)NNall * 4, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_parmID.grow((size_t)NNall), m_parm.p, (size_t)NNall * 4, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_contPT.grow((size_t)NNall), m_cont.p, (size_t)NNall * 8, cudaMemcpyDeviceToHost));
+        if (wantStat) RF_CUDA(cudaMemcpy(h_stat.grow((size_t)NNall), m_stat.p, (size_t)NNall * 8, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_tnRCNT.grow((size_t)NLall), m_rcnt.p, (size_t)NLall * 4, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_tnACNT.grow((size_t)NLall), m_acnt.p, (size_t)NLall * 4, cudaMemcpyDeviceToHost));
+        RF_CUDA(cudaMemcpy(h_tnCLAS.grow(2 * (size_t)NLall), m_clas.p, 2 * (size_t)NLall * 4, cudaMemcpyDeviceToHost));
+        // rank 0 now returns the WHOLE forest: every tree id, leaf count and seed
+        ids.resize(cfg.ntree); h_leafCount.resize(cfg.ntree); h_seed.resize(cfg.ntree);
+        for (int b = 0; b < cfg.ntree; b++) { ids[b] = b + 1; h_leafCount[b] = allLeaf[b]; h_seed[b] = seedA[b]; }
+      }
+    }
+    const int Tout = (int)ids.size();
 
     // ---- hand over ----
-    out->ntree = T; out->n = n;
+    out->ntree = Tout; out->n = n;
     out->total_nodes = (int64_t)h_treeID.n; out->total_leaves = (int64_t)h_tnRCNT.n;
-    out->tree_ids = (int32_t*)host_alloc((size_t)T * 4); memcpy(out->tree_ids, ids.data(), (size_t)T * 4);
+    out->tree_ids = (int32_t*)host_alloc((size_t)Tout * 4); memcpy(out->tree_ids, ids.data(), (size_t)Tout * 4);
     out->mwcpSZ = (int32_t*)host_calloc(std::max<size_t>(h_treeID.n, 1) * 4);
-    out->mwcpCT = (int32_t*)host_calloc((size_t)T * 4); out->mwcpPT = nullptr; out->mwcp_total = 0;
+    out->mwcpCT = (int32_t*)host_calloc((size_t)Tout * 4); out->mwcpPT = nullptr; out->mwcp_total = 0;
     out->treeID = h_treeID.release(); out->nodeID = h_nodeID.release(); out->parmID = h_parmID.release();
     out->contPT = h_contPT.release(); out->splitStat = wantStat ? h_stat.release() : nullptr;
-    out->leafCount = (int32_t*)host_alloc((size_t)T * 4); memcpy(out->leafCount, h_leafCount.data(), (size_t)T * 4);
-    out->seed = (int32_t*)host_alloc((size_t)T * 4); memcpy(out->seed, h_seed.data(), (size_t)T * 4);
+    out->leafCount = (int32_t*)host_alloc((size_t)Tout * 4); memcpy(out->leafCount, h_leafCount.data(), (size_t)Tout * 4);
+    out->seed = (int32_t*)host_alloc((size_t)Tout * 4); memcpy(out->seed, h_seed.data(), (size_t)Tout * 4);
     out->tnRCNT = h_tnRCNT.release(); out->tnACNT = h_tnACNT.release(); out->tnCLAS = h_tnCLAS.release();
     out->oobEnsbCLS = host_copy(d_oobNum.p, 2 * (size_t)n); out->allEnsbCLS = host_copy(d_allNum.p, 2 * (size_t)n);
     out->oobEnsbDen = host_copy(d_oobDen.p, (size_t)n); out->allEnsbDen = host_copy(d_allDen.p, (size_t)n);
@@ -697,6 +800,8 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     out->perfClas = h_perf;
     out->split_candidates = totalCand; out->algorithmic_bytes = totalAlgo;
     out->grow_kernel_ms = growMs; out->total_device_ms = totalMs; out->kernel_launches = launches;
+    out->grow_kernel_algorithmic_bytes = growAlgo; out->membership_algorithmic_bytes = membAlgo; out->bootstrap_algorithmic_bytes = bootAlgo;
+    out->membership_kernel_ms = membMs; out->bootstrap_ms = bootMs; out->collective_ms = collMs;
   } catch (CudaFail f) {
     rfslam_b200_free_forest(out);
     return f.code;

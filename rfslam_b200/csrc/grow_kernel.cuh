@@ -1437,7 +1437,6 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     if (tid == 0) {
       s->cur.start = 0; s->cur.len = base; s->cur.m = (uint32_t)(tne >> 32); s->cur.E = (uint32_t)(tne & 0xffffffffu);
       s->cur.rtsum = trt; s->cur.nodeID = 1; s->cur.parentRec = kNone; s->cur.depth = 0; s->cur.buf = 0;
-      s->algoBytes += 4ull * (unsigned long long)w.bootSize[tree];
     }
     __syncthreads();
   }

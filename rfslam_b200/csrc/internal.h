@@ -113,6 +113,17 @@ int  rule_table_get(int family, int slot);            // 1..6 device rule, 0 emp
 void rule_table_set(int family, int slot, int rule);
 bool rule_slot_is_foreign(int family, int slot);
 
+// comm.cu: the exchange step of a tree-sharded forest (NCCL over NVLink), all on device buffers
+void comm_allreduce_ensembles(rfslam_comm* c, double* allNum, double* oobNum, uint32_t* allDen, uint32_t* oobDen, int n);
+void comm_allreduce_sum_u64(rfslam_comm* c, unsigned long long* dev, int count);
+void comm_allgather_leaf_counts(rfslam_comm* c, const std::vector<int32_t>& mine, int ntree, std::vector<int32_t>& all);
+// gather-v to rank 0 + merge into ascending tree order; unitsOfTree[b] = units (of `width` elements) of tree b + 1.
+// Returns the merged DEVICE array on rank 0 (release with cudaFree), nullptr elsewhere.
+int32_t* comm_gather_i32(rfslam_comm* c, const int32_t* local, const std::vector<long long>& unitsOfTree, int width);
+double*  comm_gather_f64(rfslam_comm* c, const double* local, const std::vector<long long>& unitsOfTree, int width);
+int comm_rank(const rfslam_comm* c);
+int comm_world(const rfslam_comm* c);
+
 // R's NA_real_: the NaN with payload 1954 (arithmetic NaN is a different bit pattern)
 inline double rfslam_na_real() { const unsigned long long b = 0x7FF00000000007A2ull; double d; memcpy(&d, &b, 8); return d; }
 

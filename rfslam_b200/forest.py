@@ -59,7 +59,8 @@ class _Packed:
 
     def __init__(self, x, y, risk_time, stratifier, *, splitrule, ntree, mtry, nodesize, nodedepth, seed, k_for_alpha,
                  membership, samp, sampsize, split_wt, device, tree_first, tree_step, finalize, nsplit=0, xvar_types=None,
-                 split_stat=False, member_lists=False, var_categories=None, category_weights=None, bootstrap=None):
+                 split_stat=False, member_lists=False, var_categories=None, category_weights=None, bootstrap=None, comm=None,
+                 gather_forest=False):
         x = np.ascontiguousarray(x, np.float64)
         assert x.ndim == 2, "x must be [p, n]: p contiguous columns of n (randomForestSRC.c:22190)"
         p, n = x.shape
@@ -129,11 +130,13 @@ class _Packed:
         a.finalize_ensembles = 1 if finalize else 0
         a.want_split_stat = 1 if split_stat else 0
         a.want_member_lists = 1 if member_lists else 0
+        a.comm = comm.handle if comm is not None else None
+        a.gather_forest = 1 if (gather_forest and comm is not None) else 0
         self.args = a
         self.n, self.p = n, p
 
 
-def _unpack_forest(o: ForestOut, finalized: bool = True) -> Dict[str, np.ndarray]:
+def _unpack_forest(o: ForestOut, finalized: bool = True, ntree_total: int = 0) -> Dict[str, np.ndarray]:
     n, T, NN, NL = o.n, o.ntree, o.total_nodes, o.total_leaves
     res = {
         "tree_ids": _own(o, "tree_ids", T, np.int32),
@@ -150,6 +153,9 @@ def _unpack_forest(o: ForestOut, finalized: bool = True) -> Dict[str, np.ndarray
         "split_candidates": int(o.split_candidates), "algorithmic_bytes": int(o.algorithmic_bytes),
         "grow_kernel_ms": float(o.grow_kernel_ms), "total_device_ms": float(o.total_device_ms),
         "kernel_launches": int(o.kernel_launches),
+        "grow_kernel_algorithmic_bytes": int(o.grow_kernel_algorithmic_bytes), "membership_algorithmic_bytes": int(o.membership_algorithmic_bytes),
+        "bootstrap_algorithmic_bytes": int(o.bootstrap_algorithmic_bytes), "membership_kernel_ms": float(o.membership_kernel_ms),
+        "bootstrap_ms": float(o.bootstrap_ms), "collective_ms": float(o.collective_ms),
         "finalized": bool(finalized),             # False: oob/allEnsbCLS are the shard's sums (see shard.allreduce_ensembles)
     }
     if o.rmbrMembership:
@@ -159,7 +165,7 @@ def _unpack_forest(o: ForestOut, finalized: bool = True) -> Dict[str, np.ndarray
         res["nodeMembership"] = _own(o, "nodeMembership", T * n, np.int32)
         res["bootMembership"] = _own(o, "bootMembership", T * n, np.int32)
     if o.perfClas:
-        res["perfClas"] = _own(o, "perfClas", T * 3, np.float64)
+        res["perfClas"] = _own(o, "perfClas", (ntree_total or T) * 3, np.float64)
     return res
 
 
@@ -192,15 +198,17 @@ class ResidentCpiu:
 
     def grow(self, *, splitrule="poisson.split4", ntree=500, mtry=None, nodesize=5, nodedepth=-1, seed=-12345,
              k_for_alpha=2.0, membership=False, samp=None, sampsize=None, split_wt=None, tree_first=0, tree_step=0,
-             finalize=True, split_stat=False, member_lists=False, nsplit=0, bootstrap=None) -> Dict[str, np.ndarray]:
+             finalize=True, split_stat=False, member_lists=False, nsplit=0, bootstrap=None, comm=None,
+             gather_forest=False) -> Dict[str, np.ndarray]:
         k = self._pk.keep
         pk = _Packed(k["x"], k["y"], k["rt"], k["st"], splitrule=splitrule, ntree=ntree, mtry=mtry, nodesize=nodesize,
                      nodedepth=nodedepth, seed=seed, k_for_alpha=k_for_alpha, membership=membership, samp=samp,
                      sampsize=sampsize, split_wt=split_wt, device=self.device, tree_first=tree_first, tree_step=tree_step,
-                     finalize=finalize, split_stat=split_stat, member_lists=member_lists, nsplit=nsplit, bootstrap=bootstrap)
+                     finalize=finalize, split_stat=split_stat, member_lists=member_lists, nsplit=nsplit, bootstrap=bootstrap,
+                     comm=comm, gather_forest=gather_forest)
         out = ForestOut()
         capi.check(capi.lib().rfslam_b200_grow_resident(self.handle, C.byref(pk.args), C.byref(out)))
-        res = _unpack_forest(out, finalize)
+        res = _unpack_forest(out, finalize, int(ntree))
         capi.lib().rfslam_b200_free_forest(C.byref(out))
         return res
 
@@ -208,7 +216,8 @@ class ResidentCpiu:
 def rfsrc(x, y, risk_time=None, stratifier=None, *, splitrule="poisson.split4", ntree=500, mtry=None, nodesize=5,
           nodedepth=-1, seed=-12345, k_for_alpha=2.0, membership=False, samp=None, sampsize=None, split_wt=None,
           device=-1, tree_first=0, tree_step=0, finalize=True, nsplit=0, xvar_types=None, split_stat=False,
-          member_lists=False, var_categories=None, category_weights=None, bootstrap=None) -> Dict[str, np.ndarray]:
+          member_lists=False, var_categories=None, category_weights=None, bootstrap=None, comm=None,
+          gather_forest=False) -> Dict[str, np.ndarray]:
     """Grow an RF-SLAM forest from HOST arrays through rfslam_b200_grow (upload + grow + download).
 
     x [p, n] float64 (p contiguous columns), y response codes 1.0 / 2.0, risk_time [n], stratifier [n]
@@ -218,10 +227,10 @@ def rfsrc(x, y, risk_time=None, stratifier=None, *, splitrule="poisson.split4", 
                  nodedepth=nodedepth, seed=seed, k_for_alpha=k_for_alpha, membership=membership, samp=samp, sampsize=sampsize,
                  split_wt=split_wt, device=device, tree_first=tree_first, tree_step=tree_step, finalize=finalize, nsplit=nsplit,
                  xvar_types=xvar_types, split_stat=split_stat, member_lists=member_lists, var_categories=var_categories,
-                 category_weights=category_weights, bootstrap=bootstrap)
+                 category_weights=category_weights, bootstrap=bootstrap, comm=comm, gather_forest=gather_forest)
     out = ForestOut()
     capi.check(capi.lib().rfslam_b200_grow(C.byref(pk.args), C.byref(out)))
-    res = _unpack_forest(out, finalize)
+    res = _unpack_forest(out, finalize, int(ntree))
     capi.lib().rfslam_b200_free_forest(C.byref(out))
     return res
 

@@ -15,14 +15,66 @@ FOREST_KEYS = ("treeID", "nodeID", "parmID", "contPT", "mwcpSZ")
 LEAF_KEYS = ("tnRCNT", "tnACNT")
 
 
+class Comm:
+    """The library's own NCCL communicator (rfslam_b200_comm_init, csrc/comm.cu).  With it `rfsrc(..., comm=c)` /
+    `ResidentCpiu.grow(..., comm=c)` all-reduce the ensemble sums on the DEVICE before they are finalized and sent
+    home, and `gather_forest=True` gathers the shards' records to rank 0 over NVLink.  Rank 0 makes the 128-byte
+    id; it travels through whatever the program has -- here any torch.distributed backend (gloo is enough)."""
+
+    def __init__(self, rank: int, world: int, device: int, unique_id: bytes):
+        import ctypes as C
+        from . import capi
+        self.rank, self.world, self.device = rank, world, device
+        self.handle = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, 128)
+        capi.check(capi.lib().rfslam_b200_comm_init(C.byref(self.handle), rank, world, buf, device))
+
+    @staticmethod
+    def make_unique_id() -> bytes:
+        import ctypes as C
+        from . import capi
+        buf = C.create_string_buffer(128)
+        capi.check(capi.lib().rfslam_b200_comm_unique_id(buf, 128))
+        return buf.raw
+
+    @classmethod
+    def from_torch(cls, device: int, group=None) -> "Comm":
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [cls.make_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        return cls(rank, world, device, box[0])
+
+    def collectives(self):
+        import ctypes as C
+        from . import capi
+        a, g = C.c_int64(0), C.c_int64(0)
+        capi.lib().rfslam_b200_comm_collectives(self.handle, C.byref(a), C.byref(g))
+        return {"allreduce": int(a.value), "gather": int(g.value)}
+
+    def close(self):
+        from . import capi
+        if self.handle:
+            capi.lib().rfslam_b200_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def shard_tree_ids(rank: int, world: int, ntree: int) -> np.ndarray:
     """1-based ids of the trees rank `rank` grows: tree b -> rank (b - 1) mod world."""
     return np.arange(rank + 1, ntree + 1, world, dtype=np.int32)
 
 
 def allreduce_ensembles(f: Dict[str, np.ndarray], *, device=None, group=None) -> Dict[str, np.ndarray]:
-    """Sum the per-shard ensemble sums over ranks and finish them (randomForestSRC.c:8113-8125:
-    numerator / denominator where the denominator is non-zero, 0 otherwise)."""
+    """HOST-side form of the exchange (any torch.distributed backend; the CPU tests run it over gloo): sum the
+    per-shard ensemble sums over ranks and finish them (randomForestSRC.c:8113-8125: numerator / denominator where
+    the denominator is non-zero, 0 otherwise).  On GPUs pass a `Comm` to the grow call instead: the same sum is
+    then taken on the device accumulators inside the library, with no host bounce."""
     import torch
     import torch.distributed as dist
     if f.get("finalized", False):

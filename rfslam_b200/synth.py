@@ -148,7 +148,7 @@ def quantise(x: np.ndarray, levels: int) -> np.ndarray:
 
 
 def make_cpiu_torch(n: int, p: int, *, levels: int = 64, seed: int = DATA_SEED, interval: float = 0.5, max_k: int = 16,
-                    event_rate: float = 0.05, device: str = "cuda") -> Cpiu:
+                    event_rate: float = 0.05, device: str = "cuda", pin: bool = False) -> Cpiu:
     """The same schema as make_cpiu generated with torch on ``device`` (a `torch.Generator` stream, so the VALUES
     differ from the numpy generator's): for tables too large to synthesise on the host within a benchmark's
     budget (10M x 100 takes minutes in numpy, about a second on the GPU).  Returns host arrays."""
@@ -225,7 +225,7 @@ def make_cpiu_torch(n: int, p: int, *, levels: int = 64, seed: int = DATA_SEED, 
                 w = (hi - lo) / levels
                 b = torch.clamp(torch.floor((col - lo) / w), max=levels - 1)
                 x[j, idx] = lo + (b + 0.5) * w
-    xh = torch.empty((p, n), dtype=f64, pin_memory=(device != "cpu"))
+    xh = torch.empty((p, n), dtype=f64, pin_memory=(pin and device != "cpu"))
     for j in range(p):
         xh[j].copy_(x[j, idx])
     out = Cpiu(x=xh.numpy(), y=(1.0 + ev[idx].to(f64)).cpu().numpy(), rt=rt[idx].cpu().numpy(),

@@ -71,11 +71,28 @@ def test_slot_registry_mirrors_reference():
     assert L.rfslam_b200_rule_of_slot(0, 9) == 0
 
 
-def test_struct_layout_matches_header_sizes():
-    # the ctypes mirrors must have the C layout: pointer-sized alignment, no stray fields
-    assert ctypes.sizeof(capi.GrowArgs) % 8 == 0
-    assert capi.GrowArgs.x_data.offset % 8 == 0
-    assert ctypes.sizeof(capi.ForestOut) == 4 + 4 + 8 + 8 + 20 * 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8   # ... + perfClas, mwcpPT, mwcpCT, mwcp_total
+def test_struct_layout_matches_header(tmp_path):
+    """The ctypes mirrors against the header itself: a C program compiled from include/rfslam_b200.h prints the
+    size of every struct and the offset of every field; the ctypes classes must agree field by field."""
+    import subprocess
+    structs = {"rfslam_grow_args": capi.GrowArgs, "rfslam_forest_out": capi.ForestOut,
+               "rfslam_predict_args": capi.PredictArgs, "rfslam_predict_out": capi.PredictOut}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "rfslam_b200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+    # and no field of the header is missing from the mirror (sizes equal + last field at the same offset covers it)
 
 
 @pytest.mark.skipif(capi.lib().rfslam_b200_device_count() > 0, reason="a GPU is present")
