@@ -89,6 +89,26 @@ __global__ void scatter_codes_kernel(const double* sorted, const uint32_t* sorte
   }
 }
 
+// row-major mirror: rowcodes[row][c] = codes[c][row]; one thread block transposes a 32-row x 32-column tile
+__global__ void row_major_kernel(const void* const* codes, int p, int n, int pitch, uint8_t* rowcodes) {
+  __shared__ uint8_t tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;               // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    const int c = c0 + k, r = r0 + tx;
+    tile[k][tx] = (c < p && r < n) ? ((const uint8_t*)codes[c])[r] : 0;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int r = r0 + k, c = c0 + tx;
+    if (r < n && c < pitch) rowcodes[(size_t)r * pitch + c] = tile[tx][k];
+  }
+}
+__global__ void row_rec_kernel(const double* rt, const uint8_t* ev, const uint16_t* strat, RowRec* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { RowRec r; r.rt = rt[i]; r.es = (ev[i] ? 1u : 0u) | (((uint32_t)strat[i] - 1u) << 8); r.pad = 0u; out[i] = r; }
+}
+
 // every device array of a dataset comes from its pool: rfslam_b200_grow seeds the pool with the blocks of
 // the previous call (api.cu), so a second call of the same shape makes no cudaMalloc / cudaFree at all
 template <typename T>
@@ -238,6 +258,18 @@ int dataset_build(const rfslam_grow_args* a, rfslam_dataset** out, WsPool* seed)
       RF_CUDA(cudaMemcpy(d_width, ds->width.data(), (size_t)p, cudaMemcpyHostToDevice));
       RF_CUDA(cudaMemcpy(d_D, ds->D.data(), (size_t)p * sizeof(int), cudaMemcpyHostToDevice));
 
+      // row-major mirror (see DevData): only when every column is byte-coded
+      uint8_t* rowcodes = nullptr; RowRec* rowrec = nullptr; int rowPitch = 0;
+      if (ds->max_D <= 256 && !getenv("RFSLAM_NO_ROWMAJOR")) {
+        rowPitch = (p + 15) & ~15;
+        rowcodes = dalloc<uint8_t>(ds, (size_t)n * rowPitch);
+        rowrec = dalloc<RowRec>(ds, n);
+        dim3 g((unsigned)((n + 31) / 32), (unsigned)((rowPitch + 31) / 32)), b(32, 8);
+        row_major_kernel<<<g, b>>>((const void* const*)d_codes, p, n, rowPitch, rowcodes);
+        row_rec_kernel<<<G, T>>>(rt, ev, strat, rowrec, n);
+        RF_CUDA(cudaGetLastError());
+      }
+
       // dominant risk time: the modal value of a sample (any value is correct; the mode is fastest)
       double rt_mode = a->risk_time[0];
       for (int i = 0; i < n; i++) {
@@ -263,6 +295,7 @@ int dataset_build(const rfslam_grow_args* a, rfslam_dataset** out, WsPool* seed)
       d.n = n; d.p = p; d.K = ds->K;
       d.perm = perm; d.inv = inv; d.sb = sb; d.ev = ev; d.rt = rt; d.strat = strat;
       d.codes = (const void* const*)d_codes; d.width = d_width; d.D = d_D; d.uniq = (const double* const*)d_uniq;
+      d.rowcodes = rowcodes; d.rowPitch = rowPitch; d.rowrec = rowrec;
     } catch (...) {
       free_transient();
       throw;

@@ -401,7 +401,21 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         g.split_weight = d_sw.p;
       }
     }
-    const size_t smem = grow_smem_bytes(g.ncmax, ds->K, g.hbins);
+    // Shared-memory plan: two CTAs per SM need <= ~112 KB each.  The staged-subtree tile (subMax whole rows) is
+    // worth more than wide histogram passes: strata slots per pass go 4 -> 2 (same entries, same flushes, two more
+    // barriers per large node) before the tile shrinks.
+    const int tilePitch = (ds->dev.rowPitch + 15) & ~15;
+    g.hslots = hist_slots(g.hbins);
+    g.subMax = 0;
+    if (ds->dev.rowcodes && cfg.nsplit == 0 && !getenv("RFSLAM_NO_SUBTREE")) {
+      const size_t limit = 112u << 10;
+      const int wantSub = getenv("RFSLAM_SUBTREE_MAX") ? atoi(getenv("RFSLAM_SUBTREE_MAX")) : kSmallMax;
+      const int hsFull = g.hslots, hsMin = std::min(2, hsFull);
+      for (int sm = std::min(wantSub, kSmallMax); sm >= 128 && g.subMax == 0; sm >>= 1)
+        for (int hs = hsFull; hs >= hsMin; hs >>= 1)
+          if (grow_smem_bytes(g.ncmax, ds->K, g.hbins, hs, sm, tilePitch) <= limit) { g.hslots = hs; g.subMax = sm; break; }
+    }
+    const size_t smem = grow_smem_bytes(g.ncmax, ds->K, g.hbins, g.hslots, g.subMax, tilePitch);
     RF_CUDA(cudaFuncSetAttribute(rfslam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int residentCtas = 0; long long quantumCycles = 0;
     {
@@ -831,7 +845,8 @@ int score_node_impl(int rule, double k_for_alpha, int m, const double* x, const 
     g.rule = rule; g.mtry = 1; g.nodesize = 1; g.nodedepth = -1; g.alpha = 1.0 / (k_for_alpha * k_for_alpha);
     g.pw = 1; g.ncmax = 1; g.has_sort = ds->max_D > kHistBins; g.hbins = ds->hist_bins;
     { int ex = 0; frexp(std::max((double)m * std::max(ds->max_rt, 1e-300), 1.0), &ex); g.tscale = ldexp(1.0, 62 - ex); g.tinv = ldexp(1.0, ex - 62); }
-    const size_t smem = grow_smem_bytes(g.ncmax, ds->K, g.hbins);
+    g.hslots = hist_slots(g.hbins); g.subMax = 0;
+    const size_t smem = grow_smem_bytes(g.ncmax, ds->K, g.hbins, g.hslots, 0, 0);
     RF_CUDA(cudaFuncSetAttribute(rfslam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DevBuf<uint32_t> d_lists, d_sort, d_stackPerm, d_ctab, d_nodeCount, d_leafCount, d_cursor;
     DevBuf<uint16_t> d_cnt; DevBuf<NodeEnt> d_stack; DevBuf<int> d_seedB, d_boot, d_status, d_sinkCount;

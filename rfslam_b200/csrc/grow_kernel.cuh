@@ -64,6 +64,7 @@ struct NodeEnt {        // a pending node of the DFS
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr int kSmallMax = 512;
 constexpr int kLocalMax = 256;      // small nodes up to this many entries also take covariates with > 256 distinct values (local ranks)      // nodes with <= this many entries are scored entirely out of shared memory
+constexpr int kSparseRatio = 12;    // a node with fewer than n / kSparseRatio entries reads the row-major mirror of the table
 constexpr int kProfSlots = 96;   // 64..79: the phase slots again, restricted to nodes with < 64 entries   // 0..15 phases, 16..47 node time by log2(len), 48..63 node count by log2(len)/2
 
 struct GrowParams {
@@ -76,6 +77,9 @@ struct GrowParams {
   int hbins;                     // histogram stride (see GrowSmem::hb)
   double tscale, tinv;           // 2^S and 2^-S of the fixed-point exposure accumulators (see hist_add)
   int nsplit;                    // > 0: at most nsplit randomly drawn cuts per covariate (rf.c:14533-14564)
+  int hslots;                    // stratum slots per candidate histogram (GrowSmem::hs), chosen by the host to fit shared memory
+  int subMax;                    // > 0: a node of at most this many entries stages ITS WHOLE ROWS in shared memory and the subtree
+                                 //      below it is grown out of that tile (see stage_subtree); 0 = off
 };
 
 struct GrowWork {
@@ -138,6 +142,7 @@ struct GrowShared {
   long long sliceStart; int curTree; int fresh;
   // nsplit > 0: the cuts drawn for each candidate (bit = code), scratch of the draw, cuts per candidate
   uint32_t cutMask[kMaxCand][8]; uint32_t rankSel[8]; uint8_t swor[256]; int trkCuts[kMaxCand];
+  int inSub; uint32_t subSp, subStart; // growing inside a staged subtree: DFS depth at its root, list offset of its first entry
   uint8_t candLocal[kMaxCand];       // candidate re-ranked locally by this node (its codes in shared memory are node-local ranks)
   uint32_t bestWide;                 // the winning cut of a locally re-ranked candidate as a table-wide code
 };
@@ -186,6 +191,8 @@ struct GrowSmem {
   double *PT, *PW, *cT, *cW, *cTL, *cTR;
   // small-node staging: the node's entries and everything scoring needs about them
   uint32_t* smEnt; SmallRec* smRec; uint8_t* smCodes;
+  // staged subtree (subMax entries): entry words, records, the entries' whole code rows, and the node order (slot per position)
+  uint32_t* stRow; SmallRec* stRec; uint8_t* stTile; uint16_t* stIdx; int subMax, tilePitch;
   GrowShared* s;
   int hb;                            // bins per candidate histogram: pow2 >= the widest byte-coded column, 32..256
   int hs;                            // stratum slots per candidate histogram (large nodes accumulate hs strata per pass)
@@ -199,8 +206,8 @@ struct GrowSmem {
 #endif
 __host__ __device__ inline int hist_slots(int hb) { int g = 256 / hb; return g < 1 ? 1 : (g > RF_MAX_SLOTS ? RF_MAX_SLOTS : g); }
 
-__host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K, int hb) {
-  const size_t hs = (size_t)hist_slots(hb);
+__host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K, int hb, int hslots, int subMax, int tilePitch) {
+  const size_t hs = (size_t)hslots;
   size_t KS = (size_t)K + 2;
   size_t b = 0;
   b += (size_t)ncmax * hb * 8 * 2;             // sL sR
@@ -212,14 +219,17 @@ __host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K, int hb) {
   b += KS * 4 * 5;                             // segpos PN PE cN cE
   b += (size_t)kSmallMax * (16 + 4 + (size_t)ncmax) + 32;  // small-node staging (>= the 8.5 KB of sorted-walk tiles aliased onto it)
   b = (b + 15) & ~(size_t)15;
+  b += (size_t)subMax * (4 + 16 + (size_t)tilePitch + 2) + 32;   // staged subtree
+  b = (b + 15) & ~(size_t)15;
   b += sizeof(GrowShared);
   return b + 16;
 }
 
-__device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb) {
+__device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb, int hslots, int subMax, int tilePitch) {
   GrowSmem m;
   m.hb = hb;
-  m.hs = hist_slots(hb);
+  m.hs = hslots;
+  m.subMax = subMax; m.tilePitch = tilePitch;
   const size_t hsz = (size_t)ncmax * hb * m.hs;
   size_t KS = (size_t)K + 2;
   double* d = (double*)raw;
@@ -251,6 +261,14 @@ __device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb) {
   m.smEnt = u; u += kSmallMax;
   m.smCodes = (uint8_t*)u;
   u = (uint32_t*)(m.smCodes + (size_t)kSmallMax * ncmax);
+  {
+    uintptr_t al = ((uintptr_t)u + 15) & ~(uintptr_t)15;
+    m.stRec = (SmallRec*)al;
+    m.stTile = (uint8_t*)(al + (size_t)subMax * 16);
+    m.stRow = (uint32_t*)(m.stTile + (size_t)subMax * tilePitch);
+    m.stIdx = (uint16_t*)(m.stRow + subMax);
+    u = (uint32_t*)(m.stIdx + subMax + (subMax & 1));
+  }
   uintptr_t p = ((uintptr_t)u + 15) & ~(uintptr_t)15;
   m.s = (GrowShared*)p;
   // tell the compiler these all live in shared memory (LDS/STS/ATOMS instead of generic LD/ST)
@@ -1024,26 +1042,74 @@ __device__ inline void score_small(NodeCtx& c) {
   const uint32_t len = s->cur.len;
   const DevData& d = c.d;
   const GrowWork& w = c.w;
-  // stage: one thread per entry, all of an entry's gathers issued before the first shared-memory store
+  // A node of at most subMax entries stages its entries' WHOLE ROWS once (entry word, 16-byte record, every byte code
+  // of the row from the row-major mirror: tilePitch / 16 coalesced 16-byte loads per entry).  The subtree below it is
+  // then grown out of shared memory: each of its nodes fetches the codes of its own drawn covariates from the tile,
+  // partitions by permuting 16-bit slot numbers, and never touches the lists or the table in global memory again.
+  // (Deep in a tree every per-node gather used to be one DRAM round trip per level for one byte per 32-byte sector.)
+  const bool rowm = d.rowcodes != nullptr;
+  if (m.subMax > 0 && !s->inSub && len <= (uint32_t)m.subMax && !w.sinkDelta) {
+    const int chunks = m.tilePitch >> 4;
+    for (uint32_t q = (uint32_t)tid; q < len * (uint32_t)chunks; q += kThreads) {
+      const uint32_t j = q / (uint32_t)chunks, ch = q - j * (uint32_t)chunks;
+      const uint32_t row = c.list[j] & kRowMask;
+      ((uint4*)(m.stTile + (size_t)j * m.tilePitch))[ch] = ((const uint4*)(d.rowcodes + (size_t)row * (size_t)d.rowPitch))[ch];
+    }
+    for (uint32_t j = (uint32_t)tid; j < len; j += kThreads) {
+      const uint32_t ent = c.list[j];
+      const uint32_t row = ent & kRowMask, mult = (ent >> kRowBits) + 1u;
+      const RowRec rr = d.rowrec[row];
+      SmallRec r; r.mrt = (double)mult * rr.rt; r.mult = mult; r.es = (rr.es & 1u) | (c.strat ? (rr.es & 0xFFFFFF00u) : 0u);
+      m.stRow[j] = ent; m.stRec[j] = r; m.stIdx[j] = (uint16_t)j;
+    }
+    if (tid == 0) { s->inSub = 1; s->subSp = s->sp; s->subStart = s->cur.start; }
+    __syncthreads();
+    RF_PROF(14);
+  }
+  const bool sub = s->inSub != 0;
+  const uint32_t soff = sub ? s->cur.start - s->subStart : 0u;
+  // stage the node: one thread per entry, all of an entry's gathers issued before the first shared-memory store.
+  // With the row-major mirror an entry costs one 16-byte record + the sectors of ONE code row instead of three
+  // per-row arrays + one 32-byte sector per candidate column; inside a staged subtree it costs no global access.
   for (uint32_t j0 = (uint32_t)(tid - lane); j0 < len; j0 += kThreads) {
     const uint32_t j = j0 + lane;
     const bool valid = j < len;
-    const uint32_t ent = valid ? c.list[j] : 0u;
-    RF_ASSERT((ent & kRowMask) < (uint32_t)d.n, "small staging: tree %d entry %u/%u = %08x (start %u buf %u node %u)\n", c.tree, j, len, ent, s->cur.start, s->cur.buf, s->cur.nodeID);
-    const uint32_t row = ent & kRowMask, mult = (ent >> kRowBits) + 1u;
-    const uint32_t e = d.ev[row];
-    const double tv = d.rt[row];
-    const uint32_t sidx = c.strat ? (uint32_t)d.strat[row] - 1u : 0u;
-    // the stratum of the entry before this warp's first / after its last one (segment boundaries)
-    uint32_t edgeS = 0xFFFFFFFFu;
-    if (c.strat) {
-      if (lane == 0 && j > 0u) edgeS = (uint32_t)d.strat[c.list[j - 1u] & kRowMask] - 1u;
-      if (lane == 31 && j + 1u < len) edgeS = (uint32_t)d.strat[c.list[j + 1u] & kRowMask] - 1u;
+    uint32_t ent, e, sidx, mult; double mrt;
+    uint32_t edgeS = 0xFFFFFFFFu;        // the stratum of the entry before this warp's first / after its last one (segment boundaries)
+    const uint8_t* __restrict__ rc = nullptr;
+    uint32_t row = 0u;
+    if (sub) {
+      const uint32_t slot = valid ? (uint32_t)m.stIdx[soff + j] : 0u;
+      const SmallRec r = m.stRec[slot];
+      ent = m.stRow[slot]; e = r.es & 1u; sidx = r.es >> 8; mult = r.mult; mrt = r.mrt;
+      rc = m.stTile + (size_t)slot * m.tilePitch;
+      if (c.strat) {
+        if (lane == 0 && j > 0u) edgeS = m.stRec[m.stIdx[soff + j - 1u]].es >> 8;
+        if (lane == 31 && j + 1u < len) edgeS = m.stRec[m.stIdx[soff + j + 1u]].es >> 8;
+      }
+    } else {
+      ent = valid ? c.list[j] : 0u;
+      RF_ASSERT((ent & kRowMask) < (uint32_t)d.n, "small staging: tree %d entry %u/%u = %08x (start %u buf %u node %u)\n", c.tree, j, len, ent, s->cur.start, s->cur.buf, s->cur.nodeID);
+      row = ent & kRowMask; mult = (ent >> kRowBits) + 1u;
+      double tv;
+      if (rowm) {
+        const RowRec rr = d.rowrec[row];
+        e = rr.es & 1u; tv = rr.rt; sidx = c.strat ? (rr.es >> 8) : 0u;
+        rc = d.rowcodes + (size_t)row * (size_t)d.rowPitch;
+      } else {
+        e = d.ev[row]; tv = d.rt[row]; sidx = c.strat ? (uint32_t)d.strat[row] - 1u : 0u;
+      }
+      mrt = (double)mult * tv;
+      if (c.strat) {
+        if (lane == 0 && j > 0u) { const uint32_t r2 = c.list[j - 1u] & kRowMask; edgeS = rowm ? (d.rowrec[r2].es >> 8) : (uint32_t)d.strat[r2] - 1u; }
+        if (lane == 31 && j + 1u < len) { const uint32_t r2 = c.list[j + 1u] & kRowMask; edgeS = rowm ? (d.rowrec[r2].es >> 8) : (uint32_t)d.strat[r2] - 1u; }
+      }
     }
     for (int half = 0; half < nc; half += 8) {
       uint32_t raw[8];
 #pragma unroll
-      for (int q = 0; q < 8; q++) raw[q] = (half + q < nc) ? (uint32_t)((const uint8_t*)s->candPtr[half + q])[row] : 0u;
+      for (int q = 0; q < 8; q++)
+        raw[q] = (half + q < nc) ? (rc ? (uint32_t)rc[s->candCov[half + q]] : (uint32_t)((const uint8_t*)s->candPtr[half + q])[row]) : 0u;
 #pragma unroll
       for (int q = 0; q < 8; q++)
         if (valid && half + q < nc) m.smCodes[(half + q) * kSmallMax + j] = (uint8_t)raw[q];
@@ -1054,7 +1120,7 @@ __device__ inline void score_small(NodeCtx& c) {
     if (j + 1u >= len) nextS = 0xFFFFFFFFu;
     if (valid) {
       m.smEnt[j] = ent;
-      SmallRec r; r.mrt = (double)mult * tv; r.mult = mult; r.es = (e ? 1u : 0u) | (sidx << 8);
+      SmallRec r; r.mrt = mrt; r.mult = mult; r.es = (e ? 1u : 0u) | (sidx << 8);
       m.smRec[j] = r;
       if (prevS != sidx) m.segpos[sidx] = j;
       if (nextS != sidx) m.cN[sidx] = j + 1u;
@@ -1126,6 +1192,10 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
     const uint8_t* __restrict__ hptr[kMaxCand];
 #pragma unroll
     for (int ci = 0; ci < kMaxCand; ci++) hptr[ci] = (ci < nc) ? (const uint8_t*)s->candPtr[ci] : nullptr;
+    // A node that holds few of the table's rows gathers from the row-major mirror: its c code bytes of a row sit in
+    // at most rowPitch / 32 sectors, against one 32-byte sector per column from the column-major arrays (whose
+    // sectors are only shared between entries while the node still holds a good fraction of consecutive rows).
+    const bool sparse = d.rowcodes != nullptr && (unsigned long long)cur.len * (unsigned long long)kSparseRatio < (unsigned long long)d.n;
     const int hstride = m.hs * m.hb;
     for (int k0 = 1; k0 <= Kloop; k0 += m.hs) {
       // one pass accumulates the next hs strata (a contiguous entry range: the list is stratum-major),
@@ -1143,11 +1213,13 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
         if (i + kThreads < s1) entNext = list[i + kThreads];       // software pipelining: next entry's load overlaps this entry's gathers
         const uint32_t row = ent & kRowMask, mult = (ent >> kRowBits) + 1u;
         // issue every gather of this entry before the first shared-memory atomic
-        const uint32_t e = d.ev[row];
-        const double tv = unit ? 0.0 : d.rt[row];
+        uint32_t e; double tv;
+        if (d.rowrec) { const RowRec rr = d.rowrec[row]; e = rr.es & 1u; tv = unit ? 0.0 : rr.rt; }
+        else { e = d.ev[row]; tv = unit ? 0.0 : d.rt[row]; }
         const int slotOff = ((i >= bnd[0]) + (i >= bnd[1]) + (i >= bnd[2])) * m.hb;
         const bool isT0 = tv == d.rt_mode;
         const unsigned long long ft = (unsigned long long)__double2ll_rn(tv * g.tscale) * (unsigned long long)mult;
+        const uint8_t* __restrict__ rc = d.rowcodes + (size_t)row * (size_t)d.rowPitch;    // (only dereferenced when sparse)
 #pragma unroll
         for (int half = 0; half < kMaxCand; half += 8) {
           if (half < nc) {
@@ -1155,7 +1227,7 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
 #pragma unroll
             for (int q = 0; q < 8; q++) {
               const int ci = half + q;
-              raw[q] = (ci < nc && ((hmask >> ci) & 1u)) ? (uint32_t)hptr[ci][row] : 0u;
+              raw[q] = (ci < nc && ((hmask >> ci) & 1u)) ? (sparse ? (uint32_t)rc[s->candCov[ci]] : (uint32_t)hptr[ci][row]) : 0u;
             }
 #pragma unroll
             for (int q = 0; q < 8; q++) {
@@ -1354,7 +1426,7 @@ __device__ inline bool append_record(const GrowWork& w, GrowShared* s, int tree,
 extern "C" __global__ void __launch_bounds__(kThreads, RF_MIN_CTAS)
 rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  GrowSmem m = carve(smem_raw, g.ncmax, d.K, g.hbins);
+  GrowSmem m = carve(smem_raw, g.ncmax, d.K, g.hbins, g.hslots, g.subMax, (d.rowPitch + 15) & ~15);
   GrowShared* s = m.s;
   const int tid = vtid();
   const int n = d.n;
@@ -1397,7 +1469,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     s->tmark = clock64();
     ran1_seed(s->rng, w.seedB[tree]);
     ran1_init(s->rng);
-    s->nodeCount = 0; s->leafCount = 1; s->sp = 0; s->candCount = 0; s->algoBytes = 0; s->abort = 0;
+    s->nodeCount = 0; s->leafCount = 1; s->sp = 0; s->candCount = 0; s->algoBytes = 0; s->abort = 0; s->inSub = 0;
     s->histDirty = sliced ? 1 : 0;                                  // another tree's small nodes may have used the histograms
   }
   for (int k = tid; k < 32; k += kThreads) {
@@ -1455,7 +1527,8 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
   const bool bayes = rule_is_bayes(g.rule);
   // ---- depth-first growth (rf.c:21460-21792) ----
   while (true) {
-    if (sliced && tid == 0 && !s->abort && clock64() - s->sliceStart > w.quantum && atomicAdd(w.waiting, 0) > 0) s->abort = 3;   // park
+    // park -- never inside a staged subtree (its state lives in this CTA's shared memory; it is over in well under a quantum)
+    if (sliced && tid == 0 && !s->abort && !s->inSub && clock64() - s->sliceStart > w.quantum && atomicAdd(w.waiting, 0) > 0) s->abort = 3;
     __syncthreads();
     if (s->abort) break;
     const NodeEnt cur = s->cur;
@@ -1527,6 +1600,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
             } else {
               s->sp--;
               s->cur = w.stack[(size_t)tree * kStackCap + s->sp];
+              if (s->inSub && s->sp < s->subSp) s->inSub = 0;       // the DFS is back above the staged subtree's root
             }
           }
         }
@@ -1558,16 +1632,18 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
       static_assert(kSmallMax % kThreads == 0 && kEpt <= 4, "staged entries per thread");
       unsigned long long my = 0ull; bool lf[kEpt]; uint32_t en[kEpt];
       double rtL = 0.0, rtR = 0.0;
+      const bool sub = s->inSub != 0;                            // staged subtree: the "list" is the slot order in shared memory
+      const uint32_t soff = sub ? cur.start - s->subStart : 0u;
 #pragma unroll
       for (int u = 0; u < kEpt; u++) {
         const uint32_t i = (uint32_t)kEpt * tid + u;
         lf[u] = false; en[u] = 0u;
         if (i < cur.len) {
-          en[u] = m.smEnt[i];
+          en[u] = sub ? (uint32_t)m.stIdx[soff + i] : m.smEnt[i];
           lf[u] = cptr[i] <= bcode;                               // LEFT iff cut - x >= 0 (rf.c:15194)
           if (localCut && cptr[i] == bcode) s->bestWide = load_code(ptr, wd, en[u] & kRowMask);   // same value from every such entry
-          const unsigned long long mult = (en[u] >> kRowBits) + 1u;
           const SmallRec r = m.smRec[i];
+          const unsigned long long mult = r.mult;
           if (lf[u]) my += 1ull | (mult << 16) | (((r.es & 1u) ? mult : 0ull) << 40);
           if (bayes) { if (lf[u]) rtL += r.mrt; else rtR += r.mrt; }
         }
@@ -1583,8 +1659,13 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
       for (int u = 0; u < kEpt; u++) {
         const uint32_t i = (uint32_t)kEpt * tid + u;
         if (i < cur.len) {
-          if (lf[u]) { dst[before] = en[u]; before++; }
-          else dst[nL + (i - before)] = en[u];
+          if (sub) {                                              // (every thread read its slots before the scan's barriers)
+            if (lf[u]) { m.stIdx[soff + before] = (uint16_t)en[u]; before++; }
+            else m.stIdx[soff + nL + (i - before)] = (uint16_t)en[u];
+          } else {
+            if (lf[u]) { dst[before] = en[u]; before++; }
+            else dst[nL + (i - before)] = en[u];
+          }
         }
       }
     } else {
@@ -1592,6 +1673,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     // dependent code gathers, are in flight together (the kernel is latency-bound, not HBM-bound).
     // pass 1: sizes of the left child
     unsigned long long cL = 0, neL = 0; double rtL = 0.0, rtR = 0.0;
+    const bool sparseP = d.rowcodes != nullptr && (unsigned long long)cur.len * (unsigned long long)kSparseRatio < (unsigned long long)n;
     for (uint32_t base = 0; base < cur.len; base += 4u * kThreads) {
       uint32_t ent[4]; uint32_t cd[4]; uint32_t ev4[4]; double rt4[4];
 #pragma unroll
@@ -1600,9 +1682,15 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
       for (int u = 0; u < 4; u++) {
         const bool valid = ent[u] != 0xFFFFFFFFu;
         const uint32_t row = ent[u] & kRowMask;
-        cd[u] = valid ? load_code(ptr, wd, row) : 0xFFFFFFFFu;
-        ev4[u] = valid ? (uint32_t)d.ev[row] : 0u;
-        rt4[u] = (valid && bayes) ? d.rt[row] : 0.0;
+        if (sparseP) {                                             // one code-row sector + one 16-byte record per entry
+          cd[u] = valid ? (uint32_t)d.rowcodes[(size_t)row * (size_t)d.rowPitch + cov] : 0xFFFFFFFFu;
+          const RowRec rr = valid ? d.rowrec[row] : RowRec{0.0, 0u, 0u};
+          ev4[u] = rr.es & 1u; rt4[u] = bayes ? rr.rt : 0.0;
+        } else {
+          cd[u] = valid ? load_code(ptr, wd, row) : 0xFFFFFFFFu;
+          ev4[u] = valid ? (uint32_t)d.ev[row] : 0u;
+          rt4[u] = (valid && bayes) ? d.rt[row] : 0.0;
+        }
       }
 #pragma unroll
       for (int u = 0; u < 4; u++) {
@@ -1626,7 +1714,8 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
 #pragma unroll
         for (int u = 0; u < 4; u++) { const uint32_t i = base + 4u * tid + u; ent[u] = (i < cur.len) ? src[i] : 0xFFFFFFFFu; }
 #pragma unroll
-        for (int u = 0; u < 4; u++) cd[u] = (ent[u] != 0xFFFFFFFFu) ? load_code(ptr, wd, ent[u] & kRowMask) : 0xFFFFFFFFu;
+        for (int u = 0; u < 4; u++)
+          cd[u] = (ent[u] != 0xFFFFFFFFu) ? (sparseP ? (uint32_t)d.rowcodes[(size_t)(ent[u] & kRowMask) * (size_t)d.rowPitch + cov] : load_code(ptr, wd, ent[u] & kRowMask)) : 0xFFFFFFFFu;
         uint32_t mine = 0;
 #pragma unroll
         for (int u = 0; u < 4; u++) mine += (ent[u] != 0xFFFFFFFFu && cd[u] <= bcode) ? 1u : 0u;

@@ -10,6 +10,8 @@
 
 namespace rfslam {
 
+struct __align__(16) RowRec { double rt; uint32_t es; uint32_t pad; };   // es = event | (stratum - 1) << 8
+
 // Device view of the resident CPIU table.  Rows are held in INTERNAL order = sorted by
 // (stratum, original row): every stratum is one contiguous row range, so a node's in-bag list
 // (kept sorted by internal row) is stratum-major and per-stratum histograms need only D bins.
@@ -26,6 +28,14 @@ struct DevData {
   const int*      D;              // [p] number of distinct values
   const double* const* uniq;      // [p] the distinct values, ascending: cut value = uniq[c][code]
   double rt_mode;                 // the table's dominant risk time (exposure = rt_mode * count + exceptions)
+  // Row-major mirror of the table (present when every column is byte-coded): one row's codes are `rowPitch`
+  // contiguous bytes and its (risk time, event, stratum) one 16-byte record.  A node deep in a tree holds a small
+  // scattered fraction of the rows: gathering c candidate codes of a row from the column-major arrays costs c
+  // 32-byte DRAM sectors for c bytes, from here at most rowPitch / 32 sectors -- and a whole row fits the
+  // shared-memory tile that serves the subtree below a small node.
+  const uint8_t*  rowcodes;       // [n][rowPitch] or nullptr
+  int             rowPitch;       // p rounded up to a multiple of 16
+  const RowRec*   rowrec;         // [n]
 };
 
 }  // namespace rfslam
