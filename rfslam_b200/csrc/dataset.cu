@@ -258,17 +258,21 @@ int dataset_build(const rfslam_grow_args* a, rfslam_dataset** out, WsPool* seed)
       RF_CUDA(cudaMemcpy(d_width, ds->width.data(), (size_t)p, cudaMemcpyHostToDevice));
       RF_CUDA(cudaMemcpy(d_D, ds->D.data(), (size_t)p * sizeof(int), cudaMemcpyHostToDevice));
 
-      // row-major mirror (see DevData): only when every column is byte-coded
+      // Row-major mirror (see DevData): only when every column is byte-coded, and only when the column-major table
+      // does not fit the 126 MB L2 anyway.  A table that does (configs[1]: 69 MB) is served from L2 whatever the
+      // access pattern, and a mirror would push the working set out of it (measured: 1.42 s -> 1.53 s per 500 trees).
       uint8_t* rowcodes = nullptr; RowRec* rowrec = nullptr; int rowPitch = 0;
-      if (ds->max_D <= 256 && !getenv("RFSLAM_NO_ROWMAJOR")) {
+      bool wantRow = (size_t)n * (size_t)p > ((size_t)96 << 20);
+      if (const char* e = getenv("RFSLAM_ROWMAJOR")) wantRow = atoi(e) != 0;
+      rowrec = dalloc<RowRec>(ds, n);                              // the 16-byte row records are always built (one load instead of three)
+      row_rec_kernel<<<G, T>>>(rt, ev, strat, rowrec, n);
+      if (ds->max_D <= 256 && wantRow && !getenv("RFSLAM_NO_ROWMAJOR")) {
         rowPitch = (p + 15) & ~15;
         rowcodes = dalloc<uint8_t>(ds, (size_t)n * rowPitch);
-        rowrec = dalloc<RowRec>(ds, n);
         dim3 g((unsigned)((n + 31) / 32), (unsigned)((rowPitch + 31) / 32)), b(32, 8);
         row_major_kernel<<<g, b>>>((const void* const*)d_codes, p, n, rowPitch, rowcodes);
-        row_rec_kernel<<<G, T>>>(rt, ev, strat, rowrec, n);
-        RF_CUDA(cudaGetLastError());
       }
+      RF_CUDA(cudaGetLastError());
 
       // dominant risk time: the modal value of a sample (any value is correct; the mode is fastest)
       double rt_mode = a->risk_time[0];

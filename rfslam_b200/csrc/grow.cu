@@ -408,7 +408,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     g.hslots = hist_slots(g.hbins);
     g.subMax = 0;
     if (ds->dev.rowcodes && cfg.nsplit == 0 && !getenv("RFSLAM_NO_SUBTREE")) {
-      const size_t limit = 112u << 10;
+      const size_t limit = (112u << 10) - sizeof(GrowShared);     // dynamic part; GrowShared is static shared memory of the kernel
       const int wantSub = getenv("RFSLAM_SUBTREE_MAX") ? atoi(getenv("RFSLAM_SUBTREE_MAX")) : kSmallMax;
       const int hsFull = g.hslots, hsMin = std::min(2, hsFull);
       for (int sm = std::min(wantSub, kSmallMax); sm >= 128 && g.subMax == 0; sm >>= 1)
@@ -509,7 +509,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     DevBuf<uint16_t> d_cnt(pool); DevBuf<NodeEnt> d_stack(pool); DevBuf<int> d_seedA(pool), d_seedB(pool), d_boot(pool), d_ids(pool), d_status(pool);
     DevBuf<unsigned long long> d_cand(pool), d_algo(pool), d_nodeOff(pool), d_leafOff(pool);
     DevBuf<int32_t> d_samp(pool);
-    const size_t cntStride = ((size_t)n + 1) & ~(size_t)1;         // u16 count rows stay 4-byte aligned
+    const size_t cntStride = ((size_t)n + 7) & ~(size_t)7;         // u16 count rows stay 16-byte aligned (the root build reads eight at a time)
     d_lists.alloc((size_t)B * 2 * listStride);
     if (g.has_sort) d_sort.alloc((size_t)B * 4 * listStride);
     if (!cfg.by_user) d_draws.alloc((size_t)B * maxBoot); else d_samp.alloc(n);
@@ -851,7 +851,7 @@ int score_node_impl(int rule, double k_for_alpha, int m, const double* x, const 
     DevBuf<uint32_t> d_lists, d_sort, d_stackPerm, d_ctab, d_nodeCount, d_leafCount, d_cursor;
     DevBuf<uint16_t> d_cnt; DevBuf<NodeEnt> d_stack; DevBuf<int> d_seedB, d_boot, d_status, d_sinkCount;
     DevBuf<unsigned long long> d_cand, d_algo; DevBuf<Rec> d_pool; DevBuf<double> d_statPool, d_sinkCut, d_sinkDelta;
-    const size_t cntStride = ((size_t)n + 1) & ~(size_t)1;
+    const size_t cntStride = ((size_t)n + 7) & ~(size_t)7;
     d_lists.alloc(2 * (size_t)n); if (g.has_sort) d_sort.alloc(4 * (size_t)n);
     d_cnt.alloc(cntStride); d_stack.alloc(kStackCap); d_stackPerm.alloc(kStackCap);
     d_ctab.alloc(4); d_nodeCount.alloc(1); d_leafCount.alloc(1); d_cursor.alloc(1); d_status.alloc(1);

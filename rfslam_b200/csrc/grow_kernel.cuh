@@ -31,7 +31,8 @@
 #include "internal.h"
 
 #ifndef RF_ASSUME
-#define RF_ASSUME 19   // bits 4 and 8 (the staging / tile region) miscompute on nvcc 12.9 when assumed shared: left generic
+#define RF_ASSUME 3    // bits 4, 8 (the staging / tile region) and 16 (GrowShared: faults when trees are parked and resumed) miscompute on
+                       // nvcc 12.9 when assumed shared: left generic.  GrowShared is a static __shared__ object instead.
 #endif
 
 namespace rfslam {
@@ -142,6 +143,7 @@ struct GrowShared {
   long long sliceStart; int curTree; int fresh;
   // nsplit > 0: the cuts drawn for each candidate (bit = code), scratch of the draw, cuts per candidate
   uint32_t cutMask[kMaxCand][8]; uint32_t rankSel[8]; uint8_t swor[256]; int trkCuts[kMaxCand];
+  int candStride;                    // byte-coded candidates: code of row r = candPtr[k][r * candStride] (1 = column-major array, rowPitch = row-major mirror)
   int inSub; uint32_t subSp, subStart; // growing inside a staged subtree: DFS depth at its root, list offset of its first entry
   uint8_t candLocal[kMaxCand];       // candidate re-ranked locally by this node (its codes in shared memory are node-local ranks)
   uint32_t bestWide;                 // the winning cut of a locally re-ranked candidate as a table-wide code
@@ -184,6 +186,8 @@ struct __align__(16) SmallRec { double mrt; uint32_t mult; uint32_t es; };
 struct GrowSmem {
   double *sL, *sR, *hT, *hW, *statP;
   uint32_t *hN, *hE, *hNx, *hEx, *pres;
+  uint32_t *smk;                     // small nodes: [ncmax][kTabSlots][8] codes that have rows in a slot's stratum
+  double *tabL, *tabR;               // small nodes: per-candidate term tables [ncmax][kTabSlots][hb], laid over the whole histogram region
   // sorted-walk tile arrays (alias the small-node staging: the two paths never overlap in time)
   double *tileTL, *tileTR, *tileDelta; uint32_t *tileKey, *radixBase; uint8_t* tileCut;
   uint16_t* pool;                    // permissible-covariate pool of the draw step (same aliasing: used between nodes only)
@@ -204,6 +208,7 @@ struct GrowSmem {
 #ifndef RF_ROWS_MAXSEG
 #define RF_ROWS_MAXSEG 64   // small nodes: longest event stratum for which the lane = row evaluation is used
 #endif
+constexpr int kTabSlots = RF_MAX_SLOTS;    // strata per group of the small-node path (independent of the large-node passes' hs)
 __host__ __device__ inline int hist_slots(int hb) { int g = 256 / hb; return g < 1 ? 1 : (g > RF_MAX_SLOTS ? RF_MAX_SLOTS : g); }
 
 __host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K, int hb, int hslots, int subMax, int tilePitch) {
@@ -211,18 +216,20 @@ __host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K, int hb, int 
   size_t KS = (size_t)K + 2;
   size_t b = 0;
   b += (size_t)ncmax * hb * 8 * 2;             // sL sR
-  b += (size_t)ncmax * hb * hs * 8 * 2;        // hT hW
+  {                                            // hT hW hN hE hNx hEx = one region, at least the small nodes' two term tables
+    const size_t hist = (size_t)ncmax * hb * hs * 32, tabs = (size_t)ncmax * hb * kTabSlots * 16;
+    b += hist > tabs ? hist : tabs;
+  }
   b += (size_t)ncmax * 8;                      // statP
-  b += (size_t)ncmax * hb * hs * 4 * 4;        // hN hE hNx hEx
   b += (size_t)ncmax * 8 * 4;                  // pres
+  b += (size_t)ncmax * kTabSlots * 8 * 4;      // smk
   b += KS * 8 * 6;                             // PT PW cT cW cTL cTR
   b += KS * 4 * 5;                             // segpos PN PE cN cE
   b += (size_t)kSmallMax * (16 + 4 + (size_t)ncmax) + 32;  // small-node staging (>= the 8.5 KB of sorted-walk tiles aliased onto it)
   b = (b + 15) & ~(size_t)15;
   b += (size_t)subMax * (4 + 16 + (size_t)tilePitch + 2) + 32;   // staged subtree
   b = (b + 15) & ~(size_t)15;
-  b += sizeof(GrowShared);
-  return b + 16;
+  return b + 16;                               // (GrowShared is a static __shared__ object of the kernel, not part of this)
 }
 
 __device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb, int hslots, int subMax, int tilePitch) {
@@ -237,14 +244,18 @@ __device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb, i
   m.sR = d; d += (size_t)ncmax * hb;
   m.hT = d; d += hsz;
   m.hW = d; d += hsz;
+  {                                            // the u32 histograms follow at once: [hT hW hN hE hNx hEx] is one region of hsz * 32 bytes
+    uint32_t* uh = (uint32_t*)d;
+    m.hN = uh; uh += hsz; m.hE = uh; uh += hsz; m.hNx = uh; uh += hsz; m.hEx = uh; uh += hsz;
+    const size_t hist = hsz * 32, tabs = (size_t)ncmax * hb * kTabSlots * 16;
+    m.tabL = m.hT; m.tabR = m.hT + (size_t)ncmax * hb * kTabSlots;
+    d = (double*)((unsigned char*)m.hT + (hist > tabs ? hist : tabs));
+  }
   m.statP = d; d += ncmax;
   m.PT = d; d += KS; m.PW = d; d += KS; m.cT = d; d += KS; m.cW = d; d += KS; m.cTL = d; d += KS; m.cTR = d; d += KS;
   uint32_t* u = (uint32_t*)d;
-  m.hN = u; u += hsz;
-  m.hE = u; u += hsz;
-  m.hNx = u; u += hsz;
-  m.hEx = u; u += hsz;
   m.pres = u; u += (size_t)ncmax * 8;
+  m.smk = u; u += (size_t)ncmax * kTabSlots * 8;
   m.segpos = u; u += KS; m.PN = u; u += KS; m.PE = u; u += KS; m.cN = u; u += KS; m.cE = u; u += KS;
   {
     uintptr_t al = ((uintptr_t)u + 7) & ~(uintptr_t)7;
@@ -269,8 +280,8 @@ __device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb, i
     m.stIdx = (uint16_t*)(m.stRow + subMax);
     u = (uint32_t*)(m.stIdx + subMax + (subMax & 1));
   }
-  uintptr_t p = ((uintptr_t)u + 15) & ~(uintptr_t)15;
-  m.s = (GrowShared*)p;
+  m.s = nullptr;                               // set by the kernel: GrowShared is a static __shared__ object, so every s->field
+                                               // access is an LDS / STS by construction (no address-space assumption needed)
   // tell the compiler these all live in shared memory (LDS/STS/ATOMS instead of generic LD/ST)
 #define RF_SH(x) __builtin_assume(__isShared(x))
 #if RF_ASSUME & 1
@@ -284,9 +295,6 @@ __device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb, i
 #endif
 #if RF_ASSUME & 8
   RF_SH(m.tileTL); RF_SH(m.tileTR); RF_SH(m.tileDelta); RF_SH(m.tileKey); RF_SH(m.radixBase); RF_SH(m.tileCut);
-#endif
-#if RF_ASSUME & 16
-  RF_SH(m.s);
 #endif
 #undef RF_SH
   return m;
@@ -917,10 +925,10 @@ __device__ inline void small_candidate(const NodeCtx& c, int ci, uint32_t len) {
   const SmallRec* __restrict__ rec = m.smRec;
   const uint8_t* __restrict__ cptr = m.smCodes + ci * kSmallMax;
   const int nw = (c.Kloop + 31) >> 5;
-  const int G = m.hs;                                              // table slots = strata per group
-  double* tabL = m.hT + (size_t)ci * m.hs * m.hb;
-  double* tabR = m.hW + (size_t)ci * m.hs * m.hb;
-  uint32_t* mk = m.hN + (size_t)ci * m.hs * m.hb;                  // [slot][8] codes that have rows in the slot's stratum
+  const int G = kTabSlots;                                         // table slots = strata per group
+  double* tabL = m.tabL + (size_t)ci * kTabSlots * m.hb;
+  double* tabR = m.tabR + (size_t)ci * kTabSlots * m.hb;
+  uint32_t* mk = m.smk + (size_t)ci * kTabSlots * 8;               // [slot][8] codes that have rows in the slot's stratum
   if (lane < 8) m.pres[ci * 8 + lane] = 0u;
   for (int b = lane; b < Dc; b += 32) { m.sL[ci * m.hb + b] = 0.0; m.sR[ci * m.hb + b] = 0.0; }
   __syncwarp();
@@ -1047,7 +1055,6 @@ __device__ inline void score_small(NodeCtx& c) {
   // then grown out of shared memory: each of its nodes fetches the codes of its own drawn covariates from the tile,
   // partitions by permuting 16-bit slot numbers, and never touches the lists or the table in global memory again.
   // (Deep in a tree every per-node gather used to be one DRAM round trip per level for one byte per 32-byte sector.)
-  const bool rowm = d.rowcodes != nullptr;
   if (m.subMax > 0 && !s->inSub && len <= (uint32_t)m.subMax && !w.sinkDelta) {
     const int chunks = m.tilePitch >> 4;
     for (uint32_t q = (uint32_t)tid; q < len * (uint32_t)chunks; q += kThreads) {
@@ -1062,12 +1069,15 @@ __device__ inline void score_small(NodeCtx& c) {
       SmallRec r; r.mrt = (double)mult * rr.rt; r.mult = mult; r.es = (rr.es & 1u) | (c.strat ? (rr.es & 0xFFFFFF00u) : 0u);
       m.stRow[j] = ent; m.stRec[j] = r; m.stIdx[j] = (uint16_t)j;
     }
+    __syncthreads();                       // every thread has read inSub == 0 (it is inside this block) before the flag flips
     if (tid == 0) { s->inSub = 1; s->subSp = s->sp; s->subStart = s->cur.start; }
     __syncthreads();
     RF_PROF(14);
   }
   const bool sub = s->inSub != 0;
   const uint32_t soff = sub ? s->cur.start - s->subStart : 0u;
+  const int cstride = s->candStride;
+  RF_ASSERT(!sub || (s->cur.start >= s->subStart && soff + len <= (uint32_t)m.subMax), "staged subtree: tree %d node %u start %u len %u outside the tile (subStart %u subMax %d sp %u subSp %u)\n", c.tree, s->cur.nodeID, s->cur.start, len, s->subStart, m.subMax, s->sp, s->subSp);
   // stage the node: one thread per entry, all of an entry's gathers issued before the first shared-memory store.
   // With the row-major mirror an entry costs one 16-byte record + the sectors of ONE code row instead of three
   // per-row arrays + one 32-byte sector per candidate column; inside a staged subtree it costs no global access.
@@ -1080,6 +1090,7 @@ __device__ inline void score_small(NodeCtx& c) {
     uint32_t row = 0u;
     if (sub) {
       const uint32_t slot = valid ? (uint32_t)m.stIdx[soff + j] : 0u;
+      RF_ASSERT(slot < (uint32_t)m.subMax, "staged subtree: tree %d slot %u at position %u + %u (subMax %d)\n", c.tree, slot, soff, j, m.subMax);
       const SmallRec r = m.stRec[slot];
       ent = m.stRow[slot]; e = r.es & 1u; sidx = r.es >> 8; mult = r.mult; mrt = r.mrt;
       rc = m.stTile + (size_t)slot * m.tilePitch;
@@ -1091,25 +1102,20 @@ __device__ inline void score_small(NodeCtx& c) {
       ent = valid ? c.list[j] : 0u;
       RF_ASSERT((ent & kRowMask) < (uint32_t)d.n, "small staging: tree %d entry %u/%u = %08x (start %u buf %u node %u)\n", c.tree, j, len, ent, s->cur.start, s->cur.buf, s->cur.nodeID);
       row = ent & kRowMask; mult = (ent >> kRowBits) + 1u;
-      double tv;
-      if (rowm) {
-        const RowRec rr = d.rowrec[row];
-        e = rr.es & 1u; tv = rr.rt; sidx = c.strat ? (rr.es >> 8) : 0u;
-        rc = d.rowcodes + (size_t)row * (size_t)d.rowPitch;
-      } else {
-        e = d.ev[row]; tv = d.rt[row]; sidx = c.strat ? (uint32_t)d.strat[row] - 1u : 0u;
-      }
-      mrt = (double)mult * tv;
+      const RowRec rr = d.rowrec[row];
+      e = rr.es & 1u; sidx = c.strat ? (rr.es >> 8) : 0u;
+      mrt = (double)mult * rr.rt;
       if (c.strat) {
-        if (lane == 0 && j > 0u) { const uint32_t r2 = c.list[j - 1u] & kRowMask; edgeS = rowm ? (d.rowrec[r2].es >> 8) : (uint32_t)d.strat[r2] - 1u; }
-        if (lane == 31 && j + 1u < len) { const uint32_t r2 = c.list[j + 1u] & kRowMask; edgeS = rowm ? (d.rowrec[r2].es >> 8) : (uint32_t)d.strat[r2] - 1u; }
+        if (lane == 0 && j > 0u) edgeS = d.rowrec[c.list[j - 1u] & kRowMask].es >> 8;
+        if (lane == 31 && j + 1u < len) edgeS = d.rowrec[c.list[j + 1u] & kRowMask].es >> 8;
       }
     }
+    const size_t roff = (size_t)row * (size_t)cstride;
     for (int half = 0; half < nc; half += 8) {
       uint32_t raw[8];
 #pragma unroll
       for (int q = 0; q < 8; q++)
-        raw[q] = (half + q < nc) ? (rc ? (uint32_t)rc[s->candCov[half + q]] : (uint32_t)((const uint8_t*)s->candPtr[half + q])[row]) : 0u;
+        raw[q] = (half + q < nc) ? (rc ? (uint32_t)rc[s->candCov[half + q]] : (uint32_t)((const uint8_t*)s->candPtr[half + q])[roff]) : 0u;
 #pragma unroll
       for (int q = 0; q < 8; q++)
         if (valid && half + q < nc) m.smCodes[(half + q) * kSmallMax + j] = (uint8_t)raw[q];
@@ -1176,7 +1182,7 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
     m.segpos[0] = 0; m.segpos[1] = 0; m.segpos[2] = cur.len;
   }
   if (s->histDirty) {                                                // small nodes kept tables in the histograms since the last large node
-    for (int i = tid; i < g.ncmax * m.hb * m.hs; i += kThreads) { m.hN[i] = 0; m.hT[i] = 0.0; m.hW[i] = 0.0; }
+    for (int i = tid; i < g.ncmax * m.hb * m.hs; i += kThreads) { m.hN[i] = 0; m.hE[i] = 0; m.hNx[i] = 0; m.hEx[i] = 0; m.hT[i] = 0.0; m.hW[i] = 0.0; }   // (the term tables lie over all six)
   }
   for (int i = tid; i < nc * m.hb; i += kThreads) { m.sL[i] = 0.0; m.sR[i] = 0.0; }
   for (int i = tid; i < nc * 8; i += kThreads) m.pres[i] = 0u;
@@ -1192,10 +1198,8 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
     const uint8_t* __restrict__ hptr[kMaxCand];
 #pragma unroll
     for (int ci = 0; ci < kMaxCand; ci++) hptr[ci] = (ci < nc) ? (const uint8_t*)s->candPtr[ci] : nullptr;
-    // A node that holds few of the table's rows gathers from the row-major mirror: its c code bytes of a row sit in
-    // at most rowPitch / 32 sectors, against one 32-byte sector per column from the column-major arrays (whose
-    // sectors are only shared between entries while the node still holds a good fraction of consecutive rows).
-    const bool sparse = d.rowcodes != nullptr && (unsigned long long)cur.len * (unsigned long long)kSparseRatio < (unsigned long long)d.n;
+    // (candPtr / candStride already point a sparse node at the row-major mirror of the table: see the draw step)
+    const size_t cstride = (size_t)s->candStride;
     const int hstride = m.hs * m.hb;
     for (int k0 = 1; k0 <= Kloop; k0 += m.hs) {
       // one pass accumulates the next hs strata (a contiguous entry range: the list is stratum-major),
@@ -1213,13 +1217,12 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
         if (i + kThreads < s1) entNext = list[i + kThreads];       // software pipelining: next entry's load overlaps this entry's gathers
         const uint32_t row = ent & kRowMask, mult = (ent >> kRowBits) + 1u;
         // issue every gather of this entry before the first shared-memory atomic
-        uint32_t e; double tv;
-        if (d.rowrec) { const RowRec rr = d.rowrec[row]; e = rr.es & 1u; tv = unit ? 0.0 : rr.rt; }
-        else { e = d.ev[row]; tv = unit ? 0.0 : d.rt[row]; }
+        const RowRec rr = d.rowrec[row];
+        const uint32_t e = rr.es & 1u; const double tv = unit ? 0.0 : rr.rt;
+        const size_t roff = (size_t)row * cstride;
         const int slotOff = ((i >= bnd[0]) + (i >= bnd[1]) + (i >= bnd[2])) * m.hb;
         const bool isT0 = tv == d.rt_mode;
         const unsigned long long ft = (unsigned long long)__double2ll_rn(tv * g.tscale) * (unsigned long long)mult;
-        const uint8_t* __restrict__ rc = d.rowcodes + (size_t)row * (size_t)d.rowPitch;    // (only dereferenced when sparse)
 #pragma unroll
         for (int half = 0; half < kMaxCand; half += 8) {
           if (half < nc) {
@@ -1227,7 +1230,7 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
 #pragma unroll
             for (int q = 0; q < 8; q++) {
               const int ci = half + q;
-              raw[q] = (ci < nc && ((hmask >> ci) & 1u)) ? (sparse ? (uint32_t)rc[s->candCov[ci]] : (uint32_t)hptr[ci][row]) : 0u;
+              raw[q] = (ci < nc && ((hmask >> ci) & 1u)) ? (uint32_t)hptr[ci][roff] : 0u;
             }
 #pragma unroll
             for (int q = 0; q < 8; q++) {
@@ -1351,6 +1354,7 @@ __device__ inline void node_prologue_nsplit(const DevData& d, const GrowParams& 
       m.pool[sl - 1] = m.pool[size0 - 1 - k];
       const int Dv = d.D[cov];
       s->candCov[k] = cov; s->candD[k] = Dv; s->candW[k] = d.width[cov]; s->candPtr[k] = d.codes[cov]; s->candHist[k] = Dv <= kHistBins;
+      s->candStride = 1;
     }
     if (tid < 8) { m.pres[k * 8 + tid] = 0u; s->cutMask[k][tid] = 0u; s->rankSel[tid] = 0u; }
     __syncthreads();
@@ -1426,8 +1430,14 @@ __device__ inline bool append_record(const GrowWork& w, GrowShared* s, int tree,
 extern "C" __global__ void __launch_bounds__(kThreads, RF_MIN_CTAS)
 rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ GrowShared g_state;
   GrowSmem m = carve(smem_raw, g.ncmax, d.K, g.hbins, g.hslots, g.subMax, (d.rowPitch + 15) & ~15);
-  GrowShared* s = m.s;
+  m.s = &g_state;
+  GrowShared* s = &g_state;
+#ifdef RF_CHECK
+  { unsigned dyn; asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    RF_ASSERT((size_t)((unsigned char*)(m.stIdx + m.subMax) - smem_raw) <= (size_t)dyn, "shared memory: carve-up ends at %llu of %u bytes\n", (unsigned long long)((unsigned char*)(m.stIdx + m.subMax) - smem_raw), dyn); }
+#endif
   const int tid = vtid();
   const int n = d.n;
   const bool sliced = w.treeState != nullptr;
@@ -1480,26 +1490,38 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
   __syncthreads();
 
   // ---- root: in-bag entry list in internal row order from the bootstrap counts (rf.c:492-627) ----
+  // Eight consecutive rows per thread and tile: one 16-byte load of their u16 counts, one block scan per 8 * kThreads
+  // rows (the counts are streamed once; a tile per kThreads rows was one dependent load + two barriers per row).
   {
+    constexpr int kRpt = 8;
     uint32_t base = 0;
     unsigned long long ne = 0; double rts = 0.0;
-    const uint32_t ntiles = ((uint32_t)n + kThreads - 1) / kThreads;
+    const uint32_t ntiles = ((uint32_t)n + kRpt * kThreads - 1) / (kRpt * kThreads);
+    const uint4* cnt8 = (const uint4*)cnt;                                   // cntStride is a multiple of 8 counts
     for (uint32_t t = 0; t < ntiles; t++) {
-      uint32_t i = t * kThreads + tid;
-      uint32_t cval = (i < (uint32_t)n) ? cnt[i] : 0u;
-      uint32_t nent = (cval + kMaxMult - 1) / kMaxMult;
+      const uint32_t i0 = (t * kThreads + tid) * kRpt;
+      uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+      if (i0 < (uint32_t)n) raw = cnt8[i0 / kRpt];                           // rows past n inside the last vector hold zero counts
+      uint32_t cv[kRpt] = {raw.x & 0xFFFFu, raw.x >> 16, raw.y & 0xFFFFu, raw.y >> 16, raw.z & 0xFFFFu, raw.z >> 16, raw.w & 0xFFFFu, raw.w >> 16};
+      uint32_t mine = 0;
+#pragma unroll
+      for (int k = 0; k < kRpt; k++) { if (i0 + k >= (uint32_t)n) cv[k] = 0u; mine += (cv[k] + kMaxMult - 1) / kMaxMult; }
       unsigned long long tot;
-      unsigned long long inc = block_incl_scan<unsigned long long>((unsigned long long)nent, s->scrU, tot);
-      uint32_t pos = base + (uint32_t)(inc - nent);
-      uint32_t left = cval;
-      for (uint32_t q = 0; q < nent; q++) {
-        uint32_t mu = left > kMaxMult ? kMaxMult : left;
-        listA[pos + q] = ((mu - 1u) << kRowBits) | i;
-        left -= mu;
-      }
-      if (cval) {
-        ne += ((unsigned long long)cval << 32) | (unsigned long long)(d.ev[i] ? cval : 0u);
-        rts += (double)cval * d.rt[i];
+      unsigned long long inc = block_incl_scan<unsigned long long>((unsigned long long)mine, s->scrU, tot);
+      uint32_t pos = base + (uint32_t)(inc - mine);
+#pragma unroll
+      for (int k = 0; k < kRpt; k++) {
+        uint32_t left = cv[k];
+        if (left) {
+          const RowRec rr = d.rowrec[i0 + k];
+          ne += ((unsigned long long)left << 32) | (unsigned long long)((rr.es & 1u) ? left : 0u);
+          rts += (double)left * rr.rt;
+          while (left) {
+            const uint32_t mu = left > kMaxMult ? kMaxMult : left;
+            listA[pos++] = ((mu - 1u) << kRowBits) | (i0 + k);
+            left -= mu;
+          }
+        }
       }
       base += (uint32_t)tot;
       __syncthreads();
@@ -1574,10 +1596,17 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
         __syncwarp();
         const int ncd = s->nc;
         if (lane == 0) s->algoBytes += (unsigned long long)cur.m * (12ull * (unsigned long long)ncd + 20ull);
+        // A node that holds few of the table's rows gathers from the row-major mirror (when the table has one): the c
+        // code bytes of a row sit in at most rowPitch / 32 sectors there, against one 32-byte sector per column from
+        // the column-major arrays (whose sectors are shared between entries only while the node still holds a good
+        // fraction of consecutive rows).  One stride per node: code = candPtr[k][row * candStride].
+        const bool sparse = d.rowcodes != nullptr && (unsigned long long)cur.len * (unsigned long long)kSparseRatio < (unsigned long long)d.n;
+        if (lane == 0) s->candStride = sparse ? d.rowPitch : 1;
         if (lane < ncd) {                                  // candidate metadata: one parallel round of loads
           const int cov = s->candCov[lane];
           const int Dv = d.D[cov];
-          s->candD[lane] = Dv; s->candW[lane] = d.width[cov]; s->candPtr[lane] = d.codes[cov]; s->candHist[lane] = Dv <= kHistBins; s->candLocal[lane] = 0;
+          s->candD[lane] = Dv; s->candW[lane] = d.width[cov]; s->candHist[lane] = Dv <= kHistBins; s->candLocal[lane] = 0;
+          s->candPtr[lane] = sparse ? (const void*)(d.rowcodes + cov) : d.codes[cov];
         }
       }
     }
@@ -1673,7 +1702,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     // dependent code gathers, are in flight together (the kernel is latency-bound, not HBM-bound).
     // pass 1: sizes of the left child
     unsigned long long cL = 0, neL = 0; double rtL = 0.0, rtR = 0.0;
-    const bool sparseP = d.rowcodes != nullptr && (unsigned long long)cur.len * (unsigned long long)kSparseRatio < (unsigned long long)n;
+    const size_t pstride = (wd == 1) ? (size_t)s->candStride : 1;   // (the winning candidate's pointer follows the node's layout)
     for (uint32_t base = 0; base < cur.len; base += 4u * kThreads) {
       uint32_t ent[4]; uint32_t cd[4]; uint32_t ev4[4]; double rt4[4];
 #pragma unroll
@@ -1682,15 +1711,9 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
       for (int u = 0; u < 4; u++) {
         const bool valid = ent[u] != 0xFFFFFFFFu;
         const uint32_t row = ent[u] & kRowMask;
-        if (sparseP) {                                             // one code-row sector + one 16-byte record per entry
-          cd[u] = valid ? (uint32_t)d.rowcodes[(size_t)row * (size_t)d.rowPitch + cov] : 0xFFFFFFFFu;
-          const RowRec rr = valid ? d.rowrec[row] : RowRec{0.0, 0u, 0u};
-          ev4[u] = rr.es & 1u; rt4[u] = bayes ? rr.rt : 0.0;
-        } else {
-          cd[u] = valid ? load_code(ptr, wd, row) : 0xFFFFFFFFu;
-          ev4[u] = valid ? (uint32_t)d.ev[row] : 0u;
-          rt4[u] = (valid && bayes) ? d.rt[row] : 0.0;
-        }
+        cd[u] = valid ? (wd == 1 ? (uint32_t)((const uint8_t*)ptr)[(size_t)row * pstride] : load_code(ptr, wd, row)) : 0xFFFFFFFFu;
+        const RowRec rr = valid ? d.rowrec[row] : RowRec{0.0, 0u, 0u};
+        ev4[u] = rr.es & 1u; rt4[u] = bayes ? rr.rt : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < 4; u++) {
@@ -1715,7 +1738,7 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
         for (int u = 0; u < 4; u++) { const uint32_t i = base + 4u * tid + u; ent[u] = (i < cur.len) ? src[i] : 0xFFFFFFFFu; }
 #pragma unroll
         for (int u = 0; u < 4; u++)
-          cd[u] = (ent[u] != 0xFFFFFFFFu) ? (sparseP ? (uint32_t)d.rowcodes[(size_t)(ent[u] & kRowMask) * (size_t)d.rowPitch + cov] : load_code(ptr, wd, ent[u] & kRowMask)) : 0xFFFFFFFFu;
+          cd[u] = (ent[u] != 0xFFFFFFFFu) ? (wd == 1 ? (uint32_t)((const uint8_t*)ptr)[(size_t)(ent[u] & kRowMask) * pstride] : load_code(ptr, wd, ent[u] & kRowMask)) : 0xFFFFFFFFu;
         uint32_t mine = 0;
 #pragma unroll
         for (int u = 0; u < 4; u++) mine += (ent[u] != 0xFFFFFFFFu && cd[u] <= bcode) ? 1u : 0u;

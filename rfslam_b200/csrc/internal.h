@@ -33,9 +33,9 @@ struct DevData {
   // scattered fraction of the rows: gathering c candidate codes of a row from the column-major arrays costs c
   // 32-byte DRAM sectors for c bytes, from here at most rowPitch / 32 sectors -- and a whole row fits the
   // shared-memory tile that serves the subtree below a small node.
-  const uint8_t*  rowcodes;       // [n][rowPitch] or nullptr
+  const uint8_t*  rowcodes;       // [n][rowPitch] or nullptr (built only for tables that do not fit L2 anyway)
   int             rowPitch;       // p rounded up to a multiple of 16
-  const RowRec*   rowrec;         // [n]
+  const RowRec*   rowrec;         // [n] always present
 };
 
 }  // namespace rfslam
