@@ -180,8 +180,9 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 // (draws, tracker combine, records).  Hardware warp w issues on scheduler w % 4, so with several CTAs
 // per SM every CTA's serial warp would pile onto scheduler 0; rotating the numbering per CTA spreads
 // them (CTAs b and b + 148 share an SM under the round-robin placement and get different rotations).
-__device__ __forceinline__ int warp_rot() { return (int)((blockIdx.x * 5u + (blockIdx.x / 148u) * 3u) & (unsigned)(kWarps - 1)); }
-__device__ __forceinline__ int warp_id() { return (int)(((threadIdx.x >> 5) + (unsigned)warp_rot()) & (unsigned)(kWarps - 1)); }
+__device__ __forceinline__ unsigned warp_wrap(unsigned v) { return (kWarps & (kWarps - 1)) == 0 ? (v & (unsigned)(kWarps - 1)) : (v % (unsigned)kWarps); }
+__device__ __forceinline__ int warp_rot() { return (int)warp_wrap(blockIdx.x * 5u + (blockIdx.x / 148u) * 3u); }
+__device__ __forceinline__ int warp_id() { return (int)warp_wrap((threadIdx.x >> 5) + (unsigned)warp_rot()); }
 __device__ __forceinline__ int vtid() { return (warp_id() << 5) | (int)(threadIdx.x & 31); }
 
 template <typename T>

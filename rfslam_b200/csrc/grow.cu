@@ -253,6 +253,11 @@ void launch_bootstrap_draw(const int* d_seedA, const int* d_bootSize, uint32_t* 
   bootstrap_draw_kernel<<<ntrees, 32>>>(d_seedA, d_bootSize, d_draws, stride, n);
 }
 
+}  // namespace rfslam
+#include "grow_variant.h"
+RFSLAM_DEFINE_VARIANT(t256, rfslam_grow_kernel)
+namespace rfslam {
+
 int validate_grow_args(const rfslam_grow_args* a, GrowConfig* cfg) {
   if (!a) { set_error("null arguments"); return RFSLAM_EINVAL; }
   if (a->seed >= 0) { set_error("Random seed must be less than zero (rf.c:6454)"); return RFSLAM_EINVAL; }
@@ -401,33 +406,52 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         g.split_weight = d_sw.p;
       }
     }
-    // Shared-memory plan: two CTAs per SM need <= ~112 KB each.  The staged-subtree tile (subMax whole rows) is
-    // worth more than wide histogram passes: strata slots per pass go 4 -> 2 (same entries, same flushes, two more
-    // barriers per large node) before the tile shrinks.
+    // Kernel plan per launch: CTA width (grow_variant.h) and the shared-memory carve-up that goes with it.
+    //   * 256 threads, two CTAs per SM: the default;
+    //   * 320 threads, two CTAs per SM: mtry of 9 or 10 -- one warp per candidate instead of two scoring rounds;
+    //   * 512 threads, one CTA per SM: a launch with no more trees than SMs (a forest sharded over many GPUs), where half
+    //     of every SM would idle and the passes over large nodes are the per-tree critical path.
+    // Shared memory: the staged-subtree tile (subMax whole rows) is worth more than wide histogram passes, so the strata
+    // slots per pass go 4 -> 2 (same entries, same flushes, two more barriers per large node) before the tile shrinks.
     const int tilePitch = (ds->dev.rowPitch + 15) & ~15;
-    g.hslots = hist_slots(g.hbins);
-    g.subMax = 0;
-    if (ds->dev.rowcodes && cfg.nsplit == 0 && !getenv("RFSLAM_NO_SUBTREE")) {
-      const size_t limit = (112u << 10) - sizeof(GrowShared);     // dynamic part; GrowShared is static shared memory of the kernel
-      const int wantSub = getenv("RFSLAM_SUBTREE_MAX") ? atoi(getenv("RFSLAM_SUBTREE_MAX")) : kSmallMax;
-      const int hsFull = g.hslots, hsMin = std::min(2, hsFull);
-      for (int sm = std::min(wantSub, kSmallMax); sm >= 128 && g.subMax == 0; sm >>= 1)
-        for (int hs = hsFull; hs >= hsMin; hs >>= 1)
-          if (grow_smem_bytes(g.ncmax, ds->K, g.hbins, hs, sm, tilePitch) <= limit) { g.hslots = hs; g.subMax = sm; break; }
-    }
-    const size_t smem = grow_smem_bytes(g.ncmax, ds->K, g.hbins, g.hslots, g.subMax, tilePitch);
-    RF_CUDA(cudaFuncSetAttribute(rfslam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int residentCtas = 0; long long quantumCycles = 0;
+    int sms = 0; long long quantumCycles = 0;
     {
-      int perSm = 0, dev = 0, sms = 0, khz = 0;
-      RF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, rfslam_grow_kernel, kThreads, smem));
+      int dev = 0, khz = 0;
       RF_CUDA(cudaGetDevice(&dev));
       RF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
       RF_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));                  // kHz = cycles per ms
-      residentCtas = std::max(1, perSm) * sms;
       const char* q = getenv("RFSLAM_QUANTUM_MS");
       quantumCycles = (long long)((q ? atof(q) : 10.0) * (double)khz);
     }
+    struct Plan { const GrowVariant* kv; GrowParams g; size_t smem; int residentCtas; };
+    auto make_plan = [&](int trees) -> Plan {
+      Plan pl; pl.g = g;
+      pl.kv = grow_variant_t256();
+      if (!g.has_sort) {                                   // (the sorted-walk path's tile arrays are laid out for 256 threads)
+        if (trees <= sms) pl.kv = grow_variant_t512();
+        else if (g.ncmax > 8) pl.kv = grow_variant_t320();
+      }
+      if (const char* e = getenv("RFSLAM_CTA_THREADS")) {
+        const int v = atoi(e);
+        if (!g.has_sort) pl.kv = v == 512 ? grow_variant_t512() : v == 320 ? grow_variant_t320() : grow_variant_t256();
+      }
+      const int ctasWanted = pl.kv->threads == 512 ? 1 : 2;
+      pl.g.hslots = hist_slots(g.hbins);
+      pl.g.subMax = 0;
+      if (ds->dev.rowcodes && cfg.nsplit == 0 && !getenv("RFSLAM_NO_SUBTREE")) {
+        const size_t limit = ((ctasWanted == 1 ? 200u : 112u) << 10) - sizeof(GrowShared);     // dynamic part; GrowShared is static shared memory
+        const int wantSub = getenv("RFSLAM_SUBTREE_MAX") ? atoi(getenv("RFSLAM_SUBTREE_MAX")) : kSmallMax;
+        const int hsFull = pl.g.hslots, hsMin = std::min(2, hsFull);
+        for (int sm = std::min(wantSub, kSmallMax); sm >= 128 && pl.g.subMax == 0; sm >>= 1)
+          for (int hs = hsFull; hs >= hsMin; hs >>= 1)
+            if (grow_smem_bytes(g.ncmax, ds->K, g.hbins, hs, sm, tilePitch) <= limit) { pl.g.hslots = hs; pl.g.subMax = sm; break; }
+      }
+      pl.smem = grow_smem_bytes(g.ncmax, ds->K, g.hbins, pl.g.hslots, pl.g.subMax, tilePitch);
+      int perSm = 0;
+      RF_CUDA(pl.kv->prepare(pl.smem, &perSm));
+      pl.residentCtas = std::max(1, perSm) * sms;
+      return pl;
+    };
 
     // ---- batch size from free memory ----
     size_t freeB = 0, totalB = 0;
@@ -568,18 +592,19 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         w.candCount = d_cand.p; w.algoBytes = d_algo.p; w.status = d_status.p;
         w.prof = profile ? d_prof.p : nullptr;
         // more trees than resident CTAs: the grid is the resident CTAs and trees are time-sliced
+        const Plan pl = make_plan(nb);
         int gridTrees = nb;
         DevBuf<int> d_tstate(pool); DevBuf<unsigned char> d_saved(pool);
-        if (nb > residentCtas && !getenv("RFSLAM_NO_SLICING")) {
+        if (nb > pl.residentCtas && !getenv("RFSLAM_NO_SLICING")) {
           d_tstate.alloc((size_t)nb + 2); d_tstate.zero();
           d_saved.alloc((size_t)nb * sizeof(GrowShared));
           RF_CUDA(cudaMemcpyAsync(d_tstate.p + nb, &nb, 4, cudaMemcpyHostToDevice));     // waiting = nb; ticket = 0
           w.treeState = d_tstate.p; w.waiting = d_tstate.p + nb; w.ticket = (unsigned*)(d_tstate.p + nb + 1);
           w.saved = d_saved.p; w.quantum = quantumCycles;
-          gridTrees = residentCtas;
+          gridTrees = pl.residentCtas;
         }
         RF_CUDA(cudaEventRecord(ev1));
-        rfslam_grow_kernel<<<gridTrees, kThreads, smem>>>(ds->dev, g, w);
+        pl.kv->launch(ds->dev, pl.g, w, gridTrees, pl.smem);
         launches++;
         RF_CUDA(cudaEventRecord(ev2));
         RF_CUDA(cudaGetLastError());

@@ -130,7 +130,7 @@ struct GrowShared {
   int have; double bestDelta; int bestCand; uint32_t bestCode;
   int cutsSeen;
   // scratch for block reductions / scans
-  double scrD[kWarps]; unsigned long long scrU[kWarps]; int scrI[kWarps];
+  double scrD[32]; unsigned long long scrU[32]; int scrI[32];   // (sized for the widest CTA: the struct is the same in every build of the kernel)
   uint32_t nodeCount, leafCount, sp;
   unsigned long long candCount, algoBytes;
   int abort;
@@ -614,18 +614,19 @@ __device__ inline void radix_pass(const uint32_t* kin, const uint32_t* vin, uint
                                   uint32_t len, int shift, GrowShared* s, uint32_t* rbase) {
   const int tid = vtid(), lane = lane_id(), wid = warp_id();
   __syncthreads();
-  constexpr int kDigPer = 256 / kThreads;                // digits owned by one thread (consecutive)
-  for (int q = 0; q < kDigPer; q++) rbase[tid * kDigPer + q] = 0;
+  constexpr int kDigPer = (256 + kThreads - 1) / kThreads;   // digits owned by one thread (consecutive); threads past digit 255 own none
+  const bool owns = tid * kDigPer < 256;
+  for (int q = 0; q < kDigPer; q++) if (owns) rbase[tid * kDigPer + q] = 0;
   __syncthreads();
   for (uint32_t i = tid; i < len; i += kThreads) atomicAdd(&rbase[(kin[i] >> shift) & 255u], 1u);
   __syncthreads();
   uint32_t cnt[kDigPer]; uint32_t mine = 0;
-  for (int q = 0; q < kDigPer; q++) { cnt[q] = rbase[tid * kDigPer + q]; mine += cnt[q]; }
+  for (int q = 0; q < kDigPer; q++) { cnt[q] = owns ? rbase[tid * kDigPer + q] : 0u; mine += cnt[q]; }
   unsigned long long tot;
   unsigned long long inc = block_incl_scan<unsigned long long>((unsigned long long)mine, s->scrU, tot);
   __syncthreads();
   uint32_t run = (uint32_t)(inc - mine);
-  for (int q = 0; q < kDigPer; q++) { rbase[tid * kDigPer + q] = run; run += cnt[q]; }
+  for (int q = 0; q < kDigPer; q++) { if (owns) rbase[tid * kDigPer + q] = run; run += cnt[q]; }
   __syncthreads();
   const uint32_t ntiles = (len + kThreads - 1) / kThreads;
   for (uint32_t t = 0; t < ntiles; t++) {
@@ -1427,8 +1428,11 @@ __device__ inline bool append_record(const GrowWork& w, GrowShared* s, int tree,
 #ifndef RF_MIN_CTAS
 #define RF_MIN_CTAS 2
 #endif
+#ifndef RF_KERNEL_NAME
+#define RF_KERNEL_NAME rfslam_grow_kernel      // the 256-thread build; grow_variants.cu instantiates wider CTAs under other names
+#endif
 extern "C" __global__ void __launch_bounds__(kThreads, RF_MIN_CTAS)
-rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
+RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ GrowShared g_state;
   GrowSmem m = carve(smem_raw, g.ncmax, d.K, g.hbins, g.hslots, g.subMax, (d.rowPitch + 15) & ~15);
@@ -1657,8 +1661,8 @@ rfslam_grow_kernel(DevData d, GrowParams g, GrowWork w) {
     if (small) {
       // the node is staged in shared memory: thread t owns entries 2t and 2t+1, one block scan of a
       // packed (left entries | left rows << 16 | left events << 40) word gives sizes and positions
-      constexpr int kEpt = kSmallMax / kThreads;               // staged entries per thread (consecutive)
-      static_assert(kSmallMax % kThreads == 0 && kEpt <= 4, "staged entries per thread");
+      constexpr int kEpt = (kSmallMax + kThreads - 1) / kThreads;   // staged entries per thread (consecutive)
+      static_assert(kEpt <= 4, "staged entries per thread");
       unsigned long long my = 0ull; bool lf[kEpt]; uint32_t en[kEpt];
       double rtL = 0.0, rtR = 0.0;
       const bool sub = s->inSub != 0;                            // staged subtree: the "list" is the slot order in shared memory

@@ -380,3 +380,35 @@ def test_bootstrap_larger_than_the_table_is_sized_or_refused():
     big = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, splitrule=4, ntree=2, nodesize=5, seed=-3, sampsize=40 * d.n, membership=True)
     want = port.grow(d.x, d.y, d.rt, d.strat, rule=4, ntree=2, nodesize=5, seed=-3, sampsize=40 * d.n)
     parity.assert_forest_equal(big, want, d.n, 2, label="sampsize 40n")
+
+
+@pytest.mark.parametrize("threads", [256, 320, 512])
+def test_every_cta_width_grows_the_same_forest(threads, monkeypatch):
+    """The tree kernel is built at three CTA widths (csrc/grow_variant.h); which one a launch takes depends on mtry and on
+    how many trees it holds.  Forced one by one here -- with enough trees to be time-sliced and mtry = 10, the case the
+    ten-warp build exists for -- they must all grow the oracle's forest."""
+    d = make_cpiu(2500, 30, levels=32, seed=33)
+    ntree = 320
+    monkeypatch.setenv("RFSLAM_CTA_THREADS", str(threads))
+    monkeypatch.setenv("RFSLAM_QUANTUM_MS", "0.2")
+    got = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, splitrule=1, ntree=ntree, nodesize=5, mtry=10, seed=-19, membership=True)
+    want = port.grow(d.x, d.y, d.rt, d.strat, rule=1, ntree=ntree, nodesize=5, mtry=10, seed=-19)
+    parity.assert_forest_equal(got, want, d.n, ntree, label=f"cta{threads}")
+
+
+def test_row_major_mirror_and_staged_subtrees_match_oracle(monkeypatch):
+    """Tables beyond L2 get a row-major mirror and grow small subtrees out of a shared-memory tile (csrc/grow_kernel.cuh
+    stage_subtree); forced on here for a table that would not take that path by size."""
+    monkeypatch.setenv("RFSLAM_ROWMAJOR", "1")
+    for rule, levels, nodesize, p in ((4, 64, 5, 40), (1, 200, 3, 17), (5, 16, 10, 9)):
+        d = make_cpiu(30000, p, levels=levels, seed=44 + rule)
+        ntree = 3
+        got = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, splitrule=rule, ntree=ntree, nodesize=nodesize, seed=-23, membership=True)
+        want = port.grow(d.x, d.y, d.rt, d.strat, rule=rule, ntree=ntree, nodesize=nodesize, seed=-23)
+        parity.assert_forest_equal(got, want, d.n, ntree, label=f"rowmajor rule {rule}")
+    d = make_cpiu(6000, 12, levels=32, seed=50)                       # and time-sliced (staged subtrees are never parked)
+    monkeypatch.setenv("RFSLAM_QUANTUM_MS", "0.05")
+    monkeypatch.setenv("RFSLAM_CTA_THREADS", "256")
+    got = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, splitrule=4, ntree=400, nodesize=5, seed=-29, membership=True)
+    want = port.grow(d.x, d.y, d.rt, d.strat, rule=4, ntree=400, nodesize=5, seed=-29)
+    parity.assert_forest_equal(got, want, d.n, 400, label="rowmajor sliced")
