@@ -15,6 +15,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -301,6 +302,10 @@ int predict_forest(const rfslam_predict_args* a, rfslam_predict_out* out) {
   const int64_t mAll = restore ? n : a->fobservation_size;
   const int64_t r0 = restore ? 0 : a->frow_first;
   const int64_t M = restore ? n : (a->frow_count > 0 ? a->frow_count : mAll - r0);
+  const bool timing = getenv("RFSLAM_TIMING") != nullptr;
+  auto wall = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tw0 = wall();
+  double twForest = 0, twReplay = 0, twSweep = 0;
   try {
     if (a->device >= 0) RF_CUDA(cudaSetDevice(a->device));
     Streams st;
@@ -382,6 +387,7 @@ int predict_forest(const rfslam_predict_args* a, rfslam_predict_out* out) {
     if (haveClas) RF_CUDA(cudaMemcpyAsync(d_clas, a->tnCLAS, 2 * (size_t)NL * 4, cudaMemcpyHostToDevice));
     else RF_CUDA(cudaMemsetAsync(d_clas, 0, 2 * (size_t)NL * 4));
 
+    if (timing) { RF_CUDA(cudaDeviceSynchronize()); twForest = wall(); }
     // ---- bootstrap replay (restore mode, missing tnCLAS, or bootMembership wanted) ----
     Buf b_cnt16, b_y, b_seed, b_bs, b_draws, b_samp;
     uint16_t* d_cnt = nullptr; double* d_y = nullptr;
@@ -422,6 +428,7 @@ int predict_forest(const rfslam_predict_args* a, rfslam_predict_out* out) {
       RF_CUDA(cudaGetLastError());
     }
 
+    if (timing) { RF_CUDA(cudaDeviceSynchronize()); twReplay = wall(); }
     // ---- row tiles ----
     size_t freeB = 0, totalB = 0;
     RF_CUDA(cudaMemGetInfo(&freeB, &totalB));
@@ -507,6 +514,7 @@ int predict_forest(const rfslam_predict_args* a, rfslam_predict_out* out) {
     RF_CUDA(cudaEventRecord(st.e1));
     RF_CUDA(cudaGetLastError());
     RF_CUDA(cudaEventSynchronize(st.e1));
+    if (timing) twSweep = wall();
     RF_CUDA(cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost));
     if (bad == 5) { host_free(h_perf); set_error("by.user in-bag counts must be in [0, 65535]"); throw CudaFail{RFSLAM_EINVAL}; }
     float totMs = 0.f;
@@ -536,10 +544,13 @@ int predict_forest(const rfslam_predict_args* a, rfslam_predict_out* out) {
       RF_CUDA(cudaGetLastError());
       out->bootMembership = (int32_t*)fetch(d_wide, (size_t)ntree * n * 4);
     }
+    if (timing) fprintf(stderr, "[rfslam_b200_predict] forest upload + restore %.1f ms, bootstrap replay %.1f ms, row sweeps %.1f ms (routing kernels %.1f ms), download %.1f ms\n",
+                        twForest - tw0, twReplay - twForest, twSweep - twReplay, (double)out->kernel_ms, wall() - twSweep);
   } catch (CudaFail f) {
     rfslam_b200_free_predict(out);
     return f.code;
   }
+  if (timing) fprintf(stderr, "[rfslam_b200_predict] call %.1f ms (incl. releasing device buffers)\n", wall() - tw0);
   return RFSLAM_OK;
 }
 
