@@ -433,23 +433,32 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
       }
       if (const char* e = getenv("RFSLAM_CTA_THREADS")) {
         const int v = atoi(e);
-        if (!g.has_sort) pl.kv = v == 512 ? grow_variant_t512() : v == 320 ? grow_variant_t320() : grow_variant_t256();
+        if (!g.has_sort) pl.kv = v == 512 ? grow_variant_t512() : v == 320 ? grow_variant_t320() : v == 128 ? grow_variant_t128() : grow_variant_t256();
       }
-      const int ctasWanted = pl.kv->threads == 512 ? 1 : 2;
+      const int ctasWanted = pl.kv->ctasPerSm;
+      // shared memory available to one CTA's dynamic part (227 KB per SM, 1 KB reserved per CTA, GrowShared is static)
+      const size_t limit = (size_t)(227u << 10) / (size_t)ctasWanted - 1024 - sizeof(GrowShared);
       pl.g.hslots = hist_slots(g.hbins);
+      pl.g.tabSlots = kTabSlots;
+      if (const char* e = getenv("RFSLAM_TAB_SLOTS")) pl.g.tabSlots = std::max(1, std::min(kTabSlots, atoi(e)));
+      if (const char* e = getenv("RFSLAM_HIST_SLOTS")) pl.g.hslots = std::max(1, std::min(pl.g.hslots, atoi(e)));
+      while (grow_smem_bytes(g.ncmax, ds->K, g.hbins, pl.g.hslots, pl.g.tabSlots, 0, tilePitch) > limit && (pl.g.hslots > 1 || pl.g.tabSlots > 1)) {
+        if (pl.g.hslots * 2 > pl.g.tabSlots) pl.g.hslots >>= 1; else pl.g.tabSlots >>= 1;      // (histogram 32 B / bin, tables 16 B / bin)
+      }
       pl.g.subMax = 0;
       if (ds->dev.rowcodes && cfg.nsplit == 0 && !getenv("RFSLAM_NO_SUBTREE")) {
-        const size_t limit = ((ctasWanted == 1 ? 200u : 112u) << 10) - sizeof(GrowShared);     // dynamic part; GrowShared is static shared memory
         const int wantSub = getenv("RFSLAM_SUBTREE_MAX") ? atoi(getenv("RFSLAM_SUBTREE_MAX")) : kSmallMax;
         const int hsFull = pl.g.hslots, hsMin = std::min(2, hsFull);
         for (int sm = std::min(wantSub, kSmallMax); sm >= 128 && pl.g.subMax == 0; sm >>= 1)
           for (int hs = hsFull; hs >= hsMin; hs >>= 1)
-            if (grow_smem_bytes(g.ncmax, ds->K, g.hbins, hs, sm, tilePitch) <= limit) { pl.g.hslots = hs; pl.g.subMax = sm; break; }
+            if (grow_smem_bytes(g.ncmax, ds->K, g.hbins, hs, pl.g.tabSlots, sm, tilePitch) <= limit) { pl.g.hslots = hs; pl.g.subMax = sm; break; }
       }
-      pl.smem = grow_smem_bytes(g.ncmax, ds->K, g.hbins, pl.g.hslots, pl.g.subMax, tilePitch);
+      pl.smem = grow_smem_bytes(g.ncmax, ds->K, g.hbins, pl.g.hslots, pl.g.tabSlots, pl.g.subMax, tilePitch);
       int perSm = 0;
       RF_CUDA(pl.kv->prepare(pl.smem, &perSm));
       pl.residentCtas = std::max(1, perSm) * sms;
+      if (getenv("RFSLAM_TIMING")) fprintf(stderr, "[rfslam_b200_grow] plan for %d trees: %d threads/CTA, %d CTAs/SM resident, %zu B dynamic smem, hist slots %d, table slots %d, subtree tile %d\n",
+                                          trees, pl.kv->threads, perSm, pl.smem, pl.g.hslots, pl.g.tabSlots, pl.g.subMax);
       return pl;
     };
 
@@ -870,8 +879,8 @@ int score_node_impl(int rule, double k_for_alpha, int m, const double* x, const 
     g.rule = rule; g.mtry = 1; g.nodesize = 1; g.nodedepth = -1; g.alpha = 1.0 / (k_for_alpha * k_for_alpha);
     g.pw = 1; g.ncmax = 1; g.has_sort = ds->max_D > kHistBins; g.hbins = ds->hist_bins;
     { int ex = 0; frexp(std::max((double)m * std::max(ds->max_rt, 1e-300), 1.0), &ex); g.tscale = ldexp(1.0, 62 - ex); g.tinv = ldexp(1.0, ex - 62); }
-    g.hslots = hist_slots(g.hbins); g.subMax = 0;
-    const size_t smem = grow_smem_bytes(g.ncmax, ds->K, g.hbins, g.hslots, 0, 0);
+    g.hslots = hist_slots(g.hbins); g.tabSlots = kTabSlots; g.subMax = 0;
+    const size_t smem = grow_smem_bytes(g.ncmax, ds->K, g.hbins, g.hslots, g.tabSlots, 0, 0);
     RF_CUDA(cudaFuncSetAttribute(rfslam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DevBuf<uint32_t> d_lists, d_sort, d_stackPerm, d_ctab, d_nodeCount, d_leafCount, d_cursor;
     DevBuf<uint16_t> d_cnt; DevBuf<NodeEnt> d_stack; DevBuf<int> d_seedB, d_boot, d_status, d_sinkCount;

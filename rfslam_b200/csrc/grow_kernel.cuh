@@ -79,6 +79,7 @@ struct GrowParams {
   double tscale, tinv;           // 2^S and 2^-S of the fixed-point exposure accumulators (see hist_add)
   int nsplit;                    // > 0: at most nsplit randomly drawn cuts per covariate (rf.c:14533-14564)
   int hslots;                    // stratum slots per candidate histogram (GrowSmem::hs), chosen by the host to fit shared memory
+  int tabSlots;                  // strata per group of the small-node path (<= RF_MAX_SLOTS): sizes the term tables (GrowSmem::ts)
   int subMax;                    // > 0: a node of at most this many entries stages ITS WHOLE ROWS in shared memory and the subtree
                                  //      below it is grown out of that tile (see stage_subtree); 0 = off
 };
@@ -159,6 +160,17 @@ struct GrowShared {
     }                                                                                  \
   } while (0)
 
+// the same inside a candidate's warp (small_candidate): thread 0 of the CTA stamps the sub-phases of ITS candidate
+#define RF_PROFC(slot)                                                                 \
+  do {                                                                                 \
+    if (c.w.prof && vtid() == 0) {                                                     \
+      long long now__ = clock64();                                                     \
+      s->prof[slot] += (unsigned long long)(now__ - s->tmark);                         \
+      if (s->cur.len < 64u) s->prof[64 + (slot)] += (unsigned long long)(now__ - s->tmark); \
+      s->tmark = now__;                                                                \
+    }                                                                                  \
+  } while (0)
+
 __device__ __forceinline__ Rec* rec_ptr(const GrowWork& w, int tree, uint32_t q) {
   uint32_t c = w.ctab[(size_t)tree * w.maxChunksPerTree + q / kRecChunk];
   return w.pool + (size_t)c * kRecChunk + (q % kRecChunk);
@@ -200,6 +212,7 @@ struct GrowSmem {
   GrowShared* s;
   int hb;                            // bins per candidate histogram: pow2 >= the widest byte-coded column, 32..256
   int hs;                            // stratum slots per candidate histogram (large nodes accumulate hs strata per pass)
+  int ts;                            // table slots per candidate of the small-node path (strata per group)
 };
 
 #ifndef RF_MAX_SLOTS
@@ -211,18 +224,18 @@ struct GrowSmem {
 constexpr int kTabSlots = RF_MAX_SLOTS;    // strata per group of the small-node path (independent of the large-node passes' hs)
 __host__ __device__ inline int hist_slots(int hb) { int g = 256 / hb; return g < 1 ? 1 : (g > RF_MAX_SLOTS ? RF_MAX_SLOTS : g); }
 
-__host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K, int hb, int hslots, int subMax, int tilePitch) {
+__host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K, int hb, int hslots, int tabSlots, int subMax, int tilePitch) {
   const size_t hs = (size_t)hslots;
   size_t KS = (size_t)K + 2;
   size_t b = 0;
   b += (size_t)ncmax * hb * 8 * 2;             // sL sR
   {                                            // hT hW hN hE hNx hEx = one region, at least the small nodes' two term tables
-    const size_t hist = (size_t)ncmax * hb * hs * 32, tabs = (size_t)ncmax * hb * kTabSlots * 16;
+    const size_t hist = (size_t)ncmax * hb * hs * 32, tabs = (size_t)ncmax * hb * tabSlots * 16;
     b += hist > tabs ? hist : tabs;
   }
   b += (size_t)ncmax * 8;                      // statP
   b += (size_t)ncmax * 8 * 4;                  // pres
-  b += (size_t)ncmax * kTabSlots * 8 * 4;      // smk
+  b += (size_t)ncmax * tabSlots * 8 * 4;       // smk
   b += KS * 8 * 6;                             // PT PW cT cW cTL cTR
   b += KS * 4 * 5;                             // segpos PN PE cN cE
   b += (size_t)kSmallMax * (16 + 4 + (size_t)ncmax) + 32;  // small-node staging (>= the 8.5 KB of sorted-walk tiles aliased onto it)
@@ -232,10 +245,11 @@ __host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K, int hb, int 
   return b + 16;                               // (GrowShared is a static __shared__ object of the kernel, not part of this)
 }
 
-__device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb, int hslots, int subMax, int tilePitch) {
+__device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb, int hslots, int tabSlots, int subMax, int tilePitch) {
   GrowSmem m;
   m.hb = hb;
   m.hs = hslots;
+  m.ts = tabSlots;
   m.subMax = subMax; m.tilePitch = tilePitch;
   const size_t hsz = (size_t)ncmax * hb * m.hs;
   size_t KS = (size_t)K + 2;
@@ -247,15 +261,15 @@ __device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb, i
   {                                            // the u32 histograms follow at once: [hT hW hN hE hNx hEx] is one region of hsz * 32 bytes
     uint32_t* uh = (uint32_t*)d;
     m.hN = uh; uh += hsz; m.hE = uh; uh += hsz; m.hNx = uh; uh += hsz; m.hEx = uh; uh += hsz;
-    const size_t hist = hsz * 32, tabs = (size_t)ncmax * hb * kTabSlots * 16;
-    m.tabL = m.hT; m.tabR = m.hT + (size_t)ncmax * hb * kTabSlots;
+    const size_t hist = hsz * 32, tabs = (size_t)ncmax * hb * tabSlots * 16;
+    m.tabL = m.hT; m.tabR = m.hT + (size_t)ncmax * hb * tabSlots;
     d = (double*)((unsigned char*)m.hT + (hist > tabs ? hist : tabs));
   }
   m.statP = d; d += ncmax;
   m.PT = d; d += KS; m.PW = d; d += KS; m.cT = d; d += KS; m.cW = d; d += KS; m.cTL = d; d += KS; m.cTR = d; d += KS;
   uint32_t* u = (uint32_t*)d;
   m.pres = u; u += (size_t)ncmax * 8;
-  m.smk = u; u += (size_t)ncmax * kTabSlots * 8;
+  m.smk = u; u += (size_t)ncmax * tabSlots * 8;
   m.segpos = u; u += KS; m.PN = u; u += KS; m.PE = u; u += KS; m.cN = u; u += KS; m.cE = u; u += KS;
   {
     uintptr_t al = ((uintptr_t)u + 7) & ~(uintptr_t)7;
@@ -926,10 +940,10 @@ __device__ inline void small_candidate(const NodeCtx& c, int ci, uint32_t len) {
   const SmallRec* __restrict__ rec = m.smRec;
   const uint8_t* __restrict__ cptr = m.smCodes + ci * kSmallMax;
   const int nw = (c.Kloop + 31) >> 5;
-  const int G = kTabSlots;                                         // table slots = strata per group
-  double* tabL = m.tabL + (size_t)ci * kTabSlots * m.hb;
-  double* tabR = m.tabR + (size_t)ci * kTabSlots * m.hb;
-  uint32_t* mk = m.smk + (size_t)ci * kTabSlots * 8;               // [slot][8] codes that have rows in the slot's stratum
+  const int G = m.ts;                                              // table slots = strata per group
+  double* tabL = m.tabL + (size_t)ci * G * m.hb;
+  double* tabR = m.tabR + (size_t)ci * G * m.hb;
+  uint32_t* mk = m.smk + (size_t)ci * G * 8;               // [slot][8] codes that have rows in the slot's stratum
   if (lane < 8) m.pres[ci * 8 + lane] = 0u;
   for (int b = lane; b < Dc; b += 32) { m.sL[ci * m.hb + b] = 0.0; m.sR[ci * m.hb + b] = 0.0; }
   __syncwarp();
@@ -943,6 +957,7 @@ __device__ inline void small_candidate(const NodeCtx& c, int ci, uint32_t len) {
     plo = __reduce_or_sync(0xffffffffu, plo); phi = __reduce_or_sync(0xffffffffu, phi);
     if (lane == 0) { m.pres[ci * 8 + (base >> 5)] = plo; if (Dc > base + 32) m.pres[ci * 8 + (base >> 5) + 1] = phi; }
   }
+  RF_PROFC(5);
   double statP = 0.0;
   int w8 = 0; uint32_t word = s->evMask[0];
   uint32_t bigR0 = 0u, bigR1 = 0u;                                 // a long stratum met while collecting a group: handled after it
@@ -1008,6 +1023,7 @@ __device__ inline void small_candidate(const NodeCtx& c, int ci, uint32_t len) {
       }
     }
     __syncwarp();
+    RF_PROFC(7);
 #pragma unroll 1
     for (int wq = 0; wq < nwords; wq++) {                          // lane = cut: add this group's strata in ascending order
       const int q = (wq << 5) + lane;
@@ -1032,6 +1048,7 @@ __device__ inline void small_candidate(const NodeCtx& c, int ci, uint32_t len) {
 #pragma unroll
     for (int q = 0; q < RF_MAX_SLOTS; q++) if (q < ng) statP += tP[q];
     __syncwarp();
+    RF_PROFC(15);
     }
     if (bigR1 != 0u) {
       statP += stream_stratum(c, ci, Dc, bigR0, bigR1);
@@ -1425,6 +1442,34 @@ __device__ inline bool append_record(const GrowWork& w, GrowShared* s, int tree,
   return true;
 }
 
+
+// A node the DFS will not try to split (node gate rf.c:15354-15371 + purity rf.c:6391-6416, see the kernel's loop): its
+// record is all there is to it, so it is written as soon as the node is met -- by the split that creates it or by the
+// pop that reaches it -- and never becomes an iteration of the CTA's node loop (half of all nodes are such leaves).
+__device__ __forceinline__ bool node_is_leaf(const GrowParams& g, const NodeEnt& e) {
+  const bool attempt = (e.m >= 2u * (uint32_t)g.nodesize) && (g.nodedepth < 0 || e.depth < (uint32_t)g.nodedepth);
+  return !(attempt && e.E > 0u && e.E < e.m);
+}
+
+// lane 0 of warp 0: pop pending right children until one needs an attempt (it becomes s->cur; returns true: the caller
+// restores its permissible mask from stackPerm[s->sp]) or the stack is empty (s->abort = 2, tree finished)
+__device__ inline bool pop_next(const GrowParams& g, const GrowWork& w, GrowShared* s, int tree) {
+  while (true) {
+    if (s->sp == 0) { s->abort = 2; return false; }
+    s->sp--;
+    const NodeEnt e = w.stack[(size_t)tree * kStackCap + s->sp];
+    if (s->inSub && s->sp < s->subSp) s->inSub = 0;                 // the DFS is back above the staged subtree's root
+    if (node_is_leaf(g, e)) {
+      uint32_t q;
+      append_record(w, s, tree, e.nodeID, 0u, e.E, e.m, nan(""), e.parentRec, &q);
+      if (s->abort) return false;
+      continue;
+    }
+    s->cur = e;
+    return true;
+  }
+}
+
 #ifndef RF_MIN_CTAS
 #define RF_MIN_CTAS 2
 #endif
@@ -1435,7 +1480,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, RF_MIN_CTAS)
 RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ GrowShared g_state;
-  GrowSmem m = carve(smem_raw, g.ncmax, d.K, g.hbins, g.hslots, g.subMax, (d.rowPitch + 15) & ~15);
+  GrowSmem m = carve(smem_raw, g.ncmax, d.K, g.hbins, g.hslots, g.tabSlots, g.subMax, (d.rowPitch + 15) & ~15);
   m.s = &g_state;
   GrowShared* s = &g_state;
 #ifdef RF_CHECK
@@ -1624,21 +1669,14 @@ RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
     const bool split = attempt && s->have;
     if (!split) {
       if (warp_id() == 0) {
+        int restore = 0;
         if (lane_id() == 0) {
           uint32_t q;
           append_record(w, s, tree, cur.nodeID, 0u, cur.E, cur.m, nan(""), cur.parentRec, &q);
-          if (!s->abort) {
-            if (s->sp == 0) {
-              s->abort = 2;                                 // finished
-            } else {
-              s->sp--;
-              s->cur = w.stack[(size_t)tree * kStackCap + s->sp];
-              if (s->inSub && s->sp < s->subSp) s->inSub = 0;       // the DFS is back above the staged subtree's root
-            }
-          }
+          if (!s->abort) restore = pop_next(g, w, s, tree) ? 1 : 0;
         }
-        __syncwarp();
-        if (!s->abort) {
+        restore = __shfl_sync(0xffffffffu, restore, 0);
+        if (restore) {
           const uint32_t* sp = w.stackPerm + ((size_t)tree * kStackCap + s->sp) * g.pw;
 #pragma unroll 1
           for (int k = lane_id(); k < g.pw; k += 32) s->perm[k] = sp[k];
@@ -1765,34 +1803,48 @@ RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
     }
     RF_PROF(9);
     if (warp_id() == 0) {
+      int act = 0;                                                   // 1: right child pushed (save the mask), 2: a pending node popped (restore its mask)
       if (lane_id() == 0) {
         uint32_t q;
         append_record(w, s, tree, cur.nodeID, (uint32_t)cov + 1u, localCut ? s->bestWide : bcode, kNone, s->bestDelta, cur.parentRec, &q);
         s->algoBytes += 16ull * (unsigned long long)cur.m;
         if (!s->abort) {
-          if (s->sp >= (uint32_t)kStackCap) { atomicExch(w.status, 2); s->abort = 1; }
-          else {
-            s->leafCount++;
-            NodeEnt r;
-            r.start = cur.start + nL; r.len = cur.len - nL;
-            r.m = cur.m - (uint32_t)(tneL >> 32); r.E = cur.E - (uint32_t)(tneL & 0xffffffffu);
-            r.rtsum = trtR; r.nodeID = s->leafCount; r.parentRec = q; r.depth = cur.depth + 1; r.buf = cur.buf ^ 1u;
-            w.stack[(size_t)tree * kStackCap + s->sp] = r;
-            NodeEnt l;
-            l.start = cur.start; l.len = nL; l.m = (uint32_t)(tneL >> 32); l.E = (uint32_t)(tneL & 0xffffffffu);
-            l.rtsum = trtL; l.nodeID = cur.nodeID; l.parentRec = kNone; l.depth = cur.depth + 1; l.buf = cur.buf ^ 1u;
-            s->cur = l;
+          s->leafCount++;
+          NodeEnt r;
+          r.start = cur.start + nL; r.len = cur.len - nL;
+          r.m = cur.m - (uint32_t)(tneL >> 32); r.E = cur.E - (uint32_t)(tneL & 0xffffffffu);
+          r.rtsum = trtR; r.nodeID = s->leafCount; r.parentRec = q; r.depth = cur.depth + 1; r.buf = cur.buf ^ 1u;
+          NodeEnt l;
+          l.start = cur.start; l.len = nL; l.m = (uint32_t)(tneL >> 32); l.E = (uint32_t)(tneL & 0xffffffffu);
+          l.rtsum = trtL; l.nodeID = cur.nodeID; l.parentRec = kNone; l.depth = cur.depth + 1; l.buf = cur.buf ^ 1u;
+          if (!node_is_leaf(g, l)) {                                 // descend left, the right child waits on the stack (a leaf among them is written by the pop)
+            if (s->sp >= (uint32_t)kStackCap) { atomicExch(w.status, 2); s->abort = 1; }
+            else { w.stack[(size_t)tree * kStackCap + s->sp] = r; s->cur = l; act = 1; }
+          } else {                                                   // the left child is a leaf: its record follows its parent's at once (pre-order)
+            uint32_t ql;
+            append_record(w, s, tree, l.nodeID, 0u, l.E, l.m, nan(""), kNone, &ql);
+            if (!s->abort) {
+              if (!node_is_leaf(g, r)) s->cur = r;                   // straight on to the right child: same permissible mask, nothing to push
+              else {
+                append_record(w, s, tree, r.nodeID, 0u, r.E, r.m, nan(""), r.parentRec, &ql);
+                if (!s->abort) act = pop_next(g, w, s, tree) ? 2 : 0;
+              }
+            }
           }
         }
       }
-      __syncwarp();
-      if (!s->abort) {
+      act = __shfl_sync(0xffffffffu, act, 0);
+      if (act == 1) {
         // children inherit the parent's (possibly updated) permissible mask (rf.c:10725-10727)
         uint32_t* sp = w.stackPerm + ((size_t)tree * kStackCap + s->sp) * g.pw;
 #pragma unroll 1
         for (int k = lane_id(); k < g.pw; k += 32) sp[k] = s->perm[k];
         __syncwarp();
         if (lane_id() == 0) s->sp++;
+      } else if (act == 2) {
+        const uint32_t* sp = w.stackPerm + ((size_t)tree * kStackCap + s->sp) * g.pw;
+#pragma unroll 1
+        for (int k = lane_id(); k < g.pw; k += 32) s->perm[k] = sp[k];
       }
     }
     RF_PROF(11);

@@ -8,9 +8,11 @@ namespace rfslam {
 struct DevData; struct GrowParams; struct GrowWork;
 struct GrowVariant {
   int threads;
+  int ctasPerSm;                                                          // resident CTAs per SM the build is compiled for (launch bounds)
   cudaError_t (*prepare)(size_t smem, int* ctasPerSm);                    // opt in to `smem` bytes of dynamic shared memory; resident CTAs per SM
   void (*launch)(const DevData& d, const GrowParams& g, const GrowWork& w, int grid, size_t smem);
 };
+const GrowVariant* grow_variant_t128();
 const GrowVariant* grow_variant_t256();
 const GrowVariant* grow_variant_t320();
 const GrowVariant* grow_variant_t512();
@@ -27,7 +29,7 @@ const GrowVariant* grow_variant_t512();
     kernel<<<grid, kThreads, smem>>>(d, g, w);                                                                    \
   }                                                                                                               \
   const GrowVariant* grow_variant_##tag() {                                                                       \
-    static const GrowVariant v = {kThreads, prepare_##tag, launch_##tag};                                         \
+    static const GrowVariant v = {kThreads, RF_MIN_CTAS, prepare_##tag, launch_##tag};                                         \
     return &v;                                                                                                    \
   }                                                                                                               \
   }
