@@ -63,7 +63,10 @@ struct NodeEnt {        // a pending node of the DFS
 };
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;
-constexpr int kSmallMax = 512;
+#ifndef RF_SMALL_MAX
+#define RF_SMALL_MAX 512
+#endif
+constexpr int kSmallMax = RF_SMALL_MAX;      // nodes with <= this many entries are scored entirely out of shared memory
 constexpr int kLocalMax = 256;      // small nodes up to this many entries also take covariates with > 256 distinct values (local ranks)      // nodes with <= this many entries are scored entirely out of shared memory
 constexpr int kSparseRatio = 12;    // a node with fewer than n / kSparseRatio entries reads the row-major mirror of the table
 constexpr int kProfSlots = 96;   // 64..79: the phase slots again, restricted to nodes with < 64 entries   // 0..15 phases, 16..47 node time by log2(len), 48..63 node count by log2(len)/2
@@ -156,6 +159,7 @@ struct GrowShared {
       long long now__ = clock64();                                                     \
       s->prof[slot] += (unsigned long long)(now__ - s->tmark);                         \
       if (s->cur.len < 64u) s->prof[64 + (slot)] += (unsigned long long)(now__ - s->tmark); \
+      else if (s->cur.len <= (uint32_t)kSmallMax) s->prof[80 + (slot)] += (unsigned long long)(now__ - s->tmark); \
       s->tmark = now__;                                                                \
     }                                                                                  \
   } while (0)
@@ -167,6 +171,7 @@ struct GrowShared {
       long long now__ = clock64();                                                     \
       s->prof[slot] += (unsigned long long)(now__ - s->tmark);                         \
       if (s->cur.len < 64u) s->prof[64 + (slot)] += (unsigned long long)(now__ - s->tmark); \
+      else if (s->cur.len <= (uint32_t)kSmallMax) s->prof[80 + (slot)] += (unsigned long long)(now__ - s->tmark); \
       s->tmark = now__;                                                                \
     }                                                                                  \
   } while (0)
@@ -1700,7 +1705,7 @@ RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
       // the node is staged in shared memory: thread t owns entries 2t and 2t+1, one block scan of a
       // packed (left entries | left rows << 16 | left events << 40) word gives sizes and positions
       constexpr int kEpt = (kSmallMax + kThreads - 1) / kThreads;   // staged entries per thread (consecutive)
-      static_assert(kEpt <= 4, "staged entries per thread");
+      static_assert(kEpt <= 8, "staged entries per thread");
       unsigned long long my = 0ull; bool lf[kEpt]; uint32_t en[kEpt];
       double rtL = 0.0, rtR = 0.0;
       const bool sub = s->inSub != 0;                            // staged subtree: the "list" is the slot order in shared memory

@@ -32,3 +32,14 @@ if k >= 80:
     print("phases for nodes with < 64 entries: total %.3e (%.1f%% of all)" % (tots, 100*tots/max(tot,1)))
     for i,nm in enumerate(names):
         if buf[64+i]: print(f"  {nm:14s} {buf[64+i]:.3e} {100*buf[64+i]/max(tots,1):5.1f}%")
+
+if k >= 96:
+    tots = sum(buf[80+i] for i in list(range(12))+[14,15])
+    print("phases for nodes with 64..512 entries: total %.3e (%.1f%% of all)" % (tots, 100*tots/max(tot,1)))
+    for i,nm in enumerate(names):
+        if buf[80+i]: print(f"  {nm:14s} {buf[80+i]:.3e} {100*buf[80+i]/max(tots,1):5.1f}%")
+    totl = tot - tots - sum(buf[64+i] for i in list(range(12))+[14,15])
+    print("phases for nodes with > 512 entries: total %.3e (%.1f%% of all)" % (totl, 100*totl/max(tot,1)))
+    for i,nm in enumerate(names):
+        v = buf[i] - buf[64+i] - buf[80+i]
+        if v: print(f"  {nm:14s} {v:.3e} {100*v/max(totl,1):5.1f}%")
