@@ -35,6 +35,9 @@ extern "C" {
 
 /* option bits the path understands; same values as the reference (rf.h:108-158) */
 #define RFSLAM_OPT_PERF        0x00000004u   /* optLow: performance of the OOB ensemble (rf.h:110) */
+#define RFSLAM_OPT_PERF_CALB   0x00000008u   /* optLow: perf.type "brier" (rf.h:111, R/utilities.R:267-269) */
+#define RFSLAM_OPT_PERF_GMN2   0x00004000u   /* optLow: perf.type "g.mean" (rf.h:122) */
+#define RFSLAM_OPT_CLAS_RFQ    0x00008000u   /* optLow: rfq = TRUE, quantile-classifier vote (rf.h:123, rf.c:1181-1197) */
 #define RFSLAM_OPT_BOOT_TYP1   0x00080000u   /* optLow  (by.user = TYP1|TYP2, rf.c:520) */
 #define RFSLAM_OPT_BOOT_TYP2   0x00100000u
 #define RFSLAM_OPTH_MEMB_USER  0x00000040u   /* optHigh: return nodeMembership / bootMembership */
@@ -145,7 +148,9 @@ typedef struct rfslam_forest_out {
   int64_t   kernel_launches;   /* kernels of this library launched by the call */
   int64_t   rmbr_stride;       /* row stride of rmbrMembership (= maxBootstrapSize, rf.c:18296) */
   /* perfClas (rf.c:25, rf.c:17454): [ntree][1 + 2] OOB misclassification rate of the forest and per class
-     (getClassificationIndex rf.c:1067, getConditionalClassificationIndex rf.c:1025).  Present when opt_low has
+     (getClassificationIndex rf.c:1067, getConditionalClassificationIndex rf.c:1025); with RFSLAM_OPT_PERF_CALB the
+     normalised Brier score and its per-class terms (getBrierScore rf.c:974), with RFSLAM_OPT_PERF_GMN2 the g-mean
+     index alone (getGMeanIndex rf.c:1096); RFSLAM_OPT_CLAS_RFQ switches the vote (getMaxVote rf.c:1175).  Present when opt_low has
      RFSLAM_OPT_PERF and the call finalizes the ensembles of the whole forest; only the last row is filled
      (perfBlock = ntree, rf.c:8155), the others hold NA_REAL as in the reference. */
   double   *perfClas;
@@ -355,6 +360,48 @@ int  rfslam_b200_last_profile(uint64_t *slots, int capacity);
 const char *rfslam_b200_last_error(void);
 const char *rfslam_b200_version(void);
 int  rfslam_b200_device_count(void);
+
+/* ---------------------------------------------------------------- CPIU construction ---------- */
+/* The step before the forest path: `cpiu.fc` / `event` of utilities/cpiu.R:361-668 and the Rcpp helpers of
+   utilities/cpiu.cpp:27-249, for all persons at once.  A person's follow-up is cut into ceil(t_outcome / (interval *
+   unit_norm)) counting-process information units; rows of person 0 come first. */
+#define RFSLAM_CPIU_INDICATOR   0   /* i.*  does an event fall in (t.start, t.end]?      assemble_indicator    cpiu.cpp:27-50   */
+#define RFSLAM_CPIU_COUNT_PREV  1   /* n.*  events in PREVIOUS intervals                   assemble_accumulator  cpiu.cpp:75-113 flag 1 */
+#define RFSLAM_CPIU_COUNT_CUR   2   /* ni.* events in THIS interval                        assemble_accumulator  flag 0 */
+#define RFSLAM_CPIU_ELAPSED     3   /* t.*  time since the last event                      assemble_time_elapsed cpiu.cpp:129-165 */
+#define RFSLAM_CPIU_CONTINUOUS  4   /* c.*  carried-forward measurement (k.to.persist)     assemble_continuous   cpiu.cpp:186-249 */
+
+typedef struct {
+  int32_t        persons;
+  const double  *t_outcome;          /* [persons] time of the outcome / end of follow-up, in unit_norm units (cpiu.R:476) */
+  const double  *t_death;            /* [persons] (cpiu.R:575) */
+  const int32_t *death;              /* [persons] death indicator */
+  double         interval;           /* interval length in years (default 0.5) */
+  double         unit_norm;          /* time units per year (default 365): interval.mod = interval * unit_norm (cpiu.R:472) */
+  int32_t        n_vars;             /* derived variables */
+  const int32_t *var_kind;           /* [n_vars] RFSLAM_CPIU_* */
+  const int32_t *var_width;          /* [n_vars] event / measurement slots per person (<= 64) */
+  const double *const *var_times;    /* [n_vars] -> [persons][width]; NaN = missing slot (never in an interval, cpiu.R:583-584) */
+  const double *const *var_values;   /* [n_vars] -> [persons][width] for CONTINUOUS (sorted by time first, cpiu.R:488-494), else NULL */
+  int32_t        k_to_persist;       /* intervals a measurement is carried forward; -1 = for ever (cpiu.cpp:214-216) */
+  int32_t        device;
+} rfslam_cpiu_args;
+
+typedef struct {
+  int64_t  rows;                     /* CPIUs = sum over persons of their intervals */
+  int32_t  n_vars;
+  int32_t *person;                   /* [rows] 0-based person */
+  int32_t *int_n;                    /* [rows] interval number 1.. = the stratifier of the Poisson rules (cpiu.R:567) */
+  double  *t_start, *t_end;          /* [rows] (cpiu.R:568-571) */
+  double  *rt;                       /* [rows] risk time in years (cpiu.R:572-574) */
+  int32_t *i_death;                  /* [rows] (cpiu.R:575-577) */
+  double  *vars;                     /* [n_vars][rows]; a value of -1 is NA_REAL (cpiu.R:642) */
+  double   kernel_ms;
+  int64_t  kernel_launches;
+} rfslam_cpiu_out;
+
+int  rfslam_b200_cpiu_build(const rfslam_cpiu_args *args, rfslam_cpiu_out *out);
+void rfslam_b200_free_cpiu(rfslam_cpiu_out *out);
 
 #ifdef __cplusplus
 }

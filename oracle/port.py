@@ -24,13 +24,14 @@ class OrcArgs(C.Structure):
     _fields_ = [(k, C.c_int) for k in ("n", "p", "ntree", "mtry", "nodesize", "nodedepth", "rule", "seed", "max_boot")] + [
         ("k_for_alpha", C.c_double),
         ("x", _pd), ("y", _pd), ("rt", _pd), ("strat", _pi), ("samp", _pi), ("boot_size", _pi),
-        ("split_weight", _pd), ("tree_seeds", _pi), ("nsplit", C.c_int)]
+        ("split_weight", _pd), ("tree_seeds", _pi), ("nsplit", C.c_int), ("xtype", C.c_char_p), ("xlevels", _pi)]
 
 
 class OrcOut(C.Structure):
     _fields_ = [("ntree", C.c_int), ("n", C.c_int),
                 ("total_nodes", C.c_long), ("total_leaves", C.c_long), ("candidates", C.c_long), ("rmbr_stride", C.c_long),
                 ("treeID", _pi), ("nodeID", _pi), ("parmID", _pi), ("contPT", _pd), ("splitStat", _pd),
+                ("mwcpSZ", _pi), ("mwcpPT", C.POINTER(C.c_uint)), ("mwcpCT", _pi), ("mwcp_total", C.c_long),
                 ("leafCount", _pi), ("seed", _pi), ("bootMembership", _pi), ("nodeMembership", _pi),
                 ("tnRCNT", _pi), ("tnACNT", _pi), ("tnCLAS", _pi), ("rmbr", _pi), ("ambr", _pi),
                 ("oobNum", _pd), ("allNum", _pd), ("oobDen", _pi), ("allDen", _pi), ("oobEns", _pd), ("allEns", _pd)]
@@ -56,7 +57,7 @@ def lib():
         L.orc_bootstrap.restype = None; L.orc_bootstrap.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _pi]
         L.orc_ran1_stream.restype = None; L.orc_ran1_stream.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.orc_predict.restype = None
-        L.orc_predict.argtypes = [C.c_int, C.c_int, C.c_long, _pi, _pi, _pi, _pd, _pi, _pi, _pi, _pd, C.c_int, _pd, _pi]
+        L.orc_predict.argtypes = [C.c_int, C.c_int, C.c_long, _pi, _pi, _pi, _pd, _pi, _pi, _pi, _pd, C.c_int, _pd, _pi, _pi, C.POINTER(C.c_uint)]
         _lib = L
     return _lib
 
@@ -72,9 +73,11 @@ def _arr(ptr, n, dtype):
 
 
 def grow(x, y, rt, strat, *, rule=4, ntree=4, mtry=None, nodesize=5, nodedepth=-1, seed=-12345,
-         k_for_alpha=2.0, samp=None, split_weight=None, tree_seeds=None, nsplit=0, sampsize=None) -> Dict[str, np.ndarray]:
+         k_for_alpha=2.0, samp=None, split_weight=None, tree_seeds=None, nsplit=0, sampsize=None,
+         xtype=None, xlevels=None, perf="misclass", rfq=False) -> Dict[str, np.ndarray]:
     L = lib()
     p, n = x.shape
+    perf_mode = {"misclass": 0, "brier": 1, "gmean": 2}[perf]
     x = np.ascontiguousarray(x, np.float64); y = np.ascontiguousarray(y, np.float64)
     rt = np.ascontiguousarray(rt, np.float64); strat = np.ascontiguousarray(strat, np.int32)
     if mtry is None:
@@ -96,13 +99,17 @@ def grow(x, y, rt, strat, *, rule=4, ntree=4, mtry=None, nodesize=5, nodedepth=-
         sw = np.ascontiguousarray(split_weight, np.float64); keep.append(sw); a.split_weight = _dp(sw)
     if tree_seeds is not None:
         ts = np.ascontiguousarray(tree_seeds, np.int32); keep.append(ts); a.tree_seeds = _ip(ts)
+    if xtype is not None:
+        xt = "".join(xtype).encode(); xl = np.ascontiguousarray(xlevels, np.int32); keep += [xt, xl]
+        a.xtype = xt; a.xlevels = _ip(xl)
     op = L.orc_grow(C.byref(a))
     o = op.contents
     tn, tl = o.total_nodes, o.total_leaves
     res = {
         "treeID": _arr(o.treeID, tn, np.int32), "nodeID": _arr(o.nodeID, tn, np.int32),
         "parmID": _arr(o.parmID, tn, np.int32), "contPT": _arr(o.contPT, tn, np.float64),
-        "splitStat": _arr(o.splitStat, tn, np.float64), "mwcpSZ": np.zeros(tn, np.int32),
+        "splitStat": _arr(o.splitStat, tn, np.float64), "mwcpSZ": _arr(o.mwcpSZ, tn, np.int32),
+        "mwcpPT": _arr(o.mwcpPT, o.mwcp_total, np.uint32).astype(np.int32), "mwcpCT": _arr(o.mwcpCT, ntree, np.int32),
         "leafCount": _arr(o.leafCount, ntree, np.int32), "seed": _arr(o.seed, ntree, np.int32),
         "bootMembership": _arr(o.bootMembership, ntree * n, np.int32),
         "nodeMembership": _arr(o.nodeMembership, ntree * n, np.int32),
@@ -118,9 +125,9 @@ def grow(x, y, rt, strat, *, rule=4, ntree=4, mtry=None, nodesize=5, nodedepth=-
     perf = np.full(ntree * 3, na, np.float64)
     last = np.zeros(3, np.float64)
     oob_den = _arr(o.oobDen, n, np.int32)
-    L.orc_perf_clas.restype = None
-    L.orc_perf_clas.argtypes = [C.c_int, _pd, _pd, _pi, C.c_double, _pd]
-    L.orc_perf_clas(n, _dp(y), _dp(res["oobEnsbCLS"]), _ip(oob_den), C.c_double(na), _dp(last))
+    L.orc_perf_clas2.restype = None
+    L.orc_perf_clas2.argtypes = [C.c_int, _pd, _pd, _pi, C.c_double, C.c_int, C.c_int, _pd]
+    L.orc_perf_clas2(n, _dp(y), _dp(res["oobEnsbCLS"]), _ip(oob_den), C.c_double(na), perf_mode, int(bool(rfq)), _dp(last))
     perf[-3:] = last
     res["perfClas"] = perf
     L.orc_free(op)
@@ -168,5 +175,9 @@ def predict(forest: Dict[str, np.ndarray], fx: np.ndarray):
     lc = np.ascontiguousarray(forest["leafCount"], np.int32); rc = np.ascontiguousarray(forest["tnRCNT"], np.int32)
     te = np.ascontiguousarray(forest["tnCLAS"].reshape(-1, 2)[:, 1], np.int32)
     ens = np.zeros(2 * m, np.float64); mem = np.zeros(ntree * m, np.int32)
-    L.orc_predict(ntree, p, tid.size, _ip(tid), _ip(nid), _ip(pid), _dp(cpt), _ip(lc), _ip(rc), _ip(te), _dp(fx), m, _dp(ens), _ip(mem))
+    msz = np.ascontiguousarray(forest.get("mwcpSZ", np.zeros(tid.size, np.int32)), np.int32)
+    mpt = np.ascontiguousarray(forest.get("mwcpPT", np.zeros(0, np.int32)), np.int32).view(np.uint32)
+    if mpt.size == 0: mpt = np.zeros(1, np.uint32)
+    L.orc_predict(ntree, p, tid.size, _ip(tid), _ip(nid), _ip(pid), _dp(cpt), _ip(lc), _ip(rc), _ip(te), _dp(fx), m, _dp(ens), _ip(mem),
+                  _ip(msz), mpt.ctypes.data_as(C.POINTER(C.c_uint)))
     return ens, mem

@@ -135,7 +135,8 @@ def grow(x: np.ndarray, y: np.ndarray, risk_time: np.ndarray, stratifier: np.nda
          nsplit: int = 0, split_weight: Optional[np.ndarray] = None,
          xtype: Optional[Sequence[str]] = None, xlevels: Optional[np.ndarray] = None,
          var_categories: Optional[np.ndarray] = None, category_weights: Optional[np.ndarray] = None,
-         statistics: bool = False, sampsize: Optional[int] = None, impl: str = "ref", quants: bool = False) -> Dict[str, np.ndarray]:
+         statistics: bool = False, sampsize: Optional[int] = None, impl: str = "ref", quants: bool = False,
+         perf: str = "misclass", rfq: bool = False) -> Dict[str, np.ndarray]:
     """Run the reference's rfsrcGrow.  ``x`` is [p, n] float64 (p contiguous columns of n), ``y``
     the response codes in {1.0, 2.0}.  ``samp`` ([ntree, n] int32 in-bag counts) selects
     bootstrap="by.user" (R/utilities.R:43-45 -> bits 2^19+2^20).  ``statistics`` sets OPT_NODE_STAT
@@ -156,6 +157,10 @@ def grow(x: np.ndarray, y: np.ndarray, risk_time: np.ndarray, stratifier: np.nda
         opt_high += (1 << 18)                  # terminal.quants outgoing: tnCLAS (R/utilities.R:462-483)
     if membership:
         opt_high += (1 << 6)
+    # perf.type (R/utilities.R:254-272): "brier" -> OPT_PERF_CALB 2^3, "g.mean" -> OPT_PERF_GMN2 2^14; rfq -> OPT_CLAS_RFQ 2^15
+    opt_low += {"misclass": 0, "brier": 1 << 3, "gmean": 1 << 14}[perf]
+    if rfq:
+        opt_low += (1 << 15)
     if statistics:
         assert nthreads == 1, "spltST is only in tree order with one thread"
         opt_low += 0x08000000
@@ -236,6 +241,10 @@ def trim_forest(res: Dict[str, np.ndarray], n: int) -> Dict[str, np.ndarray]:
             full = res[k]
             parts = [full[b * stride: b * stride + leaf[b]] for b in range(ntree)]
             out[k] = np.concatenate(parts) if parts else full[:0]
+    if "mwcpPT" in res and "mwcpCT" in res:
+        # mwcpPT is allocated at its theoretical maximum; the words in use are the first sum(mwcpCT), written in the order
+        # trees were saved (thread-completion order, like the records)
+        out["mwcpPT"] = res["mwcpPT"][: int(res["mwcpCT"].sum())]
     if "tnCLAS" in res and res["tnCLAS"].size:
         full = res["tnCLAS"]
         parts = [full[b * stride * 2: b * stride * 2 + 2 * leaf[b]] for b in range(ntree)]
@@ -256,7 +265,8 @@ def per_tree(res: Dict[str, np.ndarray]) -> Dict[int, Dict[str, np.ndarray]]:
 
 def predict(x: np.ndarray, y: np.ndarray, forest: Dict[str, np.ndarray], fx: Optional[np.ndarray], *,
             k_for_alpha: float = 2.0, membership: bool = True, samp: Optional[np.ndarray] = None,
-            nodesize: int = 5, impl: str = "ref", quants: bool = False) -> Dict[str, np.ndarray]:
+            nodesize: int = 5, impl: str = "ref", quants: bool = False,
+            xtype: Optional[Sequence[str]] = None, xlevels: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
     """Run the reference's rfsrcPredict on a (trimmed) grow output.  ``fx`` [p, m_test] selects
     RF_PRED; ``fx=None`` is restore mode (RF_REST) (randomForestSRC.c:22361)."""
     L = lib(impl)
@@ -281,7 +291,13 @@ def predict(x: np.ndarray, y: np.ndarray, forest: Dict[str, np.ndarray], fx: Opt
         max_boot = n
         samp_arg = P.i(np.zeros(0, np.int32))
     total = forest["treeID"].size
-    hc_zero = P.lst([P.i(forest["parmID"]), P.d(forest["contPT"]), P.i(forest["mwcpSZ"]), P.nil()])
+    has_mwcp = "mwcpPT" in forest and np.asarray(forest["mwcpPT"]).size > 0
+    hc_zero = P.lst([P.i(forest["parmID"]), P.d(forest["contPT"]), P.i(forest["mwcpSZ"]),
+                     P.i(np.asarray(forest["mwcpPT"], np.int32)) if has_mwcp else P.nil()])
+    if xtype is None:
+        xtype = ["R"] * p
+    if xlevels is None:
+        xlevels = np.zeros(p, np.int32)
     partial = P.lst([P.i(0), P.i(0), P.i(0), P.nil(), P.i(0), P.nil(), P.nil()])
     if fx is not None:
         fx = np.ascontiguousarray(fx, dtype=np.float64)
@@ -294,7 +310,7 @@ def predict(x: np.ndarray, y: np.ndarray, forest: Dict[str, np.ndarray], fx: Opt
     z_d = lambda: P.d(np.zeros(0))
     args = [
         P.i(0), P.i(-1), P.i(opt_low), P.i(opt_high), P.i(ntree), P.i(n), P.i(1), P.s(["C"]), P.i(2),
-        P.d(np.asarray(y, np.float64)), P.i(p), P.s(["R"] * p), P.i(np.zeros(p, np.int32)),
+        P.d(np.asarray(y, np.float64)), P.i(p), P.s(list(xtype)), P.i(np.asarray(xlevels, np.int32)),
         P.d_alias(x.reshape(-1)),
         P.d(k_for_alpha), P.i(max_boot), P.i(boot_sizes), samp_arg, P.d(np.ones(n)),
         P.i(0), z_d(), P.i(total), P.i(forest["seed"]), P.i(0),

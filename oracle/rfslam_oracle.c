@@ -16,7 +16,11 @@
  *   bootstrap .............. rf.c:492-627 (by.root SWR rf.c:529-533, by.user rf.c:520-526)
  *   node gate / purity ..... rf.c:15342-15457, rf.c:6370-6426, rf.c:13235-13270
  *   covariate draws ........ rf.c:14793-15150, rf.c:8362-8386, rf.c:8305-8308, rf.c:8206-8214
- *   cut enumeration ........ rf.c:14433-14568 (nsplit = 0), rf.c:15165-15216 (LEFT iff cut - x >= 0)
+ *   cut enumeration ........ rf.c:14433-14568, rf.c:15165-15216 (LEFT iff cut - x >= 0)
+ *   factor (MWCP) cuts ..... rf.c:14452-14518 (deterministic / random), rf.c:1416-1559 (makeFactor, bookPair: the
+ *                            complementary pairs by left-side cardinality, lexicographic inside a cardinality, the
+ *                            middle cardinality of an even level count halved), rf.c:15232-15330 (getRandomPair,
+ *                            createRandomBinaryPair, convertRelToAbsBinaryPair), rf.c:1607-1616 (splitOnFactor)
  *   split statistics ....... sc.c:639-1687 (poissonSplit1..6), called from rf.c:13404-13529
  *   best-split tracker ..... rf.c:15471-15551 (EPSILON = 1e-9 absolute, rf.h:169)
  *   fork / node ids ........ rf.c:10568-10734, rf.c:21620-21691
@@ -168,7 +172,7 @@ typedef struct {
   int leafCount;
   int Kmax;
   /* growing per-tree outputs */
-  int *nodeID, *parmID; double *contPT, *stat; long nnodes, cap;
+  int *nodeID, *parmID; double *contPT, *stat; unsigned *mwcp; long nnodes, cap;   /* mwcp[k] != 0: factor split, the LEFT level mask */
   int *nodeMembership;         /* [n] leaf id of every row */
   int *tnRCNT, *tnACNT, *tnE;  /* indexed by leaf id (1-based), capacity n+1 */
   int *rmbr, *ambr; long rmbrIter, ambrIter;
@@ -177,14 +181,16 @@ typedef struct {
   double *xs; int *ord; suff_t *L, *R, *P; double *statL, *statR; double *gval; int *gend;
 } tree_ctx;
 
-static void push_node(tree_ctx *c, int nodeID, int parm, double cut, double stat) {
+static void push_node(tree_ctx *c, int nodeID, int parm, double cut, double stat, unsigned mwcp) {
   if (c->nnodes == c->cap) {
     c->cap = c->cap ? 2 * c->cap : 1024;
     c->nodeID = realloc(c->nodeID, c->cap * sizeof(int));
     c->parmID = realloc(c->parmID, c->cap * sizeof(int));
     c->contPT = realloc(c->contPT, c->cap * sizeof(double));
     c->stat   = realloc(c->stat,   c->cap * sizeof(double));
+    c->mwcp   = realloc(c->mwcp,   c->cap * sizeof(unsigned));
   }
+  c->mwcp[c->nnodes] = mwcp;
   c->nodeID[c->nnodes] = nodeID; c->parmID[c->nnodes] = parm; c->contPT[c->nnodes] = cut; c->stat[c->nnodes] = stat;
   c->nnodes++;
 }
@@ -201,8 +207,11 @@ static int cmp_ord(const void *pa, const void *pb) {
 /* Score every cut of covariate `cov` in a node whose in-bag rows are rep[0..m); feed each delta
    (already multiplied by the split weight) to the sequential tracker of rf.c:15471-15551.
    Returns the number of distinct values. */
+static int score_factor(tree_ctx *c, int cov, const int *rep, int m, int D,
+                        int *have_best, double *best_delta, int *best_cov, double *best_cut, unsigned *best_mask);
+
 static int score_covariate(tree_ctx *c, int cov, const int *rep, int m,
-                           int *have_best, double *best_delta, int *best_cov, double *best_cut) {
+                           int *have_best, double *best_delta, int *best_cov, double *best_cut, unsigned *best_mask) {
   const orc_args *a = c->a;
   const double *col = a->x + (size_t) cov * a->n;
   const int rule = a->rule;
@@ -217,6 +226,7 @@ static int score_covariate(tree_ctx *c, int cov, const int *rep, int m,
     c->gend[D - 1] = i + 1;
   }
   if (D < 2) return D;
+  if (a->xtype && a->xtype[cov] == 'C') return score_factor(c, cov, rep, m, D, have_best, best_delta, best_cov, best_cut, best_mask);
   /* nsplit > 0 (stackAndConstructSplitVector, randomForestSRC.c:14533-14564): with more than nsplit distinct values,
      nsplit of the D - 1 cut positions are drawn from chain B without replacement (swap-remove over 1..D-1,
      slot = ceil(ran1B * size)) and evaluated in ascending order; otherwise every position is a cut */
@@ -272,15 +282,122 @@ static int score_covariate(tree_ctx *c, int cov, const int *rep, int m,
     int flag;
     if (!*have_best) flag = 1;
     else flag = (delta - *best_delta) > 1.0e-9;
-    if (flag) { *have_best = 1; *best_delta = delta; *best_cov = cov; *best_cut = c->gval[g]; }
+    if (flag) { *have_best = 1; *best_delta = delta; *best_cov = cov; *best_cut = c->gval[g]; *best_mask = 0u; }
   }
   free(sel);
   return D;
 }
 
+/* n choose k exactly (rf.c:1531-1560 computes the same integers with fraction reduction) */
+static double choose_d(int n, int k) {
+  double t = 1.0;
+  if (k > n - k) k = n - k;
+  for (int i = 1; i <= k; i++) t = t * (double) (n - k + i) / (double) i;
+  return floor(t + 0.5);
+}
+
+/* the next combination of g of the r relative levels 1..r in lexicographic order; lv[0..g) ascending */
+static int next_combination(int *lv, int g, int r) {
+  int i = g - 1;
+  while (i >= 0 && lv[i] == r - (g - 1 - i)) i--;
+  if (i < 0) return 0;
+  lv[i]++;
+  for (int j = i + 1; j < g; j++) lv[j] = lv[j - 1] + 1;
+  return 1;
+}
+
+/* Unordered factor: the r levels present in the node (c->gval[0..D), ascending) are split into a LEFT set and its
+   complement.  Deterministic mode (rf.c:14463-14478, rf.c:14502-14517): all 2^(r-1) - 1 complementary pairs when that
+   is fewer than the node's in-bag size, grouped by the cardinality of the LEFT set (1 .. floor(r/2)), lexicographic
+   inside a group, only the first half of the middle group when r is even (bookPair, rf.c:1498-1530).  Otherwise as
+   many RANDOM pairs as the node has in-bag members (rf.c:14479-14481, nsplit > 0: rf.c:14486-14498): a cardinality
+   drawn in proportion to the group sizes, then that many levels without replacement, all from chain B
+   (getRandomPair / createRandomBinaryPair, rf.c:15232-15302).  A cut's LEFT mask holds ABSOLUTE levels: bit
+   (level - 1) (convertRelToAbsBinaryPair rf.c:15303-15330; one 32-bit word: levels <= 32). */
+static int score_factor(tree_ctx *c, int cov, const int *rep, int m, int D,
+                        int *have_best, double *best_delta, int *best_cov, double *best_cut, unsigned *best_mask) {
+  const orc_args *a = c->a;
+  const double *col = a->x + (size_t) cov * a->n;
+  const int rule = a->rule, r = D;
+  const double pairs = ldexp(1.0, r - 1) - 1.0;
+  int det, ncuts;
+  if (a->nsplit == 0) {
+    det = !(pairs >= (double) m);
+    ncuts = det ? (int) pairs : m;
+  } else {
+    int lim = a->nsplit <= m ? a->nsplit : m;
+    det = pairs <= (double) lim;
+    ncuts = det ? (int) pairs : lim;
+  }
+  unsigned *masks = malloc((size_t) ncuts * sizeof(unsigned));
+  int G = r / 2;
+  if (det) {
+    int j = 0, lv[32];
+    for (int g = 1; g <= G; g++) {
+      double gs = choose_d(r, g);
+      if (!(r & 1) && g == G) gs = gs / 2;
+      for (int i = 0; i < g; i++) lv[i] = i + 1;
+      for (long k = 0; k < (long) gs; k++) {
+        unsigned mk = 0;
+        for (int i = 0; i < g; i++) mk |= 1u << ((unsigned) c->gval[lv[i] - 1] - 1u);
+        masks[j++] = mk;
+        next_combination(lv, g, r);
+      }
+    }
+  } else {
+    double cdf[17];
+    for (int k = 1; k <= G; k++) { cdf[k] = choose_d(r, k); if (!(r & 1) && k == G) cdf[k] = floor(cdf[k] / 2); }
+    for (int k = 2; k <= G; k++) cdf[k] += cdf[k - 1];
+    for (int j = 0; j < ncuts; j++) {
+      double rv = ceil(orc_ran1(&c->chainB) * cdf[G]);
+      int g = 1; while (rv > cdf[g]) g++;
+      int lvv[33], size = r; unsigned mk = 0;
+      for (int k = 1; k <= r; k++) lvv[k] = k;
+      for (int k = 1; k <= g; k++) {
+        int slot = (int) ceil((double) orc_ran1(&c->chainB) * (size * 1.0));
+        int rel = lvv[slot];
+        lvv[slot] = lvv[size]; size--;
+        mk |= 1u << ((unsigned) c->gval[rel - 1] - 1u);
+      }
+      masks[j] = mk;
+    }
+  }
+  c->candidates += ncuts;
+
+  int K = 1;
+  if (rule_stratified(rule)) { K = 0; for (int i = 0; i < m; i++) if (a->strat[rep[i]] > K) K = a->strat[rep[i]]; }
+  double ysum = 0, rtsum = 0;
+  for (int i = 0; i < m; i++) { int rr = rep[c->ord[i]]; ysum += a->y[rr]; rtsum += a->rt[rr]; }
+  double alpha = 1 / (a->k_for_alpha * a->k_for_alpha);
+  double beta = alpha / (ysum / rtsum);
+  suff_t *L = c->L, *R = c->R, *P = c->P;
+  double w = a->split_weight ? a->split_weight[cov] : 1.0;
+  for (int j = 0; j < ncuts; j++) {
+    memset(L, 0, (K + 1) * sizeof(suff_t)); memset(R, 0, (K + 1) * sizeof(suff_t)); memset(P, 0, (K + 1) * sizeof(suff_t));
+    for (int i = 0; i < m; i++) {                       /* rows in covariate-sorted order, as the plugin sees them */
+      int rr = rep[c->ord[i]];
+      int left = (masks[j] >> ((unsigned) col[rr] - 1u)) & 1u;
+      suff_t *S = left ? L : R;
+      int j_ = rule_stratified(rule) ? a->strat[rr] : 1;
+      double t_ = rule_unit_time(rule) ? 1.0 : a->rt[rr];
+      double e_ = a->y[rr] - 1;
+      if (a->y[rr] == 2.0) { S[j_].E++; P[j_].E++; }
+      S[j_].N++; S[j_].T += t_; S[j_].W += e_ * t_;
+      P[j_].N++; P[j_].T += t_; P[j_].W += e_ * t_;
+    }
+    double delta = (side_stat(rule, K, L, alpha, beta) + side_stat(rule, K, R, alpha, beta) - side_stat(rule, K, P, alpha, beta)) * w;
+    int flag;
+    if (!*have_best) flag = 1;
+    else flag = (delta - *best_delta) > 1.0e-9;
+    if (flag) { *have_best = 1; *best_delta = delta; *best_cov = cov; *best_cut = NAN; *best_mask = masks[j]; }
+  }
+  free(masks);
+  return D;
+}
+
 static void grow_node(tree_ctx *c, int *rep, int m, int *all, int na, int depth, int nodeID, char *perm) {
   const orc_args *a = c->a;
-  int have_best = 0, best_cov = -1; double best_delta = 0, best_cut = 0;
+  int have_best = 0, best_cov = -1; double best_delta = 0, best_cut = 0; unsigned best_mask = 0u;
   int attempt = (m >= 2 * a->nodesize) && (a->nodedepth < 0 || depth < a->nodedepth);
   if (attempt) {
     /* purity: variance of the response codes over in-bag rows (rf.c:6391-6416) */
@@ -299,27 +416,29 @@ static void grow_node(tree_ctx *c, int *rep, int m, int *all, int na, int depth,
       int slot = (int) ceil((double) orc_ran1(&c->chainB) * (size * 1.0));
       int cov = pool[slot];
       pool[slot] = pool[size]; size--;
-      int D = score_covariate(c, cov, rep, m, &have_best, &best_delta, &best_cov, &best_cut);
+      int D = score_covariate(c, cov, rep, m, &have_best, &best_delta, &best_cov, &best_cut, &best_mask);
       if (D < 2) perm[cov] = 0;                                        /* rf.c:15004-15007 */
     }
     free(pool);
   }
   if (have_best) {
-    push_node(c, nodeID, best_cov + 1, best_cut, best_delta);
+    push_node(c, nodeID, best_cov + 1, best_cut, best_delta, best_mask);
     c->leafCount++;
     int leftID = nodeID, rightID = c->leafCount;
     const double *col = a->x + (size_t) best_cov * a->n;
     int *repL = malloc((size_t) m * sizeof(int)), *repR = malloc((size_t) m * sizeof(int)); int mL = 0, mR = 0;
-    for (int i = 0; i < m; i++) { if (best_cut - col[rep[i]] >= 0.0) repL[mL++] = rep[i]; else repR[mR++] = rep[i]; }
+#define GOES_LEFT(row) (best_mask ? (int) ((best_mask >> ((unsigned) col[row] - 1u)) & 1u) : (best_cut - col[row] >= 0.0))   /* rf.c:1607-1616 / rf.c:15194 */
+    for (int i = 0; i < m; i++) { if (GOES_LEFT(rep[i])) repL[mL++] = rep[i]; else repR[mR++] = rep[i]; }
     int *allL = malloc((size_t) na * sizeof(int)), *allR = malloc((size_t) na * sizeof(int)); int aL = 0, aR = 0;
-    for (int i = 0; i < na; i++) { if (best_cut - col[all[i]] >= 0.0) allL[aL++] = all[i]; else allR[aR++] = all[i]; }
+    for (int i = 0; i < na; i++) { if (GOES_LEFT(all[i])) allL[aL++] = all[i]; else allR[aR++] = all[i]; }
+#undef GOES_LEFT
     char *permL = malloc(a->p), *permR = malloc(a->p);
     memcpy(permL, perm, a->p); memcpy(permR, perm, a->p);
     grow_node(c, repL, mL, allL, aL, depth + 1, leftID, permL);
     grow_node(c, repR, mR, allR, aR, depth + 1, rightID, permR);
     free(repL); free(repR); free(allL); free(allR); free(permL); free(permR);
   } else {
-    push_node(c, nodeID, 0, NAN, NAN);
+    push_node(c, nodeID, 0, NAN, NAN, 0u);
     int E = 0; for (int i = 0; i < m; i++) if (a->y[rep[i]] == 2.0) E++;
     c->tnRCNT[nodeID] = m; c->tnACNT[nodeID] = na; c->tnE[nodeID] = E;
     for (int i = 0; i < na; i++) { c->nodeMembership[all[i]] = nodeID; c->ambr[c->ambrIter++] = all[i] + 1; }
@@ -332,6 +451,7 @@ orc_out *orc_grow(const orc_args *a) {
   orc_out *o = calloc(1, sizeof *o);
   o->ntree = ntree; o->n = n;
   o->leafCount = calloc(ntree, sizeof(int));
+  o->mwcpCT = calloc(ntree, sizeof(int));
   o->seed = calloc(ntree, sizeof(int));
   o->bootMembership = calloc((size_t) ntree * n, sizeof(int));
   o->nodeMembership = calloc((size_t) ntree * n, sizeof(int));
@@ -388,10 +508,13 @@ orc_out *orc_grow(const orc_args *a) {
       o->treeID = realloc(o->treeID, node_cap * sizeof(int)); o->nodeID = realloc(o->nodeID, node_cap * sizeof(int));
       o->parmID = realloc(o->parmID, node_cap * sizeof(int)); o->contPT = realloc(o->contPT, node_cap * sizeof(double));
       o->splitStat = realloc(o->splitStat, node_cap * sizeof(double));
+      o->mwcpSZ = realloc(o->mwcpSZ, node_cap * sizeof(int)); o->mwcpPT = realloc(o->mwcpPT, node_cap * sizeof(unsigned));
     }
     for (long k = 0; k < c.nnodes; k++) {
       long q = o->total_nodes + k;
       o->treeID[q] = b + 1; o->nodeID[q] = c.nodeID[k]; o->parmID[q] = c.parmID[k]; o->contPT[q] = c.contPT[k]; o->splitStat[q] = c.stat[k];
+      o->mwcpSZ[q] = c.mwcp[k] ? 1 : 0;                               /* one word: levels <= 32 (rf.c:10773-10779) */
+      if (c.mwcp[k]) { o->mwcpPT[o->mwcp_total++] = c.mwcp[k]; o->mwcpCT[b]++; }
     }
     o->total_nodes += c.nnodes;
     if (o->total_leaves + c.leafCount > leaf_cap) {
@@ -415,7 +538,7 @@ orc_out *orc_grow(const orc_args *a) {
     }
     free(rep); free(all); free(perm); free(c.tnRCNT); free(c.tnACNT); free(c.tnE);
     free(c.xs); free(c.ord); free(c.L); free(c.R); free(c.P); free(c.statL); free(c.statR); free(c.gval); free(c.gend);
-    free(c.nodeID); free(c.parmID); free(c.contPT); free(c.stat);
+    free(c.nodeID); free(c.parmID); free(c.contPT); free(c.stat); free(c.mwcp);
   }
   for (int i = 0; i < n; i++) {                     /* rf.c:8113-8125 */
     for (int k = 0; k < 2; k++) {
@@ -432,8 +555,11 @@ orc_out *orc_grow(const orc_args *a) {
    from tnCLAS-style arrays (per tree, indexed by leaf id). */
 void orc_predict(int ntree, int p, long total_nodes, const int *treeID, const int *nodeID, const int *parmID,
                  const double *contPT, const int *leafCount, const int *tnRCNT, const int *tnE,
-                 const double *fx, int m, double *ens /* [2][m] */, int *membership /* [ntree][m] */) {
+                 const double *fx, int m, double *ens /* [2][m] */, int *membership /* [ntree][m] */,
+                 const int *mwcpSZ /* [total_nodes] or NULL */, const unsigned *mwcpPT /* the words, in record order */) {
   (void) p;
+  long *mwoff = NULL;                                  /* word index of a factor split */
+  if (mwcpSZ) { mwoff = malloc(total_nodes * sizeof(long)); long at = 0; for (long q = 0; q < total_nodes; q++) { mwoff[q] = at; at += mwcpSZ[q]; } }
   long *child = malloc(total_nodes * sizeof(long));   /* right-child record index for internal nodes */
   /* pre-order: left child of record q is q+1; right child follows the whole left subtree */
   long *stack = malloc((total_nodes + 1) * sizeof(long)); long sp = 0;
@@ -455,7 +581,8 @@ void orc_predict(int ntree, int p, long total_nodes, const int *treeID, const in
       long q = root;
       while (parmID[q] != 0) {
         double xv = fx[(size_t) (parmID[q] - 1) * m + i];
-        q = (contPT[q] - xv >= 0.0) ? q + 1 : child[q];
+        if (mwcpSZ && mwcpSZ[q] > 0) q = ((mwcpPT[mwoff[q]] >> ((unsigned) xv - 1u)) & 1u) ? q + 1 : child[q];   /* rf.c:1607-1616 */
+        else q = (contPT[q] - xv >= 0.0) ? q + 1 : child[q];
       }
       int l = nodeID[q];
       if (membership) membership[(size_t) b * m + i] = l;
@@ -466,12 +593,13 @@ void orc_predict(int ntree, int p, long total_nodes, const int *treeID, const in
     leafoff += leafCount[b];
   }
   for (size_t i = 0; i < 2 * (size_t) m; i++) ens[i] /= (double) ntree;
-  free(child); free(stack);
+  free(child); free(stack); free(mwoff);
 }
 
 void orc_free(orc_out *o) {
   if (!o) return;
   free(o->treeID); free(o->nodeID); free(o->parmID); free(o->contPT); free(o->splitStat);
+  free(o->mwcpSZ); free(o->mwcpPT); free(o->mwcpCT);
   free(o->leafCount); free(o->seed); free(o->bootMembership); free(o->nodeMembership);
   free(o->tnRCNT); free(o->tnACNT); free(o->tnCLAS); free(o->rmbr); free(o->ambr);
   free(o->oobNum); free(o->allNum); free(o->oobDen); free(o->allDen); free(o->oobEns); free(o->allEns);
@@ -499,6 +627,61 @@ void orc_perf_clas(int n, const double *y, const double *ens, const int *den, do
   if (cum == 0) { out[0] = out[1] = out[2] = na; return; }
   out[0] = 1.0 - correct / (double) cum;
   for (int k = 1; k <= 2; k++) out[k] = count[k] ? 1.0 - cpv[k] / (double) count[k] : na;
+}
+
+/* The other performance types of the class family and the RFQ vote (getPerformance rf.c:7954-8010):
+   mode 0 = misclassification (as orc_perf_clas), 1 = Brier (getBrierScore rf.c:974-1024), 2 = g-mean (getGMeanIndex
+   rf.c:1096-1140; per-class slots stay NA); rfq != 0: vote = minority class iff its probability >= its prevalence
+   (getMaxVote rf.c:1181-1197, minority / majority / threshold rf.c:16859-16895). */
+void orc_perf_clas2(int n, const double *y, const double *ens, const int *den, double na, int mode, int rfq, double *out) {
+  unsigned count[3] = {0, 0, 0}, cum = 0;
+  for (int i = 0; i < n; i++) count[(unsigned) y[i]]++;
+  unsigned minority = 1, majority = 1;
+  for (unsigned k = 1; k <= 2; k++) if (count[k] < count[minority]) minority = k;
+  for (unsigned k = 1; k <= 2; k++) if (count[k] >= count[majority]) majority = k;
+  double threshold = (double) count[minority] / (double) n;
+  double *vote = malloc((size_t) n * sizeof(double));
+  for (int i = 0; i < n; i++) {
+    vote[i] = NAN;
+    if (den[i] == 0) continue;
+    cum++;
+    if (rfq) vote[i] = (ens[(size_t)(minority - 1) * n + i] >= threshold) ? (double) minority : (double) majority;
+    else {
+      double maxValue = 0.0, maxClass = 0.0;
+      for (int k = 1; k <= 2; k++)
+        if (maxValue <= ens[(size_t)(k - 1) * n + i]) { maxValue = ens[(size_t)(k - 1) * n + i]; maxClass = (double) k; }
+      vote[i] = maxClass;
+    }
+  }
+  out[0] = out[1] = out[2] = na;
+  if (cum == 0) { free(vote); return; }
+  if (mode == 1) {
+    double result = 0.0;
+    for (int against = 1; against <= 2; against++) {
+      double cpv = 0.0;
+      for (int i = 0; i < n; i++)
+        if (den[i] != 0) cpv += pow(((double) ((unsigned) y[i] == (unsigned) against) - ens[(size_t)(against - 1) * n + i]), 2.0);
+      cpv /= (double) cum;
+      out[against] = cpv; result += cpv;
+    }
+    out[0] = result * 2 / (2 - 1);
+  } else if (mode == 2) {
+    double tr[3] = {0, 0, 0}, fr[3] = {0, 0, 0}, result = 1.0;
+    for (int i = 0; i < n; i++)
+      if (den[i] > 0) { if (y[i] == vote[i]) tr[(unsigned) y[i]] += 1.0; else fr[(unsigned) y[i]] += 1.0; }
+    for (int k = 1; k <= 2; k++) {
+      double denom = tr[k] + fr[k];
+      if (denom > 0) result = result * tr[k] / denom; else result = result * (1 + tr[k]) / (1 + denom);
+    }
+    out[0] = 1.0 - sqrt(result);
+  } else {
+    double correct = 0.0, cpv[3] = {0.0, 0.0, 0.0};
+    for (int i = 0; i < n; i++)
+      if (den[i] != 0 && y[i] == vote[i]) { correct += 1.0; cpv[(unsigned) y[i]] += 1.0; }
+    out[0] = 1.0 - correct / (double) cum;
+    for (int k = 1; k <= 2; k++) out[k] = count[k] ? 1.0 - cpv[k] / (double) count[k] : na;
+  }
+  free(vote);
 }
 
 /* bootstrap-only entry (chain A replay) for the in-bag parity tests */

@@ -17,12 +17,15 @@ typedef struct {
   const double *split_weight; /* [p] or NULL */
   const int    *tree_seeds;   /* [ntree] chain-A seeds (restore) or NULL (grow) */
   int           nsplit;       /* 0 = every distinct value but the last is a cut; > 0: at most nsplit random cuts per covariate */
+  const char   *xtype;        /* [p] 'R' ordered / 'C' unordered factor (levels 1..xlevels[c], at most 32), or NULL (all 'R') */
+  const int    *xlevels;      /* [p] factor sizes (0 for 'R') or NULL */
 } orc_args;
 
 typedef struct {
   int ntree, n;
   long total_nodes, total_leaves, candidates, rmbr_stride;
   int *treeID, *nodeID, *parmID; double *contPT, *splitStat;      /* pre-order, tree order */
+  int *mwcpSZ; unsigned *mwcpPT; int *mwcpCT; long mwcp_total;     /* factor splits: words per node, the words, words per tree */
   int *leafCount, *seed;
   int *bootMembership, *nodeMembership;                            /* [ntree][n] */
   int *tnRCNT, *tnACNT, *tnCLAS;                                   /* per tree, leafCount[b] entries */
@@ -35,7 +38,7 @@ orc_out *orc_grow(const orc_args *a);
 void     orc_free(orc_out *o);
 void     orc_predict(int ntree, int p, long total_nodes, const int *treeID, const int *nodeID, const int *parmID,
                      const double *contPT, const int *leafCount, const int *tnRCNT, const int *tnE,
-                     const double *fx, int m, double *ens, int *membership);
+                     const double *fx, int m, double *ens, int *membership, const int *mwcpSZ, const unsigned *mwcpPT);
 double   orc_poisson_stat(int rule, int n, double k_for_alpha, const char *membership,
                           const double *response, const double *strat, const double *rt);
 void     orc_chain_seeds(int seed, int ntree, int *seedA, int *seedB);
@@ -43,6 +46,7 @@ void     orc_chain_seeds_restore(int ntree, int *seedB);
 void     orc_bootstrap(int seed, int ntree, int n, int tree, int *draws);
 void     orc_ran1_stream(int seed, int count, float *out);
 void     orc_perf_clas(int n, const double *y, const double *ens, const int *den, double na, double *out);
+void     orc_perf_clas2(int n, const double *y, const double *ens, const int *den, double na, int mode, int rfq, double *out);
 
 #ifdef __cplusplus
 }

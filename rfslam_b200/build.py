@@ -11,8 +11,8 @@ LIB = os.path.join(HERE, "librfslam_b200.so")
 # the same sources with device-side checks of the entry lists and the DFS state (-DRF_CHECK); tests/ runs its
 # time-slicing stress against it (compute-sanitizer is not available on the test boxes)
 CHECK_LIB = os.path.join(HERE, "librfslam_b200_check.so")
-SOURCES = ["api.cu", "dataset.cu", "grow.cu", "predict.cu", "hostpool.cu", "plugin.cu", "comm.cu", "grow_t128.cu", "grow_t320.cu", "grow_t512.cu"]
-HEADERS = ["common.cuh", "internal.h", "grow_kernel.cuh", "grow_variant.h", os.path.join("..", "..", "include", "rfslam_b200.h")]
+SOURCES = ["api.cu", "dataset.cu", "grow.cu", "predict.cu", "hostpool.cu", "plugin.cu", "comm.cu", "cpiu.cu", "grow_t128.cu", "grow_t256f.cu", "grow_t320.cu", "grow_t512.cu"]
+HEADERS = ["common.cuh", "internal.h", "grow_kernel.cuh", "grow_variant.h", "perf.cuh", os.path.join("..", "..", "include", "rfslam_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

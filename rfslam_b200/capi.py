@@ -93,6 +93,7 @@ SYMBOLS = [
     "rfslam_b200_device_count", "rfslam_b200_last_profile", "rfslam_b200_free_array", "rfslam_b200_host_pool_trim",
     "rfslam_b200_comm_unique_id", "rfslam_b200_comm_init", "rfslam_b200_comm_destroy", "rfslam_b200_comm_rank",
     "rfslam_b200_comm_world", "rfslam_b200_comm_collectives", "rfslam_b200_nccl_version",
+    "rfslam_b200_cpiu_build", "rfslam_b200_free_cpiu",
 ]
 # the reference's own plugin symbols, exported with its signatures (src/splitCustom.h:24-44, src/splitCustom.c:23-67)
 REFERENCE_SYMBOLS = ["registerThis", "registerCustomFunctions"] + [f"poissonSplit{k}" for k in range(1, 7)]

@@ -15,6 +15,8 @@
 
 namespace rfslam {
 
+constexpr int kMaxFactorLevelsHost = 9;   // = kMaxFactorLevels of the tree kernel (grow_kernel.cuh)
+
 namespace {
 
 __global__ void iota_kernel(uint32_t* v, int n) {
@@ -204,11 +206,26 @@ int dataset_build(const rfslam_grow_args* a, rfslam_dataset** out, WsPool* seed)
       row_arrays_kernel<<<G, T>>>(perm, d_y, d_rt_in, d_u32b, ev, rt, strat, n, d_bad);
 
       // ---- rank-code every covariate column ----------------------------------------------
-      ds->D.resize(p); ds->width.resize(p); ds->codes_h.resize(p); ds->uniq_h.resize(p);
+      ds->D.resize(p); ds->width.resize(p); ds->codes_h.resize(p); ds->uniq_h.resize(p); ds->ftype.assign(p, 0);
       for (int c = 0; c < p; c++) {
-        if (a->x_type && !(a->x_type[c] == 'R' || a->x_type[c] == 'I' || a->x_type[c] == 'B')) {
-          set_error("covariate %d has type '%c': unordered-factor (MWCP) splits are outside the accelerated path", c + 1, a->x_type[c]);
+        const bool isFactor = a->x_type && a->x_type[c] == 'C';
+        if (a->x_type && !(a->x_type[c] == 'R' || a->x_type[c] == 'I' || a->x_type[c] == 'B' || isFactor)) {
+          set_error("covariate %d has type '%c': only real / integer / boolean / unordered-factor covariates are on the accelerated path", c + 1, a->x_type[c]);
           throw CudaFail{RFSLAM_ENOSUP};
+        }
+        if (isFactor) {                                  // levels are the integers 1 .. xLevels (one MWCP word: rf.c:1421)
+          if (!a->x_levels || a->x_levels[c] < 1 || a->x_levels[c] > 32) {
+            set_error("factor covariate %d: xLevels must be in [1, 32] (one MWCP word)", c + 1);
+            throw CudaFail{a->x_levels && a->x_levels[c] > 32 ? RFSLAM_ENOSUP : RFSLAM_EINVAL};
+          }
+          const double* col = a->x_data + (size_t)c * n;
+          for (int i = 0; i < n; i++) {
+            const double v = col[i];
+            if (!(v >= 1.0 && v <= (double)a->x_levels[c] && v == (double)(int)v)) {
+              set_error("factor covariate %d, row %d: level %g is not an integer in [1, %d]", c + 1, i + 1, v, a->x_levels[c]);
+              throw CudaFail{RFSLAM_EINVAL};
+            }
+          }
         }
         RF_CUDA(cudaMemcpy(d_col, a->x_data + (size_t)c * n, (size_t)n * 8, cudaMemcpyHostToDevice));
         column_keys_kernel<<<G, T>>>(d_col, d_keys, n, d_bad);
@@ -221,6 +238,16 @@ int dataset_build(const rfslam_grow_args* a, rfslam_dataset** out, WsPool* seed)
         RF_CUDA(cudaMemcpy(&last, d_u32b + (n - 1), 4, cudaMemcpyDeviceToHost));
         int D = (int)last + 1;
         ds->D[c] = D;
+        ds->ftype[c] = isFactor ? 1 : 0;
+        if (isFactor) {
+          // a factor's cuts are level SUBSETS: 2^(D-1) - 1 of them share one candidate's per-cut accumulators (hist_bins)
+          if (D > kMaxFactorLevelsHost) {
+            set_error("factor covariate %d takes %d distinct levels: unordered-factor splits are accelerated for at most %d levels present", c + 1, D, kMaxFactorLevelsHost);
+            throw CudaFail{RFSLAM_ENOSUP};
+          }
+          ds->has_factor = true;
+          while (ds->hist_bins < (1 << (D > 1 ? D - 1 : 0))) ds->hist_bins *= 2;
+        }
         ds->max_D = std::max(ds->max_D, D);
         if (D <= kHistBins) while (ds->hist_bins < D) ds->hist_bins *= 2;
         else ds->hist_bins = kHistBins;            // small nodes re-rank such a column locally: up to 256 ranks per node
@@ -257,6 +284,11 @@ int dataset_build(const rfslam_grow_args* a, rfslam_dataset** out, WsPool* seed)
       RF_CUDA(cudaMemcpy(d_uniq, ds->uniq_h.data(), (size_t)p * sizeof(double*), cudaMemcpyHostToDevice));
       RF_CUDA(cudaMemcpy(d_width, ds->width.data(), (size_t)p, cudaMemcpyHostToDevice));
       RF_CUDA(cudaMemcpy(d_D, ds->D.data(), (size_t)p * sizeof(int), cudaMemcpyHostToDevice));
+      uint8_t* d_ftype = nullptr;
+      if (ds->has_factor) {
+        d_ftype = dalloc<uint8_t>(ds, p);
+        RF_CUDA(cudaMemcpy(d_ftype, ds->ftype.data(), (size_t)p, cudaMemcpyHostToDevice));
+      }
 
       // Row-major mirror (see DevData): only when every column is byte-coded, and only when the column-major table
       // does not fit the 126 MB L2 anyway.  A table that does (configs[1]: 69 MB) is served from L2 whatever the
@@ -299,7 +331,7 @@ int dataset_build(const rfslam_grow_args* a, rfslam_dataset** out, WsPool* seed)
       d.n = n; d.p = p; d.K = ds->K;
       d.perm = perm; d.inv = inv; d.sb = sb; d.ev = ev; d.rt = rt; d.strat = strat;
       d.codes = (const void* const*)d_codes; d.width = d_width; d.D = d_D; d.uniq = (const double* const*)d_uniq;
-      d.rowcodes = rowcodes; d.rowPitch = rowPitch; d.rowrec = rowrec;
+      d.rowcodes = rowcodes; d.rowPitch = rowPitch; d.rowrec = rowrec; d.ftype = d_ftype;
     } catch (...) {
       free_transient();
       throw;

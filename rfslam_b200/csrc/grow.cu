@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "grow_kernel.cuh"
+#include "perf.cuh"
 #include "internal.h"
 
 namespace rfslam {
@@ -89,7 +90,7 @@ __global__ void user_count_kernel(const int32_t* samp, const uint32_t* perm, uin
 __global__ void compact_kernel(GrowWork w, DevData d, const int* treeIds, const unsigned long long* nodeOff,
                                const unsigned long long* leafOff,
                                int32_t* treeID, int32_t* nodeID, int32_t* parmID, double* contPT, double* splitStat,
-                               uint4* rec4, int32_t* tnRCNT, int32_t* tnCLAS) {
+                               uint4* rec4, int32_t* tnRCNT, int32_t* tnCLAS, int32_t* mwcpWord) {
   const int t = blockIdx.y;
   const uint32_t cntN = w.nodeCount[t];
   const unsigned long long off = nodeOff[t], loff = leafOff[t];
@@ -100,11 +101,21 @@ __global__ void compact_kernel(GrowWork w, DevData d, const int* treeIds, const 
     Rec r = w.pool[at];
     treeID[off + q] = treeIds[t];
     nodeID[off + q] = (int32_t)r.nodeID;
-    parmID[off + q] = (int32_t)r.parm;
+    const uint32_t cov1 = r.parm & ~kFactorFlag;                   // covariate + 1
+    parmID[off + q] = (int32_t)cov1;
     splitStat[off + q] = w.statPool[at];
-    // the traversal kernels read ONE 16-byte record per visited node: {covariate + 1, cut code, right child, node id}
+    // the traversal kernels read ONE 16-byte record per visited node: {covariate + 1 (| factor flag), cut code or
+    // LEFT mask over codes, right child, node id}
     rec4[off + q] = r.parm ? make_uint4(r.parm, r.a, r.b, r.nodeID) : make_uint4(0u, 0u, 0u, r.nodeID);
-    if (r.parm) {
+    if (mwcpWord) mwcpWord[off + q] = 0;
+    if (r.parm & kFactorFlag) {
+      // wire format of a factor split (saveTree rf.c:10773-10779): contPT = NA, one MWCP word whose bit (level - 1) is
+      // set for the levels that go LEFT (convertRelToAbsBinaryPair rf.c:15303-15330); codes -> absolute levels here
+      contPT[off + q] = na;
+      uint32_t word = 0u, mk = r.a;
+      while (mk) { const int cd = __ffs(mk) - 1; mk &= mk - 1u; word |= 1u << ((uint32_t)d.uniq[cov1 - 1][cd] - 1u); }
+      mwcpWord[off + q] = (int32_t)word;
+    } else if (r.parm) {
       contPT[off + q] = d.uniq[r.parm - 1][r.a];
     } else {
       contPT[off + q] = na;
@@ -134,8 +145,10 @@ __global__ void membership_kernel(DevData d, int ntrees, const unsigned long lon
     unsigned long long q = off;
     uint4 r = rec4[q];
     while (r.x != 0u) {
-      const uint32_t cd = load_code(d.codes[r.x - 1u], d.width[r.x - 1u], (uint32_t)i);
-      q = (cd <= r.y) ? q + 1 : off + r.z;
+      const uint32_t cv = (r.x & ~kFactorFlag) - 1u;
+      const uint32_t cd = load_code(d.codes[cv], d.width[cv], (uint32_t)i);
+      const bool left = (r.x & kFactorFlag) ? (((r.y >> cd) & 1u) != 0u) : (cd <= r.y);     // splitOnFactor rf.c:1607-1616
+      q = left ? q + 1 : off + r.z;
       r = rec4[q];
       steps++;
     }
@@ -195,29 +208,6 @@ __global__ void finalize_kernel(double* num, const uint32_t* den, int n) {
   if (i < n) {
     uint32_t dd = den[i];
     if (dd) { num[i] /= (double)dd; num[(size_t)n + i] /= (double)dd; }     // rf.c:8115-8121
-  }
-}
-
-// perfClas (rf.c:7954-8010 default branch): votes of the finalized OOB ensemble.  getMaxVote (rf.c:1175)
-// keeps the LAST class whose probability is >= the running maximum, i.e. class 2 on a tie; the
-// classification index counts rows with an OOB prediction (rf.c:1067), the conditional index divides by
-// ALL rows of the class (rf.c:1025-1066).  acc = {rows class 1, rows class 2, rows with OOB, correct 1, correct 2}
-__global__ void perf_kernel(const double* oob, const uint32_t* den, const uint8_t* ev, const uint32_t* inv, int n,
-                            unsigned long long* acc) {
-  unsigned long long c0 = 0, c1 = 0, cum = 0, ok0 = 0, ok1 = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int cls = ev[inv[i]] ? 1 : 0;
-    if (cls) c1++; else c0++;
-    if (den[i] != 0u) {
-      cum++;
-      const double p1 = oob[i], p2 = oob[(size_t)n + i];
-      const int vote = (p1 <= p2) ? 1 : 0;
-      if (vote == cls) { if (cls) ok1++; else ok0++; }
-    }
-  }
-  c0 = warp_sum(c0); c1 = warp_sum(c1); cum = warp_sum(cum); ok0 = warp_sum(ok0); ok1 = warp_sum(ok1);
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&acc[0], c0); atomicAdd(&acc[1], c1); atomicAdd(&acc[2], cum); atomicAdd(&acc[3], ok0); atomicAdd(&acc[4], ok1);
   }
 }
 
@@ -386,6 +376,8 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     g.has_sort = ds->max_D > kHistBins;
     g.hbins = ds->hist_bins;
     g.nsplit = cfg.nsplit;
+    g.seqDraw = (cfg.nsplit > 0 || ds->has_factor) ? 1 : 0;
+    g.facCuts = ds->has_factor ? 256 : 0;
     if (cfg.nsplit > 0 && ds->max_D > kHistBins) {
       set_error("nsplit = %d with a covariate of %d distinct values: random cut subsets are accelerated for covariates of at most %d distinct values", cfg.nsplit, ds->max_D, kHistBins);
       return RFSLAM_ENOSUP;
@@ -435,6 +427,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         const int v = atoi(e);
         if (!g.has_sort) pl.kv = v == 512 ? grow_variant_t512() : v == 320 ? grow_variant_t320() : v == 128 ? grow_variant_t128() : grow_variant_t256();
       }
+      if (ds->has_factor) pl.kv = grow_variant_t256f();       // the build with the level-subset paths
       const int ctasWanted = pl.kv->ctasPerSm;
       // shared memory available to one CTA's dynamic part (227 KB per SM, 1 KB reserved per CTA, GrowShared is static)
       const size_t limit = (size_t)(227u << 10) / (size_t)ctasWanted - 1024 - sizeof(GrowShared);
@@ -442,18 +435,18 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
       pl.g.tabSlots = kTabSlots;
       if (const char* e = getenv("RFSLAM_TAB_SLOTS")) pl.g.tabSlots = std::max(1, std::min(kTabSlots, atoi(e)));
       if (const char* e = getenv("RFSLAM_HIST_SLOTS")) pl.g.hslots = std::max(1, std::min(pl.g.hslots, atoi(e)));
-      while (grow_smem_bytes(g.ncmax, ds->K, g.hbins, pl.g.hslots, pl.g.tabSlots, 0, tilePitch) > limit && (pl.g.hslots > 1 || pl.g.tabSlots > 1)) {
+      while (grow_smem_bytes(g.ncmax, ds->K, g.hbins, pl.g.hslots, pl.g.tabSlots, 0, tilePitch, g.facCuts) > limit && (pl.g.hslots > 1 || pl.g.tabSlots > 1)) {
         if (pl.g.hslots * 2 > pl.g.tabSlots) pl.g.hslots >>= 1; else pl.g.tabSlots >>= 1;      // (histogram 32 B / bin, tables 16 B / bin)
       }
       pl.g.subMax = 0;
-      if (ds->dev.rowcodes && cfg.nsplit == 0 && !getenv("RFSLAM_NO_SUBTREE")) {
+      if (ds->dev.rowcodes && !g.seqDraw && !getenv("RFSLAM_NO_SUBTREE")) {
         const int wantSub = getenv("RFSLAM_SUBTREE_MAX") ? atoi(getenv("RFSLAM_SUBTREE_MAX")) : kSmallMax;
         const int hsFull = pl.g.hslots, hsMin = std::min(2, hsFull);
         for (int sm = std::min(wantSub, kSmallMax); sm >= 128 && pl.g.subMax == 0; sm >>= 1)
           for (int hs = hsFull; hs >= hsMin; hs >>= 1)
-            if (grow_smem_bytes(g.ncmax, ds->K, g.hbins, hs, pl.g.tabSlots, sm, tilePitch) <= limit) { pl.g.hslots = hs; pl.g.subMax = sm; break; }
+            if (grow_smem_bytes(g.ncmax, ds->K, g.hbins, hs, pl.g.tabSlots, sm, tilePitch, g.facCuts) <= limit) { pl.g.hslots = hs; pl.g.subMax = sm; break; }
       }
-      pl.smem = grow_smem_bytes(g.ncmax, ds->K, g.hbins, pl.g.hslots, pl.g.tabSlots, pl.g.subMax, tilePitch);
+      pl.smem = grow_smem_bytes(g.ncmax, ds->K, g.hbins, pl.g.hslots, pl.g.tabSlots, pl.g.subMax, tilePitch, g.facCuts);
       int perSm = 0;
       RF_CUDA(pl.kv->prepare(pl.smem, &perSm));
       pl.residentCtas = std::max(1, perSm) * sms;
@@ -494,7 +487,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     DevBuf<unsigned long long> d_pathSum(pool);
     d_pathSum.alloc(1); d_pathSum.zero();
 
-    HostOut<int32_t> h_treeID, h_nodeID, h_parmID, h_tnRCNT, h_tnACNT, h_tnCLAS;
+    HostOut<int32_t> h_treeID, h_nodeID, h_parmID, h_tnRCNT, h_tnACNT, h_tnCLAS, h_mwcpW;
     HostOut<double> h_contPT, h_stat;
     std::vector<int32_t> h_leafCount(T), h_seed(T);
     long long totalCand = 0, totalAlgo = 0, launches = 0;
@@ -521,7 +514,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         used += bytes;
       }
     };
-    Acc g_tree(pool), g_node(pool), g_parm(pool), g_cont(pool), g_stat(pool), g_rcnt(pool), g_acnt(pool), g_clas(pool);
+    Acc g_tree(pool), g_node(pool), g_parm(pool), g_cont(pool), g_stat(pool), g_rcnt(pool), g_acnt(pool), g_clas(pool), g_mwcp(pool);
     // events and the copy stream are released on every exit path; the stream is drained first, so no copy can
     // still target a page-locked output block when the HostOut destructors (declared above) hand it back
     struct Sync {
@@ -649,11 +642,13 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         DevBuf<int32_t> f_tree(pool), f_node(pool), f_parm(pool), f_rcnt(pool), f_acnt(pool), f_clas(pool);
         DevBuf<double> f_cont(pool), f_stat(pool); DevBuf<uint4> f_rec4(pool);
         f_tree.alloc(NN); f_node.alloc(NN); f_parm.alloc(NN); f_cont.alloc(NN); f_stat.alloc(NN); f_rec4.alloc(NN);
+        DevBuf<int32_t> f_mwcp(pool);
+        if (ds->has_factor) f_mwcp.alloc(NN);
         f_rcnt.alloc(NL); f_acnt.alloc(NL); f_clas.alloc(2 * NL); f_acnt.zero();
         uint32_t maxNodes = *std::max_element(hNodes.begin(), hNodes.end());
         dim3 gk((unsigned)std::min<uint32_t>((maxNodes + 255) / 256, 2048), (unsigned)nb);
         compact_kernel<<<gk, 256>>>(w, ds->dev, d_ids.p, d_nodeOff.p, d_leafOff.p, f_tree.p, f_node.p, f_parm.p, f_cont.p, f_stat.p,
-                                    f_rec4.p, f_rcnt.p, f_clas.p);
+                                    f_rec4.p, f_rcnt.p, f_clas.p, ds->has_factor ? f_mwcp.p : nullptr);
         RF_CUDA(cudaEventRecord(evC));
         RF_CUDA(cudaEventRecord(evM.a));
         membership_kernel<<<(n + 127) / 128, 128>>>(ds->dev, nb, d_nodeOff.p, d_leafOff.p, f_rec4.p,
@@ -667,6 +662,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
           const size_t hintN = (size_t)(estNodes * T), hintL = hintN / 2 + T;
           g_tree.append(f_tree.p, NN * 4, hintN * 4); g_node.append(f_node.p, NN * 4, hintN * 4); g_parm.append(f_parm.p, NN * 4, hintN * 4);
           g_cont.append(f_cont.p, NN * 8, hintN * 8);
+          if (ds->has_factor) g_mwcp.append(f_mwcp.p, NN * 4, hintN * 4);
           if (wantStat) g_stat.append(f_stat.p, NN * 8, hintN * 8);
           g_rcnt.append(f_rcnt.p, NL * 4, hintL * 4); g_acnt.append(f_acnt.p, NL * 4, hintL * 4); g_clas.append(f_clas.p, 2 * NL * 4, hintL * 8);
           RF_CUDA(cudaEventSynchronize(ev3));
@@ -679,6 +675,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         RF_CUDA(cudaMemcpyAsync(h_nodeID.grow(NN), f_node.p, NN * 4, cudaMemcpyDeviceToHost, copyStream));
         RF_CUDA(cudaMemcpyAsync(h_parmID.grow(NN), f_parm.p, NN * 4, cudaMemcpyDeviceToHost, copyStream));
         RF_CUDA(cudaMemcpyAsync(h_contPT.grow(NN), f_cont.p, NN * 8, cudaMemcpyDeviceToHost, copyStream));
+        if (ds->has_factor) RF_CUDA(cudaMemcpyAsync(h_mwcpW.grow(NN), f_mwcp.p, NN * 4, cudaMemcpyDeviceToHost, copyStream));
         if (wantStat) RF_CUDA(cudaMemcpyAsync(h_stat.grow(NN), f_stat.p, NN * 8, cudaMemcpyDeviceToHost, copyStream));
         RF_CUDA(cudaMemcpyAsync(h_tnRCNT.grow(NL), f_rcnt.p, NL * 4, cudaMemcpyDeviceToHost, copyStream));
         RF_CUDA(cudaMemcpyAsync(h_tnCLAS.grow(2 * NL), f_clas.p, 2 * NL * 4, cudaMemcpyDeviceToHost, copyStream));
@@ -762,22 +759,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     // perfClas: only for a whole, finalized forest (a shard's ensembles are partial sums)
     double* h_perf = nullptr;
     if (cfg.finalize && (a->opt_low & RFSLAM_OPT_PERF) && wholeForest) {
-      DevBuf<unsigned long long> d_acc(pool);
-      d_acc.alloc(5); d_acc.zero();
-      perf_kernel<<<296, 256>>>(d_oobNum.p, d_oobDen.p, ds->dev.ev, ds->dev.inv, n, d_acc.p);
-      launches++;
-      unsigned long long acc[5];
-      RF_CUDA(cudaMemcpy(acc, d_acc.p, sizeof acc, cudaMemcpyDeviceToHost));
-      const size_t PT = (size_t)cfg.ntree;                         // [ntree][3]; a rank of a sharded forest returns the whole forest's table too
-      h_perf = (double*)host_alloc(PT * 3 * sizeof(double));
-      const double na = rfslam_na_real();
-      for (size_t k = 0; k < PT * 3; k++) h_perf[k] = na;
-      double* last = h_perf + (PT - 1) * 3;                       // serialTreeID == ntree (rf.c:8155)
-      if (acc[2] != 0) {
-        last[0] = 1.0 - (double)(acc[3] + acc[4]) / (double)acc[2];
-        if (acc[0]) last[1] = 1.0 - (double)acc[3] / (double)acc[0];
-        if (acc[1]) last[2] = 1.0 - (double)acc[4] / (double)acc[1];
-      }
+      h_perf = perf_clas_table(a->opt_low, cfg.ntree, n, d_oobNum.p, d_oobDen.p, ds->dev.ev, ds->dev.inv, nullptr, &launches);   // [ntree][3]; a rank of a sharded forest returns the whole forest's table too
     }
     unsigned long long pathSum = 0;
     RF_CUDA(cudaMemcpy(&pathSum, d_pathSum.p, 8, cudaMemcpyDeviceToHost));
@@ -802,6 +784,8 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
       m_node.p = comm_gather_i32(comm, (const int32_t*)g_node.p, nodeUnits, 1);
       m_parm.p = comm_gather_i32(comm, (const int32_t*)g_parm.p, nodeUnits, 1);
       m_cont.p = comm_gather_f64(comm, (const double*)g_cont.p, nodeUnits, 1);
+      Dev m_mwcp;
+      if (ds->has_factor) m_mwcp.p = comm_gather_i32(comm, (const int32_t*)g_mwcp.p, nodeUnits, 1);
       if (wantStat) m_stat.p = comm_gather_f64(comm, (const double*)g_stat.p, nodeUnits, 1);
       m_rcnt.p = comm_gather_i32(comm, (const int32_t*)g_rcnt.p, leafUnits, 1);
       m_acnt.p = comm_gather_i32(comm, (const int32_t*)g_acnt.p, leafUnits, 1);
@@ -812,6 +796,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         RF_CUDA(cudaMemcpy(h_nodeID.grow((size_t)NNall), m_node.p, (size_t)NNall * 4, cudaMemcpyDeviceToHost));
         RF_CUDA(cudaMemcpy(h_parmID.grow((size_t)NNall), m_parm.p, (size_t)NNall * 4, cudaMemcpyDeviceToHost));
         RF_CUDA(cudaMemcpy(h_contPT.grow((size_t)NNall), m_cont.p, (size_t)NNall * 8, cudaMemcpyDeviceToHost));
+        if (ds->has_factor) RF_CUDA(cudaMemcpy(h_mwcpW.grow((size_t)NNall), m_mwcp.p, (size_t)NNall * 4, cudaMemcpyDeviceToHost));
         if (wantStat) RF_CUDA(cudaMemcpy(h_stat.grow((size_t)NNall), m_stat.p, (size_t)NNall * 8, cudaMemcpyDeviceToHost));
         RF_CUDA(cudaMemcpy(h_tnRCNT.grow((size_t)NLall), m_rcnt.p, (size_t)NLall * 4, cudaMemcpyDeviceToHost));
         RF_CUDA(cudaMemcpy(h_tnACNT.grow((size_t)NLall), m_acnt.p, (size_t)NLall * 4, cudaMemcpyDeviceToHost));
@@ -829,6 +814,18 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     out->tree_ids = (int32_t*)host_alloc((size_t)Tout * 4); memcpy(out->tree_ids, ids.data(), (size_t)Tout * 4);
     out->mwcpSZ = (int32_t*)host_calloc(std::max<size_t>(h_treeID.n, 1) * 4);
     out->mwcpCT = (int32_t*)host_calloc((size_t)Tout * 4); out->mwcpPT = nullptr; out->mwcp_total = 0;
+    if (ds->has_factor && h_mwcpW.n == h_treeID.n) {
+      // mwcpSZ / mwcpPT / mwcpCT (saveTree rf.c:10773-10779): one word per factor split in record order, words per tree
+      size_t words = 0;
+      for (size_t q = 0; q < h_mwcpW.n; q++) if (h_mwcpW.p[q]) words++;
+      out->mwcpPT = (int32_t*)host_alloc(std::max<size_t>(words, 1) * 4);
+      size_t at = 0; int slot = 0;
+      for (size_t q = 0; q < h_mwcpW.n; q++) {
+        if (q > 0 && h_treeID.p[q] != h_treeID.p[q - 1]) slot++;
+        if (h_mwcpW.p[q]) { out->mwcpSZ[q] = 1; out->mwcpPT[at++] = h_mwcpW.p[q]; if (slot < Tout) out->mwcpCT[slot]++; }
+      }
+      out->mwcp_total = (int64_t)words;
+    }
     out->treeID = h_treeID.release(); out->nodeID = h_nodeID.release(); out->parmID = h_parmID.release();
     out->contPT = h_contPT.release(); out->splitStat = wantStat ? h_stat.release() : nullptr;
     out->leafCount = (int32_t*)host_alloc((size_t)Tout * 4); memcpy(out->leafCount, h_leafCount.data(), (size_t)Tout * 4);
@@ -879,7 +876,7 @@ int score_node_impl(int rule, double k_for_alpha, int m, const double* x, const 
     g.rule = rule; g.mtry = 1; g.nodesize = 1; g.nodedepth = -1; g.alpha = 1.0 / (k_for_alpha * k_for_alpha);
     g.pw = 1; g.ncmax = 1; g.has_sort = ds->max_D > kHistBins; g.hbins = ds->hist_bins;
     { int ex = 0; frexp(std::max((double)m * std::max(ds->max_rt, 1e-300), 1.0), &ex); g.tscale = ldexp(1.0, 62 - ex); g.tinv = ldexp(1.0, ex - 62); }
-    g.hslots = hist_slots(g.hbins); g.tabSlots = kTabSlots; g.subMax = 0;
+    g.hslots = hist_slots(g.hbins); g.tabSlots = kTabSlots; g.subMax = 0; g.seqDraw = 0; g.facCuts = 0;
     const size_t smem = grow_smem_bytes(g.ncmax, ds->K, g.hbins, g.hslots, g.tabSlots, 0, 0);
     RF_CUDA(cudaFuncSetAttribute(rfslam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DevBuf<uint32_t> d_lists, d_sort, d_stackPerm, d_ctab, d_nodeCount, d_leafCount, d_cursor;

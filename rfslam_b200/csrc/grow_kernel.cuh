@@ -63,6 +63,13 @@ struct NodeEnt {        // a pending node of the DFS
 };
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;
+#ifndef RF_FACTORS
+#define RF_FACTORS 0
+#endif
+// Factor support is a BUILD of the kernel (grow_t256f.cu): the kernel is instruction-fetch sensitive on its once-per-node
+// code, and the level-subset paths measurably slow the all-numeric build down (1.46 s -> 1.56 s per 500 trees) by size alone.
+constexpr bool kFactors = RF_FACTORS != 0;
+constexpr uint32_t kFactorFlag = 0x80000000u;   // Rec::parm of a factor split: `a` is then the LEFT set as a mask over codes
 #ifndef RF_SMALL_MAX
 #define RF_SMALL_MAX 512
 #endif
@@ -82,6 +89,9 @@ struct GrowParams {
   double tscale, tinv;           // 2^S and 2^-S of the fixed-point exposure accumulators (see hist_add)
   int nsplit;                    // > 0: at most nsplit randomly drawn cuts per covariate (rf.c:14533-14564)
   int hslots;                    // stratum slots per candidate histogram (GrowSmem::hs), chosen by the host to fit shared memory
+  int seqDraw;                   // candidates are drawn one at a time by the whole CTA (nsplit > 0 or a factor covariate: cut draws
+                                 // interleave with the covariate draws in chain B); the tracker then reads the cut masks
+  int facCuts;                   // > 0: room for this many cut masks per factor candidate (GrowSmem::facMask)
   int tabSlots;                  // strata per group of the small-node path (<= RF_MAX_SLOTS): sizes the term tables (GrowSmem::ts)
   int subMax;                    // > 0: a node of at most this many entries stages ITS WHOLE ROWS in shared memory and the subtree
                                  //      below it is grown out of that tile (see stage_subtree); 0 = off
@@ -149,6 +159,8 @@ struct GrowShared {
   uint32_t cutMask[kMaxCand][8]; uint32_t rankSel[8]; uint8_t swor[256]; int trkCuts[kMaxCand];
   int candStride;                    // byte-coded candidates: code of row r = candPtr[k][r * candStride] (1 = column-major array, rowPitch = row-major mirror)
   int inSub; uint32_t subSp, subStart; // growing inside a staged subtree: DFS depth at its root, list offset of its first entry
+  uint8_t candFac[kMaxCand];         // candidate is an unordered factor: its cuts are the level subsets facMask[k][0 .. facN[k])
+  int facN[kMaxCand];
   uint8_t candLocal[kMaxCand];       // candidate re-ranked locally by this node (its codes in shared memory are node-local ranks)
   uint32_t bestWide;                 // the winning cut of a locally re-ranked candidate as a table-wide code
 };
@@ -214,6 +226,8 @@ struct GrowSmem {
   uint32_t* smEnt; SmallRec* smRec; uint8_t* smCodes;
   // staged subtree (subMax entries): entry words, records, the entries' whole code rows, and the node order (slot per position)
   uint32_t* stRow; SmallRec* stRec; uint8_t* stTile; uint16_t* stIdx; int subMax, tilePitch;
+  uint32_t* facMask;                 // [ncmax][facCuts] LEFT sets of a factor candidate's cuts, as masks over CODES (bit = rank code)
+  int facCuts;
   GrowShared* s;
   int hb;                            // bins per candidate histogram: pow2 >= the widest byte-coded column, 32..256
   int hs;                            // stratum slots per candidate histogram (large nodes accumulate hs strata per pass)
@@ -229,7 +243,7 @@ struct GrowSmem {
 constexpr int kTabSlots = RF_MAX_SLOTS;    // strata per group of the small-node path (independent of the large-node passes' hs)
 __host__ __device__ inline int hist_slots(int hb) { int g = 256 / hb; return g < 1 ? 1 : (g > RF_MAX_SLOTS ? RF_MAX_SLOTS : g); }
 
-__host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K, int hb, int hslots, int tabSlots, int subMax, int tilePitch) {
+__host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K, int hb, int hslots, int tabSlots, int subMax, int tilePitch, int facCuts = 0) {
   const size_t hs = (size_t)hslots;
   size_t KS = (size_t)K + 2;
   size_t b = 0;
@@ -247,10 +261,11 @@ __host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K, int hb, int 
   b = (b + 15) & ~(size_t)15;
   b += (size_t)subMax * (4 + 16 + (size_t)tilePitch + 2) + 32;   // staged subtree
   b = (b + 15) & ~(size_t)15;
+  b += (size_t)ncmax * (size_t)facCuts * 4;                      // factor cut masks
   return b + 16;                               // (GrowShared is a static __shared__ object of the kernel, not part of this)
 }
 
-__device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb, int hslots, int tabSlots, int subMax, int tilePitch) {
+__device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb, int hslots, int tabSlots, int subMax, int tilePitch, int facCuts) {
   GrowSmem m;
   m.hb = hb;
   m.hs = hslots;
@@ -298,6 +313,10 @@ __device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb, i
     m.stRow = (uint32_t*)(m.stTile + (size_t)subMax * tilePitch);
     m.stIdx = (uint16_t*)(m.stRow + subMax);
     u = (uint32_t*)(m.stIdx + subMax + (subMax & 1));
+  }
+  {
+    uintptr_t al = ((uintptr_t)u + 15) & ~(uintptr_t)15;
+    m.facMask = (uint32_t*)al; m.facCuts = facCuts;
   }
   m.s = nullptr;                               // set by the kernel: GrowShared is a static __shared__ object, so every s->field
                                                // access is an LDS / STS by construction (no address-space assumption needed)
@@ -356,6 +375,9 @@ struct NodeCtx {
   double beta;
   int Kloop;
 };
+
+__device__ inline double factor_accumulate(const NodeCtx& c, int ci, uint32_t vN, uint32_t vE, double vT, double vW);
+__device__ __forceinline__ void factor_set_presence(const NodeCtx& c, int ci);
 
 // one in-bag entry into one candidate's histogram: native 32-bit shared atomics only.
 // f64 (and 64-bit) shared atomics are CAS loops on sm_100a (ATOMS.CAST.SPIN) and were the top stall
@@ -448,6 +470,24 @@ __device__ inline void flush_stratum(const NodeCtx& c, int nc, int nslots) {
     const int Dc = s->candD[ci];
     const int nch = (Dc + 31) >> 5;
     const double t0 = c.d.rt_mode;
+    if (kFactors && s->candFac[ci]) {                                // unordered factor: per-level bins -> every level-subset cut
+      for (int slot = 0; slot < nslots; slot++) {
+        const int ho = (ci * m.hs + slot) * m.hb;
+        uint32_t vN = 0, vE = 0; double vT = 0.0, vW = 0.0;
+        if (lane < Dc) {
+          vN = m.hN[ho + lane]; vE = m.hE[ho + lane];
+          if (!c.unit) {
+            vT = t0 * (double)(vN - m.hNx[ho + lane]) + fixed_get(&m.hT[ho + lane], c.g.tinv);
+            vW = t0 * (double)(vE - m.hEx[ho + lane]) + fixed_get(&m.hW[ho + lane], c.g.tinv);
+          }
+          m.hN[ho + lane] = 0; m.hE[ho + lane] = 0; m.hNx[ho + lane] = 0; m.hEx[ho + lane] = 0; m.hT[ho + lane] = 0.0; m.hW[ho + lane] = 0.0;
+        }
+        const double termP = factor_accumulate(c, ci, vN, vE, vT, vW);
+        if (lane == 0) m.statP[ci] += termP;
+      }
+      factor_set_presence(c, ci);
+      continue;
+    }
     for (int slot = 0; slot < nslots; slot++) {
       const int ho = (ci * m.hs + slot) * m.hb;
       const uint32_t* hN = m.hN + ho; const uint32_t* hE = m.hE + ho;
@@ -485,7 +525,7 @@ __device__ inline void track_summary(const NodeCtx& c, int ci) {
   GrowSmem& m = c.m;
   GrowShared* s = m.s;
   const int lane = lane_id();
-  const int Dc = s->candD[ci];
+  const int Dc = (kFactors && s->candFac[ci]) ? s->facN[ci] + 1 : s->candD[ci];      // bins the tracker walks: codes, or a factor's cuts + the closing bin
   const int nch = (Dc + 31) >> 5;
   uint32_t word = (lane < 8) ? m.pres[ci * 8 + lane] : 0u;
   int np = warp_sum((int)__popc(word));
@@ -496,7 +536,7 @@ __device__ inline void track_summary(const NodeCtx& c, int ci) {
   const int cov = s->candCov[ci];
   const double wgt = c.g.split_weight ? c.g.split_weight[cov] : 1.0;
   const double statP = m.statP[ci];
-  const uint32_t* cm = c.g.nsplit > 0 ? s->cutMask[ci] : nullptr;    // drawn cut subset (nsplit > 0)
+  const uint32_t* cm = c.g.seqDraw ? s->cutMask[ci] : nullptr;       // the candidate's cuts as a mask (drawn subset, factor cuts)
   int ncuts = np - 1;
   if (cm) ncuts = warp_sum((lane < 8) ? (int)__popc(cm[lane]) : 0);
   double M = -INFINITY; int pos = 0x7fffffff; bool anyNan = false;
@@ -541,13 +581,13 @@ __device__ inline void track_exact(const NodeCtx& c, int ci) {
   GrowSmem& m = c.m;
   GrowShared* s = m.s;
   const int lane = lane_id();
-  const int Dc = s->candD[ci];
+  const int Dc = (kFactors && s->candFac[ci]) ? s->facN[ci] + 1 : s->candD[ci];      // bins the tracker walks: codes, or a factor's cuts + the closing bin
   const int nch = (Dc + 31) >> 5;
   const int last = s->trkLast[ci];
   const int cov = s->candCov[ci];
   int have = s->have; double best = s->bestDelta; int bestBin = -1;
   int emitted = s->cutsSeen;
-  const uint32_t* cm = c.g.nsplit > 0 ? s->cutMask[ci] : nullptr;
+  const uint32_t* cm = c.g.seqDraw ? s->cutMask[ci] : nullptr;
 #pragma unroll 1
   for (int ch = 0; ch < nch; ch++) {
     int bin = (ch << 5) + lane;
@@ -809,6 +849,131 @@ __device__ inline void sort_candidate(const NodeCtx& c, int ci, uint32_t len) {
     }
   }
   __syncthreads();
+}
+
+
+// ---- unordered factors (MWCP splits, rf.c:14452-14518) ----------------------------------------------------------
+// A factor candidate's cuts are LEFT sets of the r levels present in the node.  Deterministic mode: all 2^(r-1) - 1
+// complementary pairs, by cardinality of the LEFT set (1 .. floor(r/2)), lexicographic inside a cardinality, only the
+// first half of the middle cardinality when r is even -- the order bookPair (rf.c:1498-1530) books them in, pinned
+// against the live reference's tables for r = 2..12 (tests/test_oracle.py).  Cut j is UNRANKED on the fly (no table):
+// thread j finds its cardinality group, then the combination with that lexicographic rank.  Masks are over rank
+// CODES (bit = code of the level in this table); the forest record converts them to absolute levels (compact_kernel).
+static __device__ __constant__ const uint8_t kChoose[10][10] = {
+  {1,0,0,0,0,0,0,0,0,0}, {1,1,0,0,0,0,0,0,0,0}, {1,2,1,0,0,0,0,0,0,0}, {1,3,3,1,0,0,0,0,0,0}, {1,4,6,4,1,0,0,0,0,0},
+  {1,5,10,10,5,1,0,0,0,0}, {1,6,15,20,15,6,1,0,0,0}, {1,7,21,35,35,21,7,1,0,0}, {1,8,28,56,70,56,28,8,1,0}, {1,9,36,84,126,126,84,36,9,1}};
+constexpr int kMaxFactorLevels = 9;          // 2^8 - 1 = 255 cuts fit one candidate's accumulators (hb <= 256)
+
+// the code of the k-th (0-based) level present in the node
+__device__ __forceinline__ uint32_t nth_present_code(uint32_t presW, int k) {
+  for (int i = 0; i < k; i++) presW &= presW - 1u;
+  return (uint32_t)__ffs(presW) - 1u;
+}
+
+__device__ inline uint32_t factor_cut_mask(int r, int j, uint32_t presW) {
+  int g = 1, idx = j;
+  while (true) {                                                     // cardinality group of cut j
+    int gs = kChoose[r][g];
+    if (!(r & 1) && g == (r >> 1)) gs >>= 1;
+    if (idx < gs) break;
+    idx -= gs; g++;
+  }
+  uint32_t mask = 0u;
+  int x = 1;                                                         // relative levels 1..r
+  for (int i = 0; i < g; i++) {                                      // lexicographic unranking of a g-combination
+    while (true) {
+      const int cnt = kChoose[r - x][g - i - 1];                     // combinations that start with level x at position i
+      if (idx < cnt) break;
+      idx -= cnt; x++;
+    }
+    mask |= 1u << nth_present_code(presW, x - 1);
+    x++;
+  }
+  return mask;
+}
+
+// One stratum of a factor candidate: lane l holds the stratum's (rows, events, exposure, event exposure) at code l.
+// Adds the stratum's left / right terms of every cut to sL / sR (cut j at index j) and returns its parent term.
+// A stratum without events contributes exactly 0 to every cut and to the parent (see side_term).
+__device__ inline double factor_accumulate(const NodeCtx& c, int ci, uint32_t vN, uint32_t vE, double vT, double vW) {
+  GrowSmem& m = c.m;
+  GrowShared* s = m.s;
+  const int lane = lane_id();
+  const uint32_t tE = warp_sum(vE);
+  if (tE == 0u) return 0.0;
+  const uint32_t tN = warp_sum(vN);
+  const double tT = c.unit ? (double)tN : warp_sum(vT), tW = c.unit ? (double)tE : warp_sum(vW);
+  if (c.unit) { vT = (double)vN; vW = (double)vE; }
+  const double termP = side_term(c.bayes, (double)tE, (double)tN, tT, tW, c.g.alpha, c.beta);
+  const int ncuts = s->facN[ci], Dc = s->candD[ci];
+  const uint32_t* masks = m.facMask + (size_t)ci * m.facCuts;
+#pragma unroll 1
+  for (int base = 0; base < ncuts; base += 32) {
+    const int j = base + lane;
+    const uint32_t mk = j < ncuts ? masks[j] : 0u;
+    uint32_t LN = 0, LE = 0; double LT = 0.0, LW = 0.0;
+#pragma unroll 1
+    for (int l = 0; l < Dc; l++) {                                   // ascending level: the order the plugin's sorted rows arrive in
+      const uint32_t n_l = __shfl_sync(0xffffffffu, vN, l), e_l = __shfl_sync(0xffffffffu, vE, l);
+      const double t_l = __shfl_sync(0xffffffffu, vT, l), w_l = __shfl_sync(0xffffffffu, vW, l);
+      if ((mk >> l) & 1u) { LN += n_l; LE += e_l; LT += t_l; LW += w_l; }
+    }
+    const double tL = side_term(c.bayes, (double)LE, (double)LN, LT, LW, c.g.alpha, c.beta);
+    const double tR = side_term(c.bayes, (double)(tE - LE), (double)(tN - LN), tT - LT, tW - LW, c.g.alpha, c.beta);
+    if (j < ncuts) { m.sL[ci * m.hb + j] += tL; m.sR[ci * m.hb + j] += tR; }
+  }
+  return termP;
+}
+
+// the tracker sees a factor candidate as cuts 0 .. ncuts-1 "present" plus one closing bin it never selects
+__device__ __forceinline__ void factor_set_presence(const NodeCtx& c, int ci) {
+  const int lane = lane_id();
+  const int ncuts = c.m.s->facN[ci];
+  if (lane < 8) {
+    const int lo = lane * 32;
+    uint32_t w = 0u;
+    if (ncuts > 0 && ncuts + 1 > lo) w = (ncuts + 1 - lo >= 32) ? 0xFFFFFFFFu : ((1u << (ncuts + 1 - lo)) - 1u);
+    c.m.pres[ci * 8 + lane] = w;
+  }
+  __syncwarp();
+}
+
+// small node: the candidate's warp builds each event stratum's per-level statistics from the staged rows
+__device__ inline void small_factor_candidate(const NodeCtx& c, int ci) {
+  GrowSmem& m = c.m;
+  GrowShared* s = m.s;
+  const int lane = lane_id();
+  const int ncuts = s->facN[ci];
+  const SmallRec* __restrict__ rec = m.smRec;
+  const uint8_t* __restrict__ cptr = m.smCodes + ci * kSmallMax;
+  for (int b = lane; b <= ncuts; b += 32) { m.sL[ci * m.hb + b] = 0.0; m.sR[ci * m.hb + b] = 0.0; }
+  __syncwarp();
+  double statP = 0.0;
+  if (ncuts > 0) {
+    const int nw = (c.Kloop + 31) >> 5;
+#pragma unroll 1
+    for (int w8 = 0; w8 < nw; w8++) {
+      uint32_t word = s->evMask[w8];
+#pragma unroll 1
+      while (word) {                                                 // event strata, ascending (sc.c:760-764 sums in this order)
+        const int sidx = (w8 << 5) + __ffs(word) - 1;
+        word &= word - 1u;
+        const uint32_t a0 = m.segpos[sidx], a1 = m.cN[sidx];
+        uint32_t vN = 0, vE = 0; double vT = 0.0, vW = 0.0;
+#pragma unroll 1
+        for (uint32_t k = a0; k < a1; k++) {
+          const SmallRec r = rec[k];
+          if ((uint32_t)cptr[k] == (uint32_t)lane) {
+            vN += r.mult; vT += r.mrt;
+            if (r.es & 1u) { vE += r.mult; vW += r.mrt; }
+          }
+        }
+        statP += factor_accumulate(c, ci, vN, vE, vT, vW);
+      }
+    }
+  }
+  if (lane == 0) m.statP[ci] = statP;
+  factor_set_presence(c, ci);
 }
 
 // ---- small nodes (<= kSmallMax entries, histogram candidates only) ---------------------------
@@ -1163,7 +1328,9 @@ __device__ inline void score_small(NodeCtx& c) {
     for (int ci = wid; ci < nc; ci += kWarps)
       if (!s->candHist[ci]) local_rank_candidate(s, m.smEnt, m.smCodes + ci * kSmallMax, ci, len);
   }
-  for (int ci = wid; ci < nc; ci += kWarps) small_candidate(c, ci, len);   // the same warp summarises ci next (score_node)
+  for (int ci = wid; ci < nc; ci += kWarps) {                               // the same warp summarises ci next (score_node)
+    if (kFactors && s->candFac[ci]) small_factor_candidate(c, ci); else small_candidate(c, ci, len);
+  }
 }
 
 // ---- score all drawn candidates of the current node (steps 2-4) ------------------------------
@@ -1394,11 +1561,58 @@ __device__ inline void node_prologue_nsplit(const DevData& d, const GrowParams& 
       if (lane == 0) { if (acc0) atomicOr(&m.pres[k * 8], acc0); if (acc1) atomicOr(&m.pres[k * 8 + 1], acc1); }
     }
     __syncthreads();
+    const int covk = s->candCov[k];
+    if (kFactors && d.ftype && d.ftype[covk]) {
+      // unordered factor (stackAndConstructSplitVector, rf.c:14452-14518): deterministic when the 2^(r-1) - 1 complementary
+      // pairs of the r levels present are fewer than the node's in-bag members (nsplit > 0: no more than min(nsplit,
+      // members)), every thread then unranks its own cuts; otherwise as many RANDOM pairs as members (nsplit > 0:
+      // min(nsplit, members)), drawn from chain B by thread 0: a cardinality in proportion to the group sizes
+      // (getRandomPair rf.c:15232-15262), then that many levels without replacement (createRandomBinaryPair rf.c:15263-15302)
+      const uint32_t presW = m.pres[k * 8];                          // (a factor has at most kMaxFactorLevels codes)
+      const int r = __popc(presW);
+      int ncuts = 0; bool det = true;
+      if (r >= 2) {
+        const uint32_t pairs = (1u << (r - 1)) - 1u;
+        if (g.nsplit == 0) { det = !(pairs >= mInBag); ncuts = det ? (int)pairs : (int)mInBag; }
+        else { const uint32_t lim = min((uint32_t)g.nsplit, mInBag); det = pairs <= lim; ncuts = det ? (int)pairs : (int)lim; }
+      }
+      uint32_t* masks = m.facMask + (size_t)k * m.facCuts;
+      if (det) {
+        for (int j = tid; j < ncuts; j += kThreads) masks[j] = factor_cut_mask(r, j, presW);
+      } else if (tid == 0) {
+        double cdf[kMaxFactorLevels / 2 + 2];
+        const int G = r >> 1;
+        cdf[0] = 0.0;
+        for (int q = 1; q <= G; q++) { int gs = kChoose[r][q]; if (!(r & 1) && q == G) gs >>= 1; cdf[q] = cdf[q - 1] + (double)gs; }
+        for (int j = 0; j < ncuts; j++) {
+          const double rv = ceil(ran1_next(s->rng) * cdf[G]);         // float * double, as in the reference
+          int gi = 1; while (rv > cdf[gi]) gi++;
+          uint8_t lv[kMaxFactorLevels + 1];
+          for (int q = 1; q <= r; q++) lv[q] = (uint8_t)q;
+          int size = r; uint32_t mk = 0u;
+          for (int q = 1; q <= gi; q++) {
+            const uint32_t slot = ran1_index(s->rng, (uint32_t)size);
+            const int rel = lv[slot];
+            lv[slot] = lv[size]; size--;
+            mk |= 1u << nth_present_code(presW, rel - 1);
+          }
+          masks[j] = mk;
+        }
+      }
+      if (tid < 8) {                                                 // the tracker's cut mask: cuts 0 .. ncuts-1
+        const int lo = tid * 32;
+        s->cutMask[k][tid] = ncuts > lo ? ((ncuts - lo >= 32) ? 0xFFFFFFFFu : ((1u << (ncuts - lo)) - 1u)) : 0u;
+      }
+      if (tid == 0) { s->candFac[k] = 1; s->facN[k] = ncuts; }
+      __syncthreads();
+      continue;
+    }
     if (tid == 0) {
+      s->candFac[k] = 0; s->facN[k] = 0;
       int np = 0, last = -1;
       for (int wq = 0; wq < 8; wq++) { const uint32_t wd = m.pres[k * 8 + wq]; np += __popc(wd); if (wd) last = (wq << 5) + 31 - __clz(wd); }
       if (np >= 2) {
-        if (np > g.nsplit) {
+        if (g.nsplit > 0 && np > g.nsplit) {
           int sz = np - 1;
           for (int j = 0; j < sz; j++) s->swor[j] = (uint8_t)j;      // ranks 0 .. D-2 of the distinct values (the last is never a cut)
           for (int j = 0; j < g.nsplit; j++) {
@@ -1485,7 +1699,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, RF_MIN_CTAS)
 RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ GrowShared g_state;
-  GrowSmem m = carve(smem_raw, g.ncmax, d.K, g.hbins, g.hslots, g.tabSlots, g.subMax, (d.rowPitch + 15) & ~15);
+  GrowSmem m = carve(smem_raw, g.ncmax, d.K, g.hbins, g.hslots, g.tabSlots, g.subMax, (d.rowPitch + 15) & ~15, g.facCuts);
   m.s = &g_state;
   GrowShared* s = &g_state;
 #ifdef RF_CHECK
@@ -1627,7 +1841,7 @@ RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
     // One serial section per node, run by warp 0 between two block barriers: tracker reset, the draws
     // and the candidate metadata (a barrier + phase boundary costs ~1k cycles on a node that has a few
     // dozen rows; there used to be five of them before the first gather).
-    if (g.nsplit > 0 && attempt) {
+    if (g.seqDraw && attempt) {
       node_prologue_nsplit(d, g, s, m, w.lists + ((size_t)tree * 2 + cur.buf) * w.listStride + cur.start, cur.len, cur.m);
     } else if (warp_id() == 0) {
       const int lane = lane_id();
@@ -1659,7 +1873,7 @@ RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
         if (lane < ncd) {                                  // candidate metadata: one parallel round of loads
           const int cov = s->candCov[lane];
           const int Dv = d.D[cov];
-          s->candD[lane] = Dv; s->candW[lane] = d.width[cov]; s->candHist[lane] = Dv <= kHistBins; s->candLocal[lane] = 0;
+          s->candD[lane] = Dv; s->candW[lane] = d.width[cov]; s->candHist[lane] = Dv <= kHistBins; s->candLocal[lane] = 0; s->candFac[lane] = 0;
           s->candPtr[lane] = sparse ? (const void*)(d.rowcodes + cov) : d.codes[cov];
         }
       }
@@ -1694,6 +1908,12 @@ RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
     // ---- split: record, partition, push right, descend left ----
     const int bc = s->bestCand;
     const uint32_t bcode = s->bestCode;
+    // an unordered factor routes by level subset (splitOnFactor, rf.c:1607-1616): bestCode is the cut's index, the LEFT set
+    // is its mask over codes.  goes_left(code) covers both kinds of split with one shift: a numeric cut at code b is the
+    // mask of codes 0..b when the column has at most 32 codes, the compare otherwise.
+    const bool isFac = kFactors && s->candFac[bc] != 0;
+    const uint32_t fmask = isFac ? m.facMask[(size_t)bc * m.facCuts + bcode] : 0u;
+#define RF_GOES_LEFT(code) (isFac ? (((fmask >> (code)) & 1u) != 0u) : ((code) <= bcode))
     const void* ptr = s->candPtr[bc]; const int wd = s->candW[bc]; const int cov = s->candCov[bc];
     const uint32_t* src = w.lists + ((size_t)tree * 2 + cur.buf) * w.listStride + cur.start;
     uint32_t* dst = w.lists + ((size_t)tree * 2 + (cur.buf ^ 1u)) * w.listStride + cur.start;
@@ -1716,7 +1936,7 @@ RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
         lf[u] = false; en[u] = 0u;
         if (i < cur.len) {
           en[u] = sub ? (uint32_t)m.stIdx[soff + i] : m.smEnt[i];
-          lf[u] = cptr[i] <= bcode;                               // LEFT iff cut - x >= 0 (rf.c:15194)
+          lf[u] = RF_GOES_LEFT((uint32_t)cptr[i]);                // LEFT iff cut - x >= 0 (rf.c:15194)
           if (localCut && cptr[i] == bcode) s->bestWide = load_code(ptr, wd, en[u] & kRowMask);   // same value from every such entry
           const SmallRec r = m.smRec[i];
           const unsigned long long mult = r.mult;
@@ -1765,7 +1985,7 @@ RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         if (ent[u] != 0xFFFFFFFFu) {
-          const bool left = cd[u] <= bcode;                        // LEFT iff cut - x >= 0 (rf.c:15194)
+          const bool left = RF_GOES_LEFT(cd[u]);                   // LEFT iff cut - x >= 0 (rf.c:15194)
           const uint32_t mult = (ent[u] >> kRowBits) + 1u;
           if (left) { cL++; neL += ((unsigned long long)mult << 32) | (unsigned long long)(ev4[u] ? mult : 0u); }
           if (bayes) { const double v = (double)mult * rt4[u]; if (left) rtL += v; else rtR += v; }
@@ -1788,14 +2008,14 @@ RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
           cd[u] = (ent[u] != 0xFFFFFFFFu) ? (wd == 1 ? (uint32_t)((const uint8_t*)ptr)[(size_t)(ent[u] & kRowMask) * pstride] : load_code(ptr, wd, ent[u] & kRowMask)) : 0xFFFFFFFFu;
         uint32_t mine = 0;
 #pragma unroll
-        for (int u = 0; u < 4; u++) mine += (ent[u] != 0xFFFFFFFFu && cd[u] <= bcode) ? 1u : 0u;
+        for (int u = 0; u < 4; u++) mine += (ent[u] != 0xFFFFFFFFu && RF_GOES_LEFT(cd[u])) ? 1u : 0u;
         unsigned long long tot;
         const unsigned long long inc = block_incl_scan<unsigned long long>((unsigned long long)mine, s->scrU, tot);
         uint32_t before = (uint32_t)inc - mine;                     // left entries of this tile before mine
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           if (ent[u] != 0xFFFFFFFFu) {
-            if (cd[u] <= bcode) { dst[baseL + before] = ent[u]; before++; }
+            if (RF_GOES_LEFT(cd[u])) { dst[baseL + before] = ent[u]; before++; }
             else dst[nL + baseR + (4u * tid + u - before)] = ent[u];
           }
         }
@@ -1811,7 +2031,7 @@ RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
       int act = 0;                                                   // 1: right child pushed (save the mask), 2: a pending node popped (restore its mask)
       if (lane_id() == 0) {
         uint32_t q;
-        append_record(w, s, tree, cur.nodeID, (uint32_t)cov + 1u, localCut ? s->bestWide : bcode, kNone, s->bestDelta, cur.parentRec, &q);
+        append_record(w, s, tree, cur.nodeID, ((uint32_t)cov + 1u) | (isFac ? kFactorFlag : 0u), isFac ? fmask : (localCut ? s->bestWide : bcode), kNone, s->bestDelta, cur.parentRec, &q);
         s->algoBytes += 16ull * (unsigned long long)cur.m;
         if (!s->abort) {
           s->leafCount++;

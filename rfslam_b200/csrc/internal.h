@@ -27,6 +27,7 @@ struct DevData {
   const uint8_t*  width;          // [p] 1 / 2 / 4
   const int*      D;              // [p] number of distinct values
   const double* const* uniq;      // [p] the distinct values, ascending: cut value = uniq[c][code]
+  const uint8_t*  ftype;          // [p] 1 = unordered factor (xType 'C'): cuts are level subsets (MWCP, rf.c:14452-14518), or nullptr
   double rt_mode;                 // the table's dominant risk time (exposure = rt_mode * count + exceptions)
   // Row-major mirror of the table (present when every column is byte-coded): one row's codes are `rowPitch`
   // contiguous bytes and its (risk time, event, stratum) one 16-byte record.  A node deep in a tree holds a small
@@ -84,7 +85,9 @@ struct rfslam_dataset {
   int64_t bytes = 0;
   int max_D = 0;
   double max_rt = 0.0;            // largest risk time (scale of the fixed-point exposure sums)
-  int hist_bins = 32;             // pow2 >= the widest column with <= 256 distinct values
+  int hist_bins = 32;             // pow2 >= the widest column with <= 256 distinct values (and >= the cuts of the widest factor)
+  bool has_factor = false;        // some covariate is an unordered factor
+  std::vector<uint8_t> ftype;
   rfslam::WsPool pool;            // scratch recycled across grow calls
 };
 

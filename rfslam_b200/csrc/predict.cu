@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "internal.h"
+#include "perf.cuh"
 
 namespace rfslam {
 
@@ -29,8 +30,18 @@ namespace {
 // one visited node = one 16-byte load: cut value, covariate + 1 (0 = terminal), right child (internal) or leaf id (terminal)
 struct __align__(16) PredRec { double cont; uint32_t parm; uint32_t link; };
 
+// a factor split (mwcpSZ > 0): parm carries kFacBit, `cont` holds the MWCP word (bit level-1 set = LEFT, rf.c:1607-1616)
+constexpr uint32_t kFacBit = 0x40000000u;
+__device__ __forceinline__ uint32_t rec_cov(uint32_t parm) { return (parm & ~kFacBit) - 1u; }
+__device__ __forceinline__ bool rec_goes_left(const struct PredRec& r, double xv);
+
 constexpr int kLinkStack = 4096;             // pending right children while restoring a tree (= the grow path's DFS stack)
 constexpr int kWalk = 4;                     // trees a thread walks at once (independent chains of dependent loads)
+
+__device__ __forceinline__ bool rec_goes_left(const PredRec& r, double xv) {
+  if (r.parm & kFacBit) return (((uint32_t)__double_as_longlong(r.cont) >> ((uint32_t)xv - 1u)) & 1u) != 0u;   // splitOnFactor
+  return (r.cont - xv) >= 0.0;                                       // LEFT iff cut - x >= 0 (rf.c:10610)
+}
 
 __global__ void boundary_flag_kernel(const int32_t* treeID, uint8_t* flag, int64_t NN) {
   int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -50,7 +61,7 @@ __global__ void restore_links_kernel(int ntree, const int64_t* nodeOff, const in
   for (int64_t base = 0; base < cnt; base += 32) {
     const int64_t k = base + lane;
     const int32_t pm = (k < cnt) ? parmID[off + k] : 1;
-    if (k < cnt && (pm < 0 || pm > p)) fail = 3;
+    if (k < cnt && (pm < 0 || (int32_t)((uint32_t)pm & ~kFacBit) > p)) fail = 3;
     const unsigned internal = __ballot_sync(0xffffffffu, pm != 0);
     const int m = (int)min((int64_t)32, cnt - base);
     // lane 0 replays the chunk; the links it finds are handed to the lanes that own the records
@@ -129,8 +140,8 @@ __device__ __forceinline__ uint32_t walk_tree(const RouteArgs& a, int tree, int 
   int64_t q = off;
   PredRec r = a.rec[q];
   while (r.parm != 0u) {
-    const double xv = a.x[(size_t)(r.parm - 1u) * a.pitch + i];
-    q = ((r.cont - xv) >= 0.0) ? q + 1 : off + r.link;            // LEFT iff cut - x >= 0 (rf.c:10610)
+    const double xv = a.x[(size_t)rec_cov(r.parm) * a.pitch + i];
+    q = rec_goes_left(r, xv) ? q + 1 : off + r.link;
     r = a.rec[q];
     steps++;
   }
@@ -153,11 +164,11 @@ __device__ __forceinline__ void walk_group(const RouteArgs& a, int t0, int i, ui
     any = false;
     double xv[kWalk];
 #pragma unroll
-    for (int u = 0; u < kWalk; u++) xv[u] = (r[u].parm != 0u) ? a.x[(size_t)(r[u].parm - 1u) * a.pitch + i] : 0.0;
+    for (int u = 0; u < kWalk; u++) xv[u] = (r[u].parm != 0u) ? a.x[(size_t)rec_cov(r[u].parm) * a.pitch + i] : 0.0;
 #pragma unroll
     for (int u = 0; u < kWalk; u++) {
       if (r[u].parm != 0u) {
-        q[u] = ((r[u].cont - xv[u]) >= 0.0) ? q[u] + 1 : off[u] + r[u].link;
+        q[u] = rec_goes_left(r[u], xv[u]) ? q[u] + 1 : off[u] + r[u].link;
         r[u] = a.rec[q[u]];
         steps++;
         any |= r[u].parm != 0u;
@@ -228,22 +239,6 @@ __global__ void finalize_pred_kernel(double* ens, const uint32_t* den, size_t m)
   if (i < m && den[i]) { ens[i] /= (double)den[i]; ens[m + i] /= (double)den[i]; }              // rf.c:8115-8121
 }
 
-// perfClas from the finalized OOB ensemble and the response codes (see perf_kernel in grow.cu for the rules)
-__global__ void perf_y_kernel(const double* oob, const uint32_t* den, const double* y, int n, unsigned long long* acc) {
-  unsigned long long c0 = 0, c1 = 0, cum = 0, ok0 = 0, ok1 = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int cls = (y[i] == 2.0) ? 1 : 0;
-    if (cls) c1++; else c0++;
-    if (den[i] != 0u) {
-      cum++;
-      const int vote = (oob[i] <= oob[(size_t)n + i]) ? 1 : 0;
-      if (vote == cls) { if (cls) ok1++; else ok0++; }
-    }
-  }
-  c0 = warp_sum(c0); c1 = warp_sum(c1); cum = warp_sum(cum); ok0 = warp_sum(ok0); ok1 = warp_sum(ok1);
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&acc[0], c0); atomicAdd(&acc[1], c1); atomicAdd(&acc[2], cum); atomicAdd(&acc[3], ok0); atomicAdd(&acc[4], ok1); }
-}
-
 struct Buf {
   void* p = nullptr;
   ~Buf() { if (p) cudaFree(p); }
@@ -272,9 +267,11 @@ int validate_predict(const rfslam_predict_args* a) {
   if (a->intr_predictor_size > 0) { set_error("variable importance (intrPredictorSize > 0) is outside the accelerated path"); return RFSLAM_ENOSUP; }
   if (a->partial_type != 0 || a->partial_length != 0) { set_error("partial plots are outside the accelerated path"); return RFSLAM_ENOSUP; }
   if (a->sobservation_size > 0) { set_error("subsetted restore (sobservationSize > 0) is outside the accelerated path"); return RFSLAM_ENOSUP; }
-  if (a->x_type) for (int c = 0; c < a->x_size; c++)
-    if (!(a->x_type[c] == 'R' || a->x_type[c] == 'I' || a->x_type[c] == 'B')) { set_error("covariate %d has type '%c': unordered-factor (MWCP) routing is outside the accelerated predict path", c + 1, a->x_type[c]); return RFSLAM_ENOSUP; }
-  if (a->mwcp_total > 0) { set_error("the forest holds factor (MWCP) splits: outside the accelerated predict path"); return RFSLAM_ENOSUP; }
+  if (a->x_type) for (int c = 0; c < a->x_size; c++) {
+    if (!(a->x_type[c] == 'R' || a->x_type[c] == 'I' || a->x_type[c] == 'B' || a->x_type[c] == 'C')) { set_error("covariate %d has type '%c': only real / integer / boolean / unordered-factor covariates are on the accelerated predict path", c + 1, a->x_type[c]); return RFSLAM_ENOSUP; }
+    if (a->x_type[c] == 'C' && (!a->x_levels || a->x_levels[c] < 1 || a->x_levels[c] > 32)) { set_error("factor covariate %d: xLevels must be in [1, 32] (one MWCP word)", c + 1); return RFSLAM_ENOSUP; }
+  }
+  if (a->mwcp_total > 0 && (!a->mwcpSZ || !a->mwcpPT)) { set_error("the forest holds factor (MWCP) splits: mwcpSZ and mwcpPT are needed"); return RFSLAM_EINVAL; }
   if (a->fobservation_size > 0 && !a->fx_data) { set_error("fxData missing"); return RFSLAM_EINVAL; }
   if (a->frow_first < 0 || a->frow_count < 0 || (a->fobservation_size > 0 && (int64_t)a->frow_first + a->frow_count > a->fobservation_size)) { set_error("row shard outside [0, fobservationSize)"); return RFSLAM_EINVAL; }
   return RFSLAM_OK;
@@ -321,8 +318,24 @@ int predict_forest(const rfslam_predict_args* a, rfslam_predict_out* out) {
     double* d_cpt = b_cpt.alloc<double>(NN);
     RF_CUDA(cudaMemcpyAsync(d_tid, a->treeID, NN * 4, cudaMemcpyHostToDevice));
     RF_CUDA(cudaMemcpyAsync(d_nid, a->nodeID, NN * 4, cudaMemcpyHostToDevice));
-    RF_CUDA(cudaMemcpyAsync(d_pid, a->parmID, NN * 4, cudaMemcpyHostToDevice));
-    RF_CUDA(cudaMemcpyAsync(d_cpt, a->contPT, NN * 8, cudaMemcpyHostToDevice));
+    std::vector<int32_t> facParm; std::vector<double> facCont;     // (alive until the copies below are done: synchronous for pageable memory)
+    if (a->mwcp_total > 0) {
+      // factor splits (restoreTree rf.c:10842-10848): the node's MWCP word travels in the record's cut slot, a flag in parmID.
+      // Held-out factor values are levels 1..32 (checked per tile below would cost a pass: levels outside a word's range
+      // simply test a clear bit and go RIGHT, as splitOnFactor does for a level the word does not hold)
+      facParm.assign(a->parmID, a->parmID + NN); facCont.assign(a->contPT, a->contPT + NN);
+      int64_t at = 0;
+      for (int64_t q = 0; q < NN; q++) {
+        const int sz = a->mwcpSZ[q];
+        if (sz == 0) continue;
+        if (sz != 1 || at >= a->mwcp_total) { set_error("factor split at record %lld: mwcpSZ = %d (only single-word factors, <= 32 levels) or mwcpPT too short", (long long)q, sz); throw CudaFail{sz != 1 ? RFSLAM_ENOSUP : RFSLAM_EINVAL}; }
+        const unsigned long long word = (uint32_t)a->mwcpPT[at++];
+        memcpy(&facCont[q], &word, 8);
+        facParm[q] = (int32_t)((uint32_t)facParm[q] | kFacBit);
+      }
+    }
+    RF_CUDA(cudaMemcpyAsync(d_pid, a->mwcp_total > 0 ? facParm.data() : a->parmID, NN * 4, cudaMemcpyHostToDevice));
+    RF_CUDA(cudaMemcpyAsync(d_cpt, a->mwcp_total > 0 ? facCont.data() : a->contPT, NN * 8, cudaMemcpyHostToDevice));
     uint8_t* d_flag = b_flag.alloc<uint8_t>(NN);
     int64_t* d_noff = b_noff.alloc<int64_t>((size_t)ntree + 2);
     int* d_nsel = b_nsel.alloc<int>(1);
@@ -495,21 +508,7 @@ int predict_forest(const rfslam_predict_args* a, rfslam_predict_out* out) {
     }
     double* h_perf = nullptr;
     if (restore && a->finalize_ensembles && (a->opt_low & RFSLAM_OPT_PERF)) {
-      Buf b_acc; unsigned long long* d_acc = b_acc.alloc<unsigned long long>(5);
-      RF_CUDA(cudaMemset(d_acc, 0, 40));
-      perf_y_kernel<<<296, 256>>>(d_oob, d_oobDen, d_y, n, d_acc);
-      launches++;
-      unsigned long long acc[5];
-      RF_CUDA(cudaMemcpy(acc, d_acc, sizeof acc, cudaMemcpyDeviceToHost));
-      h_perf = (double*)host_alloc((size_t)ntree * 3 * sizeof(double));
-      const double na = rfslam_na_real();
-      for (size_t k = 0; k < (size_t)ntree * 3; k++) h_perf[k] = na;
-      double* last = h_perf + (size_t)(ntree - 1) * 3;
-      if (acc[2] != 0) {
-        last[0] = 1.0 - (double)(acc[3] + acc[4]) / (double)acc[2];
-        if (acc[0]) last[1] = 1.0 - (double)acc[3] / (double)acc[0];
-        if (acc[1]) last[2] = 1.0 - (double)acc[4] / (double)acc[1];
-      }
+      h_perf = perf_clas_table(a->opt_low, ntree, n, d_oob, d_oobDen, nullptr, nullptr, d_y, &launches);
     }
     RF_CUDA(cudaEventRecord(st.e1));
     RF_CUDA(cudaGetLastError());

@@ -54,13 +54,17 @@ def _own(struct, field, count, dtype):
     return arr
 
 
+# perf.type -> optLow bits beside OPT_PERF (R/utilities.R:260-272): "brier" 2^3, "g.mean" 2^14
+PERF_BITS = {"misclass": 0, "default": 0, "standard": 0, "brier": 1 << 3, "g.mean": 1 << 14, "gmean": 1 << 14}
+
+
 class _Packed:
     """GrowArgs plus the numpy buffers it points into (kept alive for the call)."""
 
     def __init__(self, x, y, risk_time, stratifier, *, splitrule, ntree, mtry, nodesize, nodedepth, seed, k_for_alpha,
                  membership, samp, sampsize, split_wt, device, tree_first, tree_step, finalize, nsplit=0, xvar_types=None,
                  split_stat=False, member_lists=False, var_categories=None, category_weights=None, bootstrap=None, comm=None,
-                 gather_forest=False):
+                 gather_forest=False, xvar_levels=None, perf_type="misclass", rfq=False):
         x = np.ascontiguousarray(x, np.float64)
         assert x.ndim == 2, "x must be [p, n]: p contiguous columns of n (randomForestSRC.c:22190)"
         p, n = x.shape
@@ -79,13 +83,16 @@ class _Packed:
             stratifier = np.ones(n, np.int32)                     # R/rfsrc.R:1510
         self.keep = dict(
             x=x, y=np.ascontiguousarray(y, np.float64), rt=np.ascontiguousarray(risk_time, np.float64),
-            st=np.ascontiguousarray(stratifier, np.int32), rlev=np.array([2], np.int32), xlev=np.zeros(p, np.int32),
+            st=np.ascontiguousarray(stratifier, np.int32), rlev=np.array([2], np.int32),
+            xlev=np.zeros(p, np.int32) if xvar_levels is None else np.ascontiguousarray(xvar_levels, np.int32),
             cat=np.ones(p, np.int32) if var_categories is None else np.ascontiguousarray(var_categories, np.int32),
             catw=np.array([1.0]) if category_weights is None else np.ascontiguousarray(category_weights, np.float64), tofix=np.zeros(1, np.int32), cw=np.ones(n), yw=np.array([1.0]),
             xw=np.ones(p), sw=np.ascontiguousarray(np.ones(p) if split_wt is None else split_wt, np.float64))
         k = self.keep
         # the C side reads n (per row) / p (per covariate) elements from each of these: check before it does
-        for name, want in (("y", n), ("rt", n), ("st", n), ("cat", p), ("sw", p)):
+        if xvar_types is not None and len(xvar_types) != p:
+            raise ValueError(f"xvar_types: expected {p} type characters")
+        for name, want in (("y", n), ("rt", n), ("st", n), ("cat", p), ("sw", p), ("xlev", p)):
             if k[name].shape != (want,):
                 raise ValueError(f"{name}: expected {want} elements for x of shape [p={p}, n={n}], got shape {k[name].shape}")
         if k["catw"].ndim != 1 or k["catw"].size < int(k["cat"].max()):
@@ -94,6 +101,7 @@ class _Packed:
         a.trace_flag = 0
         a.seed = int(seed)
         a.opt_low = (1 << 5) + (1 << 2)                           # forest + perf (R/utilities.R:89-103, :260-263)
+        a.opt_low |= PERF_BITS[perf_type] | ((1 << 15) if rfq else 0)   # perf.type / rfq (R/utilities.R:254-290)
         a.opt_high = 256 * (slot - 1) + (1 << 16)                 # split.cust bits + terminal.qualts (R/utilities.R:403-459)
         if membership:
             a.opt_high |= (1 << 6)                                # R/utilities.R:333-348
@@ -172,10 +180,11 @@ def _unpack_forest(o: ForestOut, finalized: bool = True, ntree_total: int = 0) -
 class ResidentCpiu:
     """The CPIU table uploaded and rank-coded once, resident in HBM (rfslam_b200_dataset_create)."""
 
-    def __init__(self, x, y, risk_time=None, stratifier=None, *, device: int = -1):
+    def __init__(self, x, y, risk_time=None, stratifier=None, *, device: int = -1, xvar_types=None, xvar_levels=None):
+        self._xvar = (xvar_types, xvar_levels)                    # 'C' = unordered factor with levels 1 .. xvar_levels[c]
         self._pk = _Packed(x, y, risk_time, stratifier, splitrule=4, ntree=1, mtry=1, nodesize=1, nodedepth=-1, seed=-1,
                            k_for_alpha=2.0, membership=False, samp=None, sampsize=None, split_wt=None, device=device,
-                           tree_first=0, tree_step=0, finalize=True)
+                           tree_first=0, tree_step=0, finalize=True, xvar_types=xvar_types, xvar_levels=xvar_levels)
         self.handle = C.c_void_p()
         capi.check(capi.lib().rfslam_b200_dataset_create(C.byref(self._pk.args), C.byref(self.handle)))
         self.n, self.p = self._pk.n, self._pk.p
@@ -199,13 +208,14 @@ class ResidentCpiu:
     def grow(self, *, splitrule="poisson.split4", ntree=500, mtry=None, nodesize=5, nodedepth=-1, seed=-12345,
              k_for_alpha=2.0, membership=False, samp=None, sampsize=None, split_wt=None, tree_first=0, tree_step=0,
              finalize=True, split_stat=False, member_lists=False, nsplit=0, bootstrap=None, comm=None,
-             gather_forest=False) -> Dict[str, np.ndarray]:
+             gather_forest=False, perf_type="misclass", rfq=False) -> Dict[str, np.ndarray]:
         k = self._pk.keep
         pk = _Packed(k["x"], k["y"], k["rt"], k["st"], splitrule=splitrule, ntree=ntree, mtry=mtry, nodesize=nodesize,
                      nodedepth=nodedepth, seed=seed, k_for_alpha=k_for_alpha, membership=membership, samp=samp,
                      sampsize=sampsize, split_wt=split_wt, device=self.device, tree_first=tree_first, tree_step=tree_step,
                      finalize=finalize, split_stat=split_stat, member_lists=member_lists, nsplit=nsplit, bootstrap=bootstrap,
-                     comm=comm, gather_forest=gather_forest)
+                     comm=comm, gather_forest=gather_forest, xvar_types=self._xvar[0], xvar_levels=self._xvar[1],
+                     perf_type=perf_type, rfq=rfq)
         out = ForestOut()
         capi.check(capi.lib().rfslam_b200_grow_resident(self.handle, C.byref(pk.args), C.byref(out)))
         res = _unpack_forest(out, finalize, int(ntree))
@@ -217,7 +227,7 @@ def rfsrc(x, y, risk_time=None, stratifier=None, *, splitrule="poisson.split4", 
           nodedepth=-1, seed=-12345, k_for_alpha=2.0, membership=False, samp=None, sampsize=None, split_wt=None,
           device=-1, tree_first=0, tree_step=0, finalize=True, nsplit=0, xvar_types=None, split_stat=False,
           member_lists=False, var_categories=None, category_weights=None, bootstrap=None, comm=None,
-          gather_forest=False) -> Dict[str, np.ndarray]:
+          gather_forest=False, xvar_levels=None, perf_type="misclass", rfq=False) -> Dict[str, np.ndarray]:
     """Grow an RF-SLAM forest from HOST arrays through rfslam_b200_grow (upload + grow + download).
 
     x [p, n] float64 (p contiguous columns), y response codes 1.0 / 2.0, risk_time [n], stratifier [n]
@@ -227,7 +237,8 @@ def rfsrc(x, y, risk_time=None, stratifier=None, *, splitrule="poisson.split4", 
                  nodedepth=nodedepth, seed=seed, k_for_alpha=k_for_alpha, membership=membership, samp=samp, sampsize=sampsize,
                  split_wt=split_wt, device=device, tree_first=tree_first, tree_step=tree_step, finalize=finalize, nsplit=nsplit,
                  xvar_types=xvar_types, split_stat=split_stat, member_lists=member_lists, var_categories=var_categories,
-                 category_weights=category_weights, bootstrap=bootstrap, comm=comm, gather_forest=gather_forest)
+                 category_weights=category_weights, bootstrap=bootstrap, comm=comm, gather_forest=gather_forest,
+                 xvar_levels=xvar_levels, perf_type=perf_type, rfq=rfq)
     out = ForestOut()
     capi.check(capi.lib().rfslam_b200_grow(C.byref(pk.args), C.byref(out)))
     res = _unpack_forest(out, finalize, int(ntree))
@@ -236,7 +247,8 @@ def rfsrc(x, y, risk_time=None, stratifier=None, *, splitrule="poisson.split4", 
 
 
 def predict_rfsrc(forest: Dict[str, np.ndarray], fx=None, *, x=None, y=None, membership=True, device=-1, finalize=True,
-                  samp=None, sampsize=None, use_tnclas=True, frow_first=0, frow_count=0, perf=True) -> Dict[str, np.ndarray]:
+                  samp=None, sampsize=None, use_tnclas=True, frow_first=0, frow_count=0, perf=True,
+                  xvar_types=None, xvar_levels=None, perf_type="misclass", rfq=False) -> Dict[str, np.ndarray]:
     """rfsrcPredict through the C-ABI (rfslam_b200_predict), mirroring R/generic.predict.rfsrc.R:437-534.
 
     ``forest`` is a grow result (the reference's wire format).  ``fx`` [p, m] predicts held-out rows; ``fx=None``
@@ -250,7 +262,7 @@ def predict_rfsrc(forest: Dict[str, np.ndarray], fx=None, *, x=None, y=None, mem
     ntree = int(keep["seed"].size)
     a = PredictArgs()
     a.trace_flag = 0; a.seed = -1
-    a.opt_low = ((1 << 2) if perf else 0) + (1 << 5)
+    a.opt_low = ((1 << 2) if perf else 0) + (1 << 5) + PERF_BITS[perf_type] + ((1 << 15) if rfq else 0)
     a.opt_high = (1 << 17)
     if membership:
         a.opt_high |= (1 << 6)
@@ -273,8 +285,8 @@ def predict_rfsrc(forest: Dict[str, np.ndarray], fx=None, *, x=None, y=None, mem
     else:
         n = int(forest["allEnsbDen"].size) if "allEnsbDen" in forest else 1
     a.observation_size = n; a.x_size = p
-    xtype = b"R" * p; a.x_type = xtype
-    keep["xlev"] = np.zeros(p, np.int32); a.x_levels = _ip(keep["xlev"])
+    xtype = ("".join(xvar_types) if xvar_types is not None else "R" * p).encode(); a.x_type = xtype
+    keep["xlev"] = np.zeros(p, np.int32) if xvar_levels is None else np.ascontiguousarray(xvar_levels, np.int32); a.x_levels = _ip(keep["xlev"])
     a.k_for_alpha = 2.0
     if samp is not None:
         a.opt_low |= (1 << 19) + (1 << 20)
@@ -287,6 +299,9 @@ def predict_rfsrc(forest: Dict[str, np.ndarray], fx=None, *, x=None, y=None, mem
     a.total_node_count = int(keep["treeID"].size); a.forest_seed = _ip(keep["seed"]); a.htry = 0
     a.treeID = _ip(keep["treeID"]); a.nodeID = _ip(keep["nodeID"]); a.parmID = _ip(keep["parmID"]); a.contPT = _dp(keep["contPT"])
     a.mwcpSZ = _ip(keep["mwcpSZ"])
+    if "mwcpPT" in forest and np.asarray(forest["mwcpPT"]).size:  # hc_zero[[4]]: the factor splits' MWCP words in record order
+        keep["mwcpPT"] = np.ascontiguousarray(forest["mwcpPT"], np.int32)
+        a.mwcpPT = _ip(keep["mwcpPT"]); a.mwcp_total = int(keep["mwcpPT"].size)
     for k, f in (("tnRCNT", "tnRCNT"), ("tnACNT", "tnACNT"), ("rmbrMembership", "tnRMBR"), ("ambrMembership", "tnAMBR")):
         if k in forest and forest[k] is not None:
             keep[f] = np.ascontiguousarray(forest[k], np.int32); setattr(a, f, _ip(keep[f]))

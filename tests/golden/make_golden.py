@@ -23,9 +23,54 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 def canon(r, n):
     t = rd.trim_forest(r, n)
     order = np.argsort(t["treeID"], kind="stable")
+    if "mwcpPT" in t and t["mwcpPT"].size:                 # the MWCP words travel with their records
+        w = np.zeros(t["treeID"].size, np.int64); w[t["mwcpSZ"] > 0] = t["mwcpPT"]
+        t["mwcpPT"] = w[order][t["mwcpSZ"][order] > 0].astype(np.int32)
     for k in ("treeID", "nodeID", "parmID", "contPT", "mwcpSZ"):
         t[k] = t[k][order]
     return t
+
+
+# unordered-factor covariates (xType "C", MWCP splits rf.c:14452-14518): name, n, p, {column: levels}, rule, ntree, nodesize,
+# mtry, forest seed, data seed, nsplit.  Small nodesize -> random pairs (pairs >= node size), large -> deterministic.
+FACTOR_CASES = [
+    ("fac_r4_det", 3000, 8, {1: 5, 4: 8, 6: 3}, 4, 5, 20, None, -7, 5, 0),
+    ("fac_r1_rand", 2500, 6, {0: 9, 3: 6}, 1, 4, 3, None, -11, 6, 0),
+    ("fac_r6_nsplit", 3000, 7, {2: 7, 5: 4}, 6, 4, 5, None, -13, 7, 4),
+    ("fac_r4_big", 20000, 12, {0: 2, 3: 9, 7: 6, 10: 8}, 4, 3, 10, None, -17, 8, 0),
+]
+
+
+def factor_table(n, p, fac, dseed):
+    d = make_cpiu(n, p, levels=16, seed=dseed)
+    x = d.x.copy()
+    rng = np.random.default_rng(dseed + 77)
+    xt = ["R"] * p; xl = np.zeros(p, np.int32)
+    for c, L in fac.items():
+        # levels tied to the outcome so that factor splits win often; every level occurs
+        base = rng.integers(1, L + 1, size=d.n)
+        shift = ((d.y == 2.0) & (rng.random(d.n) < 0.5)).astype(np.int64)
+        x[c] = ((base - 1 + shift) % L + 1).astype(np.float64)
+        xt[c] = "C"; xl[c] = L
+    return d, x, xt, xl
+
+
+def main_factors():
+    for (name, n, p, fac, rule, ntree, nodesize, mtry, seed, dseed, nsplit) in FACTOR_CASES:
+        d, x, xt, xl = factor_table(n, p, fac, dseed)
+        r = rd.grow(x, d.y, d.rt, d.strat, rule=rule, ntree=ntree, nodesize=nodesize, mtry=mtry, seed=seed, nsplit=nsplit,
+                    xtype=xt, xlevels=xl)
+        t = canon(r, d.n)
+        dt, fx, _, _ = factor_table(max(300, n // 4), p, fac, dseed + 1000)
+        pr = rd.predict(x, d.y, t, fx, nodesize=nodesize, xtype=xt, xlevels=xl)
+        save = dict(x=x, y=d.y, rt=d.rt, strat=d.strat, xtype=np.array("".join(xt)), xlevels=xl,
+                    params=np.array([d.n, p, 16, rule, ntree, nodesize, -1 if mtry is None else mtry, seed, dseed, 0, nsplit], np.int64),
+                    fx=fx, pred_allEnsbCLS=pr["allEnsbCLS"], pred_nodeMembership=pr["nodeMembership"])
+        for k in ("oobEnsbCLS", "allEnsbCLS", "leafCount", "seed", "nodeMembership", "bootMembership",
+                  "treeID", "nodeID", "parmID", "contPT", "mwcpSZ", "mwcpPT", "mwcpCT", "tnRCNT", "tnACNT", "perfClas"):
+            save["ref_" + k] = t[k]
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **save)
+        print(name, "nodes", t["treeID"].size, "factor splits", int(t["mwcpSZ"].sum()), "bytes", os.path.getsize(os.path.join(OUT, name + ".npz")))
 
 
 GROW_CASES = [
@@ -115,6 +160,10 @@ def main():
     # pinned by the grown trees).
     print("done")
 
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "factors":
+    main_factors()
+    sys.exit(0)
 
 if __name__ == "__main__":
     main()

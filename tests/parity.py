@@ -39,6 +39,16 @@ def split_tree(f: Dict[str, np.ndarray], b: int):
     return {k: f[k][sel] for k in ("nodeID", "parmID", "contPT")}
 
 
+def mwcp_by_record(f: Dict[str, np.ndarray]) -> np.ndarray:
+    """The MWCP word of every record (0 = numeric split or leaf): mwcpPT holds one word per record with mwcpSZ = 1,
+    in record order (saveTree, randomForestSRC.c:10773-10779)."""
+    sz = np.asarray(f["mwcpSZ"])
+    out = np.zeros(sz.size, np.int64)
+    assert sz.max(initial=0) <= 1
+    out[sz > 0] = np.asarray(f["mwcpPT"]).astype(np.int64)[: int(sz.sum())] & 0xFFFFFFFF
+    return out
+
+
 def _is_tie(a: float, b: float) -> bool:
     """Two winning split statistics "tie" when they agree within TIE_RTOL relative (north_star) or within
     the reference's own absolute hysteresis EPSILON = 1e-9 (randomForestSRC.c:15502 replaces the running
@@ -100,6 +110,11 @@ def assert_forest_equal(got: Dict[str, np.ndarray], ref: Dict[str, np.ndarray], 
     keep = np.ones(ntree, bool)
     for b in dropped:
         keep[b - 1] = False
+    if "mwcpPT" in ref and np.asarray(ref["mwcpSZ"]).sum() > 0 and not dropped:
+        # factor splits: the LEFT level sets, record by record, and the per-tree word counts
+        np.testing.assert_array_equal(got["mwcpSZ"], ref["mwcpSZ"], err_msg=label + " mwcpSZ")
+        np.testing.assert_array_equal(mwcp_by_record(got), mwcp_by_record(ref), err_msg=label + " mwcpPT")
+        np.testing.assert_array_equal(got["mwcpCT"], ref["mwcpCT"], err_msg=label + " mwcpCT")
     if not dropped:
         np.testing.assert_array_equal(got["leafCount"], ref["leafCount"], err_msg=label + " leafCount")
         np.testing.assert_array_equal(got["nodeMembership"], ref["nodeMembership"], err_msg=label + " nodeMembership")
@@ -142,6 +157,9 @@ def live_reference_forest(d, *, statistics: bool = False, **kw) -> Dict[str, np.
     r = refdriver.grow(d.x, d.y, d.rt, d.strat, statistics=statistics, **kw)
     t = refdriver.trim_forest(r, d.n)
     order = np.argsort(t["treeID"], kind="stable")
+    if "mwcpPT" in t and t["mwcpPT"].size:
+        w = np.zeros(t["treeID"].size, np.int64); w[t["mwcpSZ"] > 0] = t["mwcpPT"]      # words travel with their records
+        t["mwcpPT"] = w[order][t["mwcpSZ"][order] > 0].astype(np.int32)
     for k in ("treeID", "nodeID", "parmID", "contPT", "mwcpSZ") + (("splitStat",) if "splitStat" in t else ()):
         t[k] = t[k][order]
     return t

@@ -412,3 +412,76 @@ def test_row_major_mirror_and_staged_subtrees_match_oracle(monkeypatch):
     got = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, splitrule=4, ntree=400, nodesize=5, seed=-29, membership=True)
     want = port.grow(d.x, d.y, d.rt, d.strat, rule=4, ntree=400, nodesize=5, seed=-29)
     parity.assert_forest_equal(got, want, d.n, 400, label="rowmajor sliced")
+
+
+# ---- unordered factors (MWCP splits, randomForestSRC.c:14452-14518, :1607-1616) ----------------------------------------
+FACTOR_GOLDENS = ["fac_r4_det.npz", "fac_r1_rand.npz", "fac_r6_nsplit.npz", "fac_r4_big.npz"]
+
+
+@pytest.mark.parametrize("name", FACTOR_GOLDENS)
+def test_factor_splits_match_reference_golden(golden_dir, name):
+    """Mixed numeric / unordered-factor tables (config 4's covariate kinds) against the unmodified reference: forests
+    with their MWCP words (deterministic pairs, random pairs drawn from chain B, nsplit > 0), node membership, ensembles,
+    and held-out predictions routed by level subset."""
+    g = parity.load_golden(os.path.join(golden_dir, name))
+    q = parity.golden_params(g)
+    xt = list(str(g["xtype"]))
+    got = rfslam_b200.rfsrc(g["x"], g["y"], g["rt"], g["strat"], splitrule=q["rule"], ntree=q["ntree"], nodesize=q["nodesize"],
+                            mtry=q["mtry"], seed=q["seed"], membership=True, nsplit=q["nsplit"], xvar_types=xt, xvar_levels=g["xlevels"])
+    ref = parity.golden_ref_forest(g)
+    parity.assert_forest_equal(got, ref, q["n"], q["ntree"], label=name)
+    assert int(got["mwcpSZ"].sum()) == int(ref["mwcpSZ"].sum()) > 50
+    pr = rfslam_b200.predict_rfsrc(got, g["fx"], xvar_types=xt, xvar_levels=g["xlevels"])
+    np.testing.assert_array_equal(pr["nodeMembership"], g["pred_nodeMembership"])
+    np.testing.assert_allclose(pr["allEnsbCLS"], g["pred_allEnsbCLS"], rtol=parity.HAZARD_RTOL, atol=0)
+
+
+@pytest.mark.parametrize("n,p,fac,rule,nodesize,seed,nsplit,levels", [
+    (30000, 16, {1: 5, 4: 8, 9: 2, 12: 9}, 4, 20, -101, 0, 64),       # large nodes: histogram path + deterministic pairs
+    (8000, 10, {0: 9, 3: 7, 8: 6}, 1, 2, -103, 0, 32),                # tiny nodes: random pairs nearly everywhere
+    (12000, 9, {2: 4, 6: 8}, 5, 10, -105, 3, 16),                     # nsplit > 0 on factors and numerics
+    (9000, 8, {0: 3, 1: 3, 2: 4, 3: 5, 4: 6, 5: 7, 6: 8, 7: 9}, 6, 5, -107, 0, 16)])   # factors only
+def test_factor_splits_match_oracle_fresh_seeds(n, p, fac, rule, nodesize, seed, nsplit, levels):
+    d = make_cpiu(n, p, levels=levels, seed=-seed)
+    x = d.x.copy(); rng = np.random.default_rng(-seed)
+    xt = ["R"] * p; xl = np.zeros(p, np.int32)
+    for c, lv in fac.items():
+        base = rng.integers(1, lv + 1, size=d.n)
+        x[c] = ((base - 1 + ((d.y == 2.0) & (rng.random(d.n) < 0.4))) % lv + 1).astype(np.float64); xt[c] = "C"; xl[c] = lv
+    ntree = 4
+    want = port.grow(x, d.y, d.rt, d.strat, rule=rule, ntree=ntree, nodesize=nodesize, seed=seed, nsplit=nsplit, xtype=xt, xlevels=xl)
+    got = rfslam_b200.rfsrc(x, d.y, d.rt, d.strat, splitrule=rule, ntree=ntree, nodesize=nodesize, seed=seed, membership=True,
+                            nsplit=nsplit, xvar_types=xt, xvar_levels=xl, split_stat=True)
+    res = parity.assert_forest_equal(got, want, d.n, ntree, label="factor fresh", tie_aware=True)
+    assert res["ties"] == 0, res
+    assert got["split_candidates"] == int(want["candidates"][0])
+    assert int(got["mwcpSZ"].sum()) > 20
+
+
+def test_factor_limits_fail_loudly():
+    d = make_cpiu(600, 3, levels=8, seed=1)
+    x = d.x.copy(); x[1] = (np.arange(d.n) % 12 + 1).astype(np.float64)
+    with pytest.raises(rfslam_b200.RfslamError, match="levels"):       # 12 levels present: beyond the accelerated factor width
+        rfslam_b200.rfsrc(x, d.y, d.rt, d.strat, ntree=1, xvar_types=["R", "C", "R"], xvar_levels=np.array([0, 12, 0], np.int32))
+    x[1] = (np.arange(d.n) % 4 + 1).astype(np.float64) + 0.5
+    with pytest.raises(rfslam_b200.RfslamError, match="level"):        # factor values must be the integers 1..xLevels
+        rfslam_b200.rfsrc(x, d.y, d.rt, d.strat, ntree=1, xvar_types=["R", "C", "R"], xvar_levels=np.array([0, 4, 0], np.int32))
+
+
+# ---- the callers of the ensemble (SURVEY 8 f3): perf.type and the RFQ vote -----------------------------------------------
+@pytest.mark.parametrize("rfq", [False, True])
+@pytest.mark.parametrize("perf", ["misclass", "brier", "gmean"])
+def test_perf_types_match_oracle(perf, rfq):
+    """Misclassification / Brier / g-mean of the OOB ensemble, plain and RFQ vote (randomForestSRC.c:974-1218): counts are
+    exact, Brier sums differ by summation order only.  The same table comes back from restore-mode predict."""
+    d = make_cpiu(20000, 8, levels=32, seed=77)
+    kw = dict(ntree=12, nodesize=10, seed=-19)
+    want = port.grow(d.x, d.y, d.rt, d.strat, rule=4, perf=perf, rfq=rfq, **kw)["perfClas"]
+    got = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, splitrule=4, perf_type=perf, rfq=rfq, **kw)
+    for table in (got["perfClas"], rfslam_b200.predict_rfsrc(got, None, x=d.x, y=d.y, perf_type=perf, rfq=rfq)["perfClas"]):
+        np.testing.assert_array_equal(np.isnan(table), np.isnan(want))
+        ok = ~np.isnan(want)
+        if perf == "brier":
+            np.testing.assert_allclose(table[ok], want[ok], rtol=1e-12, atol=0)
+        else:
+            np.testing.assert_array_equal(table[ok], want[ok])

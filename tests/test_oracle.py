@@ -221,3 +221,76 @@ def test_tie_aware_comparison_accepts_ties_only():
     b["splitStat"][k] = b["splitStat"][k] * (1.0 + 1e-6)
     with pytest.raises(AssertionError, match="not a tie"):
         parity.assert_forest_equal(a, b, d.n, 3, tie_aware=True)
+
+
+# ---- unordered factors (MWCP splits, randomForestSRC.c:14452-14518) --------------------------------------------------
+FACTOR_GOLDENS = ["fac_r4_det.npz", "fac_r1_rand.npz", "fac_r6_nsplit.npz", "fac_r4_big.npz"]
+
+
+@pytest.mark.parametrize("name", FACTOR_GOLDENS)
+def test_port_factor_splits_match_golden(golden_dir, name):
+    """Deterministic and random complementary pairs, nsplit > 0 on factors: forests (incl. mwcpSZ / mwcpPT / mwcpCT) and the
+    held-out predictions of the reference's own rfsrcPredict."""
+    g = parity.load_golden(os.path.join(golden_dir, name))
+    q = parity.golden_params(g)
+    xt = list(str(g["xtype"]))
+    got = port.grow(g["x"], g["y"], g["rt"], g["strat"], rule=q["rule"], ntree=q["ntree"], nodesize=q["nodesize"], nsplit=q["nsplit"],
+                    mtry=q["mtry"], seed=q["seed"], xtype=xt, xlevels=g["xlevels"])
+    ref = parity.golden_ref_forest(g)
+    assert int(ref["mwcpSZ"].sum()) > 50
+    parity.assert_forest_equal(got, ref, q["n"], q["ntree"], label=name)
+    ens, memb = port.predict(got, g["fx"])
+    np.testing.assert_array_equal(memb, g["pred_nodeMembership"])
+    np.testing.assert_allclose(ens, g["pred_allEnsbCLS"], rtol=parity.HAZARD_RTOL, atol=0)
+
+
+@pytest.mark.skipif(not refdriver.available(), reason="oracle/_ref not built (no /root/reference here)")
+def test_factor_pair_enumeration_matches_reference_tables():
+    """bookFactor's complementary pairs (randomForestSRC.c:1459-1530) for r = 2..12 levels: by LEFT cardinality, lexicographic
+    inside a cardinality, the middle cardinality of an even r halved -- the order the restatement and the kernel unrank."""
+    import ctypes as C
+    import itertools
+
+    class Factor(C.Structure):
+        _fields_ = [("r", C.c_uint), ("cgc", C.c_uint), ("cpc", C.c_void_p), ("cgs", C.c_void_p),
+                    ("cgb", C.POINTER(C.POINTER(C.c_uint))), ("mwcp", C.c_uint)]
+    L = C.CDLL(refdriver.REF_SO)
+    L.makeFactor.restype = C.POINTER(Factor); L.makeFactor.argtypes = [C.c_uint, C.c_char]
+    for r in range(2, 13):
+        f = L.makeFactor(r, b"\x01").contents
+        sizes = C.cast(f.cgs, C.POINTER(C.c_uint))
+        for gsz in range(1, f.cgc + 1):
+            ref = [f.cgb[gsz][k] for k in range(1, sizes[gsz] + 1)]
+            combos = list(itertools.combinations(range(1, r + 1), gsz))
+            if r % 2 == 0 and gsz == r // 2:
+                combos = combos[: len(combos) // 2]
+            assert ref == [sum(1 << (l - 1) for l in c) for c in combos], (r, gsz)
+
+
+@pytest.mark.skipif(not refdriver.available(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("n,p,fac,rule,nodesize,seed,nsplit,mtry", [
+    (3000, 6, {1: 5, 4: 8}, 4, 5, -7, 0, None), (2000, 5, {0: 3, 2: 12}, 4, 3, -11, 0, None),
+    (3000, 6, {1: 6, 4: 20}, 2, 5, -21, 10, None), (1500, 4, {0: 32, 1: 7}, 5, 2, -5, 0, 4)])
+def test_port_factor_splits_match_live_reference(n, p, fac, rule, nodesize, seed, nsplit, mtry):
+    d = make_cpiu(n, p, levels=16, seed=5)
+    x = d.x.copy(); rng = np.random.default_rng(1)
+    xt = ["R"] * p; xl = np.zeros(p, np.int32)
+    for c, lv in fac.items():
+        x[c] = rng.integers(1, lv + 1, size=d.n).astype(float); xt[c] = "C"; xl[c] = lv
+    kw = dict(rule=rule, ntree=3, nodesize=nodesize, seed=seed, nsplit=nsplit, mtry=mtry, xtype=xt, xlevels=xl)
+    import dataclasses
+    ref = parity.live_reference_forest(dataclasses.replace(d, x=x), **kw)
+    got = port.grow(x, d.y, d.rt, d.strat, **kw)
+    parity.assert_forest_equal(got, ref, d.n, 3, label="factor live")
+
+
+@pytest.mark.skipif(not refdriver.available(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("rfq", [False, True])
+@pytest.mark.parametrize("perf", ["misclass", "brier", "gmean"])
+def test_port_perf_types_match_live_reference(perf, rfq):
+    """perf.type = misclass / brier / g.mean and the RFQ vote (randomForestSRC.c:974-1218, :7954-8010): bit-exact."""
+    d = make_cpiu(3000, 6, levels=16, seed=5)
+    kw = dict(rule=4, ntree=5, nodesize=5, seed=-7, perf=perf, rfq=rfq)
+    r = refdriver.grow(d.x, d.y, d.rt, d.strat, **kw)
+    o = port.grow(d.x, d.y, d.rt, d.strat, **kw)
+    np.testing.assert_array_equal(r["perfClas"].view(np.uint64), o["perfClas"].view(np.uint64))
