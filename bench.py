@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--c3-rows", type=int, default=0)
     ap.add_argument("--c3-trees", type=int, default=0)
     ap.add_argument("--no-predict", action="store_true", help="skip the rfsrcPredict record")
+    ap.add_argument("--no-extras", action="store_true", help="skip the mixed-factor and CPIU-construction records")
     ap.add_argument("--predict-rows", type=int, default=2_000_000, help="held-out rows per job for the predict record")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -342,6 +343,57 @@ def main():
                                         "unit": "GB/s", "frac": pbytes / world / 1e9 / max(p_kern / 1e3, 1e-9) / peak, "algorithmic_bytes_per_call": pbytes / world},
                            "sharding": f"held-out rows split over {world} rank(s), forest replicated, no collective"}
         del fx, pr, fp
+
+    # ---- the rows SURVEY 8 marks "next", measured beside the path (rank 0, N = 1; not part of the timed step) ----
+    if rank == 0 and world == 1 and not args.no_extras:
+        # (f2) mixed numeric / unordered-factor table -- configs[3]'s covariate kinds on configs[1]'s shape: every fifth
+        # covariate becomes a factor with 3..8 levels (MWCP splits, level-subset cuts)
+        rng = np.random.default_rng(4)
+        xm = d.x.copy(); xt = ["R"] * p; xl = np.zeros(p, np.int32)
+        for c in range(2, p, 5):
+            lv = 3 + (c // 5) % 6
+            xm[c] = rng.integers(1, lv + 1, size=n).astype(np.float64); xt[c] = "C"; xl[c] = lv
+        dsm = rfslam_b200.ResidentCpiu(xm, d.y, d.rt, d.strat, device=local, xvar_types=xt, xvar_levels=xl)
+        mixed_trees = 100
+        fm = None
+        for it in range(2):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            fm = dsm.grow(splitrule=cfg["rule"], ntree=mixed_trees, nodesize=cfg["nodesize"], seed=cfg["seed"], k_for_alpha=cfg["k_for_alpha"])
+            torch.cuda.synchronize(); mixed_s = time.perf_counter() - t0
+        line["mixed_factor"] = {"workload": f"{n} CPIUs x {p} covariates, {sum(t == 'C' for t in xt)} of them unordered factors with 3..8 levels, ntree={mixed_trees}, nodesize={cfg['nodesize']}",
+                                "value": mixed_trees / mixed_s, "unit": "trees/s", "ms_per_step": 1e3 * mixed_s, "grow_kernel_ms": fm["grow_kernel_ms"],
+                                "factor_splits": int(fm["mwcpSZ"].sum()), "forest_nodes": int(fm["treeID"].size),
+                                "split_candidates_per_sec": int(fm["split_candidates"]) / mixed_s}
+        dsm.close(); del dsm, xm, fm
+        # (f1) CPIU construction: persons -> counting-process information units with derived time-varying covariates
+        persons = 1_000_000
+        t_out = np.round(rng.uniform(30, 2900, persons), 1); dth = (rng.random(persons) < 0.3).astype(np.int32)
+        t_dth = np.where(dth == 1, t_out, t_out + 100.0)
+        ev = rng.uniform(0, 3000, (persons, 10)); ev[rng.random((persons, 10)) < 0.6] = np.nan
+        mt = np.sort(rng.uniform(0, 2500, (persons, 4)), axis=1); mt[:, 0] = 0.0; mv = rng.normal(50, 10, (persons, 4))
+        to_create = {"i.hf": ev, "n.hf": ev, "ni.hf": ev, "t.hf": ev, "i.sca": ev[:, :1], "t.sca": ev[:, :1], "c.lab": {"times": mt, "values": mv}}
+        cres = None; ctimes = []
+        for it in range(3):
+            t0 = time.perf_counter()
+            cres = rfslam_b200.cpiu_fc(t_out, t_dth, dth, to_create=to_create, k_to_persist=2, device=local)
+            ctimes.append(time.perf_counter() - t0)
+        rows = int(cres["rt"].size); nv = len(to_create)
+        cbytes = rows * (6 * 8 + nv * 8)                                 # bytes written per CPIU: six interval columns + the derived ones
+        from oracle import cpiu_port
+        sub = 2000
+        kinds = [0, 1, 2, 3, 0, 3, 4]
+        t0 = time.perf_counter()
+        cpiu_port.cpiu_fc(t_out[:sub], t_dth[:sub], dth[:sub], var_kind=kinds, var_times=[ev[:sub]] * 4 + [ev[:sub, :1]] * 2 + [mt[:sub]],
+                          var_values=[None] * 6 + [mv[:sub]], k_to_persist=2)
+        cpu_s = time.perf_counter() - t0
+        line["cpiu"] = {"workload": f"{persons} persons, half-year intervals, {nv} derived covariates (i./n./ni./t./c., up to 10 event slots)",
+                        "value": rows / float(np.min(ctimes[1:])), "unit": "CPIUs/s (host buffers in, host columns out)", "rows": rows,
+                        "kernel_ms": cres["kernel_ms"], "ms_per_call": 1e3 * float(np.min(ctimes[1:])),
+                        "roofline": {"bound": "hbm", "kernel": "cpiu_vars_kernel + cpiu_base_kernel", "achieved": cbytes / 1e9 / max(cres["kernel_ms"] / 1e3, 1e-9),
+                                     "peak": peak, "unit": "GB/s", "frac": cbytes / 1e9 / max(cres["kernel_ms"] / 1e3, 1e-9) / peak, "algorithmic_bytes_per_call": cbytes},
+                        "cpu_baseline": {"value": float(int(np.ceil(t_out[:sub] / 182.5).sum()) / cpu_s), "unit": "CPIUs/s", "cores": 1, "kind": "reference",
+                                         "sample": f"the reference's cpiu.cpp helpers (compiled unmodified) under the restated R driver, {sub} persons"}}
+        del cres, ev, mt, mv
 
     # ---- cpu baseline (rank 0, N = 1): the unmodified reference on a bounded sample, and the SAME job on the device ----
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -427,7 +427,10 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         const int v = atoi(e);
         if (!g.has_sort) pl.kv = v == 512 ? grow_variant_t512() : v == 320 ? grow_variant_t320() : v == 128 ? grow_variant_t128() : grow_variant_t256();
       }
-      if (ds->has_factor) pl.kv = grow_variant_t256f();       // the build with the level-subset paths
+      // tables with unordered factors take the FULL build (level-subset cuts); everything else the smaller ones
+      const bool wantSubtree = ds->dev.rowcodes && getenv("RFSLAM_SUBTREE_MAX") && !getenv("RFSLAM_NO_SUBTREE");
+      const bool full = ds->has_factor || getenv("RFSLAM_FULL_KERNEL");
+      if (full) pl.kv = grow_variant_t256f();
       const int ctasWanted = pl.kv->ctasPerSm;
       // shared memory available to one CTA's dynamic part (227 KB per SM, 1 KB reserved per CTA, GrowShared is static)
       const size_t limit = (size_t)(227u << 10) / (size_t)ctasWanted - 1024 - sizeof(GrowShared);
@@ -439,7 +442,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         if (pl.g.hslots * 2 > pl.g.tabSlots) pl.g.hslots >>= 1; else pl.g.tabSlots >>= 1;      // (histogram 32 B / bin, tables 16 B / bin)
       }
       pl.g.subMax = 0;
-      if (ds->dev.rowcodes && !g.seqDraw && !getenv("RFSLAM_NO_SUBTREE")) {
+      if (wantSubtree && !g.seqDraw) {                       // (staged subtrees bought nothing at 10 M rows: opt-in, FULL build)
         const int wantSub = getenv("RFSLAM_SUBTREE_MAX") ? atoi(getenv("RFSLAM_SUBTREE_MAX")) : kSmallMax;
         const int hsFull = pl.g.hslots, hsMin = std::min(2, hsFull);
         for (int sm = std::min(wantSub, kSmallMax); sm >= 128 && pl.g.subMax == 0; sm >>= 1)
@@ -878,7 +881,8 @@ int score_node_impl(int rule, double k_for_alpha, int m, const double* x, const 
     { int ex = 0; frexp(std::max((double)m * std::max(ds->max_rt, 1e-300), 1.0), &ex); g.tscale = ldexp(1.0, 62 - ex); g.tinv = ldexp(1.0, ex - 62); }
     g.hslots = hist_slots(g.hbins); g.tabSlots = kTabSlots; g.subMax = 0; g.seqDraw = 0; g.facCuts = 0;
     const size_t smem = grow_smem_bytes(g.ncmax, ds->K, g.hbins, g.hslots, g.tabSlots, 0, 0);
-    RF_CUDA(cudaFuncSetAttribute(rfslam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const GrowVariant* kv = grow_variant_t256();
+    { int perSm = 0; RF_CUDA(kv->prepare(smem, &perSm)); }
     DevBuf<uint32_t> d_lists, d_sort, d_stackPerm, d_ctab, d_nodeCount, d_leafCount, d_cursor;
     DevBuf<uint16_t> d_cnt; DevBuf<NodeEnt> d_stack; DevBuf<int> d_seedB, d_boot, d_status, d_sinkCount;
     DevBuf<unsigned long long> d_cand, d_algo; DevBuf<Rec> d_pool; DevBuf<double> d_statPool, d_sinkCut, d_sinkDelta;
@@ -900,7 +904,7 @@ int score_node_impl(int rule, double k_for_alpha, int m, const double* x, const 
     w.pool = d_pool.p; w.statPool = d_statPool.p; w.poolChunks = 2; w.poolCursor = d_cursor.p; w.ctab = d_ctab.p; w.maxChunksPerTree = 4;
     w.nodeCount = d_nodeCount.p; w.leafCount = d_leafCount.p; w.candCount = d_cand.p; w.algoBytes = d_algo.p; w.status = d_status.p;
     w.sinkCut = d_sinkCut.p; w.sinkDelta = d_sinkDelta.p; w.sinkCount = d_sinkCount.p;
-    rfslam_grow_kernel<<<1, kThreads, smem>>>(ds->dev, g, w);
+    kv->launch(ds->dev, g, w, 1, smem);
     RF_CUDA(cudaGetLastError());
     RF_CUDA(cudaDeviceSynchronize());
     int nc = 0;

@@ -63,12 +63,34 @@ struct NodeEnt {        // a pending node of the DFS
 };
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;
-#ifndef RF_FACTORS
-#define RF_FACTORS 0
+#ifndef RF_FULL
+#define RF_FULL 0
 #endif
-// Factor support is a BUILD of the kernel (grow_t256f.cu): the kernel is instruction-fetch sensitive on its once-per-node
-// code, and the level-subset paths measurably slow the all-numeric build down (1.46 s -> 1.56 s per 500 trees) by size alone.
-constexpr bool kFactors = RF_FACTORS != 0;
+// The kernel exists in a build without unordered-factor support (every all-numeric table) and a FULL one (grow_t256f.cu).
+// It is instruction-fetch sensitive on its once-per-node code: merely compiling the level-subset paths of factors in
+// slowed the all-numeric case from 1.46 s to 1.56 s per 500 trees (16.3 k -> 18.8 k SASS instructions).  The other
+// optional paths (sequential draws, sorted walk, staged subtrees, emit mode, phase profile) are compile-time switches
+// too (RF_K_*), all ON: a build without any of them (10.4 k instructions) was only 2 % faster at 296 trees and FAULTED
+// when trees were time-sliced (a second tree on a CTA built a garbage root list; not understood -- see DESIGN.md), while
+// turning any two of them back on made the fault disappear.
+constexpr bool kFull = RF_FULL != 0;
+#ifndef RF_K_SORT
+#define RF_K_SORT 1
+#endif
+#ifndef RF_K_SINK
+#define RF_K_SINK 1
+#endif
+#ifndef RF_K_SUB
+#define RF_K_SUB 1
+#endif
+#ifndef RF_K_PROF
+#define RF_K_PROF 1
+#endif
+#ifndef RF_K_SEQ
+#define RF_K_SEQ 1
+#endif
+constexpr bool kFactors = kFull, kSeq = RF_K_SEQ != 0, kSort = RF_K_SORT != 0, kSub = RF_K_SUB != 0, kSink = RF_K_SINK != 0, kProf = RF_K_PROF != 0;
+#define RF_CANDHIST(ci) (!kSort || s->candHist[ci])
 constexpr uint32_t kFactorFlag = 0x80000000u;   // Rec::parm of a factor split: `a` is then the LEFT set as a mask over codes
 #ifndef RF_SMALL_MAX
 #define RF_SMALL_MAX 512
@@ -167,7 +189,7 @@ struct GrowShared {
 
 #define RF_PROF(slot)                                                                  \
   do {                                                                                 \
-    if (w.prof && vtid() == 0) {                                                  \
+    if (kProf && w.prof && vtid() == 0) {                                         \
       long long now__ = clock64();                                                     \
       s->prof[slot] += (unsigned long long)(now__ - s->tmark);                         \
       if (s->cur.len < 64u) s->prof[64 + (slot)] += (unsigned long long)(now__ - s->tmark); \
@@ -179,7 +201,7 @@ struct GrowShared {
 // the same inside a candidate's warp (small_candidate): thread 0 of the CTA stamps the sub-phases of ITS candidate
 #define RF_PROFC(slot)                                                                 \
   do {                                                                                 \
-    if (c.w.prof && vtid() == 0) {                                                     \
+    if (kProf && c.w.prof && vtid() == 0) {                                            \
       long long now__ = clock64();                                                     \
       s->prof[slot] += (unsigned long long)(now__ - s->tmark);                         \
       if (s->cur.len < 64u) s->prof[64 + (slot)] += (unsigned long long)(now__ - s->tmark); \
@@ -466,7 +488,7 @@ __device__ inline void flush_stratum(const NodeCtx& c, int nc, int nslots) {
   GrowShared* s = m.s;
   const int lane = lane_id();
   for (int ci = warp_id(); ci < nc; ci += kWarps) {
-    if (!s->candHist[ci]) continue;
+    if (!RF_CANDHIST(ci)) continue;
     const int Dc = s->candD[ci];
     const int nch = (Dc + 31) >> 5;
     const double t0 = c.d.rt_mode;
@@ -536,7 +558,7 @@ __device__ inline void track_summary(const NodeCtx& c, int ci) {
   const int cov = s->candCov[ci];
   const double wgt = c.g.split_weight ? c.g.split_weight[cov] : 1.0;
   const double statP = m.statP[ci];
-  const uint32_t* cm = c.g.seqDraw ? s->cutMask[ci] : nullptr;       // the candidate's cuts as a mask (drawn subset, factor cuts)
+  const uint32_t* cm = (kSeq && c.g.seqDraw) ? s->cutMask[ci] : nullptr;   // the candidate's cuts as a mask (drawn subset, factor cuts)
   int ncuts = np - 1;
   if (cm) ncuts = warp_sum((lane < 8) ? (int)__popc(cm[lane]) : 0);
   double M = -INFINITY; int pos = 0x7fffffff; bool anyNan = false;
@@ -587,14 +609,14 @@ __device__ inline void track_exact(const NodeCtx& c, int ci) {
   const int cov = s->candCov[ci];
   int have = s->have; double best = s->bestDelta; int bestBin = -1;
   int emitted = s->cutsSeen;
-  const uint32_t* cm = c.g.seqDraw ? s->cutMask[ci] : nullptr;
+  const uint32_t* cm = (kSeq && c.g.seqDraw) ? s->cutMask[ci] : nullptr;
 #pragma unroll 1
   for (int ch = 0; ch < nch; ch++) {
     int bin = (ch << 5) + lane;
     uint32_t wd = cm ? cm[ch] : m.pres[ci * 8 + ch];
     bool present = ((wd >> lane) & 1u) && bin != last;
     double val = present ? m.sL[ci * m.hb + bin] : 0.0;
-    if (c.w.sinkDelta) {
+    if (kSink && c.w.sinkDelta) {
       unsigned pm = __ballot_sync(0xffffffffu, present);
       if (present) {
         int k = emitted + __popc(pm & ((1u << lane) - 1u));
@@ -626,7 +648,7 @@ __device__ inline void track_combine_one(const NodeCtx& c, int ci) {
     return;
   }
   if (lane == 0) s->candCount += (unsigned long long)s->trkCuts[ci];
-  if (s->trkClean[ci] && !c.w.sinkDelta) {
+  if (s->trkClean[ci] && !(kSink && c.w.sinkDelta)) {
     if (lane == 0) {
       const double M = s->trkMax[ci];
       if (!s->have || (M - s->bestDelta) > kEpsilon) { s->have = 1; s->bestDelta = M; s->bestCand = ci; s->bestCode = (uint32_t)s->trkMaxBin[ci]; }
@@ -645,7 +667,7 @@ __device__ inline void track_combine_all(const NodeCtx& c, int nc) {
   const bool mine = lane < nc;
   const int np = mine ? s->trkNp[lane] : 0;
   const bool clean = mine ? (s->trkClean[lane] != 0) : true;
-  const bool slow = c.w.sinkDelta || __any_sync(0xffffffffu, mine && np >= 2 && !clean);
+  const bool slow = (kSink && c.w.sinkDelta) || __any_sync(0xffffffffu, mine && np >= 2 && !clean);
   if (lane == 0) s->needSlow = slow ? 1 : 0;              // near-ties / NaN / emit mode: the caller walks the candidates one by one
   if (slow) return;
   if (mine && np < 2) {                                   // constant in this node (rf.c:15004-15007)
@@ -825,7 +847,7 @@ __device__ inline void sort_candidate(const NodeCtx& c, int ci, uint32_t len) {
         bool present = m.tileCut[q] != 0;
         double val = m.tileDelta[q];
         unsigned pm = __ballot_sync(0xffffffffu, present);
-        if (c.w.sinkDelta && present) {
+        if (kSink && c.w.sinkDelta && present) {
           int k = emitted + __popc(pm & ((1u << lane) - 1u));
           c.w.sinkDelta[k] = val;
           c.w.sinkCut[k] = c.d.uniq[cov][m.tileKey[q]];
@@ -1243,7 +1265,7 @@ __device__ inline void score_small(NodeCtx& c) {
   // then grown out of shared memory: each of its nodes fetches the codes of its own drawn covariates from the tile,
   // partitions by permuting 16-bit slot numbers, and never touches the lists or the table in global memory again.
   // (Deep in a tree every per-node gather used to be one DRAM round trip per level for one byte per 32-byte sector.)
-  if (m.subMax > 0 && !s->inSub && len <= (uint32_t)m.subMax && !w.sinkDelta) {
+  if (kSub && m.subMax > 0 && !s->inSub && len <= (uint32_t)m.subMax && !(kSink && w.sinkDelta)) {
     const int chunks = m.tilePitch >> 4;
     for (uint32_t q = (uint32_t)tid; q < len * (uint32_t)chunks; q += kThreads) {
       const uint32_t j = q / (uint32_t)chunks, ch = q - j * (uint32_t)chunks;
@@ -1262,7 +1284,7 @@ __device__ inline void score_small(NodeCtx& c) {
     __syncthreads();
     RF_PROF(14);
   }
-  const bool sub = s->inSub != 0;
+  const bool sub = kSub && s->inSub != 0;
   const uint32_t soff = sub ? s->cur.start - s->subStart : 0u;
   const int cstride = s->candStride;
   RF_ASSERT(!sub || (s->cur.start >= s->subStart && soff + len <= (uint32_t)m.subMax), "staged subtree: tree %d node %u start %u len %u outside the tile (subStart %u subMax %d sp %u subSp %u)\n", c.tree, s->cur.nodeID, s->cur.start, len, s->subStart, m.subMax, s->sp, s->subSp);
@@ -1324,7 +1346,7 @@ __device__ inline void score_small(NodeCtx& c) {
   __syncthreads();
   RF_PROF(3);
   if (tid == 0) s->histDirty = 1;                                    // the candidates keep tables in the large-node histograms
-  if (m.hb >= kLocalMax) {                                          // only tables with a covariate of > 256 distinct values get here
+  if (kSort && m.hb >= kLocalMax) {                                 // only tables with a covariate of > 256 distinct values get here
     for (int ci = wid; ci < nc; ci += kWarps)
       if (!s->candHist[ci]) local_rank_candidate(s, m.smEnt, m.smCodes + ci * kSmallMax, ci, len);
   }
@@ -1347,11 +1369,11 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
   NodeCtx c{d, g, w, m, list, tree, bayes, unit, strat, beta, Kloop};
 
   bool allHist = true;
-  for (int ci = 0; ci < nc; ci++) if (!s->candHist[ci]) allHist = false;
+  for (int ci = 0; ci < nc; ci++) if (!RF_CANDHIST(ci)) allHist = false;
   const bool small = (allHist && cur.len <= (uint32_t)kSmallMax) ||
-                     (cur.len <= (uint32_t)kLocalMax && m.hb >= kLocalMax && !w.sinkDelta && g.nsplit == 0);
+                     (kSort && cur.len <= (uint32_t)kLocalMax && m.hb >= kLocalMax && !(kSink && w.sinkDelta) && g.nsplit == 0);
   bool anyHist = false, anySort = false;
-  for (int ci = 0; ci < nc; ci++) { if (s->candHist[ci]) anyHist = true; else anySort = true; }
+  for (int ci = 0; ci < nc; ci++) { if (RF_CANDHIST(ci)) anyHist = true; else anySort = true; }
   if (small) {
     if (tid == 0) s->isSmall = 1;
     score_small(c);
@@ -1384,7 +1406,7 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
 
   if (anyHist) {
     unsigned hmask = 0u;
-    for (int ci = 0; ci < nc; ci++) if (s->candHist[ci]) hmask |= 1u << ci;
+    for (int ci = 0; ci < nc; ci++) if (RF_CANDHIST(ci)) hmask |= 1u << ci;
     const uint8_t* __restrict__ hptr[kMaxCand];
 #pragma unroll
     for (int ci = 0; ci < kMaxCand; ci++) hptr[ci] = (ci < nc) ? (const uint8_t*)s->candPtr[ci] : nullptr;
@@ -1437,16 +1459,16 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
       RF_PROF(4);
     }
   }
-  if (anySort) { stratum_totals(c, cur.len); RF_PROF(5); }
+  if (kSort && anySort) { stratum_totals(c, cur.len); RF_PROF(5); }
   }
   // shared tail: warp ci summarises candidate ci (the warp that scored it), then warp 0 replays the
   // tracker in draw order
   for (int ci = warp_id(); ci < nc; ci += kWarps)
-    if (s->candHist[ci]) track_summary(c, ci);
+    if (RF_CANDHIST(ci)) track_summary(c, ci);
   __syncthreads();
   RF_PROF(4);
 
-  if (!anySort) {
+  if (!kSort || !anySort) {
     if (warp_id() == 0) track_combine_all(c, nc);
     __syncthreads();
     RF_PROF(6);
@@ -1454,7 +1476,7 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
   }
 #pragma unroll 1
   for (int ci = 0; ci < nc; ci++) {
-    if (s->candHist[ci]) {
+    if (RF_CANDHIST(ci)) {
       if (warp_id() == 0) track_combine_one(c, ci);
       __syncthreads();
       RF_PROF(6);
@@ -1677,7 +1699,7 @@ __device__ inline bool pop_next(const GrowParams& g, const GrowWork& w, GrowShar
     if (s->sp == 0) { s->abort = 2; return false; }
     s->sp--;
     const NodeEnt e = w.stack[(size_t)tree * kStackCap + s->sp];
-    if (s->inSub && s->sp < s->subSp) s->inSub = 0;                 // the DFS is back above the staged subtree's root
+    if (kSub && s->inSub && s->sp < s->subSp) s->inSub = 0;         // the DFS is back above the staged subtree's root
     if (node_is_leaf(g, e)) {
       uint32_t q;
       append_record(w, s, tree, e.nodeID, 0u, e.E, e.m, nan(""), e.parentRec, &q);
@@ -1818,12 +1840,12 @@ RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
   // ---- depth-first growth (rf.c:21460-21792) ----
   while (true) {
     // park -- never inside a staged subtree (its state lives in this CTA's shared memory; it is over in well under a quantum)
-    if (sliced && tid == 0 && !s->abort && !s->inSub && clock64() - s->sliceStart > w.quantum && atomicAdd(w.waiting, 0) > 0) s->abort = 3;
+    if (sliced && tid == 0 && !s->abort && !(kSub && s->inSub) && clock64() - s->sliceStart > w.quantum && atomicAdd(w.waiting, 0) > 0) s->abort = 3;
     __syncthreads();
     if (s->abort) break;
     const NodeEnt cur = s->cur;
     RF_ASSERT((size_t)cur.start + cur.len <= w.listStride && cur.len >= 1u && cur.buf <= 1u && s->sp <= (uint32_t)kStackCap, "node state: tree %d start %u len %u buf %u sp %u nodeID %u\n", tree, cur.start, cur.len, cur.buf, s->sp, cur.nodeID);
-    if (w.prof && tid == 0) {
+    if (kProf && w.prof && tid == 0) {
       long long now = clock64();
       if (s->prof[13]) s->prof[16 + s->prof[12]] += (unsigned long long)now - s->prof[13];
       int cls = 31 - __clz(cur.len | 1u);
@@ -1837,11 +1859,11 @@ RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
     // i.e. > 1.4e-8 for any m < 2^26 whenever both classes are present, and exactly 0 otherwise --
     // so "variance > EPSILON" is the integer test 0 < E < m
     if (attempt) attempt = cur.E > 0u && cur.E < cur.m;
-    if (w.sinkDelta) attempt = true;                       // single-node scoring mode: no gate
+    if (kSink && w.sinkDelta) attempt = true;              // single-node scoring mode: no gate
     // One serial section per node, run by warp 0 between two block barriers: tracker reset, the draws
     // and the candidate metadata (a barrier + phase boundary costs ~1k cycles on a node that has a few
     // dozen rows; there used to be five of them before the first gather).
-    if (g.seqDraw && attempt) {
+    if (kSeq && g.seqDraw && attempt) {
       node_prologue_nsplit(d, g, s, m, w.lists + ((size_t)tree * 2 + cur.buf) * w.listStride + cur.start, cur.len, cur.m);
     } else if (warp_id() == 0) {
       const int lane = lane_id();
@@ -1881,7 +1903,7 @@ RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
     __syncthreads();
     RF_PROF(1);
     if (attempt && s->nc > 0) score_node(d, g, w, m, tree);   // ends with a block barrier
-    if (w.sinkDelta) {                                     // emit-only mode stops after the root
+    if (kSink && w.sinkDelta) {                            // emit-only mode stops after the root
       if (tid == 0) *w.sinkCount = s->cutsSeen;
       break;
     }
@@ -1918,7 +1940,7 @@ RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
     const uint32_t* src = w.lists + ((size_t)tree * 2 + cur.buf) * w.listStride + cur.start;
     uint32_t* dst = w.lists + ((size_t)tree * 2 + (cur.buf ^ 1u)) * w.listStride + cur.start;
     const bool small = s->isSmall != 0;
-    const bool localCut = small && s->candLocal[bc] != 0;
+    const bool localCut = kSort && small && s->candLocal[bc] != 0;
     const uint8_t* cptr = m.smCodes + bc * kSmallMax;
     uint32_t nL; unsigned long long tneL; double trtL = 0.0, trtR = 0.0;
     if (small) {
@@ -1928,7 +1950,7 @@ RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
       static_assert(kEpt <= 8, "staged entries per thread");
       unsigned long long my = 0ull; bool lf[kEpt]; uint32_t en[kEpt];
       double rtL = 0.0, rtR = 0.0;
-      const bool sub = s->inSub != 0;                            // staged subtree: the "list" is the slot order in shared memory
+      const bool sub = kSub && s->inSub != 0;                    // staged subtree: the "list" is the slot order in shared memory
       const uint32_t soff = sub ? cur.start - s->subStart : 0u;
 #pragma unroll
       for (int u = 0; u < kEpt; u++) {
@@ -2087,7 +2109,7 @@ RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
     continue;
   }
   if (tid == 0) {
-    if (w.prof) for (int k = 0; k < kProfSlots; k++) w.prof[(size_t)tree * kProfSlots + k] = s->prof[k];
+    if (kProf && w.prof) for (int k = 0; k < kProfSlots; k++) w.prof[(size_t)tree * kProfSlots + k] = s->prof[k];
     w.nodeCount[tree] = s->nodeCount;
     w.leafCount[tree] = s->leafCount;
     w.candCount[tree] = s->candCount;

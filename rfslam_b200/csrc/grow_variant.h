@@ -14,7 +14,7 @@ struct GrowVariant {
 };
 const GrowVariant* grow_variant_t128();
 const GrowVariant* grow_variant_t256();
-const GrowVariant* grow_variant_t256f();   // + unordered-factor support
+const GrowVariant* grow_variant_t256f();   // the FULL build: factors, nsplit, wide covariates, staged subtrees, emit mode, profile
 const GrowVariant* grow_variant_t320();
 const GrowVariant* grow_variant_t512();
 }  // namespace rfslam

@@ -398,8 +398,9 @@ def test_every_cta_width_grows_the_same_forest(threads, monkeypatch):
 
 def test_row_major_mirror_and_staged_subtrees_match_oracle(monkeypatch):
     """Tables beyond L2 get a row-major mirror and grow small subtrees out of a shared-memory tile (csrc/grow_kernel.cuh
-    stage_subtree); forced on here for a table that would not take that path by size."""
+    stage_subtree, opt-in: RFSLAM_SUBTREE_MAX); both forced on here for a table that would not take those paths by size."""
     monkeypatch.setenv("RFSLAM_ROWMAJOR", "1")
+    monkeypatch.setenv("RFSLAM_SUBTREE_MAX", "512")
     for rule, levels, nodesize, p in ((4, 64, 5, 40), (1, 200, 3, 17), (5, 16, 10, 9)):
         d = make_cpiu(30000, p, levels=levels, seed=44 + rule)
         ntree = 3
