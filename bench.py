@@ -457,6 +457,11 @@ def main():
                                    f"ONE forest of ntree={c3['ntree']} sharded over {world} GPU(s), mtry=ceil(sqrt(p))=10, nodesize={c3['nodesize']}, poisson.split{c3['rule']}"),
                       "scaling": "strong", "trees": c3["ntree"], "trees_per_gpu": len(range(rank + 1, c3["ntree"] + 1, world)), "steps": 1, "warmup": 0,
                       "value": c3["ntree"] / c3_s, "unit": "trees/s", "ms_per_step": 1e3 * c3_s, "grow_kernel_ms": c3_kern,
+                      # where this rank's step went: the tree kernel, the other device work (bootstrap replay, OOB / full-ensemble
+                      # traversal, compaction), and the host side -- a COLD step: ~20 GB of forest records come home into page-locked
+                      # blocks that are allocated here for the first time (a second step of the same shape reuses them: 0.1 s)
+                      "device_ms": f3["total_device_ms"], "bootstrap_ms": f3["bootstrap_ms"], "membership_kernel_ms": f3["membership_kernel_ms"],
+                      "host_side_ms": 1e3 * c3_s - f3["total_device_ms"],
                       "split_candidates_per_sec": c3_cand / c3_s, "forest_nodes": c3_nodes, "table_bytes_hbm": int(ds3.hbm_bytes),
                       "roofline": {"bound": "hbm", "kernel": "rfslam_grow_kernel", "achieved": a3, "peak": peak, "unit": "GB/s", "frac": a3 / peak,
                                    "algorithmic_bytes_per_launch": c3_algo / world, "traffic": ncu_traffic("configs2"),

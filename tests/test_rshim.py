@@ -82,3 +82,39 @@ def test_both_libraries_return_the_same_named_lists(case):
                     np.testing.assert_array_equal(np.isnan(pg[k]), np.isnan(pr[k]), err_msg=k)
                     ok = ~np.isnan(pr[k])
                     np.testing.assert_allclose(pg[k][ok], pr[k][ok], rtol=parity.HAZARD_RTOL, atol=0, err_msg=k)
+
+
+@pytest.mark.gpu
+@needs_shim
+@needs_ref
+def test_both_libraries_agree_on_a_mixed_factor_table():
+    """xType "C" covariates through the 44 / 58-argument entries: parmID / contPT = NA / mwcpSZ / mwcpPT[1:sum(mwcpCT)] /
+    mwcpCT as R reads them (R/rfsrc.R:1772-1800), and predictions of either library's forest by either library."""
+    d = make_cpiu(3000, 8, levels=16, seed=5)
+    x = d.x.copy(); rng = np.random.default_rng(9)
+    xt = ["R"] * 8; xl = np.zeros(8, np.int32)
+    for c, lv in {1: 5, 4: 8, 6: 3}.items():
+        x[c] = rng.integers(1, lv + 1, size=d.n).astype(np.float64); xt[c] = "C"; xl[c] = lv
+    ntree = 4
+    kw = dict(rule=4, ntree=ntree, nodesize=10, seed=-77, membership=True, xtype=xt, xlevels=xl)
+    ref = refdriver.grow(x, d.y, d.rt, d.strat, impl="ref", **kw)
+    got = refdriver.grow(x, d.y, d.rt, d.strat, impl="b200", **kw)
+    assert [k for k in got if not k.startswith("_")] == [k for k in ref if not k.startswith("_")]
+
+    def canon(t):
+        t = refdriver.trim_forest(t, d.n)
+        order = np.argsort(t["treeID"], kind="stable")
+        w = np.zeros(t["treeID"].size, np.int64); w[t["mwcpSZ"] > 0] = t["mwcpPT"][: int((t["mwcpSZ"] > 0).sum())]
+        t["mwcpPT"] = w[order][t["mwcpSZ"][order] > 0].astype(np.int32)
+        for k in ("treeID", "nodeID", "parmID", "contPT", "mwcpSZ"):
+            t[k] = t[k][order]
+        return t
+    tg, tr = canon(got), canon(ref)
+    assert int(tr["mwcpSZ"].sum()) > 20
+    parity.assert_forest_equal(tg, tr, d.n, ntree, label="rshim factors")
+    fx = x[:, ::3].copy()
+    for forest in (tr, tg):
+        pr = refdriver.predict(x, d.y, forest, fx, impl="ref", nodesize=10, xtype=xt, xlevels=xl)
+        pg = refdriver.predict(x, d.y, forest, fx, impl="b200", nodesize=10, xtype=xt, xlevels=xl)
+        np.testing.assert_array_equal(pg["nodeMembership"], pr["nodeMembership"])
+        np.testing.assert_allclose(pg["allEnsbCLS"], pr["allEnsbCLS"], rtol=parity.HAZARD_RTOL, atol=0)
