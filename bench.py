@@ -354,7 +354,7 @@ def main():
             lv = 3 + (c // 5) % 6
             xm[c] = rng.integers(1, lv + 1, size=n).astype(np.float64); xt[c] = "C"; xl[c] = lv
         dsm = rfslam_b200.ResidentCpiu(xm, d.y, d.rt, d.strat, device=local, xvar_types=xt, xvar_levels=xl)
-        mixed_trees = 100
+        mixed_trees = 296                                                # one full wave of the 256-thread build
         fm = None
         for it in range(2):
             torch.cuda.synchronize(); t0 = time.perf_counter()

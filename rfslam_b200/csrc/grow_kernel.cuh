@@ -181,6 +181,8 @@ struct GrowShared {
   uint32_t cutMask[kMaxCand][8]; uint32_t rankSel[8]; uint8_t swor[256]; int trkCuts[kMaxCand];
   int candStride;                    // byte-coded candidates: code of row r = candPtr[k][r * candStride] (1 = column-major array, rowPitch = row-major mirror)
   int inSub; uint32_t subSp, subStart; // growing inside a staged subtree: DFS depth at its root, list offset of its first entry
+  uint8_t candMask[kMaxCand];        // sequential draws: the tracker takes this candidate's cuts from cutMask (drawn subset, factor cuts)
+  int seqNext;
   uint8_t candFac[kMaxCand];         // candidate is an unordered factor: its cuts are the level subsets facMask[k][0 .. facN[k])
   int facN[kMaxCand];
   uint8_t candLocal[kMaxCand];       // candidate re-ranked locally by this node (its codes in shared memory are node-local ranks)
@@ -558,7 +560,7 @@ __device__ inline void track_summary(const NodeCtx& c, int ci) {
   const int cov = s->candCov[ci];
   const double wgt = c.g.split_weight ? c.g.split_weight[cov] : 1.0;
   const double statP = m.statP[ci];
-  const uint32_t* cm = (kSeq && c.g.seqDraw) ? s->cutMask[ci] : nullptr;   // the candidate's cuts as a mask (drawn subset, factor cuts)
+  const uint32_t* cm = (kSeq && c.g.seqDraw && s->candMask[ci]) ? s->cutMask[ci] : nullptr;   // the candidate's cuts as a mask (drawn subset, factor cuts)
   int ncuts = np - 1;
   if (cm) ncuts = warp_sum((lane < 8) ? (int)__popc(cm[lane]) : 0);
   double M = -INFINITY; int pos = 0x7fffffff; bool anyNan = false;
@@ -609,7 +611,7 @@ __device__ inline void track_exact(const NodeCtx& c, int ci) {
   const int cov = s->candCov[ci];
   int have = s->have; double best = s->bestDelta; int bestBin = -1;
   int emitted = s->cutsSeen;
-  const uint32_t* cm = (kSeq && c.g.seqDraw) ? s->cutMask[ci] : nullptr;
+  const uint32_t* cm = (kSeq && c.g.seqDraw && s->candMask[ci]) ? s->cutMask[ci] : nullptr;
 #pragma unroll 1
   for (int ch = 0; ch < nch; ch++) {
     int bin = (ch << 5) + lane;
@@ -1558,16 +1560,32 @@ __device__ inline void node_prologue_nsplit(const DevData& d, const GrowParams& 
   __syncthreads();
   const int size0 = s->poolSize;
   const int nd = min(g.mtry, size0);
+  // Thread 0 draws covariates until one needs a look at the node before the chain can go on: a candidate whose cuts are
+  // DRAWN (nsplit > 0) or a factor (random pairs when the node is small).  Plain numeric candidates (nsplit = 0) consume
+  // no further draws and are scored exactly as in the all-at-once prologue, so a run of them costs one barrier.
+  int kDone = 0;
 #pragma unroll 1
-  for (int k = 0; k < nd; k++) {
-    if (tid == 0) {                                                  // the covariate (rf.c:8378-8381, rf.c:8305-8307)
-      const uint32_t sl = ran1_index(s->rng, (uint32_t)(size0 - k));
-      const int cov = m.pool[sl - 1];
-      m.pool[sl - 1] = m.pool[size0 - 1 - k];
-      const int Dv = d.D[cov];
-      s->candCov[k] = cov; s->candD[k] = Dv; s->candW[k] = d.width[cov]; s->candPtr[k] = d.codes[cov]; s->candHist[k] = Dv <= kHistBins;
+  while (kDone < nd) {
+    if (tid == 0) {
+      int kk = kDone;
+      while (kk < nd) {                                              // the covariate (rf.c:8378-8381, rf.c:8305-8307)
+        const uint32_t sl = ran1_index(s->rng, (uint32_t)(size0 - kk));
+        const int cov = m.pool[sl - 1];
+        m.pool[sl - 1] = m.pool[size0 - 1 - kk];
+        const int Dv = d.D[cov];
+        s->candCov[kk] = cov; s->candD[kk] = Dv; s->candW[kk] = d.width[cov]; s->candPtr[kk] = d.codes[cov]; s->candHist[kk] = Dv <= kHistBins;
+        const bool plain = g.nsplit == 0 && !(kFactors && d.ftype && d.ftype[cov]);
+        s->candMask[kk] = plain ? 0 : 1; s->candFac[kk] = 0; s->facN[kk] = 0;
+        kk++;
+        if (!plain) break;
+      }
       s->candStride = 1;
+      s->seqNext = kk;
     }
+    __syncthreads();
+    const int k = s->seqNext - 1;                                    // the last candidate drawn
+    kDone = k + 1;
+    if (!s->candMask[k]) continue;                                   // (only possible at the end of the node's draws)
     if (tid < 8) { m.pres[k * 8 + tid] = 0u; s->cutMask[k][tid] = 0u; s->rankSel[tid] = 0u; }
     __syncthreads();
     {                                                                // which codes occur in the node
@@ -1630,7 +1648,6 @@ __device__ inline void node_prologue_nsplit(const DevData& d, const GrowParams& 
       continue;
     }
     if (tid == 0) {
-      s->candFac[k] = 0; s->facN[k] = 0;
       int np = 0, last = -1;
       for (int wq = 0; wq < 8; wq++) { const uint32_t wd = m.pres[k * 8 + wq]; np += __popc(wd); if (wd) last = (wq << 5) + 31 - __clz(wd); }
       if (np >= 2) {
