@@ -297,6 +297,7 @@ def main():
         "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(cfg), "n": n, "p": p, "ntree_total": trees_total, "l2": "256 MB flush buffer written between timed steps",
                    "parallelism": f"tree-sharded x{world}" + ("; NCCL all-reduce of the ensemble sums + gather of the forest records to rank 0 inside the step" if world > 1 else "")},
+        "step_ms": [1e3 * w for w in walls],                        # rank 0's wall clock of every timed step
         "split_candidates_per_sec": cand_total / step_s,
         "device_ms_per_step": dev_mean, "grow_kernel_ms_per_step": kern_mean, "forest_nodes": nodes_total,
         "clocks": clocks,

@@ -114,59 +114,68 @@ void comm_allreduce_sum_u64(rfslam_comm* c, unsigned long long* dev, int count) 
   c->allreduces += 1;
 }
 
-// (2) gather-v of one shard array to rank 0 and merge into tree order.  `local` holds this rank's trees
-// back to back (`width` elements per unit); unitsOfTree[b] = units of tree b + 1 (all ranks know all trees).
-// Rank 0 receives into scratch and returns the merged device array (caller frees with cudaFree); others return nullptr.
-template <typename T>
-T* comm_gather_merge(rfslam_comm* c, const T* local, const std::vector<long long>& unitsOfTree, int width, ncclDataType_t dt) {
+// (2) gather-v of the shard arrays to rank 0, merged into ascending tree order.  All of a call's arrays share one layout
+// per unit kind (records, leaves): the offset tables go to the device once, every array is then three asynchronous steps
+// on the communicator's stream -- NCCL recv of the other ranks' segments over NVLink, one merge kernel, nothing else.  The
+// merge writes the caller's destination directly: a device array, or the PAGE-LOCKED HOST block the forest is returned in
+// (host memory from cudaHostAlloc is device-accessible under unified addressing), so rank 0's download IS the merge --
+// no merged device copy, no second pass over PCIe.  comm_gather_finish synchronises and releases the scratch.
+void comm_gather_layout(rfslam_comm* c, const std::vector<long long>& unitsOfTree, GatherLayout& L) {
   const int W = c->world, ntree = (int)unitsOfTree.size();
-  std::vector<long long> rankUnits(W, 0), srcOff(ntree), dstOff(ntree), len(ntree);
+  L.W = W; L.ntree = ntree; L.rankUnits.assign(W, 0); L.total = 0;
+  std::vector<long long> srcOff(ntree), dstOff(ntree), len(ntree);
   std::vector<int> srcRank(ntree);
-  long long total = 0;
   for (int b = 0; b < ntree; b++) {
     const int r = b % W;
-    srcRank[b] = r; srcOff[b] = rankUnits[r]; dstOff[b] = total; len[b] = unitsOfTree[b];
-    rankUnits[r] += unitsOfTree[b]; total += unitsOfTree[b];
+    srcRank[b] = r; srcOff[b] = L.rankUnits[r]; dstOff[b] = L.total; len[b] = unitsOfTree[b];
+    L.rankUnits[r] += unitsOfTree[b]; L.total += unitsOfTree[b];
   }
-  std::vector<T*> recv(W, nullptr);
-  T* merged = nullptr;
-  auto cleanup = [&]() { for (int r = 1; r < W; r++) if (recv[r]) cudaFree(recv[r]); };
-  try {
-    if (c->rank == 0) {
-      for (int r = 1; r < W; r++) RF_CUDA(cudaMalloc((void**)&recv[r], std::max<size_t>((size_t)rankUnits[r] * width * sizeof(T), 16)));
-      recv[0] = const_cast<T*>(local);
-    }
-    RF_NCCL(g_nccl.GroupStart());
-    if (c->rank == 0) { for (int r = 1; r < W; r++) RF_NCCL(g_nccl.Recv(recv[r], (size_t)rankUnits[r] * width, dt, r, c->comm, c->stream)); }
-    else RF_NCCL(g_nccl.Send(local, (size_t)rankUnits[c->rank] * width, dt, 0, c->comm, c->stream));
-    RF_NCCL(g_nccl.GroupEnd());
-    c->gathers += 1;
-    if (c->rank == 0) {
-      RF_CUDA(cudaMalloc((void**)&merged, std::max<size_t>((size_t)total * width * sizeof(T), 16)));
-      T** d_src = nullptr; int* d_rank = nullptr; long long *d_so = nullptr, *d_do = nullptr, *d_len = nullptr;
-      RF_CUDA(cudaMalloc((void**)&d_src, W * sizeof(T*))); RF_CUDA(cudaMalloc((void**)&d_rank, (size_t)ntree * 4));
-      RF_CUDA(cudaMalloc((void**)&d_so, (size_t)ntree * 8)); RF_CUDA(cudaMalloc((void**)&d_do, (size_t)ntree * 8)); RF_CUDA(cudaMalloc((void**)&d_len, (size_t)ntree * 8));
-      RF_CUDA(cudaMemcpyAsync(d_src, recv.data(), W * sizeof(T*), cudaMemcpyHostToDevice, c->stream));
-      RF_CUDA(cudaMemcpyAsync(d_rank, srcRank.data(), (size_t)ntree * 4, cudaMemcpyHostToDevice, c->stream));
-      RF_CUDA(cudaMemcpyAsync(d_so, srcOff.data(), (size_t)ntree * 8, cudaMemcpyHostToDevice, c->stream));
-      RF_CUDA(cudaMemcpyAsync(d_do, dstOff.data(), (size_t)ntree * 8, cudaMemcpyHostToDevice, c->stream));
-      RF_CUDA(cudaMemcpyAsync(d_len, len.data(), (size_t)ntree * 8, cudaMemcpyHostToDevice, c->stream));
-      merge_segments_kernel<T><<<ntree, 256, 0, c->stream>>>(merged, (const T* const*)d_src, d_rank, d_so, d_do, d_len, width);
-      RF_CUDA(cudaGetLastError());
-      RF_CUDA(cudaStreamSynchronize(c->stream));
-      cudaFree(d_src); cudaFree(d_rank); cudaFree(d_so); cudaFree(d_do); cudaFree(d_len);
-    } else {
-      RF_CUDA(cudaStreamSynchronize(c->stream));
-    }
-  } catch (...) { cleanup(); if (merged) cudaFree(merged); throw; }
-  cleanup();
-  return merged;
+  if (c->rank != 0) return;
+  RF_CUDA(cudaMalloc((void**)&L.d_rank, (size_t)ntree * 4));
+  RF_CUDA(cudaMalloc((void**)&L.d_so, (size_t)ntree * 8)); RF_CUDA(cudaMalloc((void**)&L.d_do, (size_t)ntree * 8)); RF_CUDA(cudaMalloc((void**)&L.d_len, (size_t)ntree * 8));
+  RF_CUDA(cudaMemcpy(L.d_rank, srcRank.data(), (size_t)ntree * 4, cudaMemcpyHostToDevice));
+  RF_CUDA(cudaMemcpy(L.d_so, srcOff.data(), (size_t)ntree * 8, cudaMemcpyHostToDevice));
+  RF_CUDA(cudaMemcpy(L.d_do, dstOff.data(), (size_t)ntree * 8, cudaMemcpyHostToDevice));
+  RF_CUDA(cudaMemcpy(L.d_len, len.data(), (size_t)ntree * 8, cudaMemcpyHostToDevice));
 }
-template int32_t* comm_gather_merge<int32_t>(rfslam_comm*, const int32_t*, const std::vector<long long>&, int, ncclDataType_t);
-template double* comm_gather_merge<double>(rfslam_comm*, const double*, const std::vector<long long>&, int, ncclDataType_t);
 
-int32_t* comm_gather_i32(rfslam_comm* c, const int32_t* local, const std::vector<long long>& units, int width) { return comm_gather_merge<int32_t>(c, local, units, width, ncclInt32); }
-double*  comm_gather_f64(rfslam_comm* c, const double* local, const std::vector<long long>& units, int width) { return comm_gather_merge<double>(c, local, units, width, ncclDouble); }
+template <typename T>
+void comm_gather_into(rfslam_comm* c, GatherLayout& L, const T* local, int width, ncclDataType_t dt, T* dst) {
+  const int W = c->world;
+  std::vector<void*> recv(W, nullptr);
+  if (c->rank == 0) {
+    for (int r = 1; r < W; r++) {
+      void* q = nullptr;
+      RF_CUDA(cudaMalloc(&q, std::max<size_t>((size_t)L.rankUnits[r] * width * sizeof(T), 16)));
+      recv[r] = q; L.devKeep.push_back(q);
+    }
+    recv[0] = const_cast<T*>(local);
+  }
+  RF_NCCL(g_nccl.GroupStart());
+  if (c->rank == 0) { for (int r = 1; r < W; r++) RF_NCCL(g_nccl.Recv(recv[r], (size_t)L.rankUnits[r] * width, dt, r, c->comm, c->stream)); }
+  else RF_NCCL(g_nccl.Send(local, (size_t)L.rankUnits[c->rank] * width, dt, 0, c->comm, c->stream));
+  RF_NCCL(g_nccl.GroupEnd());
+  c->gathers += 1;
+  if (c->rank != 0) return;
+  void* d_src = nullptr;
+  RF_CUDA(cudaMalloc(&d_src, W * sizeof(void*)));
+  L.devKeep.push_back(d_src);
+  L.hostKeep.push_back(recv);                                        // (alive until the copy below has run)
+  RF_CUDA(cudaMemcpyAsync(d_src, L.hostKeep.back().data(), W * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+  merge_segments_kernel<T><<<L.ntree, 256, 0, c->stream>>>(dst, (const T* const*)d_src, L.d_rank, L.d_so, L.d_do, L.d_len, width);
+  RF_CUDA(cudaGetLastError());
+}
+void comm_gather_i32_into(rfslam_comm* c, GatherLayout& L, const int32_t* local, int width, int32_t* dst) { comm_gather_into<int32_t>(c, L, local, width, ncclInt32, dst); }
+void comm_gather_f64_into(rfslam_comm* c, GatherLayout& L, const double* local, int width, double* dst) { comm_gather_into<double>(c, L, local, width, ncclDouble, dst); }
+
+void comm_gather_finish(rfslam_comm* c, GatherLayout& L) {
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  for (void* q : L.devKeep) cudaFree(q);
+  L.devKeep.clear(); L.hostKeep.clear();
+  for (void* q : {(void*)L.d_rank, (void*)L.d_so, (void*)L.d_do, (void*)L.d_len}) if (q) cudaFree(q);
+  L.d_rank = nullptr; L.d_so = L.d_do = L.d_len = nullptr;
+  if (e != cudaSuccess) { set_error("CUDA error %s while gathering the forest", cudaGetErrorString(e)); throw CudaFail{RFSLAM_ENODEV}; }
+}
 
 // leafCount of every tree of the forest on every rank: rank r contributes its trees at b = r, r + W, ...
 void comm_allgather_leaf_counts(rfslam_comm* c, const std::vector<int32_t>& mine, int ntree, std::vector<int32_t>& all) {

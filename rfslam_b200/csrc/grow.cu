@@ -774,36 +774,59 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     // ---- gather the shards' records to rank 0 (NCCL send / recv over NVLink, then a device merge into tree order) ----
     std::vector<int32_t> allLeaf;
     if (gather) {
-      const double t0 = wall();
+      const bool tmg = getenv("RFSLAM_TIMING") != nullptr;
+      const double tA = wall();
       RF_CUDA(cudaDeviceSynchronize());
+      const double t0 = wall();
       comm_allgather_leaf_counts(comm, h_leafCount, cfg.ntree, allLeaf);
+      const double tB = wall();
       std::vector<long long> nodeUnits(cfg.ntree), leafUnits(cfg.ntree);
       for (int b = 0; b < cfg.ntree; b++) { leafUnits[b] = allLeaf[b]; nodeUnits[b] = 2ll * allLeaf[b] - 1; }
       long long NNall = 0, NLall = 0;
       for (int b = 0; b < cfg.ntree; b++) { NNall += nodeUnits[b]; NLall += leafUnits[b]; }
-      struct Dev { void* p = nullptr; ~Dev() { if (p) cudaFree(p); } };
-      Dev m_tree, m_node, m_parm, m_cont, m_stat, m_rcnt, m_acnt, m_clas;
-      m_tree.p = comm_gather_i32(comm, (const int32_t*)g_tree.p, nodeUnits, 1);
-      m_node.p = comm_gather_i32(comm, (const int32_t*)g_node.p, nodeUnits, 1);
-      m_parm.p = comm_gather_i32(comm, (const int32_t*)g_parm.p, nodeUnits, 1);
-      m_cont.p = comm_gather_f64(comm, (const double*)g_cont.p, nodeUnits, 1);
-      Dev m_mwcp;
-      if (ds->has_factor) m_mwcp.p = comm_gather_i32(comm, (const int32_t*)g_mwcp.p, nodeUnits, 1);
-      if (wantStat) m_stat.p = comm_gather_f64(comm, (const double*)g_stat.p, nodeUnits, 1);
-      m_rcnt.p = comm_gather_i32(comm, (const int32_t*)g_rcnt.p, leafUnits, 1);
-      m_acnt.p = comm_gather_i32(comm, (const int32_t*)g_acnt.p, leafUnits, 1);
-      m_clas.p = comm_gather_i32(comm, (const int32_t*)g_clas.p, leafUnits, 2);
+      // rank 0's destinations are the page-locked host blocks the forest is returned in: the merge kernels write them
+      // directly (device-accessible under unified addressing), so the gather, the merge and the download are one pass.
+      // A destination that is not device-accessible (a block the pool had to malloc) goes through a device array.
+      const bool root = comm_rank(comm) == 0;
+      struct Stage { void* dev = nullptr; void* host = nullptr; size_t bytes = 0; };
+      std::vector<Stage> staged;
+      auto target = [&](void* hostDst, size_t bytes) -> void* {
+        if (!root) return nullptr;
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, hostDst) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) return at.devicePointer;
+        cudaGetLastError();
+        Stage st; st.host = hostDst; st.bytes = bytes;
+        RF_CUDA(cudaMalloc(&st.dev, std::max<size_t>(bytes, 16)));
+        staged.push_back(st);
+        return st.dev;
+      };
+      GatherLayout LN, LL;
+      try {
+        comm_gather_layout(comm, nodeUnits, LN); comm_gather_layout(comm, leafUnits, LL);
+        const size_t nn = root ? (size_t)NNall : 0, nl = root ? (size_t)NLall : 0;
+        comm_gather_i32_into(comm, LN, (const int32_t*)g_tree.p, 1, (int32_t*)target(h_treeID.grow(nn), nn * 4));
+        comm_gather_i32_into(comm, LN, (const int32_t*)g_node.p, 1, (int32_t*)target(h_nodeID.grow(nn), nn * 4));
+        comm_gather_i32_into(comm, LN, (const int32_t*)g_parm.p, 1, (int32_t*)target(h_parmID.grow(nn), nn * 4));
+        comm_gather_f64_into(comm, LN, (const double*)g_cont.p, 1, (double*)target(h_contPT.grow(nn), nn * 8));
+        if (ds->has_factor) comm_gather_i32_into(comm, LN, (const int32_t*)g_mwcp.p, 1, (int32_t*)target(h_mwcpW.grow(nn), nn * 4));
+        if (wantStat) comm_gather_f64_into(comm, LN, (const double*)g_stat.p, 1, (double*)target(h_stat.grow(nn), nn * 8));
+        comm_gather_i32_into(comm, LL, (const int32_t*)g_rcnt.p, 1, (int32_t*)target(h_tnRCNT.grow(nl), nl * 4));
+        comm_gather_i32_into(comm, LL, (const int32_t*)g_acnt.p, 1, (int32_t*)target(h_tnACNT.grow(nl), nl * 4));
+        comm_gather_i32_into(comm, LL, (const int32_t*)g_clas.p, 2, (int32_t*)target(h_tnCLAS.grow(2 * nl), 2 * nl * 4));
+        const double tC = wall();
+        comm_gather_finish(comm, LN); comm_gather_finish(comm, LL);
+        for (auto& st : staged) RF_CUDA(cudaMemcpy(st.host, st.dev, st.bytes, cudaMemcpyDeviceToHost));
+        if (tmg) fprintf(stderr, "[rfslam_b200_grow] rank %d exchange: device drain %.1f ms, leaf counts %.1f ms, issue (layouts, host blocks, recv buffers, NCCL, merges) %.1f ms, wait + release %.1f ms, %zu staged arrays\n",
+                         comm_rank(comm), t0 - tA, tB - t0, tC - tB, wall() - tC, staged.size());
+      } catch (...) {
+        for (auto& st : staged) cudaFree(st.dev);
+        try { comm_gather_finish(comm, LN); } catch (...) {}
+        try { comm_gather_finish(comm, LL); } catch (...) {}
+        throw;
+      }
+      for (auto& st : staged) cudaFree(st.dev);
       collMs += wall() - t0;
-      if (comm_rank(comm) == 0) {
-        RF_CUDA(cudaMemcpy(h_treeID.grow((size_t)NNall), m_tree.p, (size_t)NNall * 4, cudaMemcpyDeviceToHost));
-        RF_CUDA(cudaMemcpy(h_nodeID.grow((size_t)NNall), m_node.p, (size_t)NNall * 4, cudaMemcpyDeviceToHost));
-        RF_CUDA(cudaMemcpy(h_parmID.grow((size_t)NNall), m_parm.p, (size_t)NNall * 4, cudaMemcpyDeviceToHost));
-        RF_CUDA(cudaMemcpy(h_contPT.grow((size_t)NNall), m_cont.p, (size_t)NNall * 8, cudaMemcpyDeviceToHost));
-        if (ds->has_factor) RF_CUDA(cudaMemcpy(h_mwcpW.grow((size_t)NNall), m_mwcp.p, (size_t)NNall * 4, cudaMemcpyDeviceToHost));
-        if (wantStat) RF_CUDA(cudaMemcpy(h_stat.grow((size_t)NNall), m_stat.p, (size_t)NNall * 8, cudaMemcpyDeviceToHost));
-        RF_CUDA(cudaMemcpy(h_tnRCNT.grow((size_t)NLall), m_rcnt.p, (size_t)NLall * 4, cudaMemcpyDeviceToHost));
-        RF_CUDA(cudaMemcpy(h_tnACNT.grow((size_t)NLall), m_acnt.p, (size_t)NLall * 4, cudaMemcpyDeviceToHost));
-        RF_CUDA(cudaMemcpy(h_tnCLAS.grow(2 * (size_t)NLall), m_clas.p, 2 * (size_t)NLall * 4, cudaMemcpyDeviceToHost));
+      if (root) {
         // rank 0 now returns the WHOLE forest: every tree id, leaf count and seed
         ids.resize(cfg.ntree); h_leafCount.resize(cfg.ntree); h_seed.resize(cfg.ntree);
         for (int b = 0; b < cfg.ntree; b++) { ids[b] = b + 1; h_leafCount[b] = allLeaf[b]; h_seed[b] = seedA[b]; }

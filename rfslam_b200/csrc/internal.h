@@ -130,10 +130,17 @@ bool rule_slot_is_foreign(int family, int slot);
 void comm_allreduce_ensembles(rfslam_comm* c, double* allNum, double* oobNum, uint32_t* allDen, uint32_t* oobDen, int n);
 void comm_allreduce_sum_u64(rfslam_comm* c, unsigned long long* dev, int count);
 void comm_allgather_leaf_counts(rfslam_comm* c, const std::vector<int32_t>& mine, int ntree, std::vector<int32_t>& all);
-// gather-v to rank 0 + merge into ascending tree order; unitsOfTree[b] = units (of `width` elements) of tree b + 1.
-// Returns the merged DEVICE array on rank 0 (release with cudaFree), nullptr elsewhere.
-int32_t* comm_gather_i32(rfslam_comm* c, const int32_t* local, const std::vector<long long>& unitsOfTree, int width);
-double*  comm_gather_f64(rfslam_comm* c, const double* local, const std::vector<long long>& unitsOfTree, int width);
+// gather-v to rank 0 + merge into ascending tree order (comm.cu); unitsOfTree[b] = units (of `width` elements) of tree b + 1.
+// The destination of rank 0 is device-accessible memory: a device array or a page-locked host block.
+struct GatherLayout {
+  int W = 0, ntree = 0; std::vector<long long> rankUnits; long long total = 0;
+  int* d_rank = nullptr; long long *d_so = nullptr, *d_do = nullptr, *d_len = nullptr;
+  std::vector<void*> devKeep; std::vector<std::vector<void*>> hostKeep;
+};
+void comm_gather_layout(rfslam_comm* c, const std::vector<long long>& unitsOfTree, GatherLayout& L);
+void comm_gather_i32_into(rfslam_comm* c, GatherLayout& L, const int32_t* local, int width, int32_t* dst);
+void comm_gather_f64_into(rfslam_comm* c, GatherLayout& L, const double* local, int width, double* dst);
+void comm_gather_finish(rfslam_comm* c, GatherLayout& L);     // synchronises the communicator's stream, releases the scratch
 int comm_rank(const rfslam_comm* c);
 int comm_world(const rfslam_comm* c);
 
