@@ -184,7 +184,8 @@ def main():
     ap.add_argument("--c3-trees", type=int, default=0)
     ap.add_argument("--no-predict", action="store_true", help="skip the rfsrcPredict record")
     ap.add_argument("--no-extras", action="store_true", help="skip the mixed-factor and CPIU-construction records")
-    ap.add_argument("--predict-rows", type=int, default=2_000_000, help="held-out rows per job for the predict record")
+    ap.add_argument("--predict-rows", type=int, default=2_500_000, help="held-out rows PER GPU for the predict record (configs[4]: 20 M rows over 8 GPUs)")
+    ap.add_argument("--predict-trees", type=int, default=1000, help="trees of the forest the predict record routes (configs[4]: 1000)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -321,11 +322,12 @@ def main():
         from rfslam_b200.synth import make_cpiu_torch
         # forest replicated: at N > 1 every rank grows the same cfg.ntree-tree forest for this record (trees are
         # deterministic, so the replicas are identical); the held-out rows are what is sharded
-        fp = f if world == 1 else ds.grow(splitrule=cfg["rule"], ntree=cfg["ntree"], nodesize=cfg["nodesize"], seed=cfg["seed"], k_for_alpha=cfg["k_for_alpha"])
-        m_total = args.predict_rows
-        fx = make_cpiu_torch(m_total, cfg["p"], levels=cfg["levels"], seed=20260102, device=f"cuda:{local}").x
-        lo = rank * (m_total // world)
-        cnt = (m_total // world) if rank < world - 1 else m_total - lo
+        # BASELINE configs[4]: rfsrcPredict + aggregation of a 1000-tree forest on 20 M held-out CPIUs across 8 GPUs = 2.5 M
+        # rows per GPU; the record keeps that per-GPU share at every N (at N = 8 it is the configuration itself)
+        fp = ds.grow(splitrule=cfg["rule"], ntree=args.predict_trees, nodesize=cfg["nodesize"], seed=cfg["seed"], k_for_alpha=cfg["k_for_alpha"])
+        m_total = args.predict_rows * world
+        fx = make_cpiu_torch(args.predict_rows, cfg["p"], levels=cfg["levels"], seed=20260102 + rank, device=f"cuda:{local}").x
+        lo, cnt = 0, args.predict_rows                           # every rank holds (only) its own shard of the held-out rows
         pr = None
         ptimes = []
         for it in range(3):
@@ -339,10 +341,10 @@ def main():
         pbytes = 24.0 * visits + 8.0 * rowtrees                  # B_pred = d * (8 + 16) + 8 per (row, tree)
         line["predict"] = {"metric": "row_trees_per_sec", "value": rowtrees / p_s, "rows": m_total, "trees": int(fp["leafCount"].size),
                            "ms_per_call": 1e3 * p_s, "route_kernel_ms": p_kern, "mean_depth": visits / max(rowtrees, 1.0),
-                           "h2d_bytes_per_call": int(fx.nbytes // world + sum(int(fp[k].nbytes) for k in ("treeID", "nodeID", "parmID", "contPT", "tnCLAS"))),
+                           "h2d_bytes_per_call": int(fx.nbytes + sum(int(fp[k].nbytes) for k in ("treeID", "nodeID", "parmID", "contPT", "tnCLAS"))),
                            "roofline": {"bound": "hbm", "kernel": "route_kernel", "achieved": pbytes / world / 1e9 / max(p_kern / 1e3, 1e-9), "peak": peak,
                                         "unit": "GB/s", "frac": pbytes / world / 1e9 / max(p_kern / 1e3, 1e-9) / peak, "algorithmic_bytes_per_call": pbytes / world},
-                           "sharding": f"held-out rows split over {world} rank(s), forest replicated, no collective"}
+                           "sharding": f"{args.predict_rows} held-out rows per rank over {world} rank(s) (configs[4]'s per-GPU share), forest replicated, no collective"}
         del fx, pr, fp
 
     # ---- the rows SURVEY 8 marks "next", measured beside the path (rank 0, N = 1; not part of the timed step) ----

@@ -338,6 +338,9 @@ struct HostOut {
 
 int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out* out) {
   memset(out, 0, sizeof(*out));
+  const bool tmgAll = getenv("RFSLAM_TIMING") != nullptr;
+  auto wallAll = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tw0 = wallAll(); double twBatches = 0, twHand = 0;
   GrowConfig cfg;
   int rc = validate_grow_args(a, &cfg);
   if (rc) return rc;
@@ -531,6 +534,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     struct Ev2 { cudaEvent_t a = nullptr, b = nullptr; ~Ev2() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } evM;
     RF_CUDA(cudaEventCreate(&evM.a)); RF_CUDA(cudaEventCreate(&evM.b));
     cudaStream_t copyStream = sync.st;
+    bool mwcpCleared = false;
     const bool wantStat = a->want_split_stat != 0;
 
     // ---- per-batch buffers ----
@@ -736,6 +740,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
       }
     }
 
+    twBatches = wallAll();
     // ---- the one exchange of a tree-sharded forest: sum the ensemble accumulators over ranks, on the device ----
     bool wholeForest = T == cfg.ntree;
     double collMs = 0.0;
@@ -834,13 +839,26 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     }
     const int Tout = (int)ids.size();
 
+    twHand = wallAll();
     // ---- hand over ----
     out->ntree = Tout; out->n = n;
     out->total_nodes = (int64_t)h_treeID.n; out->total_leaves = (int64_t)h_tnRCNT.n;
     out->tree_ids = (int32_t*)host_alloc((size_t)Tout * 4); memcpy(out->tree_ids, ids.data(), (size_t)Tout * 4);
-    out->mwcpSZ = (int32_t*)host_calloc(std::max<size_t>(h_treeID.n, 1) * 4);
+    {
+      // mwcpSZ is all zeros unless the table has factors: a page-locked block is cleared by the device's copy engine while
+      // the host copies the ensembles below (a 128 MB host memset was 1 % of a configs[1] step, 1 GB of it on rank 0 at N = 8)
+      const size_t bytes = std::max<size_t>(h_treeID.n, 1) * 4;
+      out->mwcpSZ = (int32_t*)host_alloc(bytes);
+      if (!out->mwcpSZ) { set_error("out of host memory"); throw CudaFail{RFSLAM_ENOMEM}; }
+      cudaPointerAttributes at{};
+      if (bytes >= (1u << 20) && cudaPointerGetAttributes(&at, out->mwcpSZ) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+        RF_CUDA(cudaMemsetAsync(at.devicePointer, 0, bytes, copyStream));
+        mwcpCleared = true;
+      } else { cudaGetLastError(); memset(out->mwcpSZ, 0, bytes); }
+    }
     out->mwcpCT = (int32_t*)host_calloc((size_t)Tout * 4); out->mwcpPT = nullptr; out->mwcp_total = 0;
     if (ds->has_factor && h_mwcpW.n == h_treeID.n) {
+      if (mwcpCleared) { RF_CUDA(cudaStreamSynchronize(copyStream)); mwcpCleared = false; }
       // mwcpSZ / mwcpPT / mwcpCT (saveTree rf.c:10773-10779): one word per factor split in record order, words per tree
       size_t words = 0;
       for (size_t q = 0; q < h_mwcpW.n; q++) if (h_mwcpW.p[q]) words++;
@@ -869,10 +887,13 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
       out->rmbr_stride = (int64_t)rmbrStride;
     }
     out->perfClas = h_perf;
+    if (mwcpCleared) RF_CUDA(cudaStreamSynchronize(copyStream));
     out->split_candidates = totalCand; out->algorithmic_bytes = totalAlgo;
     out->grow_kernel_ms = growMs; out->total_device_ms = totalMs; out->kernel_launches = launches;
     out->grow_kernel_algorithmic_bytes = growAlgo; out->membership_algorithmic_bytes = membAlgo; out->bootstrap_algorithmic_bytes = bootAlgo;
     out->membership_kernel_ms = membMs; out->bootstrap_ms = bootMs; out->collective_ms = collMs;
+    if (tmgAll) fprintf(stderr, "[rfslam_b200_grow] call %.1f ms: setup + batches (bootstrap, tree kernel, compaction, traversal, record copies) %.1f ms [device %.1f ms], exchange + ensembles + perf %.1f ms, hand-over %.1f ms\n",
+                        wallAll() - tw0, twBatches - tw0, (double)totalMs, twHand - twBatches, wallAll() - twHand);
   } catch (CudaFail f) {
     rfslam_b200_free_forest(out);
     return f.code;
