@@ -380,9 +380,9 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     g.hbins = ds->hist_bins;
     g.nsplit = cfg.nsplit;
     g.seqDraw = (cfg.nsplit > 0 || ds->has_factor) ? 1 : 0;
-    g.facCuts = ds->has_factor ? 256 : 0;
-    if (cfg.nsplit > 0 && ds->max_D > kHistBins) {
-      set_error("nsplit = %d with a covariate of %d distinct values: random cut subsets are accelerated for covariates of at most %d distinct values", cfg.nsplit, ds->max_D, kHistBins);
+    g.facCuts = g.seqDraw ? 256 : 0;                              // factor cut masks / drawn cut ordinals of wide covariates
+    if (cfg.nsplit > 256 && ds->max_D > kHistBins) {
+      set_error("nsplit = %d with a covariate of %d distinct values: at most 256 drawn cuts per covariate are kept for covariates of more than %d distinct values", cfg.nsplit, ds->max_D, kHistBins);
       return RFSLAM_ENOSUP;
     }
     {   // fixed-point scale of the exposure accumulators: the largest power of two that keeps

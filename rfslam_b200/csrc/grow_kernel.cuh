@@ -762,27 +762,44 @@ __device__ inline void stratum_totals(const NodeCtx& c, uint32_t len) {
   __syncthreads();
 }
 
-__device__ inline void sort_candidate(const NodeCtx& c, int ci, uint32_t len) {
-  GrowSmem& m = c.m;
-  GrowShared* s = m.s;
-  const int tid = vtid(), lane = lane_id(), wid = warp_id();
-  const size_t n = c.w.listStride;
-  uint32_t* kA = c.w.sortbuf + (size_t)c.tree * 4 * n;
+// stable LSD radix sort of (code, position) of the node's entries for candidate ci, in the tree's global scratch;
+// ks / vs come back pointing at the sorted keys / positions
+__device__ inline void sort_node_codes(const GrowWork& w, int tree, GrowShared* s, GrowSmem& m, const uint32_t* list, uint32_t len, int ci,
+                                       uint32_t*& ks, uint32_t*& vs) {
+  const int tid = vtid();
+  const size_t n = w.listStride;
+  uint32_t* kA = w.sortbuf + (size_t)tree * 4 * n;
   uint32_t* kB = kA + n; uint32_t* vA = kB + n; uint32_t* vB = vA + n;
-  const void* ptr = s->candPtr[ci]; const int wd = s->candW[ci]; const int Dc = s->candD[ci]; const int cov = s->candCov[ci];
+  const void* ptr = s->candPtr[ci]; const int wd = s->candW[ci]; const int Dc = s->candD[ci];
   for (uint32_t i = tid; i < len; i += kThreads) {
-    uint32_t row = c.list[i] & kRowMask;
+    uint32_t row = list[i] & kRowMask;
     kA[i] = load_code(ptr, wd, row);
     vA[i] = i;
   }
   int bits = 32 - __clz(Dc - 1);
   int npass = (bits + 7) >> 3;
-  uint32_t *ks = kA, *vs = vA, *kd = kB, *vd = vB;
+  ks = kA; vs = vA; uint32_t *kd = kB, *vd = vB;
   for (int ps = 0; ps < npass; ps++) {
     radix_pass(ks, vs, kd, vd, len, 8 * ps, s, m.radixBase);
     uint32_t* t1 = ks; ks = kd; kd = t1;
     uint32_t* t2 = vs; vs = vd; vd = t2;
   }
+  __syncthreads();
+}
+
+__device__ inline void sort_candidate(const NodeCtx& c, int ci, uint32_t len) {
+  GrowSmem& m = c.m;
+  GrowShared* s = m.s;
+  const int tid = vtid(), lane = lane_id(), wid = warp_id();
+  const int cov = s->candCov[ci];
+  uint32_t *ks, *vs;
+  sort_node_codes(c.w, c.tree, s, m, c.list, len, ci, ks, vs);
+  // nsplit > 0 on a covariate with more distinct values than nsplit: only the DRAWN cut ordinals (ascending, 1-based rank of
+  // the distinct value the cut follows; node_prologue_nsplit) are candidates (rf.c:14533-14564)
+  const bool drawn = kSeq && c.g.seqDraw && s->candMask[ci] && s->facN[ci] > 0;
+  const uint32_t* sel = m.facMask + (size_t)ci * m.facCuts;
+  const int nsel = drawn ? s->facN[ci] : 0;
+  uint32_t cutBase = 0;                                              // cuts in the tiles before this one
   __syncthreads();
   // parent statistic and carries
   double statP = 0.0;
@@ -837,6 +854,18 @@ __device__ inline void sort_candidate(const NodeCtx& c, int ci, uint32_t len) {
       if (tid == kThreads - 1) {
         m.cN[a] = LN; m.cE[a] = LE; m.cT[a] = LT; m.cW[a] = LW; m.cTL[a] = myL; m.cTR[a] = myR;
       }
+      __syncthreads();
+    }
+    if (drawn) {                                                     // keep a cut only if its ordinal was drawn
+      int tot;
+      const int inc = block_incl_scan<int>(cut ? 1 : 0, s->scrI, tot);
+      if (cut) {
+        const uint32_t ord = cutBase + (uint32_t)inc;
+        int lo = 0, hi = nsel;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (sel[mid] < ord) lo = mid + 1; else hi = mid; }
+        cut = lo < nsel && sel[lo] == ord;
+      }
+      cutBase += (uint32_t)tot;
       __syncthreads();
     }
     m.tileDelta[tid] = cut ? (accL + accR - statP) * wgt : 0.0;
@@ -1540,7 +1569,7 @@ __device__ inline void draw_candidates(const DevData& d, const GrowParams& g, Gr
 // candidate, one pass of the CTA over the node's entries collects which codes occur, then thread 0 draws
 // the cut ranks (swap-remove over 1..D-1, slot = ceil(ran1B * size)) and turns them into a code mask the
 // tracker uses in place of "every present code but the last".
-__device__ inline void node_prologue_nsplit(const DevData& d, const GrowParams& g, GrowShared* s, GrowSmem& m,
+__device__ inline void node_prologue_nsplit(const DevData& d, const GrowParams& g, const GrowWork& w, int tree, GrowShared* s, GrowSmem& m,
                                             const uint32_t* list, uint32_t len, uint32_t mInBag) {
   const int tid = vtid(), lane = lane_id();
   if (warp_id() == 0) {
@@ -1586,6 +1615,39 @@ __device__ inline void node_prologue_nsplit(const DevData& d, const GrowParams& 
     const int k = s->seqNext - 1;                                    // the last candidate drawn
     kDone = k + 1;
     if (!s->candMask[k]) continue;                                   // (only possible at the end of the node's draws)
+    if (kSort && !s->candHist[k]) {
+      // nsplit > 0 on a covariate with more than 256 distinct values: how many cuts are drawn depends on the number of distinct
+      // values IN THIS NODE (rf.c:14544-14564), so the node's codes are sorted here to count them; the drawn cut ORDINALS
+      // (rank of the distinct value a cut follows, ascending) are kept for sort_candidate, which sorts again when it scores
+      uint32_t *ks, *vs;
+      sort_node_codes(w, tree, s, m, list, len, k, ks, vs);
+      int cnt = 0;
+      for (uint32_t i = (uint32_t)tid; i < len; i += kThreads) cnt += (i == 0u || ks[i] != ks[i - 1u]) ? 1 : 0;
+      const int np = block_sum<int>(cnt, s->scrI);
+      if (tid == 0) {
+        int nsel = 0;
+        if (np >= 2 && np > g.nsplit) {
+          // swap-remove over the ranks 1 .. np-1 (sworVector, rf.c:14551-14561) without materialising the vector: only the
+          // slots a draw has overwritten are remembered (at most nsplit of them; the accumulators are idle between nodes)
+          uint32_t* modIdx = (uint32_t*)m.sL; uint32_t* modVal = modIdx + 256;
+          uint32_t* out = m.facMask + (size_t)k * m.facCuts;
+          int nm = 0; uint32_t sz = (uint32_t)np - 1u;
+          for (int j = 0; j < g.nsplit; j++) {
+            const uint32_t idx = ran1_index(s->rng, sz);
+            uint32_t pick = idx, tail = sz; int at = -1;
+            for (int t = 0; t < nm; t++) { if (modIdx[t] == idx) { pick = modVal[t]; at = t; } if (modIdx[t] == sz) tail = modVal[t]; }
+            if (at >= 0) modVal[at] = tail; else { modIdx[nm] = idx; modVal[nm] = tail; nm++; }
+            sz--;
+            int q = nsel++;                                            // insertion into the ascending list (sort, rf.c:14563)
+            while (q > 0 && out[q - 1] > pick) { out[q] = out[q - 1]; q--; }
+            out[q] = pick;
+          }
+        }
+        s->facN[k] = nsel;
+      }
+      __syncthreads();
+      continue;
+    }
     if (tid < 8) { m.pres[k * 8 + tid] = 0u; s->cutMask[k][tid] = 0u; s->rankSel[tid] = 0u; }
     __syncthreads();
     {                                                                // which codes occur in the node
@@ -1881,7 +1943,7 @@ RF_KERNEL_NAME(DevData d, GrowParams g, GrowWork w) {
     // and the candidate metadata (a barrier + phase boundary costs ~1k cycles on a node that has a few
     // dozen rows; there used to be five of them before the first gather).
     if (kSeq && g.seqDraw && attempt) {
-      node_prologue_nsplit(d, g, s, m, w.lists + ((size_t)tree * 2 + cur.buf) * w.listStride + cur.start, cur.len, cur.m);
+      node_prologue_nsplit(d, g, w, tree, s, m, w.lists + ((size_t)tree * 2 + cur.buf) * w.listStride + cur.start, cur.len, cur.m);
     } else if (warp_id() == 0) {
       const int lane = lane_id();
       if (lane == 0) { s->nc = 0; s->have = 0; s->isSmall = 0; s->bestDelta = 0.0; s->bestCand = -1; s->bestCode = 0; s->cutsSeen = 0; }

@@ -204,7 +204,7 @@ def test_unsupported_inputs_fail_loudly():
         rfslam_b200.rfsrc(d.x, d.y + 1.0, d.rt, d.strat, ntree=2)              # response codes outside {1, 2}
     dc = make_cpiu(2000, 3, levels=0, seed=12)                                   # continuous: > 256 distinct values
     with pytest.raises(rfslam_b200.RfslamError):
-        rfslam_b200.rfsrc(dc.x, dc.y, dc.rt, dc.strat, ntree=2, nsplit=3)      # random cut subsets of such a covariate: not accelerated
+        rfslam_b200.rfsrc(dc.x, dc.y, dc.rt, dc.strat, ntree=2, nsplit=300)    # more than 256 drawn cuts of such a covariate: not kept
 
 
 def test_variable_categories_accepted():
@@ -265,7 +265,9 @@ def test_full_size_properties():
 
 @pytest.mark.parametrize("rule,n,p,levels,nsplit,nodesize,seed,dseed", [
     (4, 4000, 9, 64, 5, 5, -12345, 701), (1, 3000, 8, 32, 3, 3, -7, 702), (6, 2500, 12, 256, 10, 5, -99, 703),
-    (2, 3000, 6, 16, 1, 2, -31, 704), (4, 20000, 10, 64, 2, 20, -5, 705)])
+    (2, 3000, 6, 16, 1, 2, -31, 704), (4, 20000, 10, 64, 2, 20, -5, 705),
+    # covariates with more than 256 distinct values (continuous, levels = 0): the node's codes are sorted to count them
+    (4, 5000, 8, 0, 4, 5, -41, 706), (1, 3000, 6, 0, 1, 3, -43, 707), (5, 12000, 9, 0, 10, 20, -47, 708), (6, 2000, 5, 0, 200, 2, -49, 709)])
 def test_nsplit_random_cut_subsets_match_oracle(rule, n, p, levels, nsplit, nodesize, seed, dseed):
     # nsplit > 0 (rf.c:14533-14564): cut draws interleave with covariate draws in chain B and depend on the
     # number of distinct values in the node; the oracle's nsplit is pinned against the live reference (test_oracle)
