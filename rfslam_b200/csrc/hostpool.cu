@@ -6,6 +6,8 @@
 // a fifth of the step.  Blocks come from cudaHostAlloc instead and go back to a free list when the
 // caller releases the forest (rfslam_b200_free_forest / rfslam_b200_free_array), so a second call
 // of similar size touches no new pages and its copies run at PCIe speed, asynchronously.
+#include <unistd.h>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -25,8 +27,13 @@ constexpr size_t kSmall = 1u << 16;                 // below this plain malloc i
 
 size_t idle_cap() {
   static size_t cap = [] {
+    // idle page-locked blocks kept for reuse: a quarter of the machine's memory, at least 8 GB.  The forest gathered on
+    // rank 0 of an 8-GPU job is 8.5 GB per call: with a fixed 8 GB cap every call freed and re-pinned it (seconds per step)
     const char* e = getenv("RFSLAM_HOST_POOL_MB");
-    return (size_t)(e ? atoll(e) : 8192) << 20;
+    if (e) return (size_t)atoll(e) << 20;
+    const long pages = sysconf(_SC_PHYS_PAGES), psz = sysconf(_SC_PAGE_SIZE);
+    const size_t ram = (pages > 0 && psz > 0) ? (size_t)pages * (size_t)psz : ((size_t)32 << 30);
+    return std::max<size_t>((size_t)8 << 30, ram / 4);
   }();
   return cap;
 }
