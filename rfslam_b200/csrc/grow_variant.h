@@ -2,6 +2,7 @@
 // so that grow.cu can pick the width per launch.  Each variant lives in its own translation unit: CTA width is a
 // compile-time constant of the kernel (warp roles, staging per thread, launch bounds).
 #pragma once
+#include <cstdlib>
 #include "internal.h"
 
 namespace rfslam {
@@ -24,6 +25,7 @@ const GrowVariant* grow_variant_t512();
   static cudaError_t prepare_##tag(size_t smem, int* ctasPerSm) {                                                 \
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
     if (e != cudaSuccess) return e;                                                                               \
+    if (const char* cv = getenv("RFSLAM_CARVEOUT")) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)); \
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, kernel, kThreads, smem);                      \
   }                                                                                                               \
   static void launch_##tag(const DevData& d, const GrowParams& g, const GrowWork& w, int grid, size_t smem) {     \

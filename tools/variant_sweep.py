@@ -10,7 +10,7 @@ ntree = int(sys.argv[4]); nodesize = int(sys.argv[5])
 gen = make_cpiu_torch if n >= 4_000_000 else make_cpiu
 d = gen(n, p, levels=L)
 ds = rfslam_b200.ResidentCpiu(d.x, d.y, d.rt, d.strat)
-KEYS = ("RFSLAM_CTA_THREADS", "RFSLAM_TAB_SLOTS", "RFSLAM_HIST_SLOTS", "RFSLAM_NO_SUBTREE", "RFSLAM_SUBTREE_MAX", "RFSLAM_NO_SLICING", "RFSLAM_QUANTUM_MS", "RFSLAM_TIMING")
+KEYS = ("RFSLAM_CTA_THREADS", "RFSLAM_TAB_SLOTS", "RFSLAM_HIST_SLOTS", "RFSLAM_NO_SUBTREE", "RFSLAM_SUBTREE_MAX", "RFSLAM_NO_SLICING", "RFSLAM_QUANTUM_MS", "RFSLAM_TIMING", "RFSLAM_CARVEOUT", "RFSLAM_FULL_KERNEL")
 for cfg in sys.argv[6:] or [""]:
     for k in KEYS: os.environ.pop(k, None)
     for kv in cfg.split():
