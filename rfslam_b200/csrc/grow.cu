@@ -77,12 +77,13 @@ __global__ void bag_count_kernel(const uint32_t* draws, size_t dstride, const in
 }
 
 // by.user bootstrap (rf.c:520-526): the caller supplies the in-bag counts per original row
-__global__ void user_count_kernel(const int32_t* samp, const uint32_t* perm, uint16_t* cnt, int n, int* bad) {
+// (blockIdx.y = tree of the uploaded chunk: samp [chunk][n], cnt [chunk][cntStride])
+__global__ void user_count_kernel(const int32_t* samp, const uint32_t* perm, uint16_t* cnt, size_t cntStride, int n, int* bad) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    int32_t v = samp[perm[i]];
+    int32_t v = samp[(size_t)blockIdx.y * n + perm[i]];
     if (v < 0 || v > 65535) { atomicExch(bad, 1); v = 0; }
-    cnt[i] = (uint16_t)v;
+    cnt[(size_t)blockIdx.y * cntStride + i] = (uint16_t)v;
   }
 }
 
@@ -545,7 +546,9 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
     const size_t cntStride = ((size_t)n + 7) & ~(size_t)7;         // u16 count rows stay 16-byte aligned (the root build reads eight at a time)
     d_lists.alloc((size_t)B * 2 * listStride);
     if (g.has_sort) d_sort.alloc((size_t)B * 4 * listStride);
-    if (!cfg.by_user) d_draws.alloc((size_t)B * maxBoot); else d_samp.alloc(n);
+    // by.user: the caller's in-bag counts go up in chunks of whole trees (one copy + one launch per chunk, not per tree)
+    const int sampChunk = cfg.by_user ? (int)std::max<size_t>(1, std::min<size_t>((size_t)B, ((size_t)256 << 20) / ((size_t)n * 4))) : 0;
+    if (!cfg.by_user) d_draws.alloc((size_t)B * maxBoot); else d_samp.alloc((size_t)sampChunk * n);
     d_cnt.alloc((size_t)B * cntStride);
     d_stack.alloc((size_t)B * kStackCap); d_stackPerm.alloc((size_t)B * kStackCap * g.pw);
     d_nodeCount.alloc(B); d_leafCount.alloc(B); d_cursor.alloc(1); d_status.alloc(1);
@@ -576,10 +579,15 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         if (cfg.by_user) {
           int* d_bad = d_status.p;
           RF_CUDA(cudaMemset(d_bad, 0, 4));
-          for (int t = 0; t < nb; t++) {
-            RF_CUDA(cudaMemcpy(d_samp.p, a->bootstrap + (size_t)(hid[t] - 1) * n, (size_t)n * 4, cudaMemcpyHostToDevice));
-            user_count_kernel<<<(n + 255) / 256, 256>>>(d_samp.p, ds->dev.perm, d_cnt.p + (size_t)t * cntStride, n, d_bad);
+          for (int t0 = 0; t0 < nb; ) {
+            // trees of a shard are tree_step apart in the caller's matrix: consecutive ones (tree_step = 1) go up in one copy
+            int cnt = 1;
+            while (t0 + cnt < nb && cnt < sampChunk && hid[t0 + cnt] == hid[t0 + cnt - 1] + 1) cnt++;
+            RF_CUDA(cudaMemcpy(d_samp.p, a->bootstrap + (size_t)(hid[t0] - 1) * n, (size_t)cnt * n * 4, cudaMemcpyHostToDevice));
+            dim3 gu((unsigned)((n + 255) / 256), (unsigned)cnt);
+            user_count_kernel<<<gu, 256>>>(d_samp.p, ds->dev.perm, d_cnt.p + (size_t)t0 * cntStride, cntStride, n, d_bad);
             launches++;
+            t0 += cnt;
           }
           int bad = 0;
           RF_CUDA(cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost));
