@@ -7,7 +7,7 @@
  * This is a from-scratch restatement (plain C99, scalar, one thread) of what the reference
  * computes on the hot path, written against the behaviour of the files below (paths relative to
  * /root/reference/src; rf.c = randomForestSRC.c, sc.c = splitCustom.c).  It is pinned against
- * the reference itself: tests/test_oracle_vs_ref.py runs the UNMODIFIED reference
+ * the reference itself: tests/test_oracle.py runs the UNMODIFIED reference
  * (oracle/_ref/librfslam_ref.so, built by oracle/Makefile) and this file on the same seeded
  * inputs and requires identical forests; tests/golden/ holds outputs of the reference for the
  * GPU box, where /root/reference does not exist.
