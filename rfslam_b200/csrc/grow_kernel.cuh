@@ -97,6 +97,7 @@ constexpr uint32_t kFactorFlag = 0x80000000u;   // Rec::parm of a factor split: 
 #endif
 constexpr int kSmallMax = RF_SMALL_MAX;      // nodes with <= this many entries are scored entirely out of shared memory
 constexpr int kLocalMax = 256;      // small nodes up to this many entries also take covariates with > 256 distinct values (local ranks)      // nodes with <= this many entries are scored entirely out of shared memory
+constexpr int kTileThreads = 256;   // lanes of a sorted-walk tile (the wide-covariate path runs in the 256-thread builds only)
 constexpr int kSparseRatio = 12;    // a node with fewer than n / kSparseRatio entries reads the row-major mirror of the table
 constexpr int kProfSlots = 96;   // 64..79: the phase slots again, restricted to nodes with < 64 entries   // 0..15 phases, 16..47 node time by log2(len), 48..63 node count by log2(len)/2
 
@@ -243,6 +244,7 @@ struct GrowSmem {
   double *tabL, *tabR;               // small nodes: per-candidate term tables [ncmax][kTabSlots][hb], laid over the whole histogram region
   // sorted-walk tile arrays (alias the small-node staging: the two paths never overlap in time)
   double *tileTL, *tileTR, *tileDelta; uint32_t *tileKey, *radixBase; uint8_t* tileCut;
+  uint16_t *tileS, *tileSeg; uint8_t *tileO, *tileWcnt;   // sorted walk: stratum of a position, segment starts, origin lane, per-warp stratum counts
   uint16_t* pool;                    // permissible-covariate pool of the draw step (same aliasing: used between nodes only)
   uint32_t *segpos, *PN, *PE, *cN, *cE;
   double *PT, *PW, *cT, *cW, *cTL, *cTR;
@@ -281,7 +283,11 @@ __host__ __device__ inline size_t grow_smem_bytes(int ncmax, int K, int hb, int 
   b += (size_t)ncmax * tabSlots * 8 * 4;       // smk
   b += KS * 8 * 6;                             // PT PW cT cW cTL cTR
   b += KS * 4 * 5;                             // segpos PN PE cN cE
-  b += (size_t)kSmallMax * (16 + 4 + (size_t)ncmax) + 32;  // small-node staging (>= the 8.5 KB of sorted-walk tiles aliased onto it)
+  {                                            // small-node staging; the sorted-walk tile arrays are aliased onto it
+    const size_t stage = (size_t)kSmallMax * (16 + 4 + (size_t)ncmax) + 32;
+    const size_t tiles = (size_t)kTileThreads * (8 * 3 + 4 + 1 + 2 + 1) + 256 * 4 + (KS + 2) * 2 + (size_t)(kTileThreads / 32) * KS + 64;
+    b += stage > tiles ? stage : tiles;
+  }
   b = (b + 15) & ~(size_t)15;
   b += (size_t)subMax * (4 + 16 + (size_t)tilePitch + 2) + 32;   // staged subtree
   b = (b + 15) & ~(size_t)15;
@@ -297,6 +303,7 @@ __device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb, i
   m.subMax = subMax; m.tilePitch = tilePitch;
   const size_t hsz = (size_t)ncmax * hb * m.hs;
   size_t KS = (size_t)K + 2;
+  uintptr_t tileEnd = 0;
   double* d = (double*)raw;
   m.sL = d; d += (size_t)ncmax * hb;
   m.sR = d; d += (size_t)ncmax * hb;
@@ -318,8 +325,13 @@ __device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb, i
   {
     uintptr_t al = ((uintptr_t)u + 7) & ~(uintptr_t)7;
     u = (uint32_t*)al;
-    m.tileTL = (double*)u; m.tileTR = m.tileTL + kThreads; m.tileDelta = m.tileTR + kThreads;
-    m.tileKey = (uint32_t*)(m.tileDelta + kThreads); m.radixBase = m.tileKey + kThreads; m.tileCut = (uint8_t*)(m.radixBase + 256);
+    // (extents for kTileThreads = 256 lanes in every build: the sorted walk only ever runs in the 256-thread builds, and the
+    // host sizes the launch with this same layout)
+    m.tileTL = (double*)u; m.tileTR = m.tileTL + kTileThreads; m.tileDelta = m.tileTR + kTileThreads;
+    m.tileKey = (uint32_t*)(m.tileDelta + kTileThreads); m.radixBase = m.tileKey + kTileThreads; m.tileCut = (uint8_t*)(m.radixBase + 256);
+    m.tileS = (uint16_t*)(m.tileCut + kTileThreads); m.tileSeg = m.tileS + kTileThreads;
+    m.tileO = (uint8_t*)(m.tileSeg + KS + 2); m.tileWcnt = m.tileO + kTileThreads;
+    tileEnd = (uintptr_t)(m.tileWcnt + (size_t)(kTileThreads / 32) * KS);
     m.pool = (uint16_t*)u;
   }
   {
@@ -330,6 +342,7 @@ __device__ inline GrowSmem carve(unsigned char* raw, int ncmax, int K, int hb, i
   m.smEnt = u; u += kSmallMax;
   m.smCodes = (uint8_t*)u;
   u = (uint32_t*)(m.smCodes + (size_t)kSmallMax * ncmax);
+  if ((uintptr_t)u < tileEnd) u = (uint32_t*)tileEnd;             // (one candidate: the sorted-walk tile arrays are the larger alias)
   {
     uintptr_t al = ((uintptr_t)u + 15) & ~(uintptr_t)15;
     m.stRec = (SmallRec*)al;
@@ -794,6 +807,7 @@ __device__ inline void sort_candidate(const NodeCtx& c, int ci, uint32_t len) {
   const int cov = s->candCov[ci];
   uint32_t *ks, *vs;
   sort_node_codes(c.w, c.tree, s, m, c.list, len, ci, ks, vs);
+  RF_PROFC(14);
   // nsplit > 0 on a covariate with more distinct values than nsplit: only the DRAWN cut ordinals (ascending, 1-based rank of
   // the distinct value the cut follows; node_prologue_nsplit) are candidates (rf.c:14533-14564)
   const bool drawn = kSeq && c.g.seqDraw && s->candMask[ci] && s->facN[ci] > 0;
@@ -815,47 +829,108 @@ __device__ inline void sort_candidate(const NodeCtx& c, int ci, uint32_t len) {
   int have = s->have; double best = s->bestDelta; uint32_t bestKey = 0; int gotBest = 0;   // warp 0's view
   int totalCuts = 0;
   int emitted = s->cutsSeen;
+  // The walk, one tile of kThreads code-sorted entries at a time.  A cut's statistic is the sum over strata of the terms of
+  // each stratum's LAST row at or before the cut, and a row's terms need its own stratum's running statistics -- sixteen
+  // interleaved prefix sums along one order.  Per tile the entries are therefore regrouped by stratum (a stable rank:
+  // __match_any inside the warp, per-warp counts across warps), ONE segmented scan gives every row its stratum's
+  // statistics (carried across tiles per stratum), the rule terms are evaluated once per row, and a row hands the cut
+  // order the CHANGE it makes to its stratum's terms; one plain scan over the tile on top of the exact sum of the strata's
+  // carried terms gives every position's statistic.  (It used to be three block scans and eleven barriers per stratum and
+  // tile, every entry taking part in every stratum's scans: 65 % of the kernel on a continuous 1 M x 50 table.)
+  const int KB = c.Kloop;                                            // stratum bins of a tile; invalid lanes keep their own slot
+  unsigned long long* qNE = (unsigned long long*)m.tileTL;
+  double* qT = m.tileTR; double* qW = m.tileDelta; double* qInc = m.tileTL;
+  uint16_t* qS = m.tileS; uint8_t* qO = m.tileO; uint16_t* segStart = m.tileSeg; uint8_t* wcnt = m.tileWcnt;
   for (uint32_t t = 0; t < ntiles; t++) {
     uint32_t j = t * kThreads + tid;
     bool valid = j < len;
-    uint32_t key = 0, mult = 0, e = 0; int sa = 0; double tt = 0.0;
+    uint32_t key = 0; int a0 = KB;
+    unsigned long long vne = 0ull; double vT = 0.0, vW = 0.0;
     bool cut = false;
     if (valid) {
       key = ks[j];
-      uint32_t ent = c.list[vs[j]];
-      uint32_t row = ent & kRowMask; mult = (ent >> kRowBits) + 1u;
-      e = c.d.ev[row]; tt = c.unit ? 1.0 : c.d.rt[row];
-      sa = c.strat ? (int)c.d.strat[row] : 1;
+      const uint32_t ent = c.list[vs[j]];
+      const uint32_t row = ent & kRowMask, mult = (ent >> kRowBits) + 1u;
+      const RowRec rr = c.d.rowrec[row];
+      const uint32_t e = rr.es & 1u;
+      a0 = c.strat ? (int)(rr.es >> 8) : 0;
+      const double tt = c.unit ? 1.0 : rr.rt;
+      vne = ((unsigned long long)mult << 32) | (unsigned long long)(e ? mult : 0u);
+      vT = (double)mult * tt; vW = e ? vT : 0.0;
       cut = (j + 1 < len) && (ks[j + 1] != key);
     }
-    double accL = 0.0, accR = 0.0;
-    for (int a = 1; a <= c.Kloop; a++) {
-      if (m.PE[a] == 0) continue;                            // uniform: PE is shared
-      bool f = valid && sa == a;
-      unsigned long long vne = f ? (((unsigned long long)mult << 32) | (unsigned long long)(e ? mult : 0u)) : 0ull;
-      double vT = f ? (double)mult * tt : 0.0;
-      double vW = (f && e) ? (double)mult * tt : 0.0;
-      unsigned long long tne; double totT, totW;
-      unsigned long long ine = block_incl_scan<unsigned long long>(vne, s->scrU, tne);
-      double iT = block_incl_scan<double>(vT, s->scrD, totT);
-      double iW = block_incl_scan<double>(vW, s->scrD, totW);
-      uint32_t LN = (uint32_t)(ine >> 32) + m.cN[a], LE = (uint32_t)(ine & 0xffffffffu) + m.cE[a];
-      double LT = iT + m.cT[a], LW = iW + m.cW[a];
-      if (f) {
-        m.tileTL[tid] = side_term(c.bayes, (double)LE, (double)LN, LT, LW, c.g.alpha, c.beta);
-        m.tileTR[tid] = side_term(c.bayes, (double)(m.PE[a] - LE), (double)(m.PN[a] - LN), m.PT[a] - LT, m.PW[a] - LW, c.g.alpha, c.beta);
-      }
-      int src = block_incl_scan_max(f ? tid : -1, s->scrI);
-      __syncthreads();
-      double myL = (src >= 0) ? m.tileTL[src] : m.cTL[a];
-      double myR = (src >= 0) ? m.tileTR[src] : m.cTR[a];
-      if (cut) { accL += myL; accR += myR; }
-      __syncthreads();
-      if (tid == kThreads - 1) {
-        m.cN[a] = LN; m.cE[a] = LE; m.cT[a] = LT; m.cW[a] = LW; m.cTL[a] = myL; m.cTR[a] = myR;
-      }
-      __syncthreads();
+    // (1) stable rank by stratum inside the tile
+    for (int i = tid; i < kWarps * KB; i += kThreads) wcnt[i] = 0;
+    double bsum = 0.0;                                               // exact sum of the strata's carried terms (strata with events)
+    for (int a = 1 + tid; a <= KB; a += kThreads) if (m.PE[a] > 0) bsum += m.cTL[a] + m.cTR[a];
+    const double base = block_sum<double>(bsum, s->scrD);            // (its barriers also publish the zeroed counts)
+    const unsigned peers = __match_any_sync(0xffffffffu, a0);
+    const int rankW = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rankW == 0) wcnt[wid * KB + a0] = (uint8_t)__popc(peers);
+    __syncthreads();
+    uint32_t tot = 0;
+    if (tid < KB) {
+      uint32_t run = 0;
+      for (int w2 = 0; w2 < kWarps; w2++) { const uint32_t cw = wcnt[w2 * KB + tid]; wcnt[w2 * KB + tid] = (uint8_t)run; run += cw; }
+      tot = run;
     }
+    uint32_t totAll;
+    const uint32_t incl = block_incl_scan<uint32_t>(tot, (uint32_t*)s->scrI, totAll);
+    if (tid < KB) segStart[tid] = (uint16_t)(incl - tot);
+    __syncthreads();
+    const int ps = valid ? (int)segStart[a0] + (int)wcnt[wid * KB + a0] + rankW : tid;   // (valid entries fill [0, totAll), the tail keeps its slots)
+    qNE[ps] = vne; qT[ps] = vT; qW[ps] = vW; qS[ps] = (uint16_t)a0; qO[ps] = (uint8_t)tid;
+    __syncthreads();
+    // (2) segmented inclusive scan in stratum order: thread = position
+    const int sp = qS[tid];
+    const bool pvalid = sp < KB;
+    const bool head = tid == 0 || qS[tid - 1] != sp;
+    unsigned long long ine = qNE[tid]; double iT = qT[tid], iW = qW[tid];
+    const unsigned hbits = __ballot_sync(0xffffffffu, head);
+    const unsigned hm = hbits & (0xFFFFFFFFu >> (31 - lane));
+    const int startLane = hm ? 31 - __clz(hm) : -1;                   // -1: my segment began in an earlier warp
+    const int lim = startLane < 0 ? 0 : startLane;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long une = __shfl_up_sync(0xffffffffu, ine, o);
+      const double uT = __shfl_up_sync(0xffffffffu, iT, o), uW = __shfl_up_sync(0xffffffffu, iW, o);
+      if (lane - o >= lim) { ine += une; iT += uT; iW += uW; }
+    }
+    if (lane == 31) { s->scrU[wid] = ine; s->scrD[wid] = iT; s->scrD[kWarps + wid] = iW; }
+    if (lane == 0) s->scrI[wid] = hbits != 0u ? 1 : 0;
+    __syncthreads();
+    if (startLane < 0) {                                              // add the open segment's part in the warps before mine
+      for (int w2 = wid - 1; w2 >= 0; w2--) {
+        ine += s->scrU[w2]; iT += s->scrD[w2]; iW += s->scrD[kWarps + w2];
+        if (s->scrI[w2]) break;
+      }
+    }
+    // (3) the row's stratum statistics (carried across tiles), its terms, and the change it makes to its stratum's terms
+    const int a = sp + 1;
+    double tL = 0.0, tR = 0.0; uint32_t LN = 0, LE = 0; double LT = 0.0, LW = 0.0;
+    const bool ev = pvalid && m.PE[a] > 0;
+    if (pvalid) { LN = (uint32_t)(ine >> 32) + m.cN[a]; LE = (uint32_t)(ine & 0xffffffffu) + m.cE[a]; LT = iT + m.cT[a]; LW = iW + m.cW[a]; }
+    if (__any_sync(0xffffffffu, ev)) {
+      const double xL = side_term(c.bayes, (double)LE, (double)LN, LT, LW, c.g.alpha, c.beta);
+      const double xR = ev ? side_term(c.bayes, (double)(m.PE[a] - LE), (double)(m.PN[a] - LN), m.PT[a] - LT, m.PW[a] - LW, c.g.alpha, c.beta) : 0.0;
+      if (ev) { tL = xL; tR = xR; }
+    }
+    __syncthreads();                                                  // (every thread has read its qT / qW / scratch)
+    qT[tid] = tL; qW[tid] = tR;
+    __syncthreads();
+    double inc = 0.0;
+    if (ev) {
+      const double pL = head ? m.cTL[a] : qT[tid - 1], pR = head ? m.cTR[a] : qW[tid - 1];
+      inc = (tL - pL) + (tR - pR);
+    }
+    const bool tail = pvalid && (tid == kThreads - 1 || qS[tid + 1] != sp);
+    __syncthreads();                                                  // (carries and neighbours read before they change)
+    qInc[qO[tid]] = inc;                                              // back to the cut order
+    if (tail) { m.cN[a] = LN; m.cE[a] = LE; m.cT[a] = LT; m.cW[a] = LW; if (ev) { m.cTL[a] = tL; m.cTR[a] = tR; } }
+    __syncthreads();
+    double tsum;
+    const double sIncl = block_incl_scan<double>(qInc[tid], s->scrD, tsum);
+    const double stat = base + sIncl;                                 // sum over strata of (left term + right term) at this position
     if (drawn) {                                                     // keep a cut only if its ordinal was drawn
       int tot;
       const int inc = block_incl_scan<int>(cut ? 1 : 0, s->scrI, tot);
@@ -868,7 +943,8 @@ __device__ inline void sort_candidate(const NodeCtx& c, int ci, uint32_t len) {
       cutBase += (uint32_t)tot;
       __syncthreads();
     }
-    m.tileDelta[tid] = cut ? (accL + accR - statP) * wgt : 0.0;
+    __syncthreads();                                                  // (the scan has read every slot of qInc / the scratch)
+    m.tileDelta[tid] = cut ? (stat - statP) * wgt : 0.0;
     m.tileCut[tid] = cut ? 1 : 0;
     m.tileKey[tid] = key;
     __syncthreads();

@@ -18,7 +18,7 @@ from rfslam_b200 import capi
 buf = (C.c_uint64*96)()
 k = capi.lib().rfslam_b200_last_profile(buf, 96)
 if k:
-    names = ["root","gate+draw","segpos+zero","hist","summary+wait","sm:presence","track","sm:rows","part_count","part_scatter","leaf","split_book","x","x","small_list","sm:cuts"]
+    names = ["root","gate+draw","segpos+zero","hist","summary+wait","sm:presence","track","sm:rows|sort:walk","part_count","part_scatter","leaf","split_book","x","x","sort:radix","sm:cuts"]
     tot = sum(buf[i] for i in list(range(12))+[14,15])
     print("phase cycles (sum over trees), total %.3e" % tot)
     for i,nm in enumerate(names): print(f"  {nm:14s} {buf[i]:.3e} {100*buf[i]/max(tot,1):5.1f}%")
