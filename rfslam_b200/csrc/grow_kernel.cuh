@@ -707,14 +707,19 @@ __device__ inline void track_combine_all(const NodeCtx& c, int nc) {
 
 // ---- sorted-walk path for covariates with more than kHistBins distinct values ----------------
 __device__ inline void radix_pass(const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout,
-                                  uint32_t len, int shift, GrowShared* s, uint32_t* rbase) {
+                                  uint32_t len, int shift, GrowShared* s, uint32_t* rbase, uint32_t* dOld, void* wdRaw) {
   const int tid = vtid(), lane = lane_id(), wid = warp_id();
   __syncthreads();
   constexpr int kDigPer = (256 + kThreads - 1) / kThreads;   // digits owned by one thread (consecutive); threads past digit 255 own none
   const bool owns = tid * kDigPer < 256;
   for (int q = 0; q < kDigPer; q++) if (owns) rbase[tid * kDigPer + q] = 0;
   __syncthreads();
-  for (uint32_t i = tid; i < len; i += kThreads) atomicAdd(&rbase[(kin[i] >> shift) & 255u], 1u);
+  for (uint32_t i = tid; i - (uint32_t)lane < len; i += kThreads) {  // digit histogram, one atomic per distinct digit of a warp's 32 entries
+    const bool v = i < len;
+    const uint32_t dg = v ? ((kin[i] >> shift) & 255u) : (0x100u + (uint32_t)lane);
+    const unsigned pr = __match_any_sync(0xffffffffu, dg);
+    if (v && (pr & ((1u << lane) - 1u)) == 0u) atomicAdd(&rbase[dg], (uint32_t)__popc(pr));
+  }
   __syncthreads();
   uint32_t cnt[kDigPer]; uint32_t mine = 0;
   for (int q = 0; q < kDigPer; q++) { cnt[q] = owns ? rbase[tid * kDigPer + q] : 0u; mine += cnt[q]; }
@@ -724,6 +729,10 @@ __device__ inline void radix_pass(const uint32_t* kin, const uint32_t* vin, uint
   uint32_t run = (uint32_t)(inc - mine);
   for (int q = 0; q < kDigPer; q++) { if (owns) rbase[tid * kDigPer + q] = run; run += cnt[q]; }
   __syncthreads();
+  // stable scatter, one tile of kThreads entries at a time: the rank of an entry among its tile's entries of the same digit is
+  // its rank inside the warp (__match_any) plus the counts of the warps before it (a [warp][digit] byte table, prefixed by
+  // the digit's own thread) -- three barriers per tile (the warps used to take turns: one barrier per warp and tile)
+  uint8_t* wd = (uint8_t*)wdRaw;                                     // [kWarps][256]
   const uint32_t ntiles = (len + kThreads - 1) / kThreads;
   for (uint32_t t = 0; t < ntiles; t++) {
     uint32_t i = t * kThreads + tid;
@@ -731,18 +740,29 @@ __device__ inline void radix_pass(const uint32_t* kin, const uint32_t* vin, uint
     uint32_t key = valid ? kin[i] : 0u;
     uint32_t val = valid ? vin[i] : 0u;
     uint32_t dgt = valid ? ((key >> shift) & 255u) : (0x100u + (uint32_t)lane);
-    uint32_t pos = 0;
-    for (int wv = 0; wv < kWarps; wv++) {           // warps take turns so equal digits keep their order
-      if (wid == wv) {
-        unsigned peers = __match_any_sync(0xffffffffu, dgt);
-        uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-        if (valid) pos = rbase[dgt] + rank;
-        __syncwarp();
-        if (valid && rank == 0) rbase[dgt] += __popc(peers);
+    for (int q = tid; q < kWarps * 64; q += kThreads) ((uint32_t*)wd)[q] = 0u;
+    __syncthreads();
+    const unsigned peers = __match_any_sync(0xffffffffu, dgt);
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rank == 0) wd[wid * 256 + dgt] = (uint8_t)__popc(peers);              // 1..32
+    __syncthreads();
+    for (int q = 0; q < kDigPer; q++) {
+      if (owns) {
+        const int dg = tid * kDigPer + q;
+        const uint32_t old = rbase[dg];
+        uint32_t run = 0;
+        for (int wv = 0; wv < kWarps; wv++) {                          // counts -> exclusive prefix over the warps (<= 224: a byte)
+          const uint32_t cell = wd[wv * 256 + dg];
+          wd[wv * 256 + dg] = (uint8_t)run;
+          run += cell;
+        }
+        dOld[dg] = old;
+        rbase[dg] = old + run;
       }
-      __syncthreads();
     }
-    if (valid) { kout[pos] = key; vout[pos] = val; }
+    __syncthreads();
+    if (valid) { const uint32_t pos = dOld[dgt] + (uint32_t)wd[wid * 256 + dgt] + rank; kout[pos] = key; vout[pos] = val; }
+    __syncthreads();
   }
   __syncthreads();
 }
@@ -793,7 +813,7 @@ __device__ inline void sort_node_codes(const GrowWork& w, int tree, GrowShared* 
   int npass = (bits + 7) >> 3;
   ks = kA; vs = vA; uint32_t *kd = kB, *vd = vB;
   for (int ps = 0; ps < npass; ps++) {
-    radix_pass(ks, vs, kd, vd, len, 8 * ps, s, m.radixBase);
+    radix_pass(ks, vs, kd, vd, len, 8 * ps, s, m.radixBase, m.tileKey, m.tileTR);   // (tileTL is the draw step's covariate pool: the nsplit prologue sorts too)
     uint32_t* t1 = ks; ks = kd; kd = t1;
     uint32_t* t2 = vs; vs = vd; vd = t2;
   }
