@@ -431,9 +431,9 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         const int v = atoi(e);
         if (!g.has_sort) pl.kv = v == 512 ? grow_variant_t512() : v == 320 ? grow_variant_t320() : v == 128 ? grow_variant_t128() : grow_variant_t256();
       }
-      // tables with unordered factors take the FULL build (level-subset cuts); everything else the smaller ones
+      // tables with unordered factors or covariates of more than 256 distinct values take the FULL build
       const bool wantSubtree = ds->dev.rowcodes && getenv("RFSLAM_SUBTREE_MAX") && !getenv("RFSLAM_NO_SUBTREE");
-      const bool full = ds->has_factor || getenv("RFSLAM_FULL_KERNEL");
+      const bool full = ds->has_factor || g.has_sort || getenv("RFSLAM_FULL_KERNEL");
       if (full) pl.kv = grow_variant_t256f();
       const int ctasWanted = pl.kv->ctasPerSm;
       // shared memory available to one CTA's dynamic part (227 KB per SM, 1 KB reserved per CTA, GrowShared is static)
@@ -933,7 +933,7 @@ int score_node_impl(int rule, double k_for_alpha, int m, const double* x, const 
     { int ex = 0; frexp(std::max((double)m * std::max(ds->max_rt, 1e-300), 1.0), &ex); g.tscale = ldexp(1.0, 62 - ex); g.tinv = ldexp(1.0, ex - 62); }
     g.hslots = hist_slots(g.hbins); g.tabSlots = kTabSlots; g.subMax = 0; g.seqDraw = 0; g.facCuts = 0;
     const size_t smem = grow_smem_bytes(g.ncmax, ds->K, g.hbins, g.hslots, g.tabSlots, 0, 0);
-    const GrowVariant* kv = grow_variant_t256();
+    const GrowVariant* kv = grow_variant_t256f();                // the FULL build: emit mode, wide covariates
     { int perSm = 0; RF_CUDA(kv->prepare(smem, &perSm)); }
     DevBuf<uint32_t> d_lists, d_sort, d_stackPerm, d_ctab, d_nodeCount, d_leafCount, d_cursor;
     DevBuf<uint16_t> d_cnt; DevBuf<NodeEnt> d_stack; DevBuf<int> d_seedB, d_boot, d_status, d_sinkCount;

@@ -66,19 +66,20 @@ constexpr uint32_t kNone = 0xFFFFFFFFu;
 #ifndef RF_FULL
 #define RF_FULL 0
 #endif
-// The kernel exists in a build without unordered-factor support (every all-numeric table) and a FULL one (grow_t256f.cu).
-// It is instruction-fetch sensitive on its once-per-node code: merely compiling the level-subset paths of factors in
-// slowed the all-numeric case from 1.46 s to 1.56 s per 500 trees (16.3 k -> 18.8 k SASS instructions).  The other
-// optional paths (sequential draws, sorted walk, staged subtrees, emit mode, phase profile) are compile-time switches
-// too (RF_K_*), all ON: a build without any of them (10.4 k instructions) was only 2 % faster at 296 trees and FAULTED
-// when trees were time-sliced (a second tree on a CTA built a garbage root list; not understood -- see DESIGN.md), while
-// turning any two of them back on made the fault disappear.
+// The kernel exists in a LEAN build (tables whose covariates all have <= 256 distinct values and no unordered factor: every
+// benchmarked configuration) and a FULL one (grow_t256f.cu).  It is instruction-fetch sensitive on its once-per-node code:
+// merely compiling the level-subset paths of factors in slowed the all-numeric case from 1.46 s to 1.56 s per 500 trees
+// (16.3 k -> 18.8 k SASS instructions), the rebuilt sorted walk another 2 %.  So the paths a lean table never executes are
+// compile-time switches (RF_K_*): factors, the sorted walk of wide covariates and the single-node emit mode are FULL-only;
+// sequential draws, staged subtrees and the phase profile stay in both.  (A build with ALL of them off -- 10.4 k
+// instructions -- was only 2 % faster at 296 trees and FAULTED when trees were time-sliced: the second tree on a CTA read
+// garbage in-bag counts.  Not understood; the lean build as shipped passed the same stress, see DESIGN.md.)
 constexpr bool kFull = RF_FULL != 0;
 #ifndef RF_K_SORT
-#define RF_K_SORT 1
+#define RF_K_SORT RF_FULL
 #endif
 #ifndef RF_K_SINK
-#define RF_K_SINK 1
+#define RF_K_SINK RF_FULL
 #endif
 #ifndef RF_K_SUB
 #define RF_K_SUB 1
