@@ -70,10 +70,12 @@ constexpr uint32_t kNone = 0xFFFFFFFFu;
 // benchmarked configuration) and a FULL one (grow_t256f.cu).  It is instruction-fetch sensitive on its once-per-node code:
 // merely compiling the level-subset paths of factors in slowed the all-numeric case from 1.46 s to 1.56 s per 500 trees
 // (16.3 k -> 18.8 k SASS instructions), the rebuilt sorted walk another 2 %.  So the paths a lean table never executes are
-// compile-time switches (RF_K_*): factors, the sorted walk of wide covariates and the single-node emit mode are FULL-only;
-// sequential draws, staged subtrees and the phase profile stay in both.  (A build with ALL of them off -- 10.4 k
-// instructions -- was only 2 % faster at 296 trees and FAULTED when trees were time-sliced: the second tree on a CTA read
-// garbage in-bag counts.  Not understood; the lean build as shipped passed the same stress, see DESIGN.md.)
+// compile-time switches (RF_K_*): factors, the sorted walk of wide covariates, the single-node emit mode and the phase
+// profile are FULL-only (each switch measured: -3 % for the sorted walk + emit mode, -3 % for the profile stamps);
+// sequential draws and staged subtrees stay in both.  Compiling the sequential-draw path OUT (RF_K_SEQ = 0) makes
+// time-sliced launches FAULT (the second tree on a CTA reads garbage in-bag counts; bisected to this one switch, although
+// a table that never draws sequentially executes the same statements either way) -- not understood; every
+// shipped build keeps it in and passes the time-slicing stress tests.
 constexpr bool kFull = RF_FULL != 0;
 #ifndef RF_K_SORT
 #define RF_K_SORT RF_FULL
@@ -85,7 +87,7 @@ constexpr bool kFull = RF_FULL != 0;
 #define RF_K_SUB 1
 #endif
 #ifndef RF_K_PROF
-#define RF_K_PROF 1
+#define RF_K_PROF RF_FULL
 #endif
 #ifndef RF_K_SEQ
 #define RF_K_SEQ 1
