@@ -433,7 +433,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
       }
       // tables with unordered factors or covariates of more than 256 distinct values take the FULL build
       const bool wantSubtree = ds->dev.rowcodes && getenv("RFSLAM_SUBTREE_MAX") && !getenv("RFSLAM_NO_SUBTREE");
-      const bool full = ds->has_factor || g.has_sort || getenv("RFSLAM_PROFILE") || getenv("RFSLAM_FULL_KERNEL");
+      const bool full = ds->has_factor || g.has_sort || wantSubtree || getenv("RFSLAM_PROFILE") || getenv("RFSLAM_FULL_KERNEL");
       if (full) pl.kv = grow_variant_t256f();
       const int ctasWanted = pl.kv->ctasPerSm;
       // shared memory available to one CTA's dynamic part (227 KB per SM, 1 KB reserved per CTA, GrowShared is static)

@@ -72,7 +72,7 @@ constexpr uint32_t kNone = 0xFFFFFFFFu;
 // (16.3 k -> 18.8 k SASS instructions), the rebuilt sorted walk another 2 %.  So the paths a lean table never executes are
 // compile-time switches (RF_K_*): factors, the sorted walk of wide covariates, the single-node emit mode and the phase
 // profile are FULL-only (each switch measured: -3 % for the sorted walk + emit mode, -3 % for the profile stamps);
-// sequential draws and staged subtrees stay in both.  Compiling the sequential-draw path OUT (RF_K_SEQ = 0) makes
+// sequential draws stay in both (staged subtrees, opt-in and unhelpful at 10 M rows, are FULL-only too).  Compiling the sequential-draw path OUT (RF_K_SEQ = 0) makes
 // time-sliced launches FAULT (the second tree on a CTA reads garbage in-bag counts; bisected to this one switch, although
 // a table that never draws sequentially executes the same statements either way) -- not understood; every
 // shipped build keeps it in and passes the time-slicing stress tests.
@@ -84,7 +84,7 @@ constexpr bool kFull = RF_FULL != 0;
 #define RF_K_SINK RF_FULL
 #endif
 #ifndef RF_K_SUB
-#define RF_K_SUB 1
+#define RF_K_SUB RF_FULL
 #endif
 #ifndef RF_K_PROF
 #define RF_K_PROF RF_FULL
