@@ -10,6 +10,7 @@
 #include <cstring>
 #include <vector>
 
+#define RF_PASS_CAND 8            // the lean 256-thread build of this translation unit serves mtry <= 8 (make_plan)
 #include "grow_kernel.cuh"
 #include "perf.cuh"
 #include "internal.h"
@@ -431,6 +432,7 @@ int grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out
         const int v = atoi(e);
         if (!g.has_sort) pl.kv = v == 512 ? grow_variant_t512() : v == 320 ? grow_variant_t320() : v == 128 ? grow_variant_t128() : grow_variant_t256();
       }
+      if (pl.kv == grow_variant_t256() && g.ncmax > 8) pl.kv = grow_variant_t320();   // (the lean 256-thread build's histogram pass holds 8 candidates)
       // tables with unordered factors or covariates of more than 256 distinct values take the FULL build
       const bool wantSubtree = ds->dev.rowcodes && getenv("RFSLAM_SUBTREE_MAX") && !getenv("RFSLAM_NO_SUBTREE");
       const bool full = ds->has_factor || g.has_sort || wantSubtree || getenv("RFSLAM_PROFILE") || getenv("RFSLAM_FULL_KERNEL");

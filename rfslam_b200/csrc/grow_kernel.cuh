@@ -100,6 +100,11 @@ constexpr uint32_t kFactorFlag = 0x80000000u;   // Rec::parm of a factor split: 
 #endif
 constexpr int kSmallMax = RF_SMALL_MAX;      // nodes with <= this many entries are scored entirely out of shared memory
 constexpr int kLocalMax = 256;      // small nodes up to this many entries also take covariates with > 256 distinct values (local ranks)      // nodes with <= this many entries are scored entirely out of shared memory
+#ifndef RF_PASS_CAND
+#define RF_PASS_CAND 16
+#endif
+constexpr int kPassCand = RF_PASS_CAND;   // candidates the unrolled histogram pass of a large node is compiled for (8: the lean 256-thread build,
+                                          // launched only when mtry <= 8; the layout of GrowShared keeps kMaxCand slots in every build)
 constexpr int kTileThreads = 256;   // lanes of a sorted-walk tile (the wide-covariate path runs in the 256-thread builds only)
 constexpr int kSparseRatio = 12;    // a node with fewer than n / kSparseRatio entries reads the row-major mirror of the table
 constexpr int kProfSlots = 96;   // 64..79: the phase slots again, restricted to nodes with < 64 entries   // 0..15 phases, 16..47 node time by log2(len), 48..63 node count by log2(len)/2
@@ -1537,9 +1542,9 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
   if (anyHist) {
     unsigned hmask = 0u;
     for (int ci = 0; ci < nc; ci++) if (RF_CANDHIST(ci)) hmask |= 1u << ci;
-    const uint8_t* __restrict__ hptr[kMaxCand];
+    const uint8_t* __restrict__ hptr[kPassCand];
 #pragma unroll
-    for (int ci = 0; ci < kMaxCand; ci++) hptr[ci] = (ci < nc) ? (const uint8_t*)s->candPtr[ci] : nullptr;
+    for (int ci = 0; ci < kPassCand; ci++) hptr[ci] = (ci < nc) ? (const uint8_t*)s->candPtr[ci] : nullptr;
     // (candPtr / candStride already point a sparse node at the row-major mirror of the table: see the draw step)
     const size_t cstride = (size_t)s->candStride;
     const int hstride = m.hs * m.hb;
@@ -1566,7 +1571,7 @@ __device__ inline void score_node(const DevData& d, const GrowParams& g, const G
         const bool isT0 = tv == d.rt_mode;
         const unsigned long long ft = (unsigned long long)__double2ll_rn(tv * g.tscale) * (unsigned long long)mult;
 #pragma unroll
-        for (int half = 0; half < kMaxCand; half += 8) {
+        for (int half = 0; half < kPassCand; half += 8) {
           if (half < nc) {
             uint32_t raw[8];                                       // histogram candidates are byte-coded
 #pragma unroll
