@@ -37,6 +37,11 @@ extern "C" {
 #define RFSLAM_OPT_PERF        0x00000004u   /* optLow: performance of the OOB ensemble (rf.h:110) */
 #define RFSLAM_OPT_PERF_CALB   0x00000008u   /* optLow: perf.type "brier" (rf.h:111, R/utilities.R:267-269) */
 #define RFSLAM_OPT_PERF_GMN2   0x00004000u   /* optLow: perf.type "g.mean" (rf.h:122) */
+#define RFSLAM_OPT_VIMP_TYP1   0x00000100u   /* optLow: importance by permutation (rf.h:116); TYP2 = random daughters, neither = anti */
+#define RFSLAM_OPT_VIMP_TYP2   0x00000200u   /* optLow (rf.h:117): not on the accelerated path */
+#define RFSLAM_OPT_VIMP_JOIN   0x00000400u   /* optLow: joint importance (rf.h:118): not on the accelerated path */
+#define RFSLAM_OPT_VIMP_LEOB   0x01000000u   /* optLow: per-tree (Breiman-Cutler) importance (rf.h:131); clear = ensemble importance */
+#define RFSLAM_OPT_VIMP        0x02000000u   /* optLow: importance requested (rf.h:132); needs RFSLAM_OPT_PERF (rf.c:1282-1286) */
 #define RFSLAM_OPT_CLAS_RFQ    0x00008000u   /* optLow: rfq = TRUE, quantile-classifier vote (rf.h:123, rf.c:1181-1197) */
 #define RFSLAM_OPT_BOOT_TYP1   0x00080000u   /* optLow  (by.user = TYP1|TYP2, rf.c:520) */
 #define RFSLAM_OPT_BOOT_TYP2   0x00100000u
@@ -168,6 +173,12 @@ typedef struct rfslam_forest_out {
   double    membership_kernel_ms;
   double    bootstrap_ms;
   double    collective_ms;     /* all-reduce (+ gather) through comm, host clock around the device work */
+  /* vimpClas (rf.c:37, rf.c:17537): [xSize][1 + 2] permutation importance of every covariate (processDefaultGrow:
+     intrPredictorSize = xSize, rf.c:1220) with RFSLAM_OPT_PERF | RFSLAM_OPT_VIMP | RFSLAM_OPT_VIMP_TYP1 on a whole forest
+     (no tree sharding); per tree with RFSLAM_OPT_VIMP_LEOB, else from perturbed ensembles; NULL otherwise */
+  double   *vimpClas;
+  int32_t   vimp_count;
+  double    vimp_ms;           /* device time of the importance pass (not part of total_device_ms) */
 } rfslam_forest_out;
 
 int  rfslam_b200_grow(const rfslam_grow_args *args, rfslam_forest_out *out);
@@ -293,6 +304,12 @@ typedef struct rfslam_predict_out {
   int64_t   kernel_launches;
   int64_t   row_tree_visits;   /* (row, tree) pairs routed */
   int64_t   node_visits;       /* records read while routing (sum of path lengths) */
+  /* vimpClas (rf.c:37, rf.c:17537): [vimp_count = intrPredictorSize][1 + 2] permutation importance of the covariates in
+     intr_predictor, restore mode with RFSLAM_OPT_PERF | RFSLAM_OPT_VIMP | RFSLAM_OPT_VIMP_TYP1; per tree (Breiman-Cutler)
+     with RFSLAM_OPT_VIMP_LEOB, else from perturbed ensembles; NULL otherwise */
+  double   *vimpClas;
+  int32_t   vimp_count;
+  double    vimp_ms;           /* device time of the importance pass */
 } rfslam_predict_out;
 
 int  rfslam_b200_predict(const rfslam_predict_args *args, rfslam_predict_out *out);

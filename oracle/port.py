@@ -181,3 +181,39 @@ def predict(forest: Dict[str, np.ndarray], fx: np.ndarray):
     L.orc_predict(ntree, p, tid.size, _ip(tid), _ip(nid), _ip(pid), _dp(cpt), _ip(lc), _ip(rc), _ip(te), _dp(fx), m, _dp(ens), _ip(mem),
                   _ip(msz), mpt.ctypes.data_as(C.POINTER(C.c_uint)))
     return ens, mem
+
+
+def chain_seed_c(seed: int, ntree: int, restore: bool = False) -> np.ndarray:
+    """Chain-C seeds (the VIMP chain): third block of the seed LCG in grow mode, second block from 0 in restore mode."""
+    L = lib()
+    c = np.zeros(ntree, np.int32)
+    L.orc_chain_seed_c(int(seed), ntree, 1 if restore else 0, _ip(c))
+    return c
+
+
+def vimp_permute(forest: Dict[str, np.ndarray], x, y, boot, seed_c, *, intr=None, per_tree: bool = True,
+                 perf: str = "misclass", rfq: bool = False) -> np.ndarray:
+    """Permutation importance [len(intr)][3] of a trimmed forest in tree order (treeID ascending); ``boot`` [ntree][n]
+    in-bag counts, ``forest['tnCLAS']`` the leaves' class counts."""
+    L = lib()
+    x = np.ascontiguousarray(x, np.float64); y = np.ascontiguousarray(y, np.float64)
+    p, n = x.shape
+    ntree = forest["leafCount"].size
+    tid = np.ascontiguousarray(forest["treeID"], np.int32); nid = np.ascontiguousarray(forest["nodeID"], np.int32)
+    pid = np.ascontiguousarray(forest["parmID"], np.int32); cpt = np.ascontiguousarray(forest["contPT"], np.float64)
+    lc = np.ascontiguousarray(forest["leafCount"], np.int32); tc = np.ascontiguousarray(forest["tnCLAS"], np.int32)
+    msz = np.ascontiguousarray(forest.get("mwcpSZ", np.zeros(tid.size, np.int32)), np.int32)
+    mpt = np.ascontiguousarray(forest.get("mwcpPT", np.zeros(0, np.int32)), np.int32).view(np.uint32)
+    if mpt.size == 0: mpt = np.zeros(1, np.uint32)
+    boot = np.ascontiguousarray(boot, np.int32).reshape(ntree, n)
+    sc = np.ascontiguousarray(seed_c, np.int32)
+    intr = np.ascontiguousarray(np.arange(1, p + 1) if intr is None else intr, np.int32)
+    out = np.zeros(intr.size * 3, np.float64)
+    na = np.frombuffer(np.uint64(0x7FF00000000007A2).tobytes(), np.float64)[0]
+    L.orc_vimp_permute.restype = None
+    L.orc_vimp_permute.argtypes = [C.c_int, C.c_int, C.c_int, C.c_long, _pi, _pi, _pi, _pd, _pi, _pi, _pi, C.POINTER(C.c_uint), _pd, _pd, _pi, _pi,
+                                   C.c_int, _pi, C.c_int, C.c_int, C.c_int, C.c_double, _pd]
+    L.orc_vimp_permute(ntree, p, n, tid.size, _ip(tid), _ip(nid), _ip(pid), _dp(cpt), _ip(lc), _ip(tc), _ip(msz),
+                       mpt.ctypes.data_as(C.POINTER(C.c_uint)), _dp(x), _dp(y), _ip(boot), _ip(sc), int(intr.size), _ip(intr),
+                       1 if per_tree else 0, {"misclass": 0, "brier": 1, "gmean": 2}[perf], 1 if rfq else 0, na, _dp(out))
+    return out.reshape(-1, 3)

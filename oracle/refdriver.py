@@ -128,6 +128,15 @@ def split_slot(rule: int) -> int:
     return rule + 1
 
 
+# importance (R/utilities.R:150-208): OPT_VIMP 2^25, per-tree (Breiman-Cutler) adds OPT_VIMP_LEOB 2^24, "permute" TYP1 2^8,
+# "random" TYP2 2^9, "anti" neither
+def importance_bits(importance: Optional[str]) -> int:
+    if importance in (None, "none"):
+        return 0
+    kind = {"anti": 0, "permute": 1 << 8, "random": 1 << 9}[importance.split(".")[0]]
+    return (1 << 25) + kind + (0 if importance.endswith(".ensemble") else (1 << 24))
+
+
 def grow(x: np.ndarray, y: np.ndarray, risk_time: np.ndarray, stratifier: np.ndarray, *,
          rule: int = 4, ntree: int = 4, mtry: Optional[int] = None, nodesize: int = 5,
          nodedepth: int = -1, seed: int = -12345, k_for_alpha: float = 2.0,
@@ -136,7 +145,7 @@ def grow(x: np.ndarray, y: np.ndarray, risk_time: np.ndarray, stratifier: np.nda
          xtype: Optional[Sequence[str]] = None, xlevels: Optional[np.ndarray] = None,
          var_categories: Optional[np.ndarray] = None, category_weights: Optional[np.ndarray] = None,
          statistics: bool = False, sampsize: Optional[int] = None, impl: str = "ref", quants: bool = False,
-         perf: str = "misclass", rfq: bool = False) -> Dict[str, np.ndarray]:
+         perf: str = "misclass", rfq: bool = False, importance: Optional[str] = None) -> Dict[str, np.ndarray]:
     """Run the reference's rfsrcGrow.  ``x`` is [p, n] float64 (p contiguous columns of n), ``y``
     the response codes in {1.0, 2.0}.  ``samp`` ([ntree, n] int32 in-bag counts) selects
     bootstrap="by.user" (R/utilities.R:43-45 -> bits 2^19+2^20).  ``statistics`` sets OPT_NODE_STAT
@@ -161,6 +170,7 @@ def grow(x: np.ndarray, y: np.ndarray, risk_time: np.ndarray, stratifier: np.nda
     opt_low += {"misclass": 0, "brier": 1 << 3, "gmean": 1 << 14}[perf]
     if rfq:
         opt_low += (1 << 15)
+    opt_low += importance_bits(importance)
     if statistics:
         assert nthreads == 1, "spltST is only in tree order with one thread"
         opt_low += 0x08000000
@@ -266,7 +276,9 @@ def per_tree(res: Dict[str, np.ndarray]) -> Dict[int, Dict[str, np.ndarray]]:
 def predict(x: np.ndarray, y: np.ndarray, forest: Dict[str, np.ndarray], fx: Optional[np.ndarray], *,
             k_for_alpha: float = 2.0, membership: bool = True, samp: Optional[np.ndarray] = None,
             nodesize: int = 5, impl: str = "ref", quants: bool = False,
-            xtype: Optional[Sequence[str]] = None, xlevels: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
+            xtype: Optional[Sequence[str]] = None, xlevels: Optional[np.ndarray] = None,
+            importance: Optional[str] = None, xvar_imp: Optional[Sequence[int]] = None, seed: int = -1,
+            perf: str = "misclass", rfq: bool = False, nthreads: int = -1) -> Dict[str, np.ndarray]:
     """Run the reference's rfsrcPredict on a (trimmed) grow output.  ``fx`` [p, m_test] selects
     RF_PRED; ``fx=None`` is restore mode (RF_REST) (randomForestSRC.c:22361)."""
     L = lib(impl)
@@ -275,6 +287,9 @@ def predict(x: np.ndarray, y: np.ndarray, forest: Dict[str, np.ndarray], fx: Opt
     ntree = forest["leafCount"].size
     P = _Packer(impl)
     opt_low = (1 << 5) + (1 << 2)
+    opt_low += {"misclass": 0, "brier": 1 << 3, "gmean": 1 << 14}[perf] + ((1 << 15) if rfq else 0)
+    opt_low += importance_bits(importance)
+    intr = np.asarray(xvar_imp if xvar_imp is not None else (np.arange(1, p + 1) if importance_bits(importance) else []), np.int32)   # 1-based
     opt_high = (1 << 17)
     if quants:
         opt_high += (1 << 19)                  # terminal.quants incoming: tnCLAS is passed (R/utilities.R:462-483)
@@ -309,7 +324,7 @@ def predict(x: np.ndarray, y: np.ndarray, forest: Dict[str, np.ndarray], fx: Opt
     z_i = lambda: P.i(np.zeros(0, np.int32))
     z_d = lambda: P.d(np.zeros(0))
     args = [
-        P.i(0), P.i(-1), P.i(opt_low), P.i(opt_high), P.i(ntree), P.i(n), P.i(1), P.s(["C"]), P.i(2),
+        P.i(0), P.i(seed), P.i(opt_low), P.i(opt_high), P.i(ntree), P.i(n), P.i(1), P.s(["C"]), P.i(2),
         P.d(np.asarray(y, np.float64)), P.i(p), P.s(list(xtype)), P.i(np.asarray(xlevels, np.int32)),
         P.d_alias(x.reshape(-1)),
         P.d(k_for_alpha), P.i(max_boot), P.i(boot_sizes), samp_arg, P.d(np.ones(n)),
@@ -321,8 +336,8 @@ def predict(x: np.ndarray, y: np.ndarray, forest: Dict[str, np.ndarray], fx: Opt
         z_d(), z_d(), z_d(), z_d(), z_d(), z_d(),
         P.i(forest["tnCLAS"]) if (quants and "tnCLAS" in forest) else z_i(),
         P.i(1), P.i(1), P.i(0),
-        P.i(0), z_i(), partial, P.i(0), z_i(),
-        P.i(m_test), P.i(0), z_d(), fx_arg, P.i(ntree), P.i(-1),
+        P.i(int(intr.size)), P.i(intr), partial, P.i(0), z_i(),
+        P.i(m_test), P.i(0), z_d(), fx_arg, P.i(ntree), P.i(nthreads),
     ]
     assert len(args) == 58, len(args)
     arr = (C.c_void_p * 58)(*args)

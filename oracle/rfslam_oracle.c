@@ -684,6 +684,123 @@ void orc_perf_clas2(int n, const double *y, const double *ens, const int *den, d
   free(vote);
 }
 
+/* ------------------------------------------------------------ permutation importance (rf.c:2106-2218, 2258-2697)
+   Chain C (rf.c:6685-6692 grow; rf.c:6665 + 6685-6692 restore, where the seed LCG starts from 0 and chain A is
+   skipped): per tree, in the order of `intr`, the OOB rows' values of the target covariate are permuted among
+   themselves (permute(), rf.c:1974-2007: for i = m..1 the k-th still-empty slot receives i, k = ceil(ran1C * i)),
+   the OOB rows are dropped down the tree again (identifyPerturbedMembership rf.c:1713-1783) and either
+     leob = 1 ("permute"):          the tree's own OOB performance with and without the permutation is compared and the
+                                    differences averaged over trees (x e for the per-class slots, rf.c:2607-2633), or
+     leob = 0 ("permute.ensemble"): a perturbed OOB ensemble per covariate is accumulated over the trees and its
+                                    performance compared with the forest's (rf.c:2685-2694). */
+void orc_chain_seed_c(int seed, int ntree, int restore, int *seedC) {
+  unsigned s = restore ? 0u : (unsigned) abs(seed);
+  if (s >= 714025u) s %= 714025u;
+  for (int pass = restore ? 1 : 0; pass < 3; pass++)
+    for (int b = 0; b < ntree; b++) {
+      s = lcg_next(s);
+      s = lcg_next(s);
+      while (s == 0) s = lcg_next(s);
+      if (pass == 2) seedC[b] = -(int) s;
+    }
+}
+
+static long vimp_walk(long root, const int *parmID, const double *contPT, const long *child, const int *mwcpSZ, const long *mwoff,
+                      const unsigned *mwcpPT, const double *x, int n, int i, int target /* 1-based or 0 */, double shadow) {
+  long q = root;
+  while (parmID[q] != 0) {
+    double xv = (parmID[q] == target) ? shadow : x[(size_t) (parmID[q] - 1) * n + i];
+    if (mwcpSZ && mwcpSZ[q] > 0) q = ((mwcpPT[mwoff[q]] >> ((unsigned) xv - 1u)) & 1u) ? q + 1 : child[q];
+    else q = (contPT[q] - xv >= 0.0) ? q + 1 : child[q];
+  }
+  return q;
+}
+
+void orc_vimp_permute(int ntree, int p, int n, long total_nodes, const int *treeID, const int *nodeID, const int *parmID,
+                      const double *contPT, const int *leafCount, const int *tnCLAS /* [leaf][2] */, const int *mwcpSZ,
+                      const unsigned *mwcpPT, const double *x /* [p][n] */, const double *y, const int *boot /* [ntree][n] */,
+                      const int *seedC, int n_intr, const int *intr /* 1-based */, int leob, int perf_mode, int rfq, double na,
+                      double *vimp /* [n_intr][3] */) {
+  (void) p;
+  long *mwoff = NULL;
+  if (mwcpSZ) { mwoff = malloc(total_nodes * sizeof(long)); long at = 0; for (long q = 0; q < total_nodes; q++) { mwoff[q] = at; at += mwcpSZ[q]; } }
+  long *child = malloc(total_nodes * sizeof(long)), *stack = malloc((total_nodes + 1) * sizeof(long)); long sp = 0;
+  for (long q = 0; q < total_nodes; q++) {
+    child[q] = -1;
+    if (q > 0 && treeID[q] == treeID[q - 1] && parmID[q - 1] == 0) child[stack[--sp]] = q;
+    if (q > 0 && treeID[q] != treeID[q - 1]) sp = 0;
+    if (parmID[q] != 0) stack[sp++] = q;
+  }
+  double *ens = calloc((size_t) 2 * n, sizeof(double)); int *den = calloc(n, sizeof(int));
+  double *vens = leob ? NULL : calloc((size_t) n_intr * 2 * n, sizeof(double)); int *vden = leob ? NULL : calloc((size_t) n_intr * n, sizeof(int));
+  double *fens = calloc((size_t) 2 * n, sizeof(double)); int *fden = calloc(n, sizeof(int));      /* the forest's OOB ensemble */
+  double *sum = calloc((size_t) n_intr * 3, sizeof(double)); int *cnt = calloc((size_t) n_intr * 3, sizeof(int));
+  int *index = malloc((size_t) (n + 1) * sizeof(int)), *perm = malloc((size_t) (n + 2) * sizeof(int));
+  double *shadow = malloc((size_t) n * sizeof(double));
+  long root = 0, leafoff = 0;
+  for (int b = 0; b < ntree; b++) {
+    const int *bag = boot + (size_t) b * n;
+    int m = 0;
+    for (int i = 0; i < n; i++) if (bag[i] == 0) index[++m] = i;
+    ran1_t chainC; ran1_seed(&chainC, seedC[b]);
+    double perf0[3] = {na, na, na};
+    if (m > 0) {
+      /* the tree's own OOB estimate (summarizeTreePerformance rf.c:2834-2881) and its share of the forest ensemble */
+      memset(ens, 0, (size_t) 2 * n * sizeof(double)); memset(den, 0, (size_t) n * sizeof(int));
+      for (int k = 1; k <= m; k++) {
+        int i = index[k];
+        long q = vimp_walk(root, parmID, contPT, child, mwcpSZ, mwoff, mwcpPT, x, n, i, 0, 0.0);
+        const int *c = tnCLAS + 2 * (leafoff + nodeID[q] - 1);
+        double rc = (double) c[0] + (double) c[1];
+        ens[i] = (double) c[0] / rc; ens[(size_t) n + i] = (double) c[1] / rc; den[i] = 1;
+        fens[i] += ens[i]; fens[(size_t) n + i] += ens[(size_t) n + i]; fden[i]++;
+      }
+      if (leob) orc_perf_clas2(n, y, ens, den, na, perf_mode, rfq, perf0);
+      for (int v = 0; v < n_intr; v++) {
+        const int target = intr[v];
+        for (int k = 1; k <= m; k++) perm[k] = 0;
+        for (int i = m; i > 0; i--) {                                   /* permute(3, b, m, perm) */
+          unsigned k = (unsigned) ceil(orc_ran1(&chainC) * (i * 1.0));
+          int j;
+          for (j = 1; k > 0; j++) if (perm[j] == 0) k--;
+          perm[j - 1] = i;
+        }
+        for (int k = 1; k <= m; k++) shadow[index[k]] = x[(size_t) (target - 1) * n + index[perm[k]]];
+        if (leob) { memset(ens, 0, (size_t) 2 * n * sizeof(double)); }
+        for (int k = 1; k <= m; k++) {
+          int i = index[k];
+          long q = vimp_walk(root, parmID, contPT, child, mwcpSZ, mwoff, mwcpPT, x, n, i, target, shadow[i]);
+          const int *c = tnCLAS + 2 * (leafoff + nodeID[q] - 1);
+          double rc = (double) c[0] + (double) c[1];
+          if (leob) { ens[i] = (double) c[0] / rc; ens[(size_t) n + i] = (double) c[1] / rc; }
+          else { vens[((size_t) v * 2) * n + i] += (double) c[0] / rc; vens[((size_t) v * 2 + 1) * n + i] += (double) c[1] / rc; vden[(size_t) v * n + i]++; }
+        }
+        if (leob) {
+          double pv[3]; orc_perf_clas2(n, y, ens, den, na, perf_mode, rfq, pv);
+          for (int k = 0; k < 3; k++)
+            if (!isnan(pv[k]) && !isnan(perf0[k])) { sum[v * 3 + k] += pv[k] - perf0[k]; cnt[v * 3 + k]++; }
+        }
+      }
+    }
+    root += 2 * (long) leafCount[b] - 1; leafoff += leafCount[b];
+  }
+  if (leob) {
+    for (int v = 0; v < n_intr; v++) for (int k = 0; k < 3; k++)
+      vimp[v * 3 + k] = cnt[v * 3 + k] ? (k > 0 ? M_E * sum[v * 3 + k] / (double) cnt[v * 3 + k] : sum[v * 3 + k] / (double) cnt[v * 3 + k]) : na;
+  } else {
+    for (int i = 0; i < n; i++) if (fden[i]) { fens[i] /= fden[i]; fens[(size_t) n + i] /= fden[i]; }
+    double perf0[3]; orc_perf_clas2(n, y, fens, fden, na, perf_mode, rfq, perf0);
+    for (int v = 0; v < n_intr; v++) {
+      double *e = vens + (size_t) v * 2 * n; int *d = vden + (size_t) v * n;
+      for (int i = 0; i < n; i++) if (d[i]) { e[i] /= d[i]; e[(size_t) n + i] /= d[i]; } else { e[i] = e[(size_t) n + i] = na; }
+      double pv[3]; orc_perf_clas2(n, y, e, d, na, perf_mode, rfq, pv);
+      for (int k = 0; k < 3; k++) vimp[v * 3 + k] = (!isnan(pv[k]) && !isnan(perf0[k])) ? pv[k] - perf0[k] : pv[k];
+    }
+  }
+  free(mwoff); free(child); free(stack); free(ens); free(den); free(vens); free(vden); free(fens); free(fden);
+  free(sum); free(cnt); free(index); free(perm); free(shadow);
+}
+
 /* bootstrap-only entry (chain A replay) for the in-bag parity tests */
 void orc_bootstrap(int seed, int ntree, int n, int tree /* 0-based */, int *draws /* [n], 1-based row ids */) {
   int *seedA = malloc(ntree * sizeof(int)), *seedB = malloc(ntree * sizeof(int));

@@ -46,6 +46,11 @@ void     orc_chain_seeds_restore(int ntree, int *seedB);
 void     orc_bootstrap(int seed, int ntree, int n, int tree, int *draws);
 void     orc_ran1_stream(int seed, int count, float *out);
 void     orc_perf_clas(int n, const double *y, const double *ens, const int *den, double na, double *out);
+void     orc_chain_seed_c(int seed, int ntree, int restore, int *seedC);
+void     orc_vimp_permute(int ntree, int p, int n, long total_nodes, const int *treeID, const int *nodeID, const int *parmID,
+                          const double *contPT, const int *leafCount, const int *tnCLAS, const int *mwcpSZ, const unsigned *mwcpPT,
+                          const double *x, const double *y, const int *boot, const int *seedC, int n_intr, const int *intr,
+                          int leob, int perf_mode, int rfq, double na, double *vimp);
 void     orc_perf_clas2(int n, const double *y, const double *ens, const int *den, double na, int mode, int rfq, double *out);
 
 #ifdef __cplusplus

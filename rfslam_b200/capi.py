@@ -50,6 +50,7 @@ class ForestOut(C.Structure):
         ("mwcpPT", _pi), ("mwcpCT", _pi), ("mwcp_total", C.c_int64),
         ("grow_kernel_algorithmic_bytes", C.c_int64), ("membership_algorithmic_bytes", C.c_int64), ("bootstrap_algorithmic_bytes", C.c_int64),
         ("membership_kernel_ms", C.c_double), ("bootstrap_ms", C.c_double), ("collective_ms", C.c_double),
+        ("vimpClas", _pd), ("vimp_count", C.c_int32), ("vimp_ms", C.c_double),
     ]
 
 
@@ -81,7 +82,8 @@ class PredictOut(C.Structure):
     _fields_ = [("m", C.c_int32), ("ntree", C.c_int32), ("allEnsbCLS", _pd), ("allEnsbDen", _pu),
                 ("oobEnsbCLS", _pd), ("oobEnsbDen", _pu), ("perfClas", _pd), ("leafCount", _pi),
                 ("nodeMembership", _pi), ("bootMembership", _pi), ("kernel_ms", C.c_double), ("total_device_ms", C.c_double),
-                ("kernel_launches", C.c_int64), ("row_tree_visits", C.c_int64), ("node_visits", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("row_tree_visits", C.c_int64), ("node_visits", C.c_int64),
+                ("vimpClas", _pd), ("vimp_count", C.c_int32), ("vimp_ms", C.c_double)]
 
 
 # every symbol include/rfslam_b200.h declares (tests check the library exports exactly these)

@@ -24,6 +24,54 @@ void set_error(const char* fmt, ...) {
 
 }  // namespace rfslam
 
+namespace rfslam {
+// Importance inside a grow call (rf.c:20889-20910 computes it tree by tree while the forest grows; here the finished
+// forest is restored on its own training rows -- same trees, same bootstrap, the grow call's chain-C seeds).
+int grow_importance(const rfslam_grow_args* a, rfslam_forest_out* out) {
+  if (!(a->opt_low & RFSLAM_OPT_VIMP) || !(a->opt_low & RFSLAM_OPT_PERF)) return RFSLAM_OK;      // rf.c:1282-1286
+  const bool byUser = (a->opt_low & RFSLAM_OPT_BOOT_TYP1) && (a->opt_low & RFSLAM_OPT_BOOT_TYP2);
+  if (a->comm || a->tree_step > 1 || out->ntree != a->ntree || !a->finalize_ensembles) {
+    set_error("importance needs the whole forest in one process (no tree sharding) with finalized ensembles"); return RFSLAM_ENOSUP;
+  }
+  if (!a->x_data || !a->r_data) { set_error("importance needs xData / rData"); return RFSLAM_EINVAL; }
+  if (!out->treeID) { set_error("importance needs the forest records (RFSLAM_OPT_TREE)"); return RFSLAM_EINVAL; }
+  std::vector<int32_t> intr(a->x_size);
+  for (int k = 0; k < a->x_size; k++) intr[k] = k + 1;                                           // processDefaultGrow rf.c:1220
+  // chain C: third block of the seed LCG (rf.c:6685-6692)
+  std::vector<int> seedC(a->ntree);
+  {
+    unsigned s = (unsigned)abs(a->seed);
+    if (s >= 714025u) s %= 714025u;
+    for (int pass = 0; pass < 3; pass++)
+      for (int b = 0; b < a->ntree; b++) {
+        s = lcg_next(s); s = lcg_next(s);
+        while (s == 0) s = lcg_next(s);
+        if (pass == 2) seedC[b] = -(int)s;
+      }
+  }
+  rfslam_predict_args pa;
+  memset(&pa, 0, sizeof pa);
+  pa.seed = a->seed; pa.opt_low = a->opt_low; pa.opt_high = 0;
+  pa.ntree = a->ntree; pa.observation_size = a->observation_size; pa.y_size = a->y_size; pa.r_type = a->r_type; pa.r_levels = a->r_levels;
+  pa.r_data = a->r_data; pa.x_size = a->x_size; pa.x_type = a->x_type; pa.x_levels = a->x_levels; pa.x_data = a->x_data;
+  pa.k_for_alpha = a->k_for_alpha; pa.max_bootstrap_size = a->max_bootstrap_size; pa.bootstrap_size = a->bootstrap_size;
+  pa.bootstrap = byUser ? a->bootstrap : nullptr;
+  pa.total_node_count = (int32_t)out->total_nodes; pa.forest_seed = out->seed;
+  pa.treeID = out->treeID; pa.nodeID = out->nodeID; pa.parmID = out->parmID; pa.contPT = out->contPT; pa.mwcpSZ = out->mwcpSZ;
+  pa.mwcpPT = out->mwcpPT; pa.mwcp_total = out->mwcp_total;
+  pa.tnCLAS = out->tnCLAS; pa.tnCLAS_len = out->tnCLAS ? 2 * out->total_leaves : 0;
+  pa.intr_predictor_size = a->x_size; pa.intr_predictor = intr.data();
+  pa.device = a->device; pa.finalize_ensembles = 1;
+  rfslam_predict_out po;
+  const int rc = predict_forest_ex(&pa, &po, seedC.data());
+  if (rc) return rc;
+  out->vimpClas = po.vimpClas; out->vimp_count = po.vimp_count; out->vimp_ms = po.vimp_ms;
+  po.vimpClas = nullptr;
+  rfslam_b200_free_predict(&po);
+  return RFSLAM_OK;
+}
+}  // namespace rfslam
+
 using namespace rfslam;
 
 static std::mutex g_scratchMu;
@@ -65,9 +113,12 @@ void rfslam_b200_dataset_destroy(rfslam_dataset* ds) { dataset_free(ds); }
 
 int64_t rfslam_b200_dataset_bytes(const rfslam_dataset* ds) { return ds ? ds->bytes : 0; }
 
+
 int rfslam_b200_grow_resident(rfslam_dataset* ds, const rfslam_grow_args* args, rfslam_forest_out* out) {
   if (!ds || !args || !out) { set_error("null arguments"); return RFSLAM_EINVAL; }
-  return grow_forest(ds, args, out);
+  int rc = grow_forest(ds, args, out);
+  if (rc == RFSLAM_OK && (rc = grow_importance(args, out)) != RFSLAM_OK) rfslam_b200_free_forest(out);
+  return rc;
 }
 
 int rfslam_b200_grow(const rfslam_grow_args* args, rfslam_forest_out* out) {
@@ -98,6 +149,7 @@ int rfslam_b200_grow(const rfslam_grow_args* args, rfslam_forest_out* out) {
   }
   const double t1 = now();
   rc = grow_forest(ds, args, out);
+  if (rc == RFSLAM_OK && (rc = grow_importance(args, out)) != RFSLAM_OK) rfslam_b200_free_forest(out);
   const double t2 = now();
   {
     std::lock_guard<std::mutex> lk(g_scratchMu);
@@ -114,7 +166,7 @@ void rfslam_b200_free_forest(rfslam_forest_out* o) {
   if (!o) return;
   void* arrays[] = {o->tree_ids, o->treeID, o->nodeID, o->parmID, o->contPT, o->mwcpSZ, o->splitStat, o->leafCount, o->seed,
                     o->tnRCNT, o->tnACNT, o->tnCLAS, o->nodeMembership, o->bootMembership, o->rmbrMembership, o->ambrMembership,
-                    o->oobEnsbCLS, o->allEnsbCLS, o->oobEnsbDen, o->allEnsbDen, o->perfClas, o->mwcpPT, o->mwcpCT};
+                    o->oobEnsbCLS, o->allEnsbCLS, o->oobEnsbDen, o->allEnsbDen, o->perfClas, o->mwcpPT, o->mwcpCT, o->vimpClas};
   for (void* p : arrays) host_free(p);
   memset(o, 0, sizeof(*o));
 }
@@ -133,7 +185,7 @@ int rfslam_b200_predict(const rfslam_predict_args* args, rfslam_predict_out* out
 
 void rfslam_b200_free_predict(rfslam_predict_out* o) {
   if (!o) return;
-  void* arrays[] = {o->allEnsbCLS, o->allEnsbDen, o->oobEnsbCLS, o->oobEnsbDen, o->perfClas, o->leafCount, o->nodeMembership, o->bootMembership};
+  void* arrays[] = {o->allEnsbCLS, o->allEnsbDen, o->oobEnsbCLS, o->oobEnsbDen, o->perfClas, o->leafCount, o->nodeMembership, o->bootMembership, o->vimpClas};
   for (void* p : arrays) host_free(p);
   memset(o, 0, sizeof(*o));
 }

@@ -110,6 +110,10 @@ int  dataset_build(const rfslam_grow_args* a, rfslam_dataset** out, WsPool* seed
 void dataset_free(rfslam_dataset* ds);
 int  grow_forest(rfslam_dataset* ds, const rfslam_grow_args* a, rfslam_forest_out* out);
 int  predict_forest(const rfslam_predict_args* a, rfslam_predict_out* out);
+// seedC != nullptr: chain-C seeds of the grow call this restore belongs to (importance inside rfslam_b200_grow)
+int  predict_forest_ex(const rfslam_predict_args* a, rfslam_predict_out* out, const int* seedC);
+// importance after growth (api.cu): restores the finished forest on its training rows with the grow call's chain C
+int  grow_importance(const rfslam_grow_args* a, rfslam_forest_out* out);
 int  score_node_impl(int rule, double k_for_alpha, int m, const double* x, const double* response,
                      const int32_t* stratum, const double* risk_time, double* cut_value, double* delta,
                      int32_t* n_cuts, int device);

@@ -65,6 +65,31 @@ __global__ void perf_kernel(const double* oob, const uint32_t* den, const uint8_
   }
 }
 
+// One performance row [overall, class 1, class 2] from the counts of a pass over the rows (getPerformance's class
+// branch, rf.c:7954-8010): cum / ok = rows with an estimate per class and the correctly voted ones, cls = ALL rows of
+// each class, brier = sums of squared one-against-all errors.  `out` must hold NA_REAL on entry.
+inline void perf_from_counts(uint32_t opt_low, const unsigned long long* cumK, const unsigned long long* okK,
+                             const unsigned long long* cls, const double* brier, double* out) {
+  const unsigned long long cum = cumK[0] + cumK[1];
+  if (!cum) return;
+  if (opt_low & RFSLAM_OPT_PERF_CALB) {
+    const double cpv[2] = {brier[0] / (double)cum, brier[1] / (double)cum};
+    out[0] = (cpv[0] + cpv[1]) * 2.0 / 1.0;                         // result * levels / (levels - 1)
+    out[1] = cpv[0]; out[2] = cpv[1];
+  } else if (opt_low & RFSLAM_OPT_PERF_GMN2) {                      // two classes: the minority flag is always set (rf.c:16899-16903)
+    double result = 1.0;
+    for (int k = 0; k < 2; k++) {
+      const double t = (double)okK[k], denom = (double)cumK[k];     // true + false votes of the class
+      result = denom > 0 ? result * t / denom : result * (1 + t) / (1 + denom);
+    }
+    out[0] = 1.0 - sqrt(result);
+  } else {
+    out[0] = 1.0 - (double)(okK[0] + okK[1]) / (double)cum;
+    if (cls[0]) out[1] = 1.0 - (double)okK[0] / (double)cls[0];
+    if (cls[1]) out[2] = 1.0 - (double)okK[1] / (double)cls[1];
+  }
+}
+
 // perfClas [ntree][3]: NA_REAL except the last row (perfBlock = ntree, rf.c:8155).  `ev`/`inv` or `y` as in perf_kernel.
 inline double* perf_clas_table(uint32_t opt_low, int ntree, int n, const double* d_oob, const uint32_t* d_den,
                                const uint8_t* d_ev, const uint32_t* d_inv, const double* d_y, long long* launches) {
@@ -90,30 +115,9 @@ inline double* perf_clas_table(uint32_t opt_low, int ntree, int n, const double*
   if (!perf) { set_error("out of host memory"); throw CudaFail{RFSLAM_ENOMEM}; }
   const double na = rfslam_na_real();
   for (size_t k = 0; k < (size_t)ntree * 3; k++) perf[k] = na;
-  double* last = perf + (size_t)(ntree - 1) * 3;
-  const unsigned long long cum = acc.cum[0] + acc.cum[1];
-  if (opt_low & RFSLAM_OPT_PERF_CALB) {
-    if (cum) {
-      double cpv[2] = {0.0, 0.0};
-      for (int b = 0; b < kPerfBlocks; b++) { cpv[0] += brier[2 * b]; cpv[1] += brier[2 * b + 1]; }
-      cpv[0] /= (double)cum; cpv[1] /= (double)cum;
-      last[0] = (cpv[0] + cpv[1]) * 2.0 / 1.0;                      // result * levels / (levels - 1)
-      last[1] = cpv[0]; last[2] = cpv[1];
-    }
-  } else if (opt_low & RFSLAM_OPT_PERF_GMN2) {                      // two classes: the minority flag is always set (rf.c:16899-16903)
-    if (cum) {
-      double result = 1.0;
-      for (int k = 0; k < 2; k++) {
-        const double t = (double)acc.ok[k], denom = (double)acc.cum[k];   // true + false votes of the class
-        result = denom > 0 ? result * t / denom : result * (1 + t) / (1 + denom);
-      }
-      last[0] = 1.0 - sqrt(result);
-    }
-  } else if (cum) {
-    last[0] = 1.0 - (double)(acc.ok[0] + acc.ok[1]) / (double)cum;
-    if (cls[0]) last[1] = 1.0 - (double)acc.ok[0] / (double)cls[0];
-    if (cls[1]) last[2] = 1.0 - (double)acc.ok[1] / (double)cls[1];
-  }
+  double bsum[2] = {0.0, 0.0};
+  for (int b = 0; b < kPerfBlocks; b++) { bsum[0] += brier[2 * b]; bsum[1] += brier[2 * b + 1]; }
+  perf_from_counts(opt_low, acc.cum, acc.ok, cls, bsum, perf + (size_t)(ntree - 1) * 3);
   return perf;
 }
 

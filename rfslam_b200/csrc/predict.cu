@@ -257,6 +257,25 @@ struct Streams {
   }
 };
 
+}  // namespace
+}  // namespace rfslam
+#include "vimp.cuh"
+namespace rfslam {
+namespace {
+
+// chain-C seeds (rf.c:6685-6692): the third block of the seed LCG; in predict / restore mode the LCG starts from 0 and the
+// chain-A block is skipped (rf.c:6665)
+void chain_seed_c_restore(int ntree, std::vector<int>& seedC) {
+  unsigned s = 0;
+  seedC.resize(ntree);
+  for (int pass = 0; pass < 2; pass++)
+    for (int b = 0; b < ntree; b++) {
+      s = lcg_next(s); s = lcg_next(s);
+      while (s == 0) s = lcg_next(s);
+      if (pass == 1) seedC[b] = -(int)s;
+    }
+}
+
 int validate_predict(const rfslam_predict_args* a) {
   if (!a) { set_error("null arguments"); return RFSLAM_EINVAL; }
   if (a->ntree < 1 || a->total_node_count < 1 || a->x_size < 1 || a->observation_size < 1) { set_error("bad predict arguments (ntree, totalNodeCount, xSize, observationSize)"); return RFSLAM_EINVAL; }
@@ -264,7 +283,14 @@ int validate_predict(const rfslam_predict_args* a) {
   if (a->htry != 0) { set_error("htry must be 0 (rf.c:6490-6494)"); return RFSLAM_EINVAL; }
   if (a->ptn_count != 0) { set_error("pruned forests (ptnCount > 0) are outside the accelerated path"); return RFSLAM_ENOSUP; }
   if (a->y_size > 1) { set_error("the Poisson class path takes exactly one response (ySize = %d)", a->y_size); return RFSLAM_ENOSUP; }
-  if (a->intr_predictor_size > 0) { set_error("variable importance (intrPredictorSize > 0) is outside the accelerated path"); return RFSLAM_ENOSUP; }
+  if ((a->opt_low & RFSLAM_OPT_VIMP) && (a->opt_low & RFSLAM_OPT_PERF)) {       // without OPT_PERF the reference drops the request (rf.c:1409-1413)
+    if (!(a->opt_low & RFSLAM_OPT_VIMP_TYP1) || (a->opt_low & RFSLAM_OPT_VIMP_TYP2)) { set_error("importance: only the permutation type (\"permute\", \"permute.ensemble\") is on the accelerated path"); return RFSLAM_ENOSUP; }
+    if (a->opt_low & RFSLAM_OPT_VIMP_JOIN) { set_error("joint importance is outside the accelerated path"); return RFSLAM_ENOSUP; }
+    if (a->fobservation_size > 0) { set_error("importance on held-out rows is outside the accelerated path (restore mode and grow are)"); return RFSLAM_ENOSUP; }
+    if (a->intr_predictor_size < 0 || (a->intr_predictor_size > 0 && !a->intr_predictor)) { set_error("intrPredictor missing"); return RFSLAM_EINVAL; }
+    for (int k = 0; k < a->intr_predictor_size; k++)
+      if (a->intr_predictor[k] < 1 || a->intr_predictor[k] > a->x_size) { set_error("intrPredictor[%d] = %d is outside 1..xSize (rf.c:19248)", k, a->intr_predictor[k]); return RFSLAM_EINVAL; }
+  }
   if (a->partial_type != 0 || a->partial_length != 0) { set_error("partial plots are outside the accelerated path"); return RFSLAM_ENOSUP; }
   if (a->sobservation_size > 0) { set_error("subsetted restore (sobservationSize > 0) is outside the accelerated path"); return RFSLAM_ENOSUP; }
   if (a->x_type) for (int c = 0; c < a->x_size; c++) {
@@ -279,7 +305,9 @@ int validate_predict(const rfslam_predict_args* a) {
 
 }  // namespace
 
-int predict_forest(const rfslam_predict_args* a, rfslam_predict_out* out) {
+int predict_forest(const rfslam_predict_args* a, rfslam_predict_out* out) { return predict_forest_ex(a, out, nullptr); }
+
+int predict_forest_ex(const rfslam_predict_args* a, rfslam_predict_out* out, const int* seedC_grow) {
   memset(out, 0, sizeof(*out));
   int rc = validate_predict(a);
   if (rc) return rc;
@@ -510,6 +538,96 @@ int predict_forest(const rfslam_predict_args* a, rfslam_predict_out* out) {
     if (restore && a->finalize_ensembles && (a->opt_low & RFSLAM_OPT_PERF)) {
       h_perf = perf_clas_table(a->opt_low, ntree, n, d_oob, d_oobDen, nullptr, nullptr, d_y, &launches);
     }
+    // ---- permutation importance (restore mode; the grow entry comes here with its own chain-C seeds) ----
+    double* h_vimp = nullptr;
+    const int nIntr = a->intr_predictor_size;
+    if (restore && h_perf && (a->opt_low & RFSLAM_OPT_VIMP) && nIntr > 0) {
+      const bool leob = (a->opt_low & RFSLAM_OPT_VIMP_LEOB) != 0;
+      RF_CUDA(cudaEventRecord(st.k0));
+      Buf b_x, b_oobc, b_seedC, b_intr, b_scr, b_acc, b_vens, b_vden;
+      double* d_x = b_x.alloc<double>((size_t)p * n);
+      RF_CUDA(cudaMemcpy(d_x, a->x_data, (size_t)p * n * 8, cudaMemcpyHostToDevice));
+      int* d_oobc = b_oobc.alloc<int>(ntree);
+      vimp_oob_count_kernel<<<ntree, kVimpThreads>>>(d_cnt, cstride, n, ntree, d_oobc);
+      std::vector<int> oobc(ntree);
+      RF_CUDA(cudaMemcpy(oobc.data(), d_oobc, (size_t)ntree * 4, cudaMemcpyDeviceToHost));
+      const int maxOob = std::max(1, *std::max_element(oobc.begin(), oobc.end()));
+      const int W0 = (maxOob + 31) >> 5, G1 = (W0 + 31) >> 5, G2 = (G1 + 31) >> 5;
+      const size_t smem = ((size_t)W0 + G1 + G2) * 4;
+      if (smem > 200 * 1024) { host_free(h_perf); set_error("importance: %d OOB rows in one tree exceed the %d the permutation's shared-memory index holds", maxOob, 200 * 1024 * 8 * 32 / 33); throw CudaFail{RFSLAM_ENOSUP}; }
+      RF_CUDA(cudaFuncSetAttribute(vimp_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int perSm = 0, nsm = 0, dev = 0;
+      RF_CUDA(cudaGetDevice(&dev));
+      RF_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+      RF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, vimp_tree_kernel, kVimpThreads, smem));
+      const int grid = std::max(1, std::min(ntree, nsm * std::max(1, perSm)));
+      std::vector<int> seedC;
+      if (seedC_grow) seedC.assign(seedC_grow, seedC_grow + ntree); else chain_seed_c_restore(ntree, seedC);
+      std::vector<int> intr0(nIntr);
+      for (int k = 0; k < nIntr; k++) intr0[k] = a->intr_predictor[k] - 1;
+      int* d_seedC = b_seedC.alloc<int>(ntree); int* d_intr = b_intr.alloc<int>(nIntr);
+      RF_CUDA(cudaMemcpy(d_seedC, seedC.data(), (size_t)ntree * 4, cudaMemcpyHostToDevice));
+      RF_CUDA(cudaMemcpy(d_intr, intr0.data(), (size_t)nIntr * 4, cudaMemcpyHostToDevice));
+      unsigned long long cls[2] = {0, 0};
+      for (int i = 0; i < n; i++) cls[a->r_data[i] == 2.0 ? 1 : 0]++;
+      VimpArgs va{};
+      va.ntree = ntree; va.p = p; va.n = n; va.nIntr = nIntr;
+      va.nodeOff = d_noff; va.slotOfTree = d_sot; va.leafOff = d_loff; va.rec = d_rec; va.tnCLAS = d_clas;
+      va.cnt = d_cnt; va.cstride = cstride; va.x = d_x; va.y = d_y; va.seedC = d_seedC; va.intr = d_intr;
+      va.maxOob = maxOob; va.scratch = b_scr.alloc<uint32_t>((size_t)grid * 3 * maxOob);
+      va.leob = leob ? 1 : 0; va.rfqMinority = -1; va.rfqThreshold = 0.0;
+      if (a->opt_low & RFSLAM_OPT_CLAS_RFQ) { va.rfqMinority = cls[1] < cls[0] ? 1 : 0; va.rfqThreshold = (double)cls[va.rfqMinority] / (double)n; }
+      va.acc = b_acc.alloc<VimpAcc>((size_t)ntree * (nIntr + 1));
+      if (!leob) {
+        va.vens = b_vens.alloc<double>((size_t)nIntr * 2 * n); va.vden = b_vden.alloc<uint32_t>((size_t)nIntr * n);
+        RF_CUDA(cudaMemsetAsync(va.vens, 0, (size_t)nIntr * 2 * n * 8)); RF_CUDA(cudaMemsetAsync(va.vden, 0, (size_t)nIntr * n * 4));
+      }
+      vimp_tree_kernel<<<grid, kVimpThreads, smem>>>(va);
+      launches += 2;
+      RF_CUDA(cudaGetLastError());
+      h_vimp = (double*)host_alloc((size_t)nIntr * 3 * 8);
+      if (!h_vimp) { host_free(h_perf); set_error("out of host memory"); throw CudaFail{RFSLAM_ENOMEM}; }
+      const double na = rfslam_na_real();
+      if (leob) {
+        // per tree: performance of the tree's own OOB estimate with covariate v permuted minus without, averaged over the
+        // trees where both exist; the per-class slots are scaled by e (rf.c:2599-2633)
+        std::vector<VimpAcc> acc((size_t)ntree * (nIntr + 1));
+        RF_CUDA(cudaMemcpy(acc.data(), va.acc, acc.size() * sizeof(VimpAcc), cudaMemcpyDeviceToHost));
+        auto row = [&](const VimpAcc& c, double* o) {
+          o[0] = o[1] = o[2] = na;
+          const unsigned long long cum[2] = {c.cum[0], c.cum[1]}, ok[2] = {c.ok[0], c.ok[1]};
+          perf_from_counts(a->opt_low, cum, ok, cls, c.brier, o);
+        };
+        std::vector<double> sum((size_t)nIntr * 3, 0.0); std::vector<int> cntv((size_t)nIntr * 3, 0);
+        for (int b = 0; b < ntree; b++) {
+          double p0[3]; row(acc[(size_t)b * (nIntr + 1)], p0);
+          for (int v = 0; v < nIntr; v++) {
+            double pv[3]; row(acc[(size_t)b * (nIntr + 1) + v + 1], pv);
+            for (int k = 0; k < 3; k++) if (pv[k] == pv[k] && p0[k] == p0[k]) { sum[v * 3 + k] += pv[k] - p0[k]; cntv[v * 3 + k]++; }
+          }
+        }
+        for (int v = 0; v < nIntr; v++) for (int k = 0; k < 3; k++) {
+          const int c = cntv[v * 3 + k];
+          h_vimp[v * 3 + k] = c ? (k > 0 ? M_E * sum[v * 3 + k] / (double)c : sum[v * 3 + k] / (double)c) : na;
+        }
+      } else {
+        // ensemble: the perturbed OOB ensemble of covariate v against the forest's (rf.c:2416-2470, 2685-2694)
+        const double* f0 = h_perf + (size_t)(ntree - 1) * 3;
+        for (int v = 0; v < nIntr; v++) {
+          double* ev = va.vens + (size_t)v * 2 * n; uint32_t* dv = va.vden + (size_t)v * n;
+          finalize_pred_kernel<<<(unsigned)((n + 255) / 256), 256>>>(ev, dv, (size_t)n);
+          launches++;
+          double* r = perf_clas_table(a->opt_low, 1, n, ev, dv, nullptr, nullptr, d_y, &launches);
+          for (int k = 0; k < 3; k++) h_vimp[v * 3 + k] = (r[k] == r[k] && f0[k] == f0[k]) ? r[k] - f0[k] : r[k];
+          host_free(r);
+        }
+      }
+      RF_CUDA(cudaEventRecord(st.k1));
+      RF_CUDA(cudaEventSynchronize(st.k1));
+      float ms = 0.f; RF_CUDA(cudaEventElapsedTime(&ms, st.k0, st.k1));
+      out->vimp_ms = ms;
+    }
+    out->vimpClas = h_vimp; out->vimp_count = h_vimp ? nIntr : 0;
     RF_CUDA(cudaEventRecord(st.e1));
     RF_CUDA(cudaGetLastError());
     RF_CUDA(cudaEventSynchronize(st.e1));

@@ -128,6 +128,7 @@ SEXP rfsrcGrow(SEXP traceFlag, SEXP seedPtr, SEXP optLow, SEXP optHigh, SEXP spl
   out_real(&o, "oobEnsbCLS", f.oobEnsbCLS, 2 * n);
   out_real(&o, "allEnsbCLS", f.allEnsbCLS, 2 * n);
   if (f.perfClas) out_real(&o, "perfClas", f.perfClas, 3 * T);                       /* rf.c:17454 */
+  if (f.vimpClas) out_real(&o, "vimpClas", f.vimpClas, 3 * (long) f.vimp_count);    /* rf.c:17537: [xSize][1 + levels] */
   out_int(&o, "leafCount", f.leafCount, T);
   if (a.opt_low & RF_OPT_TREE) out_int(&o, "seed", f.seed, T);
   if (f.nodeMembership) {
@@ -212,6 +213,7 @@ SEXP rfsrcPredict(SEXP traceFlag, SEXP seedPtr, SEXP optLow, SEXP optHigh, SEXP 
   if (r.oobEnsbCLS) out_real(&o, "oobEnsbCLS", r.oobEnsbCLS, 2 * m);                 /* restore mode only (rf.c:22361) */
   out_real(&o, "allEnsbCLS", r.allEnsbCLS, 2 * m);
   if (r.perfClas) out_real(&o, "perfClas", r.perfClas, 3 * T);
+  if (r.vimpClas) out_real(&o, "vimpClas", r.vimpClas, 3 * (long) r.vimp_count);
   out_int(&o, "leafCount", r.leafCount, T);
   if (r.nodeMembership) {
     out_int(&o, "nodeMembership", r.nodeMembership, T * m);

@@ -55,6 +55,9 @@ def _own(struct, field, count, dtype):
 
 
 # perf.type -> optLow bits beside OPT_PERF (R/utilities.R:260-272): "brier" 2^3, "g.mean" 2^14
+# importance -> optLow bits (R/utilities.R:150-208): OPT_VIMP 2^25, per-tree adds OPT_VIMP_LEOB 2^24, permutation OPT_VIMP_TYP1 2^8
+IMPORTANCE_BITS = {None: 0, False: 0, "none": 0, True: (1 << 25) + (1 << 24) + (1 << 8), "permute": (1 << 25) + (1 << 24) + (1 << 8),
+                   "permute.ensemble": (1 << 25) + (1 << 8)}
 PERF_BITS = {"misclass": 0, "default": 0, "standard": 0, "brier": 1 << 3, "g.mean": 1 << 14, "gmean": 1 << 14}
 
 
@@ -64,7 +67,7 @@ class _Packed:
     def __init__(self, x, y, risk_time, stratifier, *, splitrule, ntree, mtry, nodesize, nodedepth, seed, k_for_alpha,
                  membership, samp, sampsize, split_wt, device, tree_first, tree_step, finalize, nsplit=0, xvar_types=None,
                  split_stat=False, member_lists=False, var_categories=None, category_weights=None, bootstrap=None, comm=None,
-                 gather_forest=False, xvar_levels=None, perf_type="misclass", rfq=False):
+                 gather_forest=False, xvar_levels=None, perf_type="misclass", rfq=False, importance=None):
         x = np.ascontiguousarray(x, np.float64)
         assert x.ndim == 2, "x must be [p, n]: p contiguous columns of n (randomForestSRC.c:22190)"
         p, n = x.shape
@@ -102,6 +105,9 @@ class _Packed:
         a.seed = int(seed)
         a.opt_low = (1 << 5) + (1 << 2)                           # forest + perf (R/utilities.R:89-103, :260-263)
         a.opt_low |= PERF_BITS[perf_type] | ((1 << 15) if rfq else 0)   # perf.type / rfq (R/utilities.R:254-290)
+        if importance not in IMPORTANCE_BITS:
+            raise ValueError(f"importance {importance!r}: only permutation importance (\"permute\", \"permute.ensemble\") is on the accelerated path")
+        a.opt_low |= IMPORTANCE_BITS[importance]
         a.opt_high = 256 * (slot - 1) + (1 << 16)                 # split.cust bits + terminal.qualts (R/utilities.R:403-459)
         if membership:
             a.opt_high |= (1 << 6)                                # R/utilities.R:333-348
@@ -174,6 +180,9 @@ def _unpack_forest(o: ForestOut, finalized: bool = True, ntree_total: int = 0) -
         res["bootMembership"] = _own(o, "bootMembership", T * n, np.int32)
     if o.perfClas:
         res["perfClas"] = _own(o, "perfClas", (ntree_total or T) * 3, np.float64)
+    if o.vimpClas:
+        res["importance"] = _own(o, "vimpClas", int(o.vimp_count) * 3, np.float64).reshape(-1, 3)
+        res["vimp_ms"] = float(o.vimp_ms)
     return res
 
 
@@ -208,14 +217,14 @@ class ResidentCpiu:
     def grow(self, *, splitrule="poisson.split4", ntree=500, mtry=None, nodesize=5, nodedepth=-1, seed=-12345,
              k_for_alpha=2.0, membership=False, samp=None, sampsize=None, split_wt=None, tree_first=0, tree_step=0,
              finalize=True, split_stat=False, member_lists=False, nsplit=0, bootstrap=None, comm=None,
-             gather_forest=False, perf_type="misclass", rfq=False) -> Dict[str, np.ndarray]:
+             gather_forest=False, perf_type="misclass", rfq=False, importance=None) -> Dict[str, np.ndarray]:
         k = self._pk.keep
         pk = _Packed(k["x"], k["y"], k["rt"], k["st"], splitrule=splitrule, ntree=ntree, mtry=mtry, nodesize=nodesize,
                      nodedepth=nodedepth, seed=seed, k_for_alpha=k_for_alpha, membership=membership, samp=samp,
                      sampsize=sampsize, split_wt=split_wt, device=self.device, tree_first=tree_first, tree_step=tree_step,
                      finalize=finalize, split_stat=split_stat, member_lists=member_lists, nsplit=nsplit, bootstrap=bootstrap,
                      comm=comm, gather_forest=gather_forest, xvar_types=self._xvar[0], xvar_levels=self._xvar[1],
-                     perf_type=perf_type, rfq=rfq)
+                     perf_type=perf_type, rfq=rfq, importance=importance)
         out = ForestOut()
         capi.check(capi.lib().rfslam_b200_grow_resident(self.handle, C.byref(pk.args), C.byref(out)))
         res = _unpack_forest(out, finalize, int(ntree))
@@ -227,18 +236,19 @@ def rfsrc(x, y, risk_time=None, stratifier=None, *, splitrule="poisson.split4", 
           nodedepth=-1, seed=-12345, k_for_alpha=2.0, membership=False, samp=None, sampsize=None, split_wt=None,
           device=-1, tree_first=0, tree_step=0, finalize=True, nsplit=0, xvar_types=None, split_stat=False,
           member_lists=False, var_categories=None, category_weights=None, bootstrap=None, comm=None,
-          gather_forest=False, xvar_levels=None, perf_type="misclass", rfq=False) -> Dict[str, np.ndarray]:
+          gather_forest=False, xvar_levels=None, perf_type="misclass", rfq=False, importance=None) -> Dict[str, np.ndarray]:
     """Grow an RF-SLAM forest from HOST arrays through rfslam_b200_grow (upload + grow + download).
 
     x [p, n] float64 (p contiguous columns), y response codes 1.0 / 2.0, risk_time [n], stratifier [n]
     (interval number >= 1); defaults follow R/rfsrc.R:1026-1067 (k_for_alpha = 2, nodedepth unlimited,
-    mtry = ceil(sqrt(p)), bootstrap by.root unless ``samp`` is given (by.user))."""
+    mtry = ceil(sqrt(p)), bootstrap by.root unless ``samp`` is given (by.user)).  ``importance`` = "permute" (or True:
+    per-tree permutation importance) / "permute.ensemble" adds ``importance`` [p][3] = vimpClas (R/rfsrc.R:2389-2392)."""
     pk = _Packed(x, y, risk_time, stratifier, splitrule=splitrule, ntree=ntree, mtry=mtry, nodesize=nodesize,
                  nodedepth=nodedepth, seed=seed, k_for_alpha=k_for_alpha, membership=membership, samp=samp, sampsize=sampsize,
                  split_wt=split_wt, device=device, tree_first=tree_first, tree_step=tree_step, finalize=finalize, nsplit=nsplit,
                  xvar_types=xvar_types, split_stat=split_stat, member_lists=member_lists, var_categories=var_categories,
                  category_weights=category_weights, bootstrap=bootstrap, comm=comm, gather_forest=gather_forest,
-                 xvar_levels=xvar_levels, perf_type=perf_type, rfq=rfq)
+                 xvar_levels=xvar_levels, perf_type=perf_type, rfq=rfq, importance=importance)
     out = ForestOut()
     capi.check(capi.lib().rfslam_b200_grow(C.byref(pk.args), C.byref(out)))
     res = _unpack_forest(out, finalize, int(ntree))
@@ -248,14 +258,17 @@ def rfsrc(x, y, risk_time=None, stratifier=None, *, splitrule="poisson.split4", 
 
 def predict_rfsrc(forest: Dict[str, np.ndarray], fx=None, *, x=None, y=None, membership=True, device=-1, finalize=True,
                   samp=None, sampsize=None, use_tnclas=True, frow_first=0, frow_count=0, perf=True,
-                  xvar_types=None, xvar_levels=None, perf_type="misclass", rfq=False) -> Dict[str, np.ndarray]:
+                  xvar_types=None, xvar_levels=None, perf_type="misclass", rfq=False, importance=None,
+                  xvar_importance=None) -> Dict[str, np.ndarray]:
     """rfsrcPredict through the C-ABI (rfslam_b200_predict), mirroring R/generic.predict.rfsrc.R:437-534.
 
     ``forest`` is a grow result (the reference's wire format).  ``fx`` [p, m] predicts held-out rows; ``fx=None``
     RESTORES the forest on its training rows ``x`` / ``y`` (OOB + full ensembles, perfClas).  The leaf class counts
     come from ``forest["tnCLAS"]`` when present (and ``use_tnclas``), else they are rebuilt from the training rows
     with the bootstrap replayed from ``forest["seed"]`` (or ``samp``).  ``frow_first`` / ``frow_count`` select this
-    process' shard of the held-out rows (forest replicated, no collective)."""
+    process' shard of the held-out rows (forest replicated, no collective).  In restore mode ``importance`` ("permute" /
+    "permute.ensemble") adds the permutation importance [len(xvar_importance)][3] of the 1-based covariates in
+    ``xvar_importance`` (default: all), as vimp.rfsrc obtains it (R/generic.predict.rfsrc.R:1018-1021)."""
     keep = {k: np.ascontiguousarray(forest[k], np.int32) for k in ("treeID", "nodeID", "parmID", "seed")}
     keep["contPT"] = np.ascontiguousarray(forest["contPT"], np.float64)
     keep["mwcpSZ"] = np.ascontiguousarray(forest["mwcpSZ"], np.int32) if "mwcpSZ" in forest else np.zeros(keep["treeID"].size, np.int32)
@@ -264,6 +277,9 @@ def predict_rfsrc(forest: Dict[str, np.ndarray], fx=None, *, x=None, y=None, mem
     a.trace_flag = 0; a.seed = -1
     a.opt_low = ((1 << 2) if perf else 0) + (1 << 5) + PERF_BITS[perf_type] + ((1 << 15) if rfq else 0)
     a.opt_high = (1 << 17)
+    if importance not in IMPORTANCE_BITS:
+        raise ValueError(f"importance {importance!r}: only permutation importance is on the accelerated path")
+    a.opt_low |= IMPORTANCE_BITS[importance]
     if membership:
         a.opt_high |= (1 << 6)
     a.ntree = ntree; a.y_size = 1
@@ -285,6 +301,9 @@ def predict_rfsrc(forest: Dict[str, np.ndarray], fx=None, *, x=None, y=None, mem
     else:
         n = int(forest["allEnsbDen"].size) if "allEnsbDen" in forest else 1
     a.observation_size = n; a.x_size = p
+    if IMPORTANCE_BITS[importance]:
+        keep["intr"] = np.ascontiguousarray(np.arange(1, p + 1) if xvar_importance is None else xvar_importance, np.int32)
+        a.intr_predictor_size = int(keep["intr"].size); a.intr_predictor = _ip(keep["intr"])
     xtype = ("".join(xvar_types) if xvar_types is not None else "R" * p).encode(); a.x_type = xtype
     keep["xlev"] = np.zeros(p, np.int32) if xvar_levels is None else np.ascontiguousarray(xvar_levels, np.int32); a.x_levels = _ip(keep["xlev"])
     a.k_for_alpha = 2.0
@@ -326,6 +345,9 @@ def predict_rfsrc(forest: Dict[str, np.ndarray], fx=None, *, x=None, y=None, mem
         res["oobEnsbCLS"] = _take(out.oobEnsbCLS, 2 * M, np.float64); res["oobEnsbDen"] = _take(out.oobEnsbDen, M, np.uint32)
     if out.perfClas:
         res["perfClas"] = _take(out.perfClas, 3 * ntree, np.float64)
+    if out.vimpClas:
+        res["importance"] = _take(out.vimpClas, 3 * int(out.vimp_count), np.float64).reshape(-1, 3)
+        res["vimp_ms"] = float(out.vimp_ms)
     if out.nodeMembership:
         res["nodeMembership"] = _take(out.nodeMembership, ntree * M, np.int32)
     if out.bootMembership:

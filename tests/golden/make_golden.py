@@ -161,6 +161,59 @@ def main():
     print("done")
 
 
+# permutation importance (rf.c:2106-2218, 2416-2697): name, n, p, levels, factor columns, rule, ntree, nodesize, forest seed, data seed,
+# by.user.  One forest per case (chain C does not touch the trees), importance in every mode / perf.type, in grow and in restore.
+# ONE reference thread: with OPT_VIMP_LEOB every tree resets and refills the shared RF_vimpEnsembleDen[p] / RF_vimpEnsembleCLS[p]
+# (rf.c:2265-2280) without a lock, so the reference's per-tree importance is only reproducible single-threaded.
+VIMP_CASES = [
+    ("vimp_q16", 1500, 8, 16, {}, 4, 6, 10, -21, 31, False),
+    ("vimp_fac", 2000, 7, 16, {1: 5, 4: 7}, 4, 5, 8, -23, 32, False),
+    ("vimp_byuser", 1200, 6, 32, {}, 1, 5, 5, -25, 33, True),
+]
+VIMP_MODES = [("permute", "misclass", False), ("permute.ensemble", "misclass", False), ("permute", "brier", False),
+              ("permute.ensemble", "brier", False), ("permute", "gmean", False), ("permute", "misclass", True),
+              ("permute.ensemble", "gmean", True)]
+
+
+def main_vimp():
+    for (name, n, p, levels, fac, rule, ntree, nodesize, seed, dseed, byuser) in VIMP_CASES:
+        if fac:
+            d, x, xt, xl = factor_table(n, p, fac, dseed)
+        else:
+            d = make_cpiu(n, p, levels=levels, seed=dseed); x = d.x; xt = ["R"] * p; xl = np.zeros(p, np.int32)
+        samp = None
+        if byuser:
+            rng = np.random.default_rng(dseed + 5)
+            samp = np.stack([np.bincount(rng.integers(0, d.n, d.n), minlength=d.n) for _ in range(ntree)]).astype(np.int32)
+        save = dict(x=x, y=d.y, rt=d.rt, strat=d.strat, xtype=np.array("".join(xt)), xlevels=xl,
+                    params=np.array([d.n, p, levels, rule, ntree, nodesize, seed, dseed, int(byuser)], np.int64))
+        if samp is not None:
+            save["samp"] = samp
+        t = None
+        for (imp, perf, rfq) in VIMP_MODES:
+            r = rd.grow(x, d.y, d.rt, d.strat, rule=rule, ntree=ntree, nodesize=nodesize, seed=seed, xtype=xt, xlevels=xl, samp=samp,
+                        importance=imp, perf=perf, rfq=rfq, quants=True, nthreads=1)
+            key = f"{imp}_{perf}_{int(rfq)}"
+            save["ref_vimp_" + key] = r["vimpClas"]
+            save["ref_perf_" + key] = r["perfClas"][-3:]
+            if t is None:
+                t = canon(r, d.n)
+                for k in ("leafCount", "seed", "bootMembership", "treeID", "nodeID", "parmID", "contPT", "mwcpSZ", "tnRCNT", "tnACNT", "tnCLAS") + (("mwcpPT",) if fac else ()):
+                    save["ref_" + k] = t[k]
+        # restore mode (vimp.rfsrc -> rfsrcPredict on the training rows): chain C comes from the seed LCG started at 0
+        intr = np.array([3, 1, p], np.int32)
+        save["intr"] = intr
+        for imp in ("permute", "permute.ensemble"):
+            pr = rd.predict(x, d.y, t, None, nodesize=nodesize, xtype=xt, xlevels=xl, samp=samp, importance=imp, xvar_imp=intr, quants=True, nthreads=1)
+            save["ref_restore_vimp_" + imp] = pr["vimpClas"]
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **save)
+        print(name, "nodes", t["treeID"].size, "bytes", os.path.getsize(os.path.join(OUT, name + ".npz")))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "vimp":
+    main_vimp()
+    sys.exit(0)
+
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "factors":
     main_factors()
     sys.exit(0)

@@ -488,3 +488,52 @@ def test_perf_types_match_oracle(perf, rfq):
             np.testing.assert_allclose(table[ok], want[ok], rtol=1e-12, atol=0)
         else:
             np.testing.assert_array_equal(table[ok], want[ok])
+
+
+# ---- permutation importance (randomForestSRC.c:2106-2218, 2416-2697) -----------------------------------------
+from tests.test_oracle import VIMP_GOLDENS, assert_vimp_close, vimp_golden_forest, vimp_modes   # noqa: E402
+
+
+@pytest.mark.parametrize("name", VIMP_GOLDENS)
+def test_permutation_importance_matches_reference_golden(golden_dir, name):
+    """importance = "permute" (per tree) / "permute.ensemble" inside the grow call and in restore mode against the
+    unmodified reference (one thread: its per-tree importance races otherwise): vote counts make the misclassification
+    and g-mean importances exact, Brier sums and ensemble sums differ by summation order only."""
+    g = np.load(os.path.join(golden_dir, name))
+    n, p, levels, rule, ntree, nodesize, seed, dseed, byuser = [int(v) for v in g["params"]]
+    xt = list(str(g["xtype"])); samp = g["samp"] if byuser else None
+    forest = None
+    for key, imp, perf, rfq in vimp_modes(g):
+        got = rfslam_b200.rfsrc(g["x"], g["y"], g["rt"], g["strat"], splitrule=rule, ntree=ntree, nodesize=nodesize, seed=seed,
+                                xvar_types=xt, xvar_levels=g["xlevels"], samp=samp, importance=imp, perf_type=perf, rfq=rfq)
+        np.testing.assert_array_equal(got["parmID"], g["ref_parmID"])
+        assert got["importance"].shape == (p, 3)
+        assert_vimp_close(got["importance"], g[key], exact=(imp == "permute" and perf != "brier"))
+        pk = "ref_perf_" + key[len("ref_vimp_"):]
+        np.testing.assert_allclose(got["perfClas"][-3:][~np.isnan(g[pk])], g[pk][~np.isnan(g[pk])], rtol=1e-12, atol=0)
+        forest = forest or got
+    for imp in ("permute", "permute.ensemble"):
+        for use in (True, False):                                     # leaf class counts passed, or rebuilt by the restore
+            pr = rfslam_b200.predict_rfsrc(forest, None, x=g["x"], y=g["y"], samp=samp, xvar_types=xt, xvar_levels=g["xlevels"],
+                                           importance=imp, xvar_importance=g["intr"], use_tnclas=use)
+            assert_vimp_close(pr["importance"], g["ref_restore_vimp_" + imp], exact=(imp == "permute"))
+
+
+@pytest.mark.parametrize("per_tree", [True, False], ids=["per-tree", "ensemble"])
+def test_permutation_importance_matches_oracle_at_scale(per_tree):
+    """More OOB rows than one bitmap word group (three index levels in use), trees time-sliced over the CTAs."""
+    d = make_cpiu(100000, 4, levels=32, seed=91)                       # ~36.8 k OOB rows per tree: two top-level groups
+    ntree, seed = 3, -41
+    got = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, splitrule=4, ntree=ntree, nodesize=20, seed=seed, membership=True,
+                            importance="permute" if per_tree else "permute.ensemble")
+    want = port.vimp_permute(got, d.x, d.y, got["bootMembership"], port.chain_seed_c(seed, ntree), per_tree=per_tree)
+    assert_vimp_close(got["importance"], want, exact=per_tree)
+    assert np.abs(want[:, 0]).max() > 0
+
+
+def test_importance_limits_fail_loudly():
+    d = make_cpiu(800, 4, levels=8, seed=2)
+    with pytest.raises(ValueError, match="permutation"):
+        rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=2, importance="anti")
+    with pytest.raises(rfslam_b200.RfslamError, match="whole forest"):
+        rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=4, importance="permute", tree_first=1, tree_step=2, finalize=False)

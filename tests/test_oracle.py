@@ -294,3 +294,55 @@ def test_port_perf_types_match_live_reference(perf, rfq):
     r = refdriver.grow(d.x, d.y, d.rt, d.strat, **kw)
     o = port.grow(d.x, d.y, d.rt, d.strat, **kw)
     np.testing.assert_array_equal(r["perfClas"].view(np.uint64), o["perfClas"].view(np.uint64))
+
+
+# ---- permutation importance (randomForestSRC.c:2106-2218, 2416-2697) -----------------------------------------
+VIMP_GOLDENS = ["vimp_q16.npz", "vimp_fac.npz", "vimp_byuser.npz"]
+
+
+def vimp_golden_forest(g):
+    f = {k[4:]: g[k] for k in g.files if k.startswith("ref_") and not k.startswith(("ref_vimp", "ref_perf", "ref_restore"))}
+    return f
+
+
+def vimp_modes(g):
+    for k in g.files:
+        if k.startswith("ref_vimp_"):
+            imp, perf, rfq = k[len("ref_vimp_"):].rsplit("_", 2)
+            yield k, imp, perf, bool(int(rfq))
+
+
+def assert_vimp_close(got, want, exact):
+    got = np.asarray(got).reshape(-1, 3); want = np.asarray(want).reshape(-1, 3)
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    if exact:
+        np.testing.assert_array_equal(got[ok], want[ok])
+    else:
+        np.testing.assert_allclose(got[ok], want[ok], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", VIMP_GOLDENS)
+def test_port_permutation_importance_matches_golden(golden_dir, name):
+    """The restatement of permute() / getPermuteMembership / summarize + finalizeVimpPerformance against the unmodified
+    reference: per-tree and ensemble importance, every perf.type, RFQ, numeric + factor tables, by.user bootstraps, in
+    grow mode (chain C = third seed block) and restore mode (seed LCG from 0, a covariate subset)."""
+    g = np.load(os.path.join(golden_dir, name))
+    n, p, levels, rule, ntree, nodesize, seed, dseed, byuser = [int(v) for v in g["params"]]
+    f = vimp_golden_forest(g)
+    boot = g["ref_bootMembership"]
+    for key, imp, perf, rfq in vimp_modes(g):
+        got = port.vimp_permute(f, g["x"], g["y"], boot, port.chain_seed_c(seed, ntree), per_tree=(imp == "permute"), perf=perf, rfq=rfq)
+        assert_vimp_close(got, g[key], exact=(imp == "permute" and perf != "brier"))
+    for imp in ("permute", "permute.ensemble"):
+        got = port.vimp_permute(f, g["x"], g["y"], boot, port.chain_seed_c(0, ntree, restore=True), intr=g["intr"], per_tree=(imp == "permute"))
+        assert_vimp_close(got, g["ref_restore_vimp_" + imp], exact=(imp == "permute"))
+
+
+def test_permutation_is_the_reference_one():
+    """permute() (randomForestSRC.c:1974-2007): slot 'k-th still empty' receives i for i = m..1 -- every value once."""
+    f = dict(treeID=np.ones(1, np.int32), nodeID=np.ones(1, np.int32), parmID=np.zeros(1, np.int32), contPT=np.zeros(1),
+             leafCount=np.ones(1, np.int32), tnCLAS=np.array([3, 1], np.int32))
+    x = np.arange(10, dtype=np.float64)[None, :]; y = np.ones(10); y[::3] = 2.0
+    v = port.vimp_permute(f, x, y, np.zeros((1, 10), np.int32), port.chain_seed_c(-3, 1), per_tree=True)
+    assert v.shape == (1, 3) and v[0, 0] == 0.0                       # a stump: permuting changes nothing

@@ -118,3 +118,26 @@ def test_both_libraries_agree_on_a_mixed_factor_table():
         pg = refdriver.predict(x, d.y, forest, fx, impl="b200", nodesize=10, xtype=xt, xlevels=xl)
         np.testing.assert_array_equal(pg["nodeMembership"], pr["nodeMembership"])
         np.testing.assert_allclose(pg["allEnsbCLS"], pr["allEnsbCLS"], rtol=parity.HAZARD_RTOL, atol=0)
+
+
+@pytest.mark.gpu
+@needs_shim
+@needs_ref
+@pytest.mark.parametrize("imp", ["permute", "permute.ensemble"])
+def test_both_libraries_return_the_same_importance(imp):
+    """importance = TRUE through the .Call entries: "vimpClas" [xSize][3] from rfsrcGrow and, for a covariate subset, from
+    rfsrcPredict in restore mode (what vimp.rfsrc calls), in the reference's place in the named list.  One reference thread
+    (its per-tree importance shares buffers between trees)."""
+    d = make_cpiu(2500, 7, levels=16, seed=6)
+    kw = dict(rule=4, ntree=5, nodesize=10, seed=-31, membership=True, importance=imp, nthreads=1, quants=True)
+    ref = refdriver.grow(d.x, d.y, d.rt, d.strat, impl="ref", **kw)
+    got = refdriver.grow(d.x, d.y, d.rt, d.strat, impl="b200", **kw)
+    assert [k for k in got if not k.startswith("_")] == [k for k in ref if not k.startswith("_")]
+    assert got["vimpClas"].shape == ref["vimpClas"].shape == (21,)
+    np.testing.assert_allclose(got["vimpClas"], ref["vimpClas"], rtol=0, atol=0 if imp == "permute" else 1e-12)
+    forest = _sorted_by_tree(refdriver.trim_forest(ref, d.n))
+    pkw = dict(nodesize=10, importance=imp, xvar_imp=[2, 7, 4], quants=True, nthreads=1)
+    pr = refdriver.predict(d.x, d.y, forest, None, impl="ref", **pkw)
+    pg = refdriver.predict(d.x, d.y, forest, None, impl="b200", **pkw)
+    assert pg["vimpClas"].shape == pr["vimpClas"].shape == (9,)
+    np.testing.assert_allclose(pg["vimpClas"], pr["vimpClas"], rtol=0, atol=0 if imp == "permute" else 1e-12)
