@@ -368,6 +368,20 @@ def main():
                                 "factor_splits": int(fm["mwcpSZ"].sum()), "forest_nodes": int(fm["treeID"].size),
                                 "split_candidates_per_sec": int(fm["split_candidates"]) / mixed_s}
         dsm.close(); del dsm, xm, fm
+        # (f3) permutation importance on configs[1]'s table: one wave of trees, every covariate (importance = TRUE); the
+        # reference's permute() is O(m^2) per (tree, covariate) -- 6.8e10 slot visits at these 368 k OOB rows -- so there is
+        # no CPU figure beside it at this size (parity: tests/test_gpu_parity.py at sizes the reference finishes)
+        vimp_trees = 148
+        t0 = time.perf_counter()
+        fv = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, splitrule=cfg["rule"], ntree=vimp_trees, nodesize=cfg["nodesize"],
+                               seed=cfg["seed"], k_for_alpha=cfg["k_for_alpha"], device=local, importance="permute")
+        vimp_s = time.perf_counter() - t0
+        line["importance"] = {"workload": f"{n} CPIUs x {p} covariates, ntree={vimp_trees}, per-tree permutation importance of all {p} covariates",
+                              "vimp_device_ms": fv["vimp_ms"], "call_s": vimp_s, "permutations": vimp_trees * p,
+                              "value": vimp_trees * p / max(fv["vimp_ms"] / 1e3, 1e-9), "unit": "(tree, covariate) permutations/s",
+                              "oob_row_walks_per_s": vimp_trees * (p + 1) * 0.3679 * n / max(fv["vimp_ms"] / 1e3, 1e-9),
+                              "top5_covariates": [int(i) + 1 for i in (-fv["importance"][:, 0]).argsort()[:5]]}
+        del fv
         # (f1) CPIU construction: persons -> counting-process information units with derived time-varying covariates
         persons = 1_000_000
         t_out = np.round(rng.uniform(30, 2900, persons), 1); dth = (rng.random(persons) < 0.3).astype(np.int32)

@@ -552,9 +552,8 @@ int predict_forest_ex(const rfslam_predict_args* a, rfslam_predict_out* out, con
       std::vector<int> oobc(ntree);
       RF_CUDA(cudaMemcpy(oobc.data(), d_oobc, (size_t)ntree * 4, cudaMemcpyDeviceToHost));
       const int maxOob = std::max(1, *std::max_element(oobc.begin(), oobc.end()));
-      const int W0 = (maxOob + 31) >> 5, G1 = (W0 + 31) >> 5, G2 = (G1 + 31) >> 5;
-      const size_t smem = ((size_t)W0 + G1 + G2) * 4;
-      if (smem > 200 * 1024) { host_free(h_perf); set_error("importance: %d OOB rows in one tree exceed the %d the permutation's shared-memory index holds", maxOob, 200 * 1024 * 8 * 32 / 33); throw CudaFail{RFSLAM_ENOSUP}; }
+      const size_t smem = SlotIndex::bytes(maxOob);
+      if (smem > 220 * 1024) { host_free(h_perf); set_error("importance: %d OOB rows in one tree exceed the ~1.7 M the permutation's shared-memory slot index holds", maxOob); throw CudaFail{RFSLAM_ENOSUP}; }
       RF_CUDA(cudaFuncSetAttribute(vimp_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int perSm = 0, nsm = 0, dev = 0;
       RF_CUDA(cudaGetDevice(&dev));

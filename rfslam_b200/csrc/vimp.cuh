@@ -6,9 +6,11 @@
 // covariates of interest, so warp 0 is the PRODUCER: it replays the chain (32 Park-Miller states per jump-ahead, the
 // Bays-Durham table spread over the lanes) and builds the permutation of the tree's OOB rows for covariate v --
 // permute() gives slot "k-th still-empty" the value i for i = m..1, which the reference finds by a linear walk
-// (O(m^2)); here an occupancy bitmap with two levels of empty-slot counts in shared memory answers "k-th empty" in three
-// warp-wide prefix steps.  Warps 1..7 are the CONSUMERS: while the producer works on covariate v they drop the OOB rows
-// down the tree with covariate v - 1 replaced by its permuted value and either count the votes of the tree's own
+// (O(m^2)).  Here 32 draws are resolved per step: their ranks among the slots empty at the START of the step follow from
+// the earlier draws of the step alone (rank = k + #earlier ranks below it: a ballot fixed point, exact), then every lane
+// looks its rank up in an occupancy bitmap with 8-ary empty-slot counts in shared memory (one 16-byte load per level)
+// and the 32 slots are taken at once.  Warps 1..7 are the CONSUMERS: while the producer works on covariate v they drop the
+// OOB rows down the tree with covariate v - 1 replaced by its permuted value and either count the votes of the tree's own
 // estimate (per-tree importance) or add the leaf proportions to the covariate's perturbed ensemble.
 #pragma once
 
@@ -40,12 +42,6 @@ struct VimpArgs {
   double* vens; uint32_t* vden;  // [nIntr][2][n], [nIntr][n]
 };
 
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
-  return v;
-}
-
 // chain replay by one warp: 32 draws per refill (as bootstrap_draw_kernel, grow.cu)
 struct WarpRan1 {
   int ivReg, iy, idum; float u; int pos;
@@ -55,23 +51,112 @@ struct WarpRan1 {
     ivReg = tmp->iv[lane]; iy = tmp->iy; idum = tmp->idum; pos = 32; u = 0.f;
     __syncwarp();
   }
-  __device__ __forceinline__ float next(int lane) {
-    if (pos == 32) {
-      const int myIdum = ran1_mulmod(kJump[lane], (uint32_t)idum);
-      int myIy = 0;
-      for (int k = 0; k < 32; k++) {
-        const int j = iy / 67108864;
-        const int idk = __shfl_sync(0xffffffffu, myIdum, k);
-        const int niy = __shfl_sync(0xffffffffu, ivReg, j);
-        if (lane == j) ivReg = idk;
-        iy = niy;
-        if (lane == k) myIy = niy;
-      }
-      idum = __shfl_sync(0xffffffffu, myIdum, 31);
-      u = ran1_float(myIy);
-      pos = 0;
+  __device__ __forceinline__ void refill(int lane) {
+    const int myIdum = ran1_mulmod(kJump[lane], (uint32_t)idum);
+    int myIy = 0;
+    for (int k = 0; k < 32; k++) {
+      const int j = iy / 67108864;
+      const int idk = __shfl_sync(0xffffffffu, myIdum, k);
+      const int niy = __shfl_sync(0xffffffffu, ivReg, j);
+      if (lane == j) ivReg = idk;
+      iy = niy;
+      if (lane == k) myIy = niy;
     }
-    return __shfl_sync(0xffffffffu, u, pos++);
+    idum = __shfl_sync(0xffffffffu, myIdum, 31);
+    u = ran1_float(myIy);
+  }
+  // the next `cnt` (uniform, 1..32) draws of the chain: lane j < cnt receives the j-th of them
+  __device__ __forceinline__ float take(int lane, int cnt) {
+    if (pos == 32) { refill(lane); pos = 0; }
+    float v = __shfl_sync(0xffffffffu, u, (pos + lane) & 31);
+    const bool fromNext = pos + lane >= 32;
+    if (pos + cnt > 32) {
+      refill(lane);
+      const float v2 = __shfl_sync(0xffffffffu, u, (pos + lane) & 31);
+      if (fromNext) v = v2;
+      pos = pos + cnt - 32;
+    } else {
+      pos += cnt;
+    }
+    return v;
+  }
+};
+
+// Empty-slot index of one permutation: occupancy bitmap (bit set = slot taken) and 8-ary counts of EMPTY slots --
+// c1 per 8 words (256 slots), c2 per 2048, c3 per 16384 (u16, 8 to a 16-byte load), top per 131072 (u32).
+struct SlotIndex {
+  uint32_t* bits; uint16_t* c1; uint16_t* c2; uint16_t* c3; uint32_t* top;
+  int W0, n1, n2, n3, nt;
+  __host__ __device__ static size_t bytes(int m) {
+    const int W0 = ((m + 31) >> 5), n1 = (W0 + 7) >> 3, n2 = (n1 + 7) >> 3, n3 = (n2 + 7) >> 3, nt = (n3 + 7) >> 3;
+    return (size_t)(((W0 + 7) & ~7) * 4 + (((n1 + 7) & ~7) + ((n2 + 7) & ~7) + ((n3 + 7) & ~7)) * 2 + nt * 4 + 64);
+  }
+  __device__ void carve(uint32_t* base, int mcap) {
+    const int W0c = ((mcap + 31) >> 5), n1c = (W0c + 7) >> 3, n2c = (n1c + 7) >> 3, n3c = (n2c + 7) >> 3;
+    bits = base;
+    c1 = (uint16_t*)(bits + ((W0c + 7) & ~7));
+    c2 = c1 + ((n1c + 7) & ~7);
+    c3 = c2 + ((n2c + 7) & ~7);
+    top = (uint32_t*)(c3 + ((n3c + 7) & ~7));
+  }
+  // all slots of [0, m) empty (one warp)
+  __device__ void reset(int m, int lane) {
+    W0 = (m + 31) >> 5; n1 = (W0 + 7) >> 3; n2 = (n1 + 7) >> 3; n3 = (n2 + 7) >> 3; nt = (n3 + 7) >> 3;
+    for (int k = lane; k < ((W0 + 7) & ~7); k += 32) bits[k] = k < W0 - 1 ? 0u : (k == W0 - 1 ? ((m & 31) ? ~((1u << (m & 31)) - 1u) : 0u) : 0xffffffffu);
+    for (int k = lane; k < ((n1 + 7) & ~7); k += 32) c1[k] = (uint16_t)max(0, min(m, (k + 1) * 256) - k * 256);
+    for (int k = lane; k < ((n2 + 7) & ~7); k += 32) c2[k] = (uint16_t)max(0, min(m, (k + 1) * 2048) - k * 2048);
+    for (int k = lane; k < ((n3 + 7) & ~7); k += 32) c3[k] = (uint16_t)max(0, min(m, (k + 1) * 16384) - k * 16384);
+    for (int k = lane; k < nt; k += 32) top[k] = (uint32_t)max(0, min(m, (k + 1) * 131072) - k * 131072);
+  }
+  // which of 8 u16 counts (one 16-byte load) holds the k-th empty slot; k becomes the rank inside it
+  __device__ __forceinline__ static int pick8(const uint16_t* c, uint32_t& k) {
+    const uint4 v = *reinterpret_cast<const uint4*>(c);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    int at = 7;
+#pragma unroll
+    for (int q = 7; q >= 0; q--) {                  // prefix sums in registers
+      uint32_t before = 0;
+#pragma unroll
+      for (int t = 0; t < 8; t++) if (t < q) before += (w[t >> 1] >> (16 * (t & 1))) & 0xffffu;
+      const uint32_t mine = (w[q >> 1] >> (16 * (q & 1))) & 0xffffu;
+      if (k > before && k <= before + mine) at = q;
+    }
+    uint32_t before = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) if (t < at) before += (w[t >> 1] >> (16 * (t & 1))) & 0xffffu;
+    k -= before;
+    return at;
+  }
+  // slot of the r-th (1-based) empty slot
+  __device__ __forceinline__ int select(uint32_t r) const {
+    int t = 0;
+    for (; t < nt - 1; t++) { const uint32_t c = top[t]; if (r <= c) break; r -= c; }
+    const int i3 = t * 8 + pick8(c3 + t * 8, r);
+    const int i2 = i3 * 8 + pick8(c2 + i3 * 8, r);
+    const int i1 = i2 * 8 + pick8(c1 + i2 * 8, r);
+    const uint4 a = *reinterpret_cast<const uint4*>(bits + i1 * 8), b = *reinterpret_cast<const uint4*>(bits + i1 * 8 + 4);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    int wi = 7; uint32_t before = 0, acc = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const uint32_t e = 32u - (uint32_t)__popc(w[q]);
+      if (r > acc && r <= acc + e) { wi = q; before = acc; }
+      acc += e;
+    }
+    uint32_t word = w[0];
+#pragma unroll
+    for (int q = 1; q < 8; q++) if (wi == q) word = w[q];
+    const int bit = (int)__fns(~word, 0, (int)(r - before));
+    return (i1 * 8 + wi) * 32 + bit;
+  }
+  // several lanes take their slots at once
+  __device__ __forceinline__ void take(int slot) {
+    const int wi = slot >> 5, i1 = wi >> 3, i2 = i1 >> 3, i3 = i2 >> 3, t = i3 >> 3;
+    atomicOr(&bits[wi], 1u << (slot & 31));
+    atomicSub(reinterpret_cast<uint32_t*>(c1) + (i1 >> 1), 1u << (16 * (i1 & 1)));
+    atomicSub(reinterpret_cast<uint32_t*>(c2) + (i2 >> 1), 1u << (16 * (i2 & 1)));
+    atomicSub(reinterpret_cast<uint32_t*>(c3) + (i3 >> 1), 1u << (16 * (i3 & 1)));
+    atomicSub(&top[t], 1u);
   }
 };
 
@@ -100,16 +185,15 @@ __global__ void __launch_bounds__(kVimpThreads) vimp_oob_count_kernel(const uint
   if (threadIdx.x == 0) oobCount[t] = sh;
 }
 
-// dynamic shared memory: occupancy bitmap [W0 words] | L1 empty counts per 32 words (u32) [G1] | L2 per 32 L1 groups [G2]
+// dynamic shared memory: the producer's SlotIndex (SlotIndex::bytes(maxOob))
 __global__ void __launch_bounds__(kVimpThreads) vimp_tree_kernel(VimpArgs a) {
-  extern __shared__ uint32_t dsm[];
+  extern __shared__ __align__(16) uint32_t dsm[];
   __shared__ Ran1 rngTmp;
   __shared__ int warpBase[kVimpThreads / 32 + 1];
   __shared__ VimpAcc red[kVimpThreads / 32];
   __shared__ int sM;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int W0cap = (a.maxOob + 31) >> 5, G1cap = (W0cap + 31) >> 5;
-  uint32_t* L0 = dsm; uint32_t* L1 = L0 + W0cap; uint32_t* L2 = L1 + G1cap;
+  SlotIndex si; si.carve(dsm, a.maxOob);
   uint32_t* idx = a.scratch + (size_t)blockIdx.x * 3 * a.maxOob;
   uint32_t* permBuf[2] = {idx + a.maxOob, idx + 2 * (size_t)a.maxOob};
 
@@ -139,62 +223,35 @@ __global__ void __launch_bounds__(kVimpThreads) vimp_tree_kernel(VimpArgs a) {
       for (int s = tid; s <= a.nIntr; s += kVimpThreads) { VimpAcc z{}; a.acc[(size_t)tree * (a.nIntr + 1) + s] = z; }
       continue;
     }
-    const int W0 = (m + 31) >> 5, G1 = (W0 + 31) >> 5, G2 = (G1 + 31) >> 5;
 
     for (int s = 0; s <= a.nIntr; s++) {
       if (w == 0) {
         // ---------------- producer: the permutation of covariate s ----------------
         if (s < a.nIntr) {
           uint32_t* perm = permBuf[s & 1];
-          for (int k = lane; k < W0; k += 32) L0[k] = (k == W0 - 1 && (m & 31)) ? ~((1u << (m & 31)) - 1u) : 0u;       // slots beyond m count as taken
-          for (int g = lane; g < G1; g += 32) L1[g] = (uint32_t)(min(m, (g + 1) * 1024) - g * 1024);
-          for (int h = lane; h < G2; h += 32) L2[h] = (uint32_t)(min(m, (h + 1) * 32768) - h * 32768);
+          si.reset(m, lane);
           __syncwarp();
-          for (int i = m; i > 0; i--) {
-            uint32_t k = (uint32_t)ceil((double)rng.next(lane) * ((double)i * 1.0));      // rf.c:1998
-            // level 2
-            int h = 0;
-            for (int b2 = 0; b2 < G2; b2 += 32) {
-              const uint32_t c = (b2 + lane < G2) ? L2[b2 + lane] : 0u;
-              const uint32_t inc = warp_incl_scan(c, lane);
-              const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
-              if (k <= tot) {
-                const int f = __ffs(__ballot_sync(0xffffffffu, inc >= k)) - 1;
-                k -= __shfl_sync(0xffffffffu, inc - c, f);
-                h = b2 + f;
-                break;
+          for (int i0 = m; i0 > 0; i0 -= 32) {
+            const int cntB = min(32, i0);
+            const float uu = rng.take(lane, cntB);
+            const int mine = i0 - lane;                                                     // lane j draws for i = i0 - j
+            const uint32_t k = lane < cntB ? (uint32_t)ceil((double)uu * ((double)mine * 1.0)) : 0u;     // rf.c:1998
+            // ranks among the slots empty at the start of the step: r_j = k_j + #{t < j : r_t <= r_j} (least fixed point)
+            uint32_t r = 0;
+            for (int j = 0; j < cntB; j++) {
+              const uint32_t kj = __shfl_sync(0xffffffffu, k, j);
+              uint32_t c = 0;
+              while (true) {
+                const uint32_t cn = (uint32_t)__popc(__ballot_sync(0xffffffffu, lane < j && r <= kj + c));
+                if (cn == c) break;
+                c = cn;
               }
-              k -= tot;
+              if (lane == j) r = kj + c;
             }
-            // level 1
-            int g;
-            {
-              const int gi = h * 32 + lane;
-              const uint32_t c = (gi < G1) ? L1[gi] : 0u;
-              const uint32_t inc = warp_incl_scan(c, lane);
-              const int f = __ffs(__ballot_sync(0xffffffffu, inc >= k)) - 1;
-              k -= __shfl_sync(0xffffffffu, inc - c, f);
-              g = h * 32 + f;
-            }
-            // level 0
-            int wi; uint32_t ww;
-            {
-              const int wj = g * 32 + lane;
-              const uint32_t word = (wj < W0) ? L0[wj] : 0xffffffffu;
-              const uint32_t c = 32u - (uint32_t)__popc(word);
-              const uint32_t inc = warp_incl_scan(c, lane);
-              const int f = __ffs(__ballot_sync(0xffffffffu, inc >= k)) - 1;
-              k -= __shfl_sync(0xffffffffu, inc - c, f);
-              wi = g * 32 + f;
-              ww = __shfl_sync(0xffffffffu, word, f);
-            }
-            const uint32_t freeBits = ~ww;
-            const bool mine = ((freeBits >> lane) & 1u) && (uint32_t)__popc(freeBits & ((1u << lane) - 1u)) == k - 1u;
-            const int bit = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
-            if (lane == 0) {
-              L0[wi] = ww | (1u << bit); L1[g] -= 1u; L2[h] -= 1u;
-              perm[wi * 32 + bit] = (uint32_t)i;                 // slot (1-based wi*32+bit+1) receives i
-            }
+            int slot = -1;
+            if (lane < cntB) { slot = si.select(r); perm[slot] = (uint32_t)mine; }          // slot (1-based slot + 1) receives i
+            __syncwarp();
+            if (lane < cntB) si.take(slot);
             __syncwarp();
           }
           __threadfence_block();
