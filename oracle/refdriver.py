@@ -343,7 +343,19 @@ def predict(x: np.ndarray, y: np.ndarray, forest: Dict[str, np.ndarray], fx: Opt
     arr = (C.c_void_p * 58)(*args)
     msg = C.create_string_buffer(2048)
     fn = C.cast(L.rfsrcPredict, C.c_void_p)
-    out = L.fr_guard_call(fn, 58, arr, msg, 2048)
+    # rfsrcPredict ignores its numThreads argument ("RF_numThreads = 2;//INTEGER(numThreads)[0]", randomForestSRC.c:22318) and its
+    # per-tree importance shares buffers between trees (randomForestSRC.c:2265-2280): one thread has to be forced through OpenMP
+    gomp = prev = None
+    if nthreads == 1 and impl == "ref":
+        try:
+            gomp = C.CDLL("libgomp.so.1"); prev = gomp.omp_get_max_threads(); gomp.omp_set_num_threads(1)
+        except OSError:
+            gomp = None
+    try:
+        out = L.fr_guard_call(fn, 58, arr, msg, 2048)
+    finally:
+        if gomp is not None:
+            gomp.omp_set_num_threads(prev)
     if not out:
         L.fr_release_all()
         raise RuntimeError(f"rfsrcPredict ({impl}) failed: " + msg.value.decode(errors="replace"))
