@@ -498,4 +498,12 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    # stdout carries exactly ONE line (the JSON record): anything a library writes to fd 1 meanwhile -- NCCL prints its
+    # version there when the first communicator comes up -- is sent to stderr
+    sys.stdout.flush()
+    _out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _out
+    rc = main()
+    _out.flush()
+    sys.exit(rc)
