@@ -537,6 +537,7 @@ int predict_forest_ex(const rfslam_predict_args* a, rfslam_predict_out* out, con
     double* h_perf = nullptr;
     if (restore && a->finalize_ensembles && (a->opt_low & RFSLAM_OPT_PERF)) {
       h_perf = perf_clas_table(a->opt_low, ntree, n, d_oob, d_oobDen, nullptr, nullptr, d_y, &launches);
+      out->perfClas = h_perf;                  // owned by `out` from here on: the catch below releases it with the rest
     }
     // ---- permutation importance (restore mode; the grow entry comes here with its own chain-C seeds) ----
     double* h_vimp = nullptr;
@@ -553,7 +554,7 @@ int predict_forest_ex(const rfslam_predict_args* a, rfslam_predict_out* out, con
       RF_CUDA(cudaMemcpy(oobc.data(), d_oobc, (size_t)ntree * 4, cudaMemcpyDeviceToHost));
       const int maxOob = std::max(1, *std::max_element(oobc.begin(), oobc.end()));
       const size_t smem = SlotIndex::bytes(maxOob);
-      if (smem > 220 * 1024) { host_free(h_perf); set_error("importance: %d OOB rows in one tree exceed the ~1.7 M the permutation's shared-memory slot index holds", maxOob); throw CudaFail{RFSLAM_ENOSUP}; }
+      if (smem > 220 * 1024) { set_error("importance: %d OOB rows in one tree exceed the ~1.7 M the permutation's shared-memory slot index holds", maxOob); throw CudaFail{RFSLAM_ENOSUP}; }
       RF_CUDA(cudaFuncSetAttribute(vimp_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int perSm = 0, nsm = 0, dev = 0;
       RF_CUDA(cudaGetDevice(&dev));
@@ -585,7 +586,8 @@ int predict_forest_ex(const rfslam_predict_args* a, rfslam_predict_out* out, con
       launches += 2;
       RF_CUDA(cudaGetLastError());
       h_vimp = (double*)host_alloc((size_t)nIntr * 3 * 8);
-      if (!h_vimp) { host_free(h_perf); set_error("out of host memory"); throw CudaFail{RFSLAM_ENOMEM}; }
+      if (!h_vimp) { set_error("out of host memory"); throw CudaFail{RFSLAM_ENOMEM}; }
+      out->vimpClas = h_vimp; out->vimp_count = nIntr;
       const double na = rfslam_na_real();
       if (leob) {
         // per tree: performance of the tree's own OOB estimate with covariate v permuted minus without, averaged over the
@@ -626,13 +628,12 @@ int predict_forest_ex(const rfslam_predict_args* a, rfslam_predict_out* out, con
       float ms = 0.f; RF_CUDA(cudaEventElapsedTime(&ms, st.k0, st.k1));
       out->vimp_ms = ms;
     }
-    out->vimpClas = h_vimp; out->vimp_count = h_vimp ? nIntr : 0;
     RF_CUDA(cudaEventRecord(st.e1));
     RF_CUDA(cudaGetLastError());
     RF_CUDA(cudaEventSynchronize(st.e1));
     if (timing) twSweep = wall();
     RF_CUDA(cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost));
-    if (bad == 5) { host_free(h_perf); set_error("by.user in-bag counts must be in [0, 65535]"); throw CudaFail{RFSLAM_EINVAL}; }
+    if (bad == 5) { set_error("by.user in-bag counts must be in [0, 65535]"); throw CudaFail{RFSLAM_EINVAL}; }
     float totMs = 0.f;
     RF_CUDA(cudaEventElapsedTime(&totMs, st.e0, st.e1));
     unsigned long long visits = 0;
@@ -640,7 +641,6 @@ int predict_forest_ex(const rfslam_predict_args* a, rfslam_predict_out* out, con
 
     out->m = (int32_t)M; out->ntree = ntree; out->kernel_ms = kernMs; out->total_device_ms = totMs;
     out->kernel_launches = launches; out->row_tree_visits = rowTrees; out->node_visits = (int64_t)visits;
-    out->perfClas = h_perf;
     auto fetch = [&](const void* dev, size_t bytes) -> void* {
       void* h = host_alloc(std::max<size_t>(bytes, 8));
       if (!h) { set_error("out of host memory"); throw CudaFail{RFSLAM_ENOMEM}; }
