@@ -119,3 +119,22 @@ def test_synth_is_deterministic_and_shaped():
     assert set(np.unique(a.y)) <= {1.0, 2.0} and a.strat.min() >= 1 and a.strat.max() <= 16 and (a.rt > 0).all()
     assert 0.01 < (a.y == 2).mean() < 0.15
     assert max(np.unique(c).size for c in a.x) <= 64
+
+
+def test_importance_requests_are_validated_before_device_work(monkeypatch):
+    """Only permutation importance is on the accelerated path: the other types of R/utilities.R:150-208 (anti = no type
+    bit, random = 2^9, joint = 2^10) and importance on held-out rows are refused by the argument check, GPU or not."""
+    from rfslam_b200 import forest as fmod
+    d = make_cpiu(300, 4, levels=8, seed=2)
+    stump = dict(treeID=np.ones(1, np.int32), nodeID=np.ones(1, np.int32), parmID=np.zeros(1, np.int32), contPT=np.zeros(1),
+                 mwcpSZ=np.zeros(1, np.int32), seed=np.array([-5], np.int32), tnCLAS=np.array([3, 1], np.int32))
+    for name, bits, what in (("anti", (1 << 25) + (1 << 24), "permutation"), ("random", (1 << 25) + (1 << 24) + (1 << 9), "permutation"),
+                             ("permute.joint", (1 << 25) + (1 << 24) + (1 << 10) + (1 << 8), "joint")):
+        monkeypatch.setitem(fmod.IMPORTANCE_BITS, name, bits)
+        with pytest.raises(rfslam_b200.RfslamError, match=what) as e:
+            rfslam_b200.predict_rfsrc(stump, None, x=d.x, y=d.y, importance=name)
+        assert e.value.code == 3                                      # RFSLAM_ENOSUP
+    with pytest.raises(rfslam_b200.RfslamError, match="held-out"):
+        rfslam_b200.predict_rfsrc(stump, d.x[:, :10].copy(), x=d.x, y=d.y, importance="permute")
+    with pytest.raises(rfslam_b200.RfslamError, match="intrPredictor"):
+        rfslam_b200.predict_rfsrc(stump, None, x=d.x, y=d.y, importance="permute", xvar_importance=[0, 9])
