@@ -19,7 +19,6 @@ kw = dict(splitrule=4, ntree=ntree, mtry=8, nodesize=20, seed=-7)
 rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, **kw)                     # warm-up (pools, module load)
 t0 = time.time(); plain = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, **kw); t1 = time.time()
 imp = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, importance=mode, **kw); t2 = time.time()
-oob = float((imp["oobEnsbDen"] > 0).mean())
 print(json.dumps({"workload": f"{n} x {p}, {ntree} trees, importance = {mode}", "grow_call_s": round(t1 - t0, 3),
                   "grow_with_importance_call_s": round(t2 - t1, 3), "vimp_device_ms": round(imp["vimp_ms"], 1),
                   "permutations": ntree * p, "oob_rows_per_tree": round(0.3679 * n),
