@@ -295,7 +295,8 @@ typedef struct rfslam_predict_out {
   uint32_t *allEnsbDen;        /* [m] */
   double   *oobEnsbCLS;        /* [2][n] restore mode only */
   uint32_t *oobEnsbDen;        /* [n] restore mode only */
-  double   *perfClas;          /* [ntree][3] restore mode with OPT_PERF, as rfslam_forest_out.perfClas */
+  double   *perfClas;          /* [ntree][3] with OPT_PERF, as rfslam_forest_out.perfClas: restore mode (OOB ensemble of the training
+                                  rows) or held-out rows with responses (fr_size > 0: the full ensemble against fr_data, whole row set only) */
   int32_t  *leafCount;         /* [ntree] by tree id */
   int32_t  *nodeMembership;    /* [ntree][m] by tree id, with OPT_MEMB_USER, else NULL */
   int32_t  *bootMembership;    /* [ntree][n] in-bag counts of the training rows (replayed), with OPT_MEMB_USER */

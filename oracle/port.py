@@ -217,3 +217,18 @@ def vimp_permute(forest: Dict[str, np.ndarray], x, y, boot, seed_c, *, intr=None
                        mpt.ctypes.data_as(C.POINTER(C.c_uint)), _dp(x), _dp(y), _ip(boot), _ip(sc), int(intr.size), _ip(intr),
                        1 if per_tree else 0, {"misclass": 0, "brier": 1, "gmean": 2}[perf], 1 if rfq else 0, na, _dp(out))
     return out.reshape(-1, 3)
+
+
+def perf_clas(y, ens, den=None, *, perf: str = "misclass", rfq: bool = False) -> np.ndarray:
+    """One performance row [overall, class 1, class 2] of a two-class ensemble ``ens`` [2][n] against ``y`` (getPerformance's
+    class branch).  With ``rfq`` the minority class / threshold are taken from ``y`` itself (true for the training rows)."""
+    L = lib()
+    y = np.ascontiguousarray(y, np.float64); ens = np.ascontiguousarray(ens, np.float64).reshape(-1)
+    n = y.size
+    den = np.ones(n, np.int32) if den is None else np.ascontiguousarray(den, np.int32)
+    na = np.frombuffer(np.uint64(0x7FF00000000007A2).tobytes(), np.float64)[0]
+    out = np.zeros(3, np.float64)
+    L.orc_perf_clas2.restype = None
+    L.orc_perf_clas2.argtypes = [C.c_int, _pd, _pd, _pi, C.c_double, C.c_int, C.c_int, _pd]
+    L.orc_perf_clas2(n, _dp(y), _dp(ens), _ip(den), C.c_double(na), {"misclass": 0, "brier": 1, "gmean": 2}[perf], int(bool(rfq)), _dp(out))
+    return out

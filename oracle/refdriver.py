@@ -278,9 +278,10 @@ def predict(x: np.ndarray, y: np.ndarray, forest: Dict[str, np.ndarray], fx: Opt
             nodesize: int = 5, impl: str = "ref", quants: bool = False,
             xtype: Optional[Sequence[str]] = None, xlevels: Optional[np.ndarray] = None,
             importance: Optional[str] = None, xvar_imp: Optional[Sequence[int]] = None, seed: int = -1,
-            perf: str = "misclass", rfq: bool = False, nthreads: int = -1) -> Dict[str, np.ndarray]:
+            perf: str = "misclass", rfq: bool = False, nthreads: int = -1, fy: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
     """Run the reference's rfsrcPredict on a (trimmed) grow output.  ``fx`` [p, m_test] selects
-    RF_PRED; ``fx=None`` is restore mode (RF_REST) (randomForestSRC.c:22361)."""
+    RF_PRED; ``fx=None`` is restore mode (RF_REST) (randomForestSRC.c:22361).  ``fy`` [m_test] = held-out responses (frSize = 1):
+    the reference then scores the full ensemble on the held-out rows (``perfClas``)."""
     L = lib(impl)
     p, n = x.shape
     x = np.ascontiguousarray(x, dtype=np.float64)
@@ -337,7 +338,7 @@ def predict(x: np.ndarray, y: np.ndarray, forest: Dict[str, np.ndarray], fx: Opt
         P.i(forest["tnCLAS"]) if (quants and "tnCLAS" in forest) else z_i(),
         P.i(1), P.i(1), P.i(0),
         P.i(int(intr.size)), P.i(intr), partial, P.i(0), z_i(),
-        P.i(m_test), P.i(0), z_d(), fx_arg, P.i(ntree), P.i(nthreads),
+        P.i(m_test), P.i(0 if fy is None else 1), z_d() if fy is None else P.d(np.asarray(fy, np.float64)), fx_arg, P.i(ntree), P.i(nthreads),
     ]
     assert len(args) == 58, len(args)
     arr = (C.c_void_p * 58)(*args)

@@ -91,8 +91,11 @@ inline void perf_from_counts(uint32_t opt_low, const unsigned long long* cumK, c
 }
 
 // perfClas [ntree][3]: NA_REAL except the last row (perfBlock = ntree, rf.c:8155).  `ev`/`inv` or `y` as in perf_kernel.
+// `trainCls` (predict mode): class counts of the TRAINING response -- the RFQ vote's minority class and threshold come from
+// it in every mode (rf.c:16859-16895), the per-class denominators from the rows scored (rf.c:1037-1040).
 inline double* perf_clas_table(uint32_t opt_low, int ntree, int n, const double* d_oob, const uint32_t* d_den,
-                               const uint8_t* d_ev, const uint32_t* d_inv, const double* d_y, long long* launches) {
+                               const uint8_t* d_ev, const uint32_t* d_inv, const double* d_y, long long* launches,
+                               const unsigned long long* trainCls = nullptr) {
   struct Dev { void* p = nullptr; ~Dev() { if (p) cudaFree(p); } } b_acc, b_brier, b_cnt;
   RF_CUDA(cudaMalloc(&b_acc.p, sizeof(PerfAcc))); RF_CUDA(cudaMalloc(&b_brier.p, kPerfBlocks * 2 * sizeof(double))); RF_CUDA(cudaMalloc(&b_cnt.p, 8));
   RF_CUDA(cudaMemset(b_acc.p, 0, sizeof(PerfAcc))); RF_CUDA(cudaMemset(b_cnt.p, 0, 8));
@@ -102,8 +105,9 @@ inline double* perf_clas_table(uint32_t opt_low, int ntree, int n, const double*
   const unsigned long long cls[2] = {(unsigned long long)n - c1, c1};
   int minority = -1; double threshold = 0.0;
   if (opt_low & RFSLAM_OPT_CLAS_RFQ) {                              // rf.c:16876-16895: first class with the smallest count
-    minority = cls[1] < cls[0] ? 1 : 0;
-    threshold = (double)cls[minority] / (double)n;
+    const unsigned long long* tc = trainCls ? trainCls : cls;
+    minority = tc[1] < tc[0] ? 1 : 0;
+    threshold = (double)tc[minority] / (double)(tc[0] + tc[1]);
   }
   perf_kernel<<<kPerfBlocks, 256>>>(d_oob, d_den, d_ev, d_inv, d_y, n, minority, threshold, (PerfAcc*)b_acc.p, (double*)b_brier.p);
   if (launches) *launches += 2;

@@ -539,6 +539,21 @@ int predict_forest_ex(const rfslam_predict_args* a, rfslam_predict_out* out, con
       h_perf = perf_clas_table(a->opt_low, ntree, n, d_oob, d_oobDen, nullptr, nullptr, d_y, &launches);
       out->perfClas = h_perf;                  // owned by `out` from here on: the catch below releases it with the rest
     }
+    // predict mode with held-out responses (frSize > 0): performance of the full ensemble on the held-out rows (rf.c:1323-1326,
+    // rf.c:7770-7800) -- for the whole set of rows only (a row shard holds a part of the counts)
+    if (!restore && a->finalize_ensembles && (a->opt_low & RFSLAM_OPT_PERF) && a->fr_size > 0 && a->fr_data && r0 == 0 && M == mAll) {
+      Buf b_fy;
+      double* d_fy = b_fy.alloc<double>((size_t)M);
+      RF_CUDA(cudaMemcpy(d_fy, a->fr_data, (size_t)M * 8, cudaMemcpyHostToDevice));
+      unsigned long long trainCls[2] = {0, 0};
+      if (a->opt_low & RFSLAM_OPT_CLAS_RFQ) {
+        if (!a->r_data) { set_error("rfq performance on held-out rows needs the training response (rData)"); throw CudaFail{RFSLAM_EINVAL}; }
+        for (int i = 0; i < n; i++) trainCls[a->r_data[i] == 2.0 ? 1 : 0]++;
+      }
+      h_perf = perf_clas_table(a->opt_low, ntree, (int)M, d_all, d_allDen, nullptr, nullptr, d_fy, &launches,
+                               (a->opt_low & RFSLAM_OPT_CLAS_RFQ) ? trainCls : nullptr);
+      out->perfClas = h_perf;
+    }
     // ---- permutation importance (restore mode; the grow entry comes here with its own chain-C seeds) ----
     double* h_vimp = nullptr;
     const int nIntr = a->intr_predictor_size;

@@ -259,7 +259,7 @@ def rfsrc(x, y, risk_time=None, stratifier=None, *, splitrule="poisson.split4", 
 def predict_rfsrc(forest: Dict[str, np.ndarray], fx=None, *, x=None, y=None, membership=True, device=-1, finalize=True,
                   samp=None, sampsize=None, use_tnclas=True, frow_first=0, frow_count=0, perf=True,
                   xvar_types=None, xvar_levels=None, perf_type="misclass", rfq=False, importance=None,
-                  xvar_importance=None) -> Dict[str, np.ndarray]:
+                  xvar_importance=None, fy=None) -> Dict[str, np.ndarray]:
     """rfsrcPredict through the C-ABI (rfslam_b200_predict), mirroring R/generic.predict.rfsrc.R:437-534.
 
     ``forest`` is a grow result (the reference's wire format).  ``fx`` [p, m] predicts held-out rows; ``fx=None``
@@ -268,7 +268,8 @@ def predict_rfsrc(forest: Dict[str, np.ndarray], fx=None, *, x=None, y=None, mem
     with the bootstrap replayed from ``forest["seed"]`` (or ``samp``).  ``frow_first`` / ``frow_count`` select this
     process' shard of the held-out rows (forest replicated, no collective).  In restore mode ``importance`` ("permute" /
     "permute.ensemble") adds the permutation importance [len(xvar_importance)][3] of the 1-based covariates in
-    ``xvar_importance`` (default: all), as vimp.rfsrc obtains it (R/generic.predict.rfsrc.R:1018-1021)."""
+    ``xvar_importance`` (default: all), as vimp.rfsrc obtains it (R/generic.predict.rfsrc.R:1018-1021).  ``fy`` [m] = the
+    held-out rows' responses (newdata that carries the outcome): ``perfClas`` then scores the full ensemble on them."""
     keep = {k: np.ascontiguousarray(forest[k], np.int32) for k in ("treeID", "nodeID", "parmID", "seed")}
     keep["contPT"] = np.ascontiguousarray(forest["contPT"], np.float64)
     keep["mwcpSZ"] = np.ascontiguousarray(forest["mwcpSZ"], np.int32) if "mwcpSZ" in forest else np.zeros(keep["treeID"].size, np.int32)
@@ -331,6 +332,11 @@ def predict_rfsrc(forest: Dict[str, np.ndarray], fx=None, *, x=None, y=None, mem
     a.fobservation_size = m
     if fx is not None:
         a.fx_data = _dp(fx)
+        if fy is not None:
+            keep["fy"] = np.ascontiguousarray(fy, np.float64)
+            if keep["fy"].shape != (m,):
+                raise ValueError(f"fy: expected {m} held-out responses")
+            a.fr_size = 1; a.fr_data = _dp(keep["fy"])
     a.perf_block = ntree; a.num_threads = -1
     a.device = int(device); a.finalize_ensembles = 1 if finalize else 0
     a.frow_first = int(frow_first); a.frow_count = int(frow_count)

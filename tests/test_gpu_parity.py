@@ -537,3 +537,20 @@ def test_importance_limits_fail_loudly():
         rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=2, importance="anti")
     with pytest.raises(rfslam_b200.RfslamError, match="whole forest"):
         rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, ntree=4, importance="permute", tree_first=1, tree_step=2, finalize=False)
+
+
+@pytest.mark.parametrize("perf", ["misclass", "brier", "gmean"])
+def test_held_out_performance_matches_oracle(perf):
+    """newdata that carries the outcome (frSize = 1): perfClas scores the full ensemble on the held-out rows
+    (randomForestSRC.c:1323-1326); a row shard returns no table (its counts are partial)."""
+    d = make_cpiu(20000, 8, levels=32, seed=78); t = make_cpiu(6000, 8, levels=32, seed=79)
+    f = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, splitrule=4, ntree=10, nodesize=10, seed=-29)
+    pr = rfslam_b200.predict_rfsrc(f, t.x, x=d.x, y=d.y, fy=t.y, perf_type=perf)
+    want = port.perf_clas(t.y, pr["allEnsbCLS"], perf=perf)
+    got = pr["perfClas"][-3:]
+    assert np.isnan(pr["perfClas"][:-3]).all()
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    np.testing.assert_allclose(got[ok], want[ok], rtol=1e-12 if perf == "brier" else 0, atol=0)
+    assert "perfClas" not in rfslam_b200.predict_rfsrc(f, t.x, x=d.x, y=d.y, fy=t.y, frow_first=0, frow_count=3000)
+    assert "perfClas" not in rfslam_b200.predict_rfsrc(f, t.x, fy=None)

@@ -141,3 +141,23 @@ def test_both_libraries_return_the_same_importance(imp):
     pg = refdriver.predict(d.x, d.y, forest, None, impl="b200", **pkw)
     assert pg["vimpClas"].shape == pr["vimpClas"].shape == (9,)
     np.testing.assert_allclose(pg["vimpClas"], pr["vimpClas"], rtol=0, atol=0 if imp == "permute" else 1e-12)
+
+
+@pytest.mark.gpu
+@needs_shim
+@needs_ref
+@pytest.mark.parametrize("rfq", [False, True], ids=["vote", "rfq"])
+@pytest.mark.parametrize("perf", ["misclass", "brier", "gmean"])
+def test_both_libraries_score_held_out_rows_alike(perf, rfq):
+    """rfsrcPredict on newdata with the outcome (frSize = 1, frData): the same "perfClas" row from both libraries; the RFQ
+    vote takes its minority class and threshold from the TRAINING response (randomForestSRC.c:16859-16895)."""
+    d = make_cpiu(4000, 7, levels=16, seed=8); t = make_cpiu(1500, 7, levels=16, seed=9)
+    ref = refdriver.grow(d.x, d.y, d.rt, d.strat, impl="ref", rule=4, ntree=6, nodesize=10, seed=-3, quants=True)
+    forest = _sorted_by_tree(refdriver.trim_forest(ref, d.n))
+    pkw = dict(nodesize=10, quants=True, fy=t.y, perf=perf, rfq=rfq)
+    pr = refdriver.predict(d.x, d.y, forest, t.x, impl="ref", **pkw)
+    pg = refdriver.predict(d.x, d.y, forest, t.x, impl="b200", **pkw)
+    assert [k for k in pg] == [k for k in pr]
+    a, b = pg["perfClas"], pr["perfClas"]
+    np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
+    np.testing.assert_allclose(a[~np.isnan(b)], b[~np.isnan(b)], rtol=1e-12 if perf == "brier" else 0, atol=0)
