@@ -306,7 +306,8 @@ typedef struct rfslam_predict_out {
   int64_t   row_tree_visits;   /* (row, tree) pairs routed */
   int64_t   node_visits;       /* records read while routing (sum of path lengths) */
   /* vimpClas (rf.c:37, rf.c:17537): [vimp_count = intrPredictorSize][1 + 2] permutation importance of the covariates in
-     intr_predictor, restore mode with RFSLAM_OPT_PERF | RFSLAM_OPT_VIMP | RFSLAM_OPT_VIMP_TYP1; per tree (Breiman-Cutler)
+     intr_predictor, in restore mode (over the OOB rows) or on held-out rows that carry the outcome (fr_size > 0, whole row
+     set), with RFSLAM_OPT_PERF | RFSLAM_OPT_VIMP | RFSLAM_OPT_VIMP_TYP1; per tree (Breiman-Cutler)
      with RFSLAM_OPT_VIMP_LEOB, else from perturbed ensembles; NULL otherwise */
   double   *vimpClas;
   int32_t   vimp_count;

@@ -286,7 +286,8 @@ int validate_predict(const rfslam_predict_args* a) {
   if ((a->opt_low & RFSLAM_OPT_VIMP) && (a->opt_low & RFSLAM_OPT_PERF)) {       // without OPT_PERF the reference drops the request (rf.c:1409-1413)
     if (!(a->opt_low & RFSLAM_OPT_VIMP_TYP1) || (a->opt_low & RFSLAM_OPT_VIMP_TYP2)) { set_error("importance: only the permutation type (\"permute\", \"permute.ensemble\") is on the accelerated path"); return RFSLAM_ENOSUP; }
     if (a->opt_low & RFSLAM_OPT_VIMP_JOIN) { set_error("joint importance is outside the accelerated path"); return RFSLAM_ENOSUP; }
-    if (a->fobservation_size > 0) { set_error("importance on held-out rows is outside the accelerated path (restore mode and grow are)"); return RFSLAM_ENOSUP; }
+    if (a->fobservation_size > 0 && !(a->fr_size > 0 && a->fr_data)) { set_error("importance on held-out rows needs their responses (frSize, frData)"); return RFSLAM_EINVAL; }
+    if (a->fobservation_size > 0 && a->frow_count > 0 && a->frow_count < a->fobservation_size) { set_error("importance on held-out rows needs the whole row set in one process (no row shard)"); return RFSLAM_ENOSUP; }
     if (a->intr_predictor_size < 0 || (a->intr_predictor_size > 0 && !a->intr_predictor)) { set_error("intrPredictor missing"); return RFSLAM_EINVAL; }
     for (int k = 0; k < a->intr_predictor_size; k++)
       if (a->intr_predictor[k] < 1 || a->intr_predictor[k] > a->x_size) { set_error("intrPredictor[%d] = %d is outside 1..xSize (rf.c:19248)", k, a->intr_predictor[k]); return RFSLAM_EINVAL; }
@@ -541,11 +542,12 @@ int predict_forest_ex(const rfslam_predict_args* a, rfslam_predict_out* out, con
     }
     // predict mode with held-out responses (frSize > 0): performance of the full ensemble on the held-out rows (rf.c:1323-1326,
     // rf.c:7770-7800) -- for the whole set of rows only (a row shard holds a part of the counts)
+    Buf b_fy;
+    double* d_fy = nullptr;
+    unsigned long long trainCls[2] = {0, 0};
     if (!restore && a->finalize_ensembles && (a->opt_low & RFSLAM_OPT_PERF) && a->fr_size > 0 && a->fr_data && r0 == 0 && M == mAll) {
-      Buf b_fy;
-      double* d_fy = b_fy.alloc<double>((size_t)M);
+      d_fy = b_fy.alloc<double>((size_t)M);
       RF_CUDA(cudaMemcpy(d_fy, a->fr_data, (size_t)M * 8, cudaMemcpyHostToDevice));
-      unsigned long long trainCls[2] = {0, 0};
       if (a->opt_low & RFSLAM_OPT_CLAS_RFQ) {
         if (!a->r_data) { set_error("rfq performance on held-out rows needs the training response (rData)"); throw CudaFail{RFSLAM_EINVAL}; }
         for (int i = 0; i < n; i++) trainCls[a->r_data[i] == 2.0 ? 1 : 0]++;
@@ -554,20 +556,30 @@ int predict_forest_ex(const rfslam_predict_args* a, rfslam_predict_out* out, con
                                (a->opt_low & RFSLAM_OPT_CLAS_RFQ) ? trainCls : nullptr);
       out->perfClas = h_perf;
     }
-    // ---- permutation importance (restore mode; the grow entry comes here with its own chain-C seeds) ----
+    // ---- permutation importance (restore mode, or held-out rows with responses; the grow entry comes here with its own chain-C seeds) ----
     double* h_vimp = nullptr;
     const int nIntr = a->intr_predictor_size;
-    if (restore && h_perf && (a->opt_low & RFSLAM_OPT_VIMP) && nIntr > 0) {
+    if (h_perf && (a->opt_low & RFSLAM_OPT_VIMP) && nIntr > 0) {
+      // rows the importance is taken over: the OOB rows of every tree (restore / grow), or ALL held-out rows of every tree
+      // (predict mode with responses: membershipIndex = identity, rf.c:2125-2131)
       const bool leob = (a->opt_low & RFSLAM_OPT_VIMP_LEOB) != 0;
+      const int vn = restore ? n : (int)M;
+      const double* hx = restore ? a->x_data : a->fx_data;
+      const double* hy = restore ? a->r_data : a->fr_data;
+      const double* d_vy = restore ? d_y : d_fy;
+      const uint16_t* d_vcnt = restore ? d_cnt : nullptr;
       RF_CUDA(cudaEventRecord(st.k0));
       Buf b_x, b_oobc, b_seedC, b_intr, b_scr, b_acc, b_vens, b_vden;
-      double* d_x = b_x.alloc<double>((size_t)p * n);
-      RF_CUDA(cudaMemcpy(d_x, a->x_data, (size_t)p * n * 8, cudaMemcpyHostToDevice));
-      int* d_oobc = b_oobc.alloc<int>(ntree);
-      vimp_oob_count_kernel<<<ntree, kVimpThreads>>>(d_cnt, cstride, n, ntree, d_oobc);
-      std::vector<int> oobc(ntree);
-      RF_CUDA(cudaMemcpy(oobc.data(), d_oobc, (size_t)ntree * 4, cudaMemcpyDeviceToHost));
-      const int maxOob = std::max(1, *std::max_element(oobc.begin(), oobc.end()));
+      double* d_x = b_x.alloc<double>((size_t)p * vn);
+      RF_CUDA(cudaMemcpy(d_x, hx, (size_t)p * vn * 8, cudaMemcpyHostToDevice));
+      int maxOob = vn;
+      if (restore) {
+        int* d_oobc = b_oobc.alloc<int>(ntree);
+        vimp_oob_count_kernel<<<ntree, kVimpThreads>>>(d_cnt, cstride, n, ntree, d_oobc);
+        std::vector<int> oobc(ntree);
+        RF_CUDA(cudaMemcpy(oobc.data(), d_oobc, (size_t)ntree * 4, cudaMemcpyDeviceToHost));
+        maxOob = std::max(1, *std::max_element(oobc.begin(), oobc.end()));
+      }
       const size_t smem = SlotIndex::bytes(maxOob);
       if (smem > 220 * 1024) { set_error("importance: %d OOB rows in one tree exceed the ~1.7 M the permutation's shared-memory slot index holds", maxOob); throw CudaFail{RFSLAM_ENOSUP}; }
       RF_CUDA(cudaFuncSetAttribute(vimp_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -583,19 +595,20 @@ int predict_forest_ex(const rfslam_predict_args* a, rfslam_predict_out* out, con
       int* d_seedC = b_seedC.alloc<int>(ntree); int* d_intr = b_intr.alloc<int>(nIntr);
       RF_CUDA(cudaMemcpy(d_seedC, seedC.data(), (size_t)ntree * 4, cudaMemcpyHostToDevice));
       RF_CUDA(cudaMemcpy(d_intr, intr0.data(), (size_t)nIntr * 4, cudaMemcpyHostToDevice));
-      unsigned long long cls[2] = {0, 0};
-      for (int i = 0; i < n; i++) cls[a->r_data[i] == 2.0 ? 1 : 0]++;
+      unsigned long long cls[2] = {0, 0};                             // of the rows scored: the per-class denominators (rf.c:1037-1040)
+      for (int i = 0; i < vn; i++) cls[hy[i] == 2.0 ? 1 : 0]++;
+      const unsigned long long* tcls = restore ? cls : trainCls;      // of the training rows: the RFQ vote (rf.c:16859-16895)
       VimpArgs va{};
-      va.ntree = ntree; va.p = p; va.n = n; va.nIntr = nIntr;
+      va.ntree = ntree; va.p = p; va.n = vn; va.nIntr = nIntr;
       va.nodeOff = d_noff; va.slotOfTree = d_sot; va.leafOff = d_loff; va.rec = d_rec; va.tnCLAS = d_clas;
-      va.cnt = d_cnt; va.cstride = cstride; va.x = d_x; va.y = d_y; va.seedC = d_seedC; va.intr = d_intr;
+      va.cnt = d_vcnt; va.cstride = cstride; va.x = d_x; va.y = d_vy; va.seedC = d_seedC; va.intr = d_intr;
       va.maxOob = maxOob; va.scratch = b_scr.alloc<uint32_t>((size_t)grid * 3 * maxOob);
       va.leob = leob ? 1 : 0; va.rfqMinority = -1; va.rfqThreshold = 0.0;
-      if (a->opt_low & RFSLAM_OPT_CLAS_RFQ) { va.rfqMinority = cls[1] < cls[0] ? 1 : 0; va.rfqThreshold = (double)cls[va.rfqMinority] / (double)n; }
+      if (a->opt_low & RFSLAM_OPT_CLAS_RFQ) { va.rfqMinority = tcls[1] < tcls[0] ? 1 : 0; va.rfqThreshold = (double)tcls[va.rfqMinority] / (double)(tcls[0] + tcls[1]); }
       va.acc = b_acc.alloc<VimpAcc>((size_t)ntree * (nIntr + 1));
       if (!leob) {
-        va.vens = b_vens.alloc<double>((size_t)nIntr * 2 * n); va.vden = b_vden.alloc<uint32_t>((size_t)nIntr * n);
-        RF_CUDA(cudaMemsetAsync(va.vens, 0, (size_t)nIntr * 2 * n * 8)); RF_CUDA(cudaMemsetAsync(va.vden, 0, (size_t)nIntr * n * 4));
+        va.vens = b_vens.alloc<double>((size_t)nIntr * 2 * vn); va.vden = b_vden.alloc<uint32_t>((size_t)nIntr * vn);
+        RF_CUDA(cudaMemsetAsync(va.vens, 0, (size_t)nIntr * 2 * vn * 8)); RF_CUDA(cudaMemsetAsync(va.vden, 0, (size_t)nIntr * vn * 4));
       }
       vimp_tree_kernel<<<grid, kVimpThreads, smem>>>(va);
       launches += 2;
@@ -630,10 +643,11 @@ int predict_forest_ex(const rfslam_predict_args* a, rfslam_predict_out* out, con
         // ensemble: the perturbed OOB ensemble of covariate v against the forest's (rf.c:2416-2470, 2685-2694)
         const double* f0 = h_perf + (size_t)(ntree - 1) * 3;
         for (int v = 0; v < nIntr; v++) {
-          double* ev = va.vens + (size_t)v * 2 * n; uint32_t* dv = va.vden + (size_t)v * n;
-          finalize_pred_kernel<<<(unsigned)((n + 255) / 256), 256>>>(ev, dv, (size_t)n);
+          double* ev = va.vens + (size_t)v * 2 * vn; uint32_t* dv = va.vden + (size_t)v * vn;
+          finalize_pred_kernel<<<(unsigned)((vn + 255) / 256), 256>>>(ev, dv, (size_t)vn);
           launches++;
-          double* r = perf_clas_table(a->opt_low, 1, n, ev, dv, nullptr, nullptr, d_y, &launches);
+          double* r = perf_clas_table(a->opt_low, 1, vn, ev, dv, nullptr, nullptr, d_vy, &launches,
+                                      (!restore && (a->opt_low & RFSLAM_OPT_CLAS_RFQ)) ? trainCls : nullptr);
           for (int k = 0; k < 3; k++) h_vimp[v * 3 + k] = (r[k] == r[k] && f0[k] == f0[k]) ? r[k] - f0[k] : r[k];
           host_free(r);
         }

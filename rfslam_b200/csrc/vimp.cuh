@@ -29,7 +29,7 @@ struct VimpArgs {
   const int64_t* leafOff;        // by tree id - 1
   const PredRec* rec;
   const int32_t* tnCLAS;         // [leaf][2]
-  const uint16_t* cnt; size_t cstride;   // in-bag counts [tree][row]
+  const uint16_t* cnt; size_t cstride;   // in-bag counts [tree][row]; nullptr = the importance is taken over all n rows
   const double* x;               // [p][n] the training table, original rows
   const double* y;               // [n]
   const int* seedC;              // [ntree]
@@ -198,12 +198,12 @@ __global__ void __launch_bounds__(kVimpThreads) vimp_tree_kernel(VimpArgs a) {
   uint32_t* permBuf[2] = {idx + a.maxOob, idx + 2 * (size_t)a.maxOob};
 
   for (int tree = blockIdx.x; tree < a.ntree; tree += gridDim.x) {
-    const uint16_t* cnt = a.cnt + (size_t)tree * a.cstride;
+    const uint16_t* cnt = a.cnt ? a.cnt + (size_t)tree * a.cstride : nullptr;       // nullptr: every row (held-out rows)
     // ---- the tree's OOB rows, ascending (RF_oobMembershipIndex) ----
     int base = 0;
     for (int i0 = 0; i0 < a.n; i0 += kVimpThreads) {
       const int i = i0 + tid;
-      const bool oob = i < a.n && cnt[i] == 0;
+      const bool oob = i < a.n && (!cnt || cnt[i] == 0);
       const unsigned bal = __ballot_sync(0xffffffffu, oob);
       if (lane == 0) warpBase[w] = __popc(bal);
       __syncthreads();

@@ -554,3 +554,18 @@ def test_held_out_performance_matches_oracle(perf):
     np.testing.assert_allclose(got[ok], want[ok], rtol=1e-12 if perf == "brier" else 0, atol=0)
     assert "perfClas" not in rfslam_b200.predict_rfsrc(f, t.x, x=d.x, y=d.y, fy=t.y, frow_first=0, frow_count=3000)
     assert "perfClas" not in rfslam_b200.predict_rfsrc(f, t.x, fy=None)
+
+
+@pytest.mark.parametrize("per_tree", [True, False], ids=["per-tree", "ensemble"])
+def test_importance_on_held_out_rows_matches_oracle(per_tree):
+    """predict(newdata with the outcome, importance = ...): every held-out row is permuted and dropped down every tree
+    (membershipIndex = identity, randomForestSRC.c:2125-2131), chain C seeded as in restore mode."""
+    d = make_cpiu(12000, 7, levels=32, seed=80); t = make_cpiu(5000, 7, levels=32, seed=81)
+    ntree = 6
+    f = rfslam_b200.rfsrc(d.x, d.y, d.rt, d.strat, splitrule=4, ntree=ntree, nodesize=10, seed=-33)
+    intr = [4, 1, 7]
+    pr = rfslam_b200.predict_rfsrc(f, t.x, x=d.x, y=d.y, fy=t.y, importance="permute" if per_tree else "permute.ensemble", xvar_importance=intr)
+    want = port.vimp_permute(f, t.x, t.y, np.zeros((ntree, t.n), np.int32), port.chain_seed_c(0, ntree, restore=True), intr=intr, per_tree=per_tree)
+    assert_vimp_close(pr["importance"], want, exact=per_tree)
+    with pytest.raises(rfslam_b200.RfslamError, match="whole row set"):
+        rfslam_b200.predict_rfsrc(f, t.x, x=d.x, y=d.y, fy=t.y, importance="permute", frow_first=0, frow_count=1000)

@@ -161,3 +161,9 @@ def test_both_libraries_score_held_out_rows_alike(perf, rfq):
     a, b = pg["perfClas"], pr["perfClas"]
     np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
     np.testing.assert_allclose(a[~np.isnan(b)], b[~np.isnan(b)], rtol=1e-12 if perf == "brier" else 0, atol=0)
+    # and the permutation importance of three covariates over the held-out rows (one reference thread, see above)
+    ikw = dict(pkw, importance="permute", xvar_imp=[3, 6, 1], nthreads=1)
+    vr = refdriver.predict(d.x, d.y, forest, t.x, impl="ref", **ikw)["vimpClas"]
+    vg = refdriver.predict(d.x, d.y, forest, t.x, impl="b200", **ikw)["vimpClas"]
+    np.testing.assert_array_equal(np.isnan(vg), np.isnan(vr))
+    np.testing.assert_allclose(vg[~np.isnan(vr)], vr[~np.isnan(vr)], rtol=0, atol=1e-12 if perf == "brier" else 0)
