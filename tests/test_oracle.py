@@ -346,3 +346,32 @@ def test_permutation_is_the_reference_one():
     x = np.arange(10, dtype=np.float64)[None, :]; y = np.ones(10); y[::3] = 2.0
     v = port.vimp_permute(f, x, y, np.zeros((1, 10), np.int32), port.chain_seed_c(-3, 1), per_tree=True)
     assert v.shape == (1, 3) and v[0, 0] == 0.0                       # a stump: permuting changes nothing
+
+
+@pytest.mark.skipif(not refdriver.available(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("imp,perf,rfq", [("permute", "misclass", False), ("permute.ensemble", "brier", False), ("permute", "gmean", True)])
+def test_port_importance_matches_live_reference(imp, perf, rfq):
+    """Fresh seeds, three run modes: inside the grow call, restore mode (covariate subset) and held-out rows with responses.
+    One reference thread: its per-tree importance shares buffers between trees, and rfsrcPredict hard-codes two threads."""
+    d = make_cpiu(2500, 6, levels=16, seed=41); t = make_cpiu(800, 6, levels=16, seed=42)
+    ntree, seed = 5, -57
+    raw = refdriver.grow(d.x, d.y, d.rt, d.strat, rule=4, ntree=ntree, nodesize=8, seed=seed, importance=imp, perf=perf, rfq=rfq,
+                         quants=True, nthreads=1)
+    f = refdriver.trim_forest(raw, d.n)
+    order = np.argsort(f["treeID"], kind="stable")
+    for k in ("treeID", "nodeID", "parmID", "contPT", "mwcpSZ"):
+        f[k] = f[k][order]
+    per_tree = imp == "permute"
+    exact = per_tree and perf != "brier"
+    got = port.vimp_permute(f, d.x, d.y, raw["bootMembership"], port.chain_seed_c(seed, ntree), per_tree=per_tree, perf=perf, rfq=rfq)
+    assert_vimp_close(got, raw["vimpClas"], exact=exact)
+    intr = [5, 2]
+    pkw = dict(nodesize=8, importance=imp, xvar_imp=intr, quants=True, nthreads=1, perf=perf, rfq=rfq)
+    rest = refdriver.predict(d.x, d.y, f, None, **pkw)["vimpClas"]
+    got = port.vimp_permute(f, d.x, d.y, raw["bootMembership"], port.chain_seed_c(0, ntree, restore=True), intr=intr, per_tree=per_tree, perf=perf, rfq=rfq)
+    assert_vimp_close(got, rest, exact=exact)
+    if not rfq:                                                       # (the restatement takes the RFQ threshold from the rows it scores)
+        held = refdriver.predict(d.x, d.y, f, t.x, fy=t.y, **pkw)["vimpClas"]
+        got = port.vimp_permute(f, t.x, t.y, np.zeros((ntree, t.n), np.int32), port.chain_seed_c(0, ntree, restore=True), intr=intr,
+                                per_tree=per_tree, perf=perf)
+        assert_vimp_close(got, held, exact=exact)
